@@ -1,0 +1,114 @@
+"""Host-side 2BWT index arrays: read the reference builder's files, or hold arrays built in-process.
+
+File formats follow the reference loader BWTLoad (BWT.c:107-223):
+  <prefix>.index.bwt      : inverseSa0, cumulativeFreq[1..4], then ceil(n/16) words of 2-bit codes
+  <prefix>.index.fmv      : inverseSa0, cumulativeFreq[1..4], occValue (minor, 16-bit pairs), occValueMajor
+  <prefix>.index.rev.bwt / .rev.fmv : the same for the BWT of the reversed text
+Sizes follow BWTResidentSizeInWord / BWTOccValueMinorSizeInWord / BWTOccValueMajorSizeInWord
+(BWT.c:1079-1116); the resident bwtCode is padded to a multiple of 256 symbols plus 8 words (BWT.c:176).
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+
+OCC_INTERVAL = 256
+OCC_INTERVAL_MAJOR = 65536
+CHAR_PER_WORD = 16
+
+
+def bwt_resident_words(n: int) -> int:
+    """BWTResidentSizeInWord(n) + WORD_BETWEEN_OCC/2 (BWT.c:176, :1079-1088)."""
+    rounded = (n + OCC_INTERVAL - 1) // OCC_INTERVAL * OCC_INTERVAL
+    return (rounded + CHAR_PER_WORD - 1) // CHAR_PER_WORD + 8
+
+
+def bwt_file_words(n: int) -> int:
+    return (n + CHAR_PER_WORD - 1) // CHAR_PER_WORD
+
+
+def occ_minor_words(n: int) -> int:
+    """BWTOccValueMinorSizeInWord, BWT.c:1097-1104."""
+    num = (n + OCC_INTERVAL - 1) // OCC_INTERVAL + 1
+    return (num + 1) // 2 * 4
+
+
+def occ_major_words(n: int) -> int:
+    """BWTOccValueMajorSizeInWord, BWT.c:1106-1116."""
+    num = (n + OCC_INTERVAL - 1) // OCC_INTERVAL + 1
+    per = OCC_INTERVAL_MAJOR // OCC_INTERVAL
+    return (num + per - 1) // per * 4
+
+
+@dataclasses.dataclass
+class BWTArrays:
+    """The fields of the reference's `BWT` struct that the search path reads (BWT.h:61-83)."""
+    text_length: int
+    inverse_sa0: int
+    cumulative_freq: np.ndarray   # uint32[5]
+    bwt_code: np.ndarray          # uint32[bwt_resident_words]
+    occ_value: np.ndarray         # uint32[occ_minor_words]
+    occ_value_major: np.ndarray   # uint32[occ_major_words]
+
+    def check(self) -> None:
+        n = self.text_length
+        assert self.cumulative_freq.dtype == np.uint32 and self.cumulative_freq.shape == (5,)
+        assert int(self.cumulative_freq[4]) == n
+        assert self.bwt_code.dtype == np.uint32 and self.bwt_code.shape[0] >= bwt_file_words(n)
+        assert self.occ_value.shape[0] == occ_minor_words(n)
+        assert self.occ_value_major.shape[0] == occ_major_words(n)
+
+
+@dataclasses.dataclass
+class Index2BWT:
+    fwd: BWTArrays
+    rev: BWTArrays
+
+
+def load_bwt(bwt_path: str, fmv_path: str) -> BWTArrays:
+    with open(bwt_path, "rb") as f:
+        hdr = np.fromfile(f, dtype=np.uint32, count=5)
+        inverse_sa0 = int(hdr[0])
+        cum = np.zeros(5, dtype=np.uint32)
+        cum[1:] = hdr[1:]
+        n = int(cum[4])
+        code = np.zeros(bwt_resident_words(n), dtype=np.uint32)
+        body = np.fromfile(f, dtype=np.uint32, count=bwt_file_words(n))
+        if body.shape[0] != bwt_file_words(n):
+            raise ValueError(f"{bwt_path}: truncated bwt code")
+        code[: body.shape[0]] = body
+        # BWTClearTrailingBwtCode (BWT.c:1118-1150): symbols past textLength are zeroed
+        tail = n % CHAR_PER_WORD
+        if tail:
+            keep = np.uint32((0xFFFFFFFF << (32 - 2 * tail)) & 0xFFFFFFFF)
+            code[n // CHAR_PER_WORD] &= keep
+    with open(fmv_path, "rb") as f:
+        hdr2 = np.fromfile(f, dtype=np.uint32, count=5)
+        if int(hdr2[0]) != inverse_sa0 or not np.array_equal(hdr2[1:], cum[1:]):
+            raise ValueError(f"{fmv_path}: header does not match {bwt_path}")
+        occ = np.fromfile(f, dtype=np.uint32, count=occ_minor_words(n))
+        major = np.fromfile(f, dtype=np.uint32, count=occ_major_words(n))
+        if occ.shape[0] != occ_minor_words(n) or major.shape[0] != occ_major_words(n):
+            raise ValueError(f"{fmv_path}: truncated occ tables")
+    arr = BWTArrays(n, inverse_sa0, cum, code, occ, major)
+    arr.check()
+    return arr
+
+
+def load_index(prefix: str) -> Index2BWT:
+    """Load `<prefix>.index.{bwt,fmv,rev.bwt,rev.fmv}` as written by `HSA index <prefix> <fasta>`."""
+    p = prefix + ".index"
+    return Index2BWT(load_bwt(p + ".bwt", p + ".fmv"), load_bwt(p + ".rev.bwt", p + ".rev.fmv"))
+
+
+def save_bwt(arr: BWTArrays, bwt_path: str, fmv_path: str) -> None:
+    """Write the two files in the reference's on-disk format (BWTConstruct.c:1209-1239)."""
+    n = arr.text_length
+    hdr = np.concatenate([np.asarray([arr.inverse_sa0], dtype=np.uint32), arr.cumulative_freq[1:]])
+    with open(bwt_path, "wb") as f:
+        hdr.tofile(f)
+        arr.bwt_code[: bwt_file_words(n)].tofile(f)
+    with open(fmv_path, "wb") as f:
+        hdr.tofile(f)
+        arr.occ_value.tofile(f)
+        arr.occ_value_major.tofile(f)

@@ -1,0 +1,187 @@
+/*
+ * hsa_b200.h -- C ABI of the B200-native replacement for HSA's inexact-search hot path.
+ *
+ * Drop-in boundary.  Every entry point below names the reference interface it
+ * replaces (file:line into the HSA tree).  Plain pointers and sizes only; no torch / CUDA types.
+ * All functions return 0 on success and a negative HSA_E_* code on failure; hsa_last_error() returns a
+ * human-readable description of the last failure on the calling thread.  Nothing here ever falls back
+ * to a CPU implementation: without a CUDA device every compute entry point fails with HSA_E_CUDA.
+ *
+ * Struct mirrors are byte-identical to the reference's (x86-64, gcc bit-field layout):
+ *   hsa_gap_opt_t == gap_opt_t    bwtaln.h:133-143   (68 bytes)
+ *   hsa_aln1_t    == bwt_aln1_t   bwtaln.h:41-50     (36 bytes)
+ *   hsa_width_t   == bwt_width_t  bwtaln.h:35-38     ( 8 bytes)
+ */
+#ifndef HSA_B200_H
+#define HSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSA_B200_ABI_VERSION 1
+
+/* error codes */
+#define HSA_OK            0
+#define HSA_E_ARG        -1   /* bad argument / unsupported option combination                    */
+#define HSA_E_CUDA       -2   /* CUDA runtime error (no device, OOM, launch failure)               */
+#define HSA_E_CAPACITY   -3   /* a task exceeded every device stack / hit capacity (never silent)  */
+#define HSA_E_NOMEM      -4   /* host allocation failed                                            */
+
+/* bwtaln.h:124-132 mode bits used on the path */
+#define HSA_MODE_GAPE     0x01
+#define HSA_MODE_COMPREAD 0x02
+#define HSA_MODE_LOGGAP   0x04
+#define HSA_MODE_NONSTOP  0x10
+
+typedef struct hsa_gap_opt_t {          /* == gap_opt_t, bwtaln.h:133-143; defaults bwtaln.c:21-44 */
+    int s_mm, s_gapo, s_gape;
+    int mode;
+    int indel_end_skip, max_del_occ, max_entries;
+    float fnr;
+    int max_diff, max_gapo, max_gape;
+    int max_seed_diff, seed_len;
+    int n_threads;
+    int max_top2;
+    int trim_qual;
+} hsa_gap_opt_t;
+
+typedef struct hsa_aln1_t {             /* == bwt_aln1_t, bwtaln.h:41-50 */
+    uint32_t n_mm:16, n_gapo:8, n_gape:8;
+    uint32_t k, l;
+    uint32_t rev_k, rev_l;
+    uint32_t type:30, strand:2;
+    int start, end;
+    int score;
+} hsa_aln1_t;
+
+typedef struct hsa_width_t {            /* == bwt_width_t, bwtaln.h:35-38 */
+    uint32_t w;
+    int bid;
+} hsa_width_t;
+
+/* The fields of the reference's `BWT` (BWT.h:61-83) that the path reads, as loaded by BWTLoad
+ * (BWT.c:107-223).  Host pointers; the arrays keep the reference's own layout (MSB-first 2-bit codes,
+ * 16-bit minor / 32-bit major bidirectional occ samples every 256 / 65536 symbols). */
+typedef struct hsa_bwt_view_t {
+    uint32_t textLength;
+    uint32_t inverseSa0;
+    uint32_t cumulativeFreq[5];
+    const uint32_t *bwtCode;       uint32_t bwtSizeInWord;
+    const uint32_t *occValue;      uint32_t occSizeInWord;
+    const uint32_t *occValueMajor; uint32_t occMajorSizeInWord;
+} hsa_bwt_view_t;
+
+typedef struct hsa_index hsa_index_t;   /* opaque: device-resident 2BWT search arrays (one GPU) */
+
+int         hsa_b200_abi_version(void);
+const char *hsa_last_error(void);
+void        hsa_gap_opt_default(hsa_gap_opt_t *opt);            /* gap_init_opt, bwtaln.c:21-44 */
+int         hsa_cal_maxdiff(int l, double err, double thres);   /* bwa_cal_maxdiff, bwtaln.c:46-58 (host) */
+
+/* ---- index -------------------------------------------------------------------------------------
+ * Replaces the in-memory result of BWTLoad2BWT (2BWT-Interface.c:13-66) for the search arrays: the two
+ * BWTs are copied to `device` once and re-packed there into the device layout.   */
+int  hsa_index_upload(int device, const hsa_bwt_view_t *fwd, const hsa_bwt_view_t *rev, hsa_index_t **out);
+/* Adopt arrays that already live on `device` in the REFERENCE layout (built there, or received by an
+ * NCCL broadcast); pointers are device pointers, the view's scalar fields are host values. */
+int  hsa_index_from_device(int device, const hsa_bwt_view_t *fwd_dev, const hsa_bwt_view_t *rev_dev, hsa_index_t **out);
+/* Device pointer + byte size of the packed device-layout blocks of one direction (0 fwd, 1 rev), so a
+ * caller can broadcast a built index to peer GPUs; and the inverse: wrap received blocks. */
+int  hsa_index_blocks(const hsa_index_t *idx, int which, void **dev_ptr, size_t *bytes);
+int  hsa_index_from_blocks(int device, const uint32_t meta_fwd[7], const uint32_t meta_rev[7],
+                           void *blocks_fwd_dev, void *blocks_rev_dev, int take_ownership, hsa_index_t **out);
+int  hsa_index_meta(const hsa_index_t *idx, int which, uint32_t meta[7]); /* textLength, inverseSa0, C[0..4] */
+void hsa_index_free(hsa_index_t *idx);
+
+/* ---- rank: BWTAllOccValue (BWT.c:793-837) / BWTOccValue (BWT.c:682-719) ---------------------------
+ * which: 0 = forward BWT, 1 = reverse BWT.  layout: 0 = evaluate on the reference-layout arrays,
+ * 1 = on the re-packed device layout.  occ4_out[n*4]; occ1_out[n*4] (one BWTOccValue per character). */
+int  hsa_occ_batch(const hsa_index_t *idx, int which, int layout, const uint32_t *indices, size_t n,
+                   uint32_t *occ4_out, uint32_t *occ1_out);
+
+/* ---- bwt_cal_width (bwtaln.c:73-116), type 1 (forward search on rev_bwt) and type 0 ---------------
+ * codes: concatenated base codes (0..3, N = 4); read r is codes[off[r] .. off[r]+len[r]).
+ * width_out: sum(len[r]+1) entries, read r at off[r]+r; bid_out[r] = return value. */
+int  hsa_cal_width_batch(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off,
+                         const uint32_t *len, size_t n, int type, hsa_width_t *width_out, int *bid_out);
+
+/* ---- bwt_match_gap (bwtgap.c:118-331), batched --------------------------------------------------- */
+#define HSA_SEED_NONE   0   /* aux->width_seed == NULL                                   (bwtgap.c:919,1192) */
+#define HSA_SEED_TAIL   1   /* width_seed over the last opt->seed_len bases              (bwtaln.c:344-346)  */
+#define HSA_SEED_ALIAS  2   /* width_seed aliases width_back                             (bwtgap.c:809)      */
+
+typedef struct hsa_task_t {
+    uint64_t read_off;    /* offset of the READ (forward strand, as given) in `codes`                         */
+    uint32_t read_len;    /* length of the read                                                               */
+    uint32_t strand;      /* aux->strand: 1 = search the reverse complement of the read, 0 = the read itself  */
+    uint32_t sub_off;     /* the searched sequence starts here inside the strand-resolved read                */
+    uint32_t len;         /* aux->len: number of bases searched                                               */
+    uint32_t wsrc_off;    /* width_back is computed on [wsrc_off, wsrc_off+len) of the strand-resolved read
+                             (== sub_off everywhere except the splice seeds, bwtgap.c:807-808, where it is 0) */
+    uint32_t seed_mode;   /* HSA_SEED_*                                                                       */
+    uint32_t opt_idx;     /* index into opts[]: the gap_opt_t the reference would pass in aux->opt            */
+    uint32_t reserved;
+} hsa_task_t;
+
+typedef struct hsa_result_t {     /* flat result of a batch; free with hsa_result_free                 */
+    size_t      n_items;          /* tasks (hsa_match_gap_batch / seeds) or reads (whole)               */
+    int32_t    *n_aln;            /* [n_items]                                                          */
+    uint64_t   *aln_off;          /* [n_items] first hit of the item in aln[]                           */
+    hsa_aln1_t *aln;              /* all hits, per item in discovery order (== reference order)         */
+    size_t      n_aln_total;
+    uint64_t    occ_lookups;      /* BWTAllOccValue + BWTOccValue calls the reference would have issued */
+    uint64_t    n_strict;         /* items that had to be re-run with the large-capacity kernel         */
+    float       kernel_ms;        /* device time of the search kernel(s), CUDA events on the stream     */
+    uint32_t    kernel_launches;
+} hsa_result_t;
+
+/* One reference bwt_cal_width (+ seed width) + bwt_match_gap call per task.  Host buffers in, host
+ * buffers out (pageable or pinned). */
+int  hsa_match_gap_batch(const hsa_index_t *idx, const uint8_t *codes, size_t codes_bytes,
+                         const hsa_task_t *tasks, size_t n_tasks,
+                         const hsa_gap_opt_t *opts, size_t n_opts, hsa_result_t *res);
+
+/* The whole-read part of bwa_cal_sa_reg_gap (bwtaln.c:303-360, 371-372) for n reads with ONE caller
+ * gap_opt_t: per-read filters (too many N, poly-A/T prefix), per-read max_diff from opt->fnr
+ * (bwtaln.c:330-331), seed_len clamp (:332), reverse-complement strand first, forward strand only if
+ * that found nothing, strand stamped on every hit and start/end on the first.  mode & GAPE is cleared as
+ * bwtaln.c:261 does unless keep_gape != 0.  No splice fallback: reads with n_aln == 0 are what the
+ * caller hands to bwt_splice_match. */
+int  hsa_whole_reads(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                     size_t n_reads, const hsa_gap_opt_t *opt, int keep_gape, hsa_result_t *res);
+
+/* The six seed searches of bwt_splice_match (bwtgap.c:797-820) for each read: item 6*r+s is seed s%3 of
+ * strand s/3, with the reference's prefix-width quirk; hits carry start/end as bwtgap.c:816-819. */
+int  hsa_splice_seeds(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                      size_t n_reads, const hsa_gap_opt_t *opt, hsa_result_t *res);
+
+void hsa_result_free(hsa_result_t *res);
+
+/* ---- device-resident variants for pipelines that keep reads / results in HBM (bench `value`) ------
+ * All pointers are device pointers on the index's device; `stream` is a cudaStream_t passed as void*.
+ * Results stay on the device: n_aln_dev[n_reads], aln_off_dev[n_reads], aln_dev[aln_capacity] and a
+ * 4 x uint64 stats block {hits, lookups, strict, overflow}.  No synchronisation is performed. */
+typedef struct hsa_workspace hsa_workspace_t;
+int  hsa_workspace_create(const hsa_index_t *idx, size_t max_reads, uint32_t max_len, size_t aln_capacity,
+                          hsa_workspace_t **out);
+void hsa_workspace_free(hsa_workspace_t *ws);
+int  hsa_whole_reads_device(const hsa_index_t *idx, hsa_workspace_t *ws, const uint8_t *codes_dev,
+                            const uint64_t *off_dev, const uint32_t *len_dev, size_t n_reads, uint32_t max_len,
+                            const hsa_gap_opt_t *opt, int keep_gape, int32_t *n_aln_dev, uint64_t *aln_off_dev,
+                            hsa_aln1_t *aln_dev, size_t aln_capacity, uint64_t *stats_dev, void *stream);
+/* number of kernels the last call on this workspace launched (for bench's gpu_launches) */
+uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws);
+
+/* ---- roofline probe: random 32-byte-sector loads over `footprint_bytes` ----
+ * Reports achieved GB/s (sectors * 32 B / time) at full occupancy with `loads_per_thread` dependent
+ * chains; used only by bench.py to establish the random-access denominator on this GPU. */
+int  hsa_random_sector_probe(int device, size_t footprint_bytes, int iters, double *gbs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSA_B200_H */

@@ -1,0 +1,531 @@
+/*
+ * ref_harness.c -- TEST INFRASTRUCTURE ONLY (oracle).  Never part of the product path.
+ *
+ * A small driver of OUR OWN that is linked against the UNMODIFIED reference objects compiled in place
+ * from /root/reference by oracle/Makefile (`make ref`).  It exposes the reference's hot path
+ *  through a file-in / file-out command line so that Python tests and bench.py's
+ * cpu_baseline / --impl reference legs can (a) generate golden vectors, (b) pin oracle/hsa_oracle.c and
+ * the CUDA path against the real thing, and (c) time the reference CPU path on the host cores.
+ *
+ * Reference entry points called (all unmodified):
+ *   bwa_index_main          2BWT-Builder.c:215     index construction
+ *   BWTLoad2BWT             2BWT-Interface.c:13    index load
+ *   BWTAllOccValue/OccValue BWT.c:793 / BWT.c:682  rank
+ *   bwt_cal_width           bwtaln.c:73            lower-bound widths
+ *   bwt_match_gap           bwtgap.c:118           inexact search
+ *   bwa_cal_sa_reg_gap      bwtaln.c:246           stock per-batch driver
+ *   gap_init_opt/gap_init_stack/gap_destroy_stack/seq_reverse/bwa_cal_maxdiff
+ *
+ * File formats (little-endian uint32 words):
+ *   reads  : 'HSAR' n len[n] then sum(len) bytes of base codes (A,C,G,T = 0..3, N = 4)
+ *   alns   : 'HSAA' n_items then per item: n_aln, n_aln x 12 words
+ *            {n_mm,n_gapo,n_gape,k,l,rev_k,rev_l,type,strand,start,end,score}
+ *   widths : 'HSAW' n then per read: bid, len+1, (len+1) x {w,bid}
+ *   occ in : n idx[n];  occ out: n x 16 words {fwd occ4[4], rev occ4[4], fwd occ1[c=0..3], rev occ1[c=0..3]}
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <time.h>
+#include <unistd.h>
+#include <sys/wait.h>
+#include "bwtaln.h"
+#include "bwtgap.h"
+#include "BWT.h"
+
+int bwa_index_main(int argc, char **argv);
+
+#ifdef HSA_COUNT_OCC
+static unsigned long long g_occ4 = 0, g_occ1 = 0;
+void __real_BWTAllOccValue(const BWT *bwt, unsigned int index, unsigned int *occValue);
+unsigned int __real_BWTOccValue(const BWT *bwt, unsigned int index, const unsigned int character);
+void __wrap_BWTAllOccValue(const BWT *bwt, unsigned int index, unsigned int *occValue)
+{ ++g_occ4; __real_BWTAllOccValue(bwt, index, occValue); }
+unsigned int __wrap_BWTOccValue(const BWT *bwt, unsigned int index, const unsigned int character)
+{ ++g_occ1; return __real_BWTOccValue(bwt, index, character); }
+#else
+static unsigned long long g_occ4 = 0, g_occ1 = 0;
+#endif
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void die(const char *msg) { fprintf(stderr, "ref_harness: %s\n", msg); exit(2); }
+
+/* ---------------------------------------------------------------- reads */
+typedef struct { uint32_t n; uint32_t *len; uint64_t *off; ubyte_t *codes; } reads_t;
+
+static reads_t load_reads(const char *fn)
+{
+    reads_t r; uint32_t hdr[2]; uint64_t tot = 0; uint32_t i;
+    FILE *f = fopen(fn, "rb");
+    if (!f) die("cannot open reads file");
+    if (fread(hdr, 4, 2, f) != 2 || hdr[0] != 0x52415348u) die("bad reads magic");
+    r.n = hdr[1];
+    r.len = (uint32_t*)malloc(4 * (size_t)(r.n + 1));
+    r.off = (uint64_t*)malloc(8 * (size_t)(r.n + 1));
+    if (fread(r.len, 4, r.n, f) != r.n) die("short reads file (len)");
+    for (i = 0; i < r.n; ++i) { r.off[i] = tot; tot += r.len[i]; }
+    r.off[r.n] = tot;
+    r.codes = (ubyte_t*)malloc(tot + 64);
+    if (fread(r.codes, 1, tot, f) != tot) die("short reads file (codes)");
+    fclose(f);
+    return r;
+}
+
+/* ---------------------------------------------------------------- options */
+static void apply_opt(gap_opt_t *o, const char *kv)
+{
+    const char *eq = strchr(kv, '=');
+    char key[64]; size_t kl;
+    if (!eq) die("option must be key=value");
+    kl = (size_t)(eq - kv); if (kl >= sizeof(key)) die("option key too long");
+    memcpy(key, kv, kl); key[kl] = 0;
+#define OPT_I(name) if (strcmp(key, #name) == 0) { o->name = atoi(eq + 1); return; }
+    OPT_I(s_mm) OPT_I(s_gapo) OPT_I(s_gape) OPT_I(mode) OPT_I(indel_end_skip) OPT_I(max_del_occ)
+    OPT_I(max_entries) OPT_I(max_diff) OPT_I(max_gapo) OPT_I(max_gape) OPT_I(max_seed_diff)
+    OPT_I(seed_len) OPT_I(max_top2)
+#undef OPT_I
+    if (strcmp(key, "fnr") == 0) { o->fnr = (float)atof(eq + 1); return; }
+    fprintf(stderr, "ref_harness: unknown option %s\n", key); exit(2);
+}
+
+typedef struct { int batch; int nout; int procs; int clear_gape; } hopt_t;
+
+static gap_opt_t *parse_opts(int argc, char **argv, int first, hopt_t *h)
+{
+    gap_opt_t *o = gap_init_opt();
+    int i;
+    h->batch = 0x186A0; h->nout = 0; h->procs = 1; h->clear_gape = 1;
+    for (i = first; i < argc; ++i) {
+        if (strncmp(argv[i], "batch=", 6) == 0) h->batch = atoi(argv[i] + 6);
+        else if (strncmp(argv[i], "nout=", 5) == 0) h->nout = atoi(argv[i] + 5);
+        else if (strncmp(argv[i], "procs=", 6) == 0) h->procs = atoi(argv[i] + 6);
+        else if (strncmp(argv[i], "clear_gape=", 11) == 0) h->clear_gape = atoi(argv[i] + 11);
+        else apply_opt(o, argv[i]);
+    }
+    return o;
+}
+
+/* ---------------------------------------------------------------- output */
+static void put_aln(FILE *f, int n_aln, const bwt_aln1_t *aln)
+{
+    uint32_t w[12]; int j; uint32_t n = (uint32_t)n_aln;
+    fwrite(&n, 4, 1, f);
+    for (j = 0; j < n_aln; ++j) {
+        const bwt_aln1_t *p = aln + j;
+        w[0] = p->n_mm; w[1] = p->n_gapo; w[2] = p->n_gape; w[3] = p->k; w[4] = p->l;
+        w[5] = p->rev_k; w[6] = p->rev_l; w[7] = p->type; w[8] = p->strand;
+        w[9] = (uint32_t)p->start; w[10] = (uint32_t)p->end; w[11] = (uint32_t)p->score;
+        fwrite(w, 4, 12, f);
+    }
+}
+
+static Idx2BWT *load_index(const char *prefix)
+{
+    char *str = (char*)calloc(strlen(prefix) + 10, 1);
+    Idx2BWT *bi;
+    strcpy(str, prefix); strcat(str, ".index");      /* bwtaln.c:463-469 */
+    bi = BWTLoad2BWT(str, ".sa");
+    free(str);
+    return bi;
+}
+
+/* per-read option resolution exactly as the driver does it for a read that has NOT yet seen the
+ * local_opt switch (bwtaln.c:260-261, 330-332), applied to a private copy so nothing leaks. */
+static void resolve_read_opt(gap_opt_t *dst, const gap_opt_t *src, int len, int clear_gape)
+{
+    *dst = *src;
+    if (clear_gape) dst->mode &= ~BWA_MODE_GAPE;
+    if (src->fnr > 0.0) dst->max_diff = bwa_cal_maxdiff(len, BWA_AVG_ERR, src->fnr);
+    dst->seed_len = src->seed_len < len ? src->seed_len : 0x7fffffff;
+}
+
+/* ---------------------------------------------------------------- modes */
+static int mode_occ(int argc, char **argv)
+{
+    Idx2BWT *bi; FILE *fi, *fo; uint32_t n, i, c, *idx;
+    if (argc < 5) die("usage: occ <prefix> <idx.bin> <out.bin>");
+    bi = load_index(argv[2]);
+    fi = fopen(argv[3], "rb"); if (!fi) die("cannot open idx");
+    if (fread(&n, 4, 1, fi) != 1) die("short idx");
+    idx = (uint32_t*)malloc(4 * (size_t)n);
+    if (fread(idx, 4, n, fi) != n) die("short idx");
+    fclose(fi);
+    fo = fopen(argv[4], "wb");
+    fwrite(&n, 4, 1, fo);
+    for (i = 0; i < n; ++i) {
+        unsigned int __attribute__((aligned(16))) o[16];
+        BWTAllOccValue(bi->bwt, idx[i], o);
+        BWTAllOccValue(bi->rev_bwt, idx[i], o + 4);
+        for (c = 0; c < 4; ++c) {
+            o[8 + c] = BWTOccValue(bi->bwt, idx[i], c);
+            o[12 + c] = BWTOccValue(bi->rev_bwt, idx[i], c);
+        }
+        fwrite(o, 4, 16, fo);
+    }
+    fclose(fo);
+    printf("{\"mode\":\"occ\",\"n\":%u,\"textLength\":%u,\"inverseSa0\":%u,\"rev_inverseSa0\":%u}\n",
+           n, bi->bwt->textLength, bi->bwt->inverseSa0, bi->rev_bwt->inverseSa0);
+    return 0;
+}
+
+static int mode_width(int argc, char **argv)
+{
+    Idx2BWT *bi; reads_t r; FILE *fo; uint32_t i, hdr[2]; int type;
+    if (argc < 6) die("usage: width <prefix> <reads> <type> <out>");
+    bi = load_index(argv[2]); r = load_reads(argv[3]); type = atoi(argv[4]);
+    fo = fopen(argv[5], "wb");
+    hdr[0] = 0x57415348u; hdr[1] = r.n; fwrite(hdr, 4, 2, fo);
+    for (i = 0; i < r.n; ++i) {
+        int len = (int)r.len[i];
+        bwt_width_t *w = (bwt_width_t*)calloc(len + 1, sizeof(bwt_width_t));
+        uint32_t h2[2];
+        h2[0] = (uint32_t)bwt_cal_width(bi, len, r.codes + r.off[i], w, type);
+        h2[1] = (uint32_t)(len + 1);
+        fwrite(h2, 4, 2, fo);
+        fwrite(w, sizeof(bwt_width_t), len + 1, fo);
+        free(w);
+    }
+    fclose(fo);
+    printf("{\"mode\":\"width\",\"n\":%u}\n", r.n);
+    return 0;
+}
+
+/* one bwt_match_gap call per (read, strand), strand 1 (revcomp) then 0, BOTH always searched, each with
+ * a fresh option copy; widths computed as bwtaln.c:344-348 does. */
+static int mode_percall(int argc, char **argv)
+{
+    Idx2BWT *bi; reads_t r; FILE *fo = NULL; hopt_t h; gap_opt_t *opt, ropt; uint32_t i, hdr[2];
+    int max_len = 0; bwt_aux_t aux; double t0, t1; unsigned long long n_hits = 0;
+    if (argc < 5) die("usage: percall <prefix> <reads> <out> [opts]");
+    bi = load_index(argv[2]); r = load_reads(argv[3]);
+    opt = parse_opts(argc, argv, 5, &h);
+    for (i = 0; i < r.n; ++i) if ((int)r.len[i] > max_len) max_len = (int)r.len[i];
+    if (!h.nout) { fo = fopen(argv[4], "wb"); hdr[0] = 0x41415348u; hdr[1] = 2 * r.n; fwrite(hdr, 4, 2, fo); }
+    memset(&aux, 0, sizeof(aux));
+    aux.bi_bwt = bi; aux.max_len = max_len;
+    aux.width_back = (bwt_width_t*)calloc(max_len + 1, sizeof(bwt_width_t));
+    aux.width_seed = (bwt_width_t*)calloc(max_len + 1, sizeof(bwt_width_t));
+    aux.rc_seq = (ubyte_t*)calloc(max_len + 1, 1);
+    g_occ4 = g_occ1 = 0;
+    t0 = now_s();
+    for (i = 0; i < r.n; ++i) {
+        int len = (int)r.len[i], s;
+        ubyte_t *seq = r.codes + r.off[i];
+        memcpy(aux.rc_seq, seq, len); seq_reverse(len, aux.rc_seq, 1);
+        aux.seq = seq; aux.len = len;
+        for (s = 1; s >= 0; --s) {
+            int n_aln = 0; bwt_aln1_t *aln; bwt_width_t *wseed = NULL;
+            resolve_read_opt(&ropt, opt, len, h.clear_gape);
+            aux.opt = &ropt;
+            aux.stack = gap_init_stack(ropt.max_diff, ropt.max_gapo, ropt.max_gape, &ropt);
+            memset(aux.width_back, 0, (max_len + 1) * sizeof(bwt_width_t));
+            memset(aux.width_seed, 0, (max_len + 1) * sizeof(bwt_width_t));
+            if (len > ropt.seed_len) {
+                bwt_cal_width(bi, ropt.seed_len, (s == 0 ? seq : aux.rc_seq) + (len - ropt.seed_len), aux.width_seed, 1);
+                wseed = aux.width_seed;
+            }
+            /* NOTE: the stock driver always passes a non-NULL width_seed (bwtaln.c:285); for len > seed_len
+             * (the only safe case, SURVEY.md 8c hazard 3) that is what is passed here. For len <= seed_len the
+             * harness passes NULL (no seeding) instead of reading out of bounds. */
+            bwt_cal_width(bi, len, s == 0 ? seq : aux.rc_seq, aux.width_back, 1);
+            aux.strand = s;
+            {
+                bwt_width_t *keep = aux.width_seed;
+                aux.width_seed = wseed;
+                aln = bwt_match_gap(&aux, &n_aln);
+                aux.width_seed = keep;
+            }
+            n_hits += (n_aln != 0);
+            if (fo) put_aln(fo, n_aln, aln);
+            free(aln);
+            gap_destroy_stack(aux.stack);
+        }
+    }
+    t1 = now_s();
+    if (fo) fclose(fo);
+    printf("{\"mode\":\"percall\",\"reads\":%u,\"calls\":%u,\"calls_with_hits\":%llu,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu}\n",
+           r.n, 2 * r.n, n_hits, t1 - t0, g_occ4, g_occ1);
+    return 0;
+}
+
+/* the six seed calls of bwt_splice_match (bwtgap.c:797-820), WITHOUT its early-outs, through the real
+ * bwt_cal_width / bwt_match_gap: gaps off, max_diff = max_seed_diff, seed_len = len_align,
+ * width computed on the read PREFIX (bwtgap.c:807-808) and aliased as width_back (bwtgap.c:809). */
+static int mode_seeds(int argc, char **argv)
+{
+    Idx2BWT *bi; reads_t r; FILE *fo = NULL; hopt_t h; gap_opt_t *opt, sopt; uint32_t i, hdr[2];
+    int max_len = 0; bwt_aux_t aux; double t0, t1;
+    if (argc < 5) die("usage: seeds <prefix> <reads> <out> [opts]");
+    bi = load_index(argv[2]); r = load_reads(argv[3]);
+    opt = parse_opts(argc, argv, 5, &h);
+    for (i = 0; i < r.n; ++i) if ((int)r.len[i] > max_len) max_len = (int)r.len[i];
+    if (!h.nout) { fo = fopen(argv[4], "wb"); hdr[0] = 0x41415348u; hdr[1] = 6 * r.n; fwrite(hdr, 4, 2, fo); }
+    memset(&aux, 0, sizeof(aux));
+    aux.bi_bwt = bi; aux.max_len = max_len;
+    aux.width_seed = (bwt_width_t*)calloc(max_len + 1, sizeof(bwt_width_t));
+    g_occ4 = g_occ1 = 0;
+    t0 = now_s();
+    for (i = 0; i < r.n; ++i) {
+        int len = (int)r.len[i], s, seed_len = len / 3;
+        ubyte_t *seq = r.codes + r.off[i];
+        ubyte_t *rc = (ubyte_t*)calloc(max_len + 1, 1);
+        memcpy(rc, seq, len); seq_reverse(len, rc, 1);
+        for (s = 0; s < 6; ++s) {
+            int n_aln = 0, len_align = seed_len + (s % 3 == 2 ? len % 3 : 0);
+            bwt_aln1_t *aln;
+            sopt = *opt;                                   /* bwtgap.c:769-774 */
+            sopt.mode &= ~BWA_MODE_GAPE; sopt.max_gapo = 0; sopt.max_gape = 0;
+            sopt.max_diff = opt->max_seed_diff;
+            sopt.seed_len = len_align;                     /* bwtgap.c:802 */
+            aux.opt = &sopt;
+            /* bucket count only has to cover every reachable score; results do not depend on it */
+            aux.stack = gap_init_stack(sopt.max_diff + 8, 4, 12, opt);
+            aux.strand = s / 3; aux.len = len_align;
+            aux.seq = seq; aux.rc_seq = rc;
+            if (s < 3) aux.seq = seq + (s % 3) * seed_len; else aux.rc_seq = rc + (s % 3) * seed_len;
+            memset(aux.width_seed, 0, sizeof(bwt_width_t) * (max_len + 1));
+            bwt_cal_width(bi, len_align, aux.strand == 0 ? seq : rc, aux.width_seed, 1);
+            aux.width_back = aux.width_seed;
+            aln = bwt_match_gap(&aux, &n_aln);
+            { int j; for (j = 0; j < n_aln; ++j) { aln[j].start = (s % 3) * seed_len; aln[j].end = aln[j].start + len_align - 1; } } /* bwtgap.c:816-819 */
+            if (fo) put_aln(fo, n_aln, aln);
+            free(aln);
+            gap_destroy_stack(aux.stack);
+        }
+        free(rc);
+    }
+    t1 = now_s();
+    if (fo) fclose(fo);
+    printf("{\"mode\":\"seeds\",\"reads\":%u,\"calls\":%u,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu}\n",
+           r.n, 6 * r.n, t1 - t0, g_occ4, g_occ1);
+    return 0;
+}
+
+/* the stock batch driver bwa_cal_sa_reg_gap (bwtaln.c:246) over <batch>-read batches, option leak and
+ * splice fallback included.  With procs=P the read set is cut into P contiguous shards, one forked
+ * process each (the reference has no working threading: bwtaln.c:307-311, 481-504 are commented out);
+ * timing covers only the driver calls, max over processes. */
+static double run_driver_range(Idx2BWT *bi, reads_t *r, uint32_t lo, uint32_t hi, const gap_opt_t *opt0,
+                               const hopt_t *h, FILE *fo, unsigned long long *n_whole, unsigned long long *n_any)
+{
+    gap_opt_t *opt = (gap_opt_t*)calloc(2, sizeof(gap_opt_t));
+    bwt_array_t *arr = bwt_array_init();
+    double secs = 0; uint32_t b;
+    *opt = *opt0;
+    for (b = lo; b < hi; b += (uint32_t)h->batch) {
+        uint32_t e = b + (uint32_t)h->batch < hi ? b + (uint32_t)h->batch : hi, i;
+        int n = (int)(e - b);
+        bwa_seq_t *seqs = (bwa_seq_t*)calloc(n, sizeof(bwa_seq_t));
+        double t0;
+        for (i = b; i < e; ++i) { seqs[i - b].seq = r->codes + r->off[i]; seqs[i - b].len = r->len[i]; }
+        t0 = now_s();
+        bwa_cal_sa_reg_gap(0, bi, n, seqs, opt, arr);
+        secs += now_s() - t0;
+        for (i = 0; i < (uint32_t)n; ++i) {
+            bwa_seq_t *p = seqs + i;
+            if (p->n_aln) { ++*n_any; if (p->aln[0].type != BWA_TYPE_SPLICING && p->aln[0].start == 0 && p->aln[0].end == (int)p->len - 1) ++*n_whole; }
+            if (fo) put_aln(fo, p->n_aln, p->aln);
+            free(p->aln);
+        }
+        free(seqs);
+    }
+    return secs;
+}
+
+static int mode_driver(int argc, char **argv)
+{
+    Idx2BWT *bi; reads_t r; FILE *fo = NULL; hopt_t h; gap_opt_t *opt; uint32_t hdr[2];
+    unsigned long long n_whole = 0, n_any = 0; double secs;
+    if (argc < 5) die("usage: driver <prefix> <reads> <out> [opts] [batch=N] [procs=P] [nout=1]");
+    bi = load_index(argv[2]); r = load_reads(argv[3]);
+    opt = parse_opts(argc, argv, 5, &h);
+    g_occ4 = g_occ1 = 0;
+    if (h.procs <= 1) {
+        if (!h.nout) { fo = fopen(argv[4], "wb"); hdr[0] = 0x41415348u; hdr[1] = r.n; fwrite(hdr, 4, 2, fo); }
+        secs = run_driver_range(bi, &r, 0, r.n, opt, &h, fo, &n_whole, &n_any);
+        if (fo) fclose(fo);
+    } else {
+        /* timing only: fork P workers over contiguous shards, each reports its own driver seconds */
+        int p, fds[256][2]; double mx = 0;
+        if (h.procs > 256) die("procs too large");
+        for (p = 0; p < h.procs; ++p) {
+            pid_t pid;
+            if (pipe(fds[p]) != 0) die("pipe");
+            pid = fork();
+            if (pid < 0) die("fork");
+            if (pid == 0) {
+                uint32_t lo = (uint32_t)((uint64_t)r.n * p / h.procs), hi = (uint32_t)((uint64_t)r.n * (p + 1) / h.procs);
+                double res[3]; unsigned long long w = 0, a = 0;
+                res[0] = run_driver_range(bi, &r, lo, hi, opt, &h, NULL, &w, &a);
+                res[1] = (double)w; res[2] = (double)a;
+                if (write(fds[p][1], res, sizeof(res)) != (ssize_t)sizeof(res)) _exit(3);
+                _exit(0);
+            }
+            close(fds[p][1]);
+        }
+        for (p = 0; p < h.procs; ++p) {
+            double res[3] = {0, 0, 0};
+            if (read(fds[p][0], res, sizeof(res)) != (ssize_t)sizeof(res)) die("worker failed");
+            if (res[0] > mx) mx = res[0];
+            n_whole += (unsigned long long)res[1]; n_any += (unsigned long long)res[2];
+            close(fds[p][0]);
+        }
+        while (wait(NULL) > 0) {}
+        secs = mx;
+    }
+    printf("{\"mode\":\"driver\",\"reads\":%u,\"procs\":%d,\"batch\":%d,\"aligned_any\":%llu,\"aligned_whole\":%llu,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu}\n",
+           r.n, h.procs, h.batch, n_any, n_whole, secs, g_occ4, g_occ1);
+    return 0;
+}
+
+
+/* The whole-read part of bwa_cal_sa_reg_gap (bwtaln.c:303-360) WITHOUT the splice fallback and WITHOUT
+ * the option leak: per-read filters (:314-317, :324-325), revcomp strand first, forward strand only when
+ * the revcomp search found nothing (:343-359), a private option copy per read.  The loop body calls the
+ * real bwt_cal_width / bwt_match_gap.  This is exactly the work the CUDA batch entry point does, so it is
+ * the like-for-like CPU baseline; procs=P forks P workers over contiguous shards (timing only). */
+static double run_whole_range(Idx2BWT *bi, reads_t *r, uint32_t lo, uint32_t hi, const gap_opt_t *opt,
+                              const hopt_t *h, FILE *fo, unsigned long long *n_hit)
+{
+    int max_len = 0, local_max_diff; uint32_t i; bwt_aux_t aux; gap_opt_t ropt; double t0, secs;
+    for (i = lo; i < hi; ++i) if ((int)r->len[i] > max_len) max_len = (int)r->len[i];
+    local_max_diff = opt->fnr > 0.0 ? bwa_cal_maxdiff(max_len, BWA_AVG_ERR, opt->fnr) : opt->max_diff; /* :273-274 */
+    memset(&aux, 0, sizeof(aux));
+    aux.bi_bwt = bi; aux.max_len = max_len;
+    aux.width_back = (bwt_width_t*)calloc(max_len + 1, sizeof(bwt_width_t));
+    aux.width_seed = (bwt_width_t*)calloc(max_len + 1, sizeof(bwt_width_t));
+    aux.rc_seq = (ubyte_t*)calloc(max_len + 1, 1);
+    aux.stack = gap_init_stack(local_max_diff + 2, opt->max_gapo + 1, opt->max_gape + 1, opt);
+    t0 = now_s();
+    for (i = lo; i < hi; ++i) {
+        int len = (int)r->len[i], s, j, nn = 0, n_aln = 0; bwt_aln1_t *aln = NULL;
+        ubyte_t *seq = r->codes + r->off[i];
+        int polya = len >= 15, polyt = len >= 15;
+        for (j = 0; j < len; ++j) nn += seq[j] > 3;
+        for (j = 0; j < 15 && j < len; ++j) { polya &= seq[j] == 0; polyt &= seq[j] == 3; }
+        if (nn > local_max_diff || polya || polyt) { if (fo) put_aln(fo, 0, NULL); continue; }
+        memcpy(aux.rc_seq, seq, len); seq_reverse(len, aux.rc_seq, 1);
+        aux.seq = seq; aux.len = len;
+        resolve_read_opt(&ropt, opt, len, h->clear_gape);
+        aux.opt = &ropt;
+        for (s = 1; s >= 0; --s) {
+            bwt_width_t *keep = aux.width_seed;
+            if (len > ropt.seed_len)
+                bwt_cal_width(bi, ropt.seed_len, (s == 0 ? seq : aux.rc_seq) + (len - ropt.seed_len), aux.width_seed, 1);
+            else aux.width_seed = NULL;
+            bwt_cal_width(bi, len, s == 0 ? seq : aux.rc_seq, aux.width_back, 1);
+            aux.strand = s;
+            aln = bwt_match_gap(&aux, &n_aln);
+            aux.width_seed = keep;
+            if (n_aln) { for (j = 0; j < n_aln; ++j) aln[j].strand = s; break; }
+            free(aln); aln = NULL;
+        }
+        if (n_aln) { aln[0].start = 0; aln[0].end = len - 1; ++*n_hit; }   /* :371-372 */
+        if (fo) put_aln(fo, n_aln, aln);
+        free(aln);
+    }
+    secs = now_s() - t0;
+    gap_destroy_stack(aux.stack);
+    return secs;
+}
+
+static int mode_whole(int argc, char **argv)
+{
+    Idx2BWT *bi; reads_t r; FILE *fo = NULL; hopt_t h; gap_opt_t *opt; uint32_t hdr[2];
+    unsigned long long n_hit = 0; double secs;
+    if (argc < 5) die("usage: whole <prefix> <reads> <out> [opts] [procs=P] [nout=1]");
+    bi = load_index(argv[2]); r = load_reads(argv[3]);
+    opt = parse_opts(argc, argv, 5, &h);
+    g_occ4 = g_occ1 = 0;
+    if (h.procs <= 1) {
+        if (!h.nout) { fo = fopen(argv[4], "wb"); hdr[0] = 0x41415348u; hdr[1] = r.n; fwrite(hdr, 4, 2, fo); }
+        secs = run_whole_range(bi, &r, 0, r.n, opt, &h, fo, &n_hit);
+        if (fo) fclose(fo);
+    } else {
+        int p, fds[512][2]; double mx = 0;
+        if (h.procs > 512) die("procs too large");
+        for (p = 0; p < h.procs; ++p) {
+            pid_t pid;
+            if (pipe(fds[p]) != 0) die("pipe");
+            pid = fork();
+            if (pid < 0) die("fork");
+            if (pid == 0) {
+                uint32_t lo = (uint32_t)((uint64_t)r.n * p / h.procs), hi = (uint32_t)((uint64_t)r.n * (p + 1) / h.procs);
+                double res[2]; unsigned long long w = 0;
+                res[0] = run_whole_range(bi, &r, lo, hi, opt, &h, NULL, &w);
+                res[1] = (double)w;
+                if (write(fds[p][1], res, sizeof(res)) != (ssize_t)sizeof(res)) _exit(3);
+                _exit(0);
+            }
+            close(fds[p][1]);
+        }
+        for (p = 0; p < h.procs; ++p) {
+            double res[2] = {0, 0};
+            if (read(fds[p][0], res, sizeof(res)) != (ssize_t)sizeof(res)) die("worker failed");
+            if (res[0] > mx) mx = res[0];
+            n_hit += (unsigned long long)res[1];
+            close(fds[p][0]);
+        }
+        while (wait(NULL) > 0) {}
+        secs = mx;
+    }
+    printf("{\"mode\":\"whole\",\"reads\":%u,\"procs\":%d,\"aligned\":%llu,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu}\n",
+           r.n, h.procs, n_hit, secs, g_occ4, g_occ1);
+    return 0;
+}
+
+/* dump the raw search arrays of both BWTs so that the product's own index builder can be compared bit
+ * for bit with the reference builder's output:  per direction
+ *   textLength inverseSa0 cumulativeFreq[5] bwtWords occWords occMajorWords, then the three arrays. */
+static int mode_dumpindex(int argc, char **argv)
+{
+    Idx2BWT *bi; FILE *fo; int d;
+    if (argc < 4) die("usage: dumpindex <prefix> <out>");
+    bi = load_index(argv[2]);
+    fo = fopen(argv[3], "wb");
+    for (d = 0; d < 2; ++d) {
+        BWT *b = d == 0 ? bi->bwt : bi->rev_bwt;
+        uint32_t h[10];
+        h[0] = b->textLength; h[1] = b->inverseSa0; memcpy(h + 2, b->cumulativeFreq, 20);
+        h[7] = b->bwtSizeInWord; h[8] = b->occSizeInWord; h[9] = b->occMajorSizeInWord;
+        fwrite(h, 4, 10, fo);
+        fwrite(b->bwtCode, 4, b->bwtSizeInWord, fo);
+        fwrite(b->occValue, 4, b->occSizeInWord, fo);
+        fwrite(b->occValueMajor, 4, b->occMajorSizeInWord, fo);
+    }
+    fclose(fo);
+    printf("{\"mode\":\"dumpindex\",\"textLength\":%u}\n", bi->bwt->textLength);
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 2) die("usage: hsa_ref <index|occ|width|percall|seeds|driver|whole|dumpindex|maxdiff> ...");
+    if (strcmp(argv[1], "index") == 0) {
+        /* argv: index <db> <fasta>; the builder looks for "<argv0>.ini" = "index.ini" in cwd and falls
+         * back to compiled defaults (2BWT-Builder.c:242-243, :59-100). */
+        return bwa_index_main(argc - 1, argv + 1);
+    }
+    if (strcmp(argv[1], "occ") == 0) return mode_occ(argc, argv);
+    if (strcmp(argv[1], "width") == 0) return mode_width(argc, argv);
+    if (strcmp(argv[1], "percall") == 0) return mode_percall(argc, argv);
+    if (strcmp(argv[1], "seeds") == 0) return mode_seeds(argc, argv);
+    if (strcmp(argv[1], "driver") == 0) return mode_driver(argc, argv);
+    if (strcmp(argv[1], "whole") == 0) return mode_whole(argc, argv);
+    if (strcmp(argv[1], "dumpindex") == 0) return mode_dumpindex(argc, argv);
+    if (strcmp(argv[1], "maxdiff") == 0) {
+        int l;
+        for (l = 1; l <= (argc > 2 ? atoi(argv[2]) : 300); ++l)
+            printf("%d %d\n", l, bwa_cal_maxdiff(l, BWA_AVG_ERR, argc > 3 ? atof(argv[3]) : 0.04));
+        return 0;
+    }
+    die("unknown mode");
+    return 1;
+}
