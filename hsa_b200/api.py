@@ -1,0 +1,336 @@
+"""Python host mirror of the reference's interface for the inexact-search path, over the C ABI.
+
+Names follow the reference (gap_opt_t -> GapOpt, bwt_aln1_t -> numpy structured ALN_DTYPE,
+bwa_cal_sa_reg_gap's whole-read part -> Index.whole_reads, bwt_match_gap -> Index.match_gap_batch,
+bwt_splice_match's seed calls -> Index.splice_seeds, bwt_cal_width -> Index.cal_width,
+BWTAllOccValue -> Index.occ).  All compute goes through `libhsa_b200.so` (hand-written CUDA for
+sm_100a); if the library is missing or there is no CUDA device the calls raise -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhsa_b200.so")
+
+MODE_GAPE, MODE_COMPREAD, MODE_LOGGAP, MODE_NONSTOP = 0x01, 0x02, 0x04, 0x10
+SEED_NONE, SEED_TAIL, SEED_ALIAS = 0, 1, 2
+
+
+class HsaError(RuntimeError):
+    pass
+
+
+class GapOpt(C.Structure):
+    """gap_opt_t (bwtaln.h:133-143)."""
+    _fields_ = [("s_mm", C.c_int), ("s_gapo", C.c_int), ("s_gape", C.c_int), ("mode", C.c_int),
+                ("indel_end_skip", C.c_int), ("max_del_occ", C.c_int), ("max_entries", C.c_int),
+                ("fnr", C.c_float), ("max_diff", C.c_int), ("max_gapo", C.c_int), ("max_gape", C.c_int),
+                ("max_seed_diff", C.c_int), ("seed_len", C.c_int), ("n_threads", C.c_int),
+                ("max_top2", C.c_int), ("trim_qual", C.c_int)]
+
+
+class BwtView(C.Structure):
+    _fields_ = [("textLength", C.c_uint32), ("inverseSa0", C.c_uint32), ("cumulativeFreq", C.c_uint32 * 5),
+                ("bwtCode", C.c_void_p), ("bwtSizeInWord", C.c_uint32),
+                ("occValue", C.c_void_p), ("occSizeInWord", C.c_uint32),
+                ("occValueMajor", C.c_void_p), ("occMajorSizeInWord", C.c_uint32)]
+
+
+class Task(C.Structure):
+    """hsa_task_t: one bwt_match_gap call."""
+    _fields_ = [("read_off", C.c_uint64), ("read_len", C.c_uint32), ("strand", C.c_uint32),
+                ("sub_off", C.c_uint32), ("len", C.c_uint32), ("wsrc_off", C.c_uint32),
+                ("seed_mode", C.c_uint32), ("opt_idx", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+TASK_DTYPE = np.dtype([("read_off", "<u8"), ("read_len", "<u4"), ("strand", "<u4"), ("sub_off", "<u4"),
+                       ("len", "<u4"), ("wsrc_off", "<u4"), ("seed_mode", "<u4"), ("opt_idx", "<u4"),
+                       ("reserved", "<u4")])
+assert TASK_DTYPE.itemsize == C.sizeof(Task) == 40
+
+
+class _Result(C.Structure):
+    _fields_ = [("n_items", C.c_size_t), ("n_aln", C.POINTER(C.c_int32)), ("aln_off", C.POINTER(C.c_uint64)),
+                ("aln", C.c_void_p), ("n_aln_total", C.c_size_t), ("occ_lookups", C.c_uint64),
+                ("n_strict", C.c_uint64), ("pops", C.c_uint64), ("steps", C.c_uint64),
+                ("kernel_ms", C.c_float), ("kernel_launches", C.c_uint32),
+                ("cap_items", C.c_size_t), ("cap_aln", C.c_size_t)]
+
+
+# bwt_aln1_t (bwtaln.h:41-50) as 9 little-endian words; bit-fields unpacked by helpers below
+ALN_WORDS = 9
+
+
+def aln_fields(aln9: np.ndarray) -> dict:
+    """Unpack hsa_aln1_t words into named uint32/int32 columns."""
+    return dict(n_mm=aln9[:, 0] & 0xFFFF, n_gapo=(aln9[:, 0] >> 16) & 0xFF, n_gape=(aln9[:, 0] >> 24) & 0xFF,
+                k=aln9[:, 1], l=aln9[:, 2], rev_k=aln9[:, 3], rev_l=aln9[:, 4], type=aln9[:, 5] & 0x3FFFFFFF,
+                strand=aln9[:, 5] >> 30, start=aln9[:, 6].view(np.int32), end=aln9[:, 7].view(np.int32),
+                score=aln9[:, 8].view(np.int32))
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (python -m hsa_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HsaError(f"{LIB_PATH} is missing: build it with `python -m hsa_b200.build` "
+                       "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.hsa_b200_abi_version.restype = C.c_int
+    L.hsa_last_error.restype = C.c_char_p
+    L.hsa_gap_opt_default.argtypes = [C.POINTER(GapOpt)]
+    L.hsa_cal_maxdiff.argtypes = [C.c_int, C.c_double, C.c_double]
+    L.hsa_cal_maxdiff.restype = C.c_int
+    L.hsa_index_upload.argtypes = [C.c_int, C.POINTER(BwtView), C.POINTER(BwtView), C.POINTER(C.c_void_p)]
+    L.hsa_index_from_device.argtypes = [C.c_int, C.POINTER(BwtView), C.POINTER(BwtView), C.POINTER(C.c_void_p)]
+    L.hsa_index_blocks.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.hsa_index_from_blocks.argtypes = [C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p,
+                                        C.c_int, C.POINTER(C.c_void_p)]
+    L.hsa_index_meta.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32)]
+    L.hsa_index_free.argtypes = [C.c_void_p]
+    L.hsa_occ_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.hsa_cal_width_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                      C.c_void_p, C.c_void_p]
+    L.hsa_match_gap_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.c_size_t, C.POINTER(_Result)]
+    L.hsa_whole_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(GapOpt),
+                                  C.c_int, C.POINTER(_Result)]
+    L.hsa_splice_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(GapOpt),
+                                   C.POINTER(_Result)]
+    L.hsa_result_free.argtypes = [C.POINTER(_Result)]
+    L.hsa_workspace_create.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.hsa_workspace_free.argtypes = [C.c_void_p]
+    L.hsa_workspace_last_launches.argtypes = [C.c_void_p]
+    L.hsa_workspace_last_launches.restype = C.c_uint32
+    L.hsa_whole_reads_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.c_void_p, C.c_size_t, C.POINTER(GapOpt), C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.hsa_random_sector_probe.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise HsaError(f"hsa_b200 error {rc}: {lib().hsa_last_error().decode()}")
+
+
+def gap_init_opt(**overrides) -> GapOpt:
+    """gap_init_opt (bwtaln.c:21-44) with keyword overrides."""
+    o = GapOpt()
+    lib().hsa_gap_opt_default(C.byref(o))
+    for k, v in overrides.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+def bwa_cal_maxdiff(length: int, err: float = 0.02, thres: float = 0.04) -> int:
+    """bwa_cal_maxdiff (bwtaln.c:46-58)."""
+    return lib().hsa_cal_maxdiff(length, err, thres)
+
+
+def _view_host(arr) -> BwtView:
+    v = BwtView()
+    v.textLength, v.inverseSa0 = arr.text_length, arr.inverse_sa0
+    for i in range(5):
+        v.cumulativeFreq[i] = int(arr.cumulative_freq[i])
+    v.bwtCode, v.bwtSizeInWord = arr.bwt_code.ctypes.data, arr.bwt_code.shape[0]
+    v.occValue, v.occSizeInWord = arr.occ_value.ctypes.data, arr.occ_value.shape[0]
+    v.occValueMajor, v.occMajorSizeInWord = arr.occ_value_major.ctypes.data, arr.occ_value_major.shape[0]
+    return v
+
+
+class BatchResult:
+    """Flat result of a batch: per item n_aln and its hits (rows of 9 hsa_aln1_t words), in item order."""
+
+    def __init__(self, r: _Result, copy: bool = True):
+        n = r.n_items
+        tot = r.n_aln_total
+        n_aln = np.ctypeslib.as_array(r.n_aln, shape=(max(n, 1),))[:n]
+        off = np.ctypeslib.as_array(r.aln_off, shape=(max(n, 1),))[:n]
+        if tot:
+            aln = np.ctypeslib.as_array(C.cast(r.aln, C.POINTER(C.c_uint32)), shape=(tot * ALN_WORDS,))
+            aln = aln.reshape(tot, ALN_WORDS)
+        else:
+            aln = np.zeros((0, ALN_WORDS), dtype=np.uint32)
+        self.n_aln = n_aln.copy() if copy else n_aln
+        self.aln_off = off.copy() if copy else off
+        self.aln = aln.copy() if copy else aln
+        self.occ_lookups = int(r.occ_lookups)
+        self.n_strict = int(r.n_strict)
+        self.pops, self.steps = int(r.pops), int(r.steps)
+        self.kernel_ms = float(r.kernel_ms)
+        self.kernel_launches = int(r.kernel_launches)
+
+    def item(self, i: int) -> np.ndarray:
+        o, c = int(self.aln_off[i]), int(self.n_aln[i])
+        return self.aln[o:o + c]
+
+    def ordered(self) -> np.ndarray:
+        """All hits concatenated in item order (the device arena order is arbitrary)."""
+        if self.aln.shape[0] == 0:
+            return self.aln
+        nz = np.nonzero(self.n_aln)[0]
+        cnt = self.n_aln[nz].astype(np.int64)
+        starts = self.aln_off[nz].astype(np.int64)
+        idx = np.repeat(starts - np.concatenate([[0], np.cumsum(cnt)[:-1]]), cnt) + np.arange(int(cnt.sum()))
+        return self.aln[idx]
+
+
+class Index:
+    """Device-resident 2BWT search arrays (replaces the in-memory result of BWTLoad2BWT, 2BWT-Interface.c:13)."""
+
+    def __init__(self, handle: int, device: int):
+        self._h = C.c_void_p(handle)
+        self.device = device
+        self._res = _Result()
+
+    @classmethod
+    def upload(cls, index2bwt, device: int = 0) -> "Index":
+        """From host arrays (hsa_b200.index_io.Index2BWT: loaded reference files or index_build output)."""
+        vf, vr = _view_host(index2bwt.fwd), _view_host(index2bwt.rev)
+        h = C.c_void_p()
+        _check(lib().hsa_index_upload(device, C.byref(vf), C.byref(vr), C.byref(h)))
+        return cls(h.value, device)
+
+    @classmethod
+    def from_prefix(cls, prefix: str, device: int = 0) -> "Index":
+        from .index_io import load_index
+        return cls.upload(load_index(prefix), device)
+
+    @classmethod
+    def from_blocks(cls, meta_fwd, meta_rev, blocks_fwd_ptr: int, blocks_rev_ptr: int, device: int) -> "Index":
+        """Wrap device-layout blocks that already live on `device` (e.g. received by an NCCL broadcast).
+        The caller keeps the memory alive."""
+        mf = (C.c_uint32 * 7)(*[int(x) for x in meta_fwd])
+        mr = (C.c_uint32 * 7)(*[int(x) for x in meta_rev])
+        h = C.c_void_p()
+        _check(lib().hsa_index_from_blocks(device, mf, mr, blocks_fwd_ptr, blocks_rev_ptr, 0, C.byref(h)))
+        return cls(h.value, device)
+
+    def meta(self, which: int):
+        m = (C.c_uint32 * 7)()
+        _check(lib().hsa_index_meta(self._h, which, m))
+        return list(m)
+
+    def blocks(self, which: int):
+        p, b = C.c_void_p(), C.c_size_t()
+        _check(lib().hsa_index_blocks(self._h, which, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def close(self):
+        if self._h:
+            lib().hsa_result_free(C.byref(self._res))
+            lib().hsa_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- rank ---------------------------------------------------------------------------------------
+    def occ(self, which: int, indices: np.ndarray, layout: int = 1) -> np.ndarray:
+        """BWTAllOccValue (BWT.c:793) for every index; which: 0 fwd / 1 rev; layout 0 reference, 1 device."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        o4 = np.zeros((idx.shape[0], 4), dtype=np.uint32)
+        o1 = np.zeros((idx.shape[0], 4), dtype=np.uint32)
+        _check(lib().hsa_occ_batch(self._h, which, layout, idx.ctypes.data, idx.shape[0], o4.ctypes.data, o1.ctypes.data))
+        return o4
+
+    # ---- bwt_cal_width --------------------------------------------------------------------------------
+    def cal_width(self, codes: np.ndarray, off: np.ndarray, lens: np.ndarray):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        n = lens.shape[0]
+        total = int(lens.sum()) + n
+        w = np.zeros((total, 2), dtype=np.uint32)
+        bid = np.zeros(n, dtype=np.int32)
+        _check(lib().hsa_cal_width_batch(self._h, codes.ctypes.data, off.ctypes.data, lens.ctypes.data, n, 1,
+                                         w.ctypes.data, bid.ctypes.data))
+        return bid, w
+
+    # ---- bwt_match_gap ----------------------------------------------------------------------------------
+    def match_gap_batch(self, codes: np.ndarray, tasks: np.ndarray, opts) -> BatchResult:
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
+        optarr = (GapOpt * len(opts))(*opts)
+        _check(lib().hsa_match_gap_batch(self._h, codes.ctypes.data, codes.shape[0], tasks.ctypes.data, tasks.shape[0],
+                                         C.cast(optarr, C.c_void_p), len(opts), C.byref(self._res)))
+        return BatchResult(self._res)
+
+    def whole_reads(self, codes, off, lens, opt: GapOpt, keep_gape: int = 0, copy: bool = True) -> BatchResult:
+        """Whole-read part of bwa_cal_sa_reg_gap (bwtaln.c:303-360, 371-372). Accepts numpy arrays or raw
+        (pointer, ...) triples of pinned host buffers via objects exposing .ctypes / data_ptr()."""
+        cp, op, lp, n = _ptr(codes, np.uint8), _ptr(off, np.uint64), _ptr(lens, np.uint32), _len(lens)
+        _check(lib().hsa_whole_reads(self._h, cp[0], op[0], lp[0], n, C.byref(opt), keep_gape, C.byref(self._res)))
+        return BatchResult(self._res, copy=copy)
+
+    def splice_seeds(self, codes, off, lens, opt: GapOpt) -> BatchResult:
+        """The six seed searches of bwt_splice_match (bwtgap.c:797-820) per read."""
+        cp, op, lp, n = _ptr(codes, np.uint8), _ptr(off, np.uint64), _ptr(lens, np.uint32), _len(lens)
+        _check(lib().hsa_splice_seeds(self._h, cp[0], op[0], lp[0], n, C.byref(opt), C.byref(self._res)))
+        return BatchResult(self._res)
+
+
+def _ptr(x, dtype):
+    """(address, keepalive) of a numpy array (made contiguous / typed) or a torch tensor."""
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr(), x
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return a.ctypes.data, a
+
+
+def _len(x) -> int:
+    return int(x.shape[0])
+
+
+class DeviceWorkspace:
+    """Scratch for the device-resident entry point (reads and results stay in HBM)."""
+
+    def __init__(self, index: Index):
+        self.index = index
+        h = C.c_void_p()
+        _check(lib().hsa_workspace_create(index._h, 0, 0, 0, C.byref(h)))
+        self._h = h
+
+    def whole_reads_device(self, codes_ptr, off_ptr, len_ptr, n_reads, lens_present, opt, n_aln_ptr, aln_off_ptr,
+                           aln_ptr, aln_capacity, stats_ptr, stream_ptr=0, keep_gape=0):
+        lp = np.ascontiguousarray(lens_present, dtype=np.uint32)
+        _check(lib().hsa_whole_reads_device(self.index._h, self._h, codes_ptr, off_ptr, len_ptr, n_reads,
+                                            lp.ctypes.data, lp.shape[0], C.byref(opt), keep_gape, n_aln_ptr,
+                                            aln_off_ptr, aln_ptr, aln_capacity, stats_ptr, stream_ptr))
+
+    def last_launches(self) -> int:
+        return int(lib().hsa_workspace_last_launches(self._h))
+
+    def close(self):
+        if self._h:
+            lib().hsa_workspace_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def random_sector_probe(device: int, footprint_bytes: int, iters: int = 64) -> float:
+    """Measured random 32-byte-sector load throughput in GB/s over `footprint_bytes`."""
+    g = C.c_double()
+    _check(lib().hsa_random_sector_probe(device, footprint_bytes, iters, C.byref(g)))
+    return g.value

@@ -1,0 +1,907 @@
+// hsa_b200.cu -- CUDA kernels (sm_100a) and the C ABI of include/hsa_b200.h.
+//
+// Kernels:
+//   repack_kernel        reference-layout BWT + occ tables  ->  one 32-byte sector per 64 symbols
+//   occ_kernel           BWTAllOccValue / BWTOccValue on either layout (rank parity)
+//   search_kernel        persistent, atomic work queue; one worker (hsa_core.cuh) per thread runs the
+//                        width pass (bwt_cal_width) and the bounded backtracking search (bwt_match_gap)
+//   probe_kernel         random 32-byte-sector loads: the roofline denominator of SURVEY.md 8d
+//
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "hsa_core.cuh"
+#include "../../include/hsa_b200.h"
+
+using namespace hsa;
+
+static_assert(sizeof(hsa_task_t) == sizeof(Task), "hsa_task_t must mirror hsa::Task");
+static_assert(sizeof(hsa_aln1_t) == 36, "hsa_aln1_t must be 36 bytes like bwt_aln1_t");
+static_assert(sizeof(hsa_gap_opt_t) == 64, "hsa_gap_opt_t must be 64 bytes like gap_opt_t");
+static_assert(sizeof(hsa_width_t) == 8, "hsa_width_t must be 8 bytes like bwt_width_t");
+static_assert(sizeof(DevOpt) == 64, "DevOpt is staged as 16 ints");
+
+// =====================================================================================================
+// kernels
+// =====================================================================================================
+
+__global__ void repack_kernel(RefBwt ref, u32x4 *blocks, uint32_t n_blocks)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    uint32_t occ[4];
+    occ4_ref_raw(ref, b * 64u, occ);
+    u32x4 c, w;
+    c.x = occ[0]; c.y = occ[1]; c.z = occ[2]; c.w = occ[3];
+    const uint4 v = *reinterpret_cast<const uint4 *>(ref.bwt_code + 4 * (size_t)b);
+    w.x = v.x; w.y = v.y; w.z = v.z; w.w = v.w;
+    blocks[2 * (size_t)b] = c;
+    blocks[2 * (size_t)b + 1] = w;
+}
+
+__global__ void occ_kernel(DevBwt dev, RefBwt ref, int layout, const uint32_t *idx, size_t n,
+                           uint32_t *occ4_out, uint32_t *occ1_out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t occ[4];
+    if (layout == 1) occ4_dev(dev, idx[i], occ);
+    else occ4_ref(ref, idx[i], occ);
+    for (int c = 0; c < 4; ++c) { occ4_out[4 * i + c] = occ[c]; occ1_out[4 * i + c] = occ[c]; }
+}
+
+// MINB = minimum resident 256-thread blocks per SM the register allocation must allow (2: <=128 regs,
+// 3: <=80, 4: <=64); the variant is picked at run time (HSA_B200_MINB) so occupancy can be tuned on the GPU.
+template <int MAX_POPS, int MINB>
+__global__ void __launch_bounds__(256, MINB) search_kernel(const __grid_constant__ Params P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    DevOpt *sopt = reinterpret_cast<DevOpt *>(smem);
+    uint16_t *heads = reinterpret_cast<uint16_t *>(smem + (size_t)P.n_opts * sizeof(DevOpt));
+    for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
+        reinterpret_cast<int *>(sopt)[i] = reinterpret_cast<const int *>(P.opts)[i];
+    __syncthreads();
+
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    Worker w(P, slot, heads + threadIdx.x, blockDim.x, sopt);
+
+    for (;;) {
+        const bool need = w.idle();
+        const unsigned bal = __ballot_sync(0xffffffffu, need);
+        if (bal) {
+            // warp-aggregated fetch from the atomic work queue
+            unsigned long long base = 0;
+            const int leader = __ffs(bal) - 1;
+            if ((int)lane == leader) base = atomicAdd(&P.counters[CNT_WORK], (unsigned long long)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need) {
+                const unsigned long long idx = base + __popc(bal & ((1u << lane) - 1u));
+                if (idx < P.n_groups) w.start_group((uint32_t)idx);
+                else w.retire();
+            }
+        }
+        if (__all_sync(0xffffffffu, w.retired())) break;
+        w.template iterate<MAX_POPS>();
+    }
+
+    // statistics: warp-reduce, one atomic per warp
+    unsigned long long lk = w.lookups, pp = w.pops, st = w.steps;
+    for (int o = 16; o > 0; o >>= 1) {
+        lk += __shfl_down_sync(0xffffffffu, lk, o);
+        pp += __shfl_down_sync(0xffffffffu, pp, o);
+        st += __shfl_down_sync(0xffffffffu, st, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&P.counters[CNT_LOOKUPS], lk);
+        atomicAdd(&P.counters[CNT_POPS], pp);
+        atomicAdd(&P.counters[CNT_STEPS], st);
+    }
+}
+
+// Random-sector probe: every thread walks `iters` pseudo-random 32-byte sectors of `buf` (n_sectors),
+// two independent 16-byte loads per sector like an occ lookup, `CHAINS` independent chains per thread.
+template <int CHAINS>
+__global__ void probe_kernel(const uint4 *buf, uint64_t n_sectors, int iters, unsigned long long *sink)
+{
+    uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t s[CHAINS];
+    uint32_t acc = 0;
+    for (int c = 0; c < CHAINS; ++c) s[c] = (tid * CHAINS + c) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) {
+            s[c] = s[c] * 6364136223846793005ull + 1442695040888963407ull;
+            uint64_t sec = (s[c] >> 20) % n_sectors;
+            uint4 a = __ldg(buf + 2 * sec), b = __ldg(buf + 2 * sec + 1);
+            acc += a.x ^ b.w;
+            s[c] ^= (uint64_t)(a.y & 1u);            // make the next address depend on the load
+        }
+    }
+    if (acc == 0xDEADBEEFu) atomicAdd(sink, 1ull);
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(HSA_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+    } while (0)
+
+static long env_long(const char *name, long dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atol(v) : dflt;
+}
+
+struct hsa_index {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t *ref_code[2] = {nullptr, nullptr}, *ref_occ[2] = {nullptr, nullptr}, *ref_major[2] = {nullptr, nullptr};
+    bool own_ref = false;
+    u32x4 *blocks[2] = {nullptr, nullptr};
+    bool own_blocks = false;
+    DevIndex ix;
+    RefBwt ref[2];
+    bool have_ref = false;
+    struct hsa_workspace *ws = nullptr;      // lazily created for the host-buffer entry points
+    int sm_count = 0;
+};
+
+struct Scratch {                             // worker-private device memory for one launch configuration
+    uint32_t grid = 0, block = 0, n_workers = 0;
+    uint32_t arena_cap = 0, hit_cap = 0, max_len = 0;
+    u32x4 *arena = nullptr; uint16_t *links = nullptr; u32x2 *width = nullptr; Hit *hits = nullptr;
+    void release()
+    {
+        cudaFree(arena); cudaFree(links); cudaFree(width); cudaFree(hits);
+        arena = nullptr; links = nullptr; width = nullptr; hits = nullptr; n_workers = 0;
+    }
+};
+
+struct hsa_workspace {
+    const hsa_index *idx = nullptr;
+    Scratch fast, strict;
+    unsigned long long *counters = nullptr;          // CNT_N
+    uint32_t *strict_list = nullptr; size_t strict_list_cap = 0;
+    DevOpt *opts_dev = nullptr; size_t opts_cap = 0;
+    uint16_t *len2opt_dev = nullptr; size_t len2opt_cap = 0;
+    uint8_t *status_dev = nullptr; size_t status_cap = 0;
+    // staging for the host-buffer entry points
+    uint8_t *codes_dev = nullptr; size_t codes_cap = 0;
+    uint64_t *off_dev = nullptr; uint32_t *len_dev = nullptr; size_t reads_cap = 0;
+    Task *tasks_dev = nullptr; size_t tasks_cap = 0;
+    int32_t *n_aln_dev = nullptr; size_t items_cap = 0; uint64_t *aln_off_dev = nullptr; size_t items2_cap = 0;
+    uint32_t *aln_dev = nullptr; size_t aln_cap = 0;
+    u32x2 *width_out_dev = nullptr; size_t width_out_cap = 0; int32_t *bid_dev = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t last_launches = 0;
+    int blocks_per_sm = 0;
+    int minb = 3;
+};
+
+template <typename T>
+static int ensure(T *&p, size_t &cap, size_t need)
+{
+    if (need <= cap && p) return HSA_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t n = need + need / 8 + 64;
+    CU(cudaMalloc((void **)&p, n * sizeof(T)));
+    cap = n;
+    return HSA_OK;
+}
+
+static void to_devopt(const hsa_gap_opt_t &o, DevOpt &d)
+{
+    memset(&d, 0, sizeof(d));
+    d.s_mm = o.s_mm; d.s_gapo = o.s_gapo; d.s_gape = o.s_gape; d.mode = o.mode;
+    d.indel_end_skip = o.indel_end_skip; d.max_del_occ = o.max_del_occ; d.max_entries = o.max_entries;
+    d.max_diff = o.max_diff; d.max_gapo = o.max_gapo; d.max_gape = o.max_gape;
+    d.max_seed_diff = o.max_seed_diff; d.seed_len = o.seed_len; d.max_top2 = o.max_top2;
+}
+
+static int check_opt(const hsa_gap_opt_t &o, uint32_t max_len, uint32_t *n_buckets)
+{
+    if (o.s_mm < 0 || o.s_gapo < 0 || o.s_gape < 0) return fail(HSA_E_ARG, "negative scores are not supported");
+    if (o.max_diff < 0) return fail(HSA_E_ARG, "max_diff < 0 after resolution (fnr <= 0 and max_diff unset?)");
+    if (o.max_diff > 61 || o.max_gapo > 30 || o.max_gape > 62 || o.max_gapo < 0 || o.max_gape < 0)
+        return fail(HSA_E_ARG, "max_diff/max_gapo/max_gape exceed the packed stack-entry fields (61/30/62)");
+    if (max_len > 4095) return fail(HSA_E_ARG, "reads longer than 4095 bases are not supported");
+    long nb = (long)(o.max_diff + 1) * o.s_mm + (long)(o.max_gapo + 1) * o.s_gapo + (long)(o.max_gape + 1) * o.s_gape + 1;
+    if (nb > 128) return fail(HSA_E_ARG, "score range exceeds 128 buckets: (max_diff+1)*s_mm+(max_gapo+1)*s_gapo+(max_gape+1)*s_gape+1 > 128");
+    if ((uint32_t)nb > *n_buckets) *n_buckets = (uint32_t)nb;
+    return HSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- basics
+extern "C" int hsa_b200_abi_version(void) { return HSA_B200_ABI_VERSION; }
+extern "C" const char *hsa_last_error(void) { return g_err.c_str(); }
+
+extern "C" void hsa_gap_opt_default(hsa_gap_opt_t *o)          // gap_init_opt, bwtaln.c:21-44
+{
+    memset(o, 0, sizeof(*o));
+    o->s_mm = 3; o->s_gapo = 11; o->s_gape = 4;
+    o->max_diff = -1; o->max_gapo = 1; o->max_gape = 6;
+    o->indel_end_skip = 5; o->max_del_occ = 10; o->max_entries = 2000000;
+    o->mode = HSA_MODE_GAPE | HSA_MODE_COMPREAD;
+    o->seed_len = 32; o->max_seed_diff = 2;
+    o->fnr = 0.04f;
+    o->n_threads = 1; o->max_top2 = 30; o->trim_qual = 0;
+}
+
+extern "C" int hsa_cal_maxdiff(int l, double err, double thres) // bwa_cal_maxdiff, bwtaln.c:46-58
+{
+    double elambda = exp(-l * err), sum, y = 1.0;
+    int k, x = 1;
+    for (k = 1, sum = elambda; k < 1000; ++k) {
+        y *= l * err;
+        x = (int)((unsigned)x * (unsigned)k);       // the reference's int product wraps for k > 12; keep that
+        sum += elambda * y / x;
+        if (1.0 - sum < thres) return k;
+    }
+    return 2;
+}
+
+// ---------------------------------------------------------------------------------------------- index
+static int init_index_common(hsa_index *ix, int device)
+{
+    ix->device = device;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CU(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device));
+    return HSA_OK;
+}
+
+static void fill_dev_bwt(DevBwt &d, const hsa_bwt_view_t *v, const u32x4 *blocks)
+{
+    d.blocks = blocks; d.n_blocks = v->textLength / 64 + 1; d.text_length = v->textLength; d.inverse_sa0 = v->inverseSa0;
+    for (int i = 0; i < 5; ++i) d.cum[i] = v->cumulativeFreq[i];
+}
+
+static int repack_direction(hsa_index *ix, int which, const hsa_bwt_view_t *v)
+{
+    uint32_t nb = v->textLength / 64 + 1;
+    if ((size_t)4 * nb > v->bwtSizeInWord)
+        return fail(HSA_E_ARG, "bwtCode array shorter than the resident size BWTLoad allocates (BWT.c:176)");
+    CU(cudaMalloc((void **)&ix->blocks[which], (size_t)nb * 2 * sizeof(u32x4)));
+    ix->own_blocks = true;
+    repack_kernel<<<(nb + 255) / 256, 256, 0, ix->stream>>>(ix->ref[which], ix->blocks[which], nb);
+    CU(cudaGetLastError());
+    fill_dev_bwt(which == 0 ? ix->ix.fwd : ix->ix.rev, v, ix->blocks[which]);
+    return HSA_OK;
+}
+
+static int validate_view(const hsa_bwt_view_t *v)
+{
+    if (!v || !v->bwtCode || !v->occValue || !v->occValueMajor) return fail(HSA_E_ARG, "null BWT view");
+    if (v->cumulativeFreq[4] != v->textLength) return fail(HSA_E_ARG, "cumulativeFreq[4] != textLength");
+    uint32_t n = v->textLength, num = (n + 255) / 256 + 1;
+    if (v->occSizeInWord < (num + 1) / 2 * 4 || v->occMajorSizeInWord < (num + 255) / 256 * 4)
+        return fail(HSA_E_ARG, "occ tables shorter than BWTOccValue{Minor,Major}SizeInWord (BWT.c:1097-1116)");
+    return HSA_OK;
+}
+
+extern "C" int hsa_index_upload(int device, const hsa_bwt_view_t *fwd, const hsa_bwt_view_t *rev, hsa_index_t **out)
+{
+    if (!out) return fail(HSA_E_ARG, "out is null");
+    int rc;
+    if ((rc = validate_view(fwd)) || (rc = validate_view(rev))) return rc;
+    hsa_index *ix = new hsa_index();
+    if ((rc = init_index_common(ix, device))) { delete ix; return rc; }
+    const hsa_bwt_view_t *vs[2] = {fwd, rev};
+    ix->own_ref = true; ix->have_ref = true;
+    for (int d = 0; d < 2; ++d) {
+        const hsa_bwt_view_t *v = vs[d];
+        CU(cudaMalloc((void **)&ix->ref_code[d], (size_t)v->bwtSizeInWord * 4));
+        CU(cudaMalloc((void **)&ix->ref_occ[d], (size_t)v->occSizeInWord * 4));
+        CU(cudaMalloc((void **)&ix->ref_major[d], (size_t)v->occMajorSizeInWord * 4));
+        CU(cudaMemcpyAsync(ix->ref_code[d], v->bwtCode, (size_t)v->bwtSizeInWord * 4, cudaMemcpyHostToDevice, ix->stream));
+        CU(cudaMemcpyAsync(ix->ref_occ[d], v->occValue, (size_t)v->occSizeInWord * 4, cudaMemcpyHostToDevice, ix->stream));
+        CU(cudaMemcpyAsync(ix->ref_major[d], v->occValueMajor, (size_t)v->occMajorSizeInWord * 4, cudaMemcpyHostToDevice, ix->stream));
+        ix->ref[d].bwt_code = ix->ref_code[d]; ix->ref[d].occ_value = ix->ref_occ[d]; ix->ref[d].occ_major = ix->ref_major[d];
+        ix->ref[d].text_length = v->textLength; ix->ref[d].inverse_sa0 = v->inverseSa0;
+        if ((rc = repack_direction(ix, d, v))) return rc;
+    }
+    CU(cudaStreamSynchronize(ix->stream));
+    *out = ix;
+    return HSA_OK;
+}
+
+extern "C" int hsa_index_from_device(int device, const hsa_bwt_view_t *fwd, const hsa_bwt_view_t *rev, hsa_index_t **out)
+{
+    if (!out) return fail(HSA_E_ARG, "out is null");
+    int rc;
+    if ((rc = validate_view(fwd)) || (rc = validate_view(rev))) return rc;
+    hsa_index *ix = new hsa_index();
+    if ((rc = init_index_common(ix, device))) { delete ix; return rc; }
+    const hsa_bwt_view_t *vs[2] = {fwd, rev};
+    ix->own_ref = false; ix->have_ref = true;
+    for (int d = 0; d < 2; ++d) {
+        const hsa_bwt_view_t *v = vs[d];
+        ix->ref[d].bwt_code = v->bwtCode; ix->ref[d].occ_value = v->occValue; ix->ref[d].occ_major = v->occValueMajor;
+        ix->ref[d].text_length = v->textLength; ix->ref[d].inverse_sa0 = v->inverseSa0;
+        if ((rc = repack_direction(ix, d, v))) return rc;
+    }
+    CU(cudaStreamSynchronize(ix->stream));
+    // the caller keeps ownership of the reference-layout arrays and may free them now
+    ix->have_ref = false;
+    *out = ix;
+    return HSA_OK;
+}
+
+extern "C" int hsa_index_blocks(const hsa_index_t *ix, int which, void **dev_ptr, size_t *bytes)
+{
+    if (!ix || which < 0 || which > 1) return fail(HSA_E_ARG, "bad index / direction");
+    const DevBwt &b = which == 0 ? ix->ix.fwd : ix->ix.rev;
+    if (dev_ptr) *dev_ptr = (void *)b.blocks;
+    if (bytes) *bytes = (size_t)b.n_blocks * 2 * sizeof(u32x4);
+    return HSA_OK;
+}
+
+extern "C" int hsa_index_meta(const hsa_index_t *ix, int which, uint32_t meta[7])
+{
+    if (!ix || which < 0 || which > 1) return fail(HSA_E_ARG, "bad index / direction");
+    const DevBwt &b = which == 0 ? ix->ix.fwd : ix->ix.rev;
+    meta[0] = b.text_length; meta[1] = b.inverse_sa0;
+    for (int i = 0; i < 5; ++i) meta[2 + i] = b.cum[i];
+    return HSA_OK;
+}
+
+extern "C" int hsa_index_from_blocks(int device, const uint32_t meta_fwd[7], const uint32_t meta_rev[7],
+                                     void *blocks_fwd_dev, void *blocks_rev_dev, int take_ownership, hsa_index_t **out)
+{
+    if (!out || !blocks_fwd_dev || !blocks_rev_dev) return fail(HSA_E_ARG, "null argument");
+    hsa_index *ix = new hsa_index();
+    int rc;
+    if ((rc = init_index_common(ix, device))) { delete ix; return rc; }
+    const uint32_t *ms[2] = {meta_fwd, meta_rev};
+    void *bs[2] = {blocks_fwd_dev, blocks_rev_dev};
+    for (int d = 0; d < 2; ++d) {
+        DevBwt &b = d == 0 ? ix->ix.fwd : ix->ix.rev;
+        b.blocks = (const u32x4 *)bs[d]; b.text_length = ms[d][0]; b.inverse_sa0 = ms[d][1];
+        b.n_blocks = ms[d][0] / 64 + 1;
+        for (int i = 0; i < 5; ++i) b.cum[i] = ms[d][2 + i];
+        ix->blocks[d] = (u32x4 *)bs[d];
+    }
+    ix->own_blocks = take_ownership != 0;
+    *out = ix;
+    return HSA_OK;
+}
+
+extern "C" void hsa_workspace_free(hsa_workspace_t *ws);
+
+extern "C" void hsa_index_free(hsa_index_t *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->ws) hsa_workspace_free(ix->ws);
+    if (ix->own_ref) for (int d = 0; d < 2; ++d) { cudaFree(ix->ref_code[d]); cudaFree(ix->ref_occ[d]); cudaFree(ix->ref_major[d]); }
+    if (ix->own_blocks) for (int d = 0; d < 2; ++d) cudaFree(ix->blocks[d]);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+// ---------------------------------------------------------------------------------------------- rank
+extern "C" int hsa_occ_batch(const hsa_index_t *ix, int which, int layout, const uint32_t *indices, size_t n,
+                             uint32_t *occ4_out, uint32_t *occ1_out)
+{
+    if (!ix || which < 0 || which > 1 || (layout != 0 && layout != 1)) return fail(HSA_E_ARG, "bad argument");
+    if (layout == 0 && !ix->have_ref) return fail(HSA_E_ARG, "reference-layout arrays are not resident in this index");
+    if (n == 0) return HSA_OK;
+    CU(cudaSetDevice(ix->device));
+    uint32_t *d_idx = nullptr, *d4 = nullptr, *d1 = nullptr;
+    CU(cudaMalloc((void **)&d_idx, n * 4)); CU(cudaMalloc((void **)&d4, n * 16)); CU(cudaMalloc((void **)&d1, n * 16));
+    CU(cudaMemcpyAsync(d_idx, indices, n * 4, cudaMemcpyHostToDevice, ix->stream));
+    occ_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ix->stream>>>(which == 0 ? ix->ix.fwd : ix->ix.rev, ix->ref[which],
+                                                                    layout, d_idx, n, d4, d1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(occ4_out, d4, n * 16, cudaMemcpyDeviceToHost, ix->stream));
+    if (occ1_out) CU(cudaMemcpyAsync(occ1_out, d1, n * 16, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+    cudaFree(d_idx); cudaFree(d4); cudaFree(d1);
+    return HSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- workspace
+static int scratch_alloc(Scratch &s, uint32_t grid, uint32_t block, uint32_t arena_cap, uint32_t hit_cap, uint32_t max_len)
+{
+    uint32_t nw = grid * block;
+    if (s.n_workers >= nw && s.arena_cap == arena_cap && s.hit_cap == hit_cap && s.max_len >= max_len) {
+        s.grid = grid; s.block = block;
+        return HSA_OK;
+    }
+    s.release();
+    CU(cudaMalloc((void **)&s.arena, (size_t)nw * arena_cap * sizeof(u32x4)));
+    CU(cudaMalloc((void **)&s.links, (size_t)nw * arena_cap * sizeof(uint16_t)));
+    CU(cudaMalloc((void **)&s.width, (size_t)nw * 2 * (max_len + 1) * sizeof(u32x2)));
+    CU(cudaMalloc((void **)&s.hits, (size_t)nw * hit_cap * sizeof(Hit)));
+    s.grid = grid; s.block = block; s.n_workers = nw; s.arena_cap = arena_cap; s.hit_cap = hit_cap; s.max_len = max_len;
+    return HSA_OK;
+}
+
+extern "C" int hsa_workspace_create(const hsa_index_t *ix, size_t max_reads, uint32_t max_len, size_t aln_capacity,
+                                    hsa_workspace_t **out)
+{
+    (void)max_reads; (void)aln_capacity;
+    if (!ix || !out) return fail(HSA_E_ARG, "null argument");
+    CU(cudaSetDevice(ix->device));
+    hsa_workspace *ws = new hsa_workspace();
+    ws->idx = ix;
+    CU(cudaMalloc((void **)&ws->counters, CNT_N * sizeof(unsigned long long)));
+    CU(cudaEventCreate(&ws->ev0)); CU(cudaEventCreate(&ws->ev1));
+    (void)max_len;
+    *out = ws;
+    return HSA_OK;
+}
+
+extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
+{
+    if (!ws) return;
+    ws->fast.release(); ws->strict.release();
+    cudaFree(ws->counters); cudaFree(ws->strict_list); cudaFree(ws->opts_dev); cudaFree(ws->len2opt_dev);
+    cudaFree(ws->status_dev); cudaFree(ws->codes_dev); cudaFree(ws->off_dev); cudaFree(ws->len_dev);
+    cudaFree(ws->tasks_dev); cudaFree(ws->n_aln_dev); cudaFree(ws->aln_off_dev); cudaFree(ws->aln_dev);
+    cudaFree(ws->width_out_dev); cudaFree(ws->bid_dev);
+    if (ws->ev0) cudaEventDestroy(ws->ev0);
+    if (ws->ev1) cudaEventDestroy(ws->ev1);
+    delete ws;
+}
+
+extern "C" uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws) { return ws ? ws->last_launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- launch
+static const void *search_fn(int minb)
+{
+    switch (minb) {
+    case 2: return (const void *)search_kernel<2, 2>;
+    case 4: return (const void *)search_kernel<2, 4>;
+    default: return (const void *)search_kernel<2, 3>;
+    }
+}
+
+struct Batch {                      // everything one launch needs, device pointers
+    uint32_t kind = 0, n_groups = 0, n_items = 0, max_len = 0, n_opts = 0, n_buckets = 1;
+    int32_t filter_max_n = 0;
+    const uint8_t *codes = nullptr; const Task *tasks = nullptr;
+    const uint64_t *read_off = nullptr; const uint32_t *read_len = nullptr;
+    int32_t *n_aln = nullptr; uint64_t *aln_off = nullptr; uint32_t *aln = nullptr; uint64_t aln_cap = 0;
+    u32x2 *width_out = nullptr; int32_t *bid_out = nullptr;
+};
+
+static int launch_search(hsa_workspace *ws, const Batch &b, Scratch &sc, const uint32_t *group_list, uint32_t n_work,
+                         cudaStream_t stream)
+{
+    Params P;
+    memset(&P, 0, sizeof(P));
+    P.ix = ws->idx->ix; P.codes = b.codes; P.kind = b.kind; P.n_groups = n_work; P.group_list = group_list;
+    P.tasks = b.tasks; P.read_off = b.read_off; P.read_len = b.read_len;
+    P.opts = ws->opts_dev; P.n_opts = b.n_opts; P.len2opt = ws->len2opt_dev; P.max_len = sc.max_len;
+    P.filter_max_n = b.filter_max_n;
+    P.arena = sc.arena; P.links = sc.links; P.arena_cap = sc.arena_cap;
+    P.width = sc.width; P.width_stride = 2 * (sc.max_len + 1);
+    P.hits = sc.hits; P.hit_cap = sc.hit_cap; P.n_buckets = b.n_buckets;
+    P.n_aln = b.n_aln; P.aln_off = b.aln_off; P.status = ws->status_dev; P.aln = b.aln; P.aln_cap = b.aln_cap;
+    P.counters = ws->counters; P.strict_list = ws->strict_list;
+    P.width_out = b.width_out; P.bid_out = b.bid_out;
+    size_t smem = (size_t)b.n_opts * sizeof(DevOpt) + (size_t)b.n_buckets * sc.block * sizeof(uint16_t);
+    const void *fn = search_fn(ws->minb);
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[] = {(void *)&P};
+    CU(cudaLaunchKernel(fn, dim3(sc.grid), dim3(sc.block), args, smem, stream));
+    ++ws->last_launches;
+    return HSA_OK;
+}
+
+// Runs one batch whose inputs/outputs are already on the device.  `sync` selects whether the call waits
+// and handles strict re-runs (host-buffer entry points) or just enqueues (device entry point).
+static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, bool sync, uint64_t stats[CNT_N], float *ms)
+{
+    const hsa_index *ix = ws->idx;
+    CU(cudaSetDevice(ix->device));
+    ws->last_launches = 0;
+    const uint32_t block = 256;
+    size_t smem = (size_t)b.n_opts * sizeof(DevOpt) + (size_t)b.n_buckets * block * sizeof(uint16_t);
+    if (smem > 200 * 1024) return fail(HSA_E_ARG, "option table too large for shared memory");
+    if (!ws->blocks_per_sm) {
+        int occ = 0;
+        ws->minb = (int)env_long("HSA_B200_MINB", 3);
+        const void *fn = search_fn(ws->minb);
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)block, smem));
+        if (occ < 1) return fail(HSA_E_CUDA, "search kernel does not fit on an SM");
+        ws->blocks_per_sm = (int)env_long("HSA_B200_BLOCKS_PER_SM", occ);
+        if (ws->blocks_per_sm > occ) ws->blocks_per_sm = occ;
+    }
+    uint32_t grid_full = (uint32_t)(ix->sm_count * ws->blocks_per_sm);
+    uint32_t grid = std::min<uint32_t>(grid_full, (b.n_groups + block - 1) / block);
+    if (grid == 0) grid = 1;
+    uint32_t arena_cap = (uint32_t)env_long("HSA_B200_ARENA_CAP", 4096), hit_cap = (uint32_t)env_long("HSA_B200_HIT_CAP", 32);
+    if (arena_cap > 65535) arena_cap = 65535;
+    int rc;
+    // small batches get a small scratch; anything that fills the GPU gets the full-grid scratch once
+    if ((rc = scratch_alloc(ws->fast, grid, block, arena_cap, hit_cap, b.max_len))) return rc;
+    ws->fast.grid = grid;
+    if ((rc = ensure(ws->status_dev, ws->status_cap, (size_t)b.n_items + 1))) return rc;
+    if ((rc = ensure(ws->strict_list, ws->strict_list_cap, (size_t)b.n_groups + 1))) return rc;
+    CU(cudaMemsetAsync(ws->counters, 0, CNT_N * sizeof(unsigned long long), stream));
+    CU(cudaEventRecord(ws->ev0, stream));
+    if ((rc = launch_search(ws, b, ws->fast, nullptr, b.n_groups, stream))) return rc;
+    CU(cudaEventRecord(ws->ev1, stream));
+    if (!sync) return HSA_OK;
+
+    unsigned long long cnt[CNT_N];
+    CU(cudaMemcpyAsync(cnt, ws->counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
+    *ms = t;
+    if (cnt[CNT_BAD]) return fail(HSA_E_ARG, "a score exceeded the bucket table (internal sizing error)");
+    uint64_t n_strict = cnt[CNT_STRICT];
+    if (n_strict) {
+        // re-run the groups that ran out of stack / hit capacity with the large-capacity configuration
+        uint32_t sblock = 64, sgrid = (uint32_t)std::min<uint64_t>((n_strict + sblock - 1) / sblock, (uint64_t)ix->sm_count);
+        if ((rc = scratch_alloc(ws->strict, sgrid, sblock, 65535, 4096, b.max_len))) return rc;
+        uint32_t *list_dev = nullptr;
+        CU(cudaMalloc((void **)&list_dev, n_strict * 4));
+        CU(cudaMemcpyAsync(list_dev, ws->strict_list, n_strict * 4, cudaMemcpyDeviceToDevice, stream));
+        unsigned long long zero[3] = {0, 0, 0};
+        CU(cudaMemcpyAsync(ws->counters + CNT_WORK, zero, 8, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(ws->counters + CNT_STRICT, zero, 16, cudaMemcpyHostToDevice, stream));
+        CU(cudaEventRecord(ws->ev0, stream));
+        if ((rc = launch_search(ws, b, ws->strict, list_dev, (uint32_t)n_strict, stream))) { cudaFree(list_dev); return rc; }
+        CU(cudaEventRecord(ws->ev1, stream));
+        unsigned long long cnt2[CNT_N];
+        CU(cudaMemcpyAsync(cnt2, ws->counters, sizeof(cnt2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        cudaFree(list_dev);
+        CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
+        *ms += t;
+        if (cnt2[CNT_STRICT] || cnt2[CNT_BAD])
+            return fail(HSA_E_CAPACITY, "a search exceeded the strict kernel's 65535-entry stack or 4096-hit capacity");
+        for (int i = 0; i < CNT_N; ++i) cnt[i] = cnt2[i];
+    }
+    for (int i = 0; i < CNT_N; ++i) stats[i] = cnt[i];
+    stats[CNT_STRICT] = n_strict;
+    return HSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- results
+static int result_reserve(hsa_result_t *r, size_t n_items, size_t n_aln)
+{
+    if (n_items > r->cap_items || !r->n_aln) {
+        if (r->n_aln) cudaFreeHost(r->n_aln);
+        if (r->aln_off) cudaFreeHost(r->aln_off);
+        r->n_aln = nullptr; r->aln_off = nullptr; r->cap_items = 0;
+        size_t c = n_items + n_items / 8 + 16;
+        CU(cudaHostAlloc((void **)&r->n_aln, c * sizeof(int32_t), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void **)&r->aln_off, c * sizeof(uint64_t), cudaHostAllocDefault));
+        r->cap_items = c;
+    }
+    if (n_aln > r->cap_aln || !r->aln) {
+        if (r->aln) cudaFreeHost(r->aln);
+        r->aln = nullptr; r->cap_aln = 0;
+        size_t c = n_aln + n_aln / 8 + 16;
+        CU(cudaHostAlloc((void **)&r->aln, c * sizeof(hsa_aln1_t), cudaHostAllocDefault));
+        r->cap_aln = c;
+    }
+    return HSA_OK;
+}
+
+extern "C" void hsa_result_free(hsa_result_t *r)
+{
+    if (!r) return;
+    if (r->n_aln) cudaFreeHost(r->n_aln);
+    if (r->aln_off) cudaFreeHost(r->aln_off);
+    if (r->aln) cudaFreeHost(r->aln);
+    memset(r, 0, sizeof(*r));
+}
+
+static int get_ws(const hsa_index_t *ix, hsa_workspace **out)
+{
+    hsa_index *m = const_cast<hsa_index *>(ix);
+    if (!m->ws) { int rc = hsa_workspace_create(ix, 0, 0, 0, &m->ws); if (rc) return rc; }
+    *out = m->ws;
+    return HSA_OK;
+}
+
+// shared tail of the host-buffer entry points: run (retrying with a larger hit arena if needed), copy back
+static int run_and_fetch(hsa_workspace *ws, Batch &b, hsa_result_t *res)
+{
+    const hsa_index *ix = ws->idx;
+    int rc;
+    if ((rc = ensure(ws->n_aln_dev, ws->items_cap, (size_t)b.n_items + 1))) return rc;
+    if ((rc = ensure(ws->aln_off_dev, ws->items2_cap, (size_t)b.n_items + 1))) return rc;
+    size_t want = std::max<size_t>((size_t)b.n_items * 2 + 1024, ws->aln_cap / 9);
+    uint64_t stats[CNT_N];
+    float ms = 0, ms_total = 0;
+    uint32_t launches = 0;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if ((rc = ensure(ws->aln_dev, ws->aln_cap, want * 9))) return rc;
+        b.n_aln = ws->n_aln_dev; b.aln_off = ws->aln_off_dev; b.aln = ws->aln_dev; b.aln_cap = want;
+        if ((rc = run_batch(ws, b, ix->stream, true, stats, &ms))) return rc;
+        ms_total += ms; launches += ws->last_launches;
+        if (stats[CNT_ALN] <= want) break;
+        want = stats[CNT_ALN] + 1024;                // the counter kept counting past the capacity
+        if (attempt == 2) return fail(HSA_E_CAPACITY, "hit arena overflow persisted");
+    }
+    size_t total = stats[CNT_ALN];
+    if ((rc = result_reserve(res, b.n_items, total))) return rc;
+    CU(cudaMemcpyAsync(res->n_aln, ws->n_aln_dev, (size_t)b.n_items * sizeof(int32_t), cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaMemcpyAsync(res->aln_off, ws->aln_off_dev, (size_t)b.n_items * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
+    if (total) CU(cudaMemcpyAsync(res->aln, ws->aln_dev, total * sizeof(hsa_aln1_t), cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+    res->n_items = b.n_items; res->n_aln_total = total;
+    res->occ_lookups = stats[CNT_LOOKUPS]; res->n_strict = stats[CNT_STRICT];
+    res->pops = stats[CNT_POPS]; res->steps = stats[CNT_STEPS];
+    res->kernel_ms = ms_total; res->kernel_launches = launches;
+    ws->last_launches = launches;
+    return HSA_OK;
+}
+
+static int upload_reads(hsa_workspace *ws, const uint8_t *codes, const uint64_t *off, const uint32_t *len, size_t n,
+                        size_t *codes_bytes_out, uint32_t *max_len_out)
+{
+    const hsa_index *ix = ws->idx;
+    size_t bytes = 0; uint32_t ml = 0;
+    for (size_t i = 0; i < n; ++i) {
+        size_t e = off[i] + len[i];
+        if (e > bytes) bytes = e;
+        if (len[i] > ml) ml = len[i];
+        if (len[i] == 0) return fail(HSA_E_ARG, "empty read (len == 0)");
+    }
+    int rc;
+    if ((rc = ensure(ws->codes_dev, ws->codes_cap, bytes + 16))) return rc;
+    if (n + 1 > ws->reads_cap || !ws->off_dev) {
+        cudaFree(ws->off_dev); cudaFree(ws->len_dev); ws->off_dev = nullptr; ws->len_dev = nullptr;
+        size_t c = n + n / 8 + 16;
+        CU(cudaMalloc((void **)&ws->off_dev, c * sizeof(uint64_t)));
+        CU(cudaMalloc((void **)&ws->len_dev, c * sizeof(uint32_t)));
+        ws->reads_cap = c;
+    }
+    CU(cudaMemcpyAsync(ws->codes_dev, codes, bytes, cudaMemcpyHostToDevice, ix->stream));
+    CU(cudaMemcpyAsync(ws->off_dev, off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->stream));
+    CU(cudaMemcpyAsync(ws->len_dev, len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+    *codes_bytes_out = bytes; *max_len_out = ml;
+    return HSA_OK;
+}
+
+static int upload_opts(hsa_workspace *ws, const std::vector<hsa_gap_opt_t> &opts, uint32_t max_len, uint32_t *n_buckets,
+                       const std::vector<uint16_t> *len2opt)
+{
+    const hsa_index *ix = ws->idx;
+    int rc;
+    std::vector<DevOpt> d(opts.size());
+    *n_buckets = 1;
+    for (size_t i = 0; i < opts.size(); ++i) {
+        if ((rc = check_opt(opts[i], max_len, n_buckets))) return rc;
+        to_devopt(opts[i], d[i]);
+    }
+    if ((rc = ensure(ws->opts_dev, ws->opts_cap, d.size()))) return rc;
+    CU(cudaMemcpyAsync(ws->opts_dev, d.data(), d.size() * sizeof(DevOpt), cudaMemcpyHostToDevice, ix->stream));
+    if (len2opt) {
+        if ((rc = ensure(ws->len2opt_dev, ws->len2opt_cap, len2opt->size()))) return rc;
+        CU(cudaMemcpyAsync(ws->len2opt_dev, len2opt->data(), len2opt->size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ix->stream));
+    }
+    CU(cudaStreamSynchronize(ix->stream));          // d / len2opt are stack-local
+    return HSA_OK;
+}
+
+// per-read option resolution of bwa_cal_sa_reg_gap for one caller opt (bwtaln.c:260-261, 273-276, 330-332)
+static int resolve_whole_opts(const hsa_gap_opt_t *opt, int keep_gape, const std::vector<uint32_t> &lens, uint32_t max_len,
+                              std::vector<hsa_gap_opt_t> &opts, std::vector<uint16_t> &len2opt, int32_t *filter_max_n)
+{
+    len2opt.assign((size_t)max_len + 1, 0);
+    opts.clear();
+    for (uint32_t L : lens) {
+        hsa_gap_opt_t o = *opt;
+        if (!keep_gape) o.mode &= ~HSA_MODE_GAPE;
+        if (opt->fnr > 0.0) o.max_diff = hsa_cal_maxdiff((int)L, 0.02, opt->fnr);
+        o.seed_len = opt->seed_len < (int)L ? opt->seed_len : 0x7fffffff;
+        size_t j = 0;                                   // lengths that resolve to the same options share a slot
+        for (; j < opts.size(); ++j) if (opts[j].max_diff == o.max_diff && opts[j].seed_len == o.seed_len) break;
+        if (j == opts.size()) {
+            if (opts.size() >= 1024) return fail(HSA_E_ARG, "too many distinct resolved option sets");
+            opts.push_back(o);
+        }
+        len2opt[L] = (uint16_t)j;
+    }
+    *filter_max_n = opt->fnr > 0.0 ? hsa_cal_maxdiff((int)max_len, 0.02, opt->fnr) : opt->max_diff;
+    if (opts.empty()) { opts.push_back(*opt); if (opts[0].max_diff < 0) opts[0].max_diff = 0; }
+    return HSA_OK;
+}
+
+extern "C" int hsa_match_gap_batch(const hsa_index_t *ix, const uint8_t *codes, size_t codes_bytes,
+                                   const hsa_task_t *tasks, size_t n_tasks,
+                                   const hsa_gap_opt_t *opts, size_t n_opts, hsa_result_t *res)
+{
+    if (!ix || !res || (n_tasks && (!codes || !tasks || !opts))) return fail(HSA_E_ARG, "null argument");
+    if (n_tasks > 0xFFFFFFF0ull) return fail(HSA_E_ARG, "too many tasks");
+    hsa_workspace *ws; int rc;
+    if ((rc = get_ws(ix, &ws))) return rc;
+    CU(cudaSetDevice(ix->device));
+    uint32_t max_len = 0;
+    for (size_t i = 0; i < n_tasks; ++i) {
+        const hsa_task_t &t = tasks[i];
+        if (t.opt_idx >= n_opts) return fail(HSA_E_ARG, "task.opt_idx out of range");
+        if (t.read_off + t.read_len > codes_bytes || t.sub_off + t.len > t.read_len || t.wsrc_off + t.len > t.read_len)
+            return fail(HSA_E_ARG, "task window outside its read / codes buffer");
+        if (t.seed_mode > HSA_SEED_ALIAS || t.strand > 1) return fail(HSA_E_ARG, "bad task.seed_mode / strand");
+        if (t.len == 0) return fail(HSA_E_ARG, "empty task (len == 0)");
+        if (t.seed_mode == HSA_SEED_TAIL && (opts[t.opt_idx].seed_len <= 0 || (uint32_t)opts[t.opt_idx].seed_len >= t.len))
+            return fail(HSA_E_ARG, "HSA_SEED_TAIL needs 0 < opt.seed_len < task.len (bwtaln.c:344)");
+        max_len = std::max(max_len, std::max(t.len, t.read_len));
+    }
+    if (n_tasks == 0) { res->n_items = 0; res->n_aln_total = 0; return HSA_OK; }
+    std::vector<hsa_gap_opt_t> ov(opts, opts + n_opts);
+    Batch b;
+    if ((rc = upload_opts(ws, ov, max_len, &b.n_buckets, nullptr))) return rc;
+    if ((rc = ensure(ws->codes_dev, ws->codes_cap, codes_bytes + 16))) return rc;
+    if ((rc = ensure(ws->tasks_dev, ws->tasks_cap, n_tasks))) return rc;
+    CU(cudaMemcpyAsync(ws->codes_dev, codes, codes_bytes, cudaMemcpyHostToDevice, ix->stream));
+    CU(cudaMemcpyAsync(ws->tasks_dev, tasks, n_tasks * sizeof(Task), cudaMemcpyHostToDevice, ix->stream));
+    b.kind = KIND_TASKS; b.n_groups = (uint32_t)n_tasks; b.n_items = (uint32_t)n_tasks; b.max_len = max_len;
+    b.n_opts = (uint32_t)n_opts; b.codes = ws->codes_dev; b.tasks = ws->tasks_dev;
+    return run_and_fetch(ws, b, res);
+}
+
+static int reads_common(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len, size_t n,
+                        hsa_workspace **ws, uint32_t *max_len)
+{
+    if (!ix || (n && (!codes || !off || !len))) return fail(HSA_E_ARG, "null argument");
+    if (n > 0x2AAAAAA0ull) return fail(HSA_E_ARG, "too many reads in one batch");
+    int rc;
+    if ((rc = get_ws(ix, ws))) return rc;
+    CU(cudaSetDevice(ix->device));
+    size_t bytes;
+    return upload_reads(*ws, codes, off, len, n, &bytes, max_len);
+}
+
+extern "C" int hsa_whole_reads(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                               size_t n_reads, const hsa_gap_opt_t *opt, int keep_gape, hsa_result_t *res)
+{
+    if (!res || !opt) return fail(HSA_E_ARG, "null argument");
+    if (n_reads == 0) { res->n_items = 0; res->n_aln_total = 0; return HSA_OK; }
+    hsa_workspace *ws; uint32_t max_len; int rc;
+    if ((rc = reads_common(ix, codes, off, len, n_reads, &ws, &max_len))) return rc;
+    std::vector<uint8_t> seen((size_t)max_len + 1, 0);
+    for (size_t i = 0; i < n_reads; ++i) seen[len[i]] = 1;
+    std::vector<uint32_t> lens;
+    for (uint32_t L = 0; L <= max_len; ++L) if (seen[L]) lens.push_back(L);
+    std::vector<hsa_gap_opt_t> opts; std::vector<uint16_t> l2o;
+    Batch b;
+    if ((rc = resolve_whole_opts(opt, keep_gape, lens, max_len, opts, l2o, &b.filter_max_n))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b.n_buckets, &l2o))) return rc;
+    b.kind = KIND_WHOLE; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads; b.max_len = max_len;
+    b.n_opts = (uint32_t)opts.size(); b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
+    return run_and_fetch(ws, b, res);
+}
+
+extern "C" int hsa_splice_seeds(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                                size_t n_reads, const hsa_gap_opt_t *opt, hsa_result_t *res)
+{
+    if (!res || !opt) return fail(HSA_E_ARG, "null argument");
+    if (n_reads == 0) { res->n_items = 0; res->n_aln_total = 0; return HSA_OK; }
+    hsa_workspace *ws; uint32_t max_len; int rc;
+    if ((rc = reads_common(ix, codes, off, len, n_reads, &ws, &max_len))) return rc;
+    hsa_gap_opt_t so = *opt;                             // bwtgap.c:769-774
+    so.mode &= ~HSA_MODE_GAPE; so.max_gapo = 0; so.max_gape = 0; so.max_diff = opt->max_seed_diff;
+    std::vector<hsa_gap_opt_t> opts(1, so);
+    Batch b;
+    if ((rc = upload_opts(ws, opts, max_len, &b.n_buckets, nullptr))) return rc;
+    b.kind = KIND_SEEDS; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads * 6; b.max_len = max_len;
+    b.n_opts = 1; b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
+    return run_and_fetch(ws, b, res);
+}
+
+extern "C" int hsa_cal_width_batch(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off,
+                                   const uint32_t *len, size_t n, int type, hsa_width_t *width_out, int *bid_out)
+{
+    if (type != 1) return fail(HSA_E_ARG, "only bwt_cal_width type 1 (forward search on rev_bwt) is on the GPU path");
+    if (!width_out || !bid_out) return fail(HSA_E_ARG, "null argument");
+    if (n == 0) return HSA_OK;
+    hsa_workspace *ws; uint32_t max_len; int rc;
+    if ((rc = reads_common(ix, codes, off, len, n, &ws, &max_len))) return rc;
+    size_t total = 0;
+    for (size_t i = 0; i < n; ++i) total = std::max(total, (size_t)off[i] + i + len[i] + 1);
+    hsa_gap_opt_t o; hsa_gap_opt_default(&o); o.max_diff = 0;
+    std::vector<hsa_gap_opt_t> opts(1, o);
+    Batch b;
+    if ((rc = upload_opts(ws, opts, max_len, &b.n_buckets, nullptr))) return rc;
+    if ((rc = ensure(ws->width_out_dev, ws->width_out_cap, total))) return rc;
+    cudaFree(ws->bid_dev); ws->bid_dev = nullptr;
+    CU(cudaMalloc((void **)&ws->bid_dev, n * sizeof(int32_t)));
+    if ((rc = ensure(ws->n_aln_dev, ws->items_cap, n + 1))) return rc;
+    if ((rc = ensure(ws->aln_off_dev, ws->items2_cap, n + 1))) return rc;
+    if ((rc = ensure(ws->aln_dev, ws->aln_cap, 1024))) return rc;
+    b.kind = KIND_WIDTH; b.n_groups = (uint32_t)n; b.n_items = (uint32_t)n; b.max_len = max_len; b.n_opts = 1;
+    b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
+    b.n_aln = ws->n_aln_dev; b.aln_off = ws->aln_off_dev; b.aln = ws->aln_dev; b.aln_cap = ws->aln_cap / 9;
+    b.width_out = ws->width_out_dev; b.bid_out = ws->bid_dev;
+    uint64_t stats[CNT_N]; float ms;
+    if ((rc = run_batch(ws, b, ix->stream, true, stats, &ms))) return rc;
+    CU(cudaMemcpyAsync(width_out, ws->width_out_dev, total * sizeof(hsa_width_t), cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaMemcpyAsync(bid_out, ws->bid_dev, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+    return HSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- device-resident
+extern "C" int hsa_whole_reads_device(const hsa_index_t *ix, hsa_workspace_t *ws, const uint8_t *codes_dev,
+                                      const uint64_t *off_dev, const uint32_t *len_dev, size_t n_reads,
+                                      const uint32_t *lens_present, size_t n_lens_present,
+                                      const hsa_gap_opt_t *opt, int keep_gape, int32_t *n_aln_dev, uint64_t *aln_off_dev,
+                                      hsa_aln1_t *aln_dev, size_t aln_capacity, uint64_t *stats_dev, void *stream)
+{
+    if (!ix || !ws || ws->idx != ix || !opt || !lens_present || !n_lens_present) return fail(HSA_E_ARG, "bad argument");
+    if (n_reads == 0) return HSA_OK;
+    if (n_reads > 0xFFFFFFF0ull) return fail(HSA_E_ARG, "too many reads in one batch");
+    CU(cudaSetDevice(ix->device));
+    int rc;
+    std::vector<uint32_t> lens(lens_present, lens_present + n_lens_present);
+    uint32_t max_len = *std::max_element(lens.begin(), lens.end());
+    std::vector<hsa_gap_opt_t> opts; std::vector<uint16_t> l2o;
+    Batch b;
+    if ((rc = resolve_whole_opts(opt, keep_gape, lens, max_len, opts, l2o, &b.filter_max_n))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b.n_buckets, &l2o))) return rc;
+    b.kind = KIND_WHOLE; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads; b.max_len = max_len;
+    b.n_opts = (uint32_t)opts.size(); b.codes = codes_dev; b.read_off = off_dev; b.read_len = len_dev;
+    b.n_aln = n_aln_dev; b.aln_off = aln_off_dev; b.aln = reinterpret_cast<uint32_t *>(aln_dev); b.aln_cap = aln_capacity;
+    uint64_t stats[CNT_N]; float ms = 0;
+    cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
+    if ((rc = run_batch(ws, b, s, false, stats, &ms))) return rc;
+    if (stats_dev)
+        CU(cudaMemcpyAsync(stats_dev, ws->counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+    return HSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- roofline probe
+extern "C" int hsa_random_sector_probe(int device, size_t footprint_bytes, int iters, double *gbs_out)
+{
+    if (!gbs_out || footprint_bytes < 4096 || iters < 1) return fail(HSA_E_ARG, "bad argument");
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    uint4 *buf = nullptr; unsigned long long *sink = nullptr;
+    uint64_t n_sectors = footprint_bytes / 32;
+    CU(cudaMalloc((void **)&buf, n_sectors * 32));
+    CU(cudaMalloc((void **)&sink, 8));
+    CU(cudaMemset(buf, 0x5A, n_sectors * 32));
+    CU(cudaMemset(sink, 0, 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int CH = 4, block = 256;
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_kernel<CH>, block, 0));
+    int grid = sms * occ;
+    probe_kernel<CH><<<grid, block>>>(buf, n_sectors, 8, sink);          // warm-up (also pulls an L2-sized set in)
+    CU(cudaGetLastError());
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CU(cudaEventRecord(e0));
+        probe_kernel<CH><<<grid, block>>>(buf, n_sectors, iters, sink);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double bytes = (double)grid * block * CH * (double)iters * 32.0;
+        best = std::max(best, bytes / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf); cudaFree(sink);
+    *gbs_out = best;
+    return HSA_OK;
+}

@@ -180,3 +180,27 @@ def read_aln_dump(path: str) -> tuple[np.ndarray, np.ndarray]:
     assert p == raw.shape[0]
     alns = np.concatenate(rows) if rows else np.zeros((0, ALN_WORDS), dtype=np.uint32)
     return n_aln, alns
+
+
+def make_repeat_genome(length: int, seed: int, n_dups: int = 40, dup_len: int = 300, tandem: int = 12) -> np.ndarray:
+    """A random genome with dispersed near-identical duplications and tandem repeats, so that SA intervals
+    with many occurrences exist (exercises best_cnt / max_top2 / the (k,l) dedupe of bwtgap.c:201-213),
+    which an i.i.d. genome almost never does."""
+    g = make_genome(length, seed)
+    rng = np.random.default_rng(seed + 1000)
+    for _ in range(n_dups):
+        src = int(rng.integers(0, length - dup_len))
+        seg = g[src:src + dup_len].copy()
+        for _copy in range(int(rng.integers(1, 5))):
+            dst = int(rng.integers(0, length - dup_len))
+            s2 = seg.copy()
+            m = rng.random(dup_len) < 0.01
+            s2[m] = (s2[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.uint8)) & 3
+            g[dst:dst + dup_len] = s2
+    for _ in range(tandem):
+        unit = rng.integers(0, 4, size=int(rng.integers(1, 7)), dtype=np.uint8)
+        reps = int(rng.integers(20, 80))
+        t = np.tile(unit, reps)
+        dst = int(rng.integers(0, length - t.shape[0]))
+        g[dst:dst + t.shape[0]] = t
+    return g

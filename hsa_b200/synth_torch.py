@@ -1,0 +1,48 @@
+"""Device-side (torch) generators for the large synthetic workloads of BASELINE.json: a 46 Mb / 3.1 Gb
+i.i.d. genome and tens of millions of simulated reads are produced directly in HBM.  Plumbing only."""
+from __future__ import annotations
+
+import torch
+
+
+def make_genome(length: int, seed: int, device) -> torch.Tensor:
+    if length % 16 == 0:
+        raise ValueError("genome length % 16 must be != 0 (reference builder bug, 2BWT-Builder.c:189-208)")
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return torch.randint(0, 4, (length,), dtype=torch.uint8, device=device, generator=g)
+
+
+def simulate_reads(genome: torch.Tensor, n: int, length: int, seed: int, sub_rate: float = 0.01,
+                   indel_frac: float = 0.05, n_rate: float = 0.001, indel_margin: int = 8,
+                   chunk: int = 2_000_000) -> torch.Tensor:
+    """uint8 [n, length] reads (codes 0..3, N = 4): uniform start, 50 % reverse-complemented, per-base
+    substitutions, one 1-bp indel in `indel_frac` of the reads >= indel_margin from the ends, n_rate N."""
+    dev = genome.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    G = genome.shape[0]
+    out = torch.empty((n, length), dtype=torch.uint8, device=dev)
+    j = torch.arange(length, device=dev)[None, :]
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        start = torch.randint(0, G - length - 2, (m, 1), device=dev, generator=gen)
+        kind = torch.rand((m, 1), device=dev, generator=gen)
+        has_indel = kind < indel_frac
+        is_del = has_indel & (kind < indel_frac * 0.5)
+        is_ins = has_indel & ~is_del
+        pos = torch.randint(indel_margin, length - indel_margin, (m, 1), device=dev, generator=gen)
+        shift = torch.where(is_del & (j >= pos), 1, 0) - torch.where(is_ins & (j > pos), 1, 0)
+        r = genome[start + j + shift]
+        ins_base = torch.randint(0, 4, (m, 1), dtype=torch.uint8, device=dev, generator=gen)
+        r = torch.where(is_ins & (j == pos), ins_base, r)
+        sub = torch.rand((m, length), device=dev, generator=gen) < sub_rate
+        sh = torch.randint(1, 4, (m, length), dtype=torch.uint8, device=dev, generator=gen)
+        r = torch.where(sub, (r + sh) & 3, r)
+        rc = torch.rand((m, 1), device=dev, generator=gen) < 0.5
+        r = torch.where(rc, 3 - torch.flip(r, dims=[1]), r)
+        if n_rate > 0:
+            isn = torch.rand((m, length), device=dev, generator=gen) < n_rate
+            r = torch.where(isn, torch.full_like(r, 4), r)
+        out[lo:lo + m] = r
+    return out

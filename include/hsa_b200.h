@@ -8,7 +8,7 @@
  * to a CPU implementation: without a CUDA device every compute entry point fails with HSA_E_CUDA.
  *
  * Struct mirrors are byte-identical to the reference's (x86-64, gcc bit-field layout):
- *   hsa_gap_opt_t == gap_opt_t    bwtaln.h:133-143   (68 bytes)
+ *   hsa_gap_opt_t == gap_opt_t    bwtaln.h:133-143   (64 bytes)
  *   hsa_aln1_t    == bwt_aln1_t   bwtaln.h:41-50     (36 bytes)
  *   hsa_width_t   == bwt_width_t  bwtaln.h:35-38     ( 8 bytes)
  */
@@ -127,16 +127,20 @@ typedef struct hsa_task_t {
     uint32_t reserved;
 } hsa_task_t;
 
-typedef struct hsa_result_t {     /* flat result of a batch; free with hsa_result_free                 */
-    size_t      n_items;          /* tasks (hsa_match_gap_batch / seeds) or reads (whole)               */
+typedef struct hsa_result_t {     /* flat result of a batch.  ZERO-INITIALISE before first use; the library
+                                     (re)allocates the three arrays as pinned host memory and re-uses them
+                                     across calls when large enough; release with hsa_result_free          */
+    size_t      n_items;          /* tasks (hsa_match_gap_batch), reads (whole) or 6 x reads (seeds)     */
     int32_t    *n_aln;            /* [n_items]                                                          */
     uint64_t   *aln_off;          /* [n_items] first hit of the item in aln[]                           */
     hsa_aln1_t *aln;              /* all hits, per item in discovery order (== reference order)         */
     size_t      n_aln_total;
     uint64_t    occ_lookups;      /* BWTAllOccValue + BWTOccValue calls the reference would have issued */
     uint64_t    n_strict;         /* items that had to be re-run with the large-capacity kernel         */
+    uint64_t    pops, steps;      /* diagnostics: stack pops and worker iterations                      */
     float       kernel_ms;        /* device time of the search kernel(s), CUDA events on the stream     */
     uint32_t    kernel_launches;
+    size_t      cap_items, cap_aln; /* library-managed capacities                                       */
 } hsa_result_t;
 
 /* One reference bwt_cal_width (+ seed width) + bwt_match_gap call per task.  Host buffers in, host
@@ -163,14 +167,17 @@ void hsa_result_free(hsa_result_t *res);
 
 /* ---- device-resident variants for pipelines that keep reads / results in HBM (bench `value`) ------
  * All pointers are device pointers on the index's device; `stream` is a cudaStream_t passed as void*.
- * Results stay on the device: n_aln_dev[n_reads], aln_off_dev[n_reads], aln_dev[aln_capacity] and a
- * 4 x uint64 stats block {hits, lookups, strict, overflow}.  No synchronisation is performed. */
+ * Results stay on the device: n_aln_dev[n_reads], aln_off_dev[n_reads], aln_dev[aln_capacity] and an
+ * 8 x uint64 stats block {work, hits, lookups, need_strict, bad, pops, steps, -}.  Nothing is synchronised
+ * and nothing is re-run: the caller checks stats[1] <= aln_capacity and stats[3] == stats[4] == 0
+ * (reads that overflowed the fast kernel's stack must be re-submitted through hsa_whole_reads). */
 typedef struct hsa_workspace hsa_workspace_t;
 int  hsa_workspace_create(const hsa_index_t *idx, size_t max_reads, uint32_t max_len, size_t aln_capacity,
                           hsa_workspace_t **out);
 void hsa_workspace_free(hsa_workspace_t *ws);
 int  hsa_whole_reads_device(const hsa_index_t *idx, hsa_workspace_t *ws, const uint8_t *codes_dev,
-                            const uint64_t *off_dev, const uint32_t *len_dev, size_t n_reads, uint32_t max_len,
+                            const uint64_t *off_dev, const uint32_t *len_dev, size_t n_reads,
+                            const uint32_t *lens_present, size_t n_lens_present,   /* host: distinct read lengths */
                             const hsa_gap_opt_t *opt, int keep_gape, int32_t *n_aln_dev, uint64_t *aln_off_dev,
                             hsa_aln1_t *aln_dev, size_t aln_capacity, uint64_t *stats_dev, void *stream);
 /* number of kernels the last call on this workspace launched (for bench's gpu_launches) */

@@ -128,10 +128,30 @@ static void put_aln(FILE *f, int n_aln, const bwt_aln1_t *aln)
 
 static Idx2BWT *load_index(const char *prefix)
 {
-    char *str = (char*)calloc(strlen(prefix) + 10, 1);
+    char *str = (char*)calloc(strlen(prefix) + 32, 1);
     Idx2BWT *bi;
+    FILE *t;
+    strcpy(str, prefix); strcat(str, ".index.sa");
+    t = fopen(str, "rb");
     strcpy(str, prefix); strcat(str, ".index");      /* bwtaln.c:463-469 */
-    bi = BWTLoad2BWT(str, ".sa");
+    if (t) {
+        fclose(t);
+        bi = BWTLoad2BWT(str, ".sa");
+    } else {
+        /* search arrays only (.bwt/.fmv/.rev.bwt/.rev.fmv), e.g. an index written by the product's own
+         * builder: the same BWTLoad calls BWTLoad2BWT makes (2BWT-Interface.c:51-52), no SA / packed DNA.
+         * Enough for occ / width / percall / whole / seeds, which never touch hsp or the SA. */
+        char a[1100], b[1100];
+        MMPool *mmPool;
+        bi = (Idx2BWT*)calloc(1, sizeof(Idx2BWT));
+        MMMasterInitialize(3, 0, FALSE, NULL);
+        mmPool = MMPoolCreate(2097152);
+        snprintf(a, sizeof(a), "%s.bwt", str); snprintf(b, sizeof(b), "%s.fmv", str);
+        bi->bwt = BWTLoad(mmPool, a, b, NULL, NULL, NULL, NULL);
+        snprintf(a, sizeof(a), "%s.rev.bwt", str); snprintf(b, sizeof(b), "%s.rev.fmv", str);
+        bi->rev_bwt = BWTLoad(mmPool, a, b, NULL, NULL, NULL, NULL);
+        bi->hsp = NULL; bi->mmPool = mmPool;
+    }
     free(str);
     return bi;
 }

@@ -1,0 +1,132 @@
+// hsa_emu.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles hsa_b200/csrc/hsa_core.cuh (the exact source the CUDA kernels are built from) with g++ and
+// runs the worker state machine serially on the host, so the CPU test-suite (`-m "not gpu"`) can check
+// the device algorithm against the oracle in a container without a GPU.  It is NOT a fallback: nothing
+// in hsa_b200/ loads this library, and the product's C ABI fails loudly without CUDA.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../hsa_b200/csrc/hsa_core.cuh"
+#include "../../include/hsa_b200.h"
+
+using namespace hsa;
+
+struct EmuIndex {
+    std::vector<u32x4> blocks[2];
+    DevIndex ix;
+};
+
+static void repack(const hsa_bwt_view_t *v, std::vector<u32x4> &out, DevBwt &d)
+{
+    RefBwt r;
+    r.bwt_code = v->bwtCode; r.occ_value = v->occValue; r.occ_major = v->occValueMajor;
+    r.text_length = v->textLength; r.inverse_sa0 = v->inverseSa0;
+    uint32_t nb = v->textLength / 64 + 1;
+    out.resize((size_t)nb * 2);
+    for (uint32_t b = 0; b < nb; ++b) {
+        uint32_t occ[4];
+        occ4_ref_raw(r, b * 64u, occ);
+        u32x4 c, w;
+        c.x = occ[0]; c.y = occ[1]; c.z = occ[2]; c.w = occ[3];
+        w.x = v->bwtCode[4 * (size_t)b]; w.y = v->bwtCode[4 * (size_t)b + 1];
+        w.z = v->bwtCode[4 * (size_t)b + 2]; w.w = v->bwtCode[4 * (size_t)b + 3];
+        out[2 * (size_t)b] = c; out[2 * (size_t)b + 1] = w;
+    }
+    d.blocks = out.data(); d.n_blocks = nb; d.text_length = v->textLength; d.inverse_sa0 = v->inverseSa0;
+    for (int i = 0; i < 5; ++i) d.cum[i] = v->cumulativeFreq[i];
+}
+
+extern "C" {
+
+void *emu_index_new(const hsa_bwt_view_t *fwd, const hsa_bwt_view_t *rev)
+{
+    EmuIndex *e = new EmuIndex();
+    repack(fwd, e->blocks[0], e->ix.fwd);
+    repack(rev, e->blocks[1], e->ix.rev);
+    return e;
+}
+void emu_index_free(void *p) { delete (EmuIndex *)p; }
+
+void emu_occ(void *p, int which, int layout, const hsa_bwt_view_t *refview, const uint32_t *idx, size_t n, uint32_t *out4)
+{
+    EmuIndex *e = (EmuIndex *)p;
+    for (size_t i = 0; i < n; ++i) {
+        if (layout == 1) occ4_dev(which == 0 ? e->ix.fwd : e->ix.rev, idx[i], out4 + 4 * i);
+        else {
+            RefBwt r;
+            r.bwt_code = refview->bwtCode; r.occ_value = refview->occValue; r.occ_major = refview->occValueMajor;
+            r.text_length = refview->textLength; r.inverse_sa0 = refview->inverseSa0;
+            occ4_ref(r, idx[i], out4 + 4 * i);
+        }
+    }
+}
+
+static void to_devopt(const hsa_gap_opt_t &o, DevOpt &d)
+{
+    memset(&d, 0, sizeof(d));
+    d.s_mm = o.s_mm; d.s_gapo = o.s_gapo; d.s_gape = o.s_gape; d.mode = o.mode;
+    d.indel_end_skip = o.indel_end_skip; d.max_del_occ = o.max_del_occ; d.max_entries = o.max_entries;
+    d.max_diff = o.max_diff; d.max_gapo = o.max_gapo; d.max_gape = o.max_gape;
+    d.max_seed_diff = o.max_seed_diff; d.seed_len = o.seed_len; d.max_top2 = o.max_top2;
+}
+
+// Run one batch through the worker.  kind: 0 tasks, 1 whole, 2 seeds, 3 width.
+// opts: already-resolved per-call options (tasks: indexed by task.opt_idx; whole: indexed through len2opt;
+// seeds: opts[0]).  Outputs: n_aln[n_items], aln_off[n_items], status[n_items], aln[aln_cap*9].
+// Returns the number of hits written; *lookups gets the reference-equivalent occ lookup count;
+// *n_strict the number of groups that ran out of capacity (arena_cap / hit_cap).
+long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tasks, const uint64_t *read_off,
+             const uint32_t *read_len, uint32_t n_groups, const hsa_gap_opt_t *opts, uint32_t n_opts,
+             const uint16_t *len2opt, uint32_t max_len, int32_t filter_max_n, uint32_t arena_cap,
+             uint32_t hit_cap, int32_t *n_aln, uint64_t *aln_off, uint8_t *status, uint32_t *aln, uint64_t aln_cap,
+             uint32_t *width_out, int32_t *bid_out, uint64_t *lookups, uint64_t *n_strict, uint64_t *pops)
+{
+    EmuIndex *e = (EmuIndex *)p;
+    std::vector<DevOpt> dopts(n_opts ? n_opts : 1);
+    uint32_t nb = 1;
+    for (uint32_t i = 0; i < n_opts; ++i) {
+        to_devopt(opts[i], dopts[i]);
+        uint32_t b = (uint32_t)((opts[i].max_diff + 1) * opts[i].s_mm + (opts[i].max_gapo + 1) * opts[i].s_gapo +
+                                (opts[i].max_gape + 1) * opts[i].s_gape + 1);
+        if (b > nb) nb = b;
+    }
+    if (nb > 128) return -1;
+    std::vector<u32x4> arena(arena_cap);
+    std::vector<uint16_t> links(arena_cap);
+    std::vector<u32x2> width(2 * (size_t)(max_len + 1));
+    std::vector<Hit> hits(hit_cap);
+    std::vector<uint16_t> heads(nb);
+    std::vector<uint32_t> strict(n_groups + 1);
+    unsigned long long counters[CNT_N];
+    memset(counters, 0, sizeof(counters));
+
+    Params P;
+    memset(&P, 0, sizeof(P));
+    P.ix = e->ix; P.codes = codes; P.kind = kind; P.n_groups = n_groups; P.group_list = nullptr;
+    P.tasks = (const Task *)tasks; P.read_off = read_off; P.read_len = read_len;
+    P.opts = dopts.data(); P.n_opts = n_opts; P.len2opt = len2opt; P.max_len = max_len; P.filter_max_n = filter_max_n;
+    P.arena = arena.data(); P.links = links.data(); P.arena_cap = arena_cap;
+    P.width = width.data(); P.width_stride = 2 * (max_len + 1);
+    P.hits = hits.data(); P.hit_cap = hit_cap; P.n_buckets = nb;
+    P.n_aln = n_aln; P.aln_off = aln_off; P.status = status; P.aln = aln; P.aln_cap = aln_cap;
+    P.counters = counters; P.strict_list = strict.data();
+    P.width_out = (u32x2 *)width_out; P.bid_out = bid_out;
+
+    Worker w(P, 0, heads.data(), 1, dopts.data());
+    uint32_t next = 0;
+    for (;;) {
+        if (w.idle()) {
+            if (next < n_groups) w.start_group(next++);
+            else break;
+            continue;
+        }
+        w.iterate<2>();
+    }
+    *lookups = w.lookups;
+    *n_strict = counters[CNT_STRICT] + counters[CNT_BAD];
+    *pops = w.pops;
+    return (long)counters[CNT_ALN];
+}
+
+} // extern "C"

@@ -1,0 +1,178 @@
+"""ctypes binding of tests/emu/libhsa_emu.so: the device algorithm (hsa_core.cuh) compiled for the host.
+
+TEST INFRASTRUCTURE ONLY -- lets the CPU suite check the CUDA worker's logic against the oracle without
+a GPU.  The product never loads it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import oracle_lib as ol
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+LIB = os.path.join(EMU_DIR, "libhsa_emu.so")
+CORE = os.path.join(ol.ROOT, "hsa_b200", "csrc", "hsa_core.cuh")
+
+
+class Task(C.Structure):  # == hsa_task_t
+    _fields_ = [("read_off", C.c_uint64), ("read_len", C.c_uint32), ("strand", C.c_uint32),
+                ("sub_off", C.c_uint32), ("len", C.c_uint32), ("wsrc_off", C.c_uint32),
+                ("seed_mode", C.c_uint32), ("opt_idx", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def build():
+    src = os.path.join(EMU_DIR, "hsa_emu.cpp")
+    newest = max(os.path.getmtime(src), os.path.getmtime(CORE))
+    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < newest:
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", LIB, src])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        L.emu_index_new.restype = C.c_void_p
+        L.emu_index_new.argtypes = [C.POINTER(ol.BwtView), C.POINTER(ol.BwtView)]
+        L.emu_index_free.argtypes = [C.c_void_p]
+        L.emu_occ.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ol.BwtView), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.emu_run.restype = C.c_long
+        L.emu_run.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                              C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                              C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        _lib = L
+    return _lib
+
+
+def resolve_read_opt(opt: ol.GapOpt, length: int, clear_gape: int = 1) -> ol.GapOpt:
+    """Per-read option resolution of bwa_cal_sa_reg_gap before any local_opt switch (bwtaln.c:260-261, 330-332)."""
+    o = ol.GapOpt.from_buffer_copy(bytes(opt))
+    if clear_gape:
+        o.mode &= ~1
+    if opt.fnr > 0:
+        o.max_diff = ol.lib().hsao_cal_maxdiff(length, 0.02, opt.fnr)
+    o.seed_len = opt.seed_len if opt.seed_len < length else 0x7FFFFFFF
+    return o
+
+
+def aln9_to_rows12(aln9: np.ndarray) -> np.ndarray:
+    """hsa_aln1_t words -> the 12-word dump layout of oracle/ref_harness.c."""
+    n = aln9.shape[0]
+    r = np.zeros((n, 12), dtype=np.uint32)
+    r[:, 0] = aln9[:, 0] & 0xFFFF
+    r[:, 1] = (aln9[:, 0] >> 16) & 0xFF
+    r[:, 2] = (aln9[:, 0] >> 24) & 0xFF
+    r[:, 3:7] = aln9[:, 1:5]
+    r[:, 7] = aln9[:, 5] & 0x3FFFFFFF
+    r[:, 8] = aln9[:, 5] >> 30
+    r[:, 9] = aln9[:, 6]
+    r[:, 10] = aln9[:, 7]
+    r[:, 11] = aln9[:, 8]
+    return r
+
+
+def gather_rows(n_aln: np.ndarray, aln_off: np.ndarray, aln9: np.ndarray) -> np.ndarray:
+    """Hits of all items in item order (the arena order is arbitrary on the GPU)."""
+    idx = [np.arange(int(o), int(o) + int(c)) for c, o in zip(n_aln.tolist(), aln_off.tolist()) if c]
+    if not idx:
+        return np.zeros((0, 12), dtype=np.uint32)
+    return aln9_to_rows12(aln9[np.concatenate(idx)])
+
+
+class Emu:
+    def __init__(self, index):
+        self.index = index
+        self.vf, self.vr = ol._view(index.fwd), ol._view(index.rev)
+        self.h = lib().emu_index_new(C.byref(self.vf), C.byref(self.vr))
+
+    def __del__(self):
+        try:
+            lib().emu_index_free(self.h)
+        except Exception:
+            pass
+
+    def occ(self, which: int, layout: int, idx: np.ndarray) -> np.ndarray:
+        out = np.zeros((idx.shape[0], 4), dtype=np.uint32)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        lib().emu_occ(self.h, which, layout, C.byref(self.vf if which == 0 else self.vr), idx.ctypes.data,
+                      idx.shape[0], out.ctypes.data)
+        return out
+
+    def run(self, kind, rs, opts, tasks=None, len2opt=None, filter_max_n=0, arena_cap=4096, hit_cap=32,
+            n_items=None, want_width=False):
+        codes = np.ascontiguousarray(rs.codes, dtype=np.uint8)
+        off = np.ascontiguousarray(rs.offsets[:-1], dtype=np.uint64)
+        lens = np.ascontiguousarray(rs.lens, dtype=np.uint32)
+        max_len = int(lens.max()) if rs.n else 0
+        n_groups = rs.n if tasks is None else len(tasks)
+        if n_items is None:
+            n_items = n_groups * (6 if kind == 2 else 1)
+        n_aln = np.zeros(n_items, dtype=np.int32)
+        aln_off = np.zeros(n_items, dtype=np.uint64)
+        status = np.full(n_items, 0xFF, dtype=np.uint8)
+        cap = max(n_items * 8, 1024)
+        aln = np.zeros((cap, 9), dtype=np.uint32)
+        optarr = (ol.GapOpt * len(opts))(*opts)
+        tarr = (Task * len(tasks))(*tasks) if tasks is not None else None
+        l2o = np.ascontiguousarray(len2opt, dtype=np.uint16) if len2opt is not None else None
+        wout = np.zeros((int(lens.sum()) + rs.n, 2), dtype=np.uint32) if want_width else None
+        bid = np.zeros(rs.n, dtype=np.int32) if want_width else None
+        lk, ns, pops = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        total = lib().emu_run(self.h, kind, codes.ctypes.data, C.cast(tarr, C.c_void_p) if tarr is not None else None,
+                              off.ctypes.data, lens.ctypes.data, n_groups, C.cast(optarr, C.c_void_p), len(opts),
+                              l2o.ctypes.data if l2o is not None else None, max_len, filter_max_n, arena_cap, hit_cap,
+                              n_aln.ctypes.data, aln_off.ctypes.data, status.ctypes.data, aln.ctypes.data, cap,
+                              wout.ctypes.data if want_width else None, bid.ctypes.data if want_width else None,
+                              C.byref(lk), C.byref(ns), C.byref(pops))
+        assert total >= 0
+        self.last_lookups, self.last_strict, self.last_pops = lk.value, ns.value, pops.value
+        if want_width:
+            return bid, wout
+        return n_aln, aln_off, status, aln[:total]
+
+    # convenience wrappers with the same semantics as Oracle.percall / whole / seeds
+    def percall(self, rs, opt, clear_gape=1, **kw):
+        lens = sorted(set(rs.lens.tolist()))
+        opts = [resolve_read_opt(opt, L, clear_gape) for L in lens]
+        oi = {L: i for i, L in enumerate(lens)}
+        off = rs.offsets
+        tasks = []
+        for r in range(rs.n):
+            L = int(rs.lens[r])
+            sm = 1 if L > opts[oi[L]].seed_len else 0
+            for s in (1, 0):
+                tasks.append(Task(int(off[r]), L, s, 0, L, 0, sm, oi[L], 0))
+        n_aln, aln_off, status, aln = self.run(0, rs, opts, tasks=tasks, **kw)
+        return n_aln, gather_rows(n_aln, aln_off, aln), status
+
+    def whole(self, rs, opt, clear_gape=1, **kw):
+        lens = sorted(set(rs.lens.tolist()))
+        opts = [resolve_read_opt(opt, L, clear_gape) for L in lens]
+        max_len = max(lens) if lens else 0
+        l2o = np.zeros(max_len + 1, dtype=np.uint16)
+        for i, L in enumerate(lens):
+            l2o[L] = i
+        fmax = ol.lib().hsao_cal_maxdiff(max_len, 0.02, opt.fnr) if opt.fnr > 0 else opt.max_diff
+        n_aln, aln_off, status, aln = self.run(1, rs, opts, len2opt=l2o, filter_max_n=fmax, **kw)
+        return n_aln, gather_rows(n_aln, aln_off, aln), status
+
+    def seeds(self, rs, opt, **kw):
+        so = ol.GapOpt.from_buffer_copy(bytes(opt))
+        so.mode &= ~1
+        so.max_gapo = 0
+        so.max_gape = 0
+        so.max_diff = opt.max_seed_diff
+        n_aln, aln_off, status, aln = self.run(2, rs, [so], **kw)
+        return n_aln, gather_rows(n_aln, aln_off, aln), status
+
+    def width(self, rs):
+        return self.run(3, rs, [ol.default_opt()], want_width=True)

@@ -1,0 +1,57 @@
+"""CPU: the CUDA worker's source (hsa_b200/csrc/hsa_core.cuh) compiled for the host, against the golden
+vectors and the oracle.  This checks the device ALGORITHM where no GPU exists; the GPU tests
+(test_gpu_parity.py) check the compiled kernels themselves through the C ABI."""
+import numpy as np
+import pytest
+
+import emu_lib as el
+import oracle_lib as ol
+
+
+@pytest.fixture(scope="module")
+def emu(golden_index):
+    return el.Emu(golden_index)
+
+
+def test_rank_both_layouts(golden, emu):
+    idx, occ = golden.arr["occ_idx"], golden.arr["occ"]
+    for which, cols in ((0, slice(0, 4)), (1, slice(4, 8))):
+        assert np.array_equal(emu.occ(which, 0, idx), occ[:, cols])     # reference layout
+        assert np.array_equal(emu.occ(which, 1, idx), occ[:, cols])     # re-packed device layout
+
+
+def test_width(golden, emu):
+    case = "ragged_nonstop"
+    rs = golden.reads(case).subset(0, 64)
+    bid, w = emu.width(rs)
+    off = rs.offsets
+    for r, (b, ww) in enumerate(golden.widths(case)):
+        assert bid[r] == b
+        assert np.array_equal(w[off[r] + r: off[r] + r + int(rs.lens[r]) + 1], ww)
+
+
+@pytest.mark.parametrize("mode", ["percall", "whole", "seeds"])
+@pytest.mark.parametrize("case", ["cfg1_75bp_n2o1", "cfg2_100bp_default", "cfg5_150bp_n5o2", "ragged_nonstop",
+                                  "ragged_loggap_gape", "short_entries", "exact_only", "noskip_gaps"])
+def test_search_matches_reference(golden, emu, case, mode):
+    rs = golden.reads(case)
+    opt = ol.default_opt(**golden.opt_kwargs(case))
+    n_aln, rows, status = getattr(emu, mode)(rs, opt, arena_cap=65535, hit_cap=4096)
+    exp_n, exp_rows = golden.expected(case, mode)
+    assert int((status != 0).sum()) == 0
+    assert np.array_equal(n_aln, exp_n)
+    assert np.array_equal(rows, exp_rows)
+    assert emu.last_lookups == golden.lookups(case, mode)
+
+
+def test_capacity_overflow_is_flagged_not_silent(golden, emu):
+    """With a tiny stack arena the worker must flag the read for the strict re-run, never emit hits for it."""
+    case = "cfg5_150bp_n5o2"
+    rs = golden.reads(case)
+    opt = ol.default_opt(**golden.opt_kwargs(case))
+    n_aln, rows, status = emu.whole(rs, opt, arena_cap=128, hit_cap=32)
+    exp_n, _ = golden.expected(case, "whole")
+    flagged = status == 1
+    assert flagged.any() and emu.last_strict == int(flagged.sum())
+    assert np.array_equal(n_aln[~flagged], exp_n[~flagged])
+    assert (n_aln[flagged] == 0).all()

@@ -1,0 +1,170 @@
+"""GPU (-m gpu): the compiled CUDA path, called through the C ABI (libhsa_b200.so via hsa_b200.api), against
+  * the committed golden vectors produced by the unmodified reference, and
+  * the oracle on fresh seeded inputs,
+bit for bit: n_aln, {n_mm,n_gapo,n_gape,k,l,rev_k,rev_l,strand,start,end,score} per hit, hit order, and
+the count of occ lookups the reference algorithm issues."""
+import os
+
+import numpy as np
+import pytest
+
+import emu_lib as el
+import oracle_lib as ol
+from hsa_b200 import api, index_build, synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["cfg1_75bp_n2o1", "cfg2_100bp_default", "cfg5_150bp_n5o2", "ragged_nonstop", "ragged_loggap_gape",
+         "short_entries", "exact_only", "noskip_gaps"]
+
+
+def to_api_opt(o: ol.GapOpt) -> api.GapOpt:
+    return api.GapOpt.from_buffer_copy(bytes(o))
+
+
+@pytest.fixture(scope="module")
+def dev_index(golden_index):
+    ix = api.Index.upload(golden_index, 0)
+    yield ix
+    ix.close()
+
+
+def percall_tasks(rs, opt):
+    """The task list equivalent to ref_harness.c's percall mode (both strands of every read)."""
+    lens = sorted(set(rs.lens.tolist()))
+    opts = [el.resolve_read_opt(opt, L, 1) for L in lens]
+    oi = {L: i for i, L in enumerate(lens)}
+    off = rs.offsets
+    t = np.zeros(rs.n * 2, dtype=api.TASK_DTYPE)
+    L = rs.lens.astype(np.uint32)
+    for s_i, s in enumerate((1, 0)):
+        v = t[s_i::2]
+        v["read_off"] = off[:-1]
+        v["read_len"] = L
+        v["strand"] = s
+        v["len"] = L
+        v["seed_mode"] = [1 if int(x) > opts[oi[int(x)]].seed_len else 0 for x in L]
+        v["opt_idx"] = [oi[int(x)] for x in L]
+    return t, [to_api_opt(o) for o in opts]
+
+
+def test_rank_both_layouts(golden, dev_index):
+    idx, occ = golden.arr["occ_idx"], golden.arr["occ"]
+    for which, cols in ((0, slice(0, 4)), (1, slice(4, 8))):
+        assert np.array_equal(dev_index.occ(which, idx, layout=0), occ[:, cols])
+        assert np.array_equal(dev_index.occ(which, idx, layout=1), occ[:, cols])
+
+
+def test_rank_exhaustive_small(golden_index, dev_index):
+    """Every index of a prefix and a suffix of the SA range, both layouts == oracle."""
+    n = golden_index.fwd.text_length
+    idx = np.concatenate([np.arange(0, 3000), np.arange(n - 3000, n + 2)]).astype(np.uint32)
+    o = ol.Oracle(golden_index)
+    for which in (0, 1):
+        exp, _ = o.occ(which, idx)
+        assert np.array_equal(dev_index.occ(which, idx, layout=1), exp)
+        assert np.array_equal(dev_index.occ(which, idx, layout=0), exp)
+
+
+def test_width(golden, dev_index):
+    case = "ragged_nonstop"
+    rs = golden.reads(case).subset(0, 64)
+    bid, w = dev_index.cal_width(rs.codes, rs.offsets[:-1], rs.lens)
+    off = rs.offsets
+    for r, (b, ww) in enumerate(golden.widths(case)):
+        assert bid[r] == b
+        assert np.array_equal(w[off[r] + r: off[r] + r + int(rs.lens[r]) + 1], ww)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_match_gap_tasks_vs_golden(golden, dev_index, case):
+    rs = golden.reads(case)
+    opt = ol.default_opt(**golden.opt_kwargs(case))
+    tasks, opts = percall_tasks(rs, opt)
+    res = dev_index.match_gap_batch(rs.codes, tasks, opts)
+    exp_n, exp_rows = golden.expected(case, "percall")
+    assert np.array_equal(res.n_aln, exp_n)
+    assert np.array_equal(el.aln9_to_rows12(res.ordered()), exp_rows)
+    assert res.occ_lookups == golden.lookups(case, "percall")
+    assert res.kernel_launches >= 1
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_whole_reads_vs_golden(golden, dev_index, case):
+    rs = golden.reads(case)
+    opt = to_api_opt(ol.default_opt(**golden.opt_kwargs(case)))
+    res = dev_index.whole_reads(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt)
+    exp_n, exp_rows = golden.expected(case, "whole")
+    assert np.array_equal(res.n_aln, exp_n)
+    assert np.array_equal(el.aln9_to_rows12(res.ordered()), exp_rows)
+    assert res.occ_lookups == golden.lookups(case, "whole")
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_splice_seeds_vs_golden(golden, dev_index, case):
+    rs = golden.reads(case)
+    opt = to_api_opt(ol.default_opt(**golden.opt_kwargs(case)))
+    res = dev_index.splice_seeds(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt)
+    exp_n, exp_rows = golden.expected(case, "seeds")
+    assert np.array_equal(res.n_aln, exp_n)
+    assert np.array_equal(el.aln9_to_rows12(res.ordered()), exp_rows)
+    assert res.occ_lookups == golden.lookups(case, "seeds")
+
+
+def test_strict_rerun_path(golden, golden_index, monkeypatch):
+    """A deliberately tiny fast-kernel arena forces the large-capacity re-run; results must not change."""
+    monkeypatch.setenv("HSA_B200_ARENA_CAP", "96")
+    ix = api.Index.upload(golden_index, 0)
+    try:
+        case = "cfg5_150bp_n5o2"
+        rs = golden.reads(case)
+        opt = to_api_opt(ol.default_opt(**golden.opt_kwargs(case)))
+        res = ix.whole_reads(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt)
+        exp_n, exp_rows = golden.expected(case, "whole")
+        assert res.n_strict > 0 and res.kernel_launches >= 2
+        assert np.array_equal(res.n_aln, exp_n)
+        assert np.array_equal(el.aln9_to_rows12(res.ordered()), exp_rows)
+        assert res.occ_lookups == golden.lookups(case, "whole")
+    finally:
+        ix.close()
+
+
+def test_empty_and_bad_inputs(dev_index):
+    opt = api.gap_init_opt()
+    res = dev_index.whole_reads(np.zeros(0, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32), opt)
+    assert res.n_aln.shape[0] == 0
+    with pytest.raises(api.HsaError):      # empty read
+        dev_index.whole_reads(np.zeros(4, np.uint8), np.zeros(1, np.uint64), np.zeros(1, np.uint32), opt)
+    with pytest.raises(api.HsaError):      # score range beyond the bucket table must be refused, not truncated
+        dev_index.whole_reads(np.zeros(40, np.uint8), np.zeros(1, np.uint64), np.full(1, 40, np.uint32),
+                              api.gap_init_opt(s_gapo=60, max_gapo=3))
+
+
+def test_medium_batch_vs_oracle_and_properties():
+    """A fresh 2 Mb genome, 60k reads (fills the whole grid): bit-exact against the oracle on a sample,
+    plus size-independent properties on everything: every hit interval is non-empty and inside the SA range,
+    rev interval has the same width, exact reads have a score-0 hit whose interval contains their origin."""
+    g = synth.make_genome(2000003, 31)
+    index = index_build.build_index(g, device="cuda")
+    ix = api.Index.upload(index, 0)
+    try:
+        rs = synth.simulate_reads(g, 60000, 100, 32)
+        opt = api.gap_init_opt()
+        res = ix.whole_reads(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt)
+        f = api.aln_fields(res.aln)
+        n = index.fwd.text_length
+        assert (f["k"] <= f["l"]).all() and (f["l"] <= n).all()
+        assert ((f["l"] - f["k"]) == (f["rev_l"] - f["rev_k"])).all()
+        assert (f["score"] == 3 * f["n_mm"].astype(np.int64) + 11 * f["n_gapo"] + 4 * f["n_gape"]).all()
+        # per read, scores are non-decreasing except for the top2 tail (discovery order)
+        sub = rs.subset(0, 4000)
+        n_ref, rows_ref = ol.Oracle(index).whole(sub, ol.default_opt())
+        assert np.array_equal(res.n_aln[:4000], n_ref)
+        idx = np.concatenate([np.arange(int(o), int(o) + int(c)) for o, c in zip(res.aln_off[:4000], res.n_aln[:4000]) if c])
+        assert np.array_equal(el.aln9_to_rows12(res.aln[idx]), rows_ref)
+        # idempotence: a second run gives identical per-read results
+        res2 = ix.whole_reads(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt)
+        assert np.array_equal(res.n_aln, res2.n_aln) and np.array_equal(res.ordered(), res2.ordered())
+        assert res.occ_lookups == res2.occ_lookups
+    finally:
+        ix.close()

@@ -1,0 +1,44 @@
+"""CPU: the oracle (oracle/hsa_oracle.c) against the golden vectors the unmodified reference produced."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+
+@pytest.fixture(scope="module")
+def oracle(golden_index):
+    return ol.Oracle(golden_index)
+
+
+def test_maxdiff_table(golden):
+    for L, v in golden.meta["maxdiff"].items():
+        assert ol.lib().hsao_cal_maxdiff(int(L), 0.02, 0.04) == v
+
+
+def test_rank_matches_reference(golden, oracle):
+    idx, occ = golden.arr["occ_idx"], golden.arr["occ"]
+    o4f, o1f = oracle.occ(0, idx)
+    o4r, o1r = oracle.occ(1, idx)
+    assert np.array_equal(o4f, occ[:, 0:4]) and np.array_equal(o4r, occ[:, 4:8])
+    assert np.array_equal(o1f, occ[:, 8:12]) and np.array_equal(o1r, occ[:, 12:16])
+
+
+@pytest.mark.parametrize("case", ["cfg1_75bp_n2o1", "cfg2_100bp_default", "ragged_nonstop"])
+def test_width_matches_reference(golden, oracle, case):
+    rs = golden.reads(case)
+    for r, (bid, w) in enumerate(golden.widths(case)):
+        b, ww = oracle.cal_width(rs.read(r))
+        assert b == bid and np.array_equal(ww, w)
+
+
+@pytest.mark.parametrize("mode", ["percall", "whole", "seeds"])
+@pytest.mark.parametrize("case", ["cfg1_75bp_n2o1", "cfg2_100bp_default", "cfg5_150bp_n5o2", "ragged_nonstop",
+                                  "ragged_loggap_gape", "short_entries", "exact_only", "noskip_gaps"])
+def test_search_matches_reference(golden, oracle, case, mode):
+    rs = golden.reads(case)
+    opt = ol.default_opt(**golden.opt_kwargs(case))
+    n_aln, rows = getattr(oracle, mode)(rs, opt)
+    exp_n, exp_rows = golden.expected(case, mode)
+    assert np.array_equal(n_aln, exp_n)
+    assert np.array_equal(rows, exp_rows)
+    assert oracle.last_lookups == golden.lookups(case, mode)
