@@ -56,21 +56,42 @@ __global__ void occ_kernel(DevBwt dev, RefBwt ref, int layout, const uint32_t *i
     for (int c = 0; c < 4; ++c) { occ4_out[4 * i + c] = occ[c]; occ1_out[4 * i + c] = occ[c]; }
 }
 
-// MINB = minimum resident 256-thread blocks per SM the register allocation must allow (2: <=128 regs,
-// 3: <=80, 4: <=64); the variant is picked at run time (HSA_B200_MINB) so occupancy can be tuned on the GPU.
-template <int MAX_POPS, int MINB>
-__global__ void __launch_bounds__(256, MINB) search_kernel(const __grid_constant__ Params P)
+// Width kernel of the split pipeline: one thread per work item, every thread of a warp walks reads of the
+// same shape, so the loop is divergence-free (bwt_cal_width is a strictly sequential chain per read).
+__global__ void __launch_bounds__(256) width_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     DevOpt *sopt = reinterpret_cast<DevOpt *>(smem);
-    uint16_t *heads = reinterpret_cast<uint16_t *>(smem + (size_t)P.n_opts * sizeof(DevOpt));
+    for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
+        reinterpret_cast<int *>(sopt)[i] = reinterpret_cast<const int *>(P.opts)[i];
+    __syncthreads();
+    const uint32_t n = P.n_groups_dev ? *P.n_groups_dev : P.n_groups;
+    unsigned long long lk = 0;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+        uint64_t l = 0;
+        width_item(P, sopt, w, l);
+        lk += l;
+    }
+    for (int o = 16; o > 0; o >>= 1) lk += __shfl_down_sync(0xffffffffu, lk, o);
+    if ((threadIdx.x & 31u) == 0 && lk) atomicAdd(&P.counters[CNT_LOOKUPS], lk);
+}
+
+// MINB = minimum resident 256-thread blocks per SM the register allocation must allow (2: <=128 regs,
+// 3: <=80, 4: <=64); the variant is picked at run time (HSA_B200_MINB) so occupancy can be tuned on the GPU.
+template <int MAX_POPS, int BLOCK, int MINB, typename LinkT, bool FUSED>
+__global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_constant__ Params P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    DevOpt *sopt = reinterpret_cast<DevOpt *>(smem);
+    LinkT *heads = reinterpret_cast<LinkT *>(smem + (size_t)P.n_opts * sizeof(DevOpt));
     for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
         reinterpret_cast<int *>(sopt)[i] = reinterpret_cast<const int *>(P.opts)[i];
     __syncthreads();
 
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
-    Worker w(P, slot, heads + threadIdx.x, blockDim.x, sopt);
+    const uint32_t n_work = P.n_groups_dev ? *P.n_groups_dev : P.n_groups;
+    Worker<LinkT, FUSED> w(P, slot, heads + threadIdx.x, blockDim.x, sopt);
 
     for (;;) {
         const bool need = w.idle();
@@ -79,11 +100,11 @@ __global__ void __launch_bounds__(256, MINB) search_kernel(const __grid_constant
             // warp-aggregated fetch from the atomic work queue
             unsigned long long base = 0;
             const int leader = __ffs(bal) - 1;
-            if ((int)lane == leader) base = atomicAdd(&P.counters[CNT_WORK], (unsigned long long)__popc(bal));
+            if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)__popc(bal));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (need) {
                 const unsigned long long idx = base + __popc(bal & ((1u << lane) - 1u));
-                if (idx < P.n_groups) w.start_group((uint32_t)idx);
+                if (idx < n_work) w.start_group((uint32_t)idx);
                 else w.retire();
             }
         }
@@ -92,16 +113,18 @@ __global__ void __launch_bounds__(256, MINB) search_kernel(const __grid_constant
     }
 
     // statistics: warp-reduce, one atomic per warp
-    unsigned long long lk = w.lookups, pp = w.pops, st = w.steps;
+    unsigned long long lk = w.lookups, pp = w.pops, st = w.steps, ex = w.extra;
     for (int o = 16; o > 0; o >>= 1) {
         lk += __shfl_down_sync(0xffffffffu, lk, o);
         pp += __shfl_down_sync(0xffffffffu, pp, o);
         st += __shfl_down_sync(0xffffffffu, st, o);
+        ex += __shfl_down_sync(0xffffffffu, ex, o);
     }
     if (lane == 0) {
         atomicAdd(&P.counters[CNT_LOOKUPS], lk);
         atomicAdd(&P.counters[CNT_POPS], pp);
         atomicAdd(&P.counters[CNT_STEPS], st);
+        atomicAdd(&P.counters[CNT_EXTRA], ex);
     }
 }
 
@@ -164,7 +187,8 @@ struct hsa_index {
 struct Scratch {                             // worker-private device memory for one launch configuration
     uint32_t grid = 0, block = 0, n_workers = 0;
     uint32_t arena_cap = 0, hit_cap = 0, max_len = 0;
-    u32x4 *arena = nullptr; uint16_t *links = nullptr; u32x2 *width = nullptr; Hit *hits = nullptr;
+    u32x4 *arena = nullptr; void *links = nullptr; u32x2 *width = nullptr; Hit *hits = nullptr;
+    bool wide = false;                       // 32-bit links (strict) instead of 16-bit
     void release()
     {
         cudaFree(arena); cudaFree(links); cudaFree(width); cudaFree(hits);
@@ -187,10 +211,13 @@ struct hsa_workspace {
     int32_t *n_aln_dev = nullptr; size_t items_cap = 0; uint64_t *aln_off_dev = nullptr; size_t items2_cap = 0;
     uint32_t *aln_dev = nullptr; size_t aln_cap = 0;
     u32x2 *width_out_dev = nullptr; size_t width_out_cap = 0; int32_t *bid_dev = nullptr;
+    u32x2 *item_width = nullptr; size_t item_width_cap = 0;     // split pipeline: per-item width_back / width_seed
+    uint32_t *next_list = nullptr; size_t next_list_cap = 0;      // reads that go on to the forward-strand pass
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t last_launches = 0;
     int blocks_per_sm = 0;
-    int minb = 3;
+    int minb = 2;
+    uint32_t block = 0;
 };
 
 template <typename T>
@@ -218,8 +245,8 @@ static int check_opt(const hsa_gap_opt_t &o, uint32_t max_len, uint32_t *n_bucke
 {
     if (o.s_mm < 0 || o.s_gapo < 0 || o.s_gape < 0) return fail(HSA_E_ARG, "negative scores are not supported");
     if (o.max_diff < 0) return fail(HSA_E_ARG, "max_diff < 0 after resolution (fnr <= 0 and max_diff unset?)");
-    if (o.max_diff > 61 || o.max_gapo > 30 || o.max_gape > 62 || o.max_gapo < 0 || o.max_gape < 0)
-        return fail(HSA_E_ARG, "max_diff/max_gapo/max_gape exceed the packed stack-entry fields (61/30/62)");
+    if (o.max_diff > 30 || o.max_gapo > 15 || o.max_gape > 31 || o.max_gapo < 0 || o.max_gape < 0)
+        return fail(HSA_E_ARG, "max_diff/max_gapo/max_gape exceed the packed stack-record fields (30/15/31)");
     if (max_len > 4095) return fail(HSA_E_ARG, "reads longer than 4095 bases are not supported");
     long nb = (long)(o.max_diff + 1) * o.s_mm + (long)(o.max_gapo + 1) * o.s_gapo + (long)(o.max_gape + 1) * o.s_gape + 1;
     if (nb > 128) return fail(HSA_E_ARG, "score range exceeds 128 buckets: (max_diff+1)*s_mm+(max_gapo+1)*s_gapo+(max_gape+1)*s_gape+1 > 128");
@@ -417,7 +444,7 @@ extern "C" int hsa_occ_batch(const hsa_index_t *ix, int which, int layout, const
 }
 
 // ---------------------------------------------------------------------------------------------- workspace
-static int scratch_alloc(Scratch &s, uint32_t grid, uint32_t block, uint32_t arena_cap, uint32_t hit_cap, uint32_t max_len)
+static int scratch_alloc(Scratch &s, uint32_t grid, uint32_t block, uint32_t arena_cap, uint32_t hit_cap, uint32_t max_len, bool wide)
 {
     uint32_t nw = grid * block;
     if (s.n_workers >= nw && s.arena_cap == arena_cap && s.hit_cap == hit_cap && s.max_len >= max_len) {
@@ -426,8 +453,9 @@ static int scratch_alloc(Scratch &s, uint32_t grid, uint32_t block, uint32_t are
     }
     s.release();
     CU(cudaMalloc((void **)&s.arena, (size_t)nw * arena_cap * sizeof(u32x4)));
-    CU(cudaMalloc((void **)&s.links, (size_t)nw * arena_cap * sizeof(uint16_t)));
-    CU(cudaMalloc((void **)&s.width, (size_t)nw * 2 * (max_len + 1) * sizeof(u32x2)));
+    CU(cudaMalloc((void **)&s.links, (size_t)nw * arena_cap * (wide ? 4 : 2)));
+    s.wide = wide;
+    if (wide) CU(cudaMalloc((void **)&s.width, (size_t)nw * 2 * (max_len + 1) * sizeof(u32x2)));   // fused flow only
     CU(cudaMalloc((void **)&s.hits, (size_t)nw * hit_cap * sizeof(Hit)));
     s.grid = grid; s.block = block; s.n_workers = nw; s.arena_cap = arena_cap; s.hit_cap = hit_cap; s.max_len = max_len;
     return HSA_OK;
@@ -441,7 +469,8 @@ extern "C" int hsa_workspace_create(const hsa_index_t *ix, size_t max_reads, uin
     CU(cudaSetDevice(ix->device));
     hsa_workspace *ws = new hsa_workspace();
     ws->idx = ix;
-    CU(cudaMalloc((void **)&ws->counters, CNT_N * sizeof(unsigned long long)));
+    // statistics block, then 8 work-queue cursors, then 8 pass-2 list counters
+    CU(cudaMalloc((void **)&ws->counters, (CNT_N + 16) * sizeof(unsigned long long)));
     CU(cudaEventCreate(&ws->ev0)); CU(cudaEventCreate(&ws->ev1));
     (void)max_len;
     *out = ws;
@@ -455,7 +484,7 @@ extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
     cudaFree(ws->counters); cudaFree(ws->strict_list); cudaFree(ws->opts_dev); cudaFree(ws->len2opt_dev);
     cudaFree(ws->status_dev); cudaFree(ws->codes_dev); cudaFree(ws->off_dev); cudaFree(ws->len_dev);
     cudaFree(ws->tasks_dev); cudaFree(ws->n_aln_dev); cudaFree(ws->aln_off_dev); cudaFree(ws->aln_dev);
-    cudaFree(ws->width_out_dev); cudaFree(ws->bid_dev);
+    cudaFree(ws->width_out_dev); cudaFree(ws->bid_dev); cudaFree(ws->item_width); cudaFree(ws->next_list);
     if (ws->ev0) cudaEventDestroy(ws->ev0);
     if (ws->ev1) cudaEventDestroy(ws->ev1);
     delete ws;
@@ -464,17 +493,26 @@ extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
 extern "C" uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws) { return ws ? ws->last_launches : 0; }
 
 // ---------------------------------------------------------------------------------------------- launch
-static const void *search_fn(int minb)
+// launch variants: (threads per block, min blocks per SM) -> register cap 65536 / (block * minb)
+static const void *search_fn(int block, int minb, bool wide)
 {
+    if (wide) return (const void *)search_kernel<2, 256, 1, uint32_t, true>;  // large-capacity (strict), fused flow
+    if (block == 128) {
+        switch (minb) {
+        case 4: return (const void *)search_kernel<2, 128, 4, uint16_t, false>;
+        case 6: return (const void *)search_kernel<2, 128, 6, uint16_t, false>;
+        default: return (const void *)search_kernel<2, 128, 5, uint16_t, false>;
+        }
+    }
     switch (minb) {
-    case 2: return (const void *)search_kernel<2, 2>;
-    case 4: return (const void *)search_kernel<2, 4>;
-    default: return (const void *)search_kernel<2, 3>;
+    case 3: return (const void *)search_kernel<2, 256, 3, uint16_t, false>;
+    case 4: return (const void *)search_kernel<2, 256, 4, uint16_t, false>;
+    default: return (const void *)search_kernel<2, 256, 2, uint16_t, false>;
     }
 }
 
 struct Batch {                      // everything one launch needs, device pointers
-    uint32_t kind = 0, n_groups = 0, n_items = 0, max_len = 0, n_opts = 0, n_buckets = 1;
+    uint32_t kind = 0, n_groups = 0, n_items = 0, max_len = 0, n_opts = 0, n_buckets = 1, max_seed_len = 0;
     int32_t filter_max_n = 0;
     const uint8_t *codes = nullptr; const Task *tasks = nullptr;
     const uint64_t *read_off = nullptr; const uint32_t *read_len = nullptr;
@@ -482,23 +520,26 @@ struct Batch {                      // everything one launch needs, device point
     u32x2 *width_out = nullptr; int32_t *bid_out = nullptr;
 };
 
-static int launch_search(hsa_workspace *ws, const Batch &b, Scratch &sc, const uint32_t *group_list, uint32_t n_work,
-                         cudaStream_t stream)
+static void fill_params(Params &P, hsa_workspace *ws, const Batch &b)
 {
-    Params P;
     memset(&P, 0, sizeof(P));
-    P.ix = ws->idx->ix; P.codes = b.codes; P.kind = b.kind; P.n_groups = n_work; P.group_list = group_list;
+    P.ix = ws->idx->ix; P.codes = b.codes; P.kind = b.kind;
     P.tasks = b.tasks; P.read_off = b.read_off; P.read_len = b.read_len;
-    P.opts = ws->opts_dev; P.n_opts = b.n_opts; P.len2opt = ws->len2opt_dev; P.max_len = sc.max_len;
-    P.filter_max_n = b.filter_max_n;
-    P.arena = sc.arena; P.links = sc.links; P.arena_cap = sc.arena_cap;
-    P.width = sc.width; P.width_stride = 2 * (sc.max_len + 1);
-    P.hits = sc.hits; P.hit_cap = sc.hit_cap; P.n_buckets = b.n_buckets;
+    P.opts = ws->opts_dev; P.n_opts = b.n_opts; P.len2opt = ws->len2opt_dev; P.max_len = b.max_len;
+    P.filter_max_n = b.filter_max_n; P.n_buckets = b.n_buckets;
     P.n_aln = b.n_aln; P.aln_off = b.aln_off; P.status = ws->status_dev; P.aln = b.aln; P.aln_cap = b.aln_cap;
     P.counters = ws->counters; P.strict_list = ws->strict_list;
     P.width_out = b.width_out; P.bid_out = b.bid_out;
-    size_t smem = (size_t)b.n_opts * sizeof(DevOpt) + (size_t)b.n_buckets * sc.block * sizeof(uint16_t);
-    const void *fn = search_fn(ws->minb);
+}
+
+static int launch_search(hsa_workspace *ws, Params &P, Scratch &sc, cudaStream_t stream)
+{
+    P.arena = sc.arena; P.links = sc.links; P.arena_cap = sc.arena_cap;
+    P.width = sc.width;
+    if (sc.wide) { P.width_stride = 2 * (sc.max_len + 1); P.max_len = sc.max_len; }
+    P.hits = sc.hits; P.hit_cap = sc.hit_cap;
+    size_t smem = (size_t)P.n_opts * sizeof(DevOpt) + (size_t)P.n_buckets * sc.block * (sc.wide ? 4 : 2);
+    const void *fn = search_fn((int)sc.block, ws->minb, sc.wide);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {(void *)&P};
     CU(cudaLaunchKernel(fn, dim3(sc.grid), dim3(sc.block), args, smem, stream));
@@ -506,40 +547,103 @@ static int launch_search(hsa_workspace *ws, const Batch &b, Scratch &sc, const u
     return HSA_OK;
 }
 
+static int launch_width(hsa_workspace *ws, Params &P, uint32_t grid, cudaStream_t stream)
+{
+    size_t smem = (size_t)P.n_opts * sizeof(DevOpt);
+    width_kernel<<<grid, 256, smem, stream>>>(P);
+    CU(cudaGetLastError());
+    ++ws->last_launches;
+    return HSA_OK;
+}
+
 // Runs one batch whose inputs/outputs are already on the device.  `sync` selects whether the call waits
 // and handles strict re-runs (host-buffer entry points) or just enqueues (device entry point).
+//
+// Split pipeline per chunk of groups:   width(pass 1) -> search(pass 1) [-> width(pass 2) -> search(pass 2)]
+// Pass 2 exists only for whole reads: the reads whose reverse-complement strand found nothing are appended
+// to a device-side list by the pass-1 search kernel, and the pass-2 kernels read the list length from
+// device memory, so no host synchronisation separates the four launches.
 static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, bool sync, uint64_t stats[CNT_N], float *ms)
 {
     const hsa_index *ix = ws->idx;
     CU(cudaSetDevice(ix->device));
     ws->last_launches = 0;
-    const uint32_t block = 256;
+    if (!ws->block) {
+        ws->block = (uint32_t)env_long("HSA_B200_BLOCK", 128);
+        if (ws->block != 128) ws->block = 256;
+        ws->minb = (int)env_long("HSA_B200_MINB", ws->block == 128 ? 5 : 2);
+    }
+    const uint32_t block = ws->block;
     size_t smem = (size_t)b.n_opts * sizeof(DevOpt) + (size_t)b.n_buckets * block * sizeof(uint16_t);
     if (smem > 200 * 1024) return fail(HSA_E_ARG, "option table too large for shared memory");
     if (!ws->blocks_per_sm) {
         int occ = 0;
-        ws->minb = (int)env_long("HSA_B200_MINB", 3);
-        const void *fn = search_fn(ws->minb);
+        const void *fn = search_fn((int)block, ws->minb, false);
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)block, smem));
         if (occ < 1) return fail(HSA_E_CUDA, "search kernel does not fit on an SM");
         ws->blocks_per_sm = (int)env_long("HSA_B200_BLOCKS_PER_SM", occ);
         if (ws->blocks_per_sm > occ) ws->blocks_per_sm = occ;
     }
+    const uint32_t items_per_group = b.kind == KIND_SEEDS ? 6u : 1u;
+    const uint64_t n_work_total = (uint64_t)b.n_groups * items_per_group;
     uint32_t grid_full = (uint32_t)(ix->sm_count * ws->blocks_per_sm);
-    uint32_t grid = std::min<uint32_t>(grid_full, (b.n_groups + block - 1) / block);
+    uint32_t grid = (uint32_t)std::min<uint64_t>(grid_full, (n_work_total + block - 1) / block);
     if (grid == 0) grid = 1;
-    uint32_t arena_cap = (uint32_t)env_long("HSA_B200_ARENA_CAP", 4096), hit_cap = (uint32_t)env_long("HSA_B200_HIT_CAP", 32);
-    if (arena_cap > 65535) arena_cap = 65535;
+    uint32_t arena_cap = (uint32_t)env_long("HSA_B200_ARENA_CAP", 1024), hit_cap = (uint32_t)env_long("HSA_B200_HIT_CAP", 32);
+    if (arena_cap > 4094) arena_cap = 4094;          // 12-bit links, 0xFFF = nil
     int rc;
-    // small batches get a small scratch; anything that fills the GPU gets the full-grid scratch once
-    if ((rc = scratch_alloc(ws->fast, grid, block, arena_cap, hit_cap, b.max_len))) return rc;
+    if ((rc = scratch_alloc(ws->fast, grid, block, arena_cap, hit_cap, 0, false))) return rc;
     ws->fast.grid = grid;
     if ((rc = ensure(ws->status_dev, ws->status_cap, (size_t)b.n_items + 1))) return rc;
-    if ((rc = ensure(ws->strict_list, ws->strict_list_cap, (size_t)b.n_groups + 1))) return rc;
-    CU(cudaMemsetAsync(ws->counters, 0, CNT_N * sizeof(unsigned long long), stream));
+    if ((rc = ensure(ws->strict_list, ws->strict_list_cap, (size_t)n_work_total + 1))) return rc;
+
+    // per-item width buffers: width_back[max_len+1] then width_seed[seed_cap]
+    uint32_t seed_cap = 0;
+    if (b.kind == KIND_TASKS || b.kind == KIND_WHOLE) seed_cap = b.max_seed_len + 1;
+    const uint32_t wstride = (b.max_len + 1) + seed_cap + 1;        // + one slot for the item's width lookup count
+    const uint64_t budget_entries = (uint64_t)env_long("HSA_B200_WIDTH_MB", 16384) * (1ull << 20) / sizeof(u32x2);
+    uint64_t chunk_items = std::max<uint64_t>(budget_entries / wstride, 6);
+    chunk_items -= chunk_items % 6;
+    uint32_t chunk_groups = (uint32_t)std::min<uint64_t>(b.n_groups, chunk_items / items_per_group);
+    if (b.kind != KIND_WIDTH) {
+        if ((rc = ensure(ws->item_width, ws->item_width_cap, (size_t)chunk_groups * items_per_group * wstride))) return rc;
+        if (b.kind == KIND_WHOLE && (rc = ensure(ws->next_list, ws->next_list_cap, (size_t)chunk_groups + 1))) return rc;
+    }
+
+    CU(cudaMemsetAsync(ws->counters, 0, (CNT_N + 16) * sizeof(unsigned long long), stream));
     CU(cudaEventRecord(ws->ev0, stream));
-    if ((rc = launch_search(ws, b, ws->fast, nullptr, b.n_groups, stream))) return rc;
+    Params P;
+    fill_params(P, ws, b);
+    P.item_width = ws->item_width; P.item_width_stride = wstride;
+    uint32_t cursor_slot = 0;
+    for (uint32_t g0 = 0; g0 < b.n_groups; g0 += chunk_groups) {
+        const uint32_t ng = std::min(chunk_groups, b.n_groups - g0);
+        const uint32_t nw = ng * items_per_group;
+        const uint32_t wgrid = std::max<uint32_t>(1, std::min<uint32_t>((nw + 255) / 256, (uint32_t)ix->sm_count * 8));
+        // cursors live behind the statistics block; each launch gets a fresh one (slots are recycled per batch)
+        P.pass = 1; P.group_base = g0; P.n_groups = nw; P.n_groups_dev = nullptr; P.group_list = nullptr;
+        P.next_list = ws->next_list; P.next_count = reinterpret_cast<uint32_t *>(ws->counters + CNT_N + 8 + (cursor_slot % 8));
+        if ((rc = launch_width(ws, P, wgrid, stream))) return rc;
+        if (b.kind == KIND_WIDTH) continue;
+        if (cursor_slot >= 8) {      // recycle cursor / list-count slots of earlier chunks
+            CU(cudaMemsetAsync(ws->counters + CNT_N + (cursor_slot % 8), 0, 8, stream));
+            CU(cudaMemsetAsync(ws->counters + CNT_N + 8 + (cursor_slot % 8), 0, 8, stream));
+        }
+        P.cursor = ws->counters + CNT_N + (cursor_slot % 8);
+        if ((rc = launch_search(ws, P, ws->fast, stream))) return rc;
+        ++cursor_slot;
+        if (b.kind == KIND_WHOLE) {
+            const uint32_t *cnt2 = P.next_count;
+            P.pass = 2; P.group_list = ws->next_list; P.n_groups = ng; P.n_groups_dev = cnt2;
+            P.next_list = nullptr; P.next_count = nullptr;
+            if ((rc = launch_width(ws, P, wgrid, stream))) return rc;
+            if (cursor_slot >= 8) CU(cudaMemsetAsync(ws->counters + CNT_N + (cursor_slot % 8), 0, 8, stream));
+            P.cursor = ws->counters + CNT_N + (cursor_slot % 8);
+            if ((rc = launch_search(ws, P, ws->fast, stream))) return rc;
+            ++cursor_slot;
+        }
+    }
     CU(cudaEventRecord(ws->ev1, stream));
     if (!sync) return HSA_OK;
 
@@ -552,17 +656,19 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
     if (cnt[CNT_BAD]) return fail(HSA_E_ARG, "a score exceeded the bucket table (internal sizing error)");
     uint64_t n_strict = cnt[CNT_STRICT];
     if (n_strict) {
-        // re-run the groups that ran out of stack / hit capacity with the large-capacity configuration
-        uint32_t sblock = 64, sgrid = (uint32_t)std::min<uint64_t>((n_strict + sblock - 1) / sblock, (uint64_t)ix->sm_count);
-        if ((rc = scratch_alloc(ws->strict, sgrid, sblock, 65535, 4096, b.max_len))) return rc;
+        // re-run the groups that ran out of stack / hit capacity with the large-capacity, fused configuration
+        uint32_t sblock = 64, sgrid = (uint32_t)std::min<uint64_t>((n_strict + sblock - 1) / sblock, (uint64_t)ix->sm_count * 2);
+        if ((rc = scratch_alloc(ws->strict, sgrid, sblock, 1u << 18, 4096, b.max_len, true))) return rc;
         uint32_t *list_dev = nullptr;
         CU(cudaMalloc((void **)&list_dev, n_strict * 4));
         CU(cudaMemcpyAsync(list_dev, ws->strict_list, n_strict * 4, cudaMemcpyDeviceToDevice, stream));
-        unsigned long long zero[3] = {0, 0, 0};
-        CU(cudaMemcpyAsync(ws->counters + CNT_WORK, zero, 8, cudaMemcpyHostToDevice, stream));
-        CU(cudaMemcpyAsync(ws->counters + CNT_STRICT, zero, 16, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemsetAsync(ws->counters + CNT_STRICT, 0, 16, stream));
+        CU(cudaMemsetAsync(ws->counters + CNT_N, 0, 8, stream));
+        Params S;
+        fill_params(S, ws, b);
+        S.group_list = list_dev; S.n_groups = (uint32_t)n_strict; S.cursor = ws->counters + CNT_N;
         CU(cudaEventRecord(ws->ev0, stream));
-        if ((rc = launch_search(ws, b, ws->strict, list_dev, (uint32_t)n_strict, stream))) { cudaFree(list_dev); return rc; }
+        if ((rc = launch_search(ws, S, ws->strict, stream))) { cudaFree(list_dev); return rc; }
         CU(cudaEventRecord(ws->ev1, stream));
         unsigned long long cnt2[CNT_N];
         CU(cudaMemcpyAsync(cnt2, ws->counters, sizeof(cnt2), cudaMemcpyDeviceToHost, stream));
@@ -571,7 +677,7 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
         CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
         *ms += t;
         if (cnt2[CNT_STRICT] || cnt2[CNT_BAD])
-            return fail(HSA_E_CAPACITY, "a search exceeded the strict kernel's 65535-entry stack or 4096-hit capacity");
+            return fail(HSA_E_CAPACITY, "a search exceeded the large-capacity kernel's 262144-record stack or 4096-hit capacity");
         for (int i = 0; i < CNT_N; ++i) cnt[i] = cnt2[i];
     }
     for (int i = 0; i < CNT_N; ++i) stats[i] = cnt[i];
@@ -679,9 +785,13 @@ static int upload_reads(hsa_workspace *ws, const uint8_t *codes, const uint64_t 
     return HSA_OK;
 }
 
-static int upload_opts(hsa_workspace *ws, const std::vector<hsa_gap_opt_t> &opts, uint32_t max_len, uint32_t *n_buckets,
+static int upload_opts(hsa_workspace *ws, const std::vector<hsa_gap_opt_t> &opts, uint32_t max_len, Batch *bt,
                        const std::vector<uint16_t> *len2opt)
 {
+    uint32_t *n_buckets = &bt->n_buckets;
+    bt->max_seed_len = 0;
+    for (const hsa_gap_opt_t &o : opts)
+        if (o.seed_len > 0 && (uint32_t)o.seed_len < max_len) bt->max_seed_len = std::max(bt->max_seed_len, (uint32_t)o.seed_len);
     const hsa_index *ix = ws->idx;
     int rc;
     std::vector<DevOpt> d(opts.size());
@@ -748,7 +858,7 @@ extern "C" int hsa_match_gap_batch(const hsa_index_t *ix, const uint8_t *codes, 
     if (n_tasks == 0) { res->n_items = 0; res->n_aln_total = 0; return HSA_OK; }
     std::vector<hsa_gap_opt_t> ov(opts, opts + n_opts);
     Batch b;
-    if ((rc = upload_opts(ws, ov, max_len, &b.n_buckets, nullptr))) return rc;
+    if ((rc = upload_opts(ws, ov, max_len, &b, nullptr))) return rc;
     if ((rc = ensure(ws->codes_dev, ws->codes_cap, codes_bytes + 16))) return rc;
     if ((rc = ensure(ws->tasks_dev, ws->tasks_cap, n_tasks))) return rc;
     CU(cudaMemcpyAsync(ws->codes_dev, codes, codes_bytes, cudaMemcpyHostToDevice, ix->stream));
@@ -784,7 +894,7 @@ extern "C" int hsa_whole_reads(const hsa_index_t *ix, const uint8_t *codes, cons
     std::vector<hsa_gap_opt_t> opts; std::vector<uint16_t> l2o;
     Batch b;
     if ((rc = resolve_whole_opts(opt, keep_gape, lens, max_len, opts, l2o, &b.filter_max_n))) return rc;
-    if ((rc = upload_opts(ws, opts, max_len, &b.n_buckets, &l2o))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b, &l2o))) return rc;
     b.kind = KIND_WHOLE; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads; b.max_len = max_len;
     b.n_opts = (uint32_t)opts.size(); b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
     return run_and_fetch(ws, b, res);
@@ -801,7 +911,7 @@ extern "C" int hsa_splice_seeds(const hsa_index_t *ix, const uint8_t *codes, con
     so.mode &= ~HSA_MODE_GAPE; so.max_gapo = 0; so.max_gape = 0; so.max_diff = opt->max_seed_diff;
     std::vector<hsa_gap_opt_t> opts(1, so);
     Batch b;
-    if ((rc = upload_opts(ws, opts, max_len, &b.n_buckets, nullptr))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b, nullptr))) return rc;
     b.kind = KIND_SEEDS; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads * 6; b.max_len = max_len;
     b.n_opts = 1; b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
     return run_and_fetch(ws, b, res);
@@ -820,7 +930,7 @@ extern "C" int hsa_cal_width_batch(const hsa_index_t *ix, const uint8_t *codes, 
     hsa_gap_opt_t o; hsa_gap_opt_default(&o); o.max_diff = 0;
     std::vector<hsa_gap_opt_t> opts(1, o);
     Batch b;
-    if ((rc = upload_opts(ws, opts, max_len, &b.n_buckets, nullptr))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b, nullptr))) return rc;
     if ((rc = ensure(ws->width_out_dev, ws->width_out_cap, total))) return rc;
     cudaFree(ws->bid_dev); ws->bid_dev = nullptr;
     CU(cudaMalloc((void **)&ws->bid_dev, n * sizeof(int32_t)));
@@ -856,7 +966,7 @@ extern "C" int hsa_whole_reads_device(const hsa_index_t *ix, hsa_workspace_t *ws
     std::vector<hsa_gap_opt_t> opts; std::vector<uint16_t> l2o;
     Batch b;
     if ((rc = resolve_whole_opts(opt, keep_gape, lens, max_len, opts, l2o, &b.filter_max_n))) return rc;
-    if ((rc = upload_opts(ws, opts, max_len, &b.n_buckets, &l2o))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b, &l2o))) return rc;
     b.kind = KIND_WHOLE; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads; b.max_len = max_len;
     b.n_opts = (uint32_t)opts.size(); b.codes = codes_dev; b.read_off = off_dev; b.read_len = len_dev;
     b.n_aln = n_aln_dev; b.aln_off = aln_off_dev; b.aln = reinterpret_cast<uint32_t *>(aln_dev); b.aln_cap = aln_capacity;

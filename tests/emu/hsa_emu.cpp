@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <algorithm>
 #include "../../hsa_b200/csrc/hsa_core.cuh"
 #include "../../include/hsa_b200.h"
 
@@ -35,6 +36,24 @@ static void repack(const hsa_bwt_view_t *v, std::vector<u32x4> &out, DevBwt &d)
     }
     d.blocks = out.data(); d.n_blocks = nb; d.text_length = v->textLength; d.inverse_sa0 = v->inverseSa0;
     for (int i = 0; i < 5; ++i) d.cum[i] = v->cumulativeFreq[i];
+}
+
+static uint64_t g_last_extra = 0, g_last_steps = 0;
+
+template <typename LinkT, bool FUSED>
+static void run_worker(const Params &P, LinkT *heads, const DevOpt *dopts, uint32_t n_work, uint64_t st[4])
+{
+    Worker<LinkT, FUSED> w(P, 0, heads, 1, dopts);
+    uint32_t next = 0;
+    for (;;) {
+        if (w.idle()) {
+            if (next < n_work) w.start_group(next++);
+            else break;
+            continue;
+        }
+        w.template iterate<2>();
+    }
+    st[0] += w.lookups; st[1] += w.pops; st[2] += w.extra; st[3] += w.steps;
 }
 
 extern "C" {
@@ -93,10 +112,10 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
     }
     if (nb > 128) return -1;
     std::vector<u32x4> arena(arena_cap);
-    std::vector<uint16_t> links(arena_cap);
+    std::vector<uint32_t> links(arena_cap);          // large enough for either link width
     std::vector<u32x2> width(2 * (size_t)(max_len + 1));
     std::vector<Hit> hits(hit_cap);
-    std::vector<uint16_t> heads(nb);
+    std::vector<uint32_t> heads(nb);
     std::vector<uint32_t> strict(n_groups + 1);
     unsigned long long counters[CNT_N];
     memset(counters, 0, sizeof(counters));
@@ -113,20 +132,43 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
     P.counters = counters; P.strict_list = strict.data();
     P.width_out = (u32x2 *)width_out; P.bid_out = bid_out;
 
-    Worker w(P, 0, heads.data(), 1, dopts.data());
-    uint32_t next = 0;
-    for (;;) {
-        if (w.idle()) {
-            if (next < n_groups) w.start_group(next++);
-            else break;
-            continue;
+    uint64_t st[4] = {0, 0, 0, 0};
+    unsigned long long cursor = 0;
+    P.cursor = &cursor;
+    if (arena_cap > 4094) {
+        // the large-capacity configuration: fused flow (width passes + both strands inside the worker), 32-bit links
+        run_worker<uint32_t, true>(P, heads.data(), dopts.data(), n_groups, st);
+    } else {
+        // the split pipeline, launch for launch as hsa_b200.cu's run_batch enqueues it
+        const uint32_t per = kind == KIND_SEEDS ? 6u : 1u, n_work = n_groups * per;
+        uint32_t max_seed = 0;
+        for (uint32_t i = 0; i < n_opts; ++i)
+            if (opts[i].seed_len > 0 && (uint32_t)opts[i].seed_len < max_len) max_seed = std::max(max_seed, (uint32_t)opts[i].seed_len);
+        const uint32_t seed_cap = (kind == KIND_TASKS || kind == KIND_WHOLE) ? max_seed + 1 : 0;
+        const uint32_t wstride = (max_len + 1) + seed_cap + 1;
+        std::vector<u32x2> item_width((size_t)std::max(n_work, 1u) * wstride);
+        std::vector<uint32_t> next_list(n_groups + 1);
+        uint32_t next_count = 0;
+        P.item_width = item_width.data(); P.item_width_stride = wstride;
+        P.pass = 1; P.group_base = 0; P.n_groups = n_work; P.next_list = next_list.data(); P.next_count = &next_count;
+        for (uint32_t w = 0; w < n_work; ++w) width_item(P, dopts.data(), w, st[0]);
+        if (kind != KIND_WIDTH) {
+            run_worker<uint16_t, false>(P, (uint16_t *)heads.data(), dopts.data(), n_work, st);
+            if (kind == KIND_WHOLE) {
+                P.pass = 2; P.group_list = next_list.data(); P.n_groups = next_count; P.next_list = nullptr; P.next_count = nullptr;
+                for (uint32_t w = 0; w < next_count; ++w) width_item(P, dopts.data(), w, st[0]);
+                run_worker<uint16_t, false>(P, (uint16_t *)heads.data(), dopts.data(), next_count, st);
+            }
         }
-        w.iterate<2>();
     }
-    *lookups = w.lookups;
+    *lookups = st[0];
     *n_strict = counters[CNT_STRICT] + counters[CNT_BAD];
-    *pops = w.pops;
+    *pops = st[1];
+    g_last_extra = st[2]; g_last_steps = st[3];
     return (long)counters[CNT_ALN];
 }
+
+uint64_t emu_last_extra(void) { return g_last_extra; }
+uint64_t emu_last_steps(void) { return g_last_steps; }
 
 } // extern "C"

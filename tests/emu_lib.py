@@ -107,7 +107,7 @@ class Emu:
                       idx.shape[0], out.ctypes.data)
         return out
 
-    def run(self, kind, rs, opts, tasks=None, len2opt=None, filter_max_n=0, arena_cap=4096, hit_cap=32,
+    def run(self, kind, rs, opts, tasks=None, len2opt=None, filter_max_n=0, arena_cap=1024, hit_cap=32,
             n_items=None, want_width=False):
         codes = np.ascontiguousarray(rs.codes, dtype=np.uint8)
         off = np.ascontiguousarray(rs.offsets[:-1], dtype=np.uint64)

@@ -30,13 +30,16 @@ def test_width(golden, emu):
         assert np.array_equal(w[off[r] + r: off[r] + r + int(rs.lens[r]) + 1], ww)
 
 
+@pytest.mark.parametrize("arena_cap", [4094, 65535], ids=["split16", "fused32"])
 @pytest.mark.parametrize("mode", ["percall", "whole", "seeds"])
 @pytest.mark.parametrize("case", ["cfg1_75bp_n2o1", "cfg2_100bp_default", "cfg5_150bp_n5o2", "ragged_nonstop",
                                   "ragged_loggap_gape", "short_entries", "exact_only", "noskip_gaps"])
-def test_search_matches_reference(golden, emu, case, mode):
+def test_search_matches_reference(golden, emu, case, mode, arena_cap):
+    """split16: the split pipeline (width kernel -> search kernel per strand pass, 16-bit links);
+    fused32: the large-capacity configuration (fused flow, 32-bit links) used for re-runs."""
     rs = golden.reads(case)
     opt = ol.default_opt(**golden.opt_kwargs(case))
-    n_aln, rows, status = getattr(emu, mode)(rs, opt, arena_cap=65535, hit_cap=4096)
+    n_aln, rows, status = getattr(emu, mode)(rs, opt, arena_cap=arena_cap, hit_cap=4096)
     exp_n, exp_rows = golden.expected(case, mode)
     assert int((status != 0).sum()) == 0
     assert np.array_equal(n_aln, exp_n)
