@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
     const uint32_t n_work = P.n_groups_dev ? *P.n_groups_dev : P.n_groups;
     Worker<LinkT, FUSED> w(P, slot, heads + threadIdx.x, blockDim.x, sopt);
 
+    unsigned long long warp_iters = 0;
     for (;;) {
+        ++warp_iters;
         const bool need = w.idle();
         const unsigned bal = __ballot_sync(0xffffffffu, need);
         if (bal) {
@@ -120,7 +122,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
         st += __shfl_down_sync(0xffffffffu, st, o);
         ex += __shfl_down_sync(0xffffffffu, ex, o);
     }
+    unsigned mx = w.max_item_steps;
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
     if (lane == 0) {
+        atomicAdd(&P.counters[CNT_DIAG_WARP_ITERS], warp_iters);
+        atomicMax(&P.counters[CNT_DIAG_MAX_ITEM_STEPS], (unsigned long long)mx);
         atomicAdd(&P.counters[CNT_LOOKUPS], lk);
         atomicAdd(&P.counters[CNT_POPS], pp);
         atomicAdd(&P.counters[CNT_STEPS], st);
@@ -214,6 +220,9 @@ struct hsa_workspace {
     u32x2 *item_width = nullptr; size_t item_width_cap = 0;     // split pipeline: per-item width_back / width_seed
     uint32_t *next_list = nullptr; size_t next_list_cap = 0;      // reads that go on to the forward-strand pass
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> trace_ev;             // HSA_B200_TRACE=1: one event after every launch
+    std::vector<const char *> trace_name;
+    int trace = -1;
     uint32_t last_launches = 0;
     int blocks_per_sm = 0;
     int minb = 2;
@@ -470,7 +479,7 @@ extern "C" int hsa_workspace_create(const hsa_index_t *ix, size_t max_reads, uin
     hsa_workspace *ws = new hsa_workspace();
     ws->idx = ix;
     // statistics block, then 8 work-queue cursors, then 8 pass-2 list counters
-    CU(cudaMalloc((void **)&ws->counters, (CNT_N + 16) * sizeof(unsigned long long)));
+    CU(cudaMalloc((void **)&ws->counters, CNT_TOTAL * sizeof(unsigned long long)));
     CU(cudaEventCreate(&ws->ev0)); CU(cudaEventCreate(&ws->ev1));
     (void)max_len;
     *out = ws;
@@ -532,6 +541,37 @@ static void fill_params(Params &P, hsa_workspace *ws, const Batch &b)
     P.width_out = b.width_out; P.bid_out = b.bid_out;
 }
 
+static void trace_mark(hsa_workspace *ws, const char *name, cudaStream_t stream)
+{
+    if (ws->trace <= 0) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, stream);
+    ws->trace_ev.push_back(e); ws->trace_name.push_back(name);
+}
+
+static void trace_dump(hsa_workspace *ws, const unsigned long long *cnt_all)
+{
+    if (ws->trace <= 0) return;
+    cudaEvent_t prev = ws->ev0;
+    fprintf(stderr, "[hsa_b200 trace]");
+    for (size_t i = 0; i < ws->trace_ev.size(); ++i) {
+        float t = 0;
+        cudaEventElapsedTime(&t, prev, ws->trace_ev[i]);
+        fprintf(stderr, " %s=%.3fms", ws->trace_name[i], t);
+        if (prev != ws->ev0) cudaEventDestroy(prev);
+        prev = ws->trace_ev[i];
+    }
+    if (prev != ws->ev0) cudaEventDestroy(prev);
+    ws->trace_ev.clear(); ws->trace_name.clear();
+    if (cnt_all)
+        fprintf(stderr, " | steps=%llu warp_iters=%llu lane_occupancy=%.3f max_item_steps=%llu pops=%llu lookups=%llu",
+                cnt_all[CNT_STEPS], cnt_all[CNT_DIAG_WARP_ITERS],
+                cnt_all[CNT_DIAG_WARP_ITERS] ? (double)cnt_all[CNT_STEPS] / (32.0 * (double)cnt_all[CNT_DIAG_WARP_ITERS]) : 0.0,
+                cnt_all[CNT_DIAG_MAX_ITEM_STEPS], cnt_all[CNT_POPS], cnt_all[CNT_LOOKUPS]);
+    fprintf(stderr, "\n");
+}
+
 static int launch_search(hsa_workspace *ws, Params &P, Scratch &sc, cudaStream_t stream)
 {
     P.arena = sc.arena; P.links = sc.links; P.arena_cap = sc.arena_cap;
@@ -544,6 +584,7 @@ static int launch_search(hsa_workspace *ws, Params &P, Scratch &sc, cudaStream_t
     void *args[] = {(void *)&P};
     CU(cudaLaunchKernel(fn, dim3(sc.grid), dim3(sc.block), args, smem, stream));
     ++ws->last_launches;
+    trace_mark(ws, sc.wide ? "search(strict)" : "search", stream);
     return HSA_OK;
 }
 
@@ -553,6 +594,7 @@ static int launch_width(hsa_workspace *ws, Params &P, uint32_t grid, cudaStream_
     width_kernel<<<grid, 256, smem, stream>>>(P);
     CU(cudaGetLastError());
     ++ws->last_launches;
+    trace_mark(ws, "width", stream);
     return HSA_OK;
 }
 
@@ -568,6 +610,7 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
     const hsa_index *ix = ws->idx;
     CU(cudaSetDevice(ix->device));
     ws->last_launches = 0;
+    if (ws->trace < 0) ws->trace = sync ? (int)env_long("HSA_B200_TRACE", 0) : 0;
     if (!ws->block) {
         ws->block = (uint32_t)env_long("HSA_B200_BLOCK", 128);
         if (ws->block != 128) ws->block = 256;
@@ -611,7 +654,7 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
         if (b.kind == KIND_WHOLE && (rc = ensure(ws->next_list, ws->next_list_cap, (size_t)chunk_groups + 1))) return rc;
     }
 
-    CU(cudaMemsetAsync(ws->counters, 0, (CNT_N + 16) * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(ws->counters, 0, CNT_TOTAL * sizeof(unsigned long long), stream));
     CU(cudaEventRecord(ws->ev0, stream));
     Params P;
     fill_params(P, ws, b);
@@ -647,9 +690,10 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
     CU(cudaEventRecord(ws->ev1, stream));
     if (!sync) return HSA_OK;
 
-    unsigned long long cnt[CNT_N];
+    unsigned long long cnt[CNT_TOTAL];
     CU(cudaMemcpyAsync(cnt, ws->counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
+    trace_dump(ws, cnt);
     float t = 0;
     CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
     *ms = t;
@@ -670,9 +714,10 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
         CU(cudaEventRecord(ws->ev0, stream));
         if ((rc = launch_search(ws, S, ws->strict, stream))) { cudaFree(list_dev); return rc; }
         CU(cudaEventRecord(ws->ev1, stream));
-        unsigned long long cnt2[CNT_N];
+        unsigned long long cnt2[CNT_TOTAL];
         CU(cudaMemcpyAsync(cnt2, ws->counters, sizeof(cnt2), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
+        trace_dump(ws, cnt2);
         cudaFree(list_dev);
         CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
         *ms += t;

@@ -267,6 +267,8 @@ struct Hit {                    // worker-private hit record (2 x 16 bytes)
 
 // counters block (uint64 each)
 enum { CNT_WORK = 0, CNT_ALN = 1, CNT_LOOKUPS = 2, CNT_STRICT = 3, CNT_BAD = 4, CNT_POPS = 5, CNT_STEPS = 6, CNT_EXTRA = 7, CNT_N = 8 };
+// internal block behind the public statistics: 8 work-queue cursors, 8 pass-2 list counters, diagnostics
+enum { CNT_CURSOR0 = CNT_N, CNT_NEXT0 = CNT_N + 8, CNT_DIAG_WARP_ITERS = CNT_N + 16, CNT_DIAG_MAX_ITEM_STEPS = CNT_N + 17, CNT_TOTAL = CNT_N + 24 };
 
 struct Params {
     DevIndex ix;
@@ -501,10 +503,11 @@ struct Worker {
     bool ending;                    // the current task is over (handled once, at the end of the iteration)
     // statistics
     uint64_t lookups, lookups_group, pops, steps, extra;
+    uint64_t steps_item0; uint32_t max_item_steps;  // diagnostics: iterations of the longest single item
 
     HSA_HD Worker(const Params &p, uint32_t slot_, LinkT *heads_, uint32_t stride_, const DevOpt *opts_)
         : P(p), slot(slot_), heads(heads_), head_stride(stride_), opts(opts_), phase(IDLE),
-          lookups(0), lookups_group(0), pops(0), steps(0), extra(0) {}
+          lookups(0), lookups_group(0), pops(0), steps(0), extra(0), steps_item0(0), max_item_steps(0) {}
 
     HSA_HD bool idle() const { return phase == IDLE; }
     HSA_HD bool retired() const { return phase == RETIRED; }
@@ -534,6 +537,7 @@ struct Worker {
     {
         work = work_idx;
         lookups_group = 0;
+        steps_item0 = steps;
         failed = false; fail_code = STATUS_OK;
         if (FUSED) {
             gid = P.group_list ? P.group_list[work_idx] : P.group_base + work_idx;
@@ -761,6 +765,7 @@ struct Worker {
 
     HSA_HD void end_task()
     {
+        if ((uint32_t)(steps - steps_item0) > max_item_steps) max_item_steps = (uint32_t)(steps - steps_item0);
         if (failed) { fail_group(); return; }
         if (!FUSED) {
             const uint64_t mine = lookups_group + wback()[P.item_width_stride - 1].x;   // + the width kernel's share

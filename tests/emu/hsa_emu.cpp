@@ -39,14 +39,18 @@ static void repack(const hsa_bwt_view_t *v, std::vector<u32x4> &out, DevBwt &d)
 }
 
 static uint64_t g_last_extra = 0, g_last_steps = 0;
+static uint32_t *g_item_steps = nullptr;      // optional diagnostic: worker iterations per work item, launches concatenated
+static size_t g_item_steps_pos = 0;
 
 template <typename LinkT, bool FUSED>
 static void run_worker(const Params &P, LinkT *heads, const DevOpt *dopts, uint32_t n_work, uint64_t st[4])
 {
     Worker<LinkT, FUSED> w(P, 0, heads, 1, dopts);
     uint32_t next = 0;
+    uint64_t steps0 = 0;
     for (;;) {
         if (w.idle()) {
+            if (g_item_steps && next > 0) { g_item_steps[g_item_steps_pos++] = (uint32_t)(w.steps - steps0); steps0 = w.steps; }
             if (next < n_work) w.start_group(next++);
             else break;
             continue;
@@ -168,6 +172,7 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
     return (long)counters[CNT_ALN];
 }
 
+void emu_set_item_steps(uint32_t *buf) { g_item_steps = buf; g_item_steps_pos = 0; }
 uint64_t emu_last_extra(void) { return g_last_extra; }
 uint64_t emu_last_steps(void) { return g_last_steps; }
 
