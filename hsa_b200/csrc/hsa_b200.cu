@@ -3,8 +3,9 @@
 // Kernels:
 //   repack_kernel        reference-layout BWT + occ tables  ->  one 32-byte sector per 64 symbols
 //   occ_kernel           BWTAllOccValue / BWTOccValue on either layout (rank parity)
-//   search_kernel        persistent, atomic work queue; one worker (hsa_core.cuh) per thread runs the
-//                        width pass (bwt_cal_width) and the bounded backtracking search (bwt_match_gap)
+//   width_kernel         bwt_cal_width for every work item: one thread per item, writes the item's row
+//   search_kernel        persistent, atomic work queue; one search (hsa_core.cuh Worker) per thread, one kind
+//                        of step per warp trip chosen by vote: the bounded backtracking search bwt_match_gap
 //   probe_kernel         random 32-byte-sector loads: the roofline denominator of SURVEY.md 8d
 //
 // There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
@@ -60,77 +61,83 @@ __global__ void occ_kernel(DevBwt dev, RefBwt ref, int layout, const uint32_t *i
 // same shape, so the loop is divergence-free (bwt_cal_width is a strictly sequential chain per read).
 __global__ void __launch_bounds__(256) width_kernel(const __grid_constant__ Params P)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    DevOpt *sopt = reinterpret_cast<DevOpt *>(smem);
+    DevOpt *sopt = reinterpret_cast<DevOpt *>(hsa_smem);
     for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
         reinterpret_cast<int *>(sopt)[i] = reinterpret_cast<const int *>(P.opts)[i];
     __syncthreads();
-    const uint32_t n = P.n_groups_dev ? *P.n_groups_dev : P.n_groups;
-    unsigned long long lk = 0;
-    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
-        uint64_t l = 0;
-        width_item(P, sopt, w, l);
-        lk += l;
-    }
-    for (int o = 16; o > 0; o >>= 1) lk += __shfl_down_sync(0xffffffffu, lk, o);
-    if ((threadIdx.x & 31u) == 0 && lk) atomicAdd(&P.counters[CNT_LOOKUPS], lk);
+    const uint32_t n = P.n_work_dev ? *P.n_work_dev : P.n_work;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x)
+        width_item(P, sopt, w);
 }
 
-// MINB = minimum resident 256-thread blocks per SM the register allocation must allow (2: <=128 regs,
-// 3: <=80, 4: <=64); the variant is picked at run time (HSA_B200_MINB) so occupancy can be tuned on the GPU.
-template <int MAX_POPS, int BLOCK, int MINB, typename LinkT, bool FUSED>
+// Search kernel: persistent grid, one search per thread, atomic work queue.  Every trip of the loop the warp
+// votes for ONE kind of step (hsa_core.cuh: phase_vote) and only the lanes waiting for that kind take it, so
+// the lanes that execute share one instruction stream.
+// MINB = minimum resident blocks per SM the register allocation must allow; picked at run time
+// (HSA_B200_MINB) so occupancy can be tuned on the GPU.
+template <int BLOCK, int MINB, typename LinkT, bool BIDS_SMEM>
 __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_constant__ Params P)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    DevOpt *sopt = reinterpret_cast<DevOpt *>(smem);
-    LinkT *heads = reinterpret_cast<LinkT *>(smem + (size_t)P.n_opts * sizeof(DevOpt));
     for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
-        reinterpret_cast<int *>(sopt)[i] = reinterpret_cast<const int *>(P.opts)[i];
+        reinterpret_cast<int *>(hsa_smem)[i] = reinterpret_cast<const int *>(P.opts)[i];
     __syncthreads();
 
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_work = P.n_groups_dev ? *P.n_groups_dev : P.n_groups;
-    Worker<LinkT, FUSED> w(P, slot, heads + threadIdx.x, blockDim.x, sopt);
-
+    const uint32_t n_work = P.n_work_dev ? *P.n_work_dev : P.n_work;
+    Worker<LinkT, BIDS_SMEM> w(P, slot, threadIdx.x);
     unsigned long long warp_iters = 0;
+
     for (;;) {
+        const uint32_t c = w.retired() ? 3u : w.cls();
+        const unsigned bL = __ballot_sync(0xffffffffu, c == PHASE_LOOKUP);
+        const unsigned bP = __ballot_sync(0xffffffffu, c == PHASE_POP);
+        const unsigned bS = __ballot_sync(0xffffffffu, c == PHASE_SLOW);
+        if (!(bL | bP | bS)) break;
         ++warp_iters;
-        const bool need = w.idle();
-        const unsigned bal = __ballot_sync(0xffffffffu, need);
-        if (bal) {
-            // warp-aggregated fetch from the atomic work queue
-            unsigned long long base = 0;
-            const int leader = __ffs(bal) - 1;
-            if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)__popc(bal));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (need) {
-                const unsigned long long idx = base + __popc(bal & ((1u << lane) - 1u));
-                if (idx < n_work) w.start_group((uint32_t)idx);
-                else w.retire();
+        const uint32_t ph = phase_vote(P, __popc(bL), __popc(bP), __popc(bS));
+        if (ph == PHASE_LOOKUP) {
+            if (c == PHASE_LOOKUP) w.do_lookup();
+        } else if (ph == PHASE_POP) {
+            if (c == PHASE_POP) w.do_pop();
+        } else {
+            if (w.st == LS_HIT) w.do_hit();
+            __syncwarp();
+            if (w.st == LS_END) w.do_end();
+            __syncwarp();
+            const bool need = w.idle();
+            const unsigned bal = __ballot_sync(0xffffffffu, need);
+            if (bal) {
+                // warp-aggregated fetch from the atomic work queue
+                unsigned long long base = 0;
+                const int leader = __ffs(bal) - 1;
+                if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (need) {
+                    const unsigned long long idx = base + __popc(bal & ((1u << lane) - 1u));
+                    if (idx < n_work) w.start((uint32_t)idx);
+                    else w.retire();
+                }
             }
         }
-        if (__all_sync(0xffffffffu, w.retired())) break;
-        w.template iterate<MAX_POPS>();
+        __syncwarp();
     }
 
     // statistics: warp-reduce, one atomic per warp
-    unsigned long long lk = w.lookups, pp = w.pops, st = w.steps, ex = w.extra;
+    unsigned long long lk = w.lookups, pp = w.pops, st = w.steps;
+    unsigned mx = w.max_item_steps;
     for (int o = 16; o > 0; o >>= 1) {
         lk += __shfl_down_sync(0xffffffffu, lk, o);
         pp += __shfl_down_sync(0xffffffffu, pp, o);
         st += __shfl_down_sync(0xffffffffu, st, o);
-        ex += __shfl_down_sync(0xffffffffu, ex, o);
+        mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
     }
-    unsigned mx = w.max_item_steps;
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
     if (lane == 0) {
         atomicAdd(&P.counters[CNT_DIAG_WARP_ITERS], warp_iters);
         atomicMax(&P.counters[CNT_DIAG_MAX_ITEM_STEPS], (unsigned long long)mx);
         atomicAdd(&P.counters[CNT_LOOKUPS], lk);
         atomicAdd(&P.counters[CNT_POPS], pp);
         atomicAdd(&P.counters[CNT_STEPS], st);
-        atomicAdd(&P.counters[CNT_EXTRA], ex);
     }
 }
 
@@ -191,21 +198,39 @@ struct hsa_index {
 };
 
 struct Scratch {                             // worker-private device memory for one launch configuration
-    uint32_t grid = 0, block = 0, n_workers = 0;
-    uint32_t arena_cap = 0, hit_cap = 0, max_len = 0;
-    u32x4 *arena = nullptr; void *links = nullptr; u32x2 *width = nullptr; Hit *hits = nullptr;
-    bool wide = false;                       // 32-bit links (strict) instead of 16-bit
+    uint32_t n_workers = 0, arena_cap = 0, hit_cap = 0, link_bytes = 0;
+    u32x4 *arena = nullptr; void *links = nullptr; Hit *hits = nullptr;
     void release()
     {
-        cudaFree(arena); cudaFree(links); cudaFree(width); cudaFree(hits);
-        arena = nullptr; links = nullptr; width = nullptr; hits = nullptr; n_workers = 0;
+        cudaFree(arena); cudaFree(links); cudaFree(hits);
+        arena = nullptr; links = nullptr; hits = nullptr; n_workers = 0;
     }
 };
 
+struct Pipe {                                // one in-flight chunk: stream, worker scratch, item rows, pass-2 list
+    cudaStream_t stream = nullptr;           // internal stream (used when a batch runs on more than one pipe)
+    cudaEvent_t done = nullptr;
+    Scratch sc;
+    uint8_t *rows = nullptr; size_t rows_cap = 0;
+    uint32_t *next_list = nullptr; size_t next_cap = 0;
+    void release()
+    {
+        sc.release(); cudaFree(rows); cudaFree(next_list);
+        if (stream) cudaStreamDestroy(stream);
+        if (done) cudaEventDestroy(done);
+        rows = nullptr; next_list = nullptr; stream = nullptr; done = nullptr; rows_cap = next_cap = 0;
+    }
+};
+
+enum { MAX_PIPES = 4 };
+// per-pipe slots behind the core's counters: {cursor pass 1, cursor pass 2, pass-2 list count, pad}
+enum { CNT_PIPE0 = CNT_TOTAL, CNT_ALLOC = CNT_PIPE0 + 4 * (MAX_PIPES + 1) };
+
 struct hsa_workspace {
     const hsa_index *idx = nullptr;
-    Scratch fast, strict;
-    unsigned long long *counters = nullptr;          // CNT_N
+    Pipe pipes[MAX_PIPES];
+    Pipe strict;                                     // large-capacity re-runs (slot MAX_PIPES)
+    unsigned long long *counters = nullptr;          // CNT_ALLOC
     uint32_t *strict_list = nullptr; size_t strict_list_cap = 0;
     DevOpt *opts_dev = nullptr; size_t opts_cap = 0;
     uint16_t *len2opt_dev = nullptr; size_t len2opt_cap = 0;
@@ -217,16 +242,17 @@ struct hsa_workspace {
     int32_t *n_aln_dev = nullptr; size_t items_cap = 0; uint64_t *aln_off_dev = nullptr; size_t items2_cap = 0;
     uint32_t *aln_dev = nullptr; size_t aln_cap = 0;
     u32x2 *width_out_dev = nullptr; size_t width_out_cap = 0; int32_t *bid_dev = nullptr;
-    u32x2 *item_width = nullptr; size_t item_width_cap = 0;     // split pipeline: per-item width_back / width_seed
-    uint32_t *next_list = nullptr; size_t next_list_cap = 0;      // reads that go on to the forward-strand pass
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> trace_ev;             // HSA_B200_TRACE=1: one event after every launch
     std::vector<const char *> trace_name;
     int trace = -1;
     uint32_t last_launches = 0;
-    int blocks_per_sm = 0;
-    int minb = 2;
-    uint32_t block = 0;
+    // launch configuration (environment overrides are read once)
+    bool configured = false;
+    uint32_t block = 128; int minb = 5; int blocks_per_sm_cap = 0;
+    uint32_t n_pipes = 1; uint64_t chunk_items = 12u << 20;
+    uint32_t arena_cap = 1024, hit_cap = 32;
+    uint32_t vote_slow_min = VOTE_SLOW_MIN_DEFAULT; int32_t vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
 };
 
 template <typename T>
@@ -453,35 +479,27 @@ extern "C" int hsa_occ_batch(const hsa_index_t *ix, int which, int layout, const
 }
 
 // ---------------------------------------------------------------------------------------------- workspace
-static int scratch_alloc(Scratch &s, uint32_t grid, uint32_t block, uint32_t arena_cap, uint32_t hit_cap, uint32_t max_len, bool wide)
+static int scratch_alloc(Scratch &s, uint32_t n_workers, uint32_t arena_cap, uint32_t hit_cap, uint32_t link_bytes)
 {
-    uint32_t nw = grid * block;
-    if (s.n_workers >= nw && s.arena_cap == arena_cap && s.hit_cap == hit_cap && s.max_len >= max_len) {
-        s.grid = grid; s.block = block;
-        return HSA_OK;
-    }
+    if (s.n_workers >= n_workers && s.arena_cap == arena_cap && s.hit_cap == hit_cap && s.link_bytes == link_bytes) return HSA_OK;
     s.release();
-    CU(cudaMalloc((void **)&s.arena, (size_t)nw * arena_cap * sizeof(u32x4)));
-    CU(cudaMalloc((void **)&s.links, (size_t)nw * arena_cap * (wide ? 4 : 2)));
-    s.wide = wide;
-    if (wide) CU(cudaMalloc((void **)&s.width, (size_t)nw * 2 * (max_len + 1) * sizeof(u32x2)));   // fused flow only
-    CU(cudaMalloc((void **)&s.hits, (size_t)nw * hit_cap * sizeof(Hit)));
-    s.grid = grid; s.block = block; s.n_workers = nw; s.arena_cap = arena_cap; s.hit_cap = hit_cap; s.max_len = max_len;
+    CU(cudaMalloc((void **)&s.arena, (size_t)n_workers * arena_cap * sizeof(u32x4)));
+    CU(cudaMalloc((void **)&s.links, (size_t)n_workers * arena_cap * link_bytes));
+    CU(cudaMalloc((void **)&s.hits, (size_t)n_workers * hit_cap * sizeof(Hit)));
+    s.n_workers = n_workers; s.arena_cap = arena_cap; s.hit_cap = hit_cap; s.link_bytes = link_bytes;
     return HSA_OK;
 }
 
 extern "C" int hsa_workspace_create(const hsa_index_t *ix, size_t max_reads, uint32_t max_len, size_t aln_capacity,
                                     hsa_workspace_t **out)
 {
-    (void)max_reads; (void)aln_capacity;
+    (void)max_reads; (void)aln_capacity; (void)max_len;
     if (!ix || !out) return fail(HSA_E_ARG, "null argument");
     CU(cudaSetDevice(ix->device));
     hsa_workspace *ws = new hsa_workspace();
     ws->idx = ix;
-    // statistics block, then 8 work-queue cursors, then 8 pass-2 list counters
-    CU(cudaMalloc((void **)&ws->counters, CNT_TOTAL * sizeof(unsigned long long)));
-    CU(cudaEventCreate(&ws->ev0)); CU(cudaEventCreate(&ws->ev1));
-    (void)max_len;
+    CU(cudaMalloc((void **)&ws->counters, CNT_ALLOC * sizeof(unsigned long long)));
+    CU(cudaEventCreateWithFlags(&ws->ev0, cudaEventDefault)); CU(cudaEventCreateWithFlags(&ws->ev1, cudaEventDefault));
     *out = ws;
     return HSA_OK;
 }
@@ -489,11 +507,12 @@ extern "C" int hsa_workspace_create(const hsa_index_t *ix, size_t max_reads, uin
 extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
 {
     if (!ws) return;
-    ws->fast.release(); ws->strict.release();
+    for (Pipe &p : ws->pipes) p.release();
+    ws->strict.release();
     cudaFree(ws->counters); cudaFree(ws->strict_list); cudaFree(ws->opts_dev); cudaFree(ws->len2opt_dev);
     cudaFree(ws->status_dev); cudaFree(ws->codes_dev); cudaFree(ws->off_dev); cudaFree(ws->len_dev);
     cudaFree(ws->tasks_dev); cudaFree(ws->n_aln_dev); cudaFree(ws->aln_off_dev); cudaFree(ws->aln_dev);
-    cudaFree(ws->width_out_dev); cudaFree(ws->bid_dev); cudaFree(ws->item_width); cudaFree(ws->next_list);
+    cudaFree(ws->width_out_dev); cudaFree(ws->bid_dev);
     if (ws->ev0) cudaEventDestroy(ws->ev0);
     if (ws->ev1) cudaEventDestroy(ws->ev1);
     delete ws;
@@ -502,25 +521,32 @@ extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
 extern "C" uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws) { return ws ? ws->last_launches : 0; }
 
 // ---------------------------------------------------------------------------------------------- launch
-// launch variants: (threads per block, min blocks per SM) -> register cap 65536 / (block * minb)
-static const void *search_fn(int block, int minb, bool wide)
+// Kernel variants.  FAST: 16-bit link halves (<= 2046 records per worker), bound bytes in shared memory
+// (FAST_ROWS: in the rows, for reads too long for shared memory).  LARGE: 32-bit halves, 64-thread blocks.
+enum Variant { V_FAST = 0, V_FAST_ROWS = 1, V_LARGE = 2 };
+
+static const void *search_fn(Variant v, int block, int minb)
 {
-    if (wide) return (const void *)search_kernel<2, 256, 1, uint32_t, true>;  // large-capacity (strict), fused flow
+    if (v == V_LARGE) return (const void *)search_kernel<64, 1, uint64_t, false>;
+    if (v == V_FAST_ROWS) return block == 128 ? (const void *)search_kernel<128, 4, uint32_t, false>
+                                              : (const void *)search_kernel<256, 2, uint32_t, false>;
     if (block == 128) {
         switch (minb) {
-        case 4: return (const void *)search_kernel<2, 128, 4, uint16_t, false>;
-        case 6: return (const void *)search_kernel<2, 128, 6, uint16_t, false>;
-        default: return (const void *)search_kernel<2, 128, 5, uint16_t, false>;
+        case 3: return (const void *)search_kernel<128, 3, uint32_t, true>;
+        case 4: return (const void *)search_kernel<128, 4, uint32_t, true>;
+        case 6: return (const void *)search_kernel<128, 6, uint32_t, true>;
+        case 8: return (const void *)search_kernel<128, 8, uint32_t, true>;
+        default: return (const void *)search_kernel<128, 5, uint32_t, true>;
         }
     }
     switch (minb) {
-    case 3: return (const void *)search_kernel<2, 256, 3, uint16_t, false>;
-    case 4: return (const void *)search_kernel<2, 256, 4, uint16_t, false>;
-    default: return (const void *)search_kernel<2, 256, 2, uint16_t, false>;
+    case 3: return (const void *)search_kernel<256, 3, uint32_t, true>;
+    case 4: return (const void *)search_kernel<256, 4, uint32_t, true>;
+    default: return (const void *)search_kernel<256, 2, uint32_t, true>;
     }
 }
 
-struct Batch {                      // everything one launch needs, device pointers
+struct Batch {                      // everything one batch needs, device pointers
     uint32_t kind = 0, n_groups = 0, n_items = 0, max_len = 0, n_opts = 0, n_buckets = 1, max_seed_len = 0;
     int32_t filter_max_n = 0;
     const uint8_t *codes = nullptr; const Task *tasks = nullptr;
@@ -528,18 +554,6 @@ struct Batch {                      // everything one launch needs, device point
     int32_t *n_aln = nullptr; uint64_t *aln_off = nullptr; uint32_t *aln = nullptr; uint64_t aln_cap = 0;
     u32x2 *width_out = nullptr; int32_t *bid_out = nullptr;
 };
-
-static void fill_params(Params &P, hsa_workspace *ws, const Batch &b)
-{
-    memset(&P, 0, sizeof(P));
-    P.ix = ws->idx->ix; P.codes = b.codes; P.kind = b.kind;
-    P.tasks = b.tasks; P.read_off = b.read_off; P.read_len = b.read_len;
-    P.opts = ws->opts_dev; P.n_opts = b.n_opts; P.len2opt = ws->len2opt_dev; P.max_len = b.max_len;
-    P.filter_max_n = b.filter_max_n; P.n_buckets = b.n_buckets;
-    P.n_aln = b.n_aln; P.aln_off = b.aln_off; P.status = ws->status_dev; P.aln = b.aln; P.aln_cap = b.aln_cap;
-    P.counters = ws->counters; P.strict_list = ws->strict_list;
-    P.width_out = b.width_out; P.bid_out = b.bid_out;
-}
 
 static void trace_mark(hsa_workspace *ws, const char *name, cudaStream_t stream)
 {
@@ -553,141 +567,163 @@ static void trace_mark(hsa_workspace *ws, const char *name, cudaStream_t stream)
 static void trace_dump(hsa_workspace *ws, const unsigned long long *cnt_all)
 {
     if (ws->trace <= 0) return;
-    cudaEvent_t prev = ws->ev0;
     fprintf(stderr, "[hsa_b200 trace]");
     for (size_t i = 0; i < ws->trace_ev.size(); ++i) {
         float t = 0;
-        cudaEventElapsedTime(&t, prev, ws->trace_ev[i]);
-        fprintf(stderr, " %s=%.3fms", ws->trace_name[i], t);
-        if (prev != ws->ev0) cudaEventDestroy(prev);
-        prev = ws->trace_ev[i];
+        cudaEventElapsedTime(&t, ws->ev0, ws->trace_ev[i]);     // completion time since the batch started
+        fprintf(stderr, " %s@%.2f", ws->trace_name[i], t);
+        cudaEventDestroy(ws->trace_ev[i]);
     }
-    if (prev != ws->ev0) cudaEventDestroy(prev);
     ws->trace_ev.clear(); ws->trace_name.clear();
     if (cnt_all)
-        fprintf(stderr, " | steps=%llu warp_iters=%llu lane_occupancy=%.3f max_item_steps=%llu pops=%llu lookups=%llu",
+        fprintf(stderr, " | steps=%llu warp_iters=%llu lanes_per_step=%.2f max_item_steps=%llu pops=%llu lookups=%llu",
                 cnt_all[CNT_STEPS], cnt_all[CNT_DIAG_WARP_ITERS],
-                cnt_all[CNT_DIAG_WARP_ITERS] ? (double)cnt_all[CNT_STEPS] / (32.0 * (double)cnt_all[CNT_DIAG_WARP_ITERS]) : 0.0,
+                cnt_all[CNT_DIAG_WARP_ITERS] ? (double)cnt_all[CNT_STEPS] / (double)cnt_all[CNT_DIAG_WARP_ITERS] : 0.0,
                 cnt_all[CNT_DIAG_MAX_ITEM_STEPS], cnt_all[CNT_POPS], cnt_all[CNT_LOOKUPS]);
     fprintf(stderr, "\n");
 }
 
-static int launch_search(hsa_workspace *ws, Params &P, Scratch &sc, cudaStream_t stream)
+static int configure(hsa_workspace *ws)
 {
-    P.arena = sc.arena; P.links = sc.links; P.arena_cap = sc.arena_cap;
-    P.width = sc.width;
-    if (sc.wide) { P.width_stride = 2 * (sc.max_len + 1); P.max_len = sc.max_len; }
-    P.hits = sc.hits; P.hit_cap = sc.hit_cap;
-    size_t smem = (size_t)P.n_opts * sizeof(DevOpt) + (size_t)P.n_buckets * sc.block * (sc.wide ? 4 : 2);
-    const void *fn = search_fn((int)sc.block, ws->minb, sc.wide);
+    if (ws->configured) return HSA_OK;
+    ws->block = (uint32_t)env_long("HSA_B200_BLOCK", 128);
+    if (ws->block != 128) ws->block = 256;
+    ws->minb = (int)env_long("HSA_B200_MINB", ws->block == 128 ? 5 : 2);
+    ws->blocks_per_sm_cap = (int)env_long("HSA_B200_BLOCKS_PER_SM", 0);
+    ws->n_pipes = (uint32_t)std::min<long>(MAX_PIPES, std::max<long>(1, env_long("HSA_B200_PIPES", 1)));
+    ws->chunk_items = (uint64_t)std::max<long>(6 * 1024, env_long("HSA_B200_CHUNK", 12 << 20));
+    ws->chunk_items -= ws->chunk_items % 6;
+    ws->arena_cap = (uint32_t)std::min<long>(2046, std::max<long>(16, env_long("HSA_B200_ARENA_CAP", 1024)));   // 11-bit links
+    ws->hit_cap = (uint32_t)std::max<long>(1, env_long("HSA_B200_HIT_CAP", 32));
+    ws->vote_slow_min = (uint32_t)std::max<long>(1, env_long("HSA_B200_SLOW_MIN", VOTE_SLOW_MIN_DEFAULT));
+    ws->vote_pop_bias = (int32_t)env_long("HSA_B200_POP_BIAS", VOTE_POP_BIAS_DEFAULT);
+    ws->configured = true;
+    return HSA_OK;
+}
+
+// One chunk of work items through the split pipeline on `stream`:
+//   width(pass 1) -> search(pass 1) [-> width(pass 2) -> search(pass 2)]
+// Pass 2 exists only for whole reads: the reads whose reverse-complement strand found nothing are appended to a
+// device-side list by the pass-1 search kernel, and the pass-2 kernels read the list length from device memory,
+// so no host synchronisation separates the four launches.
+static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, int pipe_slot, Variant v,
+                       const uint32_t *work_list, uint32_t work_base, uint32_t n_work, cudaStream_t stream)
+{
+    const hsa_index *ix = ws->idx;
+    const bool large = v == V_LARGE;
+    const uint32_t block = large ? 64u : ws->block;
+    const size_t smem = (size_t)P.smem_opts_bytes + (size_t)block * P.smem_lane_stride;
+    const void *fn = search_fn(v, (int)block, ws->minb);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)block, smem));
+    if (occ < 1) return fail(HSA_E_CUDA, "search kernel does not fit on an SM");
+    if (!large && ws->blocks_per_sm_cap > 0 && occ > ws->blocks_per_sm_cap) occ = ws->blocks_per_sm_cap;
+    uint32_t grid_full = (uint32_t)ix->sm_count * (uint32_t)occ;
+    if (large) grid_full = std::min<uint32_t>(grid_full, 32);           // 2048 workers x ~6.4 MB of stack each
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(grid_full, (n_work + block - 1) / block));
+    int rc;
+    if ((rc = scratch_alloc(pipe.sc, grid_full * block, large ? (1u << 18) : ws->arena_cap, large ? 4096u : ws->hit_cap,
+                            large ? 8u : 4u))) return rc;
+    if ((rc = ensure(pipe.rows, pipe.rows_cap, (size_t)n_work * P.row_stride))) return rc;
+    if (b.kind == KIND_WHOLE && (rc = ensure(pipe.next_list, pipe.next_cap, (size_t)n_work + 1))) return rc;
+
+    unsigned long long *slots = ws->counters + CNT_PIPE0 + 4 * pipe_slot;
+    CU(cudaMemsetAsync(slots, 0, 4 * sizeof(unsigned long long), stream));
+    P.rows = pipe.rows;
+    P.arena = pipe.sc.arena; P.links = pipe.sc.links; P.arena_cap = pipe.sc.arena_cap;
+    P.hits = pipe.sc.hits; P.hit_cap = pipe.sc.hit_cap;
+    P.pass = 1; P.work_list = work_list; P.work_base = work_base; P.n_work = n_work; P.n_work_dev = nullptr;
+    P.next_list = pipe.next_list; P.next_count = reinterpret_cast<uint32_t *>(slots + 2);
+    P.cursor = slots;
+    const uint32_t wgrid = std::max<uint32_t>(1, std::min<uint32_t>((n_work + 255) / 256, (uint32_t)ix->sm_count * 8));
     void *args[] = {(void *)&P};
-    CU(cudaLaunchKernel(fn, dim3(sc.grid), dim3(sc.block), args, smem, stream));
-    ++ws->last_launches;
-    trace_mark(ws, sc.wide ? "search(strict)" : "search", stream);
-    return HSA_OK;
-}
-
-static int launch_width(hsa_workspace *ws, Params &P, uint32_t grid, cudaStream_t stream)
-{
-    size_t smem = (size_t)P.n_opts * sizeof(DevOpt);
-    width_kernel<<<grid, 256, smem, stream>>>(P);
+    width_kernel<<<wgrid, 256, P.smem_opts_bytes, stream>>>(P);
     CU(cudaGetLastError());
-    ++ws->last_launches;
-    trace_mark(ws, "width", stream);
+    ++ws->last_launches; trace_mark(ws, "width1", stream);
+    if (b.kind == KIND_WIDTH) return HSA_OK;
+    CU(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream));
+    ++ws->last_launches; trace_mark(ws, large ? "search1L" : "search1", stream);
+    if (b.kind == KIND_WHOLE) {
+        P.pass = 2; P.work_list = pipe.next_list; P.work_base = 0; P.n_work_dev = P.next_count;
+        P.next_list = nullptr; P.next_count = nullptr; P.cursor = slots + 1;
+        width_kernel<<<wgrid, 256, P.smem_opts_bytes, stream>>>(P);
+        CU(cudaGetLastError());
+        ++ws->last_launches; trace_mark(ws, "width2", stream);
+        CU(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream));
+        ++ws->last_launches; trace_mark(ws, large ? "search2L" : "search2", stream);
+    }
     return HSA_OK;
 }
 
-// Runs one batch whose inputs/outputs are already on the device.  `sync` selects whether the call waits
-// and handles strict re-runs (host-buffer entry points) or just enqueues (device entry point).
-//
-// Split pipeline per chunk of groups:   width(pass 1) -> search(pass 1) [-> width(pass 2) -> search(pass 2)]
-// Pass 2 exists only for whole reads: the reads whose reverse-complement strand found nothing are appended
-// to a device-side list by the pass-1 search kernel, and the pass-2 kernels read the list length from
-// device memory, so no host synchronisation separates the four launches.
+// Runs one batch whose inputs/outputs are already on the device.  `sync` selects whether the call waits and
+// handles large-capacity re-runs (host-buffer entry points) or just enqueues (device entry point).
+// The batch is cut into chunks of work items that are issued round-robin on `n_pipes` internal streams, so the
+// serial tail of one chunk's persistent kernels (a few reads take > 10^4 steps) overlaps the next chunk's bulk.
 static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, bool sync, uint64_t stats[CNT_N], float *ms)
 {
     const hsa_index *ix = ws->idx;
     CU(cudaSetDevice(ix->device));
+    int rc;
+    if ((rc = configure(ws))) return rc;
     ws->last_launches = 0;
-    if (ws->trace < 0) ws->trace = sync ? (int)env_long("HSA_B200_TRACE", 0) : 0;
-    if (!ws->block) {
-        ws->block = (uint32_t)env_long("HSA_B200_BLOCK", 128);
-        if (ws->block != 128) ws->block = 256;
-        ws->minb = (int)env_long("HSA_B200_MINB", ws->block == 128 ? 5 : 2);
-    }
-    const uint32_t block = ws->block;
-    size_t smem = (size_t)b.n_opts * sizeof(DevOpt) + (size_t)b.n_buckets * block * sizeof(uint16_t);
-    if (smem > 200 * 1024) return fail(HSA_E_ARG, "option table too large for shared memory");
-    if (!ws->blocks_per_sm) {
-        int occ = 0;
-        const void *fn = search_fn((int)block, ws->minb, false);
-        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)block, smem));
-        if (occ < 1) return fail(HSA_E_CUDA, "search kernel does not fit on an SM");
-        ws->blocks_per_sm = (int)env_long("HSA_B200_BLOCKS_PER_SM", occ);
-        if (ws->blocks_per_sm > occ) ws->blocks_per_sm = occ;
-    }
+    if (ws->trace < 0) ws->trace = (int)env_long("HSA_B200_TRACE", 0);
+    const int trace_saved = ws->trace;
+    if (!sync) ws->trace = 0;
+
     const uint32_t items_per_group = b.kind == KIND_SEEDS ? 6u : 1u;
     const uint64_t n_work_total = (uint64_t)b.n_groups * items_per_group;
-    uint32_t grid_full = (uint32_t)(ix->sm_count * ws->blocks_per_sm);
-    uint32_t grid = (uint32_t)std::min<uint64_t>(grid_full, (n_work_total + block - 1) / block);
-    if (grid == 0) grid = 1;
-    uint32_t arena_cap = (uint32_t)env_long("HSA_B200_ARENA_CAP", 1024), hit_cap = (uint32_t)env_long("HSA_B200_HIT_CAP", 32);
-    if (arena_cap > 4094) arena_cap = 4094;          // 12-bit links, 0xFFF = nil
-    int rc;
-    if ((rc = scratch_alloc(ws->fast, grid, block, arena_cap, hit_cap, 0, false))) return rc;
-    ws->fast.grid = grid;
+    const uint32_t seed_cap = (b.kind == KIND_TASKS || b.kind == KIND_WHOLE) && b.max_seed_len ? b.max_seed_len + 1 : 0;
     if ((rc = ensure(ws->status_dev, ws->status_cap, (size_t)b.n_items + 1))) return rc;
     if ((rc = ensure(ws->strict_list, ws->strict_list_cap, (size_t)n_work_total + 1))) return rc;
 
-    // per-item width buffers: width_back[max_len+1] then width_seed[seed_cap]
-    uint32_t seed_cap = 0;
-    if (b.kind == KIND_TASKS || b.kind == KIND_WHOLE) seed_cap = b.max_seed_len + 1;
-    const uint32_t wstride = (b.max_len + 1) + seed_cap + 1;        // + one slot for the item's width lookup count
-    const uint64_t budget_entries = (uint64_t)env_long("HSA_B200_WIDTH_MB", 16384) * (1ull << 20) / sizeof(u32x2);
-    uint64_t chunk_items = std::max<uint64_t>(budget_entries / wstride, 6);
-    chunk_items -= chunk_items % 6;
-    uint32_t chunk_groups = (uint32_t)std::min<uint64_t>(b.n_groups, chunk_items / items_per_group);
-    if (b.kind != KIND_WIDTH) {
-        if ((rc = ensure(ws->item_width, ws->item_width_cap, (size_t)chunk_groups * items_per_group * wstride))) return rc;
-        if (b.kind == KIND_WHOLE && (rc = ensure(ws->next_list, ws->next_list_cap, (size_t)chunk_groups + 1))) return rc;
-    }
-
-    CU(cudaMemsetAsync(ws->counters, 0, CNT_TOTAL * sizeof(unsigned long long), stream));
-    CU(cudaEventRecord(ws->ev0, stream));
     Params P;
-    fill_params(P, ws, b);
-    P.item_width = ws->item_width; P.item_width_stride = wstride;
-    uint32_t cursor_slot = 0;
-    for (uint32_t g0 = 0; g0 < b.n_groups; g0 += chunk_groups) {
-        const uint32_t ng = std::min(chunk_groups, b.n_groups - g0);
-        const uint32_t nw = ng * items_per_group;
-        const uint32_t wgrid = std::max<uint32_t>(1, std::min<uint32_t>((nw + 255) / 256, (uint32_t)ix->sm_count * 8));
-        // cursors live behind the statistics block; each launch gets a fresh one (slots are recycled per batch)
-        P.pass = 1; P.group_base = g0; P.n_groups = nw; P.n_groups_dev = nullptr; P.group_list = nullptr;
-        P.next_list = ws->next_list; P.next_count = reinterpret_cast<uint32_t *>(ws->counters + CNT_N + 8 + (cursor_slot % 8));
-        if ((rc = launch_width(ws, P, wgrid, stream))) return rc;
-        if (b.kind == KIND_WIDTH) continue;
-        if (cursor_slot >= 8) {      // recycle cursor / list-count slots of earlier chunks
-            CU(cudaMemsetAsync(ws->counters + CNT_N + (cursor_slot % 8), 0, 8, stream));
-            CU(cudaMemsetAsync(ws->counters + CNT_N + 8 + (cursor_slot % 8), 0, 8, stream));
+    memset(&P, 0, sizeof(P));
+    P.ix = ix->ix; P.codes = b.codes; P.kind = b.kind;
+    P.tasks = b.tasks; P.read_off = b.read_off; P.read_len = b.read_len;
+    P.opts = ws->opts_dev; P.len2opt = ws->len2opt_dev; P.filter_max_n = b.filter_max_n;
+    P.n_aln = b.n_aln; P.aln_off = b.aln_off; P.status = ws->status_dev; P.aln = b.aln; P.aln_cap = b.aln_cap;
+    P.counters = ws->counters; P.strict_list = ws->strict_list;
+    P.width_out = b.width_out; P.bid_out = b.bid_out;
+    P.vote_slow_min = ws->vote_slow_min; P.vote_pop_bias = ws->vote_pop_bias;
+    // fast configuration: bound bytes in shared memory if a block's share leaves room for >= 4 blocks per SM
+    set_layout(P, b.max_len, seed_cap, b.n_buckets, b.n_opts, 2, true);
+    Variant v = V_FAST;
+    if ((size_t)P.smem_opts_bytes + (size_t)ws->block * P.smem_lane_stride > 56 * 1024) {
+        v = V_FAST_ROWS;
+        set_layout(P, b.max_len, seed_cap, b.n_buckets, b.n_opts, 2, false);
+    }
+    if ((size_t)P.smem_opts_bytes + (size_t)ws->block * P.smem_lane_stride > 200 * 1024)
+        return fail(HSA_E_ARG, "option table too large for shared memory");
+
+    CU(cudaMemsetAsync(ws->counters, 0, CNT_ALLOC * sizeof(unsigned long long), stream));
+    CU(cudaEventRecord(ws->ev0, stream));
+    const uint64_t chunk = std::min<uint64_t>(ws->chunk_items, std::max<uint64_t>(n_work_total, 1));
+    const uint32_t n_chunks = (uint32_t)((n_work_total + chunk - 1) / chunk);
+    const uint32_t n_pipes = std::min<uint32_t>(ws->n_pipes, std::max<uint32_t>(n_chunks, 1));
+    if (n_pipes > 1) {
+        for (uint32_t p = 0; p < n_pipes; ++p) {
+            Pipe &pp = ws->pipes[p];
+            if (!pp.stream) CU(cudaStreamCreateWithFlags(&pp.stream, cudaStreamNonBlocking));
+            if (!pp.done) CU(cudaEventCreateWithFlags(&pp.done, cudaEventDisableTiming));
+            CU(cudaStreamWaitEvent(pp.stream, ws->ev0, 0));
         }
-        P.cursor = ws->counters + CNT_N + (cursor_slot % 8);
-        if ((rc = launch_search(ws, P, ws->fast, stream))) return rc;
-        ++cursor_slot;
-        if (b.kind == KIND_WHOLE) {
-            const uint32_t *cnt2 = P.next_count;
-            P.pass = 2; P.group_list = ws->next_list; P.n_groups = ng; P.n_groups_dev = cnt2;
-            P.next_list = nullptr; P.next_count = nullptr;
-            if ((rc = launch_width(ws, P, wgrid, stream))) return rc;
-            if (cursor_slot >= 8) CU(cudaMemsetAsync(ws->counters + CNT_N + (cursor_slot % 8), 0, 8, stream));
-            P.cursor = ws->counters + CNT_N + (cursor_slot % 8);
-            if ((rc = launch_search(ws, P, ws->fast, stream))) return rc;
-            ++cursor_slot;
+    }
+    uint32_t c = 0;
+    for (uint64_t w0 = 0; w0 < n_work_total; w0 += chunk, ++c) {
+        const uint32_t nw = (uint32_t)std::min<uint64_t>(chunk, n_work_total - w0);
+        Pipe &pp = ws->pipes[c % n_pipes];
+        cudaStream_t s = n_pipes > 1 ? pp.stream : stream;
+        if ((rc = issue_chunk(ws, b, P, pp, (int)(c % n_pipes), v, nullptr, (uint32_t)w0, nw, s))) return rc;
+    }
+    if (n_pipes > 1) {
+        for (uint32_t p = 0; p < n_pipes; ++p) {
+            CU(cudaEventRecord(ws->pipes[p].done, ws->pipes[p].stream));
+            CU(cudaStreamWaitEvent(stream, ws->pipes[p].done, 0));
         }
     }
     CU(cudaEventRecord(ws->ev1, stream));
+    ws->trace = trace_saved;
     if (!sync) return HSA_OK;
 
     unsigned long long cnt[CNT_TOTAL];
@@ -698,21 +734,18 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
     CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
     *ms = t;
     if (cnt[CNT_BAD]) return fail(HSA_E_ARG, "a score exceeded the bucket table (internal sizing error)");
-    uint64_t n_strict = cnt[CNT_STRICT];
+    const uint64_t n_strict = cnt[CNT_STRICT];
     if (n_strict) {
-        // re-run the groups that ran out of stack / hit capacity with the large-capacity, fused configuration
-        uint32_t sblock = 64, sgrid = (uint32_t)std::min<uint64_t>((n_strict + sblock - 1) / sblock, (uint64_t)ix->sm_count * 2);
-        if ((rc = scratch_alloc(ws->strict, sgrid, sblock, 1u << 18, 4096, b.max_len, true))) return rc;
+        // re-run the items that ran out of stack / hit capacity through the same pipeline with the large-capacity kernel
         uint32_t *list_dev = nullptr;
         CU(cudaMalloc((void **)&list_dev, n_strict * 4));
         CU(cudaMemcpyAsync(list_dev, ws->strict_list, n_strict * 4, cudaMemcpyDeviceToDevice, stream));
-        CU(cudaMemsetAsync(ws->counters + CNT_STRICT, 0, 16, stream));
-        CU(cudaMemsetAsync(ws->counters + CNT_N, 0, 8, stream));
-        Params S;
-        fill_params(S, ws, b);
-        S.group_list = list_dev; S.n_groups = (uint32_t)n_strict; S.cursor = ws->counters + CNT_N;
+        CU(cudaMemsetAsync(ws->counters + CNT_STRICT, 0, 2 * sizeof(unsigned long long), stream));
+        Params S = P;
+        set_layout(S, b.max_len, seed_cap, b.n_buckets, b.n_opts, 4, false);
         CU(cudaEventRecord(ws->ev0, stream));
-        if ((rc = launch_search(ws, S, ws->strict, stream))) { cudaFree(list_dev); return rc; }
+        rc = issue_chunk(ws, b, S, ws->strict, MAX_PIPES, V_LARGE, list_dev, 0, (uint32_t)n_strict, stream);
+        if (rc) { cudaFree(list_dev); return rc; }
         CU(cudaEventRecord(ws->ev1, stream));
         unsigned long long cnt2[CNT_TOTAL];
         CU(cudaMemcpyAsync(cnt2, ws->counters, sizeof(cnt2), cudaMemcpyDeviceToHost, stream));
@@ -729,6 +762,7 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
     stats[CNT_STRICT] = n_strict;
     return HSA_OK;
 }
+
 
 // ---------------------------------------------------------------------------------------------- results
 static int result_reserve(hsa_result_t *r, size_t n_items, size_t n_aln)
@@ -831,7 +865,7 @@ static int upload_reads(hsa_workspace *ws, const uint8_t *codes, const uint64_t 
 }
 
 static int upload_opts(hsa_workspace *ws, const std::vector<hsa_gap_opt_t> &opts, uint32_t max_len, Batch *bt,
-                       const std::vector<uint16_t> *len2opt)
+                       const std::vector<uint16_t> *len2opt, cudaStream_t stream)
 {
     uint32_t *n_buckets = &bt->n_buckets;
     bt->max_seed_len = 0;
@@ -846,12 +880,12 @@ static int upload_opts(hsa_workspace *ws, const std::vector<hsa_gap_opt_t> &opts
         to_devopt(opts[i], d[i]);
     }
     if ((rc = ensure(ws->opts_dev, ws->opts_cap, d.size()))) return rc;
-    CU(cudaMemcpyAsync(ws->opts_dev, d.data(), d.size() * sizeof(DevOpt), cudaMemcpyHostToDevice, ix->stream));
+    CU(cudaMemcpyAsync(ws->opts_dev, d.data(), d.size() * sizeof(DevOpt), cudaMemcpyHostToDevice, stream));
     if (len2opt) {
         if ((rc = ensure(ws->len2opt_dev, ws->len2opt_cap, len2opt->size()))) return rc;
-        CU(cudaMemcpyAsync(ws->len2opt_dev, len2opt->data(), len2opt->size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ix->stream));
+        CU(cudaMemcpyAsync(ws->len2opt_dev, len2opt->data(), len2opt->size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
     }
-    CU(cudaStreamSynchronize(ix->stream));          // d / len2opt are stack-local
+    CU(cudaStreamSynchronize(stream));              // d / len2opt are stack-local
     return HSA_OK;
 }
 
@@ -903,7 +937,7 @@ extern "C" int hsa_match_gap_batch(const hsa_index_t *ix, const uint8_t *codes, 
     if (n_tasks == 0) { res->n_items = 0; res->n_aln_total = 0; return HSA_OK; }
     std::vector<hsa_gap_opt_t> ov(opts, opts + n_opts);
     Batch b;
-    if ((rc = upload_opts(ws, ov, max_len, &b, nullptr))) return rc;
+    if ((rc = upload_opts(ws, ov, max_len, &b, nullptr, ix->stream))) return rc;
     if ((rc = ensure(ws->codes_dev, ws->codes_cap, codes_bytes + 16))) return rc;
     if ((rc = ensure(ws->tasks_dev, ws->tasks_cap, n_tasks))) return rc;
     CU(cudaMemcpyAsync(ws->codes_dev, codes, codes_bytes, cudaMemcpyHostToDevice, ix->stream));
@@ -939,7 +973,7 @@ extern "C" int hsa_whole_reads(const hsa_index_t *ix, const uint8_t *codes, cons
     std::vector<hsa_gap_opt_t> opts; std::vector<uint16_t> l2o;
     Batch b;
     if ((rc = resolve_whole_opts(opt, keep_gape, lens, max_len, opts, l2o, &b.filter_max_n))) return rc;
-    if ((rc = upload_opts(ws, opts, max_len, &b, &l2o))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b, &l2o, ix->stream))) return rc;
     b.kind = KIND_WHOLE; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads; b.max_len = max_len;
     b.n_opts = (uint32_t)opts.size(); b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
     return run_and_fetch(ws, b, res);
@@ -956,7 +990,7 @@ extern "C" int hsa_splice_seeds(const hsa_index_t *ix, const uint8_t *codes, con
     so.mode &= ~HSA_MODE_GAPE; so.max_gapo = 0; so.max_gape = 0; so.max_diff = opt->max_seed_diff;
     std::vector<hsa_gap_opt_t> opts(1, so);
     Batch b;
-    if ((rc = upload_opts(ws, opts, max_len, &b, nullptr))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b, nullptr, ix->stream))) return rc;
     b.kind = KIND_SEEDS; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads * 6; b.max_len = max_len;
     b.n_opts = 1; b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
     return run_and_fetch(ws, b, res);
@@ -975,7 +1009,7 @@ extern "C" int hsa_cal_width_batch(const hsa_index_t *ix, const uint8_t *codes, 
     hsa_gap_opt_t o; hsa_gap_opt_default(&o); o.max_diff = 0;
     std::vector<hsa_gap_opt_t> opts(1, o);
     Batch b;
-    if ((rc = upload_opts(ws, opts, max_len, &b, nullptr))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b, nullptr, ix->stream))) return rc;
     if ((rc = ensure(ws->width_out_dev, ws->width_out_cap, total))) return rc;
     cudaFree(ws->bid_dev); ws->bid_dev = nullptr;
     CU(cudaMalloc((void **)&ws->bid_dev, n * sizeof(int32_t)));
@@ -1010,13 +1044,13 @@ extern "C" int hsa_whole_reads_device(const hsa_index_t *ix, hsa_workspace_t *ws
     uint32_t max_len = *std::max_element(lens.begin(), lens.end());
     std::vector<hsa_gap_opt_t> opts; std::vector<uint16_t> l2o;
     Batch b;
+    cudaStream_t s = (cudaStream_t)stream;          // NULL = the legacy default stream, as everywhere in CUDA
     if ((rc = resolve_whole_opts(opt, keep_gape, lens, max_len, opts, l2o, &b.filter_max_n))) return rc;
-    if ((rc = upload_opts(ws, opts, max_len, &b, &l2o))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b, &l2o, s))) return rc;
     b.kind = KIND_WHOLE; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads; b.max_len = max_len;
     b.n_opts = (uint32_t)opts.size(); b.codes = codes_dev; b.read_off = off_dev; b.read_len = len_dev;
     b.n_aln = n_aln_dev; b.aln_off = aln_off_dev; b.aln = reinterpret_cast<uint32_t *>(aln_dev); b.aln_cap = aln_capacity;
     uint64_t stats[CNT_N]; float ms = 0;
-    cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
     if ((rc = run_batch(ws, b, s, false, stats, &ms))) return rc;
     if (stats_dev)
         CU(cudaMemcpyAsync(stats_dev, ws->counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));

@@ -1,7 +1,7 @@
-// hsa_core.cuh -- the inexact-search state machine, one logical worker per CUDA thread.
+// hsa_core.cuh -- the inexact-search state machine, one search per CUDA thread, phase-voted per warp.
 //
 // The file is plain C++ with a handful of macros so that the SAME source is compiled
-//   * by nvcc for sm_100a (the product: hsa_kernels.cu), and
+//   * by nvcc for sm_100a (the product: hsa_b200.cu), and
 //   * by g++ for tests/emu (a host emulation used ONLY by the CPU test-suite to check the logic
 //     against the oracle where no GPU exists; it is never linked into the product library).
 //
@@ -17,19 +17,24 @@
 // How it differs from the reference in structure (not in results) -- see DESIGN.md:
 //   * device index layout: one 32-byte sector per 64 BWT symbols = {occ[4] at block start, 4 packed words},
 //     so one occ lookup touches exactly one sector instead of two (+ a major-table row);
-//   * every step of every phase (width pass, node expansion, exact-match tail) is the same
-//     "occ4 at k and at l+1" memory operation, so divergent workers still share the load/popcount code;
-//   * the score-bucketed stack is a per-worker arena of 16-byte records threaded into per-bucket LIFO
-//     lists, bucket heads in shared memory, non-empty buckets in a 128-bit register mask;
-//   * children are pushed LAZILY: the (up to 4) deletion children of a node are one "family" record and
-//     its (up to 4) mismatch children another, each holding the parent's interval and a 4-bit mask of the
-//     children that exist.  A child is materialised -- one more occ4 pair at the parent's interval -- only
-//     when it is actually popped AND survives the reference's pop-time pruning (bwtgap.c:161-173).  About
-//     nine of ten pushed entries of the reference are never popped, so this removes most stack traffic;
+//   * a search is a per-lane state machine with four kinds of step -- POP (take the next stack entry and
+//     apply the reference's pop-time pruning), LOOKUP (one "occ4 at k and at l+1" pair: node expansion,
+//     bwt_match_exact step, or materialisation of a lazily stored child), HIT (record a hit, gap_shadow)
+//     and END/START (results out, next work item in).  A warp executes ONE kind of step per trip, chosen by
+//     vote (phase_vote), so that all participating lanes run the same instruction stream;
+//   * ONE 16-byte stack record per node expansion: the expanded node's interval and counts.  Its children
+//     (bwtgap.c:267-325) are two "memberships" of that record -- the gap children (insertion + up to four
+//     deletions) in the bucket of score+gap, the mismatch children in the bucket of score+s_mm -- each a
+//     5-bit mask in the record's link word.  A child is materialised (one more occ4 pair at the parent's
+//     interval) only when it is popped AND survives the pop-time pruning (bwtgap.c:161-173).  About nine of
+//     ten entries the reference pushes are never popped, so this removes most stack traffic;
 //   * the lowest-score child (the exact-match extension) is never pushed: it is the next node popped by
 //     construction (pushed last into the currently-lowest bucket), so it is carried in registers;
 //   * children whose score already exceeds best_score + s_mm after the first hit are only counted
-//     (they can never be popped, bwtgap.c:158-159), keeping the max_entries test exact.
+//     (they can never be popped, bwtgap.c:158-159), keeping the max_entries test exact;
+//   * of bwt_width_t only what the hot path compares is kept close: one byte per position
+//     (min(bid,63) | (w[i-1]==w[i]) << 7) in shared memory; the 32-bit w values stay in the item's row in
+//     global memory for gap_shadow.
 #pragma once
 #include <stdint.h>
 
@@ -45,6 +50,18 @@
 #else
 #define HSA_HD inline
 #define HSA_D  inline
+#endif
+
+// Per-block shared memory (device) / per-run scratch (host emulation): option table, then per lane the bucket
+// heads and the bound bytes.
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) unsigned char hsa_smem[];
+#endif
+#if defined(__CUDA_ARCH__)
+#define HSA_SMEM hsa_smem
+#else
+static thread_local unsigned char *hsa_smem_host = nullptr;
+#define HSA_SMEM hsa_smem_host
 #endif
 
 namespace hsa {
@@ -274,41 +291,71 @@ struct Params {
     DevIndex ix;
     const uint8_t *codes;           // base codes, 0..3, N = 4
     uint32_t kind;
-    uint32_t n_groups;              // work items: tasks (KIND_TASKS) or reads (KIND_WHOLE / KIND_SEEDS)
-    const uint32_t *group_list;     // optional indirection (strict re-runs): work index -> group id
+    uint32_t pass;                  // KIND_WHOLE: 1 = reverse-complement strand pass, 2 = forward strand pass
+    uint32_t n_work;                // work items of this launch ...
+    const uint32_t *n_work_dev;     // ... or, if set, read from device memory (pass 2)
+    const uint32_t *work_list;      // optional: work index -> item id (pass-2 list, large-capacity re-runs)
+    uint32_t work_base;             // item id of work index 0 when there is no list
     const Task *tasks;              // KIND_TASKS
-    const uint64_t *read_off;       // KIND_WHOLE / KIND_SEEDS
+    const uint64_t *read_off;       // KIND_WHOLE / KIND_SEEDS / KIND_WIDTH
     const uint32_t *read_len;
-    const DevOpt *opts;             // option table (device memory; staged to shared memory by the kernel)
+    const DevOpt *opts;             // option table (device memory; staged to shared memory by the kernels)
     uint32_t n_opts;
-    const uint16_t *len2opt;        // KIND_WHOLE: read length -> opts[] index ; KIND_SEEDS: unused (opts[0])
-    uint32_t max_len;               // longest read in the batch
+    const uint16_t *len2opt;        // KIND_WHOLE: read length -> opts[] index ; otherwise unused
+    uint32_t max_len;               // longest searched sequence in the batch
     int32_t  filter_max_n;          // KIND_WHOLE: local_opt.max_diff of bwtaln.c:273-274 (N filter :314-317)
+    // per-work-item rows written by the width kernel (row of work index w at rows + w * row_stride):
+    //   [0, 4*(max_len+1))            w of width_back, uint32 each
+    //   [row_bid_off, +max_len+1)     bound bytes of width_back: min(bid,63) | (w[i-1]==w[i]) << 7
+    //   [row_seed_off, +seed_cap)     bound bytes of width_seed (HSA_SEED_TAIL only)
+    //   [row_tail_off, +8)            {occ lookups of the width pass, flags (bit 0: read filtered)}
+    uint8_t *rows;
+    uint32_t row_stride, row_bid_off, row_seed_off, row_tail_off;
     // worker-private scratch, indexed by worker slot
-    u32x4 *arena;  void *links;  uint32_t arena_cap;         // stack records + per-bucket / free-list links (LinkT)
-    u32x2 *width;  uint32_t width_stride;                     // [2*(max_len+1)] per worker: back, seed
+    u32x4 *arena;  void *links;  uint32_t arena_cap;
     Hit *hits;     uint32_t hit_cap;
     uint32_t n_buckets;             // size of the score-indexed head table (<= 128)
+    uint32_t smem_opts_bytes;       // shared memory: option table first ...
+    uint32_t smem_lane_stride;      // ... then per lane: heads[n_buckets], bound bytes back, bound bytes seed
+    uint32_t smem_bid_off, smem_seed_off;   // offsets of the bound bytes inside a lane's region
     // outputs
     int32_t  *n_aln;                // [n_items]
     uint64_t *aln_off;              // [n_items]
     uint8_t  *status;               // [n_items]
-    uint32_t *aln;                  // n_aln_cap x 9 words (== hsa_aln1_t)
+    uint32_t *aln;                  // aln_cap x 9 words (== hsa_aln1_t)
     uint64_t  aln_cap;
-    unsigned long long *counters;   // CNT_N
-    uint32_t *strict_list;          // groups that must be re-run with larger capacities
+    unsigned long long *counters;   // CNT_TOTAL
+    uint32_t *strict_list;          // items that must be re-run with larger capacities
     u32x2 *width_out;               // KIND_WIDTH: read r's len+1 entries at read_off[r] + r
     int32_t *bid_out;               // KIND_WIDTH: bwt_cal_width's return value per read
-    // split pipeline (width kernel -> search kernel, one strand per pass); unused by the fused worker
-    uint32_t pass;                  // KIND_WHOLE: 1 = reverse-complement strand pass, 2 = forward strand pass
-    uint32_t group_base;            // first group of this chunk (work index 0)
-    const uint32_t *n_groups_dev;   // if set, the number of work items is read from device memory (pass 2)
-    u32x2 *item_width;              // [work item][item_width_stride]: width_back, then width_seed
-    uint32_t item_width_stride;
     uint32_t *next_list;            // pass 1: reads without a hit are appended here ...
     uint32_t *next_count;           // ... and counted here (device memory)
     unsigned long long *cursor;     // atomic work-queue cursor of this launch
+    uint32_t vote_slow_min;         // phase_vote(): lanes that must wait for a SLOW step before one is run
+    int32_t  vote_pop_bias;         // phase_vote(): LOOKUP runs if n_lookup + bias >= n_pop
 };
+
+enum : uint32_t { ROW_FLAG_FILTERED = 1u };
+
+// Row / shared-memory geometry of one launch configuration (shared by the host code and the emulation).
+// seed_cap = longest width_seed in the batch + 1 (0 if none); head_bytes = 2 (fast kernel) or 4 (large capacity).
+HSA_HD void set_layout(Params &P, uint32_t max_len, uint32_t seed_cap, uint32_t n_buckets, uint32_t n_opts,
+                       uint32_t head_bytes, bool bids_smem)
+{
+    const uint32_t nb4 = (max_len + 1 + 3u) & ~3u, ns4 = (seed_cap + 3u) & ~3u;
+    P.max_len = max_len; P.n_buckets = n_buckets; P.n_opts = n_opts;
+    P.row_bid_off = 4u * (max_len + 1);
+    P.row_seed_off = P.row_bid_off + nb4;
+    P.row_tail_off = P.row_seed_off + ns4;
+    P.row_stride = (P.row_tail_off + 8u + 15u) & ~15u;
+    P.smem_opts_bytes = n_opts * (uint32_t)sizeof(DevOpt);
+    const uint32_t heads = (n_buckets * head_bytes + 3u) & ~3u;
+    P.smem_bid_off = heads;
+    P.smem_seed_off = heads + (bids_smem ? nb4 : 0u);
+    uint32_t stride = P.smem_seed_off + (bids_smem ? ns4 : 0u);
+    if (((stride >> 2) & 1u) == 0) stride += 4;         // odd number of words per lane: lanes spread over the banks
+    P.smem_lane_stride = stride;
+}
 
 // ---- tasks ------------------------------------------------------------------------------------------
 struct TaskDesc {                   // one bwt_match_gap call, resolved
@@ -324,37 +371,40 @@ HSA_HD uint32_t task_base(const TaskDesc &t, uint32_t p)
     return ld_ro_u8(t.rd + p);
 }
 
-// sub-task `sub` of group `gid`:  KIND_TASKS: the task itself;  KIND_WHOLE: sub 0 = reverse-complement strand,
-// sub 1 = forward strand (bwtaln.c:343);  KIND_SEEDS: sub = strand*3 + segment (bwtgap.c:797-812);  KIND_WIDTH.
-HSA_HD TaskDesc make_task(const Params &P, const DevOpt *opts, uint32_t gid, uint32_t sub)
+// Item ids:  KIND_TASKS: task index;  KIND_WHOLE: read index (the strand comes from P.pass: pass 1 = reverse
+// complement, pass 2 = forward, bwtaln.c:343);  KIND_SEEDS: read * 6 + strand * 3 + segment (bwtgap.c:797-812);
+// KIND_WIDTH: read index.
+HSA_HD uint32_t work_item(const Params &P, uint32_t w) { return P.work_list ? P.work_list[w] : P.work_base + w; }
+
+HSA_HD TaskDesc make_task(const Params &P, const DevOpt *opts, uint32_t item)
 {
     TaskDesc t;
     t.aln_start = t.aln_end = -1;
+    t.out_idx = item;
     if (P.kind == KIND_TASKS) {
-        const Task &k = P.tasks[gid];
+        const Task &k = P.tasks[item];
         t.rd = P.codes + k.read_off; t.rd_len = k.read_len; t.strand = k.strand; t.sub_off = k.sub_off; t.len = k.len;
-        t.wsrc_off = k.wsrc_off; t.seed_mode = k.seed_mode; t.opt_idx = k.opt_idx; t.out_idx = gid;
+        t.wsrc_off = k.wsrc_off; t.seed_mode = k.seed_mode; t.opt_idx = k.opt_idx;
     } else if (P.kind == KIND_WHOLE) {
-        t.rd = P.codes + P.read_off[gid]; t.rd_len = P.read_len[gid];
-        t.strand = 1 - sub;                                 // revcomp first (bwtaln.c:343)
+        t.rd = P.codes + P.read_off[item]; t.rd_len = P.read_len[item];
+        t.strand = P.pass == 2 ? 0u : 1u;                   // revcomp first (bwtaln.c:343)
         t.sub_off = 0; t.len = t.rd_len; t.wsrc_off = 0;
         t.opt_idx = P.len2opt[t.rd_len];
         t.seed_mode = (int32_t)t.rd_len > opts[t.opt_idx].seed_len ? SEED_TAIL : SEED_NONE;   // bwtaln.c:332,344
-        t.out_idx = gid;
     } else if (P.kind == KIND_WIDTH) {                      // bwt_cal_width alone (type 1), read as given
-        t.rd = P.codes + P.read_off[gid]; t.rd_len = P.read_len[gid];
-        t.strand = 0; t.sub_off = 0; t.len = t.rd_len; t.wsrc_off = 0; t.seed_mode = SEED_NONE; t.opt_idx = 0; t.out_idx = gid;
+        t.rd = P.codes + P.read_off[item]; t.rd_len = P.read_len[item];
+        t.strand = 0; t.sub_off = 0; t.len = t.rd_len; t.wsrc_off = 0; t.seed_mode = SEED_NONE; t.opt_idx = 0;
     } else {                                                // KIND_SEEDS, bwtgap.c:797-812
+        const uint32_t gid = item / 6, sub = item % 6;
         t.rd = P.codes + P.read_off[gid]; t.rd_len = P.read_len[gid];
-        uint32_t seg = sub % 3, sl = t.rd_len / 3;
+        const uint32_t seg = sub % 3, sl = t.rd_len / 3;
         t.strand = sub / 3;
         t.len = sl + (seg == 2 ? t.rd_len % 3 : 0);
         t.sub_off = seg * sl;
         t.wsrc_off = 0;                                     // width on the read PREFIX (bwtgap.c:807-808)
         t.seed_mode = SEED_ALIAS;                           // bwtgap.c:809
         t.opt_idx = 0;
-        t.out_idx = gid * 6 + sub;
-        t.aln_start = (int32_t)t.sub_off; t.aln_end = (int32_t)(t.sub_off + t.len - 1);
+        t.aln_start = (int32_t)t.sub_off; t.aln_end = (int32_t)(t.sub_off + t.len - 1);   // bwtgap.c:816-819
     }
     return t;
 }
@@ -388,11 +438,20 @@ HSA_HD uint32_t occ1_dev(const DevBwt &b, uint32_t index, uint32_t c)
     return base + (uint32_t)popc64(m0 & k0) + (uint32_t)popc64(m1 & k1);
 }
 
-// bwt_cal_width, type 1 (bwtaln.c:73-97, 113-114): `n` bases starting at strand-resolved position `src`.
-// Returns bid; *lookups += the BWTOccValue calls the reference issues.
-HSA_HD int32_t cal_width_dev(const DevIndex &ix, const TaskDesc &t, uint32_t src, uint32_t n, u32x2 *dst, uint64_t &lookups)
+// the bound byte of one bwt_width_t entry given the previous entry's w (0xFFFFFFFF for entry 0: never equal,
+// because w <= textLength + 1 < 2^32 - 1 for every index the uint32 SA coordinates can hold)
+HSA_HD uint8_t bound_byte(uint32_t bid, uint32_t w, uint32_t w_prev)
 {
-    uint32_t k = 0, l = ix.fwd.text_length;
+    return (uint8_t)((bid < 63u ? bid : 63u) | (w == w_prev ? 0x80u : 0u));
+}
+
+// bwt_cal_width, type 1 (bwtaln.c:73-97, 113-114): `n` bases starting at strand-resolved position `src`.
+// Writes any of: w_out[n+1] (uint32), b_out[n+1] (bound bytes), pair_out[n+1] (bwt_width_t).  Returns bid;
+// lookups += the BWTOccValue calls the reference issues.
+HSA_HD int32_t cal_width_dev(const DevIndex &ix, const TaskDesc &t, uint32_t src, uint32_t n,
+                             uint32_t *w_out, uint8_t *b_out, u32x2 *pair_out, uint32_t &lookups)
+{
+    uint32_t k = 0, l = ix.fwd.text_length, w_prev = 0xFFFFFFFFu;
     int32_t bid = 0;
     for (uint32_t j = 0; j < n; ++j) {
         const uint32_t c = task_base(t, src + j);
@@ -403,115 +462,164 @@ HSA_HD int32_t cal_width_dev(const DevIndex &ix, const TaskDesc &t, uint32_t src
             lookups += 2;
         }
         if (k > l || c > 3) { k = 0; l = ix.fwd.text_length; ++bid; }
-        u32x2 v; v.x = l - k + 1; v.y = (uint32_t)bid;
-        dst[j] = v;
+        const uint32_t w = l - k + 1;
+        if (w_out) w_out[j] = w;
+        if (b_out) b_out[j] = bound_byte((uint32_t)bid, w, w_prev);
+        if (pair_out) { u32x2 v; v.x = w; v.y = (uint32_t)bid; pair_out[j] = v; }
+        w_prev = w;
     }
-    u32x2 last; last.x = 0; last.y = (uint32_t)(++bid);
-    dst[n] = last;
+    ++bid;                                                  // bwtaln.c:113-114
+    if (w_out) w_out[n] = 0;
+    if (b_out) b_out[n] = bound_byte((uint32_t)bid, 0, w_prev);
+    if (pair_out) { u32x2 v; v.x = 0; v.y = (uint32_t)bid; pair_out[n] = v; }
     return bid;
 }
 
-// Split pipeline, width kernel body for work item `w`: resolves the task, applies the whole-read filters in
-// pass 1, writes width_back (+ width_seed) of the item.  A filtered read is marked by width[0].bid = ~0.
-HSA_HD void width_item(const Params &P, const DevOpt *opts, uint32_t w, uint64_t &lookups)
+// Width kernel body for work index `w`: resolves the task, applies the whole-read filters in pass 1 and writes
+// the item's row (w of width_back, bound bytes of width_back and width_seed, lookup count).
+HSA_HD void width_item(const Params &P, const DevOpt *opts, uint32_t w)
 {
-    uint32_t gid, sub;
-    if (P.kind == KIND_SEEDS) { gid = P.group_base + w / 6; sub = w % 6; }
-    else if (P.kind == KIND_WHOLE) { gid = P.pass == 2 ? P.group_list[w] : P.group_base + w; sub = P.pass == 2 ? 1 : 0; }
-    else { gid = P.group_base + w; sub = 0; }
-    const TaskDesc t = make_task(P, opts, gid, sub);
+    const uint32_t item = work_item(P, w);
+    const TaskDesc t = make_task(P, opts, item);
+    uint32_t lk = 0;
     if (P.kind == KIND_WIDTH) {                              // hsa_cal_width_batch: straight to the caller's layout
-        P.bid_out[gid] = cal_width_dev(P.ix, t, 0, t.len, P.width_out + P.read_off[gid] + gid, lookups);
+        P.bid_out[item] = cal_width_dev(P.ix, t, 0, t.len, nullptr, nullptr, P.width_out + P.read_off[item] + item, lk);
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&P.counters[CNT_LOOKUPS], (unsigned long long)lk);
+#else
+        P.counters[CNT_LOOKUPS] += lk;
+#endif
         return;
     }
-    u32x2 *wb = P.item_width + (size_t)w * P.item_width_stride;
+    uint8_t *row = P.rows + (size_t)w * P.row_stride;
+    uint32_t *tail = reinterpret_cast<uint32_t *>(row + P.row_tail_off);
     if (P.kind == KIND_WHOLE && P.pass == 1 && read_filtered(t.rd, t.rd_len, P.filter_max_n)) {
-        u32x2 v; v.x = 0; v.y = 0xFFFFFFFFu;
-        wb[0] = v;
+        tail[0] = 0; tail[1] = ROW_FLAG_FILTERED;
         P.n_aln[t.out_idx] = 0; P.aln_off[t.out_idx] = 0; P.status[t.out_idx] = STATUS_OK;
         return;
     }
-    uint64_t lk = 0;
-    cal_width_dev(P.ix, t, t.wsrc_off, t.len, wb, lk);
+    cal_width_dev(P.ix, t, t.wsrc_off, t.len, reinterpret_cast<uint32_t *>(row), row + P.row_bid_off, nullptr, lk);
     if (t.seed_mode == SEED_TAIL) {
         const uint32_t sl = (uint32_t)opts[t.opt_idx].seed_len;
-        cal_width_dev(P.ix, t, t.sub_off + (t.len - sl), sl, wb + (P.max_len + 1), lk);
+        cal_width_dev(P.ix, t, t.sub_off + (t.len - sl), sl, nullptr, row + P.row_seed_off, nullptr, lk);
     }
-    // the item's last slot carries its lookup count; the search worker adds it when the item completes, so
-    // items that are re-run with the large-capacity kernel are not counted twice
-    u32x2 c; c.x = (uint32_t)lk; c.y = 0;
-    wb[P.item_width_stride - 1] = c;
-    (void)lookups;
+    // the row's tail carries the width pass's lookup count; the search worker adds it when the item completes,
+    // so items that are re-run with the large-capacity kernel are not counted twice
+    tail[0] = lk; tail[1] = 0;
 }
 
 // ---- the worker -------------------------------------------------------------------------------------
-// Stack record (16 bytes) = {k, l, rev_l, meta}; meta = i:12 | diff:1 | state:2 | mm:5 | go:4 | ge:5 | kind:2.
-//   kind PLAIN : one search node (gap_entry_t, bwtaln.h:52-58), rev_k == rev_l - (l - k) always holds.
-//   kind FAM_D : the deletion children (bwtgap.c:276-282 / 292-298) of the node stored in the record:
-//                k,l,rev_l,mm,go,ge,state are the PARENT's, i is the children's i (parent's i before --i).
-//   kind FAM_MM: the mismatch children (bwtgap.c:303-313) of the parent; i is the parent's i before --i.
-// A family's 4-bit child mask lives in the top bits of the record's link word (LinkT: 16 bit = 12-bit
-// link + mask for the fast kernel, 32 bit = 28-bit link + mask for the large-capacity kernel).
-enum : uint32_t { KIND_PLAIN = 0, KIND_FAM_D = 1, KIND_FAM_MM = 2 };
+// Stack record (16 bytes) = the EXPANDED node: {k, l, rev_l, meta}; meta = i:12 | state:2 @13 | mm:5 @15 |
+// go:4 @20 | ge:5 @24, i being the node's i before bwtgap.c:244's --i.  rev_k == rev_l - (l - k) holds for
+// every node ever created, so it is not stored.
+// Link word of a record = two halves, one per membership:
+//   half A (low)  : gap children, in the bucket of score + (state == M ? s_gapo : s_gape);
+//                   mask bit 0 = the insertion (bwtgap.c:274 / :284), bits 1..4 = deletion of symbol 0..3
+//                   (bwtgap.c:276-282 / :292-298)
+//   half B (high) : mismatch children, in the bucket of score + s_mm; mask bit j-1 = the reference's loop
+//                   index j = 1..4 (bwtgap.c:303-313; j = 4 exists only when the base is N)
+//   each half = next:NEXT_BITS | mask:5.  Children are taken highest bit first = the reverse of the
+//   reference's push order, as its LIFO buckets do.  A half leaves its bucket list when its mask empties; the
+//   record is freed when both masks are empty.
+enum : uint32_t { PEND_NONE = 0, PEND_DEL = 1, PEND_MM = 2 };
+enum : uint32_t { LS_IDLE = 0, LS_POP = 1, LS_LOOKUP = 2, LS_HIT = 3, LS_END = 4, LS_RETIRED = 5 };
+enum : uint32_t { PHASE_SLOW = 0, PHASE_LOOKUP = 1, PHASE_POP = 2 };
 
-// FUSED = true : one worker runs width passes and both strands of its group itself (large-capacity re-runs,
-//                 the host emulation's reference flow);
-// FUSED = false: split pipeline -- widths come from the width kernel's per-item buffer, one task per work item.
-template <typename LinkT, bool FUSED>
+// Which kind of step a warp executes next, from the number of lanes waiting for each kind.  SLOW steps (hit
+// recording, task end, work fetch + task start) are long and rare: they run once enough lanes have queued up
+// for them, or when nothing else can run.
+enum { VOTE_SLOW_MIN_DEFAULT = 6, VOTE_POP_BIAS_DEFAULT = -12 };
+HSA_HD uint32_t phase_vote(const Params &P, uint32_t n_lookup, uint32_t n_pop, uint32_t n_slow)
+{
+    if (n_slow >= P.vote_slow_min || (n_lookup == 0 && n_pop == 0)) return PHASE_SLOW;
+    if (n_pop == 0) return PHASE_LOOKUP;
+    if (n_lookup == 0) return PHASE_POP;
+    return (int32_t)n_lookup + P.vote_pop_bias >= (int32_t)n_pop ? PHASE_LOOKUP : PHASE_POP;
+}
+
+template <typename LinkT, bool BIDS_SMEM>
 struct Worker {
-    static constexpr uint32_t LINK_BITS = sizeof(LinkT) * 8 - 4;
-    static constexpr uint32_t NIL = (1u << LINK_BITS) - 1u;
+    static constexpr uint32_t HALF_BITS = sizeof(LinkT) * 4;         // 16 (fast kernel) or 32 (large capacity)
+    static constexpr uint32_t NEXT_BITS = HALF_BITS - 5;
+    static constexpr uint32_t NIL = (1u << NEXT_BITS) - 1u;
+    static constexpr uint32_t HALF_MASK = HALF_BITS == 32 ? 0xFFFFFFFFu : ((1u << (HALF_BITS & 31)) - 1u);
+    static constexpr uint32_t HEAD_BYTES = HALF_BITS == 32 ? 4 : 2;
 
     // environment
     const Params &P;
     uint32_t slot;                  // worker slot -> scratch
-    LinkT *heads;                   // bucket heads of this worker: heads[b * head_stride]
-    uint32_t head_stride;
-    const DevOpt *opts;             // option table as seen by this worker (shared memory on the device)
+    uint32_t sm_heads, sm_bid, sm_seed;   // byte offsets of this lane's regions in shared memory
 
-    // group / task bookkeeping
-    uint32_t gid, n_sub, sub;       // current group, number of sub-tasks in it, current sub-task
-    uint32_t work;                  // work-queue index of the current item (split pipeline: width buffer slot)
-    bool short_circuit;
     // current task
+    uint32_t st;                    // LS_*
+    uint32_t work;                  // work-queue index of the current item == its row
     const uint8_t *rd;              // the read
-    uint32_t rd_len, strand, sub_off, len, wsrc_off, seed_mode, opt_idx, out_idx;
-    int32_t aln_start, aln_end;     // start/end stamped on hits (seeds); -1 = leave zero
-    // phase
-    enum Phase : uint32_t { IDLE = 0, WSEED = 1, WBACK = 2, SEARCH = 3, RETIRED = 4 };
-    uint32_t phase;
-    // width pass state
-    uint32_t wk, wl, wj, wn; int32_t wbid; uint32_t wsrc; u32x2 *wdst;
+    uint32_t rd_len, strand, sub_off, len, seed_mode, seed_shift, opt_idx, out_idx;
+    int32_t aln_start, aln_end;
+    uint8_t *row;                   // the item's row (global)
     // search state
     uint64_t mask0, mask1;          // non-empty buckets
-    uint32_t n_live, n_phantom;     // entries the reference would hold: stored (families count their children); counted-only
+    uint32_t n_live, n_phantom;     // entries the reference would hold: stored children; counted-only children
     uint32_t top, free_head;        // arena bump pointer and free list
     int32_t best_score, max_diff, best_cnt;
     uint32_t n_hits;
-    bool failed;                    // task ran out of capacity -> group must be re-run strict
-    uint8_t fail_code;
+    uint32_t fail_code;             // != STATUS_OK: the task ran out of capacity / hit a sizing error
     // candidate node
-    bool have, direct, exact;
-    uint32_t pend;                  // 0: interval known; else KIND_FAM_*: ck/cl/crl are the PARENT's, child pend_j
-    uint32_t pend_j;
-    uint32_t ck, cl, crl;           // k, l, rev_l  (rev_k == rev_l - (l - k) for every node ever created)
+    uint32_t direct, exact, pend, pend_j;
+    uint32_t ck, cl, crl;           // k, l, rev_l  (rev_k == rev_l - (l - k))
     uint32_t ci, c_mm, c_gapo, c_gape, c_state, c_diff;
     uint32_t ci_at_pop;             // e.info & 0xffff of the entry being processed (for last_diff_pos)
     uint32_t zflags;                // which of k,l,rev_k,rev_l were zero when bwt_match_exact was entered
-    int32_t m_cur, m_seed_cur;      // remaining diffs of the candidate (bwtgap.c:161-171), set by acquire_vet()
-    bool look;                      // this lane issues an occ4 pair in the current iteration
-    bool ending;                    // the current task is over (handled once, at the end of the iteration)
+    int32_t m_cur, m_seed_cur;      // remaining diffs of the candidate (bwtgap.c:161-171), set by vet()
     // statistics
-    uint64_t lookups, lookups_group, pops, steps, extra;
-    uint64_t steps_item0; uint32_t max_item_steps;  // diagnostics: iterations of the longest single item
+    uint32_t lookups_item;          // occ lookups of the current item's search
+    uint64_t lookups, pops, steps;
+    uint32_t steps_item0, max_item_steps;
 
-    HSA_HD Worker(const Params &p, uint32_t slot_, LinkT *heads_, uint32_t stride_, const DevOpt *opts_)
-        : P(p), slot(slot_), heads(heads_), head_stride(stride_), opts(opts_), phase(IDLE),
-          lookups(0), lookups_group(0), pops(0), steps(0), extra(0), steps_item0(0), max_item_steps(0) {}
+    HSA_HD Worker(const Params &p, uint32_t slot_, uint32_t lane_in_block)
+        : P(p), slot(slot_), st(LS_IDLE), lookups(0), pops(0), steps(0), steps_item0(0), max_item_steps(0)
+    {
+        sm_heads = P.smem_opts_bytes + lane_in_block * P.smem_lane_stride;
+        sm_bid = sm_heads + P.smem_bid_off;
+        sm_seed = sm_heads + P.smem_seed_off;
+    }
 
-    HSA_HD bool idle() const { return phase == IDLE; }
-    HSA_HD bool retired() const { return phase == RETIRED; }
-    HSA_HD void retire() { phase = RETIRED; }
+    HSA_HD const DevOpt &opt() const { return reinterpret_cast<const DevOpt *>(HSA_SMEM)[opt_idx]; }
+
+    // ---------------------------------------------------------------- small accessors
+    HSA_HD uint32_t head_get(uint32_t b) const
+    {
+        if (HEAD_BYTES == 2) return reinterpret_cast<const uint16_t *>(HSA_SMEM + sm_heads)[b];
+        return reinterpret_cast<const uint32_t *>(HSA_SMEM + sm_heads)[b];
+    }
+    HSA_HD void head_set(uint32_t b, uint32_t s)
+    {
+        if (HEAD_BYTES == 2) reinterpret_cast<uint16_t *>(HSA_SMEM + sm_heads)[b] = (uint16_t)s;
+        else reinterpret_cast<uint32_t *>(HSA_SMEM + sm_heads)[b] = s;
+    }
+    // bound bytes: width_back entry i / width_seed entry i
+    HSA_HD uint32_t bb(uint32_t i) const { return BIDS_SMEM ? HSA_SMEM[sm_bid + i] : row[P.row_bid_off + i]; }
+    HSA_HD void bb_set(uint32_t i, uint32_t v)
+    {
+        if (BIDS_SMEM) HSA_SMEM[sm_bid + i] = (uint8_t)v; else row[P.row_bid_off + i] = (uint8_t)v;
+    }
+    HSA_HD uint32_t bs(uint32_t i) const
+    {
+        if (seed_mode == SEED_ALIAS) return bb(i);
+        return BIDS_SMEM ? HSA_SMEM[sm_seed + i] : row[P.row_seed_off + i];
+    }
+    HSA_HD u32x4 *arena() const { return P.arena + (size_t)slot * P.arena_cap; }
+    HSA_HD LinkT *links() const { return reinterpret_cast<LinkT *>(P.links) + (size_t)slot * P.arena_cap; }
+    HSA_HD bool bucket_nonempty(uint32_t b) const { return b < 64 ? (mask0 >> b) & 1ull : (mask1 >> (b - 64)) & 1ull; }
+    HSA_HD void bucket_set(uint32_t b) { if (b < 64) mask0 |= 1ull << b; else mask1 |= 1ull << (b - 64); }
+    HSA_HD void bucket_clear(uint32_t b) { if (b < 64) mask0 &= ~(1ull << b); else mask1 &= ~(1ull << (b - 64)); }
+    HSA_HD bool idle() const { return st == LS_IDLE; }
+    HSA_HD bool retired() const { return st == LS_RETIRED; }
+    HSA_HD void retire() { st = LS_RETIRED; }
+    HSA_HD uint32_t cls() const          // which phase this lane waits for
+    {
+        return st == LS_LOOKUP ? PHASE_LOOKUP : st == LS_POP ? PHASE_POP : PHASE_SLOW;
+    }
 
     // base p of the strand-resolved read (seq_reverse(len, seq, 1): bwaseqio.c:73-90)
     HSA_HD uint32_t base_at(uint32_t p) const
@@ -519,174 +627,276 @@ struct Worker {
         if (strand) { uint32_t c = ld_ro_u8(rd + (rd_len - 1 - p)); return c < 4 ? 3 - c : c; }
         return ld_ro_u8(rd + p);
     }
-    HSA_HD u32x2 *wback() const
+    HSA_HD void fail(uint32_t code) { if (fail_code == STATUS_OK) fail_code = code; }
+    HSA_HD bool phantom(int32_t sc) const     // bwtgap.c:158-159: can never be popped once a hit exists
     {
-        return FUSED ? P.width + (size_t)slot * P.width_stride : P.item_width + (size_t)work * P.item_width_stride;
+        return n_hits && !(opt().mode & MODE_NONSTOP) && sc > best_score + opt().s_mm;
     }
-    HSA_HD u32x2 *wseed() const
-    {
-        if (seed_mode == SEED_ALIAS) return wback();
-        return FUSED ? P.width + (size_t)slot * P.width_stride + (P.max_len + 1)
-                     : P.item_width + (size_t)work * P.item_width_stride + (P.max_len + 1);
-    }
-    HSA_HD u32x4 *arena() const { return P.arena + (size_t)slot * P.arena_cap; }
-    HSA_HD LinkT *links() const { return reinterpret_cast<LinkT *>(P.links) + (size_t)slot * P.arena_cap; }
 
-    // ---------------------------------------------------------------- group / task setup
-    HSA_HD void start_group(uint32_t work_idx)
+    // ---------------------------------------------------------------- START: next work item in
+    HSA_HD void start(uint32_t work_idx)
     {
         work = work_idx;
-        lookups_group = 0;
-        steps_item0 = steps;
-        failed = false; fail_code = STATUS_OK;
-        if (FUSED) {
-            gid = P.group_list ? P.group_list[work_idx] : P.group_base + work_idx;
-            sub = 0;
-            if (P.kind == KIND_WHOLE) {
-                n_sub = 2; short_circuit = true;
-                if (read_filtered(P.codes + P.read_off[gid], P.read_len[gid], P.filter_max_n)) {
-                    finish_item(gid, 0, 0); phase = IDLE; return;
-                }
-            } else if (P.kind == KIND_SEEDS) { n_sub = 6; short_circuit = false; }
-            else { n_sub = 1; short_circuit = false; }
-            setup_task();
-            return;
-        }
-        // split pipeline: exactly one task per work item; the width kernel has already run for it
-        short_circuit = false;
-        if (P.kind == KIND_SEEDS) { gid = P.group_base + work_idx / 6; sub = work_idx % 6; }
-        else if (P.kind == KIND_WHOLE) { gid = P.pass == 2 ? P.group_list[work_idx] : P.group_base + work_idx; sub = P.pass == 2 ? 1 : 0; }
-        else { gid = P.group_base + work_idx; sub = 0; }
-        n_sub = sub + 1;
-        load_task();
-        if (wback()[0].y == 0xFFFFFFFFu) { phase = IDLE; return; }      // filtered by the width kernel (pass 1)
-        begin_search();
-    }
-
-    HSA_HD void load_task()
-    {
-        const TaskDesc t = make_task(P, opts, gid, sub);
-        rd = t.rd; rd_len = t.rd_len; strand = t.strand; sub_off = t.sub_off; len = t.len; wsrc_off = t.wsrc_off;
+        steps_item0 = (uint32_t)steps;
+        const DevOpt *opts = reinterpret_cast<const DevOpt *>(HSA_SMEM);
+        const TaskDesc t = make_task(P, opts, work_item(P, work_idx));
+        rd = t.rd; rd_len = t.rd_len; strand = t.strand; sub_off = t.sub_off; len = t.len;
         seed_mode = t.seed_mode; opt_idx = t.opt_idx; out_idx = t.out_idx; aln_start = t.aln_start; aln_end = t.aln_end;
-    }
-
-    HSA_HD void setup_task()            // FUSED only
-    {
-        load_task();
-        if (seed_mode == SEED_TAIL) {
-            uint32_t sl = (uint32_t)opts[opt_idx].seed_len;
-            begin_width(WSEED, sub_off + (len - sl), sl, wseed());
-        } else begin_width(WBACK, wsrc_off, len, wback());
-    }
-
-    HSA_HD void begin_width(uint32_t ph, uint32_t src, uint32_t n, u32x2 *dst)
-    {
-        // n >= 1 always: the host rejects empty reads / tasks (no recursion with end_width, so that the
-        // whole worker stays in registers)
-        phase = ph; wk = 0; wl = P.ix.fwd.text_length; wj = 0; wn = n; wbid = 0; wsrc = src; wdst = dst;
-    }
-
-    HSA_HD void end_width()
-    {
-        u32x2 last; last.x = 0; last.y = (uint32_t)(++wbid);    // bwtaln.c:113-114
-        wdst[wn] = last;
-        if (phase == WSEED) begin_width(WBACK, wsrc_off, len, wback());
-        else if (P.kind == KIND_WIDTH) {
-            u32x2 *dst = P.width_out + P.read_off[gid] + gid;
-            for (uint32_t j = 0; j <= wn; ++j) dst[j] = wdst[j];
-            P.bid_out[gid] = wbid;
-            lookups += lookups_group;
-            phase = IDLE;
-        } else begin_search();
-    }
-
-    HSA_HD void begin_search()
-    {
-        const DevOpt &o = opts[opt_idx];
-        phase = SEARCH;
+        row = P.rows + (size_t)work * P.row_stride;
+        const uint32_t *tail = reinterpret_cast<const uint32_t *>(row + P.row_tail_off);
+        if (tail[1] & ROW_FLAG_FILTERED) { st = LS_IDLE; return; }       // filtered by the width kernel (pass 1)
+        const DevOpt &o = opt();
+        seed_shift = seed_mode == SEED_TAIL ? len - (uint32_t)o.seed_len : 0u;     // ii = i - (len - seed_len), :253
+        if (BIDS_SMEM) {                                   // bound bytes -> this lane's shared-memory region
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(row + P.row_bid_off);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(HSA_SMEM + sm_bid);
+            for (uint32_t j = 0; j < (len + 4) / 4; ++j) dst[j] = src[j];
+            if (seed_mode == SEED_TAIL) {
+                const uint32_t *s2 = reinterpret_cast<const uint32_t *>(row + P.row_seed_off);
+                uint32_t *d2 = reinterpret_cast<uint32_t *>(HSA_SMEM + sm_seed);
+                for (uint32_t j = 0; j < ((uint32_t)o.seed_len + 4) / 4; ++j) d2[j] = s2[j];
+            }
+        }
+        lookups_item = 0; fail_code = STATUS_OK;
         mask0 = mask1 = 0; n_live = 0; n_phantom = 0; top = 0; free_head = NIL;
         best_score = (o.max_diff + 1) * o.s_mm + (o.max_gapo + 1) * o.s_gapo + (o.max_gape + 1) * o.s_gape; // :128
         max_diff = o.max_diff; best_cnt = 0; n_hits = 0;
         // root (bwtgap.c:142) is the first node popped; carry it directly
-        have = true; direct = true; exact = false; pend = 0; pend_j = 0;
+        direct = 1; exact = 0; pend = PEND_NONE; pend_j = 0;
         ck = 0; cl = P.ix.fwd.text_length; crl = P.ix.fwd.text_length;
         ci = len; c_mm = c_gapo = c_gape = 0; c_state = ST_M; c_diff = 0; zflags = 0; ci_at_pop = len;
+        vet();
+        if (st == LS_POP) st = LS_END;                     // root pruned (wrong strand): the stack is empty
     }
 
-    // ---------------------------------------------------------------- stack
-    HSA_HD bool bucket_nonempty(uint32_t b) const { return b < 64 ? (mask0 >> b) & 1ull : (mask1 >> (b - 64)) & 1ull; }
-
-    // one record of `kind` standing for `n_children` reference entries (1 for PLAIN), all of score `sc`
-    HSA_HD void push_record(int32_t sc, uint32_t kind, uint32_t cmask, uint32_t n_children,
-                            uint32_t i, uint32_t k, uint32_t l, uint32_t rl,
-                            uint32_t mm, uint32_t go, uint32_t ge, uint32_t state, uint32_t is_diff)
+    // ---------------------------------------------------------------- pop-time tests (bwtgap.c:150-186)
+    // The candidate is in the c* registers.  Sets st: LS_POP (candidate dropped), LS_LOOKUP (needs its occ4
+    // pair: expansion, bwt_match_exact step, or materialisation), LS_HIT, LS_END.
+    HSA_HD void vet()
     {
-        const DevOpt &o = opts[opt_idx];
-        // bwtgap.c:158-159: once a hit exists, anything above best_score + s_mm can never be popped -> count only
-        if (n_hits && !(o.mode & MODE_NONSTOP) && sc > best_score + o.s_mm) { n_phantom += n_children; return; }
-        if ((uint32_t)sc >= P.n_buckets) { failed = true; fail_code = STATUS_BAD_SCORE; return; }
-        uint32_t s;
-        LinkT *lk = links();
-        if (free_head != NIL) { s = free_head; free_head = (uint32_t)lk[s] & NIL; }
-        else if (top < P.arena_cap) s = top++;
-        else { failed = true; fail_code = STATUS_NEED_STRICT; return; }
-        u32x4 e;
-        e.x = k; e.y = l; e.z = rl;
-        e.w = i | is_diff << 12 | state << 13 | mm << 15 | go << 20 | ge << 24 | kind << 29;
-        arena()[s] = e;
-        uint32_t b = (uint32_t)sc;
-        uint32_t prev = bucket_nonempty(b) ? (uint32_t)heads[b * head_stride] : NIL;
-        lk[s] = (LinkT)(prev | cmask << LINK_BITS);
-        heads[b * head_stride] = (LinkT)s;
-        if (b < 64) mask0 |= 1ull << b; else mask1 |= 1ull << (b - 64);
-        n_live += n_children;
+        const DevOpt &o = opt();
+        if (direct) {
+            // the carried child would have been pushed and popped: same loop-top test, entry included (:150-151)
+            if ((int64_t)n_live + n_phantom + 1 > (int64_t)o.max_entries) { st = LS_END; return; }
+            direct = 0;
+        }
+        m_cur = max_diff - (int32_t)(c_mm + c_gapo);                                  // :161-164
+        if (o.mode & MODE_GAPE) m_cur -= (int32_t)c_gape;
+        if (m_cur < 0) { st = LS_POP; return; }
+        m_seed_cur = o.max_seed_diff - (int32_t)(c_mm + c_gapo);                     // :167-171
+        if (o.mode & MODE_GAPE) m_seed_cur -= (int32_t)c_gape;
+        if (ci > 0 && m_cur < (int32_t)(bb(ci - 1) & 63u)) { st = LS_POP; return; }   // :172-173
+        if (pend) { st = LS_LOOKUP; return; }              // survived pop-time pruning: materialise it first
+        classify();
     }
 
-    // gap_pop (bwtgap.c:80-92): last entry of the lowest non-empty bucket -> candidate registers.
-    // A family record yields its last-pushed remaining child and stays in place until it is empty.
-    HSA_HD int32_t pop()
+    // hit test / bwt_match_exact entry (bwtgap.c:176-186) of a candidate whose interval is known
+    HSA_HD void classify()
     {
-        uint32_t b = mask0 ? (uint32_t)ffs64(mask0) : 64u + (uint32_t)ffs64(mask1);
+        const DevOpt &o = opt();
+        ci_at_pop = ci;
+        if (ci == 0) { st = LS_HIT; return; }                                         // :177-179
+        if (m_cur == 0 && (c_state == ST_M || (o.mode & MODE_GAPE) || (int32_t)c_gape == o.max_gape)) {   // :180
+            exact = 1;
+            zflags = (ck == 0) | (cl == 0) << 1 | (crl - (cl - ck) == 0) << 2 | (crl == 0) << 3;
+        }
+        st = LS_LOOKUP;
+    }
+
+    // ---------------------------------------------------------------- POP: gap_pop (bwtgap.c:80-92) + vet
+    HSA_HD void do_pop()
+    {
+        const DevOpt &o = opt();
+        ++steps;
+        // loop top of bwtgap.c:144-159
+        if (n_live == 0 || (int64_t)n_live + n_phantom > (int64_t)o.max_entries) { st = LS_END; return; }
+        const uint32_t b = mask0 ? (uint32_t)ffs64(mask0) : 64u + (uint32_t)ffs64(mask1);
         LinkT *lk = links();
-        uint32_t s = heads[b * head_stride];
-        u32x4 e = arena()[s];
-        uint32_t lw = (uint32_t)lk[s];
-        uint32_t nx = lw & NIL, cmask = lw >> LINK_BITS;
-        uint32_t kind = e.w >> 29;
-        uint32_t j = 0;
-        if (kind != KIND_PLAIN) {
-            j = 31u - (uint32_t)clz32(cmask);           // last pushed child first
-            cmask &= ~(1u << j);
-        }
-        if (kind == KIND_PLAIN || cmask == 0) {
-            if (nx == NIL) { if (b < 64) mask0 &= ~(1ull << b); else mask1 &= ~(1ull << (b - 64)); }
-            else heads[b * head_stride] = (LinkT)nx;
-            lk[s] = (LinkT)free_head; free_head = s;
-        } else lk[s] = (LinkT)(nx | cmask << LINK_BITS);
-        --n_live;
-        ck = e.x; cl = e.y; crl = e.z;
-        uint32_t ei = e.w & 0xFFFu, est = (e.w >> 13) & 3u;
-        c_mm = (e.w >> 15) & 31u; c_gapo = (e.w >> 20) & 15u; c_gape = (e.w >> 24) & 31u;
-        if (kind == KIND_PLAIN) { ci = ei; c_diff = (e.w >> 12) & 1u; c_state = est; pend = 0; }
-        else if (kind == KIND_FAM_D) {
-            ci = ei; c_diff = 1; c_state = ST_D; pend = KIND_FAM_D; pend_j = j;
-            if (est == ST_M) ++c_gapo; else ++c_gape;           // gap open (bwtgap.c:281) / extension (:297)
-        } else {
-            ci = ei - 1; c_diff = 1; c_state = ST_M; pend = KIND_FAM_MM; pend_j = j;
-            ++c_mm;                                             // bwtgap.c:312
-        }
-        have = true; direct = false; exact = false;
+        const uint32_t s = head_get(b);
+        const u32x4 e = arena()[s];
+        const LinkT lw = lk[s];
         ++pops;
-        return (int32_t)b;
+        --n_live;
+        if (!(o.mode & MODE_NONSTOP) && (int32_t)b > best_score + o.s_mm) { st = LS_END; return; }   // :158-159
+        const uint32_t pi = e.w & 0xFFFu, pst = (e.w >> 13) & 3u;
+        const uint32_t pmm = (e.w >> 15) & 31u, pgo = (e.w >> 20) & 15u, pge = (e.w >> 24) & 31u;
+        const int32_t msc = (int32_t)pmm * o.s_mm + (int32_t)pgo * o.s_gapo + (int32_t)pge * o.s_gape + o.s_mm;
+        uint32_t halfA = (uint32_t)(lw & (LinkT)HALF_MASK), halfB = (uint32_t)(lw >> HALF_BITS);
+        // when both memberships share a bucket the mismatch children were pushed last, so they come first
+        const bool isB = (int32_t)b == msc && (halfB >> NEXT_BITS) != 0;
+        uint32_t half = isB ? halfB : halfA;
+        uint32_t cmask = half >> NEXT_BITS;
+        const uint32_t nx = half & NIL;
+        const uint32_t j = 31u - (uint32_t)clz32(cmask);                // last pushed child first
+        cmask &= ~(1u << j);
+        half = nx | cmask << NEXT_BITS;
+        if (isB) halfB = half; else halfA = half;
+        if (cmask == 0) {
+            // this membership is exhausted: it leaves its bucket list
+            if (nx == NIL) bucket_clear(b); else head_set(b, nx);
+            const uint32_t other = isB ? halfA >> NEXT_BITS : halfB >> NEXT_BITS;
+            if (other == 0) { lk[s] = (LinkT)free_head; free_head = s; }
+            else lk[s] = (LinkT)halfA | (LinkT)halfB << HALF_BITS;
+        } else lk[s] = (LinkT)halfA | (LinkT)halfB << HALF_BITS;
+        // the child (bwtgap.c:267-314) as a candidate
+        ck = e.x; cl = e.y; crl = e.z;
+        c_mm = pmm; c_gapo = pgo; c_gape = pge;
+        c_diff = 1; direct = 0; exact = 0;
+        if (isB) {                                          // mismatch j+1 (bwtgap.c:303-313)
+            ci = pi - 1; ++c_mm; c_state = ST_M; pend = PEND_MM; pend_j = j;
+        } else {
+            if (pst == ST_M) ++c_gapo; else ++c_gape;       // gap open (:274,:281) / extension (:284,:297)
+            if (j == 0) { ci = pi - 1; c_state = ST_I; pend = PEND_NONE; pend_j = 0; }   // insertion: same interval
+            else { ci = pi; c_state = ST_D; pend = PEND_DEL; pend_j = j - 1; }       // deletion of symbol j-1
+        }
+        vet();
     }
 
-    // ---------------------------------------------------------------- hits
-    // action for found hits, bwtgap.c:188-241.  returns false when the search must stop (top2b break).
-    HSA_HD bool record_hit(uint32_t k, uint32_t l, uint32_t rk, uint32_t rl)
+    // ---------------------------------------------------------------- LOOKUP: one occ4 pair + what follows
+    HSA_HD void do_lookup()
     {
-        const DevOpt &o = opts[opt_idx];
-        int32_t score = (int32_t)c_mm * o.s_mm + (int32_t)c_gapo * o.s_gapo + (int32_t)c_gape * o.s_gape;
-        bool do_add = true;
+        const DevOpt &o = opt();
+        ++steps;
+        // ---- the one memory operation every kind of step shares: occ4 at k and at l + 1 -----------------
+        const DevBwt &B = P.ix.fwd;
+        uint32_t pk = ck, pl = cl + 1;
+        pk -= (pk > B.inverse_sa0); pl -= (pl > B.inverse_sa0);
+        const u32x4 kc = ld_ro4(B.blocks + 2 * (size_t)(pk >> 6)), kw = ld_ro4(B.blocks + 2 * (size_t)(pk >> 6) + 1);
+        const u32x4 lc = ld_ro4(B.blocks + 2 * (size_t)(pl >> 6)), lw = ld_ro4(B.blocks + 2 * (size_t)(pl >> 6) + 1);
+        // i: index of the base the lookup extends by.  For a pending child the lookup is the PARENT's: deletion
+        // children have ci == the parent's pre-decrement i, mismatch children ci == its post-decrement i.
+        const uint32_t i = pend == PEND_MM ? ci : ci - 1;
+        const uint32_t sc_ = base_at(sub_off + i);
+        uint32_t oL[4], oR[4], sk[4], sl[4], rsl[4];
+        occ4_from_sector(kc, kw, pk & 63u, oL);
+        occ4_from_sector(lc, lw, pl & 63u, oR);
+        {
+            // BWTAllSARangesBackward_Bidirection, 2BWT-Interface.c:235-271
+            uint32_t oc = 0;
+            for (int c = 3; c >= 0; --c) {
+                sk[c] = B.cum[c] + oL[c] + 1;
+                sl[c] = B.cum[c] + oR[c];
+                rsl[c] = crl - oc;
+                oc += oR[c] - oL[c];
+            }
+        }
+        const uint32_t vmask = (uint32_t)(sk[0] <= sl[0]) | (uint32_t)(sk[1] <= sl[1]) << 1 |
+                               (uint32_t)(sk[2] <= sl[2]) << 2 | (uint32_t)(sk[3] <= sl[3]) << 3;
+        // the one child every kind of step continues with
+        const uint32_t csel = (pend == PEND_DEL ? pend_j : pend == PEND_MM ? sc_ + pend_j + 1u : sc_) & 3u;
+        const uint32_t nk = sel4(sk, csel), nl = sel4(sl, csel), nr = sel4(rsl, csel);
+        const bool alive = (vmask >> csel) & 1u;
+
+        if (pend) {
+            // the child the reference pushed at bwtgap.c:281/297 (deletion) or :312 (mismatch): its interval
+            ck = nk; cl = nl; crl = nr; pend = PEND_NONE;
+            classify();
+            return;
+        }
+        if (exact) {
+            // one step of bwt_match_exact (2BWT-Interface.c:365-388)
+            if (sc_ > 3) { st = LS_POP; return; }                   // :376-377 (no lookup issued there)
+            lookups_item += 2;
+            if (!alive) { st = LS_POP; return; }
+            ck = nk; cl = nl; crl = nr; ci = i;
+            if (ci == 0) st = LS_HIT;
+            return;
+        }
+
+        // ---- node expansion (bwtgap.c:244-325) --------------------------------------------------------
+        lookups_item += 2;
+        const int32_t m = m_cur, m_seed = m_seed_cur;
+        const uint32_t occ = cl - ck + 1;
+        bool allow_diff = true, allow_M = true;
+        if (i > 0) {                                                                        // :252-265
+            const uint32_t b0 = bb(i - 1), b1 = bb(i);
+            if ((int32_t)(b0 & 63u) > m - 1) allow_diff = false;
+            else if ((int32_t)(b0 & 63u) == m - 1 && (int32_t)(b1 & 63u) == m - 1 && (b1 & 0x80u)) allow_M = false;
+            const int32_t ii = (int32_t)i - (int32_t)seed_shift;                            // :253
+            if (seed_mode != SEED_NONE && ii > 0) {
+                const uint32_t s0 = bs((uint32_t)ii - 1), s1 = bs((uint32_t)ii);
+                if ((int32_t)(s0 & 63u) > m_seed - 1) allow_diff = false;
+                else if ((int32_t)(s0 & 63u) == m_seed - 1 && (int32_t)(s1 & 63u) == m_seed - 1 && (s1 & 0x80u)) allow_M = false;
+            }
+        }
+        const uint32_t e_mm = c_mm, e_go = c_gapo, e_ge = c_gape, e_state = c_state;
+        const int32_t e_score = (int32_t)e_mm * o.s_mm + (int32_t)e_go * o.s_gapo + (int32_t)e_ge * o.s_gape;
+        uint32_t maskA = 0, maskB = 0;
+        if (allow_diff) {
+            int32_t tmp;
+            if (o.mode & MODE_LOGGAP) {                                                     // :267 + int_log2 :107-116
+                uint32_t v = e_ge + e_go; int32_t lg = 0;
+                while (v > 1) { v >>= 1; ++lg; }
+                tmp = lg / 2 + 1;
+            } else tmp = (int32_t)(e_go + e_ge);
+            if ((int32_t)i >= o.indel_end_skip + tmp && (int32_t)len - (int32_t)i >= o.indel_end_skip + tmp) {
+                bool ins = false, del = false;
+                if (e_state == ST_M) ins = del = (int32_t)e_go < o.max_gapo;               // :269-282
+                else if (e_state == ST_I) ins = (int32_t)e_ge < o.max_gape;                // :283-285
+                else del = (int32_t)e_ge < o.max_gape &&                                   // :286-299
+                           ((int32_t)(e_ge + e_go) < max_diff || occ < (uint32_t)o.max_del_occ);
+                maskA = (ins ? 1u : 0u) | (del ? vmask << 1 : 0u);
+            }
+            if (allow_M) {                                                                  // :302-314
+                // children j = 1..3 (and j = 4 when seq[i] is N) are mismatches: bit j-1
+                for (uint32_t j = 1; j <= 3; ++j) maskB |= ((vmask >> ((sc_ + j) & 3u)) & 1u) << (j - 1);
+                if (sc_ > 3) maskB |= ((vmask >> (sc_ & 3u)) & 1u) << 3;
+            }
+        }
+        const int32_t gsc = e_score + (e_state == ST_M ? o.s_gapo : o.s_gape), msc = e_score + o.s_mm;
+        uint32_t nA = (uint32_t)popc32(maskA), nB = (uint32_t)popc32(maskB);
+        if (nA && phantom(gsc)) { n_phantom += nA; maskA = 0; nA = 0; }
+        if (nB && phantom(msc)) { n_phantom += nB; maskB = 0; nB = 0; }
+        if (maskA | maskB) {
+            if ((maskA && (uint32_t)gsc >= P.n_buckets) || (maskB && (uint32_t)msc >= P.n_buckets)) fail(STATUS_BAD_SCORE);
+            else {
+                uint32_t s = NIL;
+                LinkT *lk = links();
+                if (free_head != NIL) { s = free_head; free_head = (uint32_t)(lk[s] & (LinkT)NIL); }
+                else if (top < P.arena_cap) s = top++;
+                else fail(STATUS_NEED_STRICT);
+                if (s != NIL) {
+                    u32x4 e;
+                    e.x = ck; e.y = cl; e.z = crl;
+                    e.w = (i + 1) | e_state << 13 | e_mm << 15 | e_go << 20 | e_ge << 24;
+                    arena()[s] = e;
+                    uint32_t halfA = NIL, halfB = NIL;
+                    if (maskA) {
+                        halfA = (bucket_nonempty((uint32_t)gsc) ? head_get((uint32_t)gsc) : NIL) | maskA << NEXT_BITS;
+                        head_set((uint32_t)gsc, s); bucket_set((uint32_t)gsc);
+                    }
+                    if (maskB) {        // after A: if both share a bucket, B links to the record itself
+                        halfB = (bucket_nonempty((uint32_t)msc) ? head_get((uint32_t)msc) : NIL) | maskB << NEXT_BITS;
+                        head_set((uint32_t)msc, s); bucket_set((uint32_t)msc);
+                    }
+                    lk[s] = (LinkT)halfA | (LinkT)halfB << HALF_BITS;
+                    n_live += nA + nB;
+                }
+            }
+        }
+        if (fail_code != STATUS_OK) { st = LS_END; return; }
+        // the exact-match child (bwtgap.c:303-313 with j = 4, or :315-325): would be pushed last into the lowest
+        // bucket and popped next -> it stays in registers
+        if (sc_ < 4 && alive) {
+            ck = nk; cl = nl; crl = nr; ci = i; c_state = ST_M; c_diff = 0; direct = 1;
+            vet();
+        } else st = LS_POP;
+    }
+
+    // ---------------------------------------------------------------- HIT: action for found hits, bwtgap.c:188-241
+    HSA_HD void do_hit()
+    {
+        const DevOpt &o = opt();
+        uint32_t k = ck, l = cl, rk = crl - (cl - ck), rl = crl;
+        if (exact) {
+            // matched down to the first base: write-back quirk of 2BWT-Interface.c:383-386
+            if (zflags & 1u) k = 0;
+            if (zflags & 2u) l = 0;
+            if (zflags & 4u) rk = 0;
+            if (zflags & 8u) rl = 0;
+        }
+        st = LS_POP;
+        const int32_t score = (int32_t)c_mm * o.s_mm + (int32_t)c_gapo * o.s_gapo + (int32_t)c_gape * o.s_gape;
         Hit *hs = P.hits + (size_t)slot * P.hit_cap;
         if (n_hits == 0) {
             best_score = score;
@@ -695,46 +905,46 @@ struct Worker {
             if (!(o.mode & MODE_NONSTOP)) max_diff = (best_diff + 1 > o.max_diff) ? o.max_diff : best_diff + 1;
         }
         if (score == best_score) best_cnt = (int32_t)((uint32_t)best_cnt + (l - k + 1));
-        else if (best_cnt > o.max_top2) return false;
-        if (c_gapo) {
+        else if (best_cnt > o.max_top2) { st = LS_END; return; }                      // top2b break
+        if (c_gapo)
             for (uint32_t j = 0; j < n_hits; ++j)
-                if (hs[j].k == k && hs[j].l == l) { do_add = false; break; }
+                if (hs[j].k == k && hs[j].l == l) return;                              // :205-213 already found
+        // gap_shadow (bwtgap.c:94-105) on width_back, in place; the bound bytes follow
+        const uint32_t x = l - k + 1, ldp = c_diff ? ci_at_pop : 0u;
+        uint32_t *w = reinterpret_cast<uint32_t *>(row);
+        uint32_t jj = 0, w_prev = 0xFFFFFFFFu;
+        for (uint32_t i = 0; i < ldp; ++i) {
+            uint32_t v = w[i], bid = bb(i) & 63u;
+            if (v > x) { v -= x; w[i] = v; }
+            else if (v == x) { bid = 1; v = P.ix.fwd.text_length - (++jj); w[i] = v; }
+            bb_set(i, bound_byte(bid, v, w_prev));
+            w_prev = v;
         }
-        if (do_add) {
-            // gap_shadow (bwtgap.c:94-105) on width_back, in place
-            uint32_t x = l - k + 1, ldp = c_diff ? ci_at_pop : 0u, jj = 0;
-            u32x2 *w = wback();
-            for (uint32_t i = 0; i < ldp; ++i) {
-                u32x2 v = w[i];
-                if (v.x > x) { v.x -= x; w[i] = v; }
-                else if (v.x == x) { v.y = 1; v.x = P.ix.fwd.text_length - (++jj); w[i] = v; }
-            }
-            if (n_hits >= P.hit_cap) { failed = true; fail_code = STATUS_NEED_STRICT; return false; }
-            Hit h;
-            h.k = k; h.l = l; h.rev_k = rk; h.rev_l = rl;
-            h.counts = c_mm | c_gapo << 16 | c_gape << 24;
-            h.score = score; h.pad0 = h.pad1 = 0;
-            hs[n_hits++] = h;
-        }
-        return true;
+        if (ldp > 0 && ldp <= len) bb_set(ldp, bound_byte(bb(ldp) & 63u, w[ldp], w_prev));
+        if (n_hits >= P.hit_cap) { fail(STATUS_NEED_STRICT); st = LS_END; return; }
+        Hit h;
+        h.k = k; h.l = l; h.rev_k = rk; h.rev_l = rl;
+        h.counts = c_mm | c_gapo << 16 | c_gape << 24;
+        h.score = score; h.pad0 = h.pad1 = 0;
+        hs[n_hits++] = h;
     }
 
-    // write the current task's hits to the output arena
+    // ---------------------------------------------------------------- END: results out
     HSA_HD void finish_item(uint32_t item, uint32_t n, uint32_t strand_stamp)
     {
         uint64_t off = 0;
-        uint8_t st = STATUS_OK;
+        uint8_t stt = STATUS_OK;
         if (n) {
 #if defined(__CUDA_ARCH__)
             off = atomicAdd(&P.counters[CNT_ALN], (unsigned long long)n);
 #else
             off = P.counters[CNT_ALN]; P.counters[CNT_ALN] += n;
 #endif
-            if (off + n > P.aln_cap) { st = STATUS_OUT_FULL; n = 0; }
+            if (off + n > P.aln_cap) { stt = STATUS_OUT_FULL; n = 0; }
             const Hit *hs = P.hits + (size_t)slot * P.hit_cap;
             for (uint32_t j = 0; j < n; ++j) {
                 uint32_t *w = P.aln + (off + j) * 9;
-                Hit h = hs[j];
+                const Hit h = hs[j];
                 w[0] = h.counts; w[1] = h.k; w[2] = h.l; w[3] = h.rev_k; w[4] = h.rev_l;
                 w[5] = strand_stamp << 30;                       // type:30 = 0, strand:2
                 int32_t s0 = 0, e0 = 0;
@@ -745,285 +955,42 @@ struct Worker {
         }
         P.n_aln[item] = (int32_t)n;
         P.aln_off[item] = off;
-        P.status[item] = st;
+        P.status[item] = stt;
     }
 
-    HSA_HD void fail_group()
+    HSA_HD void do_end()
     {
-        // discard everything this group produced; the host re-runs it with the large-capacity (fused) kernel
-        uint32_t first = out_idx, cnt = 1;
-        if (FUSED && P.kind == KIND_SEEDS) { first = gid * 6; cnt = 6; }
-        for (uint32_t j = 0; j < cnt; ++j) { P.n_aln[first + j] = 0; P.aln_off[first + j] = 0; P.status[first + j] = fail_code; }
+        const uint32_t d = (uint32_t)steps - steps_item0;
+        if (d > max_item_steps) max_item_steps = d;
+        st = LS_IDLE;
+        if (fail_code != STATUS_OK) {
+            // discard what this item produced; the host re-runs it with the large-capacity kernel
+            P.n_aln[out_idx] = 0; P.aln_off[out_idx] = 0; P.status[out_idx] = (uint8_t)fail_code;
+            const int which = fail_code == STATUS_NEED_STRICT ? CNT_STRICT : CNT_BAD;
 #if defined(__CUDA_ARCH__)
-        unsigned long long idx = atomicAdd(&P.counters[fail_code == STATUS_NEED_STRICT ? CNT_STRICT : CNT_BAD], 1ull);
+            const unsigned long long idx = atomicAdd(&P.counters[which], 1ull);
 #else
-        unsigned long long idx = P.counters[fail_code == STATUS_NEED_STRICT ? CNT_STRICT : CNT_BAD]++;
+            const unsigned long long idx = P.counters[which]++;
 #endif
-        if (fail_code == STATUS_NEED_STRICT && P.strict_list) P.strict_list[idx] = gid;
-        phase = IDLE;
-    }
-
-    HSA_HD void end_task()
-    {
-        if ((uint32_t)(steps - steps_item0) > max_item_steps) max_item_steps = (uint32_t)(steps - steps_item0);
-        if (failed) { fail_group(); return; }
-        if (!FUSED) {
-            const uint64_t mine = lookups_group + wback()[P.item_width_stride - 1].x;   // + the width kernel's share
-            phase = IDLE;
-            if (P.kind == KIND_WHOLE && P.pass == 1 && n_hits == 0) {
-                // bwtaln.c:351-358: nothing on the reverse-complement strand -> the forward strand is searched (pass 2).
-                // The read's pass-1 lookup count rides in aln_off[] until pass 2 completes, so that a read which
-                // is later re-run with the large-capacity kernel is not counted twice.
-                P.aln_off[out_idx] = mine;
+            if (fail_code == STATUS_NEED_STRICT && P.strict_list) P.strict_list[idx] = out_idx;
+            return;
+        }
+        const uint64_t mine = (uint64_t)lookups_item + reinterpret_cast<const uint32_t *>(row + P.row_tail_off)[0];
+        if (P.kind == KIND_WHOLE && P.pass == 1 && n_hits == 0) {
+            // bwtaln.c:351-358: nothing on the reverse-complement strand -> the forward strand is searched (pass 2).
+            // The read's pass-1 lookup count rides in aln_off[] until pass 2 completes, so that a read which
+            // is later re-run with the large-capacity kernel is not counted twice.
+            P.aln_off[out_idx] = mine;
 #if defined(__CUDA_ARCH__)
-                uint32_t idx = atomicAdd(P.next_count, 1u);
+            const uint32_t idx = atomicAdd(P.next_count, 1u);
 #else
-                uint32_t idx = (*P.next_count)++;
+            const uint32_t idx = (*P.next_count)++;
 #endif
-                P.next_list[idx] = gid;
-                return;
-            }
-            lookups += mine + ((P.kind == KIND_WHOLE && P.pass == 2) ? P.aln_off[out_idx] : 0ull);
-            finish_item(out_idx, n_hits, strand);
+            P.next_list[idx] = out_idx;
             return;
         }
-        bool last = (sub + 1 == n_sub) || (short_circuit && n_hits);
-        if (P.kind != KIND_WHOLE || n_hits || last) finish_item(out_idx, n_hits, strand);
-        if (last) { lookups += lookups_group; phase = IDLE; return; }
-        ++sub;
-        setup_task();
-    }
-
-    // ---------------------------------------------------------------- one iteration
-    // MAX_POPS bounds the number of stack pops tried per iteration when candidates keep dying.
-    // prefetch the two index sectors the candidate (ck, cl) will need and its width entries
-    HSA_HD void prefetch_candidate()
-    {
-        const DevBwt &B = P.ix.fwd;
-        uint32_t pk = ck, pl = cl + 1;
-        pk -= (pk > B.inverse_sa0); pl -= (pl > B.inverse_sa0);
-        prefetch_sector(B.blocks + 2 * (size_t)(pk >> 6));
-        prefetch_sector(B.blocks + 2 * (size_t)(pl >> 6));
-    }
-
-    // One trip of "get a candidate and apply the reference's pop-time tests" (bwtgap.c:144-186).
-    // Sets `look` when the candidate needs its occ4 pair (expansion, exact-match step, or family child
-    // materialisation); sets `ending` when the task is over; otherwise the candidate died or was a hit and
-    // another trip may follow.  (end_task / record_hit have exactly one call site each to keep the loop small.)
-    HSA_HD void acquire_vet()
-    {
-        const DevOpt &o = opts[opt_idx];
-        if (!have) {
-            // loop top of bwtgap.c:144-159
-            if (n_live == 0 || (int64_t)n_live + n_phantom > (int64_t)o.max_entries) { ending = true; return; }
-            int32_t sc = pop();
-            if (!(o.mode & MODE_NONSTOP) && sc > best_score + o.s_mm) { ending = true; return; }
-            prefetch_candidate();                           // overlaps with the width load of the bound test below
-        } else if (direct && !exact) {
-            // the carried child would have been pushed and popped: same loop-top test, entry included
-            if ((int64_t)n_live + n_phantom + 1 > (int64_t)o.max_entries) { ending = true; return; }
-            direct = false;
-        }
-        bool hit = false;
-        uint32_t hk = ck, hl = cl, hrk = crl - (cl - ck), hrl = crl;
-        if (exact) {
-            // still inside bwt_match_exact (2BWT-Interface.c:365-388)
-            if (ci != 0) { look = true; return; }
-            // matched down to the first base: write-back quirk of 2BWT-Interface.c:383-386
-            if (zflags & 1u) hk = 0;
-            if (zflags & 2u) hl = 0;
-            if (zflags & 4u) hrk = 0;
-            if (zflags & 8u) hrl = 0;
-            hit = true;
-        } else {
-            m_cur = max_diff - (int32_t)(c_mm + c_gapo);                               // :161-164
-            if (o.mode & MODE_GAPE) m_cur -= (int32_t)c_gape;
-            if (m_cur < 0) { have = false; return; }
-            if (seed_mode != SEED_NONE) {
-                m_seed_cur = o.max_seed_diff - (int32_t)(c_mm + c_gapo);
-                if (o.mode & MODE_GAPE) m_seed_cur -= (int32_t)c_gape;
-            }
-            if (ci > 0 && m_cur < (int32_t)wback()[ci - 1].y) { have = false; return; } // :172-173
-            if (pend) { look = true; return; }              // survived pop-time pruning: materialise it
-            ci_at_pop = ci;
-            if (ci == 0) hit = true;                                                   // :177-179
-            else {
-                if (m_cur == 0 && (c_state == ST_M || (o.mode & MODE_GAPE) || (int32_t)c_gape == o.max_gape)) { // :180
-                    exact = true;
-                    zflags = (ck == 0) | (cl == 0) << 1 | (hrk == 0) << 2 | (crl == 0) << 3;
-                }
-                look = true;
-                return;
-            }
-        }
-        if (hit) {
-            have = false;
-            if (!record_hit(hk, hl, hrk, hrl) || failed) ending = true;
-        }
-    }
-
-    // ---------------------------------------------------------------- one iteration
-    // Every lane of a warp calls iterate() every loop trip (idle and retired lanes too) and passes the same
-    // warp barriers: the divergent candidate handling above is followed by a re-convergence point, so the
-    // occ4 loads and popcounts below are issued once for all lanes that need them.  MAX_POPS bounds the
-    // number of acquire/vet trips per iteration when candidates keep dying.
-    template <int MAX_POPS>
-    HSA_HD void iterate()
-    {
-        const bool active = !(phase == IDLE || phase == RETIRED);
-        if (active) ++steps;
-        look = false; ending = false;
-#if defined(__CUDACC__)
-#pragma unroll 1
-#endif
-        for (int t = 0; t < MAX_POPS; ++t) {
-            HSA_WARP_SYNC();
-            if (active && !look && !ending && phase == SEARCH) acquire_vet();
-        }
-        if (FUSED && active && (phase == WSEED || phase == WBACK)) look = true;
-        HSA_WARP_SYNC();
-        if (look) lookup_and_step();
-        HSA_WARP_SYNC();
-        if (ending) end_task();
-    }
-
-    HSA_HD void lookup_and_step()
-    {
-        const DevOpt &o = opts[opt_idx];
-        const int32_t m = m_cur, m_seed = m_seed_cur;
-        // ---- the one memory operation every phase shares: occ4 at k and at l + 1 -------------------
-        const bool searching = !FUSED || phase == SEARCH;
-        const DevBwt &B = searching ? P.ix.fwd : P.ix.rev;
-        uint32_t pk = searching ? ck : wk, pl = (searching ? cl : wl) + 1;
-        pk -= (pk > B.inverse_sa0); pl -= (pl > B.inverse_sa0);
-        u32x4 kc = ld_ro4(B.blocks + 2 * (size_t)(pk >> 6)), kw = ld_ro4(B.blocks + 2 * (size_t)(pk >> 6) + 1);
-        u32x4 lc = ld_ro4(B.blocks + 2 * (size_t)(pl >> 6)), lw = ld_ro4(B.blocks + 2 * (size_t)(pl >> 6) + 1);
-
-        if (FUSED && phase != SEARCH) {
-            // ---- bwt_cal_width step (bwtaln.c:86-97) -------------------------------------------------
-            uint32_t c = base_at(wsrc + wj);
-            uint32_t oL[4], oR[4];
-            occ4_from_sector(kc, kw, pk & 63u, oL);
-            occ4_from_sector(lc, lw, pl & 63u, oR);
-            if (c < 4) {
-                uint32_t a = sel4(oL, c), b = sel4(oR, c);
-                wk = P.ix.fwd.cum[c] + a + 1;                  // BWTSARangeForeward, 2BWT-Interface.c:121-132
-                wl = P.ix.fwd.cum[c] + b;
-                lookups_group += 2;
-            }
-            if (wk > wl || c > 3) { wk = 0; wl = P.ix.fwd.text_length; ++wbid; }
-            u32x2 v; v.x = wl - wk + 1; v.y = (uint32_t)wbid;
-            wdst[wj] = v;
-            if (++wj == wn) end_width();
-            return;
-        }
-
-        // ---- materialise a family child / expand a node (bwtgap.c:244-325) / one bwt_match_exact step ---
-        // i: index of the base the lookup extends by.  For a pending family child the lookup is the PARENT's:
-        // FAM_D children were produced by the parent's step at i = ci - 1 ... ci is the child's i (== parent's
-        // pre-decrement i), FAM_MM children have ci == parent's post-decrement i.
-        uint32_t i = pend == KIND_FAM_MM ? ci : ci - 1;
-        uint32_t sc_ = base_at(sub_off + i);
-        u32x2 w0, w1, s0, s1;                                   // width[i-1], width[i], width_seed[ii-1], width_seed[ii]
-        bool use_seed = false;
-        w0.x = w0.y = w1.x = w1.y = s0.x = s0.y = s1.x = s1.y = 0;
-        if (!exact && !pend && i > 0) {
-            const u32x2 *w = wback();
-            w0 = w[i - 1]; w1 = w[i];
-            if (seed_mode != SEED_NONE) {
-                int32_t ii = seed_mode == SEED_ALIAS ? (int32_t)i : (int32_t)i - ((int32_t)len - o.seed_len);   // :253
-                if (ii > 0) { const u32x2 *ws = wseed(); s0 = ws[ii - 1]; s1 = ws[ii]; use_seed = true; }
-            }
-        }
-        uint32_t oL[4], oR[4], sk[4], sl[4], rsl[4];
-        occ4_from_sector(kc, kw, pk & 63u, oL);
-        occ4_from_sector(lc, lw, pl & 63u, oR);
-        {
-            // BWTAllSARangesBackward_Bidirection, 2BWT-Interface.c:235-271
-            uint32_t oc = 0;
-            for (int c = 3; c >= 0; --c) {
-                sk[c] = P.ix.fwd.cum[c] + oL[c] + 1;
-                sl[c] = P.ix.fwd.cum[c] + oR[c];
-                rsl[c] = crl - oc;
-                oc += oR[c] - oL[c];
-            }
-        }
-
-        if (pend) {
-            // the child the reference pushed at bwtgap.c:281/297 (deletion j) or :312 (mismatch j+1)
-            uint32_t c = pend == KIND_FAM_D ? pend_j : (sc_ + pend_j + 1u) & 3u;
-            ck = sel4(sk, c); cl = sel4(sl, c); crl = sel4(rsl, c);
-            pend = 0;
-            ++extra;
-            prefetch_candidate();
-            return;                                             // next iteration: hit test / exact entry / expansion
-        }
-
-        if (exact) {
-            if (sc_ > 3) { have = false; return; }             // 2BWT-Interface.c:376-377 (no lookup issued there)
-            lookups_group += 2;
-            uint32_t nk = sel4(sk, sc_), nl = sel4(sl, sc_), nr = sel4(rsl, sc_);
-            if (nk > nl) { have = false; return; }
-            ck = nk; cl = nl; crl = nr; ci = i;
-            prefetch_candidate();
-            return;
-        }
-
-        lookups_group += 2;
-        uint32_t occ = cl - ck + 1;
-        bool allow_diff = true, allow_M = true;
-        if (i > 0) {                                                                        // :252-265
-            if ((int32_t)w0.y > m - 1) allow_diff = false;
-            else if ((int32_t)w0.y == m - 1 && (int32_t)w1.y == m - 1 && w0.x == w1.x) allow_M = false;
-            if (use_seed) {
-                if ((int32_t)s0.y > m_seed - 1) allow_diff = false;
-                else if ((int32_t)s0.y == m_seed - 1 && (int32_t)s1.y == m_seed - 1 && s0.x == s1.x) allow_M = false;
-            }
-        }
-        const uint32_t e_mm = c_mm, e_go = c_gapo, e_ge = c_gape, e_state = c_state;
-        const uint32_t pk0 = ck, pl0 = cl, prl0 = crl;
-        const int32_t e_score = (int32_t)e_mm * o.s_mm + (int32_t)e_go * o.s_gapo + (int32_t)e_ge * o.s_gape;
-        const uint32_t vmask = (uint32_t)(sk[0] <= sl[0]) | (uint32_t)(sk[1] <= sl[1]) << 1 |
-                               (uint32_t)(sk[2] <= sl[2]) << 2 | (uint32_t)(sk[3] <= sl[3]) << 3;
-        int32_t tmp;
-        if (o.mode & MODE_LOGGAP) {                                                         // :267 + int_log2 :107-116
-            uint32_t v = e_ge + e_go; int32_t lg = 0;
-            while (v > 1) { v >>= 1; ++lg; }
-            tmp = lg / 2 + 1;
-        } else tmp = (int32_t)(e_go + e_ge);
-        if (allow_diff && (int32_t)i >= o.indel_end_skip + tmp && (int32_t)len - (int32_t)i >= o.indel_end_skip + tmp) {
-            bool ins = false, del = false;
-            if (e_state == ST_M) ins = del = (int32_t)e_go < o.max_gapo;                   // :269-282
-            else if (e_state == ST_I) ins = (int32_t)e_ge < o.max_gape;                    // :283-285
-            else del = (int32_t)e_ge < o.max_gape &&                                       // :286-299
-                       ((int32_t)(e_ge + e_go) < max_diff || occ < (uint32_t)o.max_del_occ);
-            const int32_t gsc = e_score + (e_state == ST_M ? o.s_gapo : o.s_gape);
-            if (ins)
-                push_record(gsc, KIND_PLAIN, 0, 1, i, pk0, pl0, prl0, e_mm, e_go + (e_state == ST_M), e_ge + (e_state != ST_M), ST_I, 1);
-            if (del && vmask)
-                push_record(gsc, KIND_FAM_D, vmask, (uint32_t)popc32(vmask), i + 1, pk0, pl0, prl0, e_mm, e_go, e_ge, e_state, 1);
-        }
-        have = false;
-        if (allow_diff && allow_M) {                                                        // :302-314
-            // children j = 1..3 (and j = 4 when seq[i] is N) are mismatches: one family record, bit j-1
-            uint32_t mmask = 0;
-            for (uint32_t j = 1; j <= 3; ++j) mmask |= ((vmask >> ((sc_ + j) & 3u)) & 1u) << (j - 1);
-            if (sc_ > 3) mmask |= ((vmask >> (sc_ & 3u)) & 1u) << 3;
-            if (mmask)
-                push_record(e_score + o.s_mm, KIND_FAM_MM, mmask, (uint32_t)popc32(mmask), i + 1, pk0, pl0, prl0, e_mm, e_go, e_ge, e_state, 1);
-            if (sc_ < 4 && ((vmask >> sc_) & 1u)) carry(i, sel4(sk, sc_), sel4(sl, sc_), sel4(rsl, sc_), e_mm, e_go, e_ge);
-        } else if (sc_ < 4) {                                                               // :315-325
-            if ((vmask >> sc_) & 1u) carry(i, sel4(sk, sc_), sel4(sl, sc_), sel4(rsl, sc_), e_mm, e_go, e_ge);
-        }
-        if (failed) ending = true;
-    }
-
-    // the exact-match child: would be pushed last into the lowest bucket and popped next -> keep in registers
-    HSA_HD void carry(uint32_t i, uint32_t k, uint32_t l, uint32_t rl, uint32_t mm, uint32_t go, uint32_t ge)
-    {
-        have = true; direct = true; exact = false; pend = 0;
-        ck = k; cl = l; crl = rl; ci = i; c_mm = mm; c_gapo = go; c_gape = ge; c_state = ST_M; c_diff = 0;
-        prefetch_candidate();
+        lookups += mine + ((P.kind == KIND_WHOLE && P.pass == 2) ? P.aln_off[out_idx] : 0ull);
+        finish_item(out_idx, n_hits, strand);
     }
 };
 

@@ -38,26 +38,67 @@ static void repack(const hsa_bwt_view_t *v, std::vector<u32x4> &out, DevBwt &d)
     for (int i = 0; i < 5; ++i) d.cum[i] = v->cumulativeFreq[i];
 }
 
-static uint64_t g_last_extra = 0, g_last_steps = 0;
-static uint32_t *g_item_steps = nullptr;      // optional diagnostic: worker iterations per work item, launches concatenated
+static uint64_t g_last_steps = 0;
+static uint32_t *g_item_steps = nullptr;      // optional diagnostic: worker steps per work item, launches concatenated
 static size_t g_item_steps_pos = 0;
+// SIMT simulation (diagnostic): 32 workers stepped in lockstep under phase_vote(); counts how often each phase
+// runs and how many lanes take part, so scheduling policies can be compared on the CPU.
+static int g_simt = 0;
+static uint32_t g_vote_slow_min = VOTE_SLOW_MIN_DEFAULT; static int32_t g_vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
+static uint64_t g_phase_runs[3], g_phase_lanes[3];
 
-template <typename LinkT, bool FUSED>
-static void run_worker(const Params &P, LinkT *heads, const DevOpt *dopts, uint32_t n_work, uint64_t st[4])
+struct Smem {                                   // stands in for one block's shared memory
+    std::vector<unsigned char> buf;
+};
+
+template <typename LinkT, bool BIDS_SMEM>
+static void run_worker(const Params &P, uint32_t n_work, uint64_t st[4])
 {
-    Worker<LinkT, FUSED> w(P, 0, heads, 1, dopts);
-    uint32_t next = 0;
-    uint64_t steps0 = 0;
-    for (;;) {
-        if (w.idle()) {
-            if (g_item_steps && next > 0) { g_item_steps[g_item_steps_pos++] = (uint32_t)(w.steps - steps0); steps0 = w.steps; }
-            if (next < n_work) w.start_group(next++);
-            else break;
-            continue;
+    if (!g_simt) {
+        Worker<LinkT, BIDS_SMEM> w(P, 0, 0);
+        uint32_t next = 0;
+        uint64_t steps0 = 0;
+        for (;;) {
+            switch (w.st) {
+            case LS_IDLE:
+                if (g_item_steps && next > 0) { g_item_steps[g_item_steps_pos++] = (uint32_t)(w.steps - steps0); steps0 = w.steps; }
+                if (next < n_work) w.start(next++); else w.retire();
+                break;
+            case LS_POP: w.do_pop(); break;
+            case LS_LOOKUP: w.do_lookup(); break;
+            case LS_HIT: w.do_hit(); break;
+            case LS_END: w.do_end(); break;
+            default: break;
+            }
+            if (w.retired()) break;
         }
-        w.template iterate<2>();
+        st[0] += w.lookups; st[1] += w.pops; st[3] += w.steps;
+        return;
     }
-    st[0] += w.lookups; st[1] += w.pops; st[2] += w.extra; st[3] += w.steps;
+    // lockstep warp: needs per-lane scratch (arena / links / hits are indexed by slot, shared memory by lane)
+    const int W = 32;
+    std::vector<Worker<LinkT, BIDS_SMEM>> ws;
+    for (int l = 0; l < W; ++l) ws.emplace_back(P, (uint32_t)l, (uint32_t)l);
+    uint32_t next = 0;
+    for (;;) {
+        uint32_t n[3] = {0, 0, 0};
+        int alive = 0;
+        for (auto &w : ws) if (!w.retired()) { ++n[w.cls()]; ++alive; }
+        if (!alive) break;
+        const uint32_t ph = phase_vote(P, n[PHASE_LOOKUP], n[PHASE_POP], n[PHASE_SLOW]);
+        ++g_phase_runs[ph]; g_phase_lanes[ph] += n[ph];
+        for (auto &w : ws) {
+            if (w.retired() || w.cls() != ph) continue;
+            if (ph == PHASE_LOOKUP) w.do_lookup();
+            else if (ph == PHASE_POP) w.do_pop();
+            else {
+                if (w.st == LS_HIT) w.do_hit();
+                if (w.st == LS_END) w.do_end();
+                if (w.st == LS_IDLE) { if (next < n_work) w.start(next++); else w.retire(); }
+            }
+        }
+    }
+    for (auto &w : ws) { st[0] += w.lookups; st[1] += w.pops; st[3] += w.steps; }
 }
 
 extern "C" {
@@ -115,65 +156,71 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
         if (b > nb) nb = b;
     }
     if (nb > 128) return -1;
-    std::vector<u32x4> arena(arena_cap);
-    std::vector<uint32_t> links(arena_cap);          // large enough for either link width
-    std::vector<u32x2> width(2 * (size_t)(max_len + 1));
-    std::vector<Hit> hits(hit_cap);
-    std::vector<uint32_t> heads(nb);
-    std::vector<uint32_t> strict(n_groups + 1);
-    unsigned long long counters[CNT_N];
-    memset(counters, 0, sizeof(counters));
+    // arena_cap <= 2046: the fast configuration (16-bit link halves, bound bytes in "shared memory");
+    // larger: the large-capacity configuration (32-bit halves, bound bytes read from the rows)
+    const bool wide = arena_cap > 2046;
+    const int lanes = g_simt ? 32 : 1;
+    const uint32_t per = kind == KIND_SEEDS ? 6u : 1u, n_work = n_groups * per;
+    uint32_t max_seed = 0;
+    for (uint32_t i = 0; i < n_opts; ++i)
+        if (opts[i].seed_len > 0 && (uint32_t)opts[i].seed_len < max_len) max_seed = std::max(max_seed, (uint32_t)opts[i].seed_len);
+    const uint32_t seed_cap = (kind == KIND_TASKS || kind == KIND_WHOLE) && max_seed ? max_seed + 1 : 0;
 
     Params P;
     memset(&P, 0, sizeof(P));
-    P.ix = e->ix; P.codes = codes; P.kind = kind; P.n_groups = n_groups; P.group_list = nullptr;
+    set_layout(P, max_len, seed_cap, nb, n_opts ? n_opts : 1, wide ? 4 : 2, !wide);
+    std::vector<unsigned char> smem((size_t)P.smem_opts_bytes + (size_t)lanes * P.smem_lane_stride + 16);
+    memcpy(smem.data(), dopts.data(), dopts.size() * sizeof(DevOpt));
+    hsa_smem_host = smem.data();
+    std::vector<u32x4> arena((size_t)arena_cap * lanes);
+    std::vector<uint64_t> links((size_t)arena_cap * lanes);          // large enough for either link width
+    std::vector<Hit> hits((size_t)hit_cap * lanes);
+    std::vector<uint32_t> strict(n_work + 1);
+    std::vector<unsigned char> rows((size_t)std::max(n_work, 1u) * P.row_stride);
+    std::vector<uint32_t> next_list(n_groups + 1);
+    uint32_t next_count = 0;
+    unsigned long long counters[CNT_TOTAL];
+    memset(counters, 0, sizeof(counters));
+
+    P.ix = e->ix; P.codes = codes; P.kind = kind;
     P.tasks = (const Task *)tasks; P.read_off = read_off; P.read_len = read_len;
-    P.opts = dopts.data(); P.n_opts = n_opts; P.len2opt = len2opt; P.max_len = max_len; P.filter_max_n = filter_max_n;
+    P.opts = dopts.data(); P.len2opt = len2opt; P.filter_max_n = filter_max_n;
+    P.rows = rows.data();
     P.arena = arena.data(); P.links = links.data(); P.arena_cap = arena_cap;
-    P.width = width.data(); P.width_stride = 2 * (max_len + 1);
-    P.hits = hits.data(); P.hit_cap = hit_cap; P.n_buckets = nb;
+    P.hits = hits.data(); P.hit_cap = hit_cap;
     P.n_aln = n_aln; P.aln_off = aln_off; P.status = status; P.aln = aln; P.aln_cap = aln_cap;
     P.counters = counters; P.strict_list = strict.data();
     P.width_out = (u32x2 *)width_out; P.bid_out = bid_out;
+    P.vote_slow_min = g_vote_slow_min; P.vote_pop_bias = g_vote_pop_bias;
 
     uint64_t st[4] = {0, 0, 0, 0};
     unsigned long long cursor = 0;
     P.cursor = &cursor;
-    if (arena_cap > 4094) {
-        // the large-capacity configuration: fused flow (width passes + both strands inside the worker), 32-bit links
-        run_worker<uint32_t, true>(P, heads.data(), dopts.data(), n_groups, st);
-    } else {
-        // the split pipeline, launch for launch as hsa_b200.cu's run_batch enqueues it
-        const uint32_t per = kind == KIND_SEEDS ? 6u : 1u, n_work = n_groups * per;
-        uint32_t max_seed = 0;
-        for (uint32_t i = 0; i < n_opts; ++i)
-            if (opts[i].seed_len > 0 && (uint32_t)opts[i].seed_len < max_len) max_seed = std::max(max_seed, (uint32_t)opts[i].seed_len);
-        const uint32_t seed_cap = (kind == KIND_TASKS || kind == KIND_WHOLE) ? max_seed + 1 : 0;
-        const uint32_t wstride = (max_len + 1) + seed_cap + 1;
-        std::vector<u32x2> item_width((size_t)std::max(n_work, 1u) * wstride);
-        std::vector<uint32_t> next_list(n_groups + 1);
-        uint32_t next_count = 0;
-        P.item_width = item_width.data(); P.item_width_stride = wstride;
-        P.pass = 1; P.group_base = 0; P.n_groups = n_work; P.next_list = next_list.data(); P.next_count = &next_count;
-        for (uint32_t w = 0; w < n_work; ++w) width_item(P, dopts.data(), w, st[0]);
-        if (kind != KIND_WIDTH) {
-            run_worker<uint16_t, false>(P, (uint16_t *)heads.data(), dopts.data(), n_work, st);
-            if (kind == KIND_WHOLE) {
-                P.pass = 2; P.group_list = next_list.data(); P.n_groups = next_count; P.next_list = nullptr; P.next_count = nullptr;
-                for (uint32_t w = 0; w < next_count; ++w) width_item(P, dopts.data(), w, st[0]);
-                run_worker<uint16_t, false>(P, (uint16_t *)heads.data(), dopts.data(), next_count, st);
-            }
+    // the split pipeline, launch for launch as hsa_b200.cu's run_batch enqueues it
+    P.pass = 1; P.work_base = 0; P.work_list = nullptr; P.n_work = n_work;
+    P.next_list = next_list.data(); P.next_count = &next_count;
+    for (uint32_t w = 0; w < n_work; ++w) width_item(P, dopts.data(), w);
+    if (kind != KIND_WIDTH) {
+        if (wide) run_worker<uint64_t, false>(P, n_work, st); else run_worker<uint32_t, true>(P, n_work, st);
+        if (kind == KIND_WHOLE) {
+            P.pass = 2; P.work_list = next_list.data(); P.n_work = next_count; P.next_list = nullptr; P.next_count = nullptr;
+            for (uint32_t w = 0; w < next_count; ++w) width_item(P, dopts.data(), w);
+            if (wide) run_worker<uint64_t, false>(P, next_count, st); else run_worker<uint32_t, true>(P, next_count, st);
         }
     }
-    *lookups = st[0];
+    hsa_smem_host = nullptr;
+    *lookups = st[0] + counters[CNT_LOOKUPS];
     *n_strict = counters[CNT_STRICT] + counters[CNT_BAD];
     *pops = st[1];
-    g_last_extra = st[2]; g_last_steps = st[3];
+    g_last_steps = st[3];
     return (long)counters[CNT_ALN];
 }
 
 void emu_set_item_steps(uint32_t *buf) { g_item_steps = buf; g_item_steps_pos = 0; }
-uint64_t emu_last_extra(void) { return g_last_extra; }
+void emu_set_vote(uint32_t slow_min, int32_t pop_bias) { g_vote_slow_min = slow_min; g_vote_pop_bias = pop_bias; }
+void emu_set_simt(int on) { g_simt = on; for (int i = 0; i < 3; ++i) { g_phase_runs[i] = 0; g_phase_lanes[i] = 0; } }
+void emu_phase_stats(uint64_t *runs, uint64_t *lanes) { for (int i = 0; i < 3; ++i) { runs[i] = g_phase_runs[i]; lanes[i] = g_phase_lanes[i]; } }
+uint64_t emu_last_extra(void) { return 0; }
 uint64_t emu_last_steps(void) { return g_last_steps; }
 
 } // extern "C"
