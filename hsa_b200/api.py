@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhsa_b200.so")
+# HSA_B200_LIB selects another build of the same library (e.g. the -DHSA_PHASE_PROF diagnostics build)
+LIB_PATH = os.environ.get("HSA_B200_LIB") or os.path.join(_HERE, "libhsa_b200.so")
 
 MODE_GAPE, MODE_COMPREAD, MODE_LOGGAP, MODE_NONSTOP = 0x01, 0x02, 0x04, 0x10
 SEED_NONE, SEED_TAIL, SEED_ALIAS = 0, 1, 2

@@ -22,7 +22,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    extra = os.environ.get("HSA_B200_NVCC_EXTRA", "").split()      # e.g. -DHSA_PHASE_PROF for the per-phase cycle counters
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     subprocess.check_call(cmd)
     return OUT
 

@@ -28,6 +28,11 @@ static_assert(sizeof(hsa_gap_opt_t) == 64, "hsa_gap_opt_t must be 64 bytes like 
 static_assert(sizeof(hsa_width_t) == 8, "hsa_width_t must be 8 bytes like bwt_width_t");
 static_assert(sizeof(DevOpt) == 64, "DevOpt is staged as 16 ints");
 
+enum { MAX_PIPES = 4 };
+// behind the core's counters: per-pipe slots {cursor pass 1, cursor pass 2, pass-2 list count, pad}, then the
+// per-phase cycle counters of the -DHSA_PHASE_PROF build {cycles, runs, lanes} x {SLOW, LOOKUP, POP}
+enum { CNT_PIPE0 = CNT_TOTAL, CNT_PROF0 = CNT_PIPE0 + 4 * (MAX_PIPES + 1), CNT_ALLOC = CNT_PROF0 + 9 };
+
 // =====================================================================================================
 // kernels
 // =====================================================================================================
@@ -59,7 +64,7 @@ __global__ void occ_kernel(DevBwt dev, RefBwt ref, int layout, const uint32_t *i
 
 // Width kernel of the split pipeline: one thread per work item, every thread of a warp walks reads of the
 // same shape, so the loop is divergence-free (bwt_cal_width is a strictly sequential chain per read).
-__global__ void __launch_bounds__(256) width_kernel(const __grid_constant__ Params P)
+__global__ void __launch_bounds__(256, 5) width_kernel(const __grid_constant__ Params P)
 {
     DevOpt *sopt = reinterpret_cast<DevOpt *>(hsa_smem);
     for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
@@ -87,15 +92,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
     const uint32_t n_work = P.n_work_dev ? *P.n_work_dev : P.n_work;
     Worker<LinkT, BIDS_SMEM> w(P, slot, threadIdx.x);
     unsigned long long warp_iters = 0;
+#ifdef HSA_PHASE_PROF
+    unsigned long long prof_cyc[3] = {0, 0, 0}, prof_runs[3] = {0, 0, 0}, prof_lanes[3] = {0, 0, 0};
+#endif
 
     for (;;) {
-        const uint32_t c = w.retired() ? 3u : w.cls();
-        const unsigned bL = __ballot_sync(0xffffffffu, c == PHASE_LOOKUP);
-        const unsigned bP = __ballot_sync(0xffffffffu, c == PHASE_POP);
-        const unsigned bS = __ballot_sync(0xffffffffu, c == PHASE_SLOW);
-        if (!(bL | bP | bS)) break;
+        // classes are two-bit codes (SLOW 0, LOOKUP 1, POP 2, retired 3): two ballots give all four counts
+        const uint32_t c = w.cls();
+        const unsigned b0 = __ballot_sync(0xffffffffu, c & 1u), b1 = __ballot_sync(0xffffffffu, c & 2u);
+        if ((b0 & b1) == 0xffffffffu) break;
         ++warp_iters;
-        const uint32_t ph = phase_vote(P, __popc(bL), __popc(bP), __popc(bS));
+        const uint32_t ph = phase_vote(P, __popc(b0 & ~b1), __popc(b1 & ~b0), __popc(~(b0 | b1)));
+#ifdef HSA_PHASE_PROF
+        const long long t_ph0 = clock64();
+        const uint32_t n_ph = ph == PHASE_LOOKUP ? __popc(b0 & ~b1) : ph == PHASE_POP ? __popc(b1 & ~b0) : __popc(~(b0 | b1));
+#endif
         if (ph == PHASE_LOOKUP) {
             if (c == PHASE_LOOKUP) w.do_lookup();
         } else if (ph == PHASE_POP) {
@@ -121,7 +132,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
             }
         }
         __syncwarp();
+#ifdef HSA_PHASE_PROF
+        if (lane == 0) { prof_cyc[ph] += (unsigned long long)(clock64() - t_ph0); prof_runs[ph] += 1; prof_lanes[ph] += n_ph; }
+#endif
     }
+#ifdef HSA_PHASE_PROF
+    if (lane == 0)
+        for (int i = 0; i < 3; ++i) {
+            atomicAdd(&P.counters[CNT_PROF0 + 3 * i], prof_cyc[i]);
+            atomicAdd(&P.counters[CNT_PROF0 + 3 * i + 1], prof_runs[i]);
+            atomicAdd(&P.counters[CNT_PROF0 + 3 * i + 2], prof_lanes[i]);
+        }
+#endif
 
     // statistics: warp-reduce, one atomic per warp
     unsigned long long lk = w.lookups, pp = w.pops, st = w.steps;
@@ -222,9 +244,6 @@ struct Pipe {                                // one in-flight chunk: stream, wor
     }
 };
 
-enum { MAX_PIPES = 4 };
-// per-pipe slots behind the core's counters: {cursor pass 1, cursor pass 2, pass-2 list count, pad}
-enum { CNT_PIPE0 = CNT_TOTAL, CNT_ALLOC = CNT_PIPE0 + 4 * (MAX_PIPES + 1) };
 
 struct hsa_workspace {
     const hsa_index *idx = nullptr;
@@ -251,7 +270,7 @@ struct hsa_workspace {
     bool configured = false;
     uint32_t block = 128; int minb = 5; int blocks_per_sm_cap = 0;
     uint32_t n_pipes = 1; uint64_t chunk_items = 12u << 20;
-    uint32_t arena_cap = 1024, hit_cap = 32;
+    uint32_t arena_cap = 1022, hit_cap = 32;
     uint32_t vote_slow_min = VOTE_SLOW_MIN_DEFAULT; int32_t vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
 };
 
@@ -521,7 +540,7 @@ extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
 extern "C" uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws) { return ws ? ws->last_launches : 0; }
 
 // ---------------------------------------------------------------------------------------------- launch
-// Kernel variants.  FAST: 16-bit link halves (<= 2046 records per worker), bound bytes in shared memory
+// Kernel variants.  FAST: 16-bit link halves (<= 1022 records per worker, 64 score buckets), bound bytes in shared memory
 // (FAST_ROWS: in the rows, for reads too long for shared memory).  LARGE: 32-bit halves, 64-thread blocks.
 enum Variant { V_FAST = 0, V_FAST_ROWS = 1, V_LARGE = 2 };
 
@@ -580,6 +599,15 @@ static void trace_dump(hsa_workspace *ws, const unsigned long long *cnt_all)
                 cnt_all[CNT_STEPS], cnt_all[CNT_DIAG_WARP_ITERS],
                 cnt_all[CNT_DIAG_WARP_ITERS] ? (double)cnt_all[CNT_STEPS] / (double)cnt_all[CNT_DIAG_WARP_ITERS] : 0.0,
                 cnt_all[CNT_DIAG_MAX_ITEM_STEPS], cnt_all[CNT_POPS], cnt_all[CNT_LOOKUPS]);
+#ifdef HSA_PHASE_PROF
+    if (cnt_all) {
+        static const char *nm[3] = {"SLOW", "LOOKUP", "POP"};
+        for (int i = 0; i < 3; ++i) {
+            const unsigned long long cyc = cnt_all[CNT_PROF0 + 3 * i], runs = cnt_all[CNT_PROF0 + 3 * i + 1], ln = cnt_all[CNT_PROF0 + 3 * i + 2];
+            fprintf(stderr, " | %s runs=%llu cyc/run=%.0f lanes/run=%.2f", nm[i], runs, runs ? (double)cyc / runs : 0.0, runs ? (double)ln / runs : 0.0);
+        }
+    }
+#endif
     fprintf(stderr, "\n");
 }
 
@@ -593,7 +621,7 @@ static int configure(hsa_workspace *ws)
     ws->n_pipes = (uint32_t)std::min<long>(MAX_PIPES, std::max<long>(1, env_long("HSA_B200_PIPES", 1)));
     ws->chunk_items = (uint64_t)std::max<long>(6 * 1024, env_long("HSA_B200_CHUNK", 12 << 20));
     ws->chunk_items -= ws->chunk_items % 6;
-    ws->arena_cap = (uint32_t)std::min<long>(2046, std::max<long>(16, env_long("HSA_B200_ARENA_CAP", 1024)));   // 11-bit links
+    ws->arena_cap = (uint32_t)std::min<long>(1022, std::max<long>(16, env_long("HSA_B200_ARENA_CAP", 1022)));   // 10-bit slot ids
     ws->hit_cap = (uint32_t)std::max<long>(1, env_long("HSA_B200_HIT_CAP", 32));
     ws->vote_slow_min = (uint32_t)std::max<long>(1, env_long("HSA_B200_SLOW_MIN", VOTE_SLOW_MIN_DEFAULT));
     ws->vote_pop_bias = (int32_t)env_long("HSA_B200_POP_BIAS", VOTE_POP_BIAS_DEFAULT);
@@ -687,11 +715,12 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
     P.width_out = b.width_out; P.bid_out = b.bid_out;
     P.vote_slow_min = ws->vote_slow_min; P.vote_pop_bias = ws->vote_pop_bias;
     // fast configuration: bound bytes in shared memory if a block's share leaves room for >= 4 blocks per SM
-    set_layout(P, b.max_len, seed_cap, b.n_buckets, b.n_opts, 2, true);
+    const uint32_t nb_fast = std::min<uint32_t>(b.n_buckets, 64);   // scores >= 64 send the item to the large-capacity kernel
+    set_layout(P, b.max_len, seed_cap, nb_fast, b.n_opts, 2, true);
     Variant v = V_FAST;
     if ((size_t)P.smem_opts_bytes + (size_t)ws->block * P.smem_lane_stride > 56 * 1024) {
         v = V_FAST_ROWS;
-        set_layout(P, b.max_len, seed_cap, b.n_buckets, b.n_opts, 2, false);
+        set_layout(P, b.max_len, seed_cap, nb_fast, b.n_opts, 2, false);
     }
     if ((size_t)P.smem_opts_bytes + (size_t)ws->block * P.smem_lane_stride > 200 * 1024)
         return fail(HSA_E_ARG, "option table too large for shared memory");
@@ -726,7 +755,7 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
     ws->trace = trace_saved;
     if (!sync) return HSA_OK;
 
-    unsigned long long cnt[CNT_TOTAL];
+    unsigned long long cnt[CNT_ALLOC];
     CU(cudaMemcpyAsync(cnt, ws->counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
     trace_dump(ws, cnt);
@@ -747,7 +776,7 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
         rc = issue_chunk(ws, b, S, ws->strict, MAX_PIPES, V_LARGE, list_dev, 0, (uint32_t)n_strict, stream);
         if (rc) { cudaFree(list_dev); return rc; }
         CU(cudaEventRecord(ws->ev1, stream));
-        unsigned long long cnt2[CNT_TOTAL];
+        unsigned long long cnt2[CNT_ALLOC];
         CU(cudaMemcpyAsync(cnt2, ws->counters, sizeof(cnt2), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         trace_dump(ws, cnt2);

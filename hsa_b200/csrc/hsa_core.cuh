@@ -79,6 +79,22 @@ HSA_HD u32x4 ld_ro4(const u32x4 *p)
     return *p;
 #endif
 }
+// one 32-byte index sector {counts, packed words} in a single 256-bit read-only load (sm_100: LDG.E.256)
+HSA_HD void ld_sector(const u32x4 *p, u32x4 &a, u32x4 &b)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+HSA_HD void st4(void *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w)      // 16-byte store
+{
+    u32x4 v; v.x = x; v.y = y; v.z = z; v.w = w;
+    *reinterpret_cast<u32x4 *>(p) = v;
+}
 HSA_HD uint32_t ld_ro1(const uint32_t *p)
 {
 #if defined(__CUDA_ARCH__)
@@ -195,9 +211,8 @@ HSA_HD void occ4_from_sector(const u32x4 &cnt, const u32x4 &w, uint32_t off, uin
 HSA_HD void occ4_dev(const DevBwt &b, uint32_t index, uint32_t occ[4])
 {
     index -= (index > b.inverse_sa0);                   // BWT.c:804
-    uint32_t blk = index >> 6;
-    u32x4 cnt = ld_ro4(b.blocks + 2 * (size_t)blk);
-    u32x4 w = ld_ro4(b.blocks + 2 * (size_t)blk + 1);
+    u32x4 cnt, w;
+    ld_sector(b.blocks + 2 * (size_t)(index >> 6), cnt, w);
     occ4_from_sector(cnt, w, index & 63u, occ);
 }
 
@@ -342,12 +357,13 @@ enum : uint32_t { ROW_FLAG_FILTERED = 1u };
 HSA_HD void set_layout(Params &P, uint32_t max_len, uint32_t seed_cap, uint32_t n_buckets, uint32_t n_opts,
                        uint32_t head_bytes, bool bids_smem)
 {
-    const uint32_t nb4 = (max_len + 1 + 3u) & ~3u, ns4 = (seed_cap + 3u) & ~3u;
+    // every row region holds a multiple of 16 entries so that the width kernel can store 16 bytes at a time
+    const uint32_t nb4 = (max_len + 1 + 15u) & ~15u, ns4 = (seed_cap + 15u) & ~15u;
     P.max_len = max_len; P.n_buckets = n_buckets; P.n_opts = n_opts;
-    P.row_bid_off = 4u * (max_len + 1);
+    P.row_bid_off = 4u * nb4;
     P.row_seed_off = P.row_bid_off + nb4;
     P.row_tail_off = P.row_seed_off + ns4;
-    P.row_stride = (P.row_tail_off + 8u + 15u) & ~15u;
+    P.row_stride = (P.row_tail_off + 8u + 31u) & ~31u;      // rows start on a 32-byte sector
     P.smem_opts_bytes = n_opts * (uint32_t)sizeof(DevOpt);
     const uint32_t heads = (n_buckets * head_bytes + 3u) & ~3u;
     P.smem_bid_off = heads;
@@ -426,8 +442,8 @@ HSA_HD bool read_filtered(const uint8_t *r, uint32_t L, int32_t max_n)
 HSA_HD uint32_t occ1_dev(const DevBwt &b, uint32_t index, uint32_t c)
 {
     index -= (index > b.inverse_sa0);
-    const u32x4 cnt = ld_ro4(b.blocks + 2 * (size_t)(index >> 6));
-    const u32x4 w = ld_ro4(b.blocks + 2 * (size_t)(index >> 6) + 1);
+    u32x4 cnt, w;
+    ld_sector(b.blocks + 2 * (size_t)(index >> 6), cnt, w);
     const uint32_t off = index & 63u, t0 = off < 32u ? off : 32u, t1 = off - t0;
     // symbols equal to c among the first t of a 64-bit group: xor with c replicated, then both bits zero
     const uint64_t pat = 0x5555555555555555ull * c;
@@ -446,32 +462,54 @@ HSA_HD uint8_t bound_byte(uint32_t bid, uint32_t w, uint32_t w_prev)
 }
 
 // bwt_cal_width, type 1 (bwtaln.c:73-97, 113-114): `n` bases starting at strand-resolved position `src`.
-// Writes any of: w_out[n+1] (uint32), b_out[n+1] (bound bytes), pair_out[n+1] (bwt_width_t).  Returns bid;
-// lookups += the BWTOccValue calls the reference issues.
+// Writes any of: w_out (uint32 per entry), b_out (bound byte per entry), pair_out (bwt_width_t per entry), n + 1
+// entries each.  w_out / b_out are 16-byte aligned and padded to a multiple of 16 entries: they are written 16
+// bytes at a time (entries past n are zero).  Returns bid; lookups += the BWTOccValue calls the reference issues.
 HSA_HD int32_t cal_width_dev(const DevIndex &ix, const TaskDesc &t, uint32_t src, uint32_t n,
                              uint32_t *w_out, uint8_t *b_out, u32x2 *pair_out, uint32_t &lookups)
 {
     uint32_t k = 0, l = ix.fwd.text_length, w_prev = 0xFFFFFFFFu;
     int32_t bid = 0;
-    for (uint32_t j = 0; j < n; ++j) {
-        const uint32_t c = task_base(t, src + j);
-        if (c < 4) {                                        // BWTSARangeForeward, 2BWT-Interface.c:121-132
-            const uint32_t a = occ1_dev(ix.rev, k, c), b = occ1_dev(ix.rev, l + 1, c);
-            k = ix.fwd.cum[c] + a + 1;
-            l = ix.fwd.cum[c] + b;
-            lookups += 2;
+    for (uint32_t j16 = 0; j16 <= n; j16 += 16) {
+        uint32_t bq[4];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (uint32_t q = 0; q < 4; ++q) {
+            uint32_t wq[4];
+            uint32_t bw = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for (uint32_t r = 0; r < 4; ++r) {
+                const uint32_t j = j16 + 4 * q + r;
+                uint32_t w = 0, byte = 0;
+                if (j < n) {
+                    const uint32_t c = task_base(t, src + j);
+                    if (c < 4) {                            // BWTSARangeForeward, 2BWT-Interface.c:121-132
+                        const uint32_t a = occ1_dev(ix.rev, k, c), b = occ1_dev(ix.rev, l + 1, c);
+                        k = ix.fwd.cum[c] + a + 1;
+                        l = ix.fwd.cum[c] + b;
+                        lookups += 2;
+                    }
+                    if (k > l || c > 3) { k = 0; l = ix.fwd.text_length; ++bid; }
+                    w = l - k + 1;
+                    byte = bound_byte((uint32_t)bid, w, w_prev);
+                    if (pair_out) { u32x2 v; v.x = w; v.y = (uint32_t)bid; pair_out[j] = v; }
+                    w_prev = w;
+                } else if (j == n) {                        // bwtaln.c:113-114
+                    ++bid;
+                    byte = bound_byte((uint32_t)bid, 0, w_prev);
+                    if (pair_out) { u32x2 v; v.x = 0; v.y = (uint32_t)bid; pair_out[j] = v; }
+                }
+                wq[r] = w;
+                bw |= byte << (8 * r);
+            }
+            if (w_out && j16 + 4 * q <= n) st4(w_out + j16 + 4 * q, wq[0], wq[1], wq[2], wq[3]);
+            bq[q] = bw;
         }
-        if (k > l || c > 3) { k = 0; l = ix.fwd.text_length; ++bid; }
-        const uint32_t w = l - k + 1;
-        if (w_out) w_out[j] = w;
-        if (b_out) b_out[j] = bound_byte((uint32_t)bid, w, w_prev);
-        if (pair_out) { u32x2 v; v.x = w; v.y = (uint32_t)bid; pair_out[j] = v; }
-        w_prev = w;
+        if (b_out) st4(b_out + j16, bq[0], bq[1], bq[2], bq[3]);
     }
-    ++bid;                                                  // bwtaln.c:113-114
-    if (w_out) w_out[n] = 0;
-    if (b_out) b_out[n] = bound_byte((uint32_t)bid, 0, w_prev);
-    if (pair_out) { u32x2 v; v.x = 0; v.y = (uint32_t)bid; pair_out[n] = v; }
     return bid;
 }
 
@@ -518,12 +556,15 @@ HSA_HD void width_item(const Params &P, const DevOpt *opts, uint32_t w)
 //                   (bwtgap.c:276-282 / :292-298)
 //   half B (high) : mismatch children, in the bucket of score + s_mm; mask bit j-1 = the reference's loop
 //                   index j = 1..4 (bwtgap.c:303-313; j = 4 exists only when the base is N)
-//   each half = next:NEXT_BITS | mask:5.  Children are taken highest bit first = the reverse of the
-//   reference's push order, as its LIFO buckets do.  A half leaves its bucket list when its mask empties; the
-//   record is freed when both masks are empty.
-enum : uint32_t { PEND_NONE = 0, PEND_DEL = 1, PEND_MM = 2 };
+//   each half = ref:NEXT_BITS+1 | mask:5, ref = slot | membership << NEXT_BITS naming the NEXT list element: a
+//   bucket list threads through halves, and the same refs sit in the bucket heads, so a pop knows which
+//   membership of the head record it is looking at (and the bucket index is the child's score).
+//   Children are taken highest bit first = the reverse of the reference's push order, as its LIFO buckets do.
+//   A half leaves its bucket list when its mask empties; the record is freed when both masks are empty.
+enum : uint32_t { PEND_NONE = 0, PEND_DEL = 4, PEND_MM = 8 };        // | child index in the low two bits
 enum : uint32_t { LS_IDLE = 0, LS_POP = 1, LS_LOOKUP = 2, LS_HIT = 3, LS_END = 4, LS_RETIRED = 5 };
-enum : uint32_t { PHASE_SLOW = 0, PHASE_LOOKUP = 1, PHASE_POP = 2 };
+enum : uint32_t { PHASE_SLOW = 0, PHASE_LOOKUP = 1, PHASE_POP = 2, PHASE_NONE = 3 };
+enum : uint32_t { META_STATE_SHIFT = 13, META_MM_SHIFT = 15, META_GO_SHIFT = 20, META_GE_SHIFT = 24 };
 
 // Which kind of step a warp executes next, from the number of lanes waiting for each kind.  SLOW steps (hit
 // recording, task end, work fetch + task start) are long and rare: they run once enough lanes have queued up
@@ -539,11 +580,14 @@ HSA_HD uint32_t phase_vote(const Params &P, uint32_t n_lookup, uint32_t n_pop, u
 
 template <typename LinkT, bool BIDS_SMEM>
 struct Worker {
-    static constexpr uint32_t HALF_BITS = sizeof(LinkT) * 4;         // 16 (fast kernel) or 32 (large capacity)
-    static constexpr uint32_t NEXT_BITS = HALF_BITS - 5;
+    static constexpr bool WIDE = sizeof(LinkT) == 8;                 // large-capacity configuration
+    static constexpr uint32_t HALF_BITS = WIDE ? 32 : 16;
+    static constexpr uint32_t NEXT_BITS = HALF_BITS - 6;             // 10 (fast: <= 1022 records) or 26
     static constexpr uint32_t NIL = (1u << NEXT_BITS) - 1u;
-    static constexpr uint32_t HALF_MASK = HALF_BITS == 32 ? 0xFFFFFFFFu : ((1u << (HALF_BITS & 31)) - 1u);
-    static constexpr uint32_t HEAD_BYTES = HALF_BITS == 32 ? 4 : 2;
+    static constexpr uint32_t REF_MASK = (1u << (NEXT_BITS + 1)) - 1u;
+    static constexpr uint32_t MASK_SHIFT = NEXT_BITS + 1;
+    static constexpr uint32_t HALF_MASK = WIDE ? 0xFFFFFFFFu : 0xFFFFu;
+    static constexpr uint32_t MAX_BUCKETS = WIDE ? 128 : 64;         // the fast kernel keeps one 64-bit bucket mask
 
     // environment
     const Params &P;
@@ -555,29 +599,34 @@ struct Worker {
     uint32_t work;                  // work-queue index of the current item == its row
     const uint8_t *rd;              // the read
     uint32_t rd_len, strand, sub_off, len, seed_mode, seed_shift, opt_idx, out_idx;
-    int32_t aln_start, aln_end;
     uint8_t *row;                   // the item's row (global)
     // search state
-    uint64_t mask0, mask1;          // non-empty buckets
+    uint64_t mask0, mask1;          // non-empty buckets (mask1: large-capacity configuration only)
     uint32_t n_live, n_phantom;     // entries the reference would hold: stored children; counted-only children
     uint32_t top, free_head;        // arena bump pointer and free list
     int32_t best_score, max_diff, best_cnt;
+    int32_t pop_cut;                // entries above this score end the search when popped (bwtgap.c:158-159)
     uint32_t n_hits;
     uint32_t fail_code;             // != STATUS_OK: the task ran out of capacity / hit a sizing error
     // candidate node
-    uint32_t direct, exact, pend, pend_j;
+    bool direct, exact, c_diff;
+    uint32_t pend;                  // PEND_*: the interval registers hold the PARENT's, child pend & 3
     uint32_t ck, cl, crl;           // k, l, rev_l  (rev_k == rev_l - (l - k))
-    uint32_t ci, c_mm, c_gapo, c_gape, c_state, c_diff;
+    uint32_t ci;
+    uint32_t c_meta;                // state / n_mm / n_gapo / n_gape in the stack record's bit layout
+    int32_t c_score;                // aln_score(n_mm, n_gapo, n_gape)
+    int32_t c_nd;                   // n_mm + n_gapo (+ n_gape with MODE_GAPE): the diffs bwtgap.c:161-164 counts
     uint32_t ci_at_pop;             // e.info & 0xffff of the entry being processed (for last_diff_pos)
     uint32_t zflags;                // which of k,l,rev_k,rev_l were zero when bwt_match_exact was entered
-    int32_t m_cur, m_seed_cur;      // remaining diffs of the candidate (bwtgap.c:161-171), set by vet()
+    int32_t m_cur;                  // remaining diffs of the candidate (bwtgap.c:161-164), set by vet()
     // statistics
     uint32_t lookups_item;          // occ lookups of the current item's search
+    uint32_t steps32, pops32;
     uint64_t lookups, pops, steps;
-    uint32_t steps_item0, max_item_steps;
+    uint32_t max_item_steps;
 
     HSA_HD Worker(const Params &p, uint32_t slot_, uint32_t lane_in_block)
-        : P(p), slot(slot_), st(LS_IDLE), lookups(0), pops(0), steps(0), steps_item0(0), max_item_steps(0)
+        : P(p), slot(slot_), st(LS_IDLE), steps32(0), pops32(0), lookups(0), pops(0), steps(0), max_item_steps(0)
     {
         sm_heads = P.smem_opts_bytes + lane_in_block * P.smem_lane_stride;
         sm_bid = sm_heads + P.smem_bid_off;
@@ -589,13 +638,13 @@ struct Worker {
     // ---------------------------------------------------------------- small accessors
     HSA_HD uint32_t head_get(uint32_t b) const
     {
-        if (HEAD_BYTES == 2) return reinterpret_cast<const uint16_t *>(HSA_SMEM + sm_heads)[b];
+        if (!WIDE) return reinterpret_cast<const uint16_t *>(HSA_SMEM + sm_heads)[b];
         return reinterpret_cast<const uint32_t *>(HSA_SMEM + sm_heads)[b];
     }
-    HSA_HD void head_set(uint32_t b, uint32_t s)
+    HSA_HD void head_set(uint32_t b, uint32_t ref)
     {
-        if (HEAD_BYTES == 2) reinterpret_cast<uint16_t *>(HSA_SMEM + sm_heads)[b] = (uint16_t)s;
-        else reinterpret_cast<uint32_t *>(HSA_SMEM + sm_heads)[b] = s;
+        if (!WIDE) reinterpret_cast<uint16_t *>(HSA_SMEM + sm_heads)[b] = (uint16_t)ref;
+        else reinterpret_cast<uint32_t *>(HSA_SMEM + sm_heads)[b] = ref;
     }
     // bound bytes: width_back entry i / width_seed entry i
     HSA_HD uint32_t bb(uint32_t i) const { return BIDS_SMEM ? HSA_SMEM[sm_bid + i] : row[P.row_bid_off + i]; }
@@ -610,38 +659,54 @@ struct Worker {
     }
     HSA_HD u32x4 *arena() const { return P.arena + (size_t)slot * P.arena_cap; }
     HSA_HD LinkT *links() const { return reinterpret_cast<LinkT *>(P.links) + (size_t)slot * P.arena_cap; }
-    HSA_HD bool bucket_nonempty(uint32_t b) const { return b < 64 ? (mask0 >> b) & 1ull : (mask1 >> (b - 64)) & 1ull; }
-    HSA_HD void bucket_set(uint32_t b) { if (b < 64) mask0 |= 1ull << b; else mask1 |= 1ull << (b - 64); }
-    HSA_HD void bucket_clear(uint32_t b) { if (b < 64) mask0 &= ~(1ull << b); else mask1 &= ~(1ull << (b - 64)); }
+    HSA_HD bool bucket_nonempty(uint32_t b) const
+    {
+        if (!WIDE) return (mask0 >> b) & 1ull;
+        return b < 64 ? (mask0 >> b) & 1ull : (mask1 >> (b - 64)) & 1ull;
+    }
+    HSA_HD void bucket_set(uint32_t b)
+    {
+        if (!WIDE) mask0 |= 1ull << b;
+        else if (b < 64) mask0 |= 1ull << b; else mask1 |= 1ull << (b - 64);
+    }
+    HSA_HD void bucket_clear(uint32_t b)
+    {
+        if (!WIDE) mask0 &= ~(1ull << b);
+        else if (b < 64) mask0 &= ~(1ull << b); else mask1 &= ~(1ull << (b - 64));
+    }
+    HSA_HD uint32_t bucket_lowest() const
+    {
+        if (!WIDE) return (uint32_t)ffs64(mask0);
+        return mask0 ? (uint32_t)ffs64(mask0) : 64u + (uint32_t)ffs64(mask1);
+    }
     HSA_HD bool idle() const { return st == LS_IDLE; }
     HSA_HD bool retired() const { return st == LS_RETIRED; }
     HSA_HD void retire() { st = LS_RETIRED; }
     HSA_HD uint32_t cls() const          // which phase this lane waits for
     {
-        return st == LS_LOOKUP ? PHASE_LOOKUP : st == LS_POP ? PHASE_POP : PHASE_SLOW;
+        return st == LS_LOOKUP ? PHASE_LOOKUP : st == LS_POP ? PHASE_POP : st == LS_RETIRED ? PHASE_NONE : PHASE_SLOW;
     }
+    HSA_HD uint32_t c_state() const { return (c_meta >> META_STATE_SHIFT) & 3u; }
+    HSA_HD uint32_t c_mm() const { return (c_meta >> META_MM_SHIFT) & 31u; }
+    HSA_HD uint32_t c_gapo() const { return (c_meta >> META_GO_SHIFT) & 15u; }
+    HSA_HD uint32_t c_gape() const { return (c_meta >> META_GE_SHIFT) & 31u; }
 
     // base p of the strand-resolved read (seq_reverse(len, seq, 1): bwaseqio.c:73-90)
     HSA_HD uint32_t base_at(uint32_t p) const
     {
-        if (strand) { uint32_t c = ld_ro_u8(rd + (rd_len - 1 - p)); return c < 4 ? 3 - c : c; }
-        return ld_ro_u8(rd + p);
+        const uint32_t c = ld_ro_u8(strand ? rd + (rd_len - 1 - p) : rd + p);
+        return (strand && c < 4) ? 3 - c : c;
     }
     HSA_HD void fail(uint32_t code) { if (fail_code == STATUS_OK) fail_code = code; }
-    HSA_HD bool phantom(int32_t sc) const     // bwtgap.c:158-159: can never be popped once a hit exists
-    {
-        return n_hits && !(opt().mode & MODE_NONSTOP) && sc > best_score + opt().s_mm;
-    }
 
     // ---------------------------------------------------------------- START: next work item in
     HSA_HD void start(uint32_t work_idx)
     {
         work = work_idx;
-        steps_item0 = (uint32_t)steps;
         const DevOpt *opts = reinterpret_cast<const DevOpt *>(HSA_SMEM);
         const TaskDesc t = make_task(P, opts, work_item(P, work_idx));
         rd = t.rd; rd_len = t.rd_len; strand = t.strand; sub_off = t.sub_off; len = t.len;
-        seed_mode = t.seed_mode; opt_idx = t.opt_idx; out_idx = t.out_idx; aln_start = t.aln_start; aln_end = t.aln_end;
+        seed_mode = t.seed_mode; opt_idx = t.opt_idx; out_idx = t.out_idx;
         row = P.rows + (size_t)work * P.row_stride;
         const uint32_t *tail = reinterpret_cast<const uint32_t *>(row + P.row_tail_off);
         if (tail[1] & ROW_FLAG_FILTERED) { st = LS_IDLE; return; }       // filtered by the width kernel (pass 1)
@@ -657,14 +722,15 @@ struct Worker {
                 for (uint32_t j = 0; j < ((uint32_t)o.seed_len + 4) / 4; ++j) d2[j] = s2[j];
             }
         }
-        lookups_item = 0; fail_code = STATUS_OK;
+        lookups_item = 0; steps32 = 0; pops32 = 0; fail_code = STATUS_OK;
         mask0 = mask1 = 0; n_live = 0; n_phantom = 0; top = 0; free_head = NIL;
         best_score = (o.max_diff + 1) * o.s_mm + (o.max_gapo + 1) * o.s_gapo + (o.max_gape + 1) * o.s_gape; // :128
+        pop_cut = (o.mode & MODE_NONSTOP) ? 0x7FFFFFFF : best_score + o.s_mm;
         max_diff = o.max_diff; best_cnt = 0; n_hits = 0;
         // root (bwtgap.c:142) is the first node popped; carry it directly
-        direct = 1; exact = 0; pend = PEND_NONE; pend_j = 0;
+        direct = true; exact = false; pend = PEND_NONE; c_diff = false;
         ck = 0; cl = P.ix.fwd.text_length; crl = P.ix.fwd.text_length;
-        ci = len; c_mm = c_gapo = c_gape = 0; c_state = ST_M; c_diff = 0; zflags = 0; ci_at_pop = len;
+        ci = len; c_meta = 0; c_score = 0; c_nd = 0; zflags = 0; ci_at_pop = len;
         vet();
         if (st == LS_POP) st = LS_END;                     // root pruned (wrong strand): the stack is empty
     }
@@ -678,13 +744,10 @@ struct Worker {
         if (direct) {
             // the carried child would have been pushed and popped: same loop-top test, entry included (:150-151)
             if ((int64_t)n_live + n_phantom + 1 > (int64_t)o.max_entries) { st = LS_END; return; }
-            direct = 0;
+            direct = false;
         }
-        m_cur = max_diff - (int32_t)(c_mm + c_gapo);                                  // :161-164
-        if (o.mode & MODE_GAPE) m_cur -= (int32_t)c_gape;
+        m_cur = max_diff - c_nd;                                                     // :161-164
         if (m_cur < 0) { st = LS_POP; return; }
-        m_seed_cur = o.max_seed_diff - (int32_t)(c_mm + c_gapo);                     // :167-171
-        if (o.mode & MODE_GAPE) m_seed_cur -= (int32_t)c_gape;
         if (ci > 0 && m_cur < (int32_t)(bb(ci - 1) & 63u)) { st = LS_POP; return; }   // :172-173
         if (pend) { st = LS_LOOKUP; return; }              // survived pop-time pruning: materialise it first
         classify();
@@ -696,8 +759,8 @@ struct Worker {
         const DevOpt &o = opt();
         ci_at_pop = ci;
         if (ci == 0) { st = LS_HIT; return; }                                         // :177-179
-        if (m_cur == 0 && (c_state == ST_M || (o.mode & MODE_GAPE) || (int32_t)c_gape == o.max_gape)) {   // :180
-            exact = 1;
+        if (m_cur == 0 && (c_state() == ST_M || (o.mode & MODE_GAPE) || (int32_t)c_gape() == o.max_gape)) {   // :180
+            exact = true;
             zflags = (ck == 0) | (cl == 0) << 1 | (crl - (cl - ck) == 0) << 2 | (crl == 0) << 3;
         }
         st = LS_LOOKUP;
@@ -707,48 +770,54 @@ struct Worker {
     HSA_HD void do_pop()
     {
         const DevOpt &o = opt();
-        ++steps;
+        ++steps32;
         // loop top of bwtgap.c:144-159
         if (n_live == 0 || (int64_t)n_live + n_phantom > (int64_t)o.max_entries) { st = LS_END; return; }
-        const uint32_t b = mask0 ? (uint32_t)ffs64(mask0) : 64u + (uint32_t)ffs64(mask1);
+        const uint32_t b = bucket_lowest();
         LinkT *lk = links();
-        const uint32_t s = head_get(b);
+        const uint32_t ref = head_get(b);
+        const uint32_t s = ref & NIL;
+        const bool isB = (ref >> NEXT_BITS) != 0;
         const u32x4 e = arena()[s];
         const LinkT lw = lk[s];
-        ++pops;
+        ++pops32;
         --n_live;
-        if (!(o.mode & MODE_NONSTOP) && (int32_t)b > best_score + o.s_mm) { st = LS_END; return; }   // :158-159
-        const uint32_t pi = e.w & 0xFFFu, pst = (e.w >> 13) & 3u;
-        const uint32_t pmm = (e.w >> 15) & 31u, pgo = (e.w >> 20) & 15u, pge = (e.w >> 24) & 31u;
-        const int32_t msc = (int32_t)pmm * o.s_mm + (int32_t)pgo * o.s_gapo + (int32_t)pge * o.s_gape + o.s_mm;
+        if ((int32_t)b > pop_cut) { st = LS_END; return; }                            // :158-159
         uint32_t halfA = (uint32_t)(lw & (LinkT)HALF_MASK), halfB = (uint32_t)(lw >> HALF_BITS);
-        // when both memberships share a bucket the mismatch children were pushed last, so they come first
-        const bool isB = (int32_t)b == msc && (halfB >> NEXT_BITS) != 0;
         uint32_t half = isB ? halfB : halfA;
-        uint32_t cmask = half >> NEXT_BITS;
-        const uint32_t nx = half & NIL;
+        uint32_t cmask = half >> MASK_SHIFT;
+        const uint32_t nref = half & REF_MASK;
         const uint32_t j = 31u - (uint32_t)clz32(cmask);                // last pushed child first
         cmask &= ~(1u << j);
-        half = nx | cmask << NEXT_BITS;
+        half = nref | cmask << MASK_SHIFT;
         if (isB) halfB = half; else halfA = half;
+        LinkT nw = (LinkT)halfA | (LinkT)halfB << HALF_BITS;
         if (cmask == 0) {
             // this membership is exhausted: it leaves its bucket list
-            if (nx == NIL) bucket_clear(b); else head_set(b, nx);
-            const uint32_t other = isB ? halfA >> NEXT_BITS : halfB >> NEXT_BITS;
-            if (other == 0) { lk[s] = (LinkT)free_head; free_head = s; }
-            else lk[s] = (LinkT)halfA | (LinkT)halfB << HALF_BITS;
-        } else lk[s] = (LinkT)halfA | (LinkT)halfB << HALF_BITS;
-        // the child (bwtgap.c:267-314) as a candidate
-        ck = e.x; cl = e.y; crl = e.z;
-        c_mm = pmm; c_gapo = pgo; c_gape = pge;
-        c_diff = 1; direct = 0; exact = 0;
-        if (isB) {                                          // mismatch j+1 (bwtgap.c:303-313)
-            ci = pi - 1; ++c_mm; c_state = ST_M; pend = PEND_MM; pend_j = j;
-        } else {
-            if (pst == ST_M) ++c_gapo; else ++c_gape;       // gap open (:274,:281) / extension (:284,:297)
-            if (j == 0) { ci = pi - 1; c_state = ST_I; pend = PEND_NONE; pend_j = 0; }   // insertion: same interval
-            else { ci = pi; c_state = ST_D; pend = PEND_DEL; pend_j = j - 1; }       // deletion of symbol j-1
+            if ((nref & NIL) == NIL) bucket_clear(b); else head_set(b, nref);
+            const uint32_t other = isB ? halfA >> MASK_SHIFT : halfB >> MASK_SHIFT;
+            if (other == 0) { nw = (LinkT)free_head; free_head = s; }
         }
+        lk[s] = nw;
+        // the child (bwtgap.c:267-314) as a candidate; its score is the bucket it was filed under
+        const uint32_t pm = e.w;
+        const uint32_t pi = pm & 0xFFFu, pst = (pm >> META_STATE_SHIFT) & 3u;
+        const bool gape_counts = (o.mode & MODE_GAPE) != 0;
+        ck = e.x; cl = e.y; crl = e.z;
+        c_score = (int32_t)b;
+        c_nd = (int32_t)(((pm >> META_MM_SHIFT) & 31u) + ((pm >> META_GO_SHIFT) & 15u) +
+                         (gape_counts ? (pm >> META_GE_SHIFT) & 31u : 0u));
+        c_diff = true; direct = false; exact = false;
+        uint32_t m = pm & ~(0xFFFu | 3u << META_STATE_SHIFT);          // counts only, state M
+        if (isB) {                                          // mismatch j+1 (bwtgap.c:303-313)
+            ci = pi - 1; m += 1u << META_MM_SHIFT; ++c_nd; pend = PEND_MM | j;
+        } else {
+            if (pst == ST_M) { m += 1u << META_GO_SHIFT; ++c_nd; }          // gap open (:274, :281)
+            else { m += 1u << META_GE_SHIFT; c_nd += gape_counts ? 1 : 0; } // gap extension (:284, :297)
+            if (j == 0) { ci = pi - 1; m |= ST_I << META_STATE_SHIFT; pend = PEND_NONE; }        // insertion: same interval
+            else { ci = pi; m |= ST_D << META_STATE_SHIFT; pend = PEND_DEL | (j - 1); }       // deletion of symbol j-1
+        }
+        c_meta = m;
         vet();
     }
 
@@ -756,16 +825,17 @@ struct Worker {
     HSA_HD void do_lookup()
     {
         const DevOpt &o = opt();
-        ++steps;
+        ++steps32;
         // ---- the one memory operation every kind of step shares: occ4 at k and at l + 1 -----------------
         const DevBwt &B = P.ix.fwd;
         uint32_t pk = ck, pl = cl + 1;
         pk -= (pk > B.inverse_sa0); pl -= (pl > B.inverse_sa0);
-        const u32x4 kc = ld_ro4(B.blocks + 2 * (size_t)(pk >> 6)), kw = ld_ro4(B.blocks + 2 * (size_t)(pk >> 6) + 1);
-        const u32x4 lc = ld_ro4(B.blocks + 2 * (size_t)(pl >> 6)), lw = ld_ro4(B.blocks + 2 * (size_t)(pl >> 6) + 1);
+        u32x4 kc, kw, lc, lw;
+        ld_sector(B.blocks + 2 * (size_t)(pk >> 6), kc, kw);
+        ld_sector(B.blocks + 2 * (size_t)(pl >> 6), lc, lw);
         // i: index of the base the lookup extends by.  For a pending child the lookup is the PARENT's: deletion
         // children have ci == the parent's pre-decrement i, mismatch children ci == its post-decrement i.
-        const uint32_t i = pend == PEND_MM ? ci : ci - 1;
+        const uint32_t i = (pend & PEND_MM) ? ci : ci - 1;
         const uint32_t sc_ = base_at(sub_off + i);
         uint32_t oL[4], oR[4], sk[4], sl[4], rsl[4];
         occ4_from_sector(kc, kw, pk & 63u, oL);
@@ -782,8 +852,8 @@ struct Worker {
         }
         const uint32_t vmask = (uint32_t)(sk[0] <= sl[0]) | (uint32_t)(sk[1] <= sl[1]) << 1 |
                                (uint32_t)(sk[2] <= sl[2]) << 2 | (uint32_t)(sk[3] <= sl[3]) << 3;
-        // the one child every kind of step continues with
-        const uint32_t csel = (pend == PEND_DEL ? pend_j : pend == PEND_MM ? sc_ + pend_j + 1u : sc_) & 3u;
+        // the one child every kind of step continues with: the pending child, else the read's base
+        const uint32_t csel = ((pend & PEND_DEL) ? pend : (pend & PEND_MM) ? sc_ + pend + 1u : sc_) & 3u;
         const uint32_t nk = sel4(sk, csel), nl = sel4(sl, csel), nr = sel4(rsl, csel);
         const bool alive = (vmask >> csel) & 1u;
 
@@ -805,8 +875,7 @@ struct Worker {
 
         // ---- node expansion (bwtgap.c:244-325) --------------------------------------------------------
         lookups_item += 2;
-        const int32_t m = m_cur, m_seed = m_seed_cur;
-        const uint32_t occ = cl - ck + 1;
+        const int32_t m = m_cur;
         bool allow_diff = true, allow_M = true;
         if (i > 0) {                                                                        // :252-265
             const uint32_t b0 = bb(i - 1), b1 = bb(i);
@@ -814,15 +883,15 @@ struct Worker {
             else if ((int32_t)(b0 & 63u) == m - 1 && (int32_t)(b1 & 63u) == m - 1 && (b1 & 0x80u)) allow_M = false;
             const int32_t ii = (int32_t)i - (int32_t)seed_shift;                            // :253
             if (seed_mode != SEED_NONE && ii > 0) {
+                const int32_t m_seed = o.max_seed_diff - c_nd;                              // :167-171
                 const uint32_t s0 = bs((uint32_t)ii - 1), s1 = bs((uint32_t)ii);
                 if ((int32_t)(s0 & 63u) > m_seed - 1) allow_diff = false;
                 else if ((int32_t)(s0 & 63u) == m_seed - 1 && (int32_t)(s1 & 63u) == m_seed - 1 && (s1 & 0x80u)) allow_M = false;
             }
         }
-        const uint32_t e_mm = c_mm, e_go = c_gapo, e_ge = c_gape, e_state = c_state;
-        const int32_t e_score = (int32_t)e_mm * o.s_mm + (int32_t)e_go * o.s_gapo + (int32_t)e_ge * o.s_gape;
-        uint32_t maskA = 0, maskB = 0;
         if (allow_diff) {
+            const uint32_t e_go = c_gapo(), e_ge = c_gape(), e_state = c_state();
+            uint32_t maskA = 0, maskB = 0;
             int32_t tmp;
             if (o.mode & MODE_LOGGAP) {                                                     // :267 + int_log2 :107-116
                 uint32_t v = e_ge + e_go; int32_t lg = 0;
@@ -834,52 +903,56 @@ struct Worker {
                 if (e_state == ST_M) ins = del = (int32_t)e_go < o.max_gapo;               // :269-282
                 else if (e_state == ST_I) ins = (int32_t)e_ge < o.max_gape;                // :283-285
                 else del = (int32_t)e_ge < o.max_gape &&                                   // :286-299
-                           ((int32_t)(e_ge + e_go) < max_diff || occ < (uint32_t)o.max_del_occ);
+                           ((int32_t)(e_ge + e_go) < max_diff || cl - ck + 1 < (uint32_t)o.max_del_occ);
                 maskA = (ins ? 1u : 0u) | (del ? vmask << 1 : 0u);
             }
             if (allow_M) {                                                                  // :302-314
                 // children j = 1..3 (and j = 4 when seq[i] is N) are mismatches: bit j-1
-                for (uint32_t j = 1; j <= 3; ++j) maskB |= ((vmask >> ((sc_ + j) & 3u)) & 1u) << (j - 1);
-                if (sc_ > 3) maskB |= ((vmask >> (sc_ & 3u)) & 1u) << 3;
+                maskB = ((vmask >> ((sc_ + 1u) & 3u)) & 1u) | ((vmask >> ((sc_ + 2u) & 3u)) & 1u) << 1 |
+                        ((vmask >> ((sc_ + 3u) & 3u)) & 1u) << 2 | (sc_ > 3 ? (vmask & 1u) << 3 : 0u);
             }
-        }
-        const int32_t gsc = e_score + (e_state == ST_M ? o.s_gapo : o.s_gape), msc = e_score + o.s_mm;
-        uint32_t nA = (uint32_t)popc32(maskA), nB = (uint32_t)popc32(maskB);
-        if (nA && phantom(gsc)) { n_phantom += nA; maskA = 0; nA = 0; }
-        if (nB && phantom(msc)) { n_phantom += nB; maskB = 0; nB = 0; }
-        if (maskA | maskB) {
-            if ((maskA && (uint32_t)gsc >= P.n_buckets) || (maskB && (uint32_t)msc >= P.n_buckets)) fail(STATUS_BAD_SCORE);
-            else {
-                uint32_t s = NIL;
-                LinkT *lk = links();
-                if (free_head != NIL) { s = free_head; free_head = (uint32_t)(lk[s] & (LinkT)NIL); }
-                else if (top < P.arena_cap) s = top++;
-                else fail(STATUS_NEED_STRICT);
-                if (s != NIL) {
-                    u32x4 e;
-                    e.x = ck; e.y = cl; e.z = crl;
-                    e.w = (i + 1) | e_state << 13 | e_mm << 15 | e_go << 20 | e_ge << 24;
-                    arena()[s] = e;
-                    uint32_t halfA = NIL, halfB = NIL;
-                    if (maskA) {
-                        halfA = (bucket_nonempty((uint32_t)gsc) ? head_get((uint32_t)gsc) : NIL) | maskA << NEXT_BITS;
-                        head_set((uint32_t)gsc, s); bucket_set((uint32_t)gsc);
+            const int32_t gsc = c_score + (e_state == ST_M ? o.s_gapo : o.s_gape), msc = c_score + o.s_mm;
+            const int32_t cut = n_hits ? pop_cut : 0x7FFFFFFF;      // bwtgap.c:158-159: can never be popped -> count only
+            uint32_t nA = (uint32_t)popc32(maskA), nB = (uint32_t)popc32(maskB);
+            if (gsc > cut) { n_phantom += nA; maskA = 0; nA = 0; }
+            if (msc > cut) { n_phantom += nB; maskB = 0; nB = 0; }
+            if (maskA | maskB) {
+                if ((maskA && (uint32_t)gsc >= P.n_buckets) || (maskB && (uint32_t)msc >= P.n_buckets))
+                    fail(WIDE ? STATUS_BAD_SCORE : STATUS_NEED_STRICT);      // the fast kernel has 64 buckets
+                else {
+                    uint32_t s = NIL;
+                    LinkT *lk = links();
+                    if (free_head != NIL) { s = free_head; free_head = (uint32_t)(lk[s] & (LinkT)NIL); }
+                    else if (top < P.arena_cap) s = top++;
+                    else fail(STATUS_NEED_STRICT);
+                    if (s != NIL) {
+                        u32x4 e;
+                        e.x = ck; e.y = cl; e.z = crl; e.w = c_meta | (i + 1);
+                        arena()[s] = e;
+                        uint32_t halfA = NIL, halfB = NIL;
+                        if (maskA) {
+                            halfA = (bucket_nonempty((uint32_t)gsc) ? head_get((uint32_t)gsc) : NIL) | maskA << MASK_SHIFT;
+                            head_set((uint32_t)gsc, s); bucket_set((uint32_t)gsc);
+                        }
+                        if (maskB) {    // after A: if both share a bucket, B links to the record's own half A
+                            halfB = (bucket_nonempty((uint32_t)msc) ? head_get((uint32_t)msc) : NIL) | maskB << MASK_SHIFT;
+                            head_set((uint32_t)msc, s | 1u << NEXT_BITS); bucket_set((uint32_t)msc);
+                        }
+                        lk[s] = (LinkT)halfA | (LinkT)halfB << HALF_BITS;
+                        n_live += nA + nB;
                     }
-                    if (maskB) {        // after A: if both share a bucket, B links to the record itself
-                        halfB = (bucket_nonempty((uint32_t)msc) ? head_get((uint32_t)msc) : NIL) | maskB << NEXT_BITS;
-                        head_set((uint32_t)msc, s); bucket_set((uint32_t)msc);
-                    }
-                    lk[s] = (LinkT)halfA | (LinkT)halfB << HALF_BITS;
-                    n_live += nA + nB;
                 }
+                if (fail_code != STATUS_OK) { st = LS_END; return; }
             }
         }
-        if (fail_code != STATUS_OK) { st = LS_END; return; }
         // the exact-match child (bwtgap.c:303-313 with j = 4, or :315-325): would be pushed last into the lowest
-        // bucket and popped next -> it stays in registers
+        // bucket and popped next -> it stays in registers.  Same counts as its parent, so m_cur stands.
         if (sc_ < 4 && alive) {
-            ck = nk; cl = nl; crl = nr; ci = i; c_state = ST_M; c_diff = 0; direct = 1;
-            vet();
+            ck = nk; cl = nl; crl = nr; ci = i; c_diff = false;
+            c_meta &= ~(3u << META_STATE_SHIFT);            // STATE_M
+            if ((int64_t)n_live + n_phantom + 1 > (int64_t)o.max_entries) { st = LS_END; return; }   // :150-151
+            if (ci > 0 && m < (int32_t)(bb(ci - 1) & 63u)) { st = LS_POP; return; }                  // :172-173
+            classify();
         } else st = LS_POP;
     }
 
@@ -896,17 +969,19 @@ struct Worker {
             if (zflags & 8u) rl = 0;
         }
         st = LS_POP;
-        const int32_t score = (int32_t)c_mm * o.s_mm + (int32_t)c_gapo * o.s_gapo + (int32_t)c_gape * o.s_gape;
+        const int32_t score = c_score;
         Hit *hs = P.hits + (size_t)slot * P.hit_cap;
         if (n_hits == 0) {
             best_score = score;
-            int32_t best_diff = (int32_t)(c_mm + c_gapo);
-            if (o.mode & MODE_GAPE) best_diff += (int32_t)c_gape;
-            if (!(o.mode & MODE_NONSTOP)) max_diff = (best_diff + 1 > o.max_diff) ? o.max_diff : best_diff + 1;
+            const int32_t best_diff = c_nd;                 // n_mm + n_gapo (+ n_gape with MODE_GAPE), :192-196
+            if (!(o.mode & MODE_NONSTOP)) {
+                max_diff = (best_diff + 1 > o.max_diff) ? o.max_diff : best_diff + 1;
+                pop_cut = best_score + o.s_mm;
+            }
         }
         if (score == best_score) best_cnt = (int32_t)((uint32_t)best_cnt + (l - k + 1));
         else if (best_cnt > o.max_top2) { st = LS_END; return; }                      // top2b break
-        if (c_gapo)
+        if (c_gapo())
             for (uint32_t j = 0; j < n_hits; ++j)
                 if (hs[j].k == k && hs[j].l == l) return;                              // :205-213 already found
         // gap_shadow (bwtgap.c:94-105) on width_back, in place; the bound bytes follow
@@ -924,7 +999,7 @@ struct Worker {
         if (n_hits >= P.hit_cap) { fail(STATUS_NEED_STRICT); st = LS_END; return; }
         Hit h;
         h.k = k; h.l = l; h.rev_k = rk; h.rev_l = rl;
-        h.counts = c_mm | c_gapo << 16 | c_gape << 24;
+        h.counts = c_mm() | c_gapo() << 16 | c_gape() << 24;
         h.score = score; h.pad0 = h.pad1 = 0;
         hs[n_hits++] = h;
     }
@@ -948,7 +1023,7 @@ struct Worker {
                 w[0] = h.counts; w[1] = h.k; w[2] = h.l; w[3] = h.rev_k; w[4] = h.rev_l;
                 w[5] = strand_stamp << 30;                       // type:30 = 0, strand:2
                 int32_t s0 = 0, e0 = 0;
-                if (P.kind == KIND_SEEDS) { s0 = aln_start; e0 = aln_end; }                 // bwtgap.c:816-819
+                if (P.kind == KIND_SEEDS) { s0 = (int32_t)sub_off; e0 = (int32_t)(sub_off + len - 1); }   // bwtgap.c:816-819
                 else if (P.kind == KIND_WHOLE && j == 0) { s0 = 0; e0 = (int32_t)rd_len - 1; } // bwtaln.c:371-372
                 w[6] = (uint32_t)s0; w[7] = (uint32_t)e0; w[8] = (uint32_t)h.score;
             }
@@ -960,8 +1035,8 @@ struct Worker {
 
     HSA_HD void do_end()
     {
-        const uint32_t d = (uint32_t)steps - steps_item0;
-        if (d > max_item_steps) max_item_steps = d;
+        if (steps32 > max_item_steps) max_item_steps = steps32;
+        steps += steps32; pops += pops32;
         st = LS_IDLE;
         if (fail_code != STATUS_OK) {
             // discard what this item produced; the host re-runs it with the large-capacity kernel

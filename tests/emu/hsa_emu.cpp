@@ -44,6 +44,8 @@ static size_t g_item_steps_pos = 0;
 // SIMT simulation (diagnostic): 32 workers stepped in lockstep under phase_vote(); counts how often each phase
 // runs and how many lanes take part, so scheduling policies can be compared on the CPU.
 static int g_simt = 0;
+static uint32_t g_rerun_cap = 0;                 // 0 = report flagged items instead of re-running them
+static uint64_t g_flagged_first = 0;
 static uint32_t g_vote_slow_min = VOTE_SLOW_MIN_DEFAULT; static int32_t g_vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
 static uint64_t g_phase_runs[3], g_phase_lanes[3];
 
@@ -156,58 +158,70 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
         if (b > nb) nb = b;
     }
     if (nb > 128) return -1;
-    // arena_cap <= 2046: the fast configuration (16-bit link halves, bound bytes in "shared memory");
-    // larger: the large-capacity configuration (32-bit halves, bound bytes read from the rows)
-    const bool wide = arena_cap > 2046;
+    // arena_cap <= 1022: the fast configuration (16-bit link halves, 64 buckets, bound bytes in "shared memory");
+    // larger: the large-capacity configuration (32-bit halves, bound bytes read from the rows).  As in
+    // hsa_b200.cu's run_batch, items the fast configuration flags are re-run with the large one when
+    // `rerun_cap` is set (emu_set_rerun).
     const int lanes = g_simt ? 32 : 1;
-    const uint32_t per = kind == KIND_SEEDS ? 6u : 1u, n_work = n_groups * per;
+    const uint32_t per = kind == KIND_SEEDS ? 6u : 1u, n_work_all = n_groups * per;
     uint32_t max_seed = 0;
     for (uint32_t i = 0; i < n_opts; ++i)
         if (opts[i].seed_len > 0 && (uint32_t)opts[i].seed_len < max_len) max_seed = std::max(max_seed, (uint32_t)opts[i].seed_len);
     const uint32_t seed_cap = (kind == KIND_TASKS || kind == KIND_WHOLE) && max_seed ? max_seed + 1 : 0;
-
-    Params P;
-    memset(&P, 0, sizeof(P));
-    set_layout(P, max_len, seed_cap, nb, n_opts ? n_opts : 1, wide ? 4 : 2, !wide);
-    std::vector<unsigned char> smem((size_t)P.smem_opts_bytes + (size_t)lanes * P.smem_lane_stride + 16);
-    memcpy(smem.data(), dopts.data(), dopts.size() * sizeof(DevOpt));
-    hsa_smem_host = smem.data();
-    std::vector<u32x4> arena((size_t)arena_cap * lanes);
-    std::vector<uint64_t> links((size_t)arena_cap * lanes);          // large enough for either link width
-    std::vector<Hit> hits((size_t)hit_cap * lanes);
-    std::vector<uint32_t> strict(n_work + 1);
-    std::vector<unsigned char> rows((size_t)std::max(n_work, 1u) * P.row_stride);
-    std::vector<uint32_t> next_list(n_groups + 1);
-    uint32_t next_count = 0;
+    std::vector<uint32_t> strict(n_work_all + 1), strict_in;
     unsigned long long counters[CNT_TOTAL];
     memset(counters, 0, sizeof(counters));
-
-    P.ix = e->ix; P.codes = codes; P.kind = kind;
-    P.tasks = (const Task *)tasks; P.read_off = read_off; P.read_len = read_len;
-    P.opts = dopts.data(); P.len2opt = len2opt; P.filter_max_n = filter_max_n;
-    P.rows = rows.data();
-    P.arena = arena.data(); P.links = links.data(); P.arena_cap = arena_cap;
-    P.hits = hits.data(); P.hit_cap = hit_cap;
-    P.n_aln = n_aln; P.aln_off = aln_off; P.status = status; P.aln = aln; P.aln_cap = aln_cap;
-    P.counters = counters; P.strict_list = strict.data();
-    P.width_out = (u32x2 *)width_out; P.bid_out = bid_out;
-    P.vote_slow_min = g_vote_slow_min; P.vote_pop_bias = g_vote_pop_bias;
-
     uint64_t st[4] = {0, 0, 0, 0};
-    unsigned long long cursor = 0;
-    P.cursor = &cursor;
-    // the split pipeline, launch for launch as hsa_b200.cu's run_batch enqueues it
-    P.pass = 1; P.work_base = 0; P.work_list = nullptr; P.n_work = n_work;
-    P.next_list = next_list.data(); P.next_count = &next_count;
-    for (uint32_t w = 0; w < n_work; ++w) width_item(P, dopts.data(), w);
-    if (kind != KIND_WIDTH) {
-        if (wide) run_worker<uint64_t, false>(P, n_work, st); else run_worker<uint32_t, true>(P, n_work, st);
-        if (kind == KIND_WHOLE) {
-            P.pass = 2; P.work_list = next_list.data(); P.n_work = next_count; P.next_list = nullptr; P.next_count = nullptr;
-            for (uint32_t w = 0; w < next_count; ++w) width_item(P, dopts.data(), w);
-            if (wide) run_worker<uint64_t, false>(P, next_count, st); else run_worker<uint32_t, true>(P, next_count, st);
+    uint64_t flagged_first = 0;
+
+    for (int round = 0; round < 2; ++round) {
+        const uint32_t cap = round == 0 ? arena_cap : g_rerun_cap;
+        const uint32_t hcap = round == 0 ? hit_cap : 4096u;
+        const bool wide = cap > 1022;
+        const uint32_t n_work = round == 0 ? n_work_all : (uint32_t)strict_in.size();
+        Params P;
+        memset(&P, 0, sizeof(P));
+        set_layout(P, max_len, seed_cap, wide ? nb : std::min(nb, 64u), n_opts ? n_opts : 1, wide ? 4 : 2, !wide);
+        std::vector<unsigned char> smem((size_t)P.smem_opts_bytes + (size_t)lanes * P.smem_lane_stride + 16);
+        memcpy(smem.data(), dopts.data(), dopts.size() * sizeof(DevOpt));
+        hsa_smem_host = smem.data();
+        std::vector<u32x4> arena((size_t)cap * lanes);
+        std::vector<uint64_t> links((size_t)cap * lanes);          // large enough for either link width
+        std::vector<Hit> hits((size_t)hcap * lanes);
+        std::vector<u32x4> rows(((size_t)std::max(n_work, 1u) * P.row_stride + 15) / 16);
+        std::vector<uint32_t> next_list(n_groups + 1);
+        uint32_t next_count = 0;
+
+        P.ix = e->ix; P.codes = codes; P.kind = kind;
+        P.tasks = (const Task *)tasks; P.read_off = read_off; P.read_len = read_len;
+        P.opts = dopts.data(); P.len2opt = len2opt; P.filter_max_n = filter_max_n;
+        P.rows = reinterpret_cast<uint8_t *>(rows.data());
+        P.arena = arena.data(); P.links = links.data(); P.arena_cap = cap;
+        P.hits = hits.data(); P.hit_cap = hcap;
+        P.n_aln = n_aln; P.aln_off = aln_off; P.status = status; P.aln = aln; P.aln_cap = aln_cap;
+        P.counters = counters; P.strict_list = strict.data();
+        P.width_out = (u32x2 *)width_out; P.bid_out = bid_out;
+        P.vote_slow_min = g_vote_slow_min; P.vote_pop_bias = g_vote_pop_bias;
+        unsigned long long cursor = 0;
+        P.cursor = &cursor;
+        // the split pipeline, launch for launch as hsa_b200.cu's issue_chunk enqueues it
+        P.pass = 1; P.work_base = 0; P.work_list = round == 0 ? nullptr : strict_in.data(); P.n_work = n_work;
+        P.next_list = next_list.data(); P.next_count = &next_count;
+        for (uint32_t w = 0; w < n_work; ++w) width_item(P, dopts.data(), w);
+        if (kind != KIND_WIDTH) {
+            if (wide) run_worker<uint64_t, false>(P, n_work, st); else run_worker<uint32_t, true>(P, n_work, st);
+            if (kind == KIND_WHOLE) {
+                P.pass = 2; P.work_list = next_list.data(); P.n_work = next_count; P.next_list = nullptr; P.next_count = nullptr;
+                for (uint32_t w = 0; w < next_count; ++w) width_item(P, dopts.data(), w);
+                if (wide) run_worker<uint64_t, false>(P, next_count, st); else run_worker<uint32_t, true>(P, next_count, st);
+            }
         }
+        if (round == 0) flagged_first = counters[CNT_STRICT];
+        if (round == 1 || !g_rerun_cap || counters[CNT_STRICT] == 0 || counters[CNT_BAD]) break;
+        strict_in.assign(strict.begin(), strict.begin() + counters[CNT_STRICT]);
+        counters[CNT_STRICT] = 0;
     }
+    g_flagged_first = flagged_first;
     hsa_smem_host = nullptr;
     *lookups = st[0] + counters[CNT_LOOKUPS];
     *n_strict = counters[CNT_STRICT] + counters[CNT_BAD];
@@ -216,6 +230,8 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
     return (long)counters[CNT_ALN];
 }
 
+void emu_set_rerun(uint32_t cap) { g_rerun_cap = cap; }
+uint64_t emu_flagged_first(void) { return g_flagged_first; }
 void emu_set_item_steps(uint32_t *buf) { g_item_steps = buf; g_item_steps_pos = 0; }
 void emu_set_vote(uint32_t slow_min, int32_t pop_bias) { g_vote_slow_min = slow_min; g_vote_pop_bias = pop_bias; }
 void emu_set_simt(int on) { g_simt = on; for (int i = 0; i < 3; ++i) { g_phase_runs[i] = 0; g_phase_lanes[i] = 0; } }

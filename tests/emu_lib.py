@@ -45,6 +45,8 @@ def lib():
         L.emu_index_free.argtypes = [C.c_void_p]
         L.emu_occ.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ol.BwtView), C.c_void_p, C.c_size_t, C.c_void_p]
         L.emu_run.restype = C.c_long
+        L.emu_set_rerun.argtypes = [C.c_uint32]
+        L.emu_flagged_first.restype = C.c_uint64
         L.emu_run.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                               C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -107,8 +109,10 @@ class Emu:
                       idx.shape[0], out.ctypes.data)
         return out
 
-    def run(self, kind, rs, opts, tasks=None, len2opt=None, filter_max_n=0, arena_cap=1024, hit_cap=32,
-            n_items=None, want_width=False):
+    def run(self, kind, rs, opts, tasks=None, len2opt=None, filter_max_n=0, arena_cap=1022, hit_cap=32,
+            n_items=None, want_width=False, rerun_cap=0):
+        """rerun_cap: 0 = items the configuration cannot hold are reported in `status` (1); otherwise they are
+        re-run with that arena capacity (the large-capacity configuration), as the product's host code does."""
         codes = np.ascontiguousarray(rs.codes, dtype=np.uint8)
         off = np.ascontiguousarray(rs.offsets[:-1], dtype=np.uint64)
         lens = np.ascontiguousarray(rs.lens, dtype=np.uint32)
@@ -127,6 +131,7 @@ class Emu:
         wout = np.zeros((int(lens.sum()) + rs.n, 2), dtype=np.uint32) if want_width else None
         bid = np.zeros(rs.n, dtype=np.int32) if want_width else None
         lk, ns, pops = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        lib().emu_set_rerun(C.c_uint32(rerun_cap))
         total = lib().emu_run(self.h, kind, codes.ctypes.data, C.cast(tarr, C.c_void_p) if tarr is not None else None,
                               off.ctypes.data, lens.ctypes.data, n_groups, C.cast(optarr, C.c_void_p), len(opts),
                               l2o.ctypes.data if l2o is not None else None, max_len, filter_max_n, arena_cap, hit_cap,
@@ -135,6 +140,7 @@ class Emu:
                               C.byref(lk), C.byref(ns), C.byref(pops))
         assert total >= 0
         self.last_lookups, self.last_strict, self.last_pops = lk.value, ns.value, pops.value
+        self.last_flagged_first = int(lib().emu_flagged_first())
         if want_width:
             return bid, wout
         return n_aln, aln_off, status, aln[:total]

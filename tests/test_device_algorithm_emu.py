@@ -30,16 +30,17 @@ def test_width(golden, emu):
         assert np.array_equal(w[off[r] + r: off[r] + r + int(rs.lens[r]) + 1], ww)
 
 
-@pytest.mark.parametrize("arena_cap", [2046, 65535], ids=["fast16", "large32"])
+@pytest.mark.parametrize("arena_cap", [1022, 65535], ids=["fast16", "large32"])
 @pytest.mark.parametrize("mode", ["percall", "whole", "seeds"])
 @pytest.mark.parametrize("case", ["cfg1_75bp_n2o1", "cfg2_100bp_default", "cfg5_150bp_n5o2", "ragged_nonstop",
                                   "ragged_loggap_gape", "short_entries", "exact_only", "noskip_gaps"])
 def test_search_matches_reference(golden, emu, case, mode, arena_cap):
-    """fast16: the fast configuration (16-bit link halves, bound bytes in shared memory);
-    large32: the large-capacity configuration (32-bit halves, bound bytes in the rows) used for re-runs."""
+    """fast16: the fast configuration (16-bit link halves, 64 score buckets, bound bytes in shared memory), with
+    the items it cannot hold re-run by the large-capacity one exactly as hsa_b200.cu's run_batch does;
+    large32: the large-capacity configuration (32-bit halves, bound bytes in the rows) for everything."""
     rs = golden.reads(case)
     opt = ol.default_opt(**golden.opt_kwargs(case))
-    n_aln, rows, status = getattr(emu, mode)(rs, opt, arena_cap=arena_cap, hit_cap=4096)
+    n_aln, rows, status = getattr(emu, mode)(rs, opt, arena_cap=arena_cap, hit_cap=4096, rerun_cap=65535)
     exp_n, exp_rows = golden.expected(case, mode)
     assert int((status != 0).sum()) == 0
     assert np.array_equal(n_aln, exp_n)

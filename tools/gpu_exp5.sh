@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+HSA_B200_LIB=$PWD/hsa_b200/libhsa_b200_prof.so.keep HSA_B200_TRACE=1 timeout 600 python tools/exp_tail.py 10000000 > gpurun_out/exp_prof.log 2>&1
+cat gpurun_out/exp_prof.log
