@@ -105,6 +105,9 @@ def lib():
                                       C.c_size_t, C.POINTER(_Result)]
     L.hsa_whole_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(GapOpt),
                                   C.c_int, C.POINTER(_Result)]
+    L.hsa_whole_reads_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(GapOpt),
+                                         C.c_int, C.POINTER(C.c_void_p)]
+    L.hsa_job_wait.argtypes = [C.c_void_p, C.POINTER(_Result)]
     L.hsa_splice_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(GapOpt),
                                    C.POINTER(_Result)]
     L.hsa_result_free.argtypes = [C.POINTER(_Result)]
@@ -196,6 +199,8 @@ class Index:
         self._h = C.c_void_p(handle)
         self.device = device
         self._res = _Result()
+        self._job_res = [_Result() for _ in range(4)]     # result buffers of the asynchronous jobs, round-robin
+        self._job_seq = 0
 
     @classmethod
     def upload(cls, index2bwt, device: int = 0) -> "Index":
@@ -233,6 +238,8 @@ class Index:
     def close(self):
         if self._h:
             lib().hsa_result_free(C.byref(self._res))
+            for r in self._job_res:
+                lib().hsa_result_free(C.byref(r))
             lib().hsa_index_free(self._h)
             self._h = None
 
@@ -280,11 +287,38 @@ class Index:
         _check(lib().hsa_whole_reads(self._h, cp[0], op[0], lp[0], n, C.byref(opt), keep_gape, C.byref(self._res)))
         return BatchResult(self._res, copy=copy)
 
+    def whole_reads_submit(self, codes, off, lens, opt: GapOpt, keep_gape: int = 0) -> "Job":
+        """Asynchronous whole_reads: enqueue H2D + kernels and return; Job.wait() finishes and fetches.  Keep
+        the host buffers alive (pinned memory recommended) until then; at most three jobs in flight."""
+        cp, op, lp, n = _ptr(codes, np.uint8), _ptr(off, np.uint64), _ptr(lens, np.uint32), _len(lens)
+        h = C.c_void_p()
+        _check(lib().hsa_whole_reads_submit(self._h, cp[0], op[0], lp[0], n, C.byref(opt), keep_gape, C.byref(h)))
+        res = self._job_res[self._job_seq % len(self._job_res)]
+        self._job_seq += 1
+        return Job(h, res, (cp, op, lp))
+
     def splice_seeds(self, codes, off, lens, opt: GapOpt) -> BatchResult:
         """The six seed searches of bwt_splice_match (bwtgap.c:797-820) per read."""
         cp, op, lp, n = _ptr(codes, np.uint8), _ptr(off, np.uint64), _ptr(lens, np.uint32), _len(lens)
         _check(lib().hsa_splice_seeds(self._h, cp[0], op[0], lp[0], n, C.byref(opt), C.byref(self._res)))
         return BatchResult(self._res)
+
+
+class Job:
+    """One batch in flight (hsa_job_t)."""
+
+    def __init__(self, handle, res, keepalive):
+        self._h, self._res, self._keep = handle, res, keepalive
+
+    def wait(self, copy: bool = True) -> BatchResult:
+        """Finish the batch and return its results (copy=False: views of the library's pinned result buffers,
+        valid until four more jobs have been submitted on the same Index)."""
+        if self._h is None:
+            raise HsaError("job already waited for")
+        h, self._h = self._h, None
+        _check(lib().hsa_job_wait(h, C.byref(self._res)))
+        self._keep = None
+        return BatchResult(self._res, copy=copy)
 
 
 def _ptr(x, dtype):

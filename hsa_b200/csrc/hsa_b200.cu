@@ -215,7 +215,10 @@ struct hsa_index {
     DevIndex ix;
     RefBwt ref[2];
     bool have_ref = false;
-    struct hsa_workspace *ws = nullptr;      // lazily created for the host-buffer entry points
+    struct hsa_workspace *ws = nullptr;      // == pool[0]; lazily created for the host-buffer entry points
+    struct hsa_workspace *pool[3] = {nullptr, nullptr, nullptr};   // one per in-flight job
+    bool pool_busy[3] = {false, false, false};
+    cudaStream_t h2d = nullptr, d2h = nullptr;                     // copy streams of the job pipeline
     int sm_count = 0;
 };
 
@@ -253,6 +256,8 @@ struct hsa_workspace {
     uint32_t *strict_list = nullptr; size_t strict_list_cap = 0;
     DevOpt *opts_dev = nullptr; size_t opts_cap = 0;
     uint16_t *len2opt_dev = nullptr; size_t len2opt_cap = 0;
+    DevOpt *opts_host = nullptr; size_t opts_host_cap = 0;            // pinned staging: copies need no host sync
+    uint16_t *len2opt_host = nullptr; size_t len2opt_host_cap = 0;
     uint8_t *status_dev = nullptr; size_t status_cap = 0;
     // staging for the host-buffer entry points
     uint8_t *codes_dev = nullptr; size_t codes_cap = 0;
@@ -343,6 +348,8 @@ static int init_index_common(hsa_index *ix, int device)
     ix->device = device;
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ix->h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ix->d2h, cudaStreamNonBlocking));
     CU(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device));
     return HSA_OK;
 }
@@ -469,7 +476,9 @@ extern "C" void hsa_index_free(hsa_index_t *ix)
 {
     if (!ix) return;
     cudaSetDevice(ix->device);
-    if (ix->ws) hsa_workspace_free(ix->ws);
+    for (hsa_workspace *w : ix->pool) if (w) hsa_workspace_free(w);
+    if (ix->h2d) cudaStreamDestroy(ix->h2d);
+    if (ix->d2h) cudaStreamDestroy(ix->d2h);
     if (ix->own_ref) for (int d = 0; d < 2; ++d) { cudaFree(ix->ref_code[d]); cudaFree(ix->ref_occ[d]); cudaFree(ix->ref_major[d]); }
     if (ix->own_blocks) for (int d = 0; d < 2; ++d) cudaFree(ix->blocks[d]);
     if (ix->stream) cudaStreamDestroy(ix->stream);
@@ -532,6 +541,7 @@ extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
     cudaFree(ws->status_dev); cudaFree(ws->codes_dev); cudaFree(ws->off_dev); cudaFree(ws->len_dev);
     cudaFree(ws->tasks_dev); cudaFree(ws->n_aln_dev); cudaFree(ws->aln_off_dev); cudaFree(ws->aln_dev);
     cudaFree(ws->width_out_dev); cudaFree(ws->bid_dev);
+    cudaFreeHost(ws->opts_host); cudaFreeHost(ws->len2opt_host);
     if (ws->ev0) cudaEventDestroy(ws->ev0);
     if (ws->ev1) cudaEventDestroy(ws->ev1);
     delete ws;
@@ -684,28 +694,11 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     return HSA_OK;
 }
 
-// Runs one batch whose inputs/outputs are already on the device.  `sync` selects whether the call waits and
-// handles large-capacity re-runs (host-buffer entry points) or just enqueues (device entry point).
-// The batch is cut into chunks of work items that are issued round-robin on `n_pipes` internal streams, so the
-// serial tail of one chunk's persistent kernels (a few reads take > 10^4 steps) overlaps the next chunk's bulk.
-static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, bool sync, uint64_t stats[CNT_N], float *ms)
+// Launch parameters of a batch in the fast configuration (shared by the enqueue and the finish half).
+static int batch_params(hsa_workspace *ws, const Batch &b, Params &P, Variant &v, uint32_t &seed_cap)
 {
     const hsa_index *ix = ws->idx;
-    CU(cudaSetDevice(ix->device));
-    int rc;
-    if ((rc = configure(ws))) return rc;
-    ws->last_launches = 0;
-    if (ws->trace < 0) ws->trace = (int)env_long("HSA_B200_TRACE", 0);
-    const int trace_saved = ws->trace;
-    if (!sync) ws->trace = 0;
-
-    const uint32_t items_per_group = b.kind == KIND_SEEDS ? 6u : 1u;
-    const uint64_t n_work_total = (uint64_t)b.n_groups * items_per_group;
-    const uint32_t seed_cap = (b.kind == KIND_TASKS || b.kind == KIND_WHOLE) && b.max_seed_len ? b.max_seed_len + 1 : 0;
-    if ((rc = ensure(ws->status_dev, ws->status_cap, (size_t)b.n_items + 1))) return rc;
-    if ((rc = ensure(ws->strict_list, ws->strict_list_cap, (size_t)n_work_total + 1))) return rc;
-
-    Params P;
+    seed_cap = (b.kind == KIND_TASKS || b.kind == KIND_WHOLE) && b.max_seed_len ? b.max_seed_len + 1 : 0;
     memset(&P, 0, sizeof(P));
     P.ix = ix->ix; P.codes = b.codes; P.kind = b.kind;
     P.tasks = b.tasks; P.read_off = b.read_off; P.read_len = b.read_len;
@@ -717,13 +710,35 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
     // fast configuration: bound bytes in shared memory if a block's share leaves room for >= 4 blocks per SM
     const uint32_t nb_fast = std::min<uint32_t>(b.n_buckets, 64);   // scores >= 64 send the item to the large-capacity kernel
     set_layout(P, b.max_len, seed_cap, nb_fast, b.n_opts, 2, true);
-    Variant v = V_FAST;
+    v = V_FAST;
     if ((size_t)P.smem_opts_bytes + (size_t)ws->block * P.smem_lane_stride > 56 * 1024) {
         v = V_FAST_ROWS;
         set_layout(P, b.max_len, seed_cap, nb_fast, b.n_opts, 2, false);
     }
     if ((size_t)P.smem_opts_bytes + (size_t)ws->block * P.smem_lane_stride > 200 * 1024)
         return fail(HSA_E_ARG, "option table too large for shared memory");
+    return HSA_OK;
+}
+
+// Enqueue half of a batch whose inputs/outputs are already on the device: nothing is synchronised.
+// The batch is cut into chunks of work items that are issued round-robin on `n_pipes` internal streams
+// (HSA_B200_PIPES / HSA_B200_CHUNK; default: one chunk on the caller's stream).
+static int batch_enqueue(hsa_workspace *ws, const Batch &b, cudaStream_t stream, bool allow_trace)
+{
+    const hsa_index *ix = ws->idx;
+    CU(cudaSetDevice(ix->device));
+    int rc;
+    if ((rc = configure(ws))) return rc;
+    ws->last_launches = 0;
+    if (ws->trace < 0) ws->trace = (int)env_long("HSA_B200_TRACE", 0);
+    const int trace_saved = ws->trace;
+    if (!allow_trace) ws->trace = 0;
+    const uint32_t items_per_group = b.kind == KIND_SEEDS ? 6u : 1u;
+    const uint64_t n_work_total = (uint64_t)b.n_groups * items_per_group;
+    if ((rc = ensure(ws->status_dev, ws->status_cap, (size_t)b.n_items + 1))) return rc;
+    if ((rc = ensure(ws->strict_list, ws->strict_list_cap, (size_t)n_work_total + 1))) return rc;
+    Params P; Variant v; uint32_t seed_cap;
+    if ((rc = batch_params(ws, b, P, v, seed_cap))) return rc;
 
     CU(cudaMemsetAsync(ws->counters, 0, CNT_ALLOC * sizeof(unsigned long long), stream));
     CU(cudaEventRecord(ws->ev0, stream));
@@ -753,11 +768,24 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
     }
     CU(cudaEventRecord(ws->ev1, stream));
     ws->trace = trace_saved;
-    if (!sync) return HSA_OK;
+    return HSA_OK;
+}
 
+// Finish half: waits for the batch, re-runs the items that ran out of stack / hit capacity through the same
+// pipeline with the large-capacity kernel, returns the statistics block.
+// `side` is the stream the statistics are read back on after the batch's end event; it differs from `stream`
+// in the job pipeline, where later jobs may already be queued on the compute stream.
+static int batch_finish(hsa_workspace *ws, const Batch &b, cudaStream_t stream, cudaStream_t side, uint64_t stats[CNT_N], float *ms)
+{
+    const hsa_index *ix = ws->idx;
+    CU(cudaSetDevice(ix->device));
+    int rc;
+    Params P; Variant v; uint32_t seed_cap;
+    if ((rc = batch_params(ws, b, P, v, seed_cap))) return rc;
     unsigned long long cnt[CNT_ALLOC];
-    CU(cudaMemcpyAsync(cnt, ws->counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
-    CU(cudaStreamSynchronize(stream));
+    CU(cudaStreamWaitEvent(side, ws->ev1, 0));
+    CU(cudaMemcpyAsync(cnt, ws->counters, sizeof(cnt), cudaMemcpyDeviceToHost, side));
+    CU(cudaStreamSynchronize(side));
     trace_dump(ws, cnt);
     float t = 0;
     CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
@@ -792,6 +820,13 @@ static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, boo
     return HSA_OK;
 }
 
+static int run_batch(hsa_workspace *ws, const Batch &b, cudaStream_t stream, bool sync, uint64_t stats[CNT_N], float *ms)
+{
+    int rc = batch_enqueue(ws, b, stream, sync);
+    if (rc || !sync) return rc;
+    return batch_finish(ws, b, stream, stream, stats, ms);
+}
+
 
 // ---------------------------------------------------------------------------------------------- results
 static int result_reserve(hsa_result_t *r, size_t n_items, size_t n_aln)
@@ -824,40 +859,88 @@ extern "C" void hsa_result_free(hsa_result_t *r)
     memset(r, 0, sizeof(*r));
 }
 
-static int get_ws(const hsa_index_t *ix, hsa_workspace **out)
+// ---------------------------------------------------------------------------------------------- jobs
+// A job = one host-buffer batch in flight:  H2D (copy stream) -> kernels (compute stream) -> D2H (copy stream).
+// hsa_*_submit enqueues the first two and returns; hsa_job_wait finishes the batch (large-capacity re-runs if
+// any), copies the results out and releases the job.  With two jobs in flight the copies of one batch overlap
+// the kernels of the other.  The blocking entry points are submit + wait.
+struct hsa_job {
+    hsa_index *ix = nullptr;
+    hsa_workspace *ws = nullptr;
+    int slot = -1;
+    Batch b;
+    size_t want = 0;                 // hit arena capacity of this attempt
+    cudaEvent_t h2d_done = nullptr;
+};
+
+static int job_begin(const hsa_index_t *ix_c, hsa_job **out)
 {
-    hsa_index *m = const_cast<hsa_index *>(ix);
-    if (!m->ws) { int rc = hsa_workspace_create(ix, 0, 0, 0, &m->ws); if (rc) return rc; }
-    *out = m->ws;
+    hsa_index *ix = const_cast<hsa_index *>(ix_c);
+    CU(cudaSetDevice(ix->device));
+    int slot = -1;
+    for (int i = 0; i < 3; ++i) if (!ix->pool_busy[i]) { slot = i; break; }
+    if (slot < 0) return fail(HSA_E_ARG, "too many jobs in flight on this index (3): wait for one first");
+    if (!ix->pool[slot]) {
+        int rc = hsa_workspace_create(ix, 0, 0, 0, &ix->pool[slot]);
+        if (rc) return rc;
+        if (slot == 0) ix->ws = ix->pool[0];
+    }
+    hsa_job *j = new hsa_job();
+    j->ix = ix; j->ws = ix->pool[slot]; j->slot = slot;
+    if (cudaEventCreateWithFlags(&j->h2d_done, cudaEventDisableTiming) != cudaSuccess) { delete j; return fail(HSA_E_CUDA, "cudaEventCreate failed"); }
+    ix->pool_busy[slot] = true;
+    *out = j;
     return HSA_OK;
 }
 
-// shared tail of the host-buffer entry points: run (retrying with a larger hit arena if needed), copy back
-static int run_and_fetch(hsa_workspace *ws, Batch &b, hsa_result_t *res)
+static void job_release(hsa_job *j)
 {
-    const hsa_index *ix = ws->idx;
+    if (!j) return;
+    if (j->slot >= 0) j->ix->pool_busy[j->slot] = false;
+    if (j->h2d_done) cudaEventDestroy(j->h2d_done);
+    delete j;
+}
+
+// inputs are queued on the copy stream: order the kernels behind them and enqueue the batch
+static int job_launch(hsa_job *j)
+{
+    hsa_index *ix = j->ix; hsa_workspace *ws = j->ws; Batch &b = j->b;
     int rc;
     if ((rc = ensure(ws->n_aln_dev, ws->items_cap, (size_t)b.n_items + 1))) return rc;
     if ((rc = ensure(ws->aln_off_dev, ws->items2_cap, (size_t)b.n_items + 1))) return rc;
-    size_t want = std::max<size_t>((size_t)b.n_items * 2 + 1024, ws->aln_cap / 9);
+    j->want = std::max<size_t>((size_t)b.n_items * 2 + 1024, ws->aln_cap / 9);
+    if ((rc = ensure(ws->aln_dev, ws->aln_cap, j->want * 9))) return rc;
+    b.n_aln = ws->n_aln_dev; b.aln_off = ws->aln_off_dev; b.aln = ws->aln_dev; b.aln_cap = j->want;
+    CU(cudaEventRecord(j->h2d_done, ix->h2d));
+    CU(cudaStreamWaitEvent(ix->stream, j->h2d_done, 0));
+    return batch_enqueue(ws, b, ix->stream, true);
+}
+
+static int job_finish(hsa_job *j, hsa_result_t *res)
+{
+    hsa_index *ix = j->ix; hsa_workspace *ws = j->ws; Batch &b = j->b;
+    int rc;
     uint64_t stats[CNT_N];
     float ms = 0, ms_total = 0;
-    uint32_t launches = 0;
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        if ((rc = ensure(ws->aln_dev, ws->aln_cap, want * 9))) return rc;
-        b.n_aln = ws->n_aln_dev; b.aln_off = ws->aln_off_dev; b.aln = ws->aln_dev; b.aln_cap = want;
-        if ((rc = run_batch(ws, b, ix->stream, true, stats, &ms))) return rc;
-        ms_total += ms; launches += ws->last_launches;
-        if (stats[CNT_ALN] <= want) break;
-        want = stats[CNT_ALN] + 1024;                // the counter kept counting past the capacity
+    uint32_t launches = ws->last_launches;
+    for (int attempt = 0;; ++attempt) {
+        if ((rc = batch_finish(ws, b, ix->stream, ix->d2h, stats, &ms))) return rc;
+        ms_total += ms;
+        if (stats[CNT_ALN] <= j->want) break;
         if (attempt == 2) return fail(HSA_E_CAPACITY, "hit arena overflow persisted");
+        j->want = stats[CNT_ALN] + 1024;             // the counter kept counting past the capacity: run again
+        if ((rc = ensure(ws->aln_dev, ws->aln_cap, j->want * 9))) return rc;
+        b.aln = ws->aln_dev; b.aln_cap = j->want;
+        if ((rc = batch_enqueue(ws, b, ix->stream, true))) return rc;
+        launches += ws->last_launches;
     }
-    size_t total = stats[CNT_ALN];
+    const size_t total = stats[CNT_ALN];
     if ((rc = result_reserve(res, b.n_items, total))) return rc;
-    CU(cudaMemcpyAsync(res->n_aln, ws->n_aln_dev, (size_t)b.n_items * sizeof(int32_t), cudaMemcpyDeviceToHost, ix->stream));
-    CU(cudaMemcpyAsync(res->aln_off, ws->aln_off_dev, (size_t)b.n_items * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
-    if (total) CU(cudaMemcpyAsync(res->aln, ws->aln_dev, total * sizeof(hsa_aln1_t), cudaMemcpyDeviceToHost, ix->stream));
-    CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaStreamWaitEvent(ix->d2h, ws->ev1, 0));
+    CU(cudaMemcpyAsync(res->n_aln, ws->n_aln_dev, (size_t)b.n_items * sizeof(int32_t), cudaMemcpyDeviceToHost, ix->d2h));
+    CU(cudaMemcpyAsync(res->aln_off, ws->aln_off_dev, (size_t)b.n_items * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->d2h));
+    if (total) CU(cudaMemcpyAsync(res->aln, ws->aln_dev, total * sizeof(hsa_aln1_t), cudaMemcpyDeviceToHost, ix->d2h));
+    CU(cudaStreamSynchronize(ix->d2h));
     res->n_items = b.n_items; res->n_aln_total = total;
     res->occ_lookups = stats[CNT_LOOKUPS]; res->n_strict = stats[CNT_STRICT];
     res->pops = stats[CNT_POPS]; res->steps = stats[CNT_STEPS];
@@ -866,17 +949,25 @@ static int run_and_fetch(hsa_workspace *ws, Batch &b, hsa_result_t *res)
     return HSA_OK;
 }
 
-static int upload_reads(hsa_workspace *ws, const uint8_t *codes, const uint64_t *off, const uint32_t *len, size_t n,
-                        size_t *codes_bytes_out, uint32_t *max_len_out)
+extern "C" int hsa_job_wait(hsa_job_t *job, hsa_result_t *res)
 {
-    const hsa_index *ix = ws->idx;
-    size_t bytes = 0; uint32_t ml = 0;
+    if (!job || !res) return fail(HSA_E_ARG, "null argument");
+    const int rc = job_finish(job, res);
+    job_release(job);
+    return rc;
+}
+
+static int upload_reads(hsa_job *j, const uint8_t *codes, const uint64_t *off, const uint32_t *len, size_t n, uint32_t *max_len_out)
+{
+    hsa_workspace *ws = j->ws;
+    size_t bytes = 0; uint32_t ml = 0, mn = 0xFFFFFFFFu;
     for (size_t i = 0; i < n; ++i) {
-        size_t e = off[i] + len[i];
+        const size_t e = off[i] + len[i];
         if (e > bytes) bytes = e;
         if (len[i] > ml) ml = len[i];
-        if (len[i] == 0) return fail(HSA_E_ARG, "empty read (len == 0)");
+        if (len[i] < mn) mn = len[i];
     }
+    if (mn == 0) return fail(HSA_E_ARG, "empty read (len == 0)");
     int rc;
     if ((rc = ensure(ws->codes_dev, ws->codes_cap, bytes + 16))) return rc;
     if (n + 1 > ws->reads_cap || !ws->off_dev) {
@@ -886,13 +977,15 @@ static int upload_reads(hsa_workspace *ws, const uint8_t *codes, const uint64_t 
         CU(cudaMalloc((void **)&ws->len_dev, c * sizeof(uint32_t)));
         ws->reads_cap = c;
     }
-    CU(cudaMemcpyAsync(ws->codes_dev, codes, bytes, cudaMemcpyHostToDevice, ix->stream));
-    CU(cudaMemcpyAsync(ws->off_dev, off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->stream));
-    CU(cudaMemcpyAsync(ws->len_dev, len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
-    *codes_bytes_out = bytes; *max_len_out = ml;
+    cudaStream_t s = j->ix->h2d;
+    CU(cudaMemcpyAsync(ws->codes_dev, codes, bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ws->off_dev, off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ws->len_dev, len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    *max_len_out = ml;
     return HSA_OK;
 }
 
+// option table (+ length -> option index map) to the device through the workspace's pinned staging: no host sync
 static int upload_opts(hsa_workspace *ws, const std::vector<hsa_gap_opt_t> &opts, uint32_t max_len, Batch *bt,
                        const std::vector<uint16_t> *len2opt, cudaStream_t stream)
 {
@@ -900,21 +993,29 @@ static int upload_opts(hsa_workspace *ws, const std::vector<hsa_gap_opt_t> &opts
     bt->max_seed_len = 0;
     for (const hsa_gap_opt_t &o : opts)
         if (o.seed_len > 0 && (uint32_t)o.seed_len < max_len) bt->max_seed_len = std::max(bt->max_seed_len, (uint32_t)o.seed_len);
-    const hsa_index *ix = ws->idx;
     int rc;
-    std::vector<DevOpt> d(opts.size());
+    if (opts.size() > ws->opts_host_cap || !ws->opts_host) {
+        cudaFreeHost(ws->opts_host); ws->opts_host = nullptr;
+        CU(cudaHostAlloc((void **)&ws->opts_host, (opts.size() + 16) * sizeof(DevOpt), cudaHostAllocDefault));
+        ws->opts_host_cap = opts.size() + 16;
+    }
     *n_buckets = 1;
     for (size_t i = 0; i < opts.size(); ++i) {
         if ((rc = check_opt(opts[i], max_len, n_buckets))) return rc;
-        to_devopt(opts[i], d[i]);
+        to_devopt(opts[i], ws->opts_host[i]);
     }
-    if ((rc = ensure(ws->opts_dev, ws->opts_cap, d.size()))) return rc;
-    CU(cudaMemcpyAsync(ws->opts_dev, d.data(), d.size() * sizeof(DevOpt), cudaMemcpyHostToDevice, stream));
+    if ((rc = ensure(ws->opts_dev, ws->opts_cap, opts.size()))) return rc;
+    CU(cudaMemcpyAsync(ws->opts_dev, ws->opts_host, opts.size() * sizeof(DevOpt), cudaMemcpyHostToDevice, stream));
     if (len2opt) {
+        if (len2opt->size() > ws->len2opt_host_cap || !ws->len2opt_host) {
+            cudaFreeHost(ws->len2opt_host); ws->len2opt_host = nullptr;
+            CU(cudaHostAlloc((void **)&ws->len2opt_host, (len2opt->size() + 64) * sizeof(uint16_t), cudaHostAllocDefault));
+            ws->len2opt_host_cap = len2opt->size() + 64;
+        }
+        memcpy(ws->len2opt_host, len2opt->data(), len2opt->size() * sizeof(uint16_t));
         if ((rc = ensure(ws->len2opt_dev, ws->len2opt_cap, len2opt->size()))) return rc;
-        CU(cudaMemcpyAsync(ws->len2opt_dev, len2opt->data(), len2opt->size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(ws->len2opt_dev, ws->len2opt_host, len2opt->size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
     }
-    CU(cudaStreamSynchronize(stream));              // d / len2opt are stack-local
     return HSA_OK;
 }
 
@@ -942,15 +1043,14 @@ static int resolve_whole_opts(const hsa_gap_opt_t *opt, int keep_gape, const std
     return HSA_OK;
 }
 
+static int empty_result(hsa_result_t *res) { res->n_items = 0; res->n_aln_total = 0; return HSA_OK; }
+
 extern "C" int hsa_match_gap_batch(const hsa_index_t *ix, const uint8_t *codes, size_t codes_bytes,
                                    const hsa_task_t *tasks, size_t n_tasks,
                                    const hsa_gap_opt_t *opts, size_t n_opts, hsa_result_t *res)
 {
     if (!ix || !res || (n_tasks && (!codes || !tasks || !opts))) return fail(HSA_E_ARG, "null argument");
     if (n_tasks > 0xFFFFFFF0ull) return fail(HSA_E_ARG, "too many tasks");
-    hsa_workspace *ws; int rc;
-    if ((rc = get_ws(ix, &ws))) return rc;
-    CU(cudaSetDevice(ix->device));
     uint32_t max_len = 0;
     for (size_t i = 0; i < n_tasks; ++i) {
         const hsa_task_t &t = tasks[i];
@@ -963,66 +1063,76 @@ extern "C" int hsa_match_gap_batch(const hsa_index_t *ix, const uint8_t *codes, 
             return fail(HSA_E_ARG, "HSA_SEED_TAIL needs 0 < opt.seed_len < task.len (bwtaln.c:344)");
         max_len = std::max(max_len, std::max(t.len, t.read_len));
     }
-    if (n_tasks == 0) { res->n_items = 0; res->n_aln_total = 0; return HSA_OK; }
+    if (n_tasks == 0) return empty_result(res);
+    hsa_job *j; int rc;
+    if ((rc = job_begin(ix, &j))) return rc;
+    hsa_workspace *ws = j->ws; Batch &b = j->b;
     std::vector<hsa_gap_opt_t> ov(opts, opts + n_opts);
-    Batch b;
-    if ((rc = upload_opts(ws, ov, max_len, &b, nullptr, ix->stream))) return rc;
-    if ((rc = ensure(ws->codes_dev, ws->codes_cap, codes_bytes + 16))) return rc;
-    if ((rc = ensure(ws->tasks_dev, ws->tasks_cap, n_tasks))) return rc;
-    CU(cudaMemcpyAsync(ws->codes_dev, codes, codes_bytes, cudaMemcpyHostToDevice, ix->stream));
-    CU(cudaMemcpyAsync(ws->tasks_dev, tasks, n_tasks * sizeof(Task), cudaMemcpyHostToDevice, ix->stream));
+    if ((rc = upload_opts(ws, ov, max_len, &b, nullptr, j->ix->h2d)) ||
+        (rc = ensure(ws->codes_dev, ws->codes_cap, codes_bytes + 16)) ||
+        (rc = ensure(ws->tasks_dev, ws->tasks_cap, n_tasks))) { job_release(j); return rc; }
+    if (cudaMemcpyAsync(ws->codes_dev, codes, codes_bytes, cudaMemcpyHostToDevice, j->ix->h2d) != cudaSuccess ||
+        cudaMemcpyAsync(ws->tasks_dev, tasks, n_tasks * sizeof(Task), cudaMemcpyHostToDevice, j->ix->h2d) != cudaSuccess) {
+        job_release(j); return fail(HSA_E_CUDA, "H2D copy of the task batch failed");
+    }
     b.kind = KIND_TASKS; b.n_groups = (uint32_t)n_tasks; b.n_items = (uint32_t)n_tasks; b.max_len = max_len;
     b.n_opts = (uint32_t)n_opts; b.codes = ws->codes_dev; b.tasks = ws->tasks_dev;
-    return run_and_fetch(ws, b, res);
+    if ((rc = job_launch(j))) { job_release(j); return rc; }
+    return hsa_job_wait(j, res);
 }
 
-static int reads_common(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len, size_t n,
-                        hsa_workspace **ws, uint32_t *max_len)
+extern "C" int hsa_whole_reads_submit(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                                      size_t n_reads, const hsa_gap_opt_t *opt, int keep_gape, hsa_job_t **job)
 {
-    if (!ix || (n && (!codes || !off || !len))) return fail(HSA_E_ARG, "null argument");
-    if (n > 0x2AAAAAA0ull) return fail(HSA_E_ARG, "too many reads in one batch");
-    int rc;
-    if ((rc = get_ws(ix, ws))) return rc;
-    CU(cudaSetDevice(ix->device));
-    size_t bytes;
-    return upload_reads(*ws, codes, off, len, n, &bytes, max_len);
+    if (!ix || !opt || !job || !n_reads || !codes || !off || !len) return fail(HSA_E_ARG, "null / empty argument");
+    if (n_reads > 0x2AAAAAA0ull) return fail(HSA_E_ARG, "too many reads in one batch");
+    hsa_job *j; int rc; uint32_t max_len = 0;
+    if ((rc = job_begin(ix, &j))) return rc;
+    hsa_workspace *ws = j->ws; Batch &b = j->b;
+    if ((rc = upload_reads(j, codes, off, len, n_reads, &max_len))) { job_release(j); return rc; }
+    std::vector<uint8_t> seen((size_t)max_len + 1, 0);
+    for (size_t i = 0; i < n_reads; ++i) seen[len[i]] = 1;
+    std::vector<uint32_t> lens;
+    for (uint32_t L = 0; L <= max_len; ++L) if (seen[L]) lens.push_back(L);
+    std::vector<hsa_gap_opt_t> opts; std::vector<uint16_t> l2o;
+    if ((rc = resolve_whole_opts(opt, keep_gape, lens, max_len, opts, l2o, &b.filter_max_n)) ||
+        (rc = upload_opts(ws, opts, max_len, &b, &l2o, j->ix->h2d))) { job_release(j); return rc; }
+    b.kind = KIND_WHOLE; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads; b.max_len = max_len;
+    b.n_opts = (uint32_t)opts.size(); b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
+    if ((rc = job_launch(j))) { job_release(j); return rc; }
+    *job = j;
+    return HSA_OK;
 }
 
 extern "C" int hsa_whole_reads(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
                                size_t n_reads, const hsa_gap_opt_t *opt, int keep_gape, hsa_result_t *res)
 {
     if (!res || !opt) return fail(HSA_E_ARG, "null argument");
-    if (n_reads == 0) { res->n_items = 0; res->n_aln_total = 0; return HSA_OK; }
-    hsa_workspace *ws; uint32_t max_len; int rc;
-    if ((rc = reads_common(ix, codes, off, len, n_reads, &ws, &max_len))) return rc;
-    std::vector<uint8_t> seen((size_t)max_len + 1, 0);
-    for (size_t i = 0; i < n_reads; ++i) seen[len[i]] = 1;
-    std::vector<uint32_t> lens;
-    for (uint32_t L = 0; L <= max_len; ++L) if (seen[L]) lens.push_back(L);
-    std::vector<hsa_gap_opt_t> opts; std::vector<uint16_t> l2o;
-    Batch b;
-    if ((rc = resolve_whole_opts(opt, keep_gape, lens, max_len, opts, l2o, &b.filter_max_n))) return rc;
-    if ((rc = upload_opts(ws, opts, max_len, &b, &l2o, ix->stream))) return rc;
-    b.kind = KIND_WHOLE; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads; b.max_len = max_len;
-    b.n_opts = (uint32_t)opts.size(); b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
-    return run_and_fetch(ws, b, res);
+    if (n_reads == 0) return empty_result(res);
+    hsa_job_t *j; int rc;
+    if ((rc = hsa_whole_reads_submit(ix, codes, off, len, n_reads, opt, keep_gape, &j))) return rc;
+    return hsa_job_wait(j, res);
 }
 
 extern "C" int hsa_splice_seeds(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
                                 size_t n_reads, const hsa_gap_opt_t *opt, hsa_result_t *res)
 {
     if (!res || !opt) return fail(HSA_E_ARG, "null argument");
-    if (n_reads == 0) { res->n_items = 0; res->n_aln_total = 0; return HSA_OK; }
-    hsa_workspace *ws; uint32_t max_len; int rc;
-    if ((rc = reads_common(ix, codes, off, len, n_reads, &ws, &max_len))) return rc;
+    if (n_reads == 0) return empty_result(res);
+    if (!ix || !codes || !off || !len) return fail(HSA_E_ARG, "null argument");
+    if (n_reads > 0x2AAAAAA0ull) return fail(HSA_E_ARG, "too many reads in one batch");
+    hsa_job *j; int rc; uint32_t max_len = 0;
+    if ((rc = job_begin(ix, &j))) return rc;
+    hsa_workspace *ws = j->ws; Batch &b = j->b;
+    if ((rc = upload_reads(j, codes, off, len, n_reads, &max_len))) { job_release(j); return rc; }
     hsa_gap_opt_t so = *opt;                             // bwtgap.c:769-774
     so.mode &= ~HSA_MODE_GAPE; so.max_gapo = 0; so.max_gape = 0; so.max_diff = opt->max_seed_diff;
     std::vector<hsa_gap_opt_t> opts(1, so);
-    Batch b;
-    if ((rc = upload_opts(ws, opts, max_len, &b, nullptr, ix->stream))) return rc;
+    if ((rc = upload_opts(ws, opts, max_len, &b, nullptr, j->ix->h2d))) { job_release(j); return rc; }
     b.kind = KIND_SEEDS; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads * 6; b.max_len = max_len;
     b.n_opts = 1; b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
-    return run_and_fetch(ws, b, res);
+    if ((rc = job_launch(j))) { job_release(j); return rc; }
+    return hsa_job_wait(j, res);
 }
 
 extern "C" int hsa_cal_width_batch(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off,
@@ -1031,8 +1141,15 @@ extern "C" int hsa_cal_width_batch(const hsa_index_t *ix, const uint8_t *codes, 
     if (type != 1) return fail(HSA_E_ARG, "only bwt_cal_width type 1 (forward search on rev_bwt) is on the GPU path");
     if (!width_out || !bid_out) return fail(HSA_E_ARG, "null argument");
     if (n == 0) return HSA_OK;
-    hsa_workspace *ws; uint32_t max_len; int rc;
-    if ((rc = reads_common(ix, codes, off, len, n, &ws, &max_len))) return rc;
+    if (!ix || !codes || !off || !len) return fail(HSA_E_ARG, "null argument");
+    hsa_job *j; uint32_t max_len; int rc;
+    if ((rc = job_begin(ix, &j))) return rc;
+    hsa_workspace *ws = j->ws;
+    rc = upload_reads(j, codes, off, len, n, &max_len);
+    if (!rc && (cudaEventRecord(j->h2d_done, j->ix->h2d) != cudaSuccess ||
+                cudaStreamWaitEvent(ix->stream, j->h2d_done, 0) != cudaSuccess)) rc = fail(HSA_E_CUDA, "event ordering failed");
+    struct Rel { hsa_job *j; ~Rel() { cudaStreamSynchronize(j->ix->stream); job_release(j); } } rel{j};
+    if (rc) return rc;
     size_t total = 0;
     for (size_t i = 0; i < n; ++i) total = std::max(total, (size_t)off[i] + i + len[i] + 1);
     hsa_gap_opt_t o; hsa_gap_opt_default(&o); o.max_diff = 0;

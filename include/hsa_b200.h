@@ -158,6 +158,15 @@ int  hsa_match_gap_batch(const hsa_index_t *idx, const uint8_t *codes, size_t co
 int  hsa_whole_reads(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
                      size_t n_reads, const hsa_gap_opt_t *opt, int keep_gape, hsa_result_t *res);
 
+/* Asynchronous form of hsa_whole_reads for double-buffered pipelines: submit enqueues the H2D copies and the
+ * kernels and returns; hsa_job_wait finishes the batch, copies the results into `res` and releases the job.
+ * The host buffers must stay valid (pinned memory recommended) until the job has been waited for; at most three
+ * jobs may be in flight per index; jobs complete in submission order. */
+typedef struct hsa_job hsa_job_t;
+int  hsa_whole_reads_submit(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                            size_t n_reads, const hsa_gap_opt_t *opt, int keep_gape, hsa_job_t **job);
+int  hsa_job_wait(hsa_job_t *job, hsa_result_t *res);
+
 /* The six seed searches of bwt_splice_match (bwtgap.c:797-820) for each read: item 6*r+s is seed s%3 of
  * strand s/3, with the reference's prefix-width quirk; hits carry start/end as bwtgap.c:816-819. */
 int  hsa_splice_seeds(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off, const uint32_t *len,

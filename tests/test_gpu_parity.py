@@ -129,6 +129,28 @@ def test_strict_rerun_path(golden, golden_index, monkeypatch):
         ix.close()
 
 
+def test_async_jobs_double_buffered(golden, dev_index):
+    """hsa_whole_reads_submit / hsa_job_wait: three batches in flight, results identical to the blocking call
+    and delivered per job; a fourth submit is refused until one job has been waited for."""
+    cases = ["cfg2_100bp_default", "cfg1_75bp_n2o1", "ragged_nonstop"]
+    jobs = []
+    for case in cases:
+        rs = golden.reads(case)
+        opt = to_api_opt(ol.default_opt(**golden.opt_kwargs(case)))
+        jobs.append(dev_index.whole_reads_submit(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt))
+    rs0 = golden.reads(cases[0])
+    with pytest.raises(api.HsaError):
+        dev_index.whole_reads_submit(rs0.codes, rs0.offsets[:-1].astype(np.uint64), rs0.lens, api.gap_init_opt())
+    for case, job in zip(cases, jobs):
+        res = job.wait()
+        exp_n, exp_rows = golden.expected(case, "whole")
+        assert np.array_equal(res.n_aln, exp_n)
+        assert np.array_equal(el.aln9_to_rows12(res.ordered()), exp_rows)
+        assert res.occ_lookups == golden.lookups(case, "whole")
+    with pytest.raises(api.HsaError):
+        jobs[0].wait()
+
+
 def test_empty_and_bad_inputs(dev_index):
     opt = api.gap_init_opt()
     res = dev_index.whole_reads(np.zeros(0, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32), opt)
