@@ -6,9 +6,15 @@ reference's `HSA index` writes (BWTConstruct.c:929-1207 occ tables, :1209-1239 f
 tests/test_index_build.py checks against the reference builder and against committed digests, so a
 synthetic genome of any size can be indexed on the GPU box where /root/reference does not exist.
 
-Algorithm: suffix array of text$ by prefix doubling on packed integer keys (torch.sort), then
-  bwt[r]  = text[sa[r]-1]              ('$' at r = inverseSa0 is dropped from the packed stream)
-  occ     = running symbol counts sampled every 256 symbols (16-bit, relative) and 65536 (32-bit)
+Algorithm (memory-lean enough for a 3.1 Gb text on one 180 GB GPU; the suffix array itself is never held):
+  * suffixes are bucketed by their first `b` symbols (b grows with the text so that a bucket holds <= 2^27
+    suffixes); buckets are visited in lexicographic order;
+  * inside a bucket the suffixes are sorted by a 63-bit key of their next 21 symbols (3 bits each, '$' and
+    everything past the end = 0, so '$' sorts first), ties are broken by successive 21-symbol keys read straight
+    from the text (two rounds suffice for an i.i.d. genome; repeats just take more rounds);
+  * each sorted bucket emits its slice of the BWT, bwt[r] = text[sa[r] - 1]; the rank of suffix 0 is inverseSa0
+    and its placeholder is dropped from the packed stream ('$' is not stored, BWT.c:804);
+  * occ = running symbol counts sampled every 256 symbols (16-bit, relative) and 65536 (32-bit).
 The reverse BWT is the same construction on the reversed text (2BWT-Builder.c:116-213).
 """
 from __future__ import annotations
@@ -19,74 +25,126 @@ import torch
 from .index_io import (BWTArrays, Index2BWT, OCC_INTERVAL, OCC_INTERVAL_MAJOR, bwt_resident_words,
                        occ_major_words, occ_minor_words)
 
+KEY_SYMS = 21                       # symbols per sort key (3 bits each -> 63 bits, non-negative int64)
+BUCKET_TARGET = 1 << 27             # suffixes per bucket the sort is sized for
 
-def suffix_array(text: torch.Tensor) -> torch.Tensor:
-    """Suffix array of text + '$' ('$' smallest): int64[n+1], sa[0] == n."""
+
+def _key_at(text: torch.Tensor, pos: torch.Tensor, start: int, n: int) -> torch.Tensor:
+    """63-bit key of symbols [start, start + KEY_SYMS) of the suffixes at `pos` ('$' / past the end = 0)."""
+    key = torch.zeros_like(pos)
+    for j in range(KEY_SYMS):
+        p = pos + (start + j)
+        inside = p < n
+        sym = torch.where(inside, text[torch.clamp(p, max=n - 1)].to(torch.int64) + 1, torch.zeros_like(p))
+        key = (key << 3) | sym
+    return key
+
+
+def _sort_bucket(text: torch.Tensor, pos: torch.Tensor, skip: int, n: int) -> torch.Tensor:
+    """Suffix positions of one bucket (all sharing their first `skip` symbols) in lexicographic order."""
+    if pos.numel() <= 1:
+        return pos
+    key = _key_at(text, pos, skip, n)
+    key, idx = torch.sort(key, stable=True)
+    pos = pos[idx]
+    del idx
+    tie = key[1:] == key[:-1]
+    del key
+    h = skip + KEY_SYMS
+    # tied[i]: element i belongs to a run of equal prefixes (length >= 2); grp: run id, increasing along the order
+    while bool(tie.any()):
+        m = pos.numel()
+        tied = torch.zeros(m, dtype=torch.bool, device=pos.device)
+        tied[1:] |= tie
+        tied[:-1] |= tie
+        start_of_run = torch.ones(m, dtype=torch.bool, device=pos.device)
+        start_of_run[1:] = ~tie
+        grp_all = torch.cumsum(start_of_run.to(torch.int64), 0)
+        where = torch.nonzero(tied).squeeze(1)          # ascending; runs are contiguous in it
+        sub = pos[where]
+        grp = grp_all[where]
+        del tied, start_of_run, grp_all
+        k2 = _key_at(text, sub, h, n)
+        k2s, o1 = torch.sort(k2, stable=True)           # by next key ...
+        g2, o2 = torch.sort(grp[o1], stable=True)       # ... then (stably) by run: ordered by (run, next key)
+        perm = o1[o2]
+        k2s = k2s[o2]
+        pos[where] = sub[perm]                          # runs keep their slots; only their inside is reordered
+        new_tie_sub = (g2[1:] == g2[:-1]) & (k2s[1:] == k2s[:-1])
+        tie = torch.zeros(m - 1, dtype=torch.bool, device=pos.device)
+        # a tie between slots where[i] and where[i+1] is a tie between adjacent elements (same run => adjacent)
+        tie[where[:-1][new_tie_sub]] = True
+        h += KEY_SYMS
+    return pos
+
+
+def bwt_of(text: torch.Tensor):
+    """(bwt symbols with '$' dropped: uint8[n], inverseSa0) of text + '$' ('$' smallest)."""
     n = int(text.shape[0])
     dev = text.device
     m = n + 1
-    K = 20                                              # symbols per initial key, 3 bits each
-    sym = torch.zeros(m + K, dtype=torch.int64, device=dev)
-    sym[:n] = text.to(torch.int64) + 1                  # '$' and everything past it = 0
-    key = torch.zeros(m, dtype=torch.int64, device=dev)
-    for j in range(K):
-        key = (key << 3) | sym[j:j + m]
-    del sym
-    order = torch.argsort(key, stable=True)
-    skey = key[order]
-    del key
-    diff = torch.ones(m, dtype=torch.int64, device=dev)
-    diff[1:] = (skey[1:] != skey[:-1]).to(torch.int64)
-    del skey
-    h = K
-    while True:
-        grp = torch.cumsum(diff, 0) - 1                 # dense rank of each sorted suffix under its first h symbols
-        if int(grp[-1].item()) + 1 == m:
-            return order
-        rank = torch.empty(m, dtype=torch.int64, device=dev)
-        rank[order] = grp
-        # only suffixes inside tied groups need the second key (a random genome has a handful)
-        same_next = diff[1:] == 0
-        tied = torch.zeros(m, dtype=torch.bool, device=dev)
-        tied[1:] |= same_next
-        tied[:-1] |= same_next
-        pos = torch.nonzero(tied).squeeze(1)            # positions in sorted order, ascending
-        suf = order[pos]
-        nxt = suf + h
-        r2 = torch.where(nxt < m, rank[torch.clamp(nxt, max=m - 1)], torch.zeros_like(nxt))
-        comp = grp[pos] * (m + 1) + r2                  # (group, rank of the next h symbols)
-        comp_sorted, sub = torch.sort(comp, stable=True)
-        order[pos] = suf[sub]                           # groups are contiguous: positions stay in place
-        nd = torch.ones(pos.shape[0], dtype=torch.int64, device=dev)
-        nd[1:] = (comp_sorted[1:] != comp_sorted[:-1]).to(torch.int64)
-        diff = torch.ones(m, dtype=torch.int64, device=dev)
-        diff[pos] = nd
-        h *= 2
+    # symbols the buckets are keyed on
+    b = 0
+    while (m >> (2 * b)) > BUCKET_TARGET:
+        b += 1
+    out = torch.empty(m, dtype=torch.uint8, device=dev)
+    inverse_sa0 = -1
+    if b == 0:
+        buckets = [None]
+    else:
+        code = torch.zeros(m, dtype=torch.int16, device=dev)
+        for j in range(b):                              # base-5 code of the first b symbols, '$'/past the end = 0
+            sym = torch.zeros(m, dtype=torch.int16, device=dev)
+            if n - j > 0:
+                sym[: n - j] = text[j:].to(torch.int16) + 1
+            code = code * 5 + sym
+            del sym
+        buckets = list(range(5 ** b))
+        counts = torch.bincount(code.to(torch.int64), minlength=5 ** b).cpu().tolist() if m <= (1 << 28) else None
+    filled = 0
+    for v in buckets:
+        if v is None:
+            pos = torch.arange(m, dtype=torch.int64, device=dev)
+        else:
+            if counts is not None and counts[v] == 0:
+                continue
+            pos = torch.nonzero(code == v).squeeze(1)
+            if pos.numel() == 0:
+                continue
+        order = _sort_bucket(text, pos, b, n)
+        del pos
+        k = int(order.numel())
+        z = torch.nonzero(order == 0)
+        if z.numel():
+            inverse_sa0 = filled + int(z.item())
+        out[filled:filled + k] = text[torch.clamp(order - 1, min=0)]   # entry at inverse_sa0 is a placeholder
+        filled += k
+        del order
+    assert filled == m and inverse_sa0 >= 0
+    bwt = torch.cat([out[:inverse_sa0], out[inverse_sa0 + 1:]])       # n symbols, '$' removed (BWT.c:804)
+    return bwt, inverse_sa0
 
 
 def _pack_2bit_msb(symbols: torch.Tensor, n_words: int) -> torch.Tensor:
-    """Pack 2-bit symbols 16 per uint32 word, first symbol in the two most significant bits (BWT.c:954)."""
+    """Pack 2-bit symbols 16 per uint32 word, first symbol in the two most significant bits (BWT.c:954).
+    Returns int64 values < 2^32."""
     dev = symbols.device
-    padded = torch.zeros(n_words * 16, dtype=torch.int64, device=dev)
-    padded[: symbols.shape[0]] = symbols.to(torch.int64)
-    shifts = (30 - 2 * torch.arange(16, device=dev, dtype=torch.int64))
-    words = (padded.view(n_words, 16) << shifts).sum(dim=1)
-    return words
+    padded = torch.zeros(n_words * 16, dtype=torch.uint8, device=dev)
+    padded[: symbols.shape[0]] = symbols
+    q = padded.view(n_words * 4, 4)
+    byts = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]          # 4 symbols per byte, first in the MSBs
+    del padded, q
+    w = byts.view(n_words, 4).to(torch.int64)
+    return (w[:, 0] << 24) | (w[:, 1] << 16) | (w[:, 2] << 8) | w[:, 3]
 
 
 def build_bwt(text: torch.Tensor) -> dict:
     """One direction.  Returns torch tensors (int64 holding uint32 values) + scalars."""
     n = int(text.shape[0])
     dev = text.device
-    sa = suffix_array(text)
-    inverse_sa0 = int(torch.nonzero(sa == 0).item())
-    prev = torch.clamp(sa - 1, min=0)
-    bwt_full = text[prev]                                # entry at inverse_sa0 is a placeholder
-    keep = torch.ones(n + 1, dtype=torch.bool, device=dev)
-    keep[inverse_sa0] = False
-    bwt = bwt_full[keep]                                 # n symbols, '$' removed (BWT.c:804)
-    del sa, prev, bwt_full, keep
-    counts = torch.bincount(bwt.to(torch.int64), minlength=4)
+    bwt, inverse_sa0 = bwt_of(text)
+    counts = torch.bincount(bwt, minlength=4)[:4].to(torch.int64) if n < (1 << 30) else \
+        torch.stack([(bwt == c).sum() for c in range(4)]).to(torch.int64)
     cum = torch.zeros(5, dtype=torch.int64, device=dev)
     cum[1:] = torch.cumsum(counts, 0)
     code = _pack_2bit_msb(bwt, bwt_resident_words(n))
@@ -94,15 +152,19 @@ def build_bwt(text: torch.Tensor) -> dict:
     num_occ = (n + OCC_INTERVAL - 1) // OCC_INTERVAL + 1
     n_pad = (num_occ - 1) * OCC_INTERVAL
     occ_abs = torch.zeros((num_occ, 4), dtype=torch.int64, device=dev)
+    full = n // OCC_INTERVAL                             # complete 256-symbol intervals
     for c in range(4):
-        ind = torch.zeros(n_pad, dtype=torch.int64, device=dev)
-        ind[:n] = (bwt == c).to(torch.int64)
-        if c == 0:
-            ind[n:] = 1          # the zero padding past textLength counts as 'A' in the last sample, exactly
-                                 # as BWTDecodeAll's A = span - C - G - T does (BWT.c:677)
-        per = ind.view(num_occ - 1, OCC_INTERVAL).sum(dim=1)
+        per = torch.zeros(num_occ - 1, dtype=torch.int64, device=dev)
+        if full:
+            per[:full] = (bwt[: full * OCC_INTERVAL].view(full, OCC_INTERVAL) == c).sum(dim=1)
+        if full < num_occ - 1:                           # the last, partial interval
+            tail = int((bwt[full * OCC_INTERVAL:] == c).sum().item())
+            if c == 0:
+                tail += n_pad - n    # the zero padding past textLength counts as 'A' in the last sample, exactly
+                                     # as BWTDecodeAll's A = span - C - G - T does (BWT.c:677)
+            per[full] = tail
         occ_abs[1:, c] = torch.cumsum(per, 0)
-        del ind, per
+        del per
     per_major = OCC_INTERVAL_MAJOR // OCC_INTERVAL
     e = torch.arange(num_occ, device=dev)
     major_rows = occ_abs[(e // per_major) * per_major]   # absolute count at the enclosing major sample
