@@ -18,6 +18,7 @@
 #include <vector>
 #include <algorithm>
 #include "hsa_core.cuh"
+#include "hsa_coop.cuh"
 #include "../../include/hsa_b200.h"
 
 using namespace hsa;
@@ -31,7 +32,7 @@ static_assert(sizeof(DevOpt) == 64, "DevOpt is staged as 16 ints");
 enum { MAX_PIPES = 4 };
 // behind the core's counters: per-pipe slots {cursor pass 1, cursor pass 2, pass-2 list count, pad}, then the
 // per-phase cycle counters of the -DHSA_PHASE_PROF build {cycles, runs, lanes} x {SLOW, LOOKUP, POP}
-enum { CNT_PIPE0 = CNT_TOTAL, CNT_PROF0 = CNT_PIPE0 + 4 * (MAX_PIPES + 1), CNT_ALLOC = CNT_PROF0 + 9 };
+enum { CNT_PIPE0 = CNT_TOTAL, CNT_PROF0 = CNT_PIPE0 + 4 * (MAX_PIPES + 2), CNT_ALLOC = CNT_PROF0 + 12 };
 
 // =====================================================================================================
 // kernels
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256, 5) width_kernel(const __grid_constant__ P
     for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
         reinterpret_cast<int *>(sopt)[i] = reinterpret_cast<const int *>(P.opts)[i];
     __syncthreads();
-    const uint32_t n = P.n_work_dev ? *P.n_work_dev : P.n_work;
+    const uint32_t n = P.n_work_dev ? min(*P.n_work_dev, P.n_work) : P.n_work;     // n_work caps a device-side count
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x)
         width_item(P, sopt, w);
 }
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
 
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_work = P.n_work_dev ? *P.n_work_dev : P.n_work;
+    const uint32_t n_work = P.n_work_dev ? min(*P.n_work_dev, P.n_work) : P.n_work;
     Worker<LinkT, BIDS_SMEM> w(P, slot, threadIdx.x);
     unsigned long long warp_iters = 0;
 #ifdef HSA_PHASE_PROF
@@ -102,6 +103,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
         const unsigned b0 = __ballot_sync(0xffffffffu, c & 1u), b1 = __ballot_sync(0xffffffffu, c & 2u);
         if ((b0 & b1) == 0xffffffffu) break;
         ++warp_iters;
+        if (P.drain_budget && (warp_iters & 63u) == 0 && w.budget != P.drain_budget) {
+            // once the queue is dry, the searches still running may only use drain_budget steps in total: what is
+            // heavier goes to the warp-cooperative kernel instead of holding the launch at lone-lane speed
+            const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(P.cursor);
+            if (cur >= n_work) w.budget = P.drain_budget;
+        }
         const uint32_t ph = phase_vote(P, __popc(b0 & ~b1), __popc(b1 & ~b0), __popc(~(b0 | b1)));
 #ifdef HSA_PHASE_PROF
         const long long t_ph0 = clock64();
@@ -160,6 +167,44 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
         atomicAdd(&P.counters[CNT_LOOKUPS], lk);
         atomicAdd(&P.counters[CNT_POPS], pp);
         atomicAdd(&P.counters[CNT_STEPS], st);
+    }
+}
+
+// Warp-cooperative kernel for the heavy searches (hsa_coop.cuh): persistent grid, one search per WARP.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) coop_kernel(const __grid_constant__ Params P)
+{
+    for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
+        reinterpret_cast<int *>(hsa_smem)[i] = reinterpret_cast<const int *>(P.opts)[i];
+    __syncthreads();
+    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const size_t wg = (size_t)blockIdx.x * (BLOCK / 32) + wib;
+    unsigned char *base = hsa_smem + P.smem_opts_bytes + (size_t)wib * P.coop_warp_smem;
+    CoopWarp &sh = *reinterpret_cast<CoopWarp *>(base);
+    uint8_t *bids = base + ((sizeof(CoopWarp) + 15) & ~size_t(15));
+    CoopScratch g;
+    g.payload = P.coop_payload + wg * P.coop_cap_chunks * COOP_CHUNK;
+    g.info = P.coop_info + wg * P.coop_cap_chunks * COOP_CHUNK;
+    g.prev = P.coop_prev + wg * P.coop_cap_chunks;
+    g.out_payload = P.coop_out_payload + wg * 32 * COOP_OUT_CAP;
+    g.out_info = P.coop_out_info + wg * 32 * COOP_OUT_CAP;
+    g.hits = P.coop_hits + wg * COOP_HIT_CAP;
+    const uint32_t n_dev = P.n_work_dev ? *P.n_work_dev : P.n_work;
+    const uint32_t n_work = n_dev < P.n_work ? n_dev : P.n_work;
+    CoopLane me;
+    coop_run(P, sh, bids, g, P.coop_cap_chunks, n_work, me);
+    if (lane == 0) {
+        atomicAdd(&P.counters[CNT_LOOKUPS], sh.lookups);
+        atomicAdd(&P.counters[CNT_POPS], sh.pops);
+        atomicAdd(&P.counters[CNT_STEPS], sh.steps);
+        atomicAdd(&P.counters[CNT_DIAG_COOP_WAVES], sh.waves);
+        atomicAdd(&P.counters[CNT_DIAG_COOP_WAVES + 1], sh.wave_steps);
+        atomicAdd(&P.counters[CNT_DIAG_COOP_WAVES + 2], sh.steps);
+#ifdef HSA_PHASE_PROF
+        atomicAdd(&P.counters[CNT_PROF0 + 9], sh.prof_chain);
+        atomicAdd(&P.counters[CNT_PROF0 + 10], sh.prof_commit);
+        atomicAdd(&P.counters[CNT_PROF0 + 11], sh.prof_total);
+#endif
     }
 }
 
@@ -238,9 +283,17 @@ struct Pipe {                                // one in-flight chunk: stream, wor
     Scratch sc;
     uint8_t *rows = nullptr; size_t rows_cap = 0;
     uint32_t *next_list = nullptr; size_t next_cap = 0;
+    // warp-cooperative stage: per-warp record chunks, per-lane push buffers, hit buffers
+    uint32_t coop_warps = 0, coop_cap_chunks = 0;
+    u32x4 *coop_payload = nullptr, *coop_out_payload = nullptr;
+    uint32_t *coop_info = nullptr, *coop_prev = nullptr, *coop_out_info = nullptr;
+    Hit *coop_hits = nullptr;
     void release()
     {
         sc.release(); cudaFree(rows); cudaFree(next_list);
+        cudaFree(coop_payload); cudaFree(coop_out_payload); cudaFree(coop_info); cudaFree(coop_prev); cudaFree(coop_out_info);
+        cudaFree(coop_hits);
+        coop_payload = coop_out_payload = nullptr; coop_info = coop_prev = coop_out_info = nullptr; coop_hits = nullptr; coop_warps = 0;
         if (stream) cudaStreamDestroy(stream);
         if (done) cudaEventDestroy(done);
         rows = nullptr; next_list = nullptr; stream = nullptr; done = nullptr; rows_cap = next_cap = 0;
@@ -251,7 +304,10 @@ struct Pipe {                                // one in-flight chunk: stream, wor
 struct hsa_workspace {
     const hsa_index *idx = nullptr;
     Pipe pipes[MAX_PIPES];
-    Pipe strict;                                     // large-capacity re-runs (slot MAX_PIPES)
+    Pipe heavy;                                      // warp-cooperative stage (slot MAX_PIPES)
+    Pipe strict;                                     // large-capacity re-runs (slot MAX_PIPES + 1)
+    uint32_t *strict2_list = nullptr; size_t strict2_list_cap = 0;   // what the cooperative stage hands on
+    bool heavy_enqueued = false; uint32_t heavy_cap = 0;             // the cooperative stage was queued behind the fast one
     unsigned long long *counters = nullptr;          // CNT_ALLOC
     uint32_t *strict_list = nullptr; size_t strict_list_cap = 0;
     DevOpt *opts_dev = nullptr; size_t opts_cap = 0;
@@ -277,6 +333,7 @@ struct hsa_workspace {
     uint32_t n_pipes = 1; uint64_t chunk_items = 12u << 20;
     uint32_t arena_cap = 1022, hit_cap = 32;
     uint32_t vote_slow_min = VOTE_SLOW_MIN_DEFAULT; int32_t vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
+    bool use_coop = true; uint32_t step_budget = 0, drain_budget = 2000;
 };
 
 template <typename T>
@@ -536,8 +593,8 @@ extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
 {
     if (!ws) return;
     for (Pipe &p : ws->pipes) p.release();
-    ws->strict.release();
-    cudaFree(ws->counters); cudaFree(ws->strict_list); cudaFree(ws->opts_dev); cudaFree(ws->len2opt_dev);
+    ws->strict.release(); ws->heavy.release();
+    cudaFree(ws->counters); cudaFree(ws->strict_list); cudaFree(ws->strict2_list); cudaFree(ws->opts_dev); cudaFree(ws->len2opt_dev);
     cudaFree(ws->status_dev); cudaFree(ws->codes_dev); cudaFree(ws->off_dev); cudaFree(ws->len_dev);
     cudaFree(ws->tasks_dev); cudaFree(ws->n_aln_dev); cudaFree(ws->aln_off_dev); cudaFree(ws->aln_dev);
     cudaFree(ws->width_out_dev); cudaFree(ws->bid_dev);
@@ -552,10 +609,11 @@ extern "C" uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws) { ret
 // ---------------------------------------------------------------------------------------------- launch
 // Kernel variants.  FAST: 16-bit link halves (<= 1022 records per worker, 64 score buckets), bound bytes in shared memory
 // (FAST_ROWS: in the rows, for reads too long for shared memory).  LARGE: 32-bit halves, 64-thread blocks.
-enum Variant { V_FAST = 0, V_FAST_ROWS = 1, V_LARGE = 2 };
+enum Variant { V_FAST = 0, V_FAST_ROWS = 1, V_LARGE = 2, V_COOP = 3 };
 
 static const void *search_fn(Variant v, int block, int minb)
 {
+    if (v == V_COOP) return (const void *)coop_kernel<128>;
     if (v == V_LARGE) return (const void *)search_kernel<64, 1, uint64_t, false>;
     if (v == V_FAST_ROWS) return block == 128 ? (const void *)search_kernel<128, 4, uint32_t, false>
                                               : (const void *)search_kernel<256, 2, uint32_t, false>;
@@ -609,7 +667,15 @@ static void trace_dump(hsa_workspace *ws, const unsigned long long *cnt_all)
                 cnt_all[CNT_STEPS], cnt_all[CNT_DIAG_WARP_ITERS],
                 cnt_all[CNT_DIAG_WARP_ITERS] ? (double)cnt_all[CNT_STEPS] / (double)cnt_all[CNT_DIAG_WARP_ITERS] : 0.0,
                 cnt_all[CNT_DIAG_MAX_ITEM_STEPS], cnt_all[CNT_POPS], cnt_all[CNT_LOOKUPS]);
+    if (cnt_all && cnt_all[CNT_DIAG_COOP_WAVES])
+        fprintf(stderr, " | coop: heavy=%llu left=%llu waves=%llu wave_steps=%llu lane_steps=%llu lanes/wave_step=%.2f",
+                cnt_all[CNT_STRICT], cnt_all[CNT_STRICT2], cnt_all[CNT_DIAG_COOP_WAVES], cnt_all[CNT_DIAG_COOP_WAVES + 1],
+                cnt_all[CNT_DIAG_COOP_WAVES + 2],
+                cnt_all[CNT_DIAG_COOP_WAVES + 1] ? (double)cnt_all[CNT_DIAG_COOP_WAVES + 2] / cnt_all[CNT_DIAG_COOP_WAVES + 1] : 0.0);
 #ifdef HSA_PHASE_PROF
+    if (cnt_all && cnt_all[CNT_PROF0 + 11])
+        fprintf(stderr, " | coop cycles: chain=%.3g other=%.3g (chain share %.2f)", (double)cnt_all[CNT_PROF0 + 9],
+                (double)cnt_all[CNT_PROF0 + 10], (double)cnt_all[CNT_PROF0 + 9] / (double)cnt_all[CNT_PROF0 + 11]);
     if (cnt_all) {
         static const char *nm[3] = {"SLOW", "LOOKUP", "POP"};
         for (int i = 0; i < 3; ++i) {
@@ -635,7 +701,38 @@ static int configure(hsa_workspace *ws)
     ws->hit_cap = (uint32_t)std::max<long>(1, env_long("HSA_B200_HIT_CAP", 32));
     ws->vote_slow_min = (uint32_t)std::max<long>(1, env_long("HSA_B200_SLOW_MIN", VOTE_SLOW_MIN_DEFAULT));
     ws->vote_pop_bias = (int32_t)env_long("HSA_B200_POP_BIAS", VOTE_POP_BIAS_DEFAULT);
+    ws->use_coop = env_long("HSA_B200_COOP", 1) != 0;
+    ws->step_budget = (uint32_t)std::max<long>(0, env_long("HSA_B200_STEP_BUDGET", 0));
+    ws->drain_budget = (uint32_t)std::max<long>(0, env_long("HSA_B200_DRAIN_BUDGET", 2000));
     ws->configured = true;
+    return HSA_OK;
+}
+
+// Where a stage of the pipeline takes its work from and where it sends what it cannot hold.
+struct StageIO {
+    const uint32_t *work_list = nullptr;     // work index -> item id (nullptr: work_base + index)
+    uint32_t work_base = 0;
+    uint32_t n_work = 0;                      // work items, or the cap of a device-side count
+    const uint32_t *n_work_dev = nullptr;     // device-side count (low word of a counter)
+    uint32_t *flag_list = nullptr;            // items handed on to the next stage ...
+    unsigned long long *flag_count = nullptr; // ... and their count
+};
+
+static int coop_scratch_alloc(Pipe &p, uint32_t warps, uint32_t cap_chunks)
+{
+    if (p.coop_warps >= warps && p.coop_cap_chunks == cap_chunks) return HSA_OK;
+    cudaFree(p.coop_payload); cudaFree(p.coop_out_payload); cudaFree(p.coop_info); cudaFree(p.coop_prev);
+    cudaFree(p.coop_out_info); cudaFree(p.coop_hits);
+    p.coop_payload = p.coop_out_payload = nullptr; p.coop_info = p.coop_prev = p.coop_out_info = nullptr; p.coop_hits = nullptr;
+    p.coop_warps = 0;
+    const size_t ent = (size_t)warps * cap_chunks * COOP_CHUNK, out = (size_t)warps * 32 * COOP_OUT_CAP;
+    CU(cudaMalloc((void **)&p.coop_payload, ent * sizeof(u32x4)));
+    CU(cudaMalloc((void **)&p.coop_info, ent * 4));
+    CU(cudaMalloc((void **)&p.coop_prev, (size_t)warps * cap_chunks * 4));
+    CU(cudaMalloc((void **)&p.coop_out_payload, out * sizeof(u32x4)));
+    CU(cudaMalloc((void **)&p.coop_out_info, out * 4));
+    CU(cudaMalloc((void **)&p.coop_hits, (size_t)warps * COOP_HIT_CAP * sizeof(Hit)));
+    p.coop_warps = warps; p.coop_cap_chunks = cap_chunks;
     return HSA_OK;
 }
 
@@ -643,26 +740,32 @@ static int configure(hsa_workspace *ws)
 //   width(pass 1) -> search(pass 1) [-> width(pass 2) -> search(pass 2)]
 // Pass 2 exists only for whole reads: the reads whose reverse-complement strand found nothing are appended to a
 // device-side list by the pass-1 search kernel, and the pass-2 kernels read the list length from device memory,
-// so no host synchronisation separates the four launches.
+// so no host synchronisation separates the four launches.  `v` picks the search kernel: the fast per-lane one,
+// the warp-cooperative one (heavy searches) or the large-capacity per-lane one (last resort).
 static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, int pipe_slot, Variant v,
-                       const uint32_t *work_list, uint32_t work_base, uint32_t n_work, cudaStream_t stream)
+                       const StageIO &io, cudaStream_t stream)
 {
     const hsa_index *ix = ws->idx;
-    const bool large = v == V_LARGE;
-    const uint32_t block = large ? 64u : ws->block;
-    const size_t smem = (size_t)P.smem_opts_bytes + (size_t)block * P.smem_lane_stride;
+    const bool large = v == V_LARGE, coop = v == V_COOP;
+    const uint32_t block = large ? 64u : coop ? 128u : ws->block;
+    const size_t smem = coop ? (size_t)P.smem_opts_bytes + (size_t)(block / 32) * P.coop_warp_smem
+                             : (size_t)P.smem_opts_bytes + (size_t)block * P.smem_lane_stride;
     const void *fn = search_fn(v, (int)block, ws->minb);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)block, smem));
     if (occ < 1) return fail(HSA_E_CUDA, "search kernel does not fit on an SM");
-    if (!large && ws->blocks_per_sm_cap > 0 && occ > ws->blocks_per_sm_cap) occ = ws->blocks_per_sm_cap;
+    if (v <= V_FAST_ROWS && ws->blocks_per_sm_cap > 0 && occ > ws->blocks_per_sm_cap) occ = ws->blocks_per_sm_cap;
     uint32_t grid_full = (uint32_t)ix->sm_count * (uint32_t)occ;
     if (large) grid_full = std::min<uint32_t>(grid_full, 32);           // 2048 workers x ~6.4 MB of stack each
-    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(grid_full, (n_work + block - 1) / block));
+    const uint32_t n_work = io.n_work;
+    const uint32_t per_block = coop ? block / 32 : block;               // searches in flight per block
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(grid_full, (n_work + per_block - 1) / per_block));
     int rc;
-    if ((rc = scratch_alloc(pipe.sc, grid_full * block, large ? (1u << 18) : ws->arena_cap, large ? 4096u : ws->hit_cap,
-                            large ? 8u : 4u))) return rc;
+    if (coop) {
+        if ((rc = coop_scratch_alloc(pipe, grid_full * (block / 32), (uint32_t)env_long("HSA_B200_COOP_CHUNKS", 2048)))) return rc;
+    } else if ((rc = scratch_alloc(pipe.sc, grid_full * block, large ? (1u << 18) : ws->arena_cap, large ? 4096u : ws->hit_cap,
+                                   large ? 8u : 4u))) return rc;
     if ((rc = ensure(pipe.rows, pipe.rows_cap, (size_t)n_work * P.row_stride))) return rc;
     if (b.kind == KIND_WHOLE && (rc = ensure(pipe.next_list, pipe.next_cap, (size_t)n_work + 1))) return rc;
 
@@ -671,17 +774,23 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     P.rows = pipe.rows;
     P.arena = pipe.sc.arena; P.links = pipe.sc.links; P.arena_cap = pipe.sc.arena_cap;
     P.hits = pipe.sc.hits; P.hit_cap = pipe.sc.hit_cap;
-    P.pass = 1; P.work_list = work_list; P.work_base = work_base; P.n_work = n_work; P.n_work_dev = nullptr;
+    P.coop_payload = pipe.coop_payload; P.coop_info = pipe.coop_info; P.coop_prev = pipe.coop_prev;
+    P.coop_out_payload = pipe.coop_out_payload; P.coop_out_info = pipe.coop_out_info; P.coop_hits = pipe.coop_hits;
+    P.coop_cap_chunks = pipe.coop_cap_chunks;
+    P.strict_list = io.flag_list; P.strict_count = io.flag_count;
+    if (v > V_FAST_ROWS) { P.step_budget = 0; P.drain_budget = 0; }
+    P.pass = 1; P.work_list = io.work_list; P.work_base = io.work_base; P.n_work = n_work; P.n_work_dev = io.n_work_dev;
     P.next_list = pipe.next_list; P.next_count = reinterpret_cast<uint32_t *>(slots + 2);
     P.cursor = slots;
     const uint32_t wgrid = std::max<uint32_t>(1, std::min<uint32_t>((n_work + 255) / 256, (uint32_t)ix->sm_count * 8));
     void *args[] = {(void *)&P};
+    const char *nm1 = large ? "search1L" : coop ? "search1C" : "search1", *nm2 = large ? "search2L" : coop ? "search2C" : "search2";
     width_kernel<<<wgrid, 256, P.smem_opts_bytes, stream>>>(P);
     CU(cudaGetLastError());
     ++ws->last_launches; trace_mark(ws, "width1", stream);
     if (b.kind == KIND_WIDTH) return HSA_OK;
     CU(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream));
-    ++ws->last_launches; trace_mark(ws, large ? "search1L" : "search1", stream);
+    ++ws->last_launches; trace_mark(ws, nm1, stream);
     if (b.kind == KIND_WHOLE) {
         P.pass = 2; P.work_list = pipe.next_list; P.work_base = 0; P.n_work_dev = P.next_count;
         P.next_list = nullptr; P.next_count = nullptr; P.cursor = slots + 1;
@@ -689,9 +798,29 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
         CU(cudaGetLastError());
         ++ws->last_launches; trace_mark(ws, "width2", stream);
         CU(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream));
-        ++ws->last_launches; trace_mark(ws, large ? "search2L" : "search2", stream);
+        ++ws->last_launches; trace_mark(ws, nm2, stream);
     }
     return HSA_OK;
+}
+
+// The warp-cooperative stage needs positive scores (a chain must only push into higher buckets) and reads short
+// enough for a warp's shared-memory block; otherwise heavy searches go straight to the large-capacity kernel.
+static bool coop_usable(hsa_workspace *ws, const Batch &b, const hsa_gap_opt_t *opts_host_unused)
+{
+    (void)opts_host_unused;
+    if (!ws->use_coop || b.kind == KIND_WIDTH) return false;
+    for (uint32_t i = 0; i < b.n_opts; ++i) {
+        const DevOpt &o = ws->opts_host[i];
+        if (o.s_mm < 1 || o.s_gapo < 1 || o.s_gape < 1) return false;
+    }
+    return b.max_len <= 2000;
+}
+
+// layout of the cooperative stage: rows as the large-capacity kernel reads them, one CoopWarp + bound bytes per warp
+static void coop_layout(Params &S, const Batch &b, uint32_t seed_cap)
+{
+    set_layout(S, b.max_len, seed_cap, std::min<uint32_t>(b.n_buckets, COOP_NB), b.n_opts, 4, false);
+    S.coop_warp_smem = (uint32_t)(((sizeof(CoopWarp) + 15) & ~size_t(15)) + (S.row_tail_off - S.row_bid_off) + 16) & ~15u;
 }
 
 // Launch parameters of a batch in the fast configuration (shared by the enqueue and the finish half).
@@ -707,6 +836,7 @@ static int batch_params(hsa_workspace *ws, const Batch &b, Params &P, Variant &v
     P.counters = ws->counters; P.strict_list = ws->strict_list;
     P.width_out = b.width_out; P.bid_out = b.bid_out;
     P.vote_slow_min = ws->vote_slow_min; P.vote_pop_bias = ws->vote_pop_bias;
+    P.step_budget = ws->step_budget; P.drain_budget = ws->drain_budget;
     // fast configuration: bound bytes in shared memory if a block's share leaves room for >= 4 blocks per SM
     const uint32_t nb_fast = std::min<uint32_t>(b.n_buckets, 64);   // scores >= 64 send the item to the large-capacity kernel
     set_layout(P, b.max_len, seed_cap, nb_fast, b.n_opts, 2, true);
@@ -758,13 +888,31 @@ static int batch_enqueue(hsa_workspace *ws, const Batch &b, cudaStream_t stream,
         const uint32_t nw = (uint32_t)std::min<uint64_t>(chunk, n_work_total - w0);
         Pipe &pp = ws->pipes[c % n_pipes];
         cudaStream_t s = n_pipes > 1 ? pp.stream : stream;
-        if ((rc = issue_chunk(ws, b, P, pp, (int)(c % n_pipes), v, nullptr, (uint32_t)w0, nw, s))) return rc;
+        StageIO io;
+        io.work_base = (uint32_t)w0; io.n_work = nw;
+        io.flag_list = ws->strict_list; io.flag_count = ws->counters + CNT_STRICT;
+        if ((rc = issue_chunk(ws, b, P, pp, (int)(c % n_pipes), v, io, s))) return rc;
     }
     if (n_pipes > 1) {
         for (uint32_t p = 0; p < n_pipes; ++p) {
             CU(cudaEventRecord(ws->pipes[p].done, ws->pipes[p].stream));
             CU(cudaStreamWaitEvent(stream, ws->pipes[p].done, 0));
         }
+    }
+    // the heavy searches the fast kernel handed on (stack / hit capacity, scores >= 64, step budgets) go through the
+    // warp-cooperative kernel right behind it: its work count is read from device memory, nothing is synchronised
+    ws->heavy_enqueued = false;
+    if (b.kind != KIND_WIDTH && coop_usable(ws, b, nullptr)) {
+        ws->heavy_cap = (uint32_t)std::min<uint64_t>(n_work_total, std::max<uint64_t>(65536, n_work_total / 4));
+        if ((rc = ensure(ws->strict2_list, ws->strict2_list_cap, (size_t)n_work_total + 1))) return rc;
+        Params S = P;
+        coop_layout(S, b, seed_cap);
+        StageIO io;
+        io.work_list = ws->strict_list; io.n_work = ws->heavy_cap;
+        io.n_work_dev = reinterpret_cast<const uint32_t *>(ws->counters + CNT_STRICT);
+        io.flag_list = ws->strict2_list; io.flag_count = ws->counters + CNT_STRICT2;
+        if ((rc = issue_chunk(ws, b, S, ws->heavy, MAX_PIPES, V_COOP, io, stream))) return rc;
+        ws->heavy_enqueued = true;
     }
     CU(cudaEventRecord(ws->ev1, stream));
     ws->trace = trace_saved;
@@ -773,6 +921,30 @@ static int batch_enqueue(hsa_workspace *ws, const Batch &b, cudaStream_t stream,
 
 // Finish half: waits for the batch, re-runs the items that ran out of stack / hit capacity through the same
 // pipeline with the large-capacity kernel, returns the statistics block.
+// One synchronous re-run stage over `n` listed items (device list `list`): returns the counters after it.
+static int run_stage_sync(hsa_workspace *ws, const Batch &b, Params S, Pipe &pipe, int slot, Variant v, const uint32_t *list,
+                          uint32_t n, uint32_t *flag_list, int flag_counter, cudaStream_t stream,
+                          unsigned long long cnt[CNT_ALLOC], float *ms)
+{
+    int rc;
+    CU(cudaMemsetAsync(ws->counters + flag_counter, 0, sizeof(unsigned long long), stream));
+    StageIO io;
+    io.work_list = list; io.n_work = n; io.flag_list = flag_list; io.flag_count = ws->counters + flag_counter;
+    CU(cudaEventRecord(ws->ev0, stream));
+    if ((rc = issue_chunk(ws, b, S, pipe, slot, v, io, stream))) return rc;
+    CU(cudaEventRecord(ws->ev1, stream));
+    CU(cudaMemcpyAsync(cnt, ws->counters, CNT_ALLOC * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    trace_dump(ws, cnt);
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
+    *ms += t;
+    return HSA_OK;
+}
+
+// Finish half: waits for the batch and completes what the queued stages could not: heavy searches beyond the
+// cooperative stage's queue share, then whatever the cooperative stage handed on (or everything heavy, when that
+// stage cannot be used) through the large-capacity kernel.  Returns the statistics block.
 // `side` is the stream the statistics are read back on after the batch's end event; it differs from `stream`
 // in the job pipeline, where later jobs may already be queued on the compute stream.
 static int batch_finish(hsa_workspace *ws, const Batch &b, cudaStream_t stream, cudaStream_t side, uint64_t stats[CNT_N], float *ms)
@@ -791,32 +963,47 @@ static int batch_finish(hsa_workspace *ws, const Batch &b, cudaStream_t stream, 
     CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
     *ms = t;
     if (cnt[CNT_BAD]) return fail(HSA_E_ARG, "a score exceeded the bucket table (internal sizing error)");
-    const uint64_t n_strict = cnt[CNT_STRICT];
-    if (n_strict) {
-        // re-run the items that ran out of stack / hit capacity through the same pipeline with the large-capacity kernel
+    const uint64_t n_heavy = cnt[CNT_STRICT];                 // handed on by the fast kernel
+    const bool coop_ok = coop_usable(ws, b, nullptr);
+    Params SC = P, SL = P;
+    coop_layout(SC, b, seed_cap);
+    set_layout(SL, b.max_len, seed_cap, b.n_buckets, b.n_opts, 4, false);
+    uint64_t done_heavy = ws->heavy_enqueued ? std::min<uint64_t>(n_heavy, ws->heavy_cap) : 0;
+    if (coop_ok) {
+        if ((rc = ensure(ws->strict2_list, ws->strict2_list_cap, (size_t)std::max<uint64_t>(n_heavy, 1) + 1))) return rc;
+        while (done_heavy < n_heavy) {                        // (rare) more heavy searches than the queued stage's share
+            const uint32_t n = (uint32_t)std::min<uint64_t>(n_heavy - done_heavy, std::max<uint32_t>(ws->heavy_cap, 65536));
+            // this round's leftovers are appended behind the earlier ones: keep CNT_STRICT2 running
+            StageIO io;
+            io.work_list = ws->strict_list + done_heavy; io.n_work = n;
+            io.flag_list = ws->strict2_list; io.flag_count = ws->counters + CNT_STRICT2;
+            CU(cudaEventRecord(ws->ev0, stream));
+            if ((rc = issue_chunk(ws, b, SC, ws->heavy, MAX_PIPES, V_COOP, io, stream))) return rc;
+            CU(cudaEventRecord(ws->ev1, stream));
+            CU(cudaMemcpyAsync(cnt, ws->counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            trace_dump(ws, cnt);
+            CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
+            *ms += t;
+            done_heavy += n;
+        }
+    }
+    // last resort: the large-capacity per-lane kernel
+    const uint32_t *last_list = coop_ok ? ws->strict2_list : ws->strict_list;
+    const uint64_t n_last = coop_ok ? cnt[CNT_STRICT2] : n_heavy;
+    if (n_last) {
         uint32_t *list_dev = nullptr;
-        CU(cudaMalloc((void **)&list_dev, n_strict * 4));
-        CU(cudaMemcpyAsync(list_dev, ws->strict_list, n_strict * 4, cudaMemcpyDeviceToDevice, stream));
-        CU(cudaMemsetAsync(ws->counters + CNT_STRICT, 0, 2 * sizeof(unsigned long long), stream));
-        Params S = P;
-        set_layout(S, b.max_len, seed_cap, b.n_buckets, b.n_opts, 4, false);
-        CU(cudaEventRecord(ws->ev0, stream));
-        rc = issue_chunk(ws, b, S, ws->strict, MAX_PIPES, V_LARGE, list_dev, 0, (uint32_t)n_strict, stream);
-        if (rc) { cudaFree(list_dev); return rc; }
-        CU(cudaEventRecord(ws->ev1, stream));
-        unsigned long long cnt2[CNT_ALLOC];
-        CU(cudaMemcpyAsync(cnt2, ws->counters, sizeof(cnt2), cudaMemcpyDeviceToHost, stream));
-        CU(cudaStreamSynchronize(stream));
-        trace_dump(ws, cnt2);
+        CU(cudaMalloc((void **)&list_dev, n_last * 4));
+        CU(cudaMemcpyAsync(list_dev, last_list, n_last * 4, cudaMemcpyDeviceToDevice, stream));
+        rc = run_stage_sync(ws, b, SL, ws->strict, MAX_PIPES + 1, V_LARGE, list_dev, (uint32_t)n_last, ws->strict_list, CNT_STRICT,
+                            stream, cnt, ms);
         cudaFree(list_dev);
-        CU(cudaEventElapsedTime(&t, ws->ev0, ws->ev1));
-        *ms += t;
-        if (cnt2[CNT_STRICT] || cnt2[CNT_BAD])
+        if (rc) return rc;
+        if (cnt[CNT_STRICT] || cnt[CNT_BAD])
             return fail(HSA_E_CAPACITY, "a search exceeded the large-capacity kernel's 262144-record stack or 4096-hit capacity");
-        for (int i = 0; i < CNT_N; ++i) cnt[i] = cnt2[i];
     }
     for (int i = 0; i < CNT_N; ++i) stats[i] = cnt[i];
-    stats[CNT_STRICT] = n_strict;
+    stats[CNT_STRICT] = n_heavy;
     return HSA_OK;
 }
 
@@ -1198,8 +1385,11 @@ extern "C" int hsa_whole_reads_device(const hsa_index_t *ix, hsa_workspace_t *ws
     b.n_aln = n_aln_dev; b.aln_off = aln_off_dev; b.aln = reinterpret_cast<uint32_t *>(aln_dev); b.aln_cap = aln_capacity;
     uint64_t stats[CNT_N]; float ms = 0;
     if ((rc = run_batch(ws, b, s, false, stats, &ms))) return rc;
-    if (stats_dev)
+    if (stats_dev) {
         CU(cudaMemcpyAsync(stats_dev, ws->counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+        // word 7: searches the queued stages left unprocessed (handed on by the cooperative kernel)
+        CU(cudaMemcpyAsync(stats_dev + 7, ws->counters + CNT_STRICT2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+    }
     return HSA_OK;
 }
 

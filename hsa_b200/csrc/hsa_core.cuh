@@ -300,7 +300,8 @@ struct Hit {                    // worker-private hit record (2 x 16 bytes)
 // counters block (uint64 each)
 enum { CNT_WORK = 0, CNT_ALN = 1, CNT_LOOKUPS = 2, CNT_STRICT = 3, CNT_BAD = 4, CNT_POPS = 5, CNT_STEPS = 6, CNT_EXTRA = 7, CNT_N = 8 };
 // internal block behind the public statistics: 8 work-queue cursors, 8 pass-2 list counters, diagnostics
-enum { CNT_CURSOR0 = CNT_N, CNT_NEXT0 = CNT_N + 8, CNT_DIAG_WARP_ITERS = CNT_N + 16, CNT_DIAG_MAX_ITEM_STEPS = CNT_N + 17, CNT_TOTAL = CNT_N + 24 };
+enum { CNT_CURSOR0 = CNT_N, CNT_NEXT0 = CNT_N + 8, CNT_DIAG_WARP_ITERS = CNT_N + 16, CNT_DIAG_MAX_ITEM_STEPS = CNT_N + 17,
+       CNT_STRICT2 = CNT_N + 18, CNT_DIAG_COOP_WAVES = CNT_N + 19 /* +1 wave_steps, +2 lane steps */, CNT_TOTAL = CNT_N + 24 };
 
 struct Params {
     DevIndex ix;
@@ -346,6 +347,14 @@ struct Params {
     uint32_t *next_list;            // pass 1: reads without a hit are appended here ...
     uint32_t *next_count;           // ... and counted here (device memory)
     unsigned long long *cursor;     // atomic work-queue cursor of this launch
+    // warp-cooperative kernel (hsa_coop.cuh): per-warp global scratch (warp w at index w of each array group)
+    u32x4 *coop_payload; uint32_t *coop_info; uint32_t *coop_prev;    // cap_chunks chunks of 32 records per warp
+    u32x4 *coop_out_payload; uint32_t *coop_out_info;                 // 32 x COOP_OUT_CAP per warp
+    Hit *coop_hits;                                                    // COOP_HIT_CAP per warp
+    uint32_t coop_cap_chunks, coop_warp_smem;
+    unsigned long long *strict_count;   // where items this launch cannot hold are counted (indexes strict_list)
+    uint32_t step_budget;           // fast kernel: searches still running after this many steps are handed on (0 = off)
+    uint32_t drain_budget;          // ... the same once the work queue has run dry (bounds the launch's serial tail)
     uint32_t vote_slow_min;         // phase_vote(): lanes that must wait for a SLOW step before one is run
     int32_t  vote_pop_bias;         // phase_vote(): LOOKUP runs if n_lookup + bias >= n_pop
 };
@@ -622,11 +631,12 @@ struct Worker {
     // statistics
     uint32_t lookups_item;          // occ lookups of the current item's search
     uint32_t steps32, pops32;
+    uint32_t budget;                // step budget in force (Params::step_budget, or drain_budget once the queue is dry)
     uint64_t lookups, pops, steps;
     uint32_t max_item_steps;
 
     HSA_HD Worker(const Params &p, uint32_t slot_, uint32_t lane_in_block)
-        : P(p), slot(slot_), st(LS_IDLE), steps32(0), pops32(0), lookups(0), pops(0), steps(0), max_item_steps(0)
+        : P(p), slot(slot_), st(LS_IDLE), steps32(0), pops32(0), budget(p.step_budget), lookups(0), pops(0), steps(0), max_item_steps(0)
     {
         sm_heads = P.smem_opts_bytes + lane_in_block * P.smem_lane_stride;
         sm_bid = sm_heads + P.smem_bid_off;
@@ -773,6 +783,7 @@ struct Worker {
         ++steps32;
         // loop top of bwtgap.c:144-159
         if (n_live == 0 || (int64_t)n_live + n_phantom > (int64_t)o.max_entries) { st = LS_END; return; }
+        if (budget && steps32 > budget) { fail(STATUS_NEED_STRICT); st = LS_END; return; }   // heavy: hand it on
         const uint32_t b = bucket_lowest();
         LinkT *lk = links();
         const uint32_t ref = head_get(b);
@@ -1041,11 +1052,11 @@ struct Worker {
         if (fail_code != STATUS_OK) {
             // discard what this item produced; the host re-runs it with the large-capacity kernel
             P.n_aln[out_idx] = 0; P.aln_off[out_idx] = 0; P.status[out_idx] = (uint8_t)fail_code;
-            const int which = fail_code == STATUS_NEED_STRICT ? CNT_STRICT : CNT_BAD;
+            unsigned long long *cnt = fail_code == STATUS_NEED_STRICT ? P.strict_count : &P.counters[CNT_BAD];
 #if defined(__CUDA_ARCH__)
-            const unsigned long long idx = atomicAdd(&P.counters[which], 1ull);
+            const unsigned long long idx = atomicAdd(cnt, 1ull);
 #else
-            const unsigned long long idx = P.counters[which]++;
+            const unsigned long long idx = (*cnt)++;
 #endif
             if (fail_code == STATUS_NEED_STRICT && P.strict_list) P.strict_list[idx] = out_idx;
             return;

@@ -136,7 +136,7 @@ typedef struct hsa_result_t {     /* flat result of a batch.  ZERO-INITIALISE be
     hsa_aln1_t *aln;              /* all hits, per item in discovery order (== reference order)         */
     size_t      n_aln_total;
     uint64_t    occ_lookups;      /* BWTAllOccValue + BWTOccValue calls the reference would have issued */
-    uint64_t    n_strict;         /* items that had to be re-run with the large-capacity kernel         */
+    uint64_t    n_strict;         /* searches the fast kernel handed on to the cooperative / large kernels */
     uint64_t    pops, steps;      /* diagnostics: stack pops and worker iterations                      */
     float       kernel_ms;        /* device time of the search kernel(s), CUDA events on the stream     */
     uint32_t    kernel_launches;
@@ -177,9 +177,11 @@ void hsa_result_free(hsa_result_t *res);
 /* ---- device-resident variants for pipelines that keep reads / results in HBM (bench `value`) ------
  * All pointers are device pointers on the index's device; `stream` is a cudaStream_t passed as void*.
  * Results stay on the device: n_aln_dev[n_reads], aln_off_dev[n_reads], aln_dev[aln_capacity] and an
- * 8 x uint64 stats block {work, hits, lookups, need_strict, bad, pops, steps, -}.  Nothing is synchronised
- * and nothing is re-run: the caller checks stats[1] <= aln_capacity and stats[3] == stats[4] == 0
- * (reads that overflowed the fast kernel's stack must be re-submitted through hsa_whole_reads). */
+ * 8 x uint64 stats block {-, hits, lookups, heavy, bad, pops, steps, unprocessed}.  Nothing is synchronised:
+ * the fast kernel and, behind it, the warp-cooperative kernel for the `heavy` searches it handed on are
+ * queued on `stream`.  The caller checks stats[1] <= aln_capacity, stats[4] == 0, stats[3] <= n_reads / 4 and
+ * stats[7] == 0 (searches even the cooperative kernel could not hold; such batches go through
+ * hsa_whole_reads, which finishes them with the large-capacity kernel). */
 typedef struct hsa_workspace hsa_workspace_t;
 int  hsa_workspace_create(const hsa_index_t *idx, size_t max_reads, uint32_t max_len, size_t aln_capacity,
                           hsa_workspace_t **out);

@@ -9,6 +9,7 @@
 #include <vector>
 #include <algorithm>
 #include "../../hsa_b200/csrc/hsa_core.cuh"
+#include "../../hsa_b200/csrc/hsa_coop.cuh"
 #include "../../include/hsa_b200.h"
 
 using namespace hsa;
@@ -44,7 +45,9 @@ static size_t g_item_steps_pos = 0;
 // SIMT simulation (diagnostic): 32 workers stepped in lockstep under phase_vote(); counts how often each phase
 // runs and how many lanes take part, so scheduling policies can be compared on the CPU.
 static int g_simt = 0;
-static uint32_t g_rerun_cap = 0;                 // 0 = report flagged items instead of re-running them
+static uint32_t g_rerun_cap = 0;
+static int g_use_coop = 0;                       // re-runs go through the warp-cooperative kernel first
+static uint32_t g_step_budget = 0;               // fast configuration: hand searches on after this many steps                 // 0 = report flagged items instead of re-running them
 static uint64_t g_flagged_first = 0;
 static uint32_t g_vote_slow_min = VOTE_SLOW_MIN_DEFAULT; static int32_t g_vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
 static uint64_t g_phase_runs[3], g_phase_lanes[3];
@@ -101,6 +104,24 @@ static void run_worker(const Params &P, uint32_t n_work, uint64_t st[4])
         }
     }
     for (auto &w : ws) { st[0] += w.lookups; st[1] += w.pops; st[3] += w.steps; }
+}
+
+// the warp-cooperative kernel (hsa_coop.cuh) for one "warp": the same source, lanes looped per phase
+static uint64_t g_coop_waves = 0, g_coop_wave_steps = 0, g_coop_steps = 0;
+static void run_coop(Params P, uint32_t n_work, uint64_t st[4])
+{
+    const uint32_t cap_chunks = 4096;
+    const size_t bid_bytes = P.row_tail_off - P.row_bid_off;
+    std::vector<u32x4> wsh((sizeof(CoopWarp) + bid_bytes + 64) / 16 + 1);
+    CoopWarp *sh = reinterpret_cast<CoopWarp *>(wsh.data());
+    uint8_t *bids = reinterpret_cast<uint8_t *>(sh) + ((sizeof(CoopWarp) + 15) & ~size_t(15));
+    std::vector<u32x4> payload((size_t)cap_chunks * COOP_CHUNK), outp((size_t)32 * COOP_OUT_CAP);
+    std::vector<uint32_t> info((size_t)cap_chunks * COOP_CHUNK), prev(cap_chunks), outi((size_t)32 * COOP_OUT_CAP);
+    std::vector<Hit> hits(COOP_HIT_CAP);
+    CoopScratch g{payload.data(), info.data(), prev.data(), outp.data(), outi.data(), hits.data()};
+    static CoopLane me[32];
+    coop_run(P, *sh, bids, g, cap_chunks, n_work, me);
+    st[0] += sh->lookups; st[1] += sh->pops; st[3] += sh->steps; g_coop_waves += sh->waves; g_coop_wave_steps += sh->wave_steps; g_coop_steps += sh->steps;
 }
 
 extern "C" {
@@ -174,14 +195,19 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
     uint64_t st[4] = {0, 0, 0, 0};
     uint64_t flagged_first = 0;
 
-    for (int round = 0; round < 2; ++round) {
+    // stages as hsa_b200.cu runs them: the given configuration; then (if re-runs are on) the warp-cooperative kernel
+    // for what it flagged; then the large-capacity configuration for what that flagged
+    for (int round = 0; round < 3; ++round) {
+        const bool coop = round == 1;
+        if (coop && !g_use_coop) continue;
         const uint32_t cap = round == 0 ? arena_cap : g_rerun_cap;
         const uint32_t hcap = round == 0 ? hit_cap : 4096u;
         const bool wide = cap > 1022;
+        if (round > 0 && strict_in.empty()) break;
         const uint32_t n_work = round == 0 ? n_work_all : (uint32_t)strict_in.size();
         Params P;
         memset(&P, 0, sizeof(P));
-        set_layout(P, max_len, seed_cap, wide ? nb : std::min(nb, 64u), n_opts ? n_opts : 1, wide ? 4 : 2, !wide);
+        set_layout(P, max_len, seed_cap, wide ? nb : std::min(nb, 64u), n_opts ? n_opts : 1, wide ? 4 : 2, !wide && !coop);
         std::vector<unsigned char> smem((size_t)P.smem_opts_bytes + (size_t)lanes * P.smem_lane_stride + 16);
         memcpy(smem.data(), dopts.data(), dopts.size() * sizeof(DevOpt));
         hsa_smem_host = smem.data();
@@ -199,7 +225,8 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
         P.arena = arena.data(); P.links = links.data(); P.arena_cap = cap;
         P.hits = hits.data(); P.hit_cap = hcap;
         P.n_aln = n_aln; P.aln_off = aln_off; P.status = status; P.aln = aln; P.aln_cap = aln_cap;
-        P.counters = counters; P.strict_list = strict.data();
+        P.counters = counters; P.strict_list = strict.data(); P.strict_count = &counters[CNT_STRICT];
+        P.step_budget = round == 0 ? g_step_budget : 0;
         P.width_out = (u32x2 *)width_out; P.bid_out = bid_out;
         P.vote_slow_min = g_vote_slow_min; P.vote_pop_bias = g_vote_pop_bias;
         unsigned long long cursor = 0;
@@ -209,17 +236,20 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
         P.next_list = next_list.data(); P.next_count = &next_count;
         for (uint32_t w = 0; w < n_work; ++w) width_item(P, dopts.data(), w);
         if (kind != KIND_WIDTH) {
-            if (wide) run_worker<uint64_t, false>(P, n_work, st); else run_worker<uint32_t, true>(P, n_work, st);
+            if (coop) run_coop(P, n_work, st);
+            else if (wide) run_worker<uint64_t, false>(P, n_work, st); else run_worker<uint32_t, true>(P, n_work, st);
             if (kind == KIND_WHOLE) {
                 P.pass = 2; P.work_list = next_list.data(); P.n_work = next_count; P.next_list = nullptr; P.next_count = nullptr;
+                cursor = 0;
                 for (uint32_t w = 0; w < next_count; ++w) width_item(P, dopts.data(), w);
-                if (wide) run_worker<uint64_t, false>(P, next_count, st); else run_worker<uint32_t, true>(P, next_count, st);
+                if (coop) run_coop(P, next_count, st);
+                else if (wide) run_worker<uint64_t, false>(P, next_count, st); else run_worker<uint32_t, true>(P, next_count, st);
             }
         }
         if (round == 0) flagged_first = counters[CNT_STRICT];
-        if (round == 1 || !g_rerun_cap || counters[CNT_STRICT] == 0 || counters[CNT_BAD]) break;
+        if (!g_rerun_cap || counters[CNT_BAD]) break;
         strict_in.assign(strict.begin(), strict.begin() + counters[CNT_STRICT]);
-        counters[CNT_STRICT] = 0;
+        if (round < 2) counters[CNT_STRICT] = 0;
     }
     g_flagged_first = flagged_first;
     hsa_smem_host = nullptr;
@@ -231,6 +261,9 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
 }
 
 void emu_set_rerun(uint32_t cap) { g_rerun_cap = cap; }
+void emu_set_coop(int on, uint32_t step_budget) { g_use_coop = on; g_step_budget = step_budget; }
+uint64_t emu_coop_waves(void) { return g_coop_waves; }
+void emu_coop_stats(uint64_t *o) { o[0] = g_coop_waves; o[1] = g_coop_wave_steps; o[2] = g_coop_steps; g_coop_waves = g_coop_wave_steps = g_coop_steps = 0; }
 uint64_t emu_flagged_first(void) { return g_flagged_first; }
 void emu_set_item_steps(uint32_t *buf) { g_item_steps = buf; g_item_steps_pos = 0; }
 void emu_set_vote(uint32_t slow_min, int32_t pop_bias) { g_vote_slow_min = slow_min; g_vote_pop_bias = pop_bias; }

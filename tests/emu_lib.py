@@ -46,6 +46,8 @@ def lib():
         L.emu_occ.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ol.BwtView), C.c_void_p, C.c_size_t, C.c_void_p]
         L.emu_run.restype = C.c_long
         L.emu_set_rerun.argtypes = [C.c_uint32]
+        L.emu_set_coop.argtypes = [C.c_int, C.c_uint32]
+        L.emu_coop_waves.restype = C.c_uint64
         L.emu_flagged_first.restype = C.c_uint64
         L.emu_run.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                               C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32,
@@ -110,7 +112,7 @@ class Emu:
         return out
 
     def run(self, kind, rs, opts, tasks=None, len2opt=None, filter_max_n=0, arena_cap=1022, hit_cap=32,
-            n_items=None, want_width=False, rerun_cap=0):
+            n_items=None, want_width=False, rerun_cap=0, coop=False, step_budget=0):
         """rerun_cap: 0 = items the configuration cannot hold are reported in `status` (1); otherwise they are
         re-run with that arena capacity (the large-capacity configuration), as the product's host code does."""
         codes = np.ascontiguousarray(rs.codes, dtype=np.uint8)
@@ -132,6 +134,7 @@ class Emu:
         bid = np.zeros(rs.n, dtype=np.int32) if want_width else None
         lk, ns, pops = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         lib().emu_set_rerun(C.c_uint32(rerun_cap))
+        lib().emu_set_coop(C.c_int(1 if coop else 0), C.c_uint32(step_budget))
         total = lib().emu_run(self.h, kind, codes.ctypes.data, C.cast(tarr, C.c_void_p) if tarr is not None else None,
                               off.ctypes.data, lens.ctypes.data, n_groups, C.cast(optarr, C.c_void_p), len(opts),
                               l2o.ctypes.data if l2o is not None else None, max_len, filter_max_n, arena_cap, hit_cap,

@@ -59,3 +59,22 @@ def test_capacity_overflow_is_flagged_not_silent(golden, emu):
     assert flagged.any() and emu.last_strict == int(flagged.sum())
     assert np.array_equal(n_aln[~flagged], exp_n[~flagged])
     assert (n_aln[flagged] == 0).all()
+
+
+@pytest.mark.parametrize("mode", ["percall", "whole", "seeds"])
+@pytest.mark.parametrize("case", ["cfg1_75bp_n2o1", "cfg2_100bp_default", "cfg5_150bp_n5o2", "ragged_nonstop",
+                                  "ragged_loggap_gape", "short_entries", "exact_only", "noskip_gaps"])
+def test_cooperative_kernel_matches_reference(golden, emu, case, mode):
+    """Every search is handed to the warp-cooperative kernel (hsa_coop.cuh: speculative waves over the lowest
+    bucket, ordered commit) by giving the fast configuration a step budget of one pop; what the cooperative
+    kernel cannot hold (scores >= 64 in NONSTOP mode) falls through to the large-capacity configuration."""
+    rs = golden.reads(case)
+    opt = ol.default_opt(**golden.opt_kwargs(case))
+    n_aln, rows, status = getattr(emu, mode)(rs, opt, arena_cap=1022, hit_cap=32, rerun_cap=65535, coop=True, step_budget=1)
+    exp_n, exp_rows = golden.expected(case, mode)
+    if case != "exact_only":                   # (max_diff 0: nothing is ever popped, so nothing runs out of budget)
+        assert emu.last_flagged_first > 0      # the fast configuration really handed searches on
+    assert int((status != 0).sum()) == 0
+    assert np.array_equal(n_aln, exp_n)
+    assert np.array_equal(rows, exp_rows)
+    assert emu.last_lookups == golden.lookups(case, mode)

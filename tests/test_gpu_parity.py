@@ -111,9 +111,41 @@ def test_splice_seeds_vs_golden(golden, dev_index, case):
     assert res.occ_lookups == golden.lookups(case, "seeds")
 
 
+@pytest.mark.parametrize("case", CASES)
+def test_cooperative_kernel_path(golden, golden_index, monkeypatch, case):
+    """A step budget of one pop makes the fast kernel hand every search that pops anything to the warp-cooperative
+    kernel (hsa_coop.cuh); whole-read, per-call and seed results and the lookup count must not change."""
+    monkeypatch.setenv("HSA_B200_STEP_BUDGET", "1")
+    ix = api.Index.upload(golden_index, 0)
+    try:
+        rs = golden.reads(case)
+        opt0 = ol.default_opt(**golden.opt_kwargs(case))
+        res = ix.whole_reads(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, to_api_opt(opt0))
+        exp_n, exp_rows = golden.expected(case, "whole")
+        if case != "exact_only":
+            assert res.n_strict > 0
+        assert np.array_equal(res.n_aln, exp_n)
+        assert np.array_equal(el.aln9_to_rows12(res.ordered()), exp_rows)
+        assert res.occ_lookups == golden.lookups(case, "whole")
+        res = ix.splice_seeds(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, to_api_opt(opt0))
+        exp_n, exp_rows = golden.expected(case, "seeds")
+        assert np.array_equal(res.n_aln, exp_n)
+        assert np.array_equal(el.aln9_to_rows12(res.ordered()), exp_rows)
+        assert res.occ_lookups == golden.lookups(case, "seeds")
+        tasks, opts = percall_tasks(rs, opt0)
+        res = ix.match_gap_batch(rs.codes, tasks, opts)
+        exp_n, exp_rows = golden.expected(case, "percall")
+        assert np.array_equal(res.n_aln, exp_n)
+        assert np.array_equal(el.aln9_to_rows12(res.ordered()), exp_rows)
+        assert res.occ_lookups == golden.lookups(case, "percall")
+    finally:
+        ix.close()
+
+
 def test_strict_rerun_path(golden, golden_index, monkeypatch):
     """A deliberately tiny fast-kernel arena forces the large-capacity re-run; results must not change."""
     monkeypatch.setenv("HSA_B200_ARENA_CAP", "96")
+    monkeypatch.setenv("HSA_B200_COOP", "0")                  # straight to the large-capacity kernel
     ix = api.Index.upload(golden_index, 0)
     try:
         case = "cfg5_150bp_n5o2"
