@@ -361,6 +361,7 @@ static int check_opt(const hsa_gap_opt_t &o, uint32_t max_len, uint32_t *n_bucke
 {
     if (o.s_mm < 0 || o.s_gapo < 0 || o.s_gape < 0) return fail(HSA_E_ARG, "negative scores are not supported");
     if (o.max_diff < 0) return fail(HSA_E_ARG, "max_diff < 0 after resolution (fnr <= 0 and max_diff unset?)");
+    if (o.max_entries < 0) return fail(HSA_E_ARG, "max_entries < 0");
     if (o.max_diff > 30 || o.max_gapo > 15 || o.max_gape > 31 || o.max_gapo < 0 || o.max_gape < 0)
         return fail(HSA_E_ARG, "max_diff/max_gapo/max_gape exceed the packed stack-record fields (30/15/31)");
     if (max_len > 4095) return fail(HSA_E_ARG, "reads longer than 4095 bases are not supported");
@@ -615,8 +616,14 @@ static const void *search_fn(Variant v, int block, int minb)
 {
     if (v == V_COOP) return (const void *)coop_kernel<128>;
     if (v == V_LARGE) return (const void *)search_kernel<64, 1, uint64_t, false>;
-    if (v == V_FAST_ROWS) return block == 128 ? (const void *)search_kernel<128, 4, uint32_t, false>
-                                              : (const void *)search_kernel<256, 2, uint32_t, false>;
+    if (v == V_FAST_ROWS) {
+        if (block != 128) return (const void *)search_kernel<256, 2, uint32_t, false>;
+        switch (minb) {
+        case 5: return (const void *)search_kernel<128, 5, uint32_t, false>;
+        case 6: return (const void *)search_kernel<128, 6, uint32_t, false>;
+        default: return (const void *)search_kernel<128, 4, uint32_t, false>;
+        }
+    }
     if (block == 128) {
         switch (minb) {
         case 3: return (const void *)search_kernel<128, 3, uint32_t, true>;
@@ -841,7 +848,7 @@ static int batch_params(hsa_workspace *ws, const Batch &b, Params &P, Variant &v
     const uint32_t nb_fast = std::min<uint32_t>(b.n_buckets, 64);   // scores >= 64 send the item to the large-capacity kernel
     set_layout(P, b.max_len, seed_cap, nb_fast, b.n_opts, 2, true);
     v = V_FAST;
-    if ((size_t)P.smem_opts_bytes + (size_t)ws->block * P.smem_lane_stride > 56 * 1024) {
+    if ((size_t)P.smem_opts_bytes + (size_t)ws->block * P.smem_lane_stride > 56 * 1024 || env_long("HSA_B200_FORCE_ROWS", 0)) {
         v = V_FAST_ROWS;
         set_layout(P, b.max_len, seed_cap, nb_fast, b.n_opts, 2, false);
     }

@@ -753,7 +753,7 @@ struct Worker {
         const DevOpt &o = opt();
         if (direct) {
             // the carried child would have been pushed and popped: same loop-top test, entry included (:150-151)
-            if ((int64_t)n_live + n_phantom + 1 > (int64_t)o.max_entries) { st = LS_END; return; }
+            if (n_live + n_phantom + 1 > (uint32_t)o.max_entries) { st = LS_END; return; }
             direct = false;
         }
         m_cur = max_diff - c_nd;                                                     // :161-164
@@ -782,7 +782,7 @@ struct Worker {
         const DevOpt &o = opt();
         ++steps32;
         // loop top of bwtgap.c:144-159
-        if (n_live == 0 || (int64_t)n_live + n_phantom > (int64_t)o.max_entries) { st = LS_END; return; }
+        if (n_live == 0 || n_live + n_phantom > (uint32_t)o.max_entries) { st = LS_END; return; }
         if (budget && steps32 > budget) { fail(STATUS_NEED_STRICT); st = LS_END; return; }   // heavy: hand it on
         const uint32_t b = bucket_lowest();
         LinkT *lk = links();
@@ -928,7 +928,8 @@ struct Worker {
             if (gsc > cut) { n_phantom += nA; maskA = 0; nA = 0; }
             if (msc > cut) { n_phantom += nB; maskB = 0; nB = 0; }
             if (maskA | maskB) {
-                if ((maskA && (uint32_t)gsc >= P.n_buckets) || (maskB && (uint32_t)msc >= P.n_buckets))
+                const uint32_t hi_sc = (uint32_t)((maskA ? gsc : 0) > (maskB ? msc : 0) ? (maskA ? gsc : 0) : (maskB ? msc : 0));
+                if (hi_sc >= P.n_buckets)
                     fail(WIDE ? STATUS_BAD_SCORE : STATUS_NEED_STRICT);      // the fast kernel has 64 buckets
                 else {
                     uint32_t s = NIL;
@@ -961,7 +962,7 @@ struct Worker {
         if (sc_ < 4 && alive) {
             ck = nk; cl = nl; crl = nr; ci = i; c_diff = false;
             c_meta &= ~(3u << META_STATE_SHIFT);            // STATE_M
-            if ((int64_t)n_live + n_phantom + 1 > (int64_t)o.max_entries) { st = LS_END; return; }   // :150-151
+            if (n_live + n_phantom + 1 > (uint32_t)o.max_entries) { st = LS_END; return; }           // :150-151
             if (ci > 0 && m < (int32_t)(bb(ci - 1) & 63u)) { st = LS_POP; return; }                  // :172-173
             classify();
         } else st = LS_POP;
