@@ -35,6 +35,14 @@
 #include "BWT.h"
 
 int bwa_index_main(int argc, char **argv);
+#ifdef HSA_WITH_GPU_SHIM
+/* shim/hsa_gpu_shim.c: the reference-side binding of libhsa_b200.so (same signature as bwa_cal_sa_reg_gap) */
+int hsa_gpu_open(const Idx2BWT *bi, int device);
+void hsa_gpu_close(void);
+void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bwt, int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt, bwt_array_t *arr);
+#endif
+typedef void (*driver_fn)(int, const Idx2BWT *, int, bwa_seq_t *, const gap_opt_t *, bwt_array_t *);
+static driver_fn g_driver = bwa_cal_sa_reg_gap;
 
 #ifdef HSA_COUNT_OCC
 static unsigned long long g_occ4 = 0, g_occ1 = 0;
@@ -346,7 +354,7 @@ static double run_driver_range(Idx2BWT *bi, reads_t *r, uint32_t lo, uint32_t hi
         double t0;
         for (i = b; i < e; ++i) { seqs[i - b].seq = r->codes + r->off[i]; seqs[i - b].len = r->len[i]; }
         t0 = now_s();
-        bwa_cal_sa_reg_gap(0, bi, n, seqs, opt, arr);
+        g_driver(0, bi, n, seqs, opt, arr);
         secs += now_s() - t0;
         for (i = 0; i < (uint32_t)n; ++i) {
             bwa_seq_t *p = seqs + i;
@@ -538,6 +546,20 @@ int main(int argc, char **argv)
     if (strcmp(argv[1], "percall") == 0) return mode_percall(argc, argv);
     if (strcmp(argv[1], "seeds") == 0) return mode_seeds(argc, argv);
     if (strcmp(argv[1], "driver") == 0) return mode_driver(argc, argv);
+#ifdef HSA_WITH_GPU_SHIM
+    if (strcmp(argv[1], "gpudriver") == 0) {
+        /* the same batch loop with bwa_cal_sa_reg_gap replaced by the GPU shim (needs a full index: the splice
+         * path reads the SA and the packed DNA) */
+        Idx2BWT *bi; int rc;
+        if (argc < 5) die("usage: gpudriver <prefix> <reads> <out> [opts] [batch=N]");
+        bi = load_index(argv[2]);
+        if (hsa_gpu_open(bi, 0)) return 3;
+        g_driver = bwa_cal_sa_reg_gap_gpu;
+        rc = mode_driver(argc, argv);
+        hsa_gpu_close();
+        return rc;
+    }
+#endif
     if (strcmp(argv[1], "whole") == 0) return mode_whole(argc, argv);
     if (strcmp(argv[1], "dumpindex") == 0) return mode_dumpindex(argc, argv);
     if (strcmp(argv[1], "maxdiff") == 0) {

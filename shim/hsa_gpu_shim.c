@@ -1,0 +1,168 @@
+/*
+ * hsa_gpu_shim.c -- the reference-side binding of libhsa_b200.so, as real code.
+ *
+ * This is the file a maintainer adds to HSA: it includes the reference's own headers (bwtaln.h, bwtgap.h) and
+ * include/hsa_b200.h and provides
+ *     bwa_cal_sa_reg_gap_gpu()  -- same signature and same observable results as bwa_cal_sa_reg_gap
+ *                                  (bwtaln.c:246-417), with the whole-read searches done on the GPU.
+ * Everything after the search -- bwt_splice_match for the reads that found nothing (bwtgap.c:748), SA lookups,
+ * SAM output -- stays the reference's host code and consumes the bwt_aln1_t arrays unchanged.
+ *
+ * It is compiled only where the reference tree exists (oracle/Makefile target `shim`, outputs under oracle/_ref/)
+ * and is exercised by tests/test_gpu_shim.py, which compares its per-read output with the stock driver's.
+ *
+ * Reference behaviours mirrored on purpose:
+ *   - local_opt is copied BEFORE MODE_GAPE is cleared in the caller's opt (bwtaln.c:254, 260-261);
+ *   - after the first read of a batch that falls through to the splice path, aux->opt points at local_opt for
+ *     the rest of the batch (:363): later reads are searched with local_opt's mode / max_gapo;
+ *   - aux->opt->max_diff / seed_len are written through aux->opt for every read (:330-332), i.e. into the
+ *     caller's opt before the switch and into local_opt after it;
+ *   - the N filter compares with local_opt.max_diff (:314-317), which drifts with those writes after the switch.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "bwtaln.h"
+#include "bwtgap.h"
+#include "BWT.h"
+#include "hsa_b200.h"
+
+static hsa_index_t *g_idx = NULL;
+static hsa_result_t g_res_a, g_res_b;
+
+static void view_of(const BWT *b, hsa_bwt_view_t *v)          /* BWT.h:61-83 */
+{
+    int i;
+    v->textLength = b->textLength; v->inverseSa0 = b->inverseSa0;
+    for (i = 0; i < 5; ++i) v->cumulativeFreq[i] = b->cumulativeFreq[i];
+    v->bwtCode = b->bwtCode;             v->bwtSizeInWord = b->bwtSizeInWord;
+    v->occValue = b->occValue;           v->occSizeInWord = b->occSizeInWord;
+    v->occValueMajor = b->occValueMajor; v->occMajorSizeInWord = b->occMajorSizeInWord;
+}
+
+int hsa_gpu_open(const Idx2BWT *bi, int device)                /* call once after BWTLoad2BWT, bwtaln.c:469 */
+{
+    hsa_bwt_view_t f, r;
+    view_of(bi->bwt, &f); view_of(bi->rev_bwt, &r);
+    if (hsa_index_upload(device, &f, &r, &g_idx)) { fprintf(stderr, "[hsa_gpu] %s\n", hsa_last_error()); return -1; }
+    return 0;
+}
+
+void hsa_gpu_close(void)
+{
+    hsa_result_free(&g_res_a); hsa_result_free(&g_res_b);
+    hsa_index_free(g_idx); g_idx = NULL;
+}
+
+static void die_gpu(void) { fprintf(stderr, "[hsa_gpu] %s\n", hsa_last_error()); exit(1); }
+
+/* same signature as bwa_cal_sa_reg_gap (bwtaln.h:199-200) */
+void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt_c, bwt_array_t *arr)
+{
+    gap_opt_t *opt = (gap_opt_t *)opt_c;                       /* the reference casts const away too (:260) */
+    gap_opt_t local_opt = *opt;                                /* :254, BEFORE the clear */
+    gap_opt_t opt_a, opt_b;
+    bwt_aux_t *aux = (bwt_aux_t *)calloc(1, sizeof(bwt_aux_t));
+    int i, j, max_len = 0, leaked = 0, first_leak = -1;
+    uint8_t *codes, *state;                                    /* state: 0 run, 1 N-filtered (untouched), 2 poly-A/T */
+    uint64_t *off, total = 0;
+    uint32_t *len;
+    uint32_t *sel; int n_sel = 0;                              /* reads handed to the GPU (index into seqs) */
+    (void)tid;
+
+    opt->mode &= ~BWA_MODE_GAPE;                               /* :261, sticks in the caller's struct */
+    for (i = 0; i < n_seqs; ++i) if ((int)seqs[i].len > max_len) max_len = seqs[i].len;
+    if (opt->fnr > 0.0) local_opt.max_diff = bwa_cal_maxdiff(max_len, BWA_AVG_ERR, opt->fnr);   /* :273-274 */
+    if (local_opt.max_diff < local_opt.max_gapo) local_opt.max_gapo = local_opt.max_diff;        /* :275-276 */
+
+    /* the options of the two GPU passes: before the switch (caller's opt, GAPE cleared) and after it (local_opt) */
+    opt_a = *opt; opt_b = local_opt;
+    opt_b.seed_len = opt->seed_len;
+
+    /* ---- pass A on every read: GPU whole-read search with the pre-switch options --------------------------------
+     * The per-read filters depend on state that drifts after the switch, so they are applied on the host further
+     * down; the GPU's own N filter uses bwa_cal_maxdiff(max_len), never stricter than the drifting one. */
+    for (i = 0; i < n_seqs; ++i) total += seqs[i].len;
+    codes = (uint8_t *)malloc(total + 16); off = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1));
+    len = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1)); state = (uint8_t *)calloc(n_seqs + 1, 1);
+    sel = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1));
+    total = 0;
+    for (i = 0; i < n_seqs; ++i) {
+        off[i] = total; len[i] = seqs[i].len;
+        memcpy(codes + total, seqs[i].seq, seqs[i].len);
+        total += seqs[i].len;
+    }
+    if (n_seqs && hsa_whole_reads(g_idx, codes, off, len, (size_t)n_seqs, (const hsa_gap_opt_t *)&opt_a, 0, &g_res_a)) die_gpu();
+
+    /* ---- sequential host part: filters, the option switch, splice fallback -------------------------------------- */
+    aux->bi_bwt = (Idx2BWT *)bi_bwt; aux->arr = arr; aux->max_len = max_len;
+    aux->stack = gap_init_stack(local_opt.max_diff, local_opt.max_gapo, local_opt.max_gape, &local_opt);   /* :279 */
+    aux->width_back = (bwt_width_t *)calloc(max_len + 1, sizeof(bwt_width_t));
+    aux->width_fore = (bwt_width_t *)calloc(max_len + 1, sizeof(bwt_width_t));
+    aux->width_seed = (bwt_width_t *)calloc(max_len + 1, sizeof(bwt_width_t));
+    aux->rc_seq = (ubyte_t *)calloc(max_len, sizeof(ubyte_t));
+    aux->opt = opt;
+
+    /* find the first read that falls through (it decides where the option switch happens) using pass-A results and
+     * the pre-switch filters; then, if the two option sets differ, re-search the reads after it with local_opt */
+    {
+        int need_b = (local_opt.mode != opt->mode) || (local_opt.max_gapo != opt->max_gapo) ||
+                     (opt->fnr <= 0.0 && local_opt.max_diff != opt->max_diff);
+        for (i = 0; i < n_seqs && first_leak < 0; ++i) {
+            bwa_seq_t *p = seqs + i; int nn = 0, pa = 1, pt = 1;
+            for (j = 0; j < (int)p->len; ++j) if (p->seq[j] > 3) ++nn;
+            if (nn > local_opt.max_diff) continue;
+            for (j = 0; j < 15; ++j) { if (p->seq[j] != 0) pa = 0; if (p->seq[j] != 3) pt = 0; }
+            if (pa || pt) continue;
+            if (g_res_a.n_aln[i] == 0) first_leak = i;
+        }
+        if (first_leak >= 0 && need_b && first_leak + 1 < n_seqs) {
+            size_t k0 = (size_t)first_leak + 1, nb = (size_t)n_seqs - k0;
+            uint64_t *off_b = (uint64_t *)malloc(sizeof(uint64_t) * nb);
+            size_t q;
+            for (q = 0; q < nb; ++q) off_b[q] = off[k0 + q] - off[k0];
+            if (hsa_whole_reads(g_idx, codes + off[k0], off_b, len + k0, nb, (const hsa_gap_opt_t *)&opt_b,
+                                (opt_b.mode & BWA_MODE_GAPE) ? 1 : 0, &g_res_b)) die_gpu();
+            free(off_b);
+            n_sel = 1;                                         /* marks "pass B valid" */
+        }
+    }
+
+    for (i = 0; i < n_seqs; ++i) {
+        bwa_seq_t *p = seqs + i;
+        const hsa_result_t *res = (n_sel && i > first_leak) ? &g_res_b : &g_res_a;
+        size_t ri = (n_sel && i > first_leak) ? (size_t)(i - first_leak - 1) : (size_t)i;
+        int nn = 0;
+        for (j = 0; j < (int)p->len; ++j) if (p->seq[j] > 3) ++nn;
+        if (nn > local_opt.max_diff) continue;                 /* :314-317 (fields stay as bwa_read_seq left them) */
+        p->sa = 0; p->type = BWA_TYPE_NO_MATCH; p->c1 = p->c2 = 0; p->n_aln = 0; p->aln = 0;    /* :319-323 */
+        {
+            int pa = 1, pt = 1;
+            for (j = 0; j < 15; ++j) { if (p->seq[j] != 0) pa = 0; if (p->seq[j] != 3) pt = 0; }
+            if (pa || pt) continue;                            /* :324-325 */
+        }
+        aux->seq = p->seq; aux->len = p->len;
+        if (opt->fnr > 0.0) aux->opt->max_diff = bwa_cal_maxdiff(p->len, BWA_AVG_ERR, opt->fnr);  /* :330-331, through aux->opt */
+        aux->opt->seed_len = opt->seed_len < (int)p->len ? opt->seed_len : 0x7fffffff;            /* :332 */
+        if (res->n_aln[ri] > 0) {
+            /* the GPU result: hits in the reference's order, strand stamped on every hit, start/end on the first */
+            p->n_aln = res->n_aln[ri];
+            p->aln = (bwt_aln1_t *)calloc(p->n_aln < 10 ? 10 : p->n_aln, sizeof(bwt_aln1_t));
+            memcpy(p->aln, res->aln + res->aln_off[ri], sizeof(bwt_aln1_t) * (size_t)p->n_aln);
+            continue;
+        }
+        /* nothing on either strand: the splice path, on the host, exactly as bwtaln.c:362-369 */
+        memset(aux->rc_seq, 0, max_len * sizeof(ubyte_t));
+        memcpy(aux->rc_seq, p->seq, p->len * sizeof(ubyte_t));
+        seq_reverse(p->len, aux->rc_seq, 1);
+        aux->strand = 0;
+        aux->opt = &local_opt; leaked = 1;
+        p->aln = bwt_splice_match(aux, &p->n_aln);
+        if (p->n_aln == 0) { free(p->aln); p->aln = NULL; }
+    }
+    (void)leaked; (void)sel;
+    free(codes); free(off); free(len); free(state); free(sel);
+    free(aux->width_seed); free(aux->width_fore); free(aux->width_back); free(aux->rc_seq);
+    gap_destroy_stack(aux->stack);
+    free(aux);
+}

@@ -1,0 +1,59 @@
+"""GPU (-m gpu): the reference-side binding as real C code (shim/hsa_gpu_shim.c).
+
+oracle/_ref/hsa_ref_gpu links the UNMODIFIED reference objects, our harness and the shim against libhsa_b200.so.
+Its `gpudriver` mode runs the reference's batch loop with bwa_cal_sa_reg_gap replaced by bwa_cal_sa_reg_gap_gpu
+(whole-read searches on the GPU; bwt_splice_match and everything after it stay reference host code); `driver` runs
+the stock CPU bwa_cal_sa_reg_gap.  Both dump every read's bwt_aln1_t array; the dumps must be identical -- including
+the reads that went through the splice fallback and the reference's option switch after the first of them
+(SURVEY.md section 3.2).  The index is built by the reference's own builder (the binaries travel with the snapshot)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hsa_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "hsa_ref")
+REF_GPU = os.path.join(ROOT, "oracle", "_ref", "hsa_ref_gpu")
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    if not (os.path.exists(REF) and os.path.exists(REF_GPU)):
+        pytest.skip("oracle/_ref binaries are not present (built only where /root/reference exists)")
+    d = tmp_path_factory.mktemp("shim")
+    g = synth.make_genome(1200011, seed=41)
+    synth.write_fasta(str(d / "g.fa"), g)
+    subprocess.run([REF, "index", "g", "g.fa"], cwd=d, check=True, capture_output=True)
+    # ordinary reads, reads with a 1-bp indel (gapped hits), spliced reads and a few hopeless ones: the last two
+    # kinds fall through to bwt_splice_match and flip the driver's option switch
+    a = synth.simulate_reads(g, 5000, 100, seed=42, indel_frac=0.15)
+    b, _ = synth.simulate_spliced_reads(g, 1500, 100, seed=43, min_intron=60, max_intron=3000)
+    rng = np.random.default_rng(44)
+    junk = synth.ReadSet(np.full(60, 100, np.uint32), rng.integers(0, 4, size=6000, dtype=np.uint8))
+    codes = np.concatenate([a.codes.reshape(-1, 100), b.codes.reshape(-1, 100), junk.codes.reshape(-1, 100)])
+    codes = codes[rng.permutation(codes.shape[0])]
+    rs = synth.ReadSet(np.full(codes.shape[0], 100, np.uint32), np.ascontiguousarray(codes).reshape(-1))
+    synth.write_reads_bin(str(d / "r.reads"), rs)
+    return d
+
+
+@pytest.mark.parametrize("opts", [[], ["mode=2"], ["fnr=0", "max_diff=3", "max_gapo=2"], ["batch=1700"]],
+                         ids=["default_gape_switch", "mode_without_gape", "fixed_maxdiff", "small_batches"])
+def test_gpu_driver_matches_stock_driver(workdir, opts):
+    args = list(opts)
+    if not any(o.startswith("batch=") for o in args):
+        args.append("batch=3000")
+    cpu = subprocess.run([REF, "driver", "g", "r.reads", "cpu.aln"] + args, cwd=workdir, check=True, capture_output=True, text=True)
+    gpu = subprocess.run([REF_GPU, "gpudriver", "g", "r.reads", "gpu.aln"] + args, cwd=workdir, capture_output=True, text=True)
+    assert gpu.returncode == 0, gpu.stderr[-2000:]
+    n_c, rows_c = synth.read_aln_dump(str(workdir / "cpu.aln"))
+    n_g, rows_g = synth.read_aln_dump(str(workdir / "gpu.aln"))
+    assert (n_c > 0).sum() > 4000 and (n_c == 0).sum() > 50        # the case really covers hits, splices and misses
+    assert np.array_equal(n_c, n_g)
+    assert np.array_equal(rows_c, rows_g)
+    assert '"aligned_any"' in cpu.stdout and '"aligned_any"' in gpu.stdout
