@@ -194,6 +194,24 @@ def test_empty_and_bad_inputs(dev_index):
                               api.gap_init_opt(s_gapo=60, max_gapo=3))
 
 
+def test_long_reads_use_the_rows_variant(golden, golden_index, dev_index):
+    """Reads of 300-700 bp do not fit the per-lane shared-memory bound bytes: the fast kernel then reads them from
+    the rows (search_kernel<..., BIDS_SMEM=false>).  Checked against the oracle, whole reads and seeds."""
+    rs = synth.ragged_reads(golden.genome, 160, 300, 700, seed=77, sub_rate=0.004)
+    opt = api.gap_init_opt(fnr=0.0, max_diff=3, max_gapo=1)
+    oopt = ol.default_opt(fnr=0.0, max_diff=3, max_gapo=1)
+    o = ol.Oracle(golden_index)
+    res = dev_index.whole_reads(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt)
+    n_ref, rows_ref = o.whole(rs, oopt)
+    assert np.array_equal(res.n_aln, n_ref)
+    assert np.array_equal(el.aln9_to_rows12(res.ordered()), rows_ref)
+    assert int((n_ref > 0).sum()) > 100
+    res = dev_index.splice_seeds(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt)
+    n_ref, rows_ref = o.seeds(rs, oopt)
+    assert np.array_equal(res.n_aln, n_ref)
+    assert np.array_equal(el.aln9_to_rows12(res.ordered()), rows_ref)
+
+
 def test_medium_batch_vs_oracle_and_properties():
     """A fresh 2 Mb genome, 60k reads (fills the whole grid): bit-exact against the oracle on a sample,
     plus size-independent properties on everything: every hit interval is non-empty and inside the SA range,

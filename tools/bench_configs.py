@@ -1,0 +1,85 @@
+"""Throughput of the other BASELINE.json configs through the public API (GPU box helper; bench.py stays on
+configs[1]).  Prints one JSON line per config:
+  cfg0  4.6 Mb genome, 100 k x 75 bp, max_diff 2 / max_gapo 1            (hsa_whole_reads)
+  cfg3  spliced 100 bp reads -> six 33/33/34 bp seed searches per read    (hsa_splice_seeds), on --genome
+  cfg4  150 bp reads, 2 % substitutions, up to two indels, max_diff 5 / max_gapo 2 (hsa_whole_reads)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from hsa_b200 import api, build, index_build, synth_torch  # noqa: E402
+
+
+def pinned(t):
+    return t.cpu().pin_memory()
+
+
+def run(name, fn, n, reps=3):
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        res = fn()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, res)
+    dt, res = best
+    print(json.dumps({"config": name, "reads": n, "wall_ms": dt * 1e3, "kernel_ms": res.kernel_ms,
+                      "reads_per_s_e2e": n / dt, "reads_per_s_kernel": n / (res.kernel_ms * 1e-3),
+                      "occ_lookups": res.occ_lookups, "items_with_hits": int((res.n_aln > 0).sum()),
+                      "heavy": res.n_strict}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--genome", type=int, default=46_000_003)
+    ap.add_argument("--reads", type=int, default=2_000_000)
+    a = ap.parse_args()
+    build.build_native()
+    dev = torch.device("cuda", 0)
+
+    # cfg0
+    g0 = synth_torch.make_genome(4_600_003, 3, dev)
+    ix0 = api.Index.upload(index_build.build_index(g0, device=dev), 0)
+    n = 100_000
+    r = synth_torch.simulate_reads(g0, n, 75, 11)
+    codes, off, lens = pinned(r.reshape(-1)), pinned(torch.arange(n, dtype=torch.int64) * 75), pinned(torch.full((n,), 75, dtype=torch.int32))
+    opt = api.gap_init_opt(fnr=0.0, max_diff=2, max_gapo=1)
+    run("cfg0: 4.6 Mb, 100k x 75 bp, n2 o1", lambda: ix0.whole_reads(codes, off, lens, opt, copy=False), n)
+    ix0.close()
+
+    g = synth_torch.make_genome(a.genome, 1, dev)
+    ix = api.Index.upload(index_build.build_index(g, device=dev), 0)
+    # cfg3: spliced reads = two exons across an intron; the seed searches are what the hot path sees
+    n = a.reads
+    gen = torch.Generator(device=dev); gen.manual_seed(5)
+    L = 100
+    start = torch.randint(0, a.genome - 60_000, (n, 1), device=dev, generator=gen)
+    split = torch.randint(33, 67, (n, 1), device=dev, generator=gen)
+    intron = torch.randint(50, 50_000, (n, 1), device=dev, generator=gen)
+    j = torch.arange(L, device=dev)[None, :]
+    reads = g[start + j + torch.where(j >= split, intron, torch.zeros_like(intron))]
+    sub = torch.rand((n, L), device=dev, generator=gen) < 0.01
+    reads = torch.where(sub, (reads + torch.randint(1, 4, (n, L), dtype=torch.uint8, device=dev, generator=gen)) & 3, reads)
+    rc = torch.rand((n, 1), device=dev, generator=gen) < 0.5
+    reads = torch.where(rc, 3 - torch.flip(reads, dims=[1]), reads)
+    codes, off, lens = pinned(reads.reshape(-1)), pinned(torch.arange(n, dtype=torch.int64) * L), pinned(torch.full((n,), L, dtype=torch.int32))
+    opt = api.gap_init_opt()
+    run(f"cfg3: {a.genome} bp, {n} spliced 100 bp reads -> 6 seed searches each (33/33/34 bp)",
+        lambda: ix.splice_seeds(codes, off, lens, opt), n, reps=2)
+    # cfg4 stress
+    n = max(a.reads // 4, 100_000)
+    r = synth_torch.simulate_reads(g, n, 150, 21, sub_rate=0.02, indel_frac=0.10)
+    codes, off, lens = pinned(r.reshape(-1)), pinned(torch.arange(n, dtype=torch.int64) * 150), pinned(torch.full((n,), 150, dtype=torch.int32))
+    opt = api.gap_init_opt(fnr=0.0, max_diff=5, max_gapo=2)
+    run(f"cfg4: {a.genome} bp, {n} x 150 bp, 2% subs, 10% indel reads, n5 o2", lambda: ix.whole_reads(codes, off, lens, opt, copy=False), n, reps=2)
+
+
+if __name__ == "__main__":
+    main()
