@@ -27,7 +27,9 @@ class Task(C.Structure):  # == hsa_task_t
 
 def build():
     src = os.path.join(EMU_DIR, "hsa_emu.cpp")
-    newest = max(os.path.getmtime(src), os.path.getmtime(CORE))
+    csrc = os.path.dirname(CORE)
+    deps = [src, os.path.join(ol.ROOT, "include", "hsa_b200.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    newest = max(os.path.getmtime(d) for d in deps)
     if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < newest:
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", LIB, src])
 
