@@ -49,7 +49,7 @@ __global__ void repack_kernel(RefBwt ref, u32x4 *blocks, uint32_t n_blocks)
     const uint4 v = *reinterpret_cast<const uint4 *>(ref.bwt_code + 4 * (size_t)b);
     w.x = v.x; w.y = v.y; w.z = v.z; w.w = v.w;
     blocks[2 * (size_t)b] = c;
-    blocks[2 * (size_t)b + 1] = w;
+    blocks[2 * (size_t)b + 1] = planes_of(w);
 }
 
 __global__ void occ_kernel(DevBwt dev, RefBwt ref, int layout, const uint32_t *idx, size_t n,

@@ -15,7 +15,7 @@
 //   splice seed calls of bwt_splice_match               bwtgap.c:797-820
 //
 // How it differs from the reference in structure (not in results) -- see DESIGN.md:
-//   * device index layout: one 32-byte sector per 64 BWT symbols = {occ[4] at block start, 4 packed words},
+//   * device index layout: one 32-byte sector per 64 BWT symbols = {occ[4] at block start, two 64-bit planes},
 //     so one occ lookup touches exactly one sector instead of two (+ a major-table row);
 //   * a search is a per-lane state machine with four kinds of step -- POP (take the next stack entry and
 //     apply the reference's pop-time pruning), LOOKUP (one "occ4 at k and at l+1" pair: node expansion,
@@ -163,7 +163,7 @@ HSA_HD uint32_t sel4(const uint32_t a[4], uint32_t c)
 // ---- index --------------------------------------------------------------------------------------
 // Device layout of one BWT direction: block b = symbols [64b, 64b+64) of the '$'-less BWT string.
 //   blocks[2b]   = occ of A,C,G,T in [0, 64b)
-//   blocks[2b+1] = the four packed words of the block, first symbol in the two MSBs (BWT.c:954)
+//   blocks[2b+1] = the block's symbols as two 64-bit planes (planes_of): low code bits, high code bits
 struct DevBwt {
     const u32x4 *blocks;
     uint32_t n_blocks;
@@ -183,28 +183,41 @@ struct RefBwt {
 
 struct DevIndex { DevBwt fwd, rev; };
 
-// counts of C,G,T (A by subtraction) among the first `t` (0..32) symbols of a 64-bit MSB-first group
-HSA_HD void count_prefix64(uint64_t g, uint32_t t, uint32_t &c, uint32_t &gg, uint32_t &tt)
+// The 64 symbols of a block as two bit planes: symbol j (0 = first) sits at bit j & 31 of word j >> 5; words x, y hold
+// the low bits of the 2-bit codes, words z, w the high bits.  `v` = the block's four packed words as the reference
+// stores them (first symbol in the two MSBs, BWT.c:954).
+HSA_HD u32x4 planes_of(const u32x4 &v)
 {
-    uint64_t x = t ? (g >> (64u - 2u * t)) : 0ull;      // keep the first t symbols; zero (=A) padding
-    uint64_t lo = x & 0x5555555555555555ull;
-    uint64_t hi = (x >> 1) & 0x5555555555555555ull;
-    uint32_t both = (uint32_t)popc64(lo & hi);
-    tt += both;
-    gg += (uint32_t)popc64(hi) - both;
-    c  += (uint32_t)popc64(lo) - both;
+    const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+    uint32_t lo[2] = {0, 0}, hi[2] = {0, 0};
+    for (uint32_t j = 0; j < 64; ++j) {
+        const uint32_t code = (in[j >> 4] >> (30u - 2u * (j & 15u))) & 3u;
+        lo[j >> 5] |= (code & 1u) << (j & 31u);
+        hi[j >> 5] |= (code >> 1) << (j & 31u);
+    }
+    u32x4 r; r.x = lo[0]; r.y = lo[1]; r.z = hi[0]; r.w = hi[1];
+    return r;
+}
+
+// masks of the first `off` (0..63) symbols of a block in its two plane words
+HSA_HD void prefix_masks(uint32_t off, uint32_t &m0, uint32_t &m1)
+{
+    m0 = off >= 32u ? 0xFFFFFFFFu : (1u << off) - 1u;
+    m1 = off > 32u ? (1u << (off - 32u)) - 1u : 0u;
 }
 
 // occ of all four symbols at SA-coordinate `index` on the device layout == BWTAllOccValue (BWT.c:793)
 HSA_HD void occ4_from_sector(const u32x4 &cnt, const u32x4 &w, uint32_t off, uint32_t occ[4])
 {
-    uint32_t c = 0, g = 0, t = 0;
-    uint32_t t0 = off < 32u ? off : 32u, t1 = off - t0;
-    count_prefix64(((uint64_t)w.x << 32) | w.y, t0, c, g, t);
-    count_prefix64(((uint64_t)w.z << 32) | w.w, t1, c, g, t);
-    occ[0] = cnt.x + (off - c - g - t);
-    occ[1] = cnt.y + c;
-    occ[2] = cnt.z + g;
+    uint32_t m0, m1;
+    prefix_masks(off, m0, m1);
+    const uint32_t l0 = w.x & m0, l1 = w.y & m1, h0 = w.z & m0, h1 = w.w & m1;
+    const uint32_t t = (uint32_t)(popc32(l0 & h0) + popc32(l1 & h1));          // code 3
+    const uint32_t h = (uint32_t)(popc32(h0) + popc32(h1));                    // codes 2, 3
+    const uint32_t l = (uint32_t)(popc32(l0) + popc32(l1));                    // codes 1, 3
+    occ[0] = cnt.x + (off + t - h - l);
+    occ[1] = cnt.y + (l - t);
+    occ[2] = cnt.z + (h - t);
     occ[3] = cnt.w + t;
 }
 
@@ -453,14 +466,12 @@ HSA_HD uint32_t occ1_dev(const DevBwt &b, uint32_t index, uint32_t c)
     index -= (index > b.inverse_sa0);
     u32x4 cnt, w;
     ld_sector(b.blocks + 2 * (size_t)(index >> 6), cnt, w);
-    const uint32_t off = index & 63u, t0 = off < 32u ? off : 32u, t1 = off - t0;
-    // symbols equal to c among the first t of a 64-bit group: xor with c replicated, then both bits zero
-    const uint64_t pat = 0x5555555555555555ull * c;
-    const uint64_t g0 = (((uint64_t)w.x << 32) | w.y) ^ pat, g1 = (((uint64_t)w.z << 32) | w.w) ^ pat;
-    const uint64_t m0 = ~(g0 | (g0 >> 1)) & 0x5555555555555555ull, m1 = ~(g1 | (g1 >> 1)) & 0x5555555555555555ull;
-    const uint64_t k0 = t0 ? (~0ull << (64u - 2u * t0)) : 0ull, k1 = t1 ? (~0ull << (64u - 2u * t1)) : 0ull;
+    uint32_t m0, m1;
+    prefix_masks(index & 63u, m0, m1);
+    // symbols equal to c: both plane bits agree with c's
+    const uint32_t fl = (c & 1u) - 1u, fh = ((c >> 1) & 1u) - 1u;            // all ones where c's bit is 0
     const uint32_t base = c == 0 ? cnt.x : c == 1 ? cnt.y : c == 2 ? cnt.z : cnt.w;
-    return base + (uint32_t)popc64(m0 & k0) + (uint32_t)popc64(m1 & k1);
+    return base + (uint32_t)popc32((w.x ^ fl) & (w.z ^ fh) & m0) + (uint32_t)popc32((w.y ^ fl) & (w.w ^ fh) & m1);
 }
 
 // the bound byte of one bwt_width_t entry given the previous entry's w (0xFFFFFFFF for entry 0: never equal,

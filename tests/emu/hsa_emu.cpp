@@ -33,7 +33,7 @@ static void repack(const hsa_bwt_view_t *v, std::vector<u32x4> &out, DevBwt &d)
         c.x = occ[0]; c.y = occ[1]; c.z = occ[2]; c.w = occ[3];
         w.x = v->bwtCode[4 * (size_t)b]; w.y = v->bwtCode[4 * (size_t)b + 1];
         w.z = v->bwtCode[4 * (size_t)b + 2]; w.w = v->bwtCode[4 * (size_t)b + 3];
-        out[2 * (size_t)b] = c; out[2 * (size_t)b + 1] = w;
+        out[2 * (size_t)b] = c; out[2 * (size_t)b + 1] = planes_of(w);
     }
     d.blocks = out.data(); d.n_blocks = nb; d.text_length = v->textLength; d.inverse_sa0 = v->inverseSa0;
     for (int i = 0; i < 5; ++i) d.cum[i] = v->cumulativeFreq[i];

@@ -48,7 +48,7 @@ def main():
         print(f"[{variant or 'default'}] {out[-1] if out else 'FAILED rc=%d %s' % (p.returncode, p.stderr[-800:])}", flush=True)
         for line in p.stderr.splitlines():
             if line.startswith("[hsa_b200 trace]"):
-                print("    " + line[:400], flush=True)
+                print("    " + line[:1400], flush=True)
                 break
 
 
