@@ -115,7 +115,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
         const uint32_t n_ph = ph == PHASE_LOOKUP ? __popc(b0 & ~b1) : ph == PHASE_POP ? __popc(b1 & ~b0) : __popc(~(b0 | b1));
 #endif
         if (ph == PHASE_LOOKUP) {
-            if (c == PHASE_LOOKUP) w.do_lookup();
+            // three stages with the warp re-converged in between (hsa_core.cuh: lookup_a / lookup_push / lookup_child)
+            typename Worker<LinkT, BIDS_SMEM>::LookupCarry lc;
+            uint32_t stage = Worker<LinkT, BIDS_SMEM>::LK_DONE;
+            if (c == PHASE_LOOKUP) stage = w.lookup_a(lc);
+            __syncwarp();
+            if (stage == Worker<LinkT, BIDS_SMEM>::LK_PUSH) stage = w.lookup_push(lc);
+            __syncwarp();
+            if (stage == Worker<LinkT, BIDS_SMEM>::LK_CHILD) w.lookup_child(lc);
         } else if (ph == PHASE_POP) {
             if (c == PHASE_POP) w.do_pop();
         } else {

@@ -844,7 +844,25 @@ struct Worker {
     }
 
     // ---------------------------------------------------------------- LOOKUP: one occ4 pair + what follows
+    // A LOOKUP step runs in three stages so that the kernel can re-converge the warp between them (the lanes reach
+    // the long stages by different routes, and without a barrier each route would run them on its own):
+    //   lookup_a      the occ4 pair; complete for materialisations and bwt_match_exact steps (-> LK_DONE); for a
+    //                 node expansion decides whether children that differ from the read may exist (-> LK_PUSH) or
+    //                 only the exact-match child (-> LK_CHILD)
+    //   lookup_push   files those children as one stack record (-> LK_CHILD, or LK_DONE if the item failed)
+    //   lookup_child  continues with the exact-match child in registers
+    enum : uint32_t { LK_DONE = 0, LK_PUSH = 1, LK_CHILD = 2 };
+    struct LookupCarry { uint32_t nk, nl, nr, vmask, sc, i; bool allow_M; };
+
     HSA_HD void do_lookup()
+    {
+        LookupCarry c;
+        uint32_t stage = lookup_a(c);
+        if (stage == LK_PUSH) stage = lookup_push(c);
+        if (stage == LK_CHILD) lookup_child(c);
+    }
+
+    HSA_HD uint32_t lookup_a(LookupCarry &out)
     {
         const DevOpt &o = opt();
         ++steps32;
@@ -879,20 +897,21 @@ struct Worker {
         const uint32_t nk = sel4(sk, csel), nl = sel4(sl, csel), nr = sel4(rsl, csel);
         const bool alive = (vmask >> csel) & 1u;
 
+        out.nk = nk; out.nl = nl; out.nr = nr; out.vmask = vmask; out.sc = sc_; out.i = i; out.allow_M = true;
         if (pend) {
             // the child the reference pushed at bwtgap.c:281/297 (deletion) or :312 (mismatch): its interval
             ck = nk; cl = nl; crl = nr; pend = PEND_NONE;
             classify();
-            return;
+            return LK_DONE;
         }
         if (exact) {
             // one step of bwt_match_exact (2BWT-Interface.c:365-388)
-            if (sc_ > 3) { st = LS_POP; return; }                   // :376-377 (no lookup issued there)
+            if (sc_ > 3) { st = LS_POP; return LK_DONE; }           // :376-377 (no lookup issued there)
             lookups_item += 2;
-            if (!alive) { st = LS_POP; return; }
+            if (!alive) { st = LS_POP; return LK_DONE; }
             ck = nk; cl = nl; crl = nr; ci = i;
             if (ci == 0) st = LS_HIT;
-            return;
+            return LK_DONE;
         }
 
         // ---- node expansion (bwtgap.c:244-325) --------------------------------------------------------
@@ -911,7 +930,17 @@ struct Worker {
                 else if ((int32_t)(s0 & 63u) == m_seed - 1 && (int32_t)(s1 & 63u) == m_seed - 1 && (s1 & 0x80u)) allow_M = false;
             }
         }
-        if (allow_diff) {
+        out.allow_M = allow_M;
+        return allow_diff ? LK_PUSH : LK_CHILD;
+    }
+
+    // node expansion, bwtgap.c:267-314: the children that differ from the read, as ONE stack record
+    HSA_HD uint32_t lookup_push(const LookupCarry &in)
+    {
+        const DevOpt &o = opt();
+        const uint32_t vmask = in.vmask, sc_ = in.sc, i = in.i;
+        const bool allow_M = in.allow_M;
+        {
             const uint32_t e_go = c_gapo(), e_ge = c_gape(), e_state = c_state();
             uint32_t maskA = 0, maskB = 0;
             int32_t tmp;
@@ -965,16 +994,22 @@ struct Worker {
                         n_live += nA + nB;
                     }
                 }
-                if (fail_code != STATUS_OK) { st = LS_END; return; }
+                if (fail_code != STATUS_OK) { st = LS_END; return LK_DONE; }
             }
         }
-        // the exact-match child (bwtgap.c:303-313 with j = 4, or :315-325): would be pushed last into the lowest
-        // bucket and popped next -> it stays in registers.  Same counts as its parent, so m_cur stands.
-        if (sc_ < 4 && alive) {
-            ck = nk; cl = nl; crl = nr; ci = i; c_diff = false;
+        return LK_CHILD;
+    }
+
+    // the exact-match child (bwtgap.c:303-313 with j = 4, or :315-325): would be pushed last into the lowest
+    // bucket and popped next -> it stays in registers.  Same counts as its parent, so m_cur stands.
+    HSA_HD void lookup_child(const LookupCarry &in)
+    {
+        const DevOpt &o = opt();
+        if (in.sc < 4 && ((in.vmask >> (in.sc & 3u)) & 1u)) {
+            ck = in.nk; cl = in.nl; crl = in.nr; ci = in.i; c_diff = false;
             c_meta &= ~(3u << META_STATE_SHIFT);            // STATE_M
             if (n_live + n_phantom + 1 > (uint32_t)o.max_entries) { st = LS_END; return; }           // :150-151
-            if (ci > 0 && m < (int32_t)(bb(ci - 1) & 63u)) { st = LS_POP; return; }                  // :172-173
+            if (ci > 0 && m_cur < (int32_t)(bb(ci - 1) & 63u)) { st = LS_POP; return; }              // :172-173
             classify();
         } else st = LS_POP;
     }
