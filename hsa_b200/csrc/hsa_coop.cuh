@@ -34,6 +34,48 @@ enum : uint32_t { COOP_CHUNK = 32, COOP_OUT_CAP = 192, COOP_NB = 64, COOP_HIT_CA
 enum : uint32_t { CH_IDLE = 0, CH_RUN = 1, CH_DEAD = 2, CH_HIT = 3, CH_SUSP = 4, CH_ENTRIES = 5, CH_FAIL = 6 };
 enum : uint32_t { COOP_NONE = 0xFFFFFFFFu };
 
+// shared-memory read-modify-writes the lanes of one phase may issue together (plain in the host emulation)
+HSA_HD uint32_t coop_add32(uint32_t *p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    const uint32_t o = *p; *p = o + v; return o;
+#endif
+}
+HSA_HD void coop_or32(uint32_t *p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+HSA_HD void coop_max32(uint32_t *p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+HSA_HD void coop_or64(unsigned long long *p, unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+HSA_HD void coop_and64(unsigned long long *p, unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAnd(p, v);
+#else
+    *p &= v;
+#endif
+}
+
 struct CoopCand {                   // one search node in flight (the c* registers of the fast kernel's Worker)
     uint32_t ck, cl, crl, ci, c_meta, pend, ci_at_pop, zflags;
     int32_t c_score, c_nd, m_cur;
@@ -45,18 +87,19 @@ struct CoopWarp {                   // one per warp, in shared memory
     const uint8_t *rd; uint8_t *row;
     uint32_t rd_len, strand, sub_off, len, seed_mode, seed_shift, opt_idx, out_idx, work, have_item;
     // search state
-    uint64_t mask;                  // non-empty buckets
+    unsigned long long mask;        // non-empty buckets
     uint32_t n_live, n_phantom, n_chunks, n_hits, fail_code, done;
     int32_t best_score, max_diff, best_cnt, pop_cut;
     uint32_t top_chunk[COOP_NB]; uint8_t top_cnt[COOP_NB];
     // wave
     uint32_t b, T, W, carried, width, exact_mode, sticky_exact, n_valid, ev_lane, ev_kind, redo, base_entries;
-    uint32_t S[COOP_CHUNK + 1]; uint8_t slot_owner[COOP_CHUNK];
+    uint32_t S[COOP_CHUNK + 1]; uint8_t slot_owner[COOP_CHUNK]; uint8_t cc[COOP_CHUNK];      // cc: children per loaded record
+    uint32_t evmask, acc_pushed, acc_lookups, acc_steps, longest, n_full;                        // wave accumulators
+    unsigned long long touched;                                                                  // buckets the committing lanes pushed to
     u32x4 ent_payload[COOP_CHUNK]; uint32_t ent_info[COOP_CHUNK];
     uint16_t cnt[32][COOP_NB];      // pushes per (lane, bucket) of the wave; exclusive prefix over lanes after the scan
     uint32_t newbase[COOP_NB]; uint16_t total[COOP_NB];
     uint8_t lane_status[32]; uint16_t lane_nout[32];
-    uint32_t lane_live[32], lane_ph[32], lane_lookups[32], lane_steps[32];
     CoopCand carry;
     // statistics of the item / the warp
     uint32_t lookups_item, steps_item, pops_item, waves_item;
@@ -74,6 +117,7 @@ struct CoopScratch {                // per-warp global memory (Params::coop_* po
 struct CoopLane {
     CoopCand c;
     uint32_t status, n_out, live, ph, lookups, steps;
+    uint64_t touched;               // buckets this lane's chain pushed to (its non-zero entries of CoopWarp::cnt)
 };
 
 struct Coop {
@@ -126,6 +170,7 @@ struct Coop {
     HSA_HD void emit(CoopLane &me, uint32_t lane, uint32_t bucket, uint32_t cmask, uint32_t kind, const u32x4 &payload)
     {
         const uint32_t rank = sh.cnt[lane][bucket]++;
+        me.touched |= 1ull << bucket;
         g.out_payload[(size_t)lane * COOP_OUT_CAP + me.n_out] = payload;
         g.out_info[(size_t)lane * COOP_OUT_CAP + me.n_out] = bucket | cmask << 8 | kind << 15 | rank << 16;
         ++me.n_out;
@@ -297,6 +342,9 @@ HSA_HD void coop_run(const Params &P, CoopWarp &sh, uint8_t *bids, const CoopScr
 {
     Coop C{P, sh, bids, g, cap_chunks};
     const DevOpt *opts = reinterpret_cast<const DevOpt *>(HSA_SMEM);
+    COOP_FOR_LANES(lane)
+    { uint32_t *row = reinterpret_cast<uint32_t *>(&sh.cnt[lane][0]); for (uint32_t q = 0; q < COOP_NB / 2; ++q) row[q] = 0; COOP_ME(lane).touched = 0; }
+    COOP_END_LANES
     COOP_FOR_LANES(lane) if (lane == 0) { sh.have_item = 0; sh.lookups = sh.pops = sh.steps = sh.waves = sh.wave_steps = 0; sh.prof_chain = sh.prof_commit = sh.prof_total = 0; } COOP_END_LANES
     for (;;) {
         // ---------------------------------------------------------------- next item
@@ -351,6 +399,7 @@ HSA_HD void coop_run(const Params &P, CoopWarp &sh, uint8_t *bids, const CoopScr
                 sh.exact_mode = sh.sticky_exact;
                 sh.width = sh.exact_mode ? 1u : 32u;
                 sh.redo = 0; sh.T = 0; sh.W = 0; sh.ev_lane = COOP_NONE;
+                sh.evmask = 0; sh.touched = 0; sh.acc_pushed = 0; sh.acc_lookups = 0; sh.acc_steps = 0; sh.longest = 0; sh.n_full = 0;
                 ++sh.waves_item;
                 if (!sh.carried) {
                     // loop top of bwtgap.c:144-159 for the first pop of the wave
@@ -380,35 +429,28 @@ HSA_HD void coop_run(const Params &P, CoopWarp &sh, uint8_t *bids, const CoopScr
             if (lane < sh.T) {
                 const uint32_t idx = coop_entry_index(sh, g.prev, sh.b, lane);
                 sh.ent_payload[lane] = g.payload[idx];
-                sh.ent_info[lane] = g.info[idx];
+                const uint32_t inf = g.info[idx];
+                sh.ent_info[lane] = inf;
+                sh.cc[lane] = (uint8_t)popc32(inf & 31u);
             }
             COOP_END_LANES
-            // P2: children in pop order -> lanes (lane 0: prefix sum of the child counts, owner table)
+            // P2: children in pop order -> lanes: every record's lane sums the child counts above it and claims its slots
             COOP_FOR_LANES(lane)
-            if (lane == 0) {
-                uint32_t s = 0;
-                const uint32_t room = sh.width - sh.carried;
-                for (uint32_t t = 0; t < sh.T; ++t) {
-                    sh.S[t] = s;
-                    const uint32_t c = (uint32_t)popc32(sh.ent_info[t] & 31u);
-                    for (uint32_t q = s; q < s + c && q < room; ++q) sh.slot_owner[q] = (uint8_t)t;
-                    s += c;
-                }
-                sh.S[sh.T] = s;
-                sh.W = (s < room ? s : room) + sh.carried;
-            }
+            if (lane < sh.T) {
+                uint32_t s0 = 0;
+                for (uint32_t t = 0; t < lane; ++t) s0 += sh.cc[t];
+                sh.S[lane] = s0;
+                const uint32_t c = sh.cc[lane], room = sh.width - sh.carried;
+                for (uint32_t q = s0; q < s0 + c && q < room; ++q) sh.slot_owner[q] = (uint8_t)lane;
+                if (lane + 1 == sh.T) { sh.S[sh.T] = s0 + c; sh.W = (s0 + c < room ? s0 + c : room) + sh.carried; }
+            } else if (lane == 0 && sh.T == 0) { sh.S[0] = 0; sh.W = sh.carried; }
             COOP_END_LANES
-#if defined(HSA_PHASE_PROF) && defined(__CUDA_ARCH__)
-            if ((threadIdx.x & 31u) == 0) sh.prof_t1 = clock64();
-#endif
             // P3: every lane of the wave gets its candidate; P4: and runs its chain
             COOP_FOR_LANES(lane)
             {
                 CoopLane &me = COOP_ME(lane);
-                me.status = CH_IDLE; me.n_out = 0; me.live = 0; me.ph = 0; me.lookups = 0; me.steps = 0;
+                me.status = CH_IDLE; me.n_out = 0; me.live = 0; me.ph = 0; me.lookups = 0; me.steps = 0; me.touched = 0;
                 if (lane < sh.W) {
-                    uint32_t *row = reinterpret_cast<uint32_t *>(&sh.cnt[lane][0]);
-                    for (uint32_t q = 0; q < COOP_NB / 2; ++q) row[q] = 0;
                     if (sh.carried && lane == 0) { me.c = sh.carry; }
                     else {
                         const uint32_t q = lane - sh.carried, t = sh.slot_owner[q], r = q - sh.S[t];
@@ -418,88 +460,99 @@ HSA_HD void coop_run(const Params &P, CoopWarp &sh, uint8_t *bids, const CoopScr
                     }
                     me.status = CH_RUN;
                     C.run_chain(me, lane);
+                    sh.lane_status[lane] = (uint8_t)me.status; sh.lane_nout[lane] = (uint16_t)me.n_out;
+                    if (me.status != CH_DEAD) coop_or32(&sh.evmask, 1u << lane);
+                    coop_max32(&sh.longest, me.steps);
                 }
-                sh.lane_status[lane] = (uint8_t)me.status; sh.lane_nout[lane] = (uint16_t)me.n_out;
-                sh.lane_live[lane] = me.live; sh.lane_ph[lane] = me.ph; sh.lane_lookups[lane] = me.lookups; sh.lane_steps[lane] = me.steps;
             }
             COOP_END_LANES
-            // P5: how much of the wave commits (lane 0)
+            // P5: how much of the wave commits: everything up to and including the first chain that did not just die
             COOP_FOR_LANES(lane)
             if (lane == 0) {
-#if defined(HSA_PHASE_PROF) && defined(__CUDA_ARCH__)
-                { const unsigned long long now = clock64(); sh.prof_chain += now - sh.prof_t1; sh.prof_commit += sh.prof_t1 - sh.prof_t0; sh.prof_total += now - sh.prof_t0; sh.prof_t0 = now; }
-#endif
+                const uint32_t ev = sh.evmask ? (uint32_t)ffs64(sh.evmask) : COOP_NONE;
+                sh.ev_lane = ev; sh.n_valid = ev == COOP_NONE ? sh.W : ev + 1;
+                sh.ev_kind = ev == COOP_NONE ? (uint32_t)CH_DEAD : sh.lane_status[ev];
+                sh.wave_steps += sh.longest;
+            }
+            COOP_END_LANES
+            COOP_FOR_LANES(lane)
+            if (lane < sh.n_valid) {
+                const CoopLane &me = COOP_ME(lane);
+                if (me.live + me.ph) coop_add32(&sh.acc_pushed, me.live + me.ph);
+                if (me.lookups) coop_add32(&sh.acc_lookups, me.lookups);
+                if (me.steps) coop_add32(&sh.acc_steps, me.steps);
+                if (me.touched) coop_or64(&sh.touched, me.touched);
+            }
+            COOP_END_LANES
+            COOP_FOR_LANES(lane)
+            if (lane == 0) {
                 const DevOpt &o = opts[sh.opt_idx];
-                uint32_t nv = sh.W, ev = COOP_NONE, kind = CH_DEAD, longest = 0;
-                for (uint32_t l = 0; l < sh.W; ++l) if (sh.lane_steps[l] > longest) longest = sh.lane_steps[l];
-                sh.wave_steps += longest;
-                for (uint32_t l = 0; l < sh.W; ++l)
-                    if (sh.lane_status[l] != CH_DEAD) { ev = l; kind = sh.lane_status[l]; nv = l + 1; break; }
-                uint64_t pushed = 0;
-                for (uint32_t l = 0; l < nv; ++l) pushed += (uint64_t)sh.lane_live[l] + sh.lane_ph[l];
-                if (!sh.exact_mode && (int64_t)sh.n_live + sh.n_phantom + (int64_t)pushed + 1 > (int64_t)o.max_entries) {
-                    sh.redo = 1; nv = 0; ev = COOP_NONE;    // the max_entries test might fire inside this wave: one chain at a time
-                }
-                sh.n_valid = nv; sh.ev_lane = ev; sh.ev_kind = kind;
-                for (uint32_t l = 0; l < nv; ++l) { sh.lookups_item += sh.lane_lookups[l]; sh.steps_item += sh.lane_steps[l]; }
+                if (!sh.exact_mode && (int64_t)sh.n_live + sh.n_phantom + (int64_t)sh.acc_pushed + 1 > (int64_t)o.max_entries)
+                    sh.redo = 1;                            // the max_entries test might fire inside this wave: one chain at a time
+                else { sh.lookups_item += sh.acc_lookups; sh.steps_item += sh.acc_steps; }
             }
             COOP_END_LANES
-            if (sh.redo) continue;
-            // P6: per bucket (lane owns buckets lane and lane + 32): exclusive prefix of the counts over the
-            // committing lanes, totals, and the chunks the bucket grows by
-            COOP_FOR_LANES(lane)
-            for (uint32_t bb_ = lane; bb_ < COOP_NB; bb_ += 32) {
-                uint32_t run = 0;
-                for (uint32_t l = 0; l < sh.n_valid; ++l) { const uint32_t c = sh.cnt[l][bb_]; sh.cnt[l][bb_] = (uint16_t)run; run += c; }
-                sh.total[bb_] = (uint16_t)run;
-            }
-            COOP_END_LANES
-            COOP_FOR_LANES(lane)
-            if (lane == 0) {
-                // consume the committed children from bucket b (before appending: appends go to higher buckets)
-                const uint32_t K = sh.n_valid - (sh.n_valid ? sh.carried : 0u);     // children taken from the bucket
-                if (K) {
-                    uint32_t full = 0;
-                    for (uint32_t t = 0; t < sh.T; ++t) {
-                        const uint32_t c = (uint32_t)popc32(sh.ent_info[t] & 31u);
-                        if (sh.S[t] + c <= K) ++full;
-                        else {
-                            if (sh.S[t] < K) {              // partially consumed: drop its (K - S[t]) highest children
-                                uint32_t cm = sh.ent_info[t] & 31u;
-                                for (uint32_t x = 0; x < K - sh.S[t]; ++x) cm &= ~(1u << (31u - (uint32_t)clz32(cm)));
-                                g.info[coop_entry_index(sh, g.prev, sh.b, t)] = (sh.ent_info[t] & ~31u) | cm;
-                            }
-                            break;
-                        }
-                    }
-                    uint32_t cnt = sh.top_cnt[sh.b], chunk = sh.top_chunk[sh.b];
-                    while (full) {
-                        const uint32_t take = full < cnt ? full : cnt;
-                        cnt -= take; full -= take;
-                        if (cnt == 0) { chunk = g.prev[chunk]; cnt = chunk == COOP_NONE ? 0u : COOP_CHUNK; if (chunk == COOP_NONE) break; }
-                    }
-                    if (chunk == COOP_NONE) { sh.mask &= ~(1ull << sh.b); sh.top_chunk[sh.b] = COOP_NONE; sh.top_cnt[sh.b] = 0; }
-                    else { sh.top_chunk[sh.b] = chunk; sh.top_cnt[sh.b] = (uint8_t)cnt; }
-                    sh.n_live -= K; sh.pops_item += K;
+            if (sh.redo) {
+                COOP_FOR_LANES(lane)
+                {
+                    CoopLane &me = COOP_ME(lane);
+                    for (uint64_t m = me.touched; m; m &= m - 1) sh.cnt[lane][ffs64(m)] = 0;
+                    me.touched = 0;
                 }
-                // grow the buckets the wave pushed to
-                for (uint32_t bb_ = 0; bb_ < COOP_NB; ++bb_) {
-                    const uint32_t tot = sh.total[bb_];
-                    if (!tot) continue;
+                COOP_END_LANES
+                continue;
+            }
+            // P6: per touched bucket (lane j owns the j-th of them): exclusive prefix of the counts over the committing
+            // lanes, the total, and the chunks the bucket grows by; in parallel, the records of bucket b the wave used up
+            COOP_FOR_LANES(lane)
+            {
+                for (uint32_t skip = lane; skip < COOP_NB; skip += 32) {    // (a second round only if > 32 buckets were touched)
+                    uint64_t m = sh.touched;
+                    for (uint32_t j = 0; j < skip && m; ++j) m &= m - 1;
+                    if (!m) break;
+                    const uint32_t bb_ = (uint32_t)ffs64(m);
+                    uint32_t run = 0;
+                    // (only the lanes that pushed there get their prefix: a lane cleans up exactly the entries it touched)
+                    for (uint32_t l = 0; l < sh.n_valid; ++l) { const uint32_t c = sh.cnt[l][bb_]; if (c) { sh.cnt[l][bb_] = (uint16_t)run; run += c; } }
+                    sh.total[bb_] = (uint16_t)run;
                     const bool empty = !((sh.mask >> bb_) & 1ull);
                     const uint32_t cnt = empty ? COOP_CHUNK : sh.top_cnt[bb_];          // an empty bucket starts a fresh chunk
-                    const uint32_t need = (cnt + tot - 1) / COOP_CHUNK;                // new chunks (ordinal q >= 1)
-                    if (sh.n_chunks + need > C.cap_chunks) { sh.fail_code = STATUS_NEED_STRICT; break; }
-                    sh.newbase[bb_] = sh.n_chunks;
-                    for (uint32_t q = 0; q < need; ++q)
-                        g.prev[sh.n_chunks + q] = q ? sh.n_chunks + q - 1 : (empty ? COOP_NONE : sh.top_chunk[bb_]);
-                    sh.n_chunks += need;
+                    const uint32_t need = (cnt + run - 1) / COOP_CHUNK;                // new chunks (ordinal q >= 1)
+                    if (need) {
+                        const uint32_t base = coop_add32(&sh.n_chunks, need);
+                        if (base + need > C.cap_chunks) sh.fail_code = STATUS_NEED_STRICT;
+                        else {
+                            sh.newbase[bb_] = base;
+                            for (uint32_t q = 0; q < need; ++q)
+                                g.prev[base + q] = q ? base + q - 1 : (empty ? COOP_NONE : sh.top_chunk[bb_]);
+                        }
+                    }
                 }
-                for (uint32_t l = 0; l < sh.n_valid; ++l) { sh.n_live += sh.lane_live[l]; sh.n_phantom += sh.lane_ph[l]; }
+                // consumption of bucket b: K children were taken from its top records
+                const uint32_t K = sh.n_valid - (sh.n_valid ? sh.carried : 0u);
+                if (lane < sh.T && K) {
+                    const uint32_t c = sh.cc[lane], s0 = sh.S[lane];
+                    if (s0 + c <= K) coop_add32(&sh.n_full, 1u);
+                    else if (s0 < K) {                      // partially consumed: drop its (K - s0) highest children
+                        uint32_t cm = sh.ent_info[lane] & 31u;
+                        for (uint32_t x = 0; x < K - s0; ++x) cm &= ~(1u << (31u - (uint32_t)clz32(cm)));
+                        g.info[coop_entry_index(sh, g.prev, sh.b, lane)] = (sh.ent_info[lane] & ~31u) | cm;
+                    }
+                }
             }
             COOP_END_LANES
-            if (sh.fail_code != STATUS_OK) { COOP_FOR_LANES(lane) if (lane == 0) sh.done = 1; COOP_END_LANES break; }
-            // P7: every committing lane writes its pushes to their places
+            if (sh.fail_code != STATUS_OK) {                  // out of record chunks: the item goes to the large-capacity kernel
+                COOP_FOR_LANES(lane)
+                {
+                    CoopLane &me = COOP_ME(lane);
+                    for (uint64_t m = me.touched; m; m &= m - 1) sh.cnt[lane][ffs64(m)] = 0;
+                    me.touched = 0;
+                    if (lane == 0) sh.done = 1;
+                }
+                COOP_END_LANES
+                break;
+            }
+            // P7: every committing lane writes its pushes to their places (pre-append geometry of the target buckets)
             COOP_FOR_LANES(lane)
             if (lane < sh.n_valid) {
                 const uint32_t n = sh.lane_nout[lane];
@@ -515,77 +568,98 @@ HSA_HD void coop_run(const Params &P, CoopWarp &sh, uint8_t *bids, const CoopScr
                 }
             }
             COOP_END_LANES
-            // P8: new tops of the grown buckets (bucket owners), then the event of the wave
+            // P8: bucket b loses the records that were used up (lane 0); the grown buckets get their new tops (owners)
             COOP_FOR_LANES(lane)
-            for (uint32_t bb_ = lane; bb_ < COOP_NB; bb_ += 32) {
-                const uint32_t tot = sh.total[bb_];
-                if (!tot) continue;
-                const bool empty = !((sh.mask >> bb_) & 1ull);
-                const uint32_t cnt = empty ? COOP_CHUNK : sh.top_cnt[bb_];
-                const uint32_t pos = cnt + tot - 1, q = pos / COOP_CHUNK;
-                sh.top_chunk[bb_] = q == 0 ? sh.top_chunk[bb_] : sh.newbase[bb_] + q - 1;
-                sh.top_cnt[bb_] = (uint8_t)(pos % COOP_CHUNK + 1);
-                sh.total[bb_] = 0xFFFF;                     // marks "became / stays non-empty" for the mask update
+            {
+                if (lane == 0) {
+                    const uint32_t K = sh.n_valid - (sh.n_valid ? sh.carried : 0u);
+                    if (K) {
+                        uint32_t full = sh.n_full, cnt = sh.top_cnt[sh.b], chunk = sh.top_chunk[sh.b];
+                        while (full) {
+                            const uint32_t take = full < cnt ? full : cnt;
+                            cnt -= take; full -= take;
+                            if (cnt == 0) { chunk = g.prev[chunk]; cnt = chunk == COOP_NONE ? 0u : COOP_CHUNK; if (chunk == COOP_NONE) break; }
+                        }
+                        if (chunk == COOP_NONE) { coop_and64(&sh.mask, ~(1ull << sh.b)); sh.top_chunk[sh.b] = COOP_NONE; sh.top_cnt[sh.b] = 0; }
+                        else { sh.top_chunk[sh.b] = chunk; sh.top_cnt[sh.b] = (uint8_t)cnt; }
+                        sh.n_live -= K; sh.pops_item += K;
+                    }
+                    sh.n_live += sh.acc_pushed;             // corrected for the phantoms just below
+                    sh.carried = 0;
+                }
+                for (uint32_t skip = lane; skip < COOP_NB; skip += 32) {
+                    uint64_t m = sh.touched;
+                    for (uint32_t j = 0; j < skip && m; ++j) m &= m - 1;
+                    if (!m) break;
+                    const uint32_t bb_ = (uint32_t)ffs64(m), tot = sh.total[bb_];
+                    if (tot) {
+                        const bool empty = !((sh.mask >> bb_) & 1ull);
+                        const uint32_t cnt = empty ? COOP_CHUNK : sh.top_cnt[bb_];
+                        const uint32_t pos = cnt + tot - 1, q = pos / COOP_CHUNK;
+                        sh.top_chunk[bb_] = q == 0 ? sh.top_chunk[bb_] : sh.newbase[bb_] + q - 1;
+                        sh.top_cnt[bb_] = (uint8_t)(pos % COOP_CHUNK + 1);
+                        coop_or64(&sh.mask, 1ull << bb_);
+                    }
+                }
             }
             COOP_END_LANES
+            // P9: phantom bookkeeping, per-lane clean-up of the count table, and the event of the wave
             COOP_FOR_LANES(lane)
-            if (lane == 0) {
-                for (uint32_t bb_ = 0; bb_ < COOP_NB; ++bb_) if (sh.total[bb_] == 0xFFFF) { sh.mask |= 1ull << bb_; sh.total[bb_] = 0; }
-                sh.carried = 0;
-            }
-            COOP_END_LANES
-            // P9: the lane whose chain ended the wave handles its event
-            COOP_FOR_LANES(lane)
-            if (lane == sh.ev_lane) {
+            {
                 CoopLane &me = COOP_ME(lane);
-                const DevOpt &o = opts[sh.opt_idx];
-                if (sh.ev_kind == CH_SUSP) { sh.carry = me.c; sh.carry.flags |= 8u; sh.carried = 1; }
-                else if (sh.ev_kind == CH_ENTRIES) sh.done = 1;
-                else if (sh.ev_kind == CH_FAIL) { sh.fail_code = STATUS_NEED_STRICT; sh.done = 1; }
-                else if (sh.ev_kind == CH_HIT) {
-                    // action for found hits, bwtgap.c:188-241 (Worker::do_hit)
-                    const CoopCand &c = me.c;
-                    uint32_t k = c.ck, l = c.cl, rk = c.crl - (c.cl - c.ck), rl = c.crl;
-                    if (c.flags & 1u) {
-                        if (c.zflags & 1u) k = 0;
-                        if (c.zflags & 2u) l = 0;
-                        if (c.zflags & 4u) rk = 0;
-                        if (c.zflags & 8u) rl = 0;
-                    }
-                    const int32_t score = c.c_score;
-                    bool add = true;
-                    if (sh.n_hits == 0) {
-                        sh.best_score = score;
-                        if (!(o.mode & MODE_NONSTOP)) {
-                            sh.max_diff = (c.c_nd + 1 > o.max_diff) ? o.max_diff : c.c_nd + 1;
-                            sh.pop_cut = sh.best_score + o.s_mm;
+                if (lane < sh.n_valid && me.ph) { coop_add32(&sh.n_phantom, me.ph); coop_add32(&sh.n_live, 0u - me.ph); }
+                for (uint64_t m = me.touched; m; m &= m - 1) sh.cnt[lane][ffs64(m)] = 0;
+                me.touched = 0;
+                if (lane == sh.ev_lane) {
+                    const DevOpt &o = opts[sh.opt_idx];
+                    if (sh.ev_kind == CH_SUSP) { sh.carry = me.c; sh.carry.flags |= 8u; sh.carried = 1; }
+                    else if (sh.ev_kind == CH_ENTRIES) sh.done = 1;
+                    else if (sh.ev_kind == CH_FAIL) { sh.fail_code = STATUS_NEED_STRICT; sh.done = 1; }
+                    else if (sh.ev_kind == CH_HIT) {
+                        // action for found hits, bwtgap.c:188-241 (Worker::do_hit)
+                        const CoopCand &c = me.c;
+                        uint32_t k = c.ck, l = c.cl, rk = c.crl - (c.cl - c.ck), rl = c.crl;
+                        if (c.flags & 1u) {
+                            if (c.zflags & 1u) k = 0;
+                            if (c.zflags & 2u) l = 0;
+                            if (c.zflags & 4u) rk = 0;
+                            if (c.zflags & 8u) rl = 0;
                         }
-                    }
-                    if (score == sh.best_score) sh.best_cnt = (int32_t)((uint32_t)sh.best_cnt + (l - k + 1));
-                    else if (sh.best_cnt > o.max_top2) { sh.done = 1; add = false; }
-                    if (add && ((c.c_meta >> META_GO_SHIFT) & 15u))
-                        for (uint32_t j = 0; j < sh.n_hits; ++j)
-                            if (g.hits[j].k == k && g.hits[j].l == l) { add = false; break; }
-                    if (add) {
-                        const uint32_t x = l - k + 1, ldp = (c.flags & 2u) ? c.ci_at_pop : 0u;
-                        uint32_t *w = reinterpret_cast<uint32_t *>(sh.row);
-                        uint32_t jj = 0, w_prev = 0xFFFFFFFFu;
-                        for (uint32_t i = 0; i < ldp; ++i) {
-                            uint32_t v = w[i], bid = bids[i] & 63u;
-                            if (v > x) { v -= x; w[i] = v; }
-                            else if (v == x) { bid = 1; v = P.ix.fwd.text_length - (++jj); w[i] = v; }
-                            bids[i] = bound_byte(bid, v, w_prev);
-                            w_prev = v;
+                        const int32_t score = c.c_score;
+                        bool add = true;
+                        if (sh.n_hits == 0) {
+                            sh.best_score = score;
+                            if (!(o.mode & MODE_NONSTOP)) {
+                                sh.max_diff = (c.c_nd + 1 > o.max_diff) ? o.max_diff : c.c_nd + 1;
+                                sh.pop_cut = sh.best_score + o.s_mm;
+                            }
                         }
-                        if (ldp > 0 && ldp <= sh.len) bids[ldp] = bound_byte(bids[ldp] & 63u, w[ldp], w_prev);
-                        if (sh.n_hits >= COOP_HIT_CAP) { sh.fail_code = STATUS_NEED_STRICT; sh.done = 1; }
-                        else {
-                            Hit h;
-                            h.k = k; h.l = l; h.rev_k = rk; h.rev_l = rl;
-                            h.counts = ((c.c_meta >> META_MM_SHIFT) & 31u) | ((c.c_meta >> META_GO_SHIFT) & 15u) << 16 |
-                                       ((c.c_meta >> META_GE_SHIFT) & 31u) << 24;
-                            h.score = score; h.pad0 = h.pad1 = 0;
-                            g.hits[sh.n_hits++] = h;
+                        if (score == sh.best_score) sh.best_cnt = (int32_t)((uint32_t)sh.best_cnt + (l - k + 1));
+                        else if (sh.best_cnt > o.max_top2) { sh.done = 1; add = false; }
+                        if (add && ((c.c_meta >> META_GO_SHIFT) & 15u))
+                            for (uint32_t j = 0; j < sh.n_hits; ++j)
+                                if (g.hits[j].k == k && g.hits[j].l == l) { add = false; break; }
+                        if (add) {
+                            const uint32_t x = l - k + 1, ldp = (c.flags & 2u) ? c.ci_at_pop : 0u;
+                            uint32_t *w = reinterpret_cast<uint32_t *>(sh.row);
+                            uint32_t jj = 0, w_prev = 0xFFFFFFFFu;
+                            for (uint32_t i = 0; i < ldp; ++i) {
+                                uint32_t v = w[i], bid = bids[i] & 63u;
+                                if (v > x) { v -= x; w[i] = v; }
+                                else if (v == x) { bid = 1; v = P.ix.fwd.text_length - (++jj); w[i] = v; }
+                                bids[i] = bound_byte(bid, v, w_prev);
+                                w_prev = v;
+                            }
+                            if (ldp > 0 && ldp <= sh.len) bids[ldp] = bound_byte(bids[ldp] & 63u, w[ldp], w_prev);
+                            if (sh.n_hits >= COOP_HIT_CAP) { sh.fail_code = STATUS_NEED_STRICT; sh.done = 1; }
+                            else {
+                                Hit h;
+                                h.k = k; h.l = l; h.rev_k = rk; h.rev_l = rl;
+                                h.counts = ((c.c_meta >> META_MM_SHIFT) & 31u) | ((c.c_meta >> META_GO_SHIFT) & 15u) << 16 |
+                                           ((c.c_meta >> META_GE_SHIFT) & 31u) << 24;
+                                h.score = score; h.pad0 = h.pad1 = 0;
+                                g.hits[sh.n_hits++] = h;
+                            }
                         }
                     }
                 }
