@@ -717,7 +717,7 @@ static int configure(hsa_workspace *ws)
     ws->vote_pop_bias = (int32_t)env_long("HSA_B200_POP_BIAS", VOTE_POP_BIAS_DEFAULT);
     ws->use_coop = env_long("HSA_B200_COOP", 1) != 0;
     ws->step_budget = (uint32_t)std::max<long>(0, env_long("HSA_B200_STEP_BUDGET", 0));
-    ws->drain_budget = (uint32_t)std::max<long>(0, env_long("HSA_B200_DRAIN_BUDGET", 2000));
+    ws->drain_budget = (uint32_t)std::max<long>(0, env_long("HSA_B200_DRAIN_BUDGET", 1000));
     ws->configured = true;
     return HSA_OK;
 }

@@ -582,14 +582,15 @@ HSA_HD void width_item(const Params &P, const DevOpt *opts, uint32_t w)
 //   Children are taken highest bit first = the reverse of the reference's push order, as its LIFO buckets do.
 //   A half leaves its bucket list when its mask empties; the record is freed when both masks are empty.
 enum : uint32_t { PEND_NONE = 0, PEND_DEL = 4, PEND_MM = 8 };        // | child index in the low two bits
-enum : uint32_t { LS_IDLE = 0, LS_POP = 1, LS_LOOKUP = 2, LS_HIT = 3, LS_END = 4, LS_RETIRED = 5 };
+// (the two low bits of a state are its phase: LOOKUP 1, POP 2, retired 3, everything else waits for a SLOW step)
+enum : uint32_t { LS_IDLE = 0, LS_LOOKUP = 1, LS_POP = 2, LS_RETIRED = 3, LS_HIT = 4, LS_END = 8 };
 enum : uint32_t { PHASE_SLOW = 0, PHASE_LOOKUP = 1, PHASE_POP = 2, PHASE_NONE = 3 };
 enum : uint32_t { META_STATE_SHIFT = 13, META_MM_SHIFT = 15, META_GO_SHIFT = 20, META_GE_SHIFT = 24 };
 
 // Which kind of step a warp executes next, from the number of lanes waiting for each kind.  SLOW steps (hit
 // recording, task end, work fetch + task start) are long and rare: they run once enough lanes have queued up
 // for them, or when nothing else can run.
-enum { VOTE_SLOW_MIN_DEFAULT = 6, VOTE_POP_BIAS_DEFAULT = -12 };
+enum { VOTE_SLOW_MIN_DEFAULT = 4, VOTE_POP_BIAS_DEFAULT = -12 };
 HSA_HD uint32_t phase_vote(const Params &P, uint32_t n_lookup, uint32_t n_pop, uint32_t n_slow)
 {
     if (n_slow >= P.vote_slow_min || (n_lookup == 0 && n_pop == 0)) return PHASE_SLOW;
@@ -705,7 +706,7 @@ struct Worker {
     HSA_HD void retire() { st = LS_RETIRED; }
     HSA_HD uint32_t cls() const          // which phase this lane waits for
     {
-        return st == LS_LOOKUP ? PHASE_LOOKUP : st == LS_POP ? PHASE_POP : st == LS_RETIRED ? PHASE_NONE : PHASE_SLOW;
+        return st & 3u;
     }
     HSA_HD uint32_t c_state() const { return (c_meta >> META_STATE_SHIFT) & 3u; }
     HSA_HD uint32_t c_mm() const { return (c_meta >> META_MM_SHIFT) & 31u; }
@@ -782,7 +783,10 @@ struct Worker {
         if (ci == 0) { st = LS_HIT; return; }                                         // :177-179
         if (m_cur == 0 && (c_state() == ST_M || (o.mode & MODE_GAPE) || (int32_t)c_gape() == o.max_gape)) {   // :180
             exact = true;
-            zflags = (ck == 0) | (cl == 0) << 1 | (crl - (cl - ck) == 0) << 2 | (crl == 0) << 3;
+            // only the root has k == 0 (k' = C[c] + occ + 1 >= 1), and with it rev_k == 0; l, rev_l and every other
+            // node's rev_k (= the parent's rev_k + the interval's smaller symbols) are >= 1
+            zflags = 0;
+            if (ck == 0) zflags = 1u | (cl == 0) << 1 | (crl - (cl - ck) == 0) << 2 | (crl == 0) << 3;
         }
         st = LS_LOOKUP;
     }
