@@ -115,6 +115,9 @@ def lib():
     L.hsa_workspace_free.argtypes = [C.c_void_p]
     L.hsa_workspace_last_launches.argtypes = [C.c_void_p]
     L.hsa_workspace_last_launches.restype = C.c_uint32
+    L.hsa_workspace_launch_timing.argtypes = [C.c_void_p, C.c_int]
+    L.hsa_workspace_launch_times.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_size_t,
+                                             C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
     L.hsa_whole_reads_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                          C.c_void_p, C.c_size_t, C.POINTER(GapOpt), C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
@@ -351,6 +354,19 @@ class DeviceWorkspace:
 
     def last_launches(self) -> int:
         return int(lib().hsa_workspace_last_launches(self._h))
+
+    def launch_timing(self, enable: bool) -> None:
+        _check(lib().hsa_workspace_launch_timing(self._h, 1 if enable else 0))
+
+    def launch_times(self):
+        """([(launch name, ms), ...], occ lookups of the searches the per-lane search kernel completed) of the last
+        call made with launch_timing(True); synchronises the device."""
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        n, lk = C.c_size_t(0), C.c_uint64(0)
+        _check(lib().hsa_workspace_launch_times(self._h, names, 4096, ms, 64, C.byref(n), C.byref(lk)))
+        nm = names.value.decode().split(";") if n.value else []
+        return [(nm[i], float(ms[i])) for i in range(n.value)], int(lk.value)
 
     def close(self):
         if self._h:

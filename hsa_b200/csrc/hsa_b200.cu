@@ -160,9 +160,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
 #endif
 
     // statistics: warp-reduce, one atomic per warp
-    unsigned long long lk = w.lookups, pp = w.pops, st = w.steps;
+    unsigned long long lk = w.lookups, pp = w.pops, st = w.steps, sl = w.search_lookups;
     unsigned mx = w.max_item_steps;
     for (int o = 16; o > 0; o >>= 1) {
+        sl += __shfl_down_sync(0xffffffffu, sl, o);
         lk += __shfl_down_sync(0xffffffffu, lk, o);
         pp += __shfl_down_sync(0xffffffffu, pp, o);
         st += __shfl_down_sync(0xffffffffu, st, o);
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
         atomicAdd(&P.counters[CNT_DIAG_WARP_ITERS], warp_iters);
         atomicMax(&P.counters[CNT_DIAG_MAX_ITEM_STEPS], (unsigned long long)mx);
         atomicAdd(&P.counters[CNT_LOOKUPS], lk);
+        atomicAdd(&P.counters[CNT_DIAG_FAST_LOOKUPS], sl);
         atomicAdd(&P.counters[CNT_POPS], pp);
         atomicAdd(&P.counters[CNT_STEPS], st);
     }
@@ -614,6 +616,46 @@ extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
 
 extern "C" uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws) { return ws ? ws->last_launches : 0; }
 
+// Per-launch timing of the workspace's next calls (bench.py: the dominant kernel's own duration and algorithmic
+// bytes).  enable: one CUDA event is recorded behind every kernel launch; read: waits for the device, returns for the
+// last call the launches' names ("width1;search1;...") and durations, and the occ lookups of the searches the
+// per-lane search kernel launches completed.
+extern "C" int hsa_workspace_launch_timing(hsa_workspace_t *ws, int enable)
+{
+    if (!ws) return fail(HSA_E_ARG, "bad argument");
+    for (cudaEvent_t e : ws->trace_ev) cudaEventDestroy(e);
+    ws->trace_ev.clear(); ws->trace_name.clear();
+    ws->trace = enable ? 2 : 0;
+    return HSA_OK;
+}
+
+extern "C" int hsa_workspace_launch_times(hsa_workspace_t *ws, char *names, size_t names_cap, float *ms, size_t ms_cap,
+                                          size_t *n_out, uint64_t *fast_search_lookups)
+{
+    if (!ws || !names || !ms || !n_out) return fail(HSA_E_ARG, "bad argument");
+    CU(cudaSetDevice(ws->idx->device));
+    CU(cudaDeviceSynchronize());
+    std::string nm;
+    size_t n = 0;
+    cudaEvent_t prev = ws->ev0;
+    for (size_t i = 0; i < ws->trace_ev.size() && n < ms_cap; ++i, ++n) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, prev, ws->trace_ev[i]));
+        ms[n] = t; prev = ws->trace_ev[i];
+        if (i) nm += ";";
+        nm += ws->trace_name[i];
+    }
+    if (nm.size() + 1 > names_cap) return fail(HSA_E_ARG, "names buffer too small");
+    memcpy(names, nm.c_str(), nm.size() + 1);
+    *n_out = n;
+    if (fast_search_lookups) {
+        unsigned long long v = 0;
+        CU(cudaMemcpy(&v, ws->counters + CNT_DIAG_FAST_LOOKUPS, sizeof(v), cudaMemcpyDeviceToHost));
+        *fast_search_lookups = v;
+    }
+    return HSA_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- launch
 // Kernel variants.  FAST: 16-bit link halves (<= 1022 records per worker, 64 score buckets), bound bytes in shared memory
 // (FAST_ROWS: in the rows, for reads too long for shared memory).  LARGE: 32-bit halves, 64-thread blocks.
@@ -667,7 +709,7 @@ static void trace_mark(hsa_workspace *ws, const char *name, cudaStream_t stream)
 
 static void trace_dump(hsa_workspace *ws, const unsigned long long *cnt_all)
 {
-    if (ws->trace <= 0) return;
+    if (ws->trace <= 0 || ws->trace == 2) return;            // 2: kept for hsa_workspace_launch_times
     fprintf(stderr, "[hsa_b200 trace]");
     for (size_t i = 0; i < ws->trace_ev.size(); ++i) {
         float t = 0;
@@ -875,8 +917,9 @@ static int batch_enqueue(hsa_workspace *ws, const Batch &b, cudaStream_t stream,
     if ((rc = configure(ws))) return rc;
     ws->last_launches = 0;
     if (ws->trace < 0) ws->trace = (int)env_long("HSA_B200_TRACE", 0);
+    if (ws->trace == 2) { for (cudaEvent_t e : ws->trace_ev) cudaEventDestroy(e); ws->trace_ev.clear(); ws->trace_name.clear(); }
     const int trace_saved = ws->trace;
-    if (!allow_trace) ws->trace = 0;
+    if (!allow_trace && ws->trace != 2) ws->trace = 0;
     const uint32_t items_per_group = b.kind == KIND_SEEDS ? 6u : 1u;
     const uint64_t n_work_total = (uint64_t)b.n_groups * items_per_group;
     if ((rc = ensure(ws->status_dev, ws->status_cap, (size_t)b.n_items + 1))) return rc;

@@ -314,7 +314,8 @@ struct Hit {                    // worker-private hit record (2 x 16 bytes)
 enum { CNT_WORK = 0, CNT_ALN = 1, CNT_LOOKUPS = 2, CNT_STRICT = 3, CNT_BAD = 4, CNT_POPS = 5, CNT_STEPS = 6, CNT_EXTRA = 7, CNT_N = 8 };
 // internal block behind the public statistics: 8 work-queue cursors, 8 pass-2 list counters, diagnostics
 enum { CNT_CURSOR0 = CNT_N, CNT_NEXT0 = CNT_N + 8, CNT_DIAG_WARP_ITERS = CNT_N + 16, CNT_DIAG_MAX_ITEM_STEPS = CNT_N + 17,
-       CNT_STRICT2 = CNT_N + 18, CNT_DIAG_COOP_WAVES = CNT_N + 19 /* +1 wave_steps, +2 lane steps */, CNT_TOTAL = CNT_N + 24 };
+       CNT_STRICT2 = CNT_N + 18, CNT_DIAG_COOP_WAVES = CNT_N + 19 /* +1 wave_steps, +2 lane steps */,
+       CNT_DIAG_FAST_LOOKUPS = CNT_N + 22 /* occ lookups of the searches the per-lane kernels completed (no width pass) */, CNT_TOTAL = CNT_N + 24 };
 
 struct Params {
     DevIndex ix;
@@ -644,11 +645,11 @@ struct Worker {
     uint32_t lookups_item;          // occ lookups of the current item's search
     uint32_t steps32, pops32;
     uint32_t budget;                // step budget in force (Params::step_budget, or drain_budget once the queue is dry)
-    uint64_t lookups, pops, steps;
+    uint64_t lookups, pops, steps, search_lookups;
     uint32_t max_item_steps;
 
     HSA_HD Worker(const Params &p, uint32_t slot_, uint32_t lane_in_block)
-        : P(p), slot(slot_), st(LS_IDLE), steps32(0), pops32(0), budget(p.step_budget), lookups(0), pops(0), steps(0), max_item_steps(0)
+        : P(p), slot(slot_), st(LS_IDLE), steps32(0), pops32(0), budget(p.step_budget), lookups(0), pops(0), steps(0), search_lookups(0), max_item_steps(0)
     {
         sm_heads = P.smem_opts_bytes + lane_in_block * P.smem_lane_stride;
         sm_bid = sm_heads + P.smem_bid_off;
@@ -1112,6 +1113,7 @@ struct Worker {
             if (fail_code == STATUS_NEED_STRICT && P.strict_list) P.strict_list[idx] = out_idx;
             return;
         }
+        search_lookups += lookups_item;
         const uint64_t mine = (uint64_t)lookups_item + reinterpret_cast<const uint32_t *>(row + P.row_tail_off)[0];
         if (P.kind == KIND_WHOLE && P.pass == 1 && n_hits == 0) {
             // bwtaln.c:351-358: nothing on the reverse-complement strand -> the forward strand is searched (pass 2).

@@ -193,6 +193,14 @@ int  hsa_whole_reads_device(const hsa_index_t *idx, hsa_workspace_t *ws, const u
                             hsa_aln1_t *aln_dev, size_t aln_capacity, uint64_t *stats_dev, void *stream);
 /* number of kernels the last call on this workspace launched (for bench's gpu_launches) */
 uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws);
+/* per-launch timing of the workspace's next calls (bench.py's roofline of the dominant kernel): enable records one
+ * CUDA event behind every kernel launch; launch_times waits for the device and returns, for the last call, the
+ * launches' names ("width1;search1;width2;search2;...": passes 1/2 of the width and search kernels, suffix C for the
+ * warp-cooperative stage) with their durations in ms, and the occ lookups of the searches that the per-lane search
+ * kernel's launches completed (the algorithmic work of that kernel; the width passes' lookups are not in it). */
+int  hsa_workspace_launch_timing(hsa_workspace_t *ws, int enable);
+int  hsa_workspace_launch_times(hsa_workspace_t *ws, char *names, size_t names_cap, float *ms, size_t ms_cap,
+                                size_t *n_out, uint64_t *fast_search_lookups);
 
 /* ---- roofline probe: random 32-byte-sector loads over `footprint_bytes` ----
  * Reports achieved GB/s (sectors * 32 B / time) at full occupancy with `loads_per_thread` dependent
