@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
 {
     for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
         reinterpret_cast<int *>(hsa_smem)[i] = reinterpret_cast<const int *>(P.opts)[i];
+    if (threadIdx.x < 5) reinterpret_cast<unsigned long long *>(hsa_smem + P.smem_stats_off)[threadIdx.x] = 0ull;
     __syncthreads();
 
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,23 +160,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
         }
 #endif
 
-    // statistics: warp-reduce, one atomic per warp
-    unsigned long long lk = w.lookups, pp = w.pops, st = w.steps, sl = w.search_lookups;
-    unsigned mx = w.max_item_steps;
-    for (int o = 16; o > 0; o >>= 1) {
-        sl += __shfl_down_sync(0xffffffffu, sl, o);
-        lk += __shfl_down_sync(0xffffffffu, lk, o);
-        pp += __shfl_down_sync(0xffffffffu, pp, o);
-        st += __shfl_down_sync(0xffffffffu, st, o);
-        mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    }
-    if (lane == 0) {
-        atomicAdd(&P.counters[CNT_DIAG_WARP_ITERS], warp_iters);
-        atomicMax(&P.counters[CNT_DIAG_MAX_ITEM_STEPS], (unsigned long long)mx);
-        atomicAdd(&P.counters[CNT_LOOKUPS], lk);
-        atomicAdd(&P.counters[CNT_DIAG_FAST_LOOKUPS], sl);
-        atomicAdd(&P.counters[CNT_POPS], pp);
-        atomicAdd(&P.counters[CNT_STEPS], st);
+    // statistics: the block's shared-memory words, one set of atomics per block
+    if (lane == 0) atomicAdd(&P.counters[CNT_DIAG_WARP_ITERS], warp_iters);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long *sv = reinterpret_cast<const unsigned long long *>(hsa_smem + P.smem_stats_off);
+        typedef Worker<LinkT, BIDS_SMEM> W;
+        atomicMax(&P.counters[CNT_DIAG_MAX_ITEM_STEPS], sv[W::STAT_MAX_ITEM_STEPS]);
+        atomicAdd(&P.counters[CNT_LOOKUPS], sv[W::STAT_LOOKUPS]);
+        atomicAdd(&P.counters[CNT_DIAG_FAST_LOOKUPS], sv[W::STAT_SEARCH_LOOKUPS]);
+        atomicAdd(&P.counters[CNT_POPS], sv[W::STAT_POPS]);
+        atomicAdd(&P.counters[CNT_STEPS], sv[W::STAT_STEPS]);
     }
 }
 
@@ -804,8 +799,9 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     const hsa_index *ix = ws->idx;
     const bool large = v == V_LARGE, coop = v == V_COOP;
     const uint32_t block = large ? 64u : coop ? 128u : ws->block;
+    if (!coop) P.smem_stats_off = (uint32_t)(((size_t)P.smem_opts_bytes + (size_t)block * P.smem_lane_stride + 7) & ~size_t(7));
     const size_t smem = coop ? (size_t)P.smem_opts_bytes + (size_t)(block / 32) * P.coop_warp_smem
-                             : (size_t)P.smem_opts_bytes + (size_t)block * P.smem_lane_stride;
+                             : (size_t)P.smem_stats_off + 5 * sizeof(unsigned long long);
     const void *fn = search_fn(v, (int)block, ws->minb);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;

@@ -348,6 +348,7 @@ struct Params {
     uint32_t smem_opts_bytes;       // shared memory: option table first ...
     uint32_t smem_lane_stride;      // ... then per lane: heads[n_buckets], bound bytes back, bound bytes seed
     uint32_t smem_bid_off, smem_seed_off;   // offsets of the bound bytes inside a lane's region
+    uint32_t smem_stats_off;        // per-lane search kernels: the block's five 64-bit statistics words (8-byte aligned)
     // outputs
     int32_t  *n_aln;                // [n_items]
     uint64_t *aln_off;              // [n_items]
@@ -721,6 +722,25 @@ struct Worker {
         return (strand && c < 4) ? 3 - c : c;
     }
     HSA_HD void fail(uint32_t code) { if (fail_code == STATUS_OK) fail_code = code; }
+    // statistics: per-block words in shared memory on the device (they would cost nine registers per lane otherwise),
+    // plain members in the host emulation
+    enum : uint32_t { STAT_LOOKUPS = 0, STAT_POPS = 1, STAT_STEPS = 2, STAT_SEARCH_LOOKUPS = 3, STAT_MAX_ITEM_STEPS = 4, STAT_N = 5 };
+    HSA_HD void stat_add(uint32_t which, uint64_t v)
+    {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(reinterpret_cast<unsigned long long *>(HSA_SMEM + P.smem_stats_off) + which, (unsigned long long)v);
+#else
+        (which == STAT_LOOKUPS ? lookups : which == STAT_POPS ? pops : which == STAT_STEPS ? steps : search_lookups) += v;
+#endif
+    }
+    HSA_HD void stat_max_steps(uint32_t v)
+    {
+#if defined(__CUDA_ARCH__)
+        atomicMax(reinterpret_cast<unsigned long long *>(HSA_SMEM + P.smem_stats_off) + STAT_MAX_ITEM_STEPS, (unsigned long long)v);
+#else
+        if (v > max_item_steps) max_item_steps = v;
+#endif
+    }
 
     // ---------------------------------------------------------------- START: next work item in
     HSA_HD void start(uint32_t work_idx)
@@ -1098,8 +1118,8 @@ struct Worker {
 
     HSA_HD void do_end()
     {
-        if (steps32 > max_item_steps) max_item_steps = steps32;
-        steps += steps32; pops += pops32;
+        stat_max_steps(steps32);
+        stat_add(STAT_STEPS, steps32); stat_add(STAT_POPS, pops32);
         st = LS_IDLE;
         if (fail_code != STATUS_OK) {
             // discard what this item produced; the host re-runs it with the large-capacity kernel
@@ -1113,7 +1133,7 @@ struct Worker {
             if (fail_code == STATUS_NEED_STRICT && P.strict_list) P.strict_list[idx] = out_idx;
             return;
         }
-        search_lookups += lookups_item;
+        stat_add(STAT_SEARCH_LOOKUPS, lookups_item);
         const uint64_t mine = (uint64_t)lookups_item + reinterpret_cast<const uint32_t *>(row + P.row_tail_off)[0];
         if (P.kind == KIND_WHOLE && P.pass == 1 && n_hits == 0) {
             // bwtaln.c:351-358: nothing on the reverse-complement strand -> the forward strand is searched (pass 2).
@@ -1128,7 +1148,7 @@ struct Worker {
             P.next_list[idx] = out_idx;
             return;
         }
-        lookups += mine + ((P.kind == KIND_WHOLE && P.pass == 2) ? P.aln_off[out_idx] : 0ull);
+        stat_add(STAT_LOOKUPS, mine + ((P.kind == KIND_WHOLE && P.pass == 2) ? P.aln_off[out_idx] : 0ull));
         finish_item(out_idx, n_hits, strand);
     }
 };
