@@ -122,6 +122,9 @@ def lib():
                                          C.c_void_p, C.c_size_t, C.POINTER(GapOpt), C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.hsa_random_sector_probe.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+    L.hsa_index_attach_sa.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]
+    L.hsa_sa_values.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.hsa_sa_values_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -211,7 +214,10 @@ class Index:
         vf, vr = _view_host(index2bwt.fwd), _view_host(index2bwt.rev)
         h = C.c_void_p()
         _check(lib().hsa_index_upload(device, C.byref(vf), C.byref(vr), C.byref(h)))
-        return cls(h.value, device)
+        ix = cls(h.value, device)
+        if getattr(index2bwt.fwd, "sa_value", None) is not None:
+            ix.attach_sa(index2bwt.fwd.sa_value, index2bwt.fwd.sa_interval)
+        return ix
 
     @classmethod
     def from_prefix(cls, prefix: str, device: int = 0) -> "Index":
@@ -251,6 +257,24 @@ class Index:
             self.close()
         except Exception:
             pass
+
+    # ---- SA index -> text position -------------------------------------------------------------------
+    def attach_sa(self, sa_value: np.ndarray, sa_interval: int) -> None:
+        """The forward BWT's loaded saValue array (BWT.c:205-223), copied to the device once."""
+        sa = np.ascontiguousarray(sa_value, dtype=np.uint32)
+        _check(lib().hsa_index_attach_sa(self._h, sa.ctypes.data, sa.shape[0], int(sa_interval)))
+
+    def sa_values(self, sa_indices: np.ndarray) -> np.ndarray:
+        """BWTSaValue (BWT.c:1195-1225) for every SA index; self.last_sa_steps = PsiMinus steps walked in total."""
+        idx = np.ascontiguousarray(sa_indices, dtype=np.uint32)
+        out = np.zeros(idx.shape[0], dtype=np.uint32)
+        st = C.c_uint64(0)
+        _check(lib().hsa_sa_values(self._h, idx.ctypes.data, idx.shape[0], out.ctypes.data, C.byref(st)))
+        self.last_sa_steps = int(st.value)
+        return out
+
+    def sa_values_device(self, idx_ptr: int, n: int, out_ptr: int, steps_ptr: int = 0, stream_ptr: int = 0) -> None:
+        _check(lib().hsa_sa_values_device(self._h, idx_ptr, n, out_ptr, steps_ptr, stream_ptr))
 
     # ---- rank ---------------------------------------------------------------------------------------
     def occ(self, which: int, indices: np.ndarray, layout: int = 1) -> np.ndarray:

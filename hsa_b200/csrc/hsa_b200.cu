@@ -63,6 +63,50 @@ __global__ void occ_kernel(DevBwt dev, RefBwt ref, int layout, const uint32_t *i
     for (int c = 0; c < 4; ++c) { occ4_out[4 * i + c] = occ[c]; occ1_out[4 * i + c] = occ[c]; }
 }
 
+// SA index -> text position (BWTSaValue, BWT.c:1195-1225): a chain of dependent sector loads per query whose length
+// is geometric (one SA index in sa_interval is sampled), so lanes are refilled from a work queue the moment their chain
+// ends instead of idling until the warp's longest chain is done.  A warp reserves SA_CHUNK queries at a time (one
+// atomic), hands them to its free lanes in order, and every lane makes one PsiMinus step per trip.
+enum : uint32_t { SA_CHUNK = 1024 };
+__global__ void __launch_bounds__(256) sa_kernel(DevBwt fwd, const uint32_t *sa_value, uint32_t sa_interval,
+                                                 const uint32_t *sa_index, size_t n, uint32_t *out,
+                                                 unsigned long long *cursor, unsigned long long *steps_total)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long base = 0, my = 0, steps = 0;
+    uint32_t remain = 0, cur = 0, walked = 0;
+    bool busy = false, dry = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        if (idle && !dry) {
+            if (remain == 0) {                          // reserve the warp's next chunk
+                if (lane == 0) base = atomicAdd(cursor, (unsigned long long)SA_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n) dry = true;
+                else remain = (uint32_t)min((unsigned long long)SA_CHUNK, (unsigned long long)n - base);
+            }
+            if (!dry) {
+                const uint32_t rank = __popc(idle & ((1u << lane) - 1u)), take = min(remain, (uint32_t)__popc(idle));
+                if (!busy && rank < take) { my = base + rank; cur = sa_index[my]; walked = 0; busy = true; }
+                base += take; remain -= take;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, busy) == 0) { if (dry) break; else continue; }
+        if (busy) {
+            if (cur % sa_interval == 0) {               // a sampled SA index: done (BWT.c:1223)
+                out[my] = __ldg(sa_value + cur / sa_interval) + walked;
+                steps += walked;
+                busy = false;
+            } else {
+                ++walked;
+                cur = cur == fwd.inverse_sa0 ? 0u : psi_minus_dev(fwd, cur);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+    if (lane == 0 && steps_total) atomicAdd(steps_total, steps);
+}
+
 // Width kernel of the split pipeline: one thread per work item, every thread of a warp walks reads of the
 // same shape, so the loop is divergence-free (bwt_cal_width is a strictly sequential chain per read).
 __global__ void __launch_bounds__(256, 5) width_kernel(const __grid_constant__ Params P)
@@ -269,6 +313,8 @@ struct hsa_index {
     bool pool_busy[3] = {false, false, false};
     cudaStream_t h2d = nullptr, d2h = nullptr;                     // copy streams of the job pipeline
     int sm_count = 0;
+    uint32_t *sa_value = nullptr; size_t sa_words = 0; uint32_t sa_interval = 0;    // forward text's SA samples (optional)
+    unsigned long long *sa_counters = nullptr;                                        // {work cursor, PsiMinus steps}
 };
 
 struct Scratch {                             // worker-private device memory for one launch configuration
@@ -543,6 +589,7 @@ extern "C" void hsa_index_free(hsa_index_t *ix)
     if (ix->d2h) cudaStreamDestroy(ix->d2h);
     if (ix->own_ref) for (int d = 0; d < 2; ++d) { cudaFree(ix->ref_code[d]); cudaFree(ix->ref_occ[d]); cudaFree(ix->ref_major[d]); }
     if (ix->own_blocks) for (int d = 0; d < 2; ++d) cudaFree(ix->blocks[d]);
+    cudaFree(ix->sa_value); cudaFree(ix->sa_counters);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -565,6 +612,74 @@ extern "C" int hsa_occ_batch(const hsa_index_t *ix, int which, int layout, const
     if (occ1_out) CU(cudaMemcpyAsync(occ1_out, d1, n * 16, cudaMemcpyDeviceToHost, ix->stream));
     CU(cudaStreamSynchronize(ix->stream));
     cudaFree(d_idx); cudaFree(d4); cudaFree(d1);
+    return HSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- SA -> position
+extern "C" int hsa_index_attach_sa(hsa_index_t *ix, const uint32_t *sa_value, size_t n_words, uint32_t sa_interval)
+{
+    if (!ix || !sa_value || sa_interval == 0) return fail(HSA_E_ARG, "bad argument");
+    const uint32_t n = ix->ix.fwd.text_length;
+    if (n_words != ((size_t)n + sa_interval) / sa_interval) return fail(HSA_E_ARG, "SA sample count does not match textLength / saInterval (BWT.c:219)");
+    CU(cudaSetDevice(ix->device));
+    cudaFree(ix->sa_value); ix->sa_value = nullptr;
+    CU(cudaMalloc((void **)&ix->sa_value, n_words * sizeof(uint32_t)));
+    if (!ix->sa_counters) CU(cudaMalloc((void **)&ix->sa_counters, 2 * sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(ix->sa_value, sa_value, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+    const uint32_t minus1 = 0xFFFFFFFFu;                 // BWT.c:222: SA[0] is kept as -1 whatever the file holds
+    CU(cudaMemcpyAsync(ix->sa_value, &minus1, sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+    ix->sa_words = n_words; ix->sa_interval = sa_interval;
+    return HSA_OK;
+}
+
+static int sa_launch(const hsa_index_t *ix, const uint32_t *idx_dev, size_t n, uint32_t *out_dev, cudaStream_t s)
+{
+    CU(cudaMemsetAsync(ix->sa_counters, 0, 2 * sizeof(unsigned long long), s));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_kernel, 256, 0));
+    const size_t want = (n + SA_CHUNK - 1) / SA_CHUNK;   // one warp per chunk is the most that can find work
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)ix->sm_count * std::max(occ, 1), (want + 7) / 8));
+    sa_kernel<<<grid, 256, 0, s>>>(ix->ix.fwd, ix->sa_value, ix->sa_interval, idx_dev, n, out_dev, ix->sa_counters, ix->sa_counters + 1);
+    CU(cudaGetLastError());
+    return HSA_OK;
+}
+
+extern "C" int hsa_sa_values(const hsa_index_t *ix, const uint32_t *sa_index, size_t n, uint32_t *sa_value_out, uint64_t *steps_total)
+{
+    if (!ix || (n && (!sa_index || !sa_value_out))) return fail(HSA_E_ARG, "bad argument");
+    if (!ix->sa_value) return fail(HSA_E_ARG, "no SA samples attached to this index (hsa_index_attach_sa)");
+    if (steps_total) *steps_total = 0;
+    if (n == 0) return HSA_OK;
+    for (size_t i = 0; i < n; ++i)
+        if (sa_index[i] > ix->ix.fwd.text_length) return fail(HSA_E_ARG, "SA index beyond textLength");
+    CU(cudaSetDevice(ix->device));
+    uint32_t *d_idx = nullptr, *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_idx, n * 4)); CU(cudaMalloc((void **)&d_out, n * 4));
+    CU(cudaMemcpyAsync(d_idx, sa_index, n * 4, cudaMemcpyHostToDevice, ix->stream));
+    int rc = sa_launch(ix, d_idx, n, d_out, ix->stream);
+    if (rc == HSA_OK) {
+        unsigned long long st = 0;
+        CU(cudaMemcpyAsync(sa_value_out, d_out, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU(cudaMemcpyAsync(&st, ix->sa_counters + 1, sizeof(st), cudaMemcpyDeviceToHost, ix->stream));
+        CU(cudaStreamSynchronize(ix->stream));
+        if (steps_total) *steps_total = st;
+    }
+    cudaFree(d_idx); cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int hsa_sa_values_device(const hsa_index_t *ix, const uint32_t *sa_index_dev, size_t n, uint32_t *sa_value_out_dev,
+                                    uint64_t *steps_total_dev, void *stream)
+{
+    if (!ix || (n && (!sa_index_dev || !sa_value_out_dev))) return fail(HSA_E_ARG, "bad argument");
+    if (!ix->sa_value) return fail(HSA_E_ARG, "no SA samples attached to this index (hsa_index_attach_sa)");
+    if (n == 0) return HSA_OK;
+    CU(cudaSetDevice(ix->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = sa_launch(ix, sa_index_dev, n, sa_value_out_dev, s);
+    if (rc) return rc;
+    if (steps_total_dev) CU(cudaMemcpyAsync(steps_total_dev, ix->sa_counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
     return HSA_OK;
 }
 

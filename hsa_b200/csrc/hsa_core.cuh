@@ -229,6 +229,40 @@ HSA_HD void occ4_dev(const DevBwt &b, uint32_t index, uint32_t occ[4])
     occ4_from_sector(cnt, w, index & 63u, occ);
 }
 
+// ---- SA index -> text position ----------------------------------------------------
+// BWTPsiMinusValue (BWT.c:1142-1165) on the device layout: the SA index of the suffix one text position to the left =
+// C[c] + occ(c, index + 1), c being the BWT symbol at `index` (BWTOccValueOnSpot, BWT.c:924-965).  The symbol and its
+// rank come out of the SAME 32-byte sector: the symbol sits at in-block offset `off`, the rank counts the block's first
+// off + 1 symbols.  index != inverseSa0 (that case is the '$' itself: BWT.c:1161-1163 returns 0).
+HSA_HD uint32_t psi_minus_dev(const DevBwt &b, uint32_t index)
+{
+    uint32_t p = index + 1;
+    p -= (p > b.inverse_sa0);                           // BWT.c:948; p in 1..n, the symbol is raw position p - 1
+    const uint32_t q = p - 1, off = q & 63u;
+    u32x4 cnt, w;
+    ld_sector(b.blocks + 2 * (size_t)(q >> 6), cnt, w);
+    const uint32_t lo = off < 32u ? w.x : w.y, hi = off < 32u ? w.z : w.w;
+    const uint32_t c = ((lo >> (off & 31u)) & 1u) | ((hi >> (off & 31u)) & 1u) << 1;
+    // the first off + 1 (1..64) symbols of the block
+    const uint32_t t = off + 1u;
+    const uint32_t m0 = t >= 32u ? 0xFFFFFFFFu : (1u << t) - 1u;
+    const uint32_t m1 = t > 32u ? (t == 64u ? 0xFFFFFFFFu : (1u << (t - 32u)) - 1u) : 0u;
+    const uint32_t fl = (c & 1u) - 1u, fh = (c >> 1) - 1u;                     // all ones where c's bit is 0
+    const uint32_t base = c == 0 ? cnt.x : c == 1 ? cnt.y : c == 2 ? cnt.z : cnt.w;
+    return b.cum[c] + base + (uint32_t)popc32((w.x ^ fl) & (w.z ^ fh) & m0) + (uint32_t)popc32((w.y ^ fl) & (w.w ^ fh) & m1);
+}
+
+// BWTSaValue, BWT.c:1195-1225: walk left until a sampled SA index; sa_value as loaded (entry 0 = -1, BWT.c:222)
+HSA_HD uint32_t sa_value_dev(const DevBwt &b, const uint32_t *sa_value, uint32_t sa_interval, uint32_t sa_index, uint32_t &steps)
+{
+    steps = 0;
+    while (sa_index % sa_interval != 0) {
+        ++steps;
+        sa_index = sa_index == b.inverse_sa0 ? 0u : psi_minus_dev(b, sa_index);
+    }
+    return ld_ro1(sa_value + sa_index / sa_interval) + steps;
+}
+
 // ---- rank on the REFERENCE layout (BWT.c:793-837, 1018-1059, 532-679) -------------------------------
 HSA_HD void count_pairs_ref(uint32_t w, uint32_t a, uint32_t b, uint32_t cnt[4])
 {

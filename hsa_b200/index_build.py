@@ -22,8 +22,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .index_io import (BWTArrays, Index2BWT, OCC_INTERVAL, OCC_INTERVAL_MAJOR, bwt_resident_words,
-                       occ_major_words, occ_minor_words)
+from .index_io import (BWTArrays, Index2BWT, OCC_INTERVAL, OCC_INTERVAL_MAJOR, SA_INTERVAL, bwt_resident_words,
+                       occ_major_words, occ_minor_words, sa_value_words)
 
 KEY_SYMS = 21                       # symbols per sort key (3 bits each -> 63 bits, non-negative int64)
 BUCKET_TARGET = 1 << 27             # suffixes per bucket the sort is sized for
@@ -78,11 +78,14 @@ def _sort_bucket(text: torch.Tensor, pos: torch.Tensor, skip: int, n: int) -> to
     return pos
 
 
-def bwt_of(text: torch.Tensor):
-    """(bwt symbols with '$' dropped: uint8[n], inverseSa0) of text + '$' ('$' smallest)."""
+def bwt_of(text: torch.Tensor, sa_interval: int = 0):
+    """(bwt symbols with '$' dropped: uint8[n], inverseSa0, SA samples or None) of text + '$' ('$' smallest).
+    sa_interval > 0: also the suffix-array samples SA[0], SA[sa_interval], ... (int64; BWTGenerateSaValue,
+    BWTConstruct.c:1310-1371), taken from the sorted buckets as they go by."""
     n = int(text.shape[0])
     dev = text.device
     m = n + 1
+    sa = torch.zeros(sa_value_words(n, sa_interval), dtype=torch.int64, device=dev) if sa_interval else None
     # symbols the buckets are keyed on
     b = 0
     while (m >> (2 * b)) > BUCKET_TARGET:
@@ -118,11 +121,18 @@ def bwt_of(text: torch.Tensor):
         if z.numel():
             inverse_sa0 = filled + int(z.item())
         out[filled:filled + k] = text[torch.clamp(order - 1, min=0)]   # entry at inverse_sa0 is a placeholder
+        if sa is not None:
+            first = (-filled) % sa_interval                 # first rank of this bucket that is a multiple of the interval
+            if first < k:
+                sa[(filled + first) // sa_interval: (filled + first) // sa_interval + (k - first + sa_interval - 1) // sa_interval] = \
+                    order[first::sa_interval]
         filled += k
         del order
     assert filled == m and inverse_sa0 >= 0
     bwt = torch.cat([out[:inverse_sa0], out[inverse_sa0 + 1:]])       # n symbols, '$' removed (BWT.c:804)
-    return bwt, inverse_sa0
+    if sa is not None:
+        sa[0] = 0xFFFFFFFF                                            # SA[0] = textLength is kept as -1 (BWT.c:222)
+    return bwt, inverse_sa0, sa
 
 
 def _pack_2bit_msb(symbols: torch.Tensor, n_words: int) -> torch.Tensor:
@@ -138,11 +148,11 @@ def _pack_2bit_msb(symbols: torch.Tensor, n_words: int) -> torch.Tensor:
     return (w[:, 0] << 24) | (w[:, 1] << 16) | (w[:, 2] << 8) | w[:, 3]
 
 
-def build_bwt(text: torch.Tensor) -> dict:
+def build_bwt(text: torch.Tensor, sa_interval: int = 0) -> dict:
     """One direction.  Returns torch tensors (int64 holding uint32 values) + scalars."""
     n = int(text.shape[0])
     dev = text.device
-    bwt, inverse_sa0 = bwt_of(text)
+    bwt, inverse_sa0, sa = bwt_of(text, sa_interval)
     counts = torch.bincount(bwt, minlength=4)[:4].to(torch.int64) if n < (1 << 30) else \
         torch.stack([(bwt == c).sum() for c in range(4)]).to(torch.int64)
     cum = torch.zeros(5, dtype=torch.int64, device=dev)
@@ -182,25 +192,29 @@ def build_bwt(text: torch.Tensor) -> dict:
     occ_major = torch.zeros(n_major_words, dtype=torch.int64, device=dev)
     maj = occ_abs[::per_major].reshape(-1)
     occ_major[: maj.shape[0]] = maj
-    return dict(text_length=n, inverse_sa0=inverse_sa0, cum=cum, code=code, occ_value=occ_value, occ_major=occ_major)
+    return dict(text_length=n, inverse_sa0=inverse_sa0, cum=cum, code=code, occ_value=occ_value, occ_major=occ_major,
+                sa=sa, sa_interval=sa_interval)
 
 
 def _to_arrays(d: dict) -> BWTArrays:
     u32 = lambda t: t.to("cpu").numpy().astype(np.uint32)   # noqa: E731
     arr = BWTArrays(d["text_length"], d["inverse_sa0"], u32(d["cum"]), u32(d["code"]), u32(d["occ_value"]),
                     u32(d["occ_major"]))
+    if d.get("sa") is not None:
+        arr.sa_value, arr.sa_interval = u32(d["sa"]), int(d["sa_interval"])
     arr.check()
     return arr
 
 
-def build_index(genome_codes, device: str | torch.device | None = None) -> Index2BWT:
-    """Build both BWTs of a genome given as base codes 0..3 (numpy uint8 or torch tensor)."""
+def build_index(genome_codes, device: str | torch.device | None = None, sa_interval: int = SA_INTERVAL) -> Index2BWT:
+    """Build both BWTs of a genome given as base codes 0..3 (numpy uint8 or torch tensor), and the forward text's
+    suffix-array samples every `sa_interval` SA indices (0 = none)."""
     if device is None:
         device = "cuda" if torch.cuda.is_available() else "cpu"
     text = torch.as_tensor(np.ascontiguousarray(genome_codes) if isinstance(genome_codes, np.ndarray) else genome_codes)
     text = text.to(device=device, dtype=torch.uint8)
     if int(text.max().item()) > 3:
         raise ValueError("genome must contain only A/C/G/T codes 0..3")
-    fwd = _to_arrays(build_bwt(text))
+    fwd = _to_arrays(build_bwt(text, sa_interval))
     rev = _to_arrays(build_bwt(torch.flip(text, dims=[0])))
     return Index2BWT(fwd, rev)

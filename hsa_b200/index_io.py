@@ -4,6 +4,9 @@ File formats follow the reference loader BWTLoad (BWT.c:107-223):
   <prefix>.index.bwt      : inverseSa0, cumulativeFreq[1..4], then ceil(n/16) words of 2-bit codes
   <prefix>.index.fmv      : inverseSa0, cumulativeFreq[1..4], occValue (minor, 16-bit pairs), occValueMajor
   <prefix>.index.rev.bwt / .rev.fmv : the same for the BWT of the reversed text
+  <prefix>.index.sa       : inverseSa0, cumulativeFreq[1..4], saInterval, then (n + saInterval) / saInterval suffix-array
+                            samples SA[0], SA[saInterval], ... of the forward text (BWTConstruct.c:1373-1392; the loader
+                            overwrites entry 0 with -1, BWT.c:218-222)
 Sizes follow BWTResidentSizeInWord / BWTOccValueMinorSizeInWord / BWTOccValueMajorSizeInWord
 (BWT.c:1079-1116); the resident bwtCode is padded to a multiple of 256 symbols plus 8 words (BWT.c:176).
 """
@@ -15,6 +18,12 @@ import numpy as np
 OCC_INTERVAL = 256
 OCC_INTERVAL_MAJOR = 65536
 CHAR_PER_WORD = 16
+SA_INTERVAL = 8                     # the reference builder's compiled default (2BWT-Builder.c:97)
+
+
+def sa_value_words(n: int, interval: int = SA_INTERVAL) -> int:
+    """saValueSizeInWord, BWT.c:219."""
+    return (n + interval) // interval
 
 
 def bwt_resident_words(n: int) -> int:
@@ -49,6 +58,8 @@ class BWTArrays:
     bwt_code: np.ndarray          # uint32[bwt_resident_words]
     occ_value: np.ndarray         # uint32[occ_minor_words]
     occ_value_major: np.ndarray   # uint32[occ_major_words]
+    sa_value: np.ndarray | None = None   # uint32[sa_value_words]: SA samples as LOADED (entry 0 = 0xFFFFFFFF); forward only
+    sa_interval: int = 0
 
     def check(self) -> None:
         n = self.text_length
@@ -57,6 +68,9 @@ class BWTArrays:
         assert self.bwt_code.dtype == np.uint32 and self.bwt_code.shape[0] >= bwt_file_words(n)
         assert self.occ_value.shape[0] == occ_minor_words(n)
         assert self.occ_value_major.shape[0] == occ_major_words(n)
+        if self.sa_value is not None:
+            assert self.sa_interval > 0 and self.sa_value.dtype == np.uint32
+            assert self.sa_value.shape[0] == sa_value_words(n, self.sa_interval)
 
 
 @dataclasses.dataclass
@@ -95,10 +109,37 @@ def load_bwt(bwt_path: str, fmv_path: str) -> BWTArrays:
     return arr
 
 
-def load_index(prefix: str) -> Index2BWT:
-    """Load `<prefix>.index.{bwt,fmv,rev.bwt,rev.fmv}` as written by `HSA index <prefix> <fasta>`."""
+def load_sa(arr: BWTArrays, sa_path: str) -> None:
+    """Attach `<prefix>.index.sa` to the forward BWT's arrays the way BWTLoad does (BWT.c:205-223)."""
+    with open(sa_path, "rb") as f:
+        hdr = np.fromfile(f, dtype=np.uint32, count=6)
+        if int(hdr[0]) != arr.inverse_sa0 or not np.array_equal(hdr[1:5], arr.cumulative_freq[1:]):
+            raise ValueError(f"{sa_path}: header does not match the BWT")
+        interval = int(hdr[5])
+        sa = np.fromfile(f, dtype=np.uint32, count=sa_value_words(arr.text_length, interval))
+        if sa.shape[0] != sa_value_words(arr.text_length, interval):
+            raise ValueError(f"{sa_path}: truncated SA samples")
+    sa[0] = 0xFFFFFFFF                                   # BWT.c:222
+    arr.sa_value, arr.sa_interval = sa, interval
+
+
+def save_sa(arr: BWTArrays, sa_path: str) -> None:
+    """BWTSaveSaValue, BWTConstruct.c:1373-1392 (entry 0 is written as textLength)."""
+    hdr = np.concatenate([np.asarray([arr.inverse_sa0], dtype=np.uint32), arr.cumulative_freq[1:],
+                          np.asarray([arr.sa_interval, arr.text_length], dtype=np.uint32)])
+    with open(sa_path, "wb") as f:
+        hdr.tofile(f)
+        arr.sa_value[1:].tofile(f)
+
+
+def load_index(prefix: str, with_sa: bool = True) -> Index2BWT:
+    """Load `<prefix>.index.{bwt,fmv,rev.bwt,rev.fmv}` (and `.sa` if present) as written by `HSA index <prefix> <fasta>`."""
+    import os
     p = prefix + ".index"
-    return Index2BWT(load_bwt(p + ".bwt", p + ".fmv"), load_bwt(p + ".rev.bwt", p + ".rev.fmv"))
+    ix = Index2BWT(load_bwt(p + ".bwt", p + ".fmv"), load_bwt(p + ".rev.bwt", p + ".rev.fmv"))
+    if with_sa and os.path.exists(p + ".sa"):
+        load_sa(ix.fwd, p + ".sa")
+    return ix
 
 
 def save_bwt(arr: BWTArrays, bwt_path: str, fmv_path: str) -> None:

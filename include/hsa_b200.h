@@ -202,6 +202,21 @@ int  hsa_workspace_launch_timing(hsa_workspace_t *ws, int enable);
 int  hsa_workspace_launch_times(hsa_workspace_t *ws, char *names, size_t names_cap, float *ms, size_t ms_cap,
                                 size_t *n_out, uint64_t *fast_search_lookups);
 
+/* ---- SA index -> text position ---------------------------------------------------
+ * Replaces BWTSaValue (BWT.c:1195-1225), the kernel of BWTRetrievePositionFromSAIndex (2BWT-Interface.c:329-362) as
+ * called by bwa_cal_pac_pos (bwtse.c:350-369) and bwt_aln_corelate_check (bwtgap.c:669-742): walk BWTPsiMinusValue
+ * (BWT.c:1142-1165) from the SA index to a sampled one and add the steps walked.
+ * attach: `sa_value` = the reference's loaded BWT::saValue of the FORWARD bwt ((textLength + saInterval) / saInterval
+ * words, BWT.c:219; entry 0 is forced to -1 as BWT.c:222 does), copied to the device once.
+ * hsa_sa_values: host buffers, n SA indices (each <= textLength, else HSA_E_ARG) -> n values, bit-identical to
+ * BWTSaValue's, including its SA[0] = -1 convention; *steps_total (may be NULL) = PsiMinus steps walked in total.
+ * hsa_sa_values_device: the same with device buffers on `stream` (cudaStream_t as void*), nothing synchronised;
+ * indices are not range-checked. */
+int  hsa_index_attach_sa(hsa_index_t *idx, const uint32_t *sa_value, size_t n_words, uint32_t sa_interval);
+int  hsa_sa_values(const hsa_index_t *idx, const uint32_t *sa_index, size_t n, uint32_t *sa_value_out, uint64_t *steps_total);
+int  hsa_sa_values_device(const hsa_index_t *idx, const uint32_t *sa_index_dev, size_t n, uint32_t *sa_value_out_dev,
+                          uint64_t *steps_total_dev, void *stream);
+
 /* ---- roofline probe: random 32-byte-sector loads over `footprint_bytes` ----
  * Reports achieved GB/s (sectors * 32 B / time) at full occupancy with `loads_per_thread` dependent
  * chains; used only by bench.py to establish the random-access denominator on this GPU. */

@@ -92,6 +92,33 @@ uint32_t hsao_occ1(const hsa_bwt_view_t *bwt, uint32_t index, uint32_t c)
     return v - cnt[c];
 }
 
+/* ------------------------------------------------------------------ SA index -> position (BWT.c) */
+
+/* BWTPsiMinusValue, BWT.c:1142-1165: the SA index of the suffix one position to the left.  BWTOccValueOnSpot(index + 1)
+ * (BWT.c:924-965) returns the BWT symbol in front of `index + 1` and its occ count up to and including itself. */
+uint32_t hsao_psi_minus(const hsa_bwt_view_t *bwt, uint32_t index)
+{
+    uint32_t p, c;
+    if (index == bwt->inverseSa0) return 0;                  /* BWT.c:1161-1163 */
+    p = index + 1;
+    p -= (p > bwt->inverseSa0);                              /* BWT.c:948 */
+    c = (bwt->bwtCode[(p - 1) / 16] >> (30 - 2 * ((p - 1) % 16))) & 3u;     /* BWT.c:954 */
+    return bwt->cumulativeFreq[c] + hsao_occ1(bwt, index + 1, c);
+}
+
+/* BWTSaValue, BWT.c:1195-1225 */
+uint32_t hsao_sa_value(const hsa_bwt_view_t *bwt, const uint32_t *sa_value, uint32_t sa_interval, uint32_t sa_index,
+                       uint32_t *steps)
+{
+    uint32_t skipped = 0;
+    while (sa_index % sa_interval != 0) {
+        ++skipped;
+        sa_index = hsao_psi_minus(bwt, sa_index);
+    }
+    if (steps) *steps = skipped;
+    return sa_value[sa_index / sa_interval] + skipped;       /* SA[0] is stored as -1 (BWT.c:222, :1221-1222) */
+}
+
 /* ------------------------------------------------------------------ SA-range stepping (2BWT-Interface.c) */
 
 /* BWTSARangeForeward, 2BWT-Interface.c:121-132: forward extension = backward step on rev_bwt with the

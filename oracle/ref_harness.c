@@ -139,7 +139,7 @@ static Idx2BWT *load_index(const char *prefix)
     char *str = (char*)calloc(strlen(prefix) + 32, 1);
     Idx2BWT *bi;
     FILE *t;
-    strcpy(str, prefix); strcat(str, ".index.sa");
+    strcpy(str, prefix); strcat(str, ".index.pac");  /* a full index (packed DNA, annotation, SA) as `index` writes it */
     t = fopen(str, "rb");
     strcpy(str, prefix); strcat(str, ".index");      /* bwtaln.c:463-469 */
     if (t) {
@@ -148,14 +148,20 @@ static Idx2BWT *load_index(const char *prefix)
     } else {
         /* search arrays only (.bwt/.fmv/.rev.bwt/.rev.fmv), e.g. an index written by the product's own
          * builder: the same BWTLoad calls BWTLoad2BWT makes (2BWT-Interface.c:51-52), no SA / packed DNA.
-         * Enough for occ / width / percall / whole / seeds, which never touch hsp or the SA. */
+         * Enough for occ / width / percall / whole / seeds / sa, which never touch hsp. */
         char a[1100], b[1100];
         MMPool *mmPool;
         bi = (Idx2BWT*)calloc(1, sizeof(Idx2BWT));
         MMMasterInitialize(3, 0, FALSE, NULL);
         mmPool = MMPoolCreate(2097152);
         snprintf(a, sizeof(a), "%s.bwt", str); snprintf(b, sizeof(b), "%s.fmv", str);
-        bi->bwt = BWTLoad(mmPool, a, b, NULL, NULL, NULL, NULL);
+        {   /* the SA samples too when they are there (mode sa): the same BWTLoad argument BWTLoad2BWT passes */
+            char c[1100]; FILE *ts;
+            snprintf(c, sizeof(c), "%s.sa", str);
+            ts = fopen(c, "rb");
+            if (ts) fclose(ts);
+            bi->bwt = BWTLoad(mmPool, a, b, ts ? c : NULL, NULL, NULL, NULL);
+        }
         snprintf(a, sizeof(a), "%s.rev.bwt", str); snprintf(b, sizeof(b), "%s.rev.fmv", str);
         bi->rev_bwt = BWTLoad(mmPool, a, b, NULL, NULL, NULL, NULL);
         bi->hsp = NULL; bi->mmPool = mmPool;
@@ -533,6 +539,39 @@ static int mode_dumpindex(int argc, char **argv)
     return 0;
 }
 
+/* sa <prefix> <idx.bin> <out.bin>: BWTSaValue (BWT.c:1195-1225) of every listed SA index on the forward BWT; needs the
+ * full index (<prefix>.index.sa) as written by `index`.  Output: n, then per index {SA value, PsiMinus steps walked}. */
+static int mode_sa(int argc, char **argv)
+{
+    Idx2BWT *bi; FILE *fi, *fo; uint32_t n, i, *idx; double secs = 0;
+    if (argc < 5) die("usage: sa <prefix> <idx.bin> <out.bin>");
+    bi = load_index(argv[2]);
+    if (!bi->bwt->saValue) die("index has no SA samples");
+    fi = fopen(argv[3], "rb"); if (!fi) die("cannot open idx");
+    if (fread(&n, 4, 1, fi) != 1) die("short idx");
+    idx = (uint32_t*)malloc(4 * (size_t)n);
+    if (fread(idx, 4, n, fi) != n) die("short idx");
+    fclose(fi);
+    {   /* timed pass: BWTSaValue alone, as bwa_cal_pac_pos / bwt_aln_corelate_check call it */
+        double t0 = now_s(); uint32_t acc = 0;
+        for (i = 0; i < n; ++i) acc ^= BWTSaValue(bi->bwt, idx[i]);
+        secs = now_s() - t0;
+        if (acc == 0x12345678u) fprintf(stderr, "\n");
+    }
+    fo = fopen(argv[4], "wb");
+    fwrite(&n, 4, 1, fo);
+    for (i = 0; i < n; ++i) {
+        uint32_t o[2], s = idx[i];
+        o[0] = BWTSaValue(bi->bwt, idx[i]);
+        o[1] = 0;
+        while (s % bi->bwt->saInterval != 0) { s = BWTPsiMinusValue(bi->bwt, s); ++o[1]; }
+        fwrite(o, 4, 2, fo);
+    }
+    fclose(fo);
+    printf("{\"mode\":\"sa\",\"n\":%u,\"textLength\":%u,\"saInterval\":%u,\"secs\":%.6f}\n", n, bi->bwt->textLength, bi->bwt->saInterval, secs);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc < 2) die("usage: hsa_ref <index|occ|width|percall|seeds|driver|whole|dumpindex|maxdiff> ...");
@@ -542,6 +581,7 @@ int main(int argc, char **argv)
         return bwa_index_main(argc - 1, argv + 1);
     }
     if (strcmp(argv[1], "occ") == 0) return mode_occ(argc, argv);
+    if (strcmp(argv[1], "sa") == 0) return mode_sa(argc, argv);
     if (strcmp(argv[1], "width") == 0) return mode_width(argc, argv);
     if (strcmp(argv[1], "percall") == 0) return mode_percall(argc, argv);
     if (strcmp(argv[1], "seeds") == 0) return mode_seeds(argc, argv);

@@ -149,6 +149,18 @@ void emu_occ(void *p, int which, int layout, const hsa_bwt_view_t *refview, cons
     }
 }
 
+// BWTSaValue through the device code (hsa_core.cuh: sa_value_dev / psi_minus_dev) on the re-packed layout
+void emu_sa_values(void *p, const uint32_t *sa_value, uint32_t sa_interval, const uint32_t *idx, size_t n, uint32_t *out,
+                   uint32_t *steps_out)
+{
+    EmuIndex *e = (EmuIndex *)p;
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t st = 0;
+        out[i] = sa_value_dev(e->ix.fwd, sa_value, sa_interval, idx[i], st);
+        steps_out[i] = st;
+    }
+}
+
 static void to_devopt(const hsa_gap_opt_t &o, DevOpt &d)
 {
     memset(&d, 0, sizeof(d));

@@ -46,6 +46,7 @@ def lib():
         L.emu_index_new.argtypes = [C.POINTER(ol.BwtView), C.POINTER(ol.BwtView)]
         L.emu_index_free.argtypes = [C.c_void_p]
         L.emu_occ.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ol.BwtView), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.emu_sa_values.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.emu_run.restype = C.c_long
         L.emu_set_rerun.argtypes = [C.c_uint32]
         L.emu_set_coop.argtypes = [C.c_int, C.c_uint32]
@@ -112,6 +113,15 @@ class Emu:
         lib().emu_occ(self.h, which, layout, C.byref(self.vf if which == 0 else self.vr), idx.ctypes.data,
                       idx.shape[0], out.ctypes.data)
         return out
+
+    def sa_values(self, idx: np.ndarray):
+        b = self.index.fwd
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        out = np.zeros(idx.shape[0], dtype=np.uint32)
+        steps = np.zeros(idx.shape[0], dtype=np.uint32)
+        lib().emu_sa_values(self.h, b.sa_value.ctypes.data, b.sa_interval, idx.ctypes.data, idx.shape[0], out.ctypes.data,
+                            steps.ctypes.data)
+        return out, steps
 
     def run(self, kind, rs, opts, tasks=None, len2opt=None, filter_max_n=0, arena_cap=1022, hit_cap=32,
             n_items=None, want_width=False, rerun_cap=0, coop=False, step_budget=0):

@@ -65,6 +65,8 @@ def index_digest(ix) -> dict:
                          cumulative_freq=[int(x) for x in b.cumulative_freq],
                          bwt_code=digest(b.bwt_code[:nfile]), occ_value=digest(b.occ_value),
                          occ_value_major=digest(b.occ_value_major))
+        if b.sa_value is not None:
+            out[name].update(sa_interval=int(b.sa_interval), sa_value=digest(b.sa_value))
     return out
 
 
@@ -88,6 +90,15 @@ def main():
         ol.run_ref(["occ", prefix, os.path.join(td, "idx.bin"), os.path.join(td, "occ.out")])
         occ = np.fromfile(os.path.join(td, "occ.out"), dtype=np.uint32)[1:].reshape(-1, 16)
         arrays = dict(occ_idx=idx, occ=occ)
+        # SA index -> text position (BWTSaValue) on the forward BWT: every residue class, the ends, inverseSa0
+        sidx = rng.integers(0, ix.fwd.text_length + 1, size=6000).astype(np.uint32)
+        sidx[:8] = [0, 1, 7, 8, ix.fwd.text_length, ix.fwd.text_length - 1, ix.fwd.inverse_sa0, ix.fwd.inverse_sa0 + 1]
+        with open(os.path.join(td, "sidx.bin"), "wb") as f:
+            np.asarray([sidx.shape[0]], dtype=np.uint32).tofile(f)
+            sidx.tofile(f)
+        ol.run_ref(["sa", prefix, os.path.join(td, "sidx.bin"), os.path.join(td, "sa.out")])
+        sa = np.fromfile(os.path.join(td, "sa.out"), dtype=np.uint32)[1:].reshape(-1, 2)
+        arrays.update(sa_idx=sidx, sa_val=sa[:, 0].copy(), sa_steps=sa[:, 1].copy())
         for name, (spec, okw) in CASES.items():
             rs = make_reads(genome, spec)
             rp = os.path.join(td, name + ".reads")

@@ -65,6 +65,8 @@ def lib():
         L.hsao_occ4.argtypes = [C.POINTER(BwtView), C.c_uint32, C.POINTER(C.c_uint32)]
         L.hsao_occ1.argtypes = [C.POINTER(BwtView), C.c_uint32, C.c_uint32]
         L.hsao_occ1.restype = C.c_uint32
+        L.hsao_sa_value.argtypes = [C.POINTER(BwtView), C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.hsao_sa_value.restype = C.c_uint32
         L.hsao_cal_maxdiff.argtypes = [C.c_int, C.c_double, C.c_double]
         L.hsao_cal_maxdiff.restype = C.c_int
         L.hsao_gap_opt_default.argtypes = [C.POINTER(GapOpt)]
@@ -113,6 +115,18 @@ class Oracle:
             for c in range(4):
                 o1[i, c] = L.hsao_occ1(C.byref(v), x, c)
         return o4, o1
+
+    def sa_values(self, indices: np.ndarray):
+        """(SA values, PsiMinus steps walked) of SA indices on the forward BWT (BWTSaValue)."""
+        L = lib()
+        b = self.index.fwd
+        out = np.zeros(indices.shape[0], dtype=np.uint32)
+        steps = np.zeros(indices.shape[0], dtype=np.uint32)
+        st = C.c_uint32(0)
+        for i, x in enumerate(indices.tolist()):
+            out[i] = L.hsao_sa_value(C.byref(self.ix.fwd), b.sa_value.ctypes.data, b.sa_interval, x, C.byref(st))
+            steps[i] = st.value
+        return out, steps
 
     def cal_width(self, seq: np.ndarray, type_: int = 1):
         L = lib()

@@ -20,6 +20,22 @@ def test_rank_both_layouts(golden, emu):
         assert np.array_equal(emu.occ(which, 1, idx), occ[:, cols])     # re-packed device layout
 
 
+def test_sa_value_device_code(golden, emu):
+    """psi_minus_dev / sa_value_dev (one sector per PsiMinus step on the re-packed layout) against BWTSaValue."""
+    val, steps = emu.sa_values(golden.arr["sa_idx"])
+    assert np.array_equal(val, golden.arr["sa_val"]) and np.array_equal(steps, golden.arr["sa_steps"])
+
+
+def test_sa_value_is_the_suffix_position(golden, emu):
+    """Independent of the reference: consecutive SA indices name lexicographically increasing suffixes of the text."""
+    text = golden.genome
+    n = text.shape[0]
+    idx = np.arange(5000, 5064, dtype=np.uint32)
+    pos, _ = emu.sa_values(idx)
+    sufs = [bytes(text[int(p): int(p) + 64]) for p in pos]
+    assert sufs == sorted(sufs) and len(set(int(p) for p in pos)) == 64 and int(pos.max()) < n
+
+
 def test_width(golden, emu):
     case = "ragged_nonstop"
     rs = golden.reads(case).subset(0, 64)

@@ -66,6 +66,56 @@ def test_rank_exhaustive_small(golden_index, dev_index):
         assert np.array_equal(dev_index.occ(which, idx, layout=0), exp)
 
 
+def test_sa_values_golden(golden, dev_index):
+    """hsa_sa_values == the reference's BWTSaValue on the golden SA indices (incl. 0, textLength, inverseSa0)."""
+    idx = golden.arr["sa_idx"]
+    assert np.array_equal(dev_index.sa_values(idx), golden.arr["sa_val"])
+    assert dev_index.last_sa_steps == int(golden.arr["sa_steps"].astype(np.int64).sum())
+
+
+def test_sa_values_every_index_is_a_permutation(golden_index, dev_index):
+    """All n + 1 SA indices: values == the oracle's, and together they are every text position exactly once
+    (SA[0], the '$' suffix, reads -1 as the reference keeps it)."""
+    n = golden_index.fwd.text_length
+    idx = np.arange(0, n + 1, dtype=np.uint32)
+    got = dev_index.sa_values(idx)
+    exp, steps = ol.Oracle(golden_index).sa_values(idx)
+    assert np.array_equal(got, exp) and dev_index.last_sa_steps == int(steps.astype(np.int64).sum())
+    assert got[0] == 0xFFFFFFFF and np.array_equal(np.sort(got[1:]), np.arange(n, dtype=np.uint32))
+
+
+def test_sa_values_bad_and_empty(golden_index, dev_index):
+    assert dev_index.sa_values(np.zeros(0, dtype=np.uint32)).shape == (0,)
+    with pytest.raises(api.HsaError):
+        dev_index.sa_values(np.asarray([golden_index.fwd.text_length + 1], dtype=np.uint32))
+
+
+def test_hit_intervals_to_positions(golden, golden_index, dev_index):
+    """The consumer's view (bwa_cal_pac_pos bwtse.c:350-369, bwt_aln_corelate_check bwtgap.c:669-742): every SA index of
+    the hit intervals of a whole-read batch -> text position; the read (strand-resolved) really occurs there within
+    its hit's edit budget for exact hits."""
+    case = "exact_only"
+    rs = golden.reads(case)
+    opt = to_api_opt(ol.default_opt(**golden.opt_kwargs(case)))
+    res = dev_index.whole_reads(rs.codes, rs.offsets[:-1], rs.lens, opt)
+    text = golden.genome
+    checked = 0
+    for r in range(rs.n):
+        if res.n_aln[r] == 0:
+            continue
+        a = res.aln[int(res.aln_off[r])]
+        k, l, strand = int(a[1]), int(a[2]), int(a[5]) >> 30
+        pos = dev_index.sa_values(np.arange(k, l + 1, dtype=np.uint32))
+        read = rs.read(r)
+        seq = (3 - read[::-1]) if strand else read
+        for p in pos.tolist():
+            assert np.array_equal(text[p: p + seq.shape[0]], seq)
+            checked += 1
+        if checked > 300:
+            break
+    assert checked > 100
+
+
 def test_width(golden, dev_index):
     case = "ragged_nonstop"
     rs = golden.reads(case).subset(0, 64)

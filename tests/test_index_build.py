@@ -24,7 +24,10 @@ def test_file_roundtrip(golden_index, tmp_path):
     p = str(tmp_path / "g.index")
     index_io.save_bwt(golden_index.fwd, p + ".bwt", p + ".fmv")
     index_io.save_bwt(golden_index.rev, p + ".rev.bwt", p + ".rev.fmv")
+    index_io.save_sa(golden_index.fwd, p + ".sa")
     back = index_io.load_index(str(tmp_path / "g"))
+    assert back.fwd.sa_interval == golden_index.fwd.sa_interval == 8
+    assert np.array_equal(back.fwd.sa_value, golden_index.fwd.sa_value) and back.rev.sa_value is None
     for name in ("fwd", "rev"):
         a, b = getattr(golden_index, name), getattr(back, name)
         assert a.inverse_sa0 == b.inverse_sa0 and np.array_equal(a.cumulative_freq, b.cumulative_freq)

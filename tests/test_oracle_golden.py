@@ -23,6 +23,19 @@ def test_rank_matches_reference(golden, oracle):
     assert np.array_equal(o1f, occ[:, 8:12]) and np.array_equal(o1r, occ[:, 12:16])
 
 
+def test_sa_value_matches_reference(golden, oracle):
+    """BWTSaValue (BWT.c:1195-1225): SA index -> text position, with the number of PsiMinus steps walked."""
+    idx = golden.arr["sa_idx"]
+    val, steps = oracle.sa_values(idx)
+    assert np.array_equal(val, golden.arr["sa_val"]) and np.array_equal(steps, golden.arr["sa_steps"])
+    # what the values mean: SA[i] is the start of the i-th smallest suffix; check a few against the text itself
+    n = golden.genome.shape[0]
+    assert val[0] == 0xFFFFFFFF                        # SA[0] (the '$' suffix) is kept as -1, BWT.c:222
+    assert val[6] == 0 and idx[6] == golden.meta["index"]["fwd"]["inverse_sa0"]   # the whole text sits at inverseSa0
+    ok = idx != 0
+    assert int(val[ok].max()) < n
+
+
 @pytest.mark.parametrize("case", ["cfg1_75bp_n2o1", "cfg2_100bp_default", "ragged_nonstop"])
 def test_width_matches_reference(golden, oracle, case):
     rs = golden.reads(case)
