@@ -278,6 +278,31 @@ __global__ void probe_kernel(const uint4 *buf, uint64_t n_sectors, int iters, un
     if (acc == 0xDEADBEEFu) atomicAdd(sink, 1ull);
 }
 
+// Second probe variant: one 256-bit load per sector (as the kernels issue them), sector picked by multiply-shift
+// instead of a 64-bit modulo, and UNROLL loads in flight per thread whose addresses do not depend on each other's data
+// (the upper bound a kernel with more memory-level parallelism could reach).
+template <int UNROLL>
+__global__ void probe_kernel_mlp(const uint4 *buf, uint64_t n_sectors, int iters, unsigned long long *sink)
+{
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t s = tid * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t v[UNROLL][8];
+#pragma unroll
+        for (int c = 0; c < UNROLL; ++c) {
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            const uint64_t sec = __umul64hi(s, n_sectors);
+            asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[c][0]), "=r"(v[c][1]), "=r"(v[c][2]), "=r"(v[c][3]), "=r"(v[c][4]), "=r"(v[c][5]), "=r"(v[c][6]), "=r"(v[c][7])
+                         : "l"(buf + 2 * sec));
+        }
+#pragma unroll
+        for (int c = 0; c < UNROLL; ++c) acc += v[c][0] ^ v[c][7];
+    }
+    if (acc == 0xDEADBEEFu) atomicAdd(sink, 1ull);
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -1592,6 +1617,25 @@ extern "C" int hsa_random_sector_probe(int device, size_t footprint_bytes, int i
         CU(cudaEventElapsedTime(&ms, e0, e1));
         double bytes = (double)grid * block * CH * (double)iters * 32.0;
         best = std::max(best, bytes / (ms * 1e-3) / 1e9);
+    }
+    // independent 256-bit loads, four / eight in flight per thread
+    for (int variant = 0; variant < 2; ++variant) {
+        const int UN = variant == 0 ? 4 : 8;
+        const void *fn = variant == 0 ? (const void *)probe_kernel_mlp<4> : (const void *)probe_kernel_mlp<8>;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, block, 0));
+        grid = sms * occ;
+        const int it2 = iters;
+        void *args[] = {(void *)&buf, (void *)&n_sectors, (void *)&it2, (void *)&sink};
+        for (int rep = 0; rep < 3; ++rep) {
+            CU(cudaEventRecord(e0));
+            CU(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, 0, nullptr));
+            CU(cudaEventRecord(e1));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            double bytes = (double)grid * block * UN * (double)iters * 32.0;
+            best = std::max(best, bytes / (ms * 1e-3) / 1e9);
+        }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(buf); cudaFree(sink);

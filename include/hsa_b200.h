@@ -218,8 +218,10 @@ int  hsa_sa_values_device(const hsa_index_t *idx, const uint32_t *sa_index_dev, 
                           uint64_t *steps_total_dev, void *stream);
 
 /* ---- roofline probe: random 32-byte-sector loads over `footprint_bytes` ----
- * Reports achieved GB/s (sectors * 32 B / time) at full occupancy with `loads_per_thread` dependent
- * chains; used only by bench.py to establish the random-access denominator on this GPU. */
+ * Reports the best achieved GB/s (sectors * 32 B / time) at full occupancy of two variants: four dependent chains per
+ * thread with two 16-byte loads per sector, and four independent 256-bit loads in flight per thread (the kernels' own
+ * load shape, multiply-shift sector choice).  Used only by bench.py / tools/bench_sa.py to establish the random-access
+ * denominator on this GPU. */
 int  hsa_random_sector_probe(int device, size_t footprint_bytes, int iters, double *gbs_out);
 
 #ifdef __cplusplus
