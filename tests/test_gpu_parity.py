@@ -293,3 +293,60 @@ def test_medium_batch_vs_oracle_and_properties():
         assert res.occ_lookups == res2.occ_lookups
     finally:
         ix.close()
+
+
+def test_million_reads_properties_against_the_text():
+    """BASELINE-scale batch shape (1 M x 100 bp, defaults) on a 4.6 Mb genome, checked without any reference run:
+      * splitting the batch in two and shuffling the reads leave every read's hits unchanged (searches are independent),
+      * EVERY gap-free hit interval, resolved to text positions through hsa_sa_values, holds the strand-resolved read
+        with exactly n_mm mismatches, and every position of the text where the read's origin lies is inside the
+        score-0 interval for error-free reads,
+      * a gapped hit's interval is non-empty and its rev interval has the same width."""
+    from hsa_b200 import synth_torch
+    import torch
+    dev = torch.device("cuda", 0)
+    G, n, L = 4_600_003, 1_000_000, 100
+    genome_t = synth_torch.make_genome(G, 11, dev)
+    index = index_build.build_index(genome_t, device=dev)
+    ix = api.Index.upload(index, 0)
+    try:
+        text = genome_t.cpu().numpy()
+        reads = synth_torch.simulate_reads(genome_t, n, L, 2024).cpu().numpy()
+        off = (np.arange(n, dtype=np.uint64) * L)
+        lens = np.full(n, L, dtype=np.uint32)
+        opt = api.gap_init_opt()
+        res = ix.whole_reads(reads.reshape(-1), off, lens, opt)
+        assert int((res.n_aln > 0).sum()) > 0.98 * n
+        # split + shuffle invariance
+        perm = np.random.default_rng(3).permutation(n)
+        res_p = ix.whole_reads(reads[perm].reshape(-1), off, lens, opt)
+        assert np.array_equal(res_p.n_aln, res.n_aln[perm])
+        half = n // 2
+        res_a = ix.whole_reads(reads[:half].reshape(-1), off[:half], lens[:half], opt)
+        assert np.array_equal(res_a.n_aln, res.n_aln[:half]) and np.array_equal(res_a.ordered(), res.ordered()[: int(res.n_aln[:half].sum())])
+        # hits of the shuffled run, per read, equal the original read's hits
+        first = np.concatenate([[0], np.cumsum(res.n_aln.astype(np.int64))[:-1]])
+        ordered, ordered_p = res.ordered(), res_p.ordered()
+        first_p = np.concatenate([[0], np.cumsum(res_p.n_aln.astype(np.int64))[:-1]])
+        one = np.nonzero(res.n_aln == 1)[0]
+        inv = np.empty(n, dtype=np.int64); inv[perm] = np.arange(n)
+        assert np.array_equal(ordered[first[one]], ordered_p[first_p[inv[one]]])
+        # every gap-free hit against the text
+        f = api.aln_fields(ordered)
+        owner = np.repeat(np.arange(n), res.n_aln)
+        width = (f["l"].astype(np.int64) - f["k"].astype(np.int64) + 1)
+        assert (width >= 1).all() and ((f["rev_l"].astype(np.int64) - f["rev_k"]) == width - 1).all()
+        sel = np.nonzero((f["n_gapo"] == 0) & (width <= 4))[0]
+        assert sel.shape[0] > 0.9 * n
+        sa_idx = np.concatenate([f["k"][sel] + j for j in range(4)])          # up to four positions per interval
+        keep = np.concatenate([width[sel] > j for j in range(4)])
+        hit_of = np.concatenate([sel] * 4)[keep]
+        pos = ix.sa_values(sa_idx[keep].astype(np.uint32)).astype(np.int64)
+        assert (pos + L <= G).all()
+        rd = reads[owner[hit_of]]
+        rc = np.where(rd[:, ::-1] < 4, 3 - rd[:, ::-1], rd[:, ::-1])
+        seq = np.where((f["strand"][hit_of] == 1)[:, None], rc, rd)
+        win = text[pos[:, None] + np.arange(L)[None, :]]
+        assert np.array_equal((win != seq).sum(axis=1), f["n_mm"][hit_of].astype(np.int64))
+    finally:
+        ix.close()
