@@ -108,6 +108,8 @@ def lib():
     L.hsa_whole_reads_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(GapOpt),
                                          C.c_int, C.POINTER(C.c_void_p)]
     L.hsa_job_wait.argtypes = [C.c_void_p, C.POINTER(_Result)]
+    L.hsa_splice_seeds_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(GapOpt),
+                                          C.POINTER(C.c_void_p)]
     L.hsa_splice_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(GapOpt),
                                    C.POINTER(_Result)]
     L.hsa_result_free.argtypes = [C.POINTER(_Result)]
@@ -320,6 +322,15 @@ class Index:
         cp, op, lp, n = _ptr(codes, np.uint8), _ptr(off, np.uint64), _ptr(lens, np.uint32), _len(lens)
         h = C.c_void_p()
         _check(lib().hsa_whole_reads_submit(self._h, cp[0], op[0], lp[0], n, C.byref(opt), keep_gape, C.byref(h)))
+        res = self._job_res[self._job_seq % len(self._job_res)]
+        self._job_seq += 1
+        return Job(h, res, (cp, op, lp))
+
+    def splice_seeds_submit(self, codes, off, lens, opt: GapOpt) -> "Job":
+        """Asynchronous splice_seeds (see whole_reads_submit)."""
+        cp, op, lp, n = _ptr(codes, np.uint8), _ptr(off, np.uint64), _ptr(lens, np.uint32), _len(lens)
+        h = C.c_void_p()
+        _check(lib().hsa_splice_seeds_submit(self._h, cp[0], op[0], lp[0], n, C.byref(opt), C.byref(h)))
         res = self._job_res[self._job_seq % len(self._job_res)]
         self._job_seq += 1
         return Job(h, res, (cp, op, lp))

@@ -1494,12 +1494,10 @@ extern "C" int hsa_whole_reads(const hsa_index_t *ix, const uint8_t *codes, cons
     return hsa_job_wait(j, res);
 }
 
-extern "C" int hsa_splice_seeds(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
-                                size_t n_reads, const hsa_gap_opt_t *opt, hsa_result_t *res)
+extern "C" int hsa_splice_seeds_submit(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                                       size_t n_reads, const hsa_gap_opt_t *opt, hsa_job_t **job)
 {
-    if (!res || !opt) return fail(HSA_E_ARG, "null argument");
-    if (n_reads == 0) return empty_result(res);
-    if (!ix || !codes || !off || !len) return fail(HSA_E_ARG, "null argument");
+    if (!ix || !opt || !job || !n_reads || !codes || !off || !len) return fail(HSA_E_ARG, "null / empty argument");
     if (n_reads > 0x2AAAAAA0ull) return fail(HSA_E_ARG, "too many reads in one batch");
     hsa_job *j; int rc; uint32_t max_len = 0;
     if ((rc = job_begin(ix, &j))) return rc;
@@ -1512,6 +1510,17 @@ extern "C" int hsa_splice_seeds(const hsa_index_t *ix, const uint8_t *codes, con
     b.kind = KIND_SEEDS; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads * 6; b.max_len = max_len;
     b.n_opts = 1; b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
     if ((rc = job_launch(j))) { job_release(j); return rc; }
+    *job = j;
+    return HSA_OK;
+}
+
+extern "C" int hsa_splice_seeds(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                                size_t n_reads, const hsa_gap_opt_t *opt, hsa_result_t *res)
+{
+    if (!res || !opt) return fail(HSA_E_ARG, "null argument");
+    if (n_reads == 0) return empty_result(res);
+    hsa_job_t *j; int rc;
+    if ((rc = hsa_splice_seeds_submit(ix, codes, off, len, n_reads, opt, &j))) return rc;
     return hsa_job_wait(j, res);
 }
 

@@ -171,6 +171,9 @@ int  hsa_job_wait(hsa_job_t *job, hsa_result_t *res);
  * strand s/3, with the reference's prefix-width quirk; hits carry start/end as bwtgap.c:816-819. */
 int  hsa_splice_seeds(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
                       size_t n_reads, const hsa_gap_opt_t *opt, hsa_result_t *res);
+/* asynchronous form (same job rules as hsa_whole_reads_submit; finish with hsa_job_wait) */
+int  hsa_splice_seeds_submit(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                             size_t n_reads, const hsa_gap_opt_t *opt, hsa_job_t **job);
 
 void hsa_result_free(hsa_result_t *res);
 

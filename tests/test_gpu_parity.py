@@ -265,6 +265,20 @@ def test_long_reads_use_the_rows_variant(golden, golden_index, dev_index):
     assert np.array_equal(el.aln9_to_rows12(res.ordered()), rows_ref)
 
 
+def test_seeds_async_job_equals_blocking_call(golden, dev_index):
+    case = "cfg2_100bp_default"
+    rs = golden.reads(case)
+    opt = to_api_opt(ol.default_opt(**golden.opt_kwargs(case)))
+    a = dev_index.splice_seeds(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt)
+    j1 = dev_index.splice_seeds_submit(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt)
+    j2 = dev_index.splice_seeds_submit(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, opt)
+    b1, b2 = j1.wait(), j2.wait()
+    for b in (b1, b2):
+        assert np.array_equal(a.n_aln, b.n_aln) and np.array_equal(a.ordered(), b.ordered()) and a.occ_lookups == b.occ_lookups
+    exp_n, exp_rows = golden.expected(case, "seeds")
+    assert np.array_equal(b1.n_aln, exp_n) and np.array_equal(el.aln9_to_rows12(b1.ordered()), exp_rows)
+
+
 def test_medium_batch_vs_oracle_and_properties():
     """A fresh 2 Mb genome, 60k reads (fills the whole grid): bit-exact against the oracle on a sample,
     plus size-independent properties on everything: every hit interval is non-empty and inside the SA range,

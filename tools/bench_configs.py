@@ -73,6 +73,21 @@ def main():
     opt = api.gap_init_opt()
     run(f"cfg3: {a.genome} bp, {n} spliced 100 bp reads -> 6 seed searches each (33/33/34 bp)",
         lambda: ix.splice_seeds(codes, off, lens, opt), n, reps=2)
+    # the same, double-buffered through the asynchronous job pair (results left in the library's pinned buffers)
+    def pipelined(steps):
+        job = ix.splice_seeds_submit(codes, off, lens, opt)
+        for k in range(steps):
+            nxt = ix.splice_seeds_submit(codes, off, lens, opt) if k + 1 < steps else None
+            last = job.wait(copy=False)
+            job = nxt
+        torch.cuda.synchronize()
+        return last
+    pipelined(4)
+    t0 = time.perf_counter()
+    last = pipelined(4)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"config": "cfg3 pipelined: 4 batches through hsa_splice_seeds_submit / hsa_job_wait", "reads": 4 * n,
+                      "wall_ms": dt * 1e3, "reads_per_s_e2e": 4 * n / dt, "kernel_ms_per_batch": last.kernel_ms}), flush=True)
     # cfg4 stress
     n = max(a.reads // 4, 100_000)
     r = synth_torch.simulate_reads(g, n, 150, 21, sub_rate=0.02, indel_frac=0.10)
