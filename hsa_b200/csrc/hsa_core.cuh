@@ -111,17 +111,6 @@ HSA_HD uint32_t ld_ro_u8(const uint8_t *p)
     return *p;
 #endif
 }
-// bring one 32-byte sector towards L1 ahead of the load that needs it (no register cost)
-HSA_HD void prefetch_sector(const void *p)
-{
-#if defined(__CUDA_ARCH__) && defined(HSA_PREFETCH) && HSA_PREFETCH == 2
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#elif defined(__CUDA_ARCH__) && defined(HSA_PREFETCH) && HSA_PREFETCH == 1
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
 HSA_HD int popc64(uint64_t x)
 {
 #if defined(__CUDA_ARCH__)
@@ -814,18 +803,6 @@ struct Worker {
         if (st == LS_POP) st = LS_END;                     // root pruned (wrong strand): the stack is empty
     }
 
-    // the two sectors the candidate's next LOOKUP step will read, requested as soon as its interval is known
-    HSA_HD void prefetch_next() const
-    {
-#if defined(HSA_PREFETCH) && HSA_PREFETCH
-        const DevBwt &B = P.ix.fwd;
-        uint32_t pk = ck, pl = cl + 1;
-        pk -= (pk > B.inverse_sa0); pl -= (pl > B.inverse_sa0);
-        prefetch_sector(B.blocks + 2 * (size_t)(pk >> 6));
-        prefetch_sector(B.blocks + 2 * (size_t)(pl >> 6));
-#endif
-    }
-
     // ---------------------------------------------------------------- pop-time tests (bwtgap.c:150-186)
     // The candidate is in the c* registers.  Sets st: LS_POP (candidate dropped), LS_LOOKUP (needs its occ4
     // pair: expansion, bwt_match_exact step, or materialisation), LS_HIT, LS_END.
@@ -840,7 +817,7 @@ struct Worker {
         m_cur = max_diff - c_nd;                                                     // :161-164
         if (m_cur < 0) { st = LS_POP; return; }
         if (ci > 0 && m_cur < (int32_t)(bb(ci - 1) & 63u)) { st = LS_POP; return; }   // :172-173
-        if (pend) { st = LS_LOOKUP; prefetch_next(); return; }   // survived pop-time pruning: materialise it first
+        if (pend) { st = LS_LOOKUP; return; }              // survived pop-time pruning: materialise it first
         classify();
     }
 
@@ -858,7 +835,6 @@ struct Worker {
             if (ck == 0) zflags = 1u | (cl == 0) << 1 | (crl - (cl - ck) == 0) << 2 | (crl == 0) << 3;
         }
         st = LS_LOOKUP;
-        prefetch_next();
     }
 
     // ---------------------------------------------------------------- POP: gap_pop (bwtgap.c:80-92) + vet
@@ -984,7 +960,7 @@ struct Worker {
             lookups_item += 2;
             if (!alive) { st = LS_POP; return LK_DONE; }
             ck = nk; cl = nl; crl = nr; ci = i;
-            if (ci == 0) st = LS_HIT; else prefetch_next();
+            if (ci == 0) st = LS_HIT;
             return LK_DONE;
         }
 
