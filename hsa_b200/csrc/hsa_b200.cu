@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
     const uint32_t n_work = P.n_work_dev ? min(*P.n_work_dev, P.n_work) : P.n_work;
     Worker<LinkT, BIDS_SMEM> w(P, slot, threadIdx.x);
     unsigned long long warp_iters = 0;
+    uint32_t pop_trips = 0;
 #ifdef HSA_PHASE_PROF
     unsigned long long prof_cyc[3] = {0, 0, 0}, prof_runs[3] = {0, 0, 0}, prof_lanes[3] = {0, 0, 0};
 #endif
@@ -148,12 +149,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
         const unsigned b0 = __ballot_sync(0xffffffffu, c & 1u), b1 = __ballot_sync(0xffffffffu, c & 2u);
         if ((b0 & b1) == 0xffffffffu) break;
         ++warp_iters;
-        if (P.drain_budget && (warp_iters & 63u) == 0 && w.budget != P.drain_budget) {
-            // once the queue is dry, the searches still running may only use drain_budget steps in total: what is
-            // heavier goes to the warp-cooperative kernel instead of holding the launch at lone-lane speed
-            const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(P.cursor);
-            if (cur >= n_work) w.budget = P.drain_budget;
-        }
         const uint32_t ph = phase_vote(P, __popc(b0 & ~b1), __popc(b1 & ~b0), __popc(~(b0 | b1)));
 #ifdef HSA_PHASE_PROF
         const long long t_ph0 = clock64();
@@ -169,6 +164,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
             __syncwarp();
             if (stage == Worker<LinkT, BIDS_SMEM>::LK_CHILD) w.lookup_child(lc);
         } else if (ph == PHASE_POP) {
+            if (P.drain_budget && (++pop_trips & 31u) == 0 && w.budget != P.drain_budget) {
+                // once the queue is dry, the searches still running may only use drain_budget steps in total: what is
+                // heavier goes to the warp-cooperative kernel instead of holding the launch at lone-lane speed
+                // (the budget is looked at when an entry is popped, so POP trips are where it is refreshed)
+                const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(P.cursor);
+                if (cur >= n_work) w.budget = P.drain_budget;
+            }
             if (c == PHASE_POP) w.do_pop();
         } else {
             if (w.st == LS_HIT) w.do_hit();

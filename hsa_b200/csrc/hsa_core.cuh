@@ -1009,8 +1009,8 @@ struct Worker {
             }
             if (allow_M) {                                                                  // :302-314
                 // children j = 1..3 (and j = 4 when seq[i] is N) are mismatches: bit j-1
-                maskB = ((vmask >> ((sc_ + 1u) & 3u)) & 1u) | ((vmask >> ((sc_ + 2u) & 3u)) & 1u) << 1 |
-                        ((vmask >> ((sc_ + 3u) & 3u)) & 1u) << 2 | (sc_ > 3 ? (vmask & 1u) << 3 : 0u);
+                // = vmask rotated right by sc_ + 1 (a 4-bit rotation: two copies side by side, shifted)
+                maskB = ((vmask * 0x11u) >> ((sc_ + 1u) & 3u)) & (sc_ > 3 ? 15u : 7u);
             }
             const int32_t gsc = c_score + (e_state == ST_M ? o.s_gapo : o.s_gape), msc = c_score + o.s_mm;
             const int32_t cut = n_hits ? pop_cut : 0x7FFFFFFF;      // bwtgap.c:158-159: can never be popped -> count only
