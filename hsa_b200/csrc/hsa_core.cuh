@@ -815,10 +815,11 @@ struct Worker {
             direct = false;
         }
         m_cur = max_diff - c_nd;                                                     // :161-164
-        if (m_cur < 0) { st = LS_POP; return; }
-        if (ci > 0 && m_cur < (int32_t)(bb(ci - 1) & 63u)) { st = LS_POP; return; }   // :172-173
-        if (pend) { st = LS_LOOKUP; return; }              // survived pop-time pruning: materialise it first
-        classify();
+        // (single-exit form: every early return costs a set of register moves on its way to the loop's back edge)
+        const bool drop = m_cur < 0 || (ci > 0 && m_cur < (int32_t)(bb(ci ? ci - 1 : 0) & 63u));       // :172-173
+        if (drop) st = LS_POP;
+        else if (pend) st = LS_LOOKUP;                     // survived pop-time pruning: materialise it first
+        else classify();
     }
 
     // hit test / bwt_match_exact entry (bwtgap.c:176-186) of a candidate whose interval is known
@@ -826,15 +827,16 @@ struct Worker {
     {
         const DevOpt &o = opt();
         ci_at_pop = ci;
-        if (ci == 0) { st = LS_HIT; return; }                                         // :177-179
-        if (m_cur == 0 && (c_state() == ST_M || (o.mode & MODE_GAPE) || (int32_t)c_gape() == o.max_gape)) {   // :180
+        const bool ex = ci != 0 && m_cur == 0 &&                                      // :177-180
+                        (c_state() == ST_M || (o.mode & MODE_GAPE) || (int32_t)c_gape() == o.max_gape);
+        if (ex) {
             exact = true;
             // only the root has k == 0 (k' = C[c] + occ + 1 >= 1), and with it rev_k == 0; l, rev_l and every other
             // node's rev_k (= the parent's rev_k + the interval's smaller symbols) are >= 1
             zflags = 0;
             if (ck == 0) zflags = 1u | (cl == 0) << 1 | (crl - (cl - ck) == 0) << 2 | (crl == 0) << 3;
         }
-        st = LS_LOOKUP;
+        st = ci == 0 ? LS_HIT : LS_LOOKUP;
     }
 
     // ---------------------------------------------------------------- POP: gap_pop (bwtgap.c:80-92) + vet
@@ -1055,13 +1057,16 @@ struct Worker {
     HSA_HD void lookup_child(const LookupCarry &in)
     {
         const DevOpt &o = opt();
-        if (in.sc < 4 && ((in.vmask >> (in.sc & 3u)) & 1u)) {
-            ck = in.nk; cl = in.nl; crl = in.nr; ci = in.i; c_diff = false;
-            c_meta &= ~(3u << META_STATE_SHIFT);            // STATE_M
-            if (n_live + n_phantom + 1 > (uint32_t)o.max_entries) { st = LS_END; return; }           // :150-151
-            if (ci > 0 && m_cur < (int32_t)(bb(ci - 1) & 63u)) { st = LS_POP; return; }              // :172-173
-            classify();
-        } else st = LS_POP;
+        const bool exists = in.sc < 4 && ((in.vmask >> (in.sc & 3u)) & 1u);
+        // (values without meaning when the child does not exist or is dropped: the next POP overwrites all of them)
+        ck = in.nk; cl = in.nl; crl = in.nr; ci = in.i; c_diff = false;
+        c_meta &= ~(3u << META_STATE_SHIFT);            // STATE_M
+        const bool over = n_live + n_phantom + 1 > (uint32_t)o.max_entries;                           // :150-151
+        const bool pruned = ci > 0 && m_cur < (int32_t)(bb(ci ? ci - 1 : 0) & 63u);                   // :172-173
+        if (!exists) st = LS_POP;
+        else if (over) st = LS_END;
+        else if (pruned) st = LS_POP;
+        else classify();
     }
 
     // ---------------------------------------------------------------- HIT: action for found hits, bwtgap.c:188-241
