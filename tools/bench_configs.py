@@ -57,11 +57,23 @@ def main():
     g = synth_torch.make_genome(a.genome, 1, dev)
     ix = api.Index.upload(index_build.build_index(g, device=dev), 0)
     # cfg3: spliced reads = two exons across an intron; the seed searches are what the hot path sees
+    for L in (100, 75):
+        spliced_seeds(a, ix, g, dev, L)
+    # cfg4 stress
+    n = max(a.reads // 4, 100_000)
+    r = synth_torch.simulate_reads(g, n, 150, 21, sub_rate=0.02, indel_frac=0.10)
+    codes, off, lens = pinned(r.reshape(-1)), pinned(torch.arange(n, dtype=torch.int64) * 150), pinned(torch.full((n,), 150, dtype=torch.int32))
+    opt = api.gap_init_opt(fnr=0.0, max_diff=5, max_gapo=2)
+    run(f"cfg4: {a.genome} bp, {n} x 150 bp, 2% subs, 10% indel reads, n5 o2", lambda: ix.whole_reads(codes, off, lens, opt, copy=False), n, reps=2)
+
+
+def spliced_seeds(a, ix, g, dev, L):
+    """cfg3: spliced reads = two exons across an intron; the six seed searches per read (len/3 bp each: 33/33/34 for
+    100 bp reads, 25/25/25 for 75 bp reads -- the 25 bp figure of BASELINE.json's config) are what the hot path sees."""
     n = a.reads
     gen = torch.Generator(device=dev); gen.manual_seed(5)
-    L = 100
     start = torch.randint(0, a.genome - 60_000, (n, 1), device=dev, generator=gen)
-    split = torch.randint(33, 67, (n, 1), device=dev, generator=gen)
+    split = torch.randint(L // 3, L - L // 3, (n, 1), device=dev, generator=gen)
     intron = torch.randint(50, 50_000, (n, 1), device=dev, generator=gen)
     j = torch.arange(L, device=dev)[None, :]
     reads = g[start + j + torch.where(j >= split, intron, torch.zeros_like(intron))]
@@ -71,7 +83,7 @@ def main():
     reads = torch.where(rc, 3 - torch.flip(reads, dims=[1]), reads)
     codes, off, lens = pinned(reads.reshape(-1)), pinned(torch.arange(n, dtype=torch.int64) * L), pinned(torch.full((n,), L, dtype=torch.int32))
     opt = api.gap_init_opt()
-    run(f"cfg3: {a.genome} bp, {n} spliced 100 bp reads -> 6 seed searches each (33/33/34 bp)",
+    run(f"cfg3: {a.genome} bp, {n} spliced {L} bp reads -> 6 seed searches each ({L // 3} bp segments)",
         lambda: ix.splice_seeds(codes, off, lens, opt), n, reps=2)
     # the same, double-buffered through the asynchronous job pair (results left in the library's pinned buffers)
     def pipelined(steps):
@@ -86,14 +98,8 @@ def main():
     t0 = time.perf_counter()
     last = pipelined(4)
     dt = time.perf_counter() - t0
-    print(json.dumps({"config": "cfg3 pipelined: 4 batches through hsa_splice_seeds_submit / hsa_job_wait", "reads": 4 * n,
+    print(json.dumps({"config": f"cfg3 pipelined ({L} bp reads): 4 batches through hsa_splice_seeds_submit / hsa_job_wait", "reads": 4 * n,
                       "wall_ms": dt * 1e3, "reads_per_s_e2e": 4 * n / dt, "kernel_ms_per_batch": last.kernel_ms}), flush=True)
-    # cfg4 stress
-    n = max(a.reads // 4, 100_000)
-    r = synth_torch.simulate_reads(g, n, 150, 21, sub_rate=0.02, indel_frac=0.10)
-    codes, off, lens = pinned(r.reshape(-1)), pinned(torch.arange(n, dtype=torch.int64) * 150), pinned(torch.full((n,), 150, dtype=torch.int32))
-    opt = api.gap_init_opt(fnr=0.0, max_diff=5, max_gapo=2)
-    run(f"cfg4: {a.genome} bp, {n} x 150 bp, 2% subs, 10% indel reads, n5 o2", lambda: ix.whole_reads(codes, off, lens, opt, copy=False), n, reps=2)
 
 
 if __name__ == "__main__":
