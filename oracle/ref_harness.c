@@ -39,6 +39,7 @@ int bwa_index_main(int argc, char **argv);
 /* shim/hsa_gpu_shim.c: the reference-side binding of libhsa_b200.so (same signature as bwa_cal_sa_reg_gap) */
 int hsa_gpu_open(const Idx2BWT *bi, int device);
 void hsa_gpu_close(void);
+void hsa_gpu_sa_values(const Idx2BWT *bi, const unsigned int *sa_index, size_t n, unsigned int *occ_pos);
 void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bwt, int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt, bwt_array_t *arr);
 #endif
 typedef void (*driver_fn)(int, const Idx2BWT *, int, bwa_seq_t *, const gap_opt_t *, bwt_array_t *);
@@ -598,6 +599,26 @@ int main(int argc, char **argv)
         rc = mode_driver(argc, argv);
         hsa_gpu_close();
         return rc;
+    }
+#endif
+#ifdef HSA_WITH_GPU_SHIM
+    if (strcmp(argv[1], "gpusa") == 0) {
+        /* gpusa <prefix> <idx.bin>: every listed SA index through BWTSaValue on the host and through the shim's GPU
+         * batch call; exits 0 only if all values agree (prints the count of mismatches) */
+        Idx2BWT *bi; FILE *fi; uint32_t n, i, bad = 0, *idx, *pos;
+        if (argc < 4) die("usage: gpusa <prefix> <idx.bin>");
+        bi = load_index(argv[2]);
+        fi = fopen(argv[3], "rb"); if (!fi) die("cannot open idx");
+        if (fread(&n, 4, 1, fi) != 1) die("short idx");
+        idx = (uint32_t*)malloc(4 * (size_t)n); pos = (uint32_t*)malloc(4 * (size_t)n);
+        if (fread(idx, 4, n, fi) != n) die("short idx");
+        fclose(fi);
+        if (hsa_gpu_open(bi, 0)) return 3;
+        hsa_gpu_sa_values(bi, idx, n, pos);
+        for (i = 0; i < n; ++i) bad += pos[i] != BWTSaValue(bi->bwt, idx[i]);
+        hsa_gpu_close();
+        printf("{\"mode\":\"gpusa\",\"n\":%u,\"mismatches\":%u}\n", n, bad);
+        return bad ? 4 : 0;
     }
 #endif
     if (strcmp(argv[1], "whole") == 0) return mode_whole(argc, argv);

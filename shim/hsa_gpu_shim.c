@@ -5,8 +5,9 @@
  * include/hsa_b200.h and provides
  *     bwa_cal_sa_reg_gap_gpu()  -- same signature and same observable results as bwa_cal_sa_reg_gap
  *                                  (bwtaln.c:246-417), with the whole-read searches done on the GPU.
- * Everything after the search -- bwt_splice_match for the reads that found nothing (bwtgap.c:748), SA lookups,
- * SAM output -- stays the reference's host code and consumes the bwt_aln1_t arrays unchanged.
+ *     hsa_gpu_sa_values()       -- BWTSaValue (BWT.c:1195) for a batch of SA indices.
+ * Everything after the search -- bwt_splice_match for the reads that found nothing (bwtgap.c:748), SAM output --
+ * stays the reference's host code and consumes the bwt_aln1_t arrays (and positions) unchanged.
  *
  * It is compiled only where the reference tree exists (oracle/Makefile target `shim`, outputs under oracle/_ref/)
  * and is exercised by tests/test_gpu_shim.py, which compares its per-read output with the stock driver's.
@@ -48,8 +49,26 @@ int hsa_gpu_open(const Idx2BWT *bi, int device)                /* call once afte
     return 0;
 }
 
+/* BWTSaValue (BWT.c:1195-1225) for a batch of SA indices: what BWTRetrievePositionFromSAIndex (2BWT-Interface.c:339)
+ * looks up for bwa_cal_pac_pos (bwtse.c:350-369) and bwt_aln_corelate_check (bwtgap.c:669-742).  The SA samples are
+ * handed to the library on first use (they need the full index, which hsa_gpu_open's search-only callers may not load). */
+static int g_sa_attached = 0;
+void hsa_gpu_sa_values(const Idx2BWT *bi, const unsigned int *sa_index, size_t n, unsigned int *occ_pos)
+{
+    if (!g_sa_attached) {
+        const BWT *b = bi->bwt;
+        if (!b->saValue || hsa_index_attach_sa(g_idx, b->saValue, b->saValueSizeInWord, b->saInterval)) {
+            fprintf(stderr, "[hsa_gpu] SA samples: %s\n", b->saValue ? hsa_last_error() : "index loaded without them");
+            exit(1);
+        }
+        g_sa_attached = 1;
+    }
+    if (hsa_sa_values(g_idx, sa_index, n, occ_pos, NULL)) { fprintf(stderr, "[hsa_gpu] %s\n", hsa_last_error()); exit(1); }
+}
+
 void hsa_gpu_close(void)
 {
+    g_sa_attached = 0;
     hsa_result_free(&g_res_a); hsa_result_free(&g_res_b);
     hsa_index_free(g_idx); g_idx = NULL;
 }

@@ -57,3 +57,17 @@ def test_gpu_driver_matches_stock_driver(workdir, opts):
     assert np.array_equal(n_c, n_g)
     assert np.array_equal(rows_c, rows_g)
     assert '"aligned_any"' in cpu.stdout and '"aligned_any"' in gpu.stdout
+
+
+def test_gpu_sa_values_match_BWTSaValue_inside_the_reference_program(workdir):
+    """`gpusa`: the reference's own BWTSaValue (host) against shim/hsa_gpu_shim.c's hsa_gpu_sa_values (GPU batch call on
+    the reference-loaded saValue array) for 200 000 SA indices of the reference-built index, compared in C."""
+    rng = np.random.default_rng(45)
+    idx = rng.integers(0, 1200011 + 1, size=200_000).astype(np.uint32)
+    idx[:4] = [0, 1, 1200011, 1200010]
+    with open(workdir / "sa.bin", "wb") as f:
+        np.asarray([idx.shape[0]], dtype=np.uint32).tofile(f)
+        idx.tofile(f)
+    r = subprocess.run([REF_GPU, "gpusa", "g", "sa.bin"], cwd=workdir, capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-2000:])
+    assert '"mismatches":0' in r.stdout
