@@ -127,6 +127,8 @@ def lib():
     L.hsa_index_attach_sa.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]
     L.hsa_sa_values.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint64)]
     L.hsa_sa_values_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hsa_index_attach_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.hsa_sa_locate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -219,6 +221,8 @@ class Index:
         ix = cls(h.value, device)
         if getattr(index2bwt.fwd, "sa_value", None) is not None:
             ix.attach_sa(index2bwt.fwd.sa_value, index2bwt.fwd.sa_interval)
+        if getattr(index2bwt, "blocks", None) is not None:
+            ix.attach_blocks(index2bwt.blocks.table())
         return ix
 
     @classmethod
@@ -274,6 +278,18 @@ class Index:
         _check(lib().hsa_sa_values(self._h, idx.ctypes.data, idx.shape[0], out.ctypes.data, C.byref(st)))
         self.last_sa_steps = int(st.value)
         return out
+
+    def attach_blocks(self, blocks4: np.ndarray) -> None:
+        """HSP::blockList rows {chrID, blockStart, blockEnd, ori} (index_io.Blocks.table())."""
+        t = np.ascontiguousarray(blocks4, dtype=np.uint32)
+        _check(lib().hsa_index_attach_blocks(self._h, t.ctypes.data, t.shape[0]))
+
+    def sa_locate(self, sa_indices: np.ndarray) -> np.ndarray:
+        """BWTRetrievePositionFromSAIndex (2BWT-Interface.c:329-362): rows {occ_pos, seq_id, ori_pos}."""
+        idx = np.ascontiguousarray(sa_indices, dtype=np.uint32)
+        o = [np.zeros(idx.shape[0], dtype=np.uint32) for _ in range(3)]
+        _check(lib().hsa_sa_locate(self._h, idx.ctypes.data, idx.shape[0], o[0].ctypes.data, o[1].ctypes.data, o[2].ctypes.data))
+        return np.stack(o, axis=1)
 
     def sa_values_device(self, idx_ptr: int, n: int, out_ptr: int, steps_ptr: int = 0, stream_ptr: int = 0) -> None:
         _check(lib().hsa_sa_values_device(self._h, idx_ptr, n, out_ptr, steps_ptr, stream_ptr))

@@ -70,7 +70,8 @@ __global__ void occ_kernel(DevBwt dev, RefBwt ref, int layout, const uint32_t *i
 enum : uint32_t { SA_CHUNK = 1024 };
 __global__ void __launch_bounds__(256) sa_kernel(DevBwt fwd, const uint32_t *sa_value, uint32_t sa_interval,
                                                  const uint32_t *sa_index, size_t n, uint32_t *out,
-                                                 unsigned long long *cursor, unsigned long long *steps_total)
+                                                 unsigned long long *cursor, unsigned long long *steps_total,
+                                                 const uint32_t *blocks4, uint32_t n_blocks, uint32_t *seq_id_out, uint32_t *ori_pos_out)
 {
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long base = 0, my = 0, steps = 0;
@@ -94,7 +95,13 @@ __global__ void __launch_bounds__(256) sa_kernel(DevBwt fwd, const uint32_t *sa_
         if (__ballot_sync(0xffffffffu, busy) == 0) { if (dry) break; else continue; }
         if (busy) {
             if (cur % sa_interval == 0) {               // a sampled SA index: done (BWT.c:1223)
-                out[my] = __ldg(sa_value + cur / sa_interval) + walked;
+                const uint32_t pos = __ldg(sa_value + cur / sa_interval) + walked;
+                out[my] = pos;
+                if (blocks4) {                          // the rest of BWTRetrievePositionFromSAIndex (2BWT-Interface.c:339-361)
+                    uint32_t sid = 0xFFFFFFFFu, op = 0xFFFFFFFFu;
+                    locate_dev(blocks4, n_blocks, pos, sid, op);
+                    seq_id_out[my] = sid; ori_pos_out[my] = op;
+                }
                 steps += walked;
                 busy = false;
             } else {
@@ -342,6 +349,7 @@ struct hsa_index {
     int sm_count = 0;
     uint32_t *sa_value = nullptr; size_t sa_words = 0; uint32_t sa_interval = 0;    // forward text's SA samples (optional)
     unsigned long long *sa_counters = nullptr;                                        // {work cursor, PsiMinus steps}
+    uint32_t *blocks4 = nullptr; uint32_t n_blocks = 0;                               // HSP::blockList rows (optional)
 };
 
 struct Scratch {                             // worker-private device memory for one launch configuration
@@ -616,7 +624,7 @@ extern "C" void hsa_index_free(hsa_index_t *ix)
     if (ix->d2h) cudaStreamDestroy(ix->d2h);
     if (ix->own_ref) for (int d = 0; d < 2; ++d) { cudaFree(ix->ref_code[d]); cudaFree(ix->ref_occ[d]); cudaFree(ix->ref_major[d]); }
     if (ix->own_blocks) for (int d = 0; d < 2; ++d) cudaFree(ix->blocks[d]);
-    cudaFree(ix->sa_value); cudaFree(ix->sa_counters);
+    cudaFree(ix->sa_value); cudaFree(ix->sa_counters); cudaFree(ix->blocks4);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -660,14 +668,30 @@ extern "C" int hsa_index_attach_sa(hsa_index_t *ix, const uint32_t *sa_value, si
     return HSA_OK;
 }
 
-static int sa_launch(const hsa_index_t *ix, const uint32_t *idx_dev, size_t n, uint32_t *out_dev, cudaStream_t s)
+extern "C" int hsa_index_attach_blocks(hsa_index_t *ix, const uint32_t *blocks4, uint32_t n_blocks)
+{
+    if (!ix || !blocks4 || n_blocks == 0) return fail(HSA_E_ARG, "bad argument");
+    for (uint32_t i = 0; i < n_blocks; ++i)
+        if (blocks4[4 * i + 1] > blocks4[4 * i + 2] || (i && blocks4[4 * i + 1] <= blocks4[4 * i - 2]))
+            return fail(HSA_E_ARG, "block list is not ascending and disjoint");
+    CU(cudaSetDevice(ix->device));
+    cudaFree(ix->blocks4); ix->blocks4 = nullptr;
+    CU(cudaMalloc((void **)&ix->blocks4, (size_t)n_blocks * 16));
+    CU(cudaMemcpy(ix->blocks4, blocks4, (size_t)n_blocks * 16, cudaMemcpyHostToDevice));
+    ix->n_blocks = n_blocks;
+    return HSA_OK;
+}
+
+static int sa_launch(const hsa_index_t *ix, const uint32_t *idx_dev, size_t n, uint32_t *out_dev, cudaStream_t s,
+                     uint32_t *seq_dev = nullptr, uint32_t *ori_dev = nullptr)
 {
     CU(cudaMemsetAsync(ix->sa_counters, 0, 2 * sizeof(unsigned long long), s));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_kernel, 256, 0));
     const size_t want = (n + SA_CHUNK - 1) / SA_CHUNK;   // one warp per chunk is the most that can find work
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)ix->sm_count * std::max(occ, 1), (want + 7) / 8));
-    sa_kernel<<<grid, 256, 0, s>>>(ix->ix.fwd, ix->sa_value, ix->sa_interval, idx_dev, n, out_dev, ix->sa_counters, ix->sa_counters + 1);
+    sa_kernel<<<grid, 256, 0, s>>>(ix->ix.fwd, ix->sa_value, ix->sa_interval, idx_dev, n, out_dev, ix->sa_counters, ix->sa_counters + 1,
+                                   seq_dev ? ix->blocks4 : nullptr, ix->n_blocks, seq_dev, ori_dev);
     CU(cudaGetLastError());
     return HSA_OK;
 }
@@ -693,6 +717,30 @@ extern "C" int hsa_sa_values(const hsa_index_t *ix, const uint32_t *sa_index, si
         if (steps_total) *steps_total = st;
     }
     cudaFree(d_idx); cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int hsa_sa_locate(const hsa_index_t *ix, const uint32_t *sa_index, size_t n, uint32_t *occ_pos_out, uint32_t *seq_id_out,
+                             uint32_t *ori_pos_out)
+{
+    if (!ix || (n && (!sa_index || !occ_pos_out || !seq_id_out || !ori_pos_out))) return fail(HSA_E_ARG, "bad argument");
+    if (!ix->sa_value) return fail(HSA_E_ARG, "no SA samples attached to this index (hsa_index_attach_sa)");
+    if (!ix->blocks4) return fail(HSA_E_ARG, "no block list attached to this index (hsa_index_attach_blocks)");
+    if (n == 0) return HSA_OK;
+    for (size_t i = 0; i < n; ++i)
+        if (sa_index[i] > ix->ix.fwd.text_length) return fail(HSA_E_ARG, "SA index beyond textLength");
+    CU(cudaSetDevice(ix->device));
+    uint32_t *d = nullptr;                               // {indices, occ_pos, seq_id, ori_pos}
+    CU(cudaMalloc((void **)&d, n * 16));
+    CU(cudaMemcpyAsync(d, sa_index, n * 4, cudaMemcpyHostToDevice, ix->stream));
+    int rc = sa_launch(ix, d, n, d + n, ix->stream, d + 2 * n, d + 3 * n);
+    if (rc == HSA_OK) {
+        CU(cudaMemcpyAsync(occ_pos_out, d + n, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU(cudaMemcpyAsync(seq_id_out, d + 2 * n, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU(cudaMemcpyAsync(ori_pos_out, d + 3 * n, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU(cudaStreamSynchronize(ix->stream));
+    }
+    cudaFree(d);
     return rc;
 }
 

@@ -254,6 +254,22 @@ HSA_HD uint32_t sa_value_dev(const DevBwt &b, const uint32_t *sa_value, uint32_t
     return ld_ro1(sa_value + sa_index / sa_interval) + steps;
 }
 
+// the block search of BWTRetrievePositionFromSAIndex (2BWT-Interface.c:339-361) over HSP::blockList rows
+// {chrID, blockStart, blockEnd, ori}: the block that holds packed-text position occ_pos -> chromosome id and 1-based
+// position in it; positions outside every block (SA[0] = -1) leave the outputs as they are, like the reference
+HSA_HD bool locate_dev(const uint32_t *b4, uint32_t n_blocks, uint32_t occ_pos, uint32_t &seq_id, uint32_t &ori_pos)
+{
+    uint32_t l = 0, h = n_blocks;
+    while (l < h) {
+        const uint32_t m = (l + h) >> 1;
+        const uint32_t start = ld_ro1(b4 + 4 * m + 1);
+        if (start > occ_pos) h = m;
+        else if (ld_ro1(b4 + 4 * m + 2) < occ_pos) l = m + 1;
+        else { seq_id = ld_ro1(b4 + 4 * m); ori_pos = occ_pos - start + ld_ro1(b4 + 4 * m + 3) + 1; return true; }
+    }
+    return false;
+}
+
 // ---- rank on the REFERENCE layout (BWT.c:793-837, 1018-1059, 532-679) -------------------------------
 HSA_HD void count_pairs_ref(uint32_t w, uint32_t a, uint32_t b, uint32_t cnt[4])
 {

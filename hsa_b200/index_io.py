@@ -74,9 +74,52 @@ class BWTArrays:
 
 
 @dataclasses.dataclass
+class Blocks:
+    """HSP::blockList (HSP.h:41-46, loaded from <prefix>.index.ann by HSPLoad, HSP.c:85-106): the N-free stretches of
+    the chromosomes in packed-text coordinates.  chr_id, start, end (inclusive), ori: uint32[n_blocks], ascending."""
+    chr_id: np.ndarray
+    start: np.ndarray
+    end: np.ndarray
+    ori: np.ndarray
+    names: list = dataclasses.field(default_factory=list)
+
+    @property
+    def n(self) -> int:
+        return int(self.start.shape[0])
+
+    def table(self) -> np.ndarray:
+        return np.ascontiguousarray(np.stack([self.chr_id, self.start, self.end, self.ori], axis=1).astype(np.uint32))
+
+
+def load_ann(path: str) -> Blocks:
+    """<prefix>.index.ann as HSPLoad reads it (HSP.c:85-106)."""
+    with open(path) as f:
+        tok = f.read().split()
+    n_chr = int(tok[1])
+    p = 3
+    names = []
+    for _ in range(n_chr):
+        names.append(tok[p + 1]); p += 2
+    nb = int(tok[p]); p += 1
+    t = np.asarray(tok[p: p + 4 * nb], dtype=np.int64).reshape(nb, 4).astype(np.uint32)
+    return Blocks(t[:, 0].copy(), t[:, 1].copy(), t[:, 2].copy(), t[:, 3].copy(), names)
+
+
+def blocks_of_records(lengths) -> Blocks:
+    """The block list the reference builder writes for a FASTA of ACGT-only records (one block per record, ori 0;
+    HSP.c:222-310)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    ends = np.cumsum(lengths)
+    return Blocks(np.arange(lengths.shape[0], dtype=np.uint32), (ends - lengths).astype(np.uint32),
+                  (ends - 1).astype(np.uint32), np.zeros(lengths.shape[0], dtype=np.uint32),
+                  [f"r{i}" for i in range(lengths.shape[0])])
+
+
+@dataclasses.dataclass
 class Index2BWT:
     fwd: BWTArrays
     rev: BWTArrays
+    blocks: Blocks | None = None
 
 
 def load_bwt(bwt_path: str, fmv_path: str) -> BWTArrays:
@@ -139,6 +182,8 @@ def load_index(prefix: str, with_sa: bool = True) -> Index2BWT:
     ix = Index2BWT(load_bwt(p + ".bwt", p + ".fmv"), load_bwt(p + ".rev.bwt", p + ".rev.fmv"))
     if with_sa and os.path.exists(p + ".sa"):
         load_sa(ix.fwd, p + ".sa")
+    if os.path.exists(p + ".ann"):
+        ix.blocks = load_ann(p + ".ann")
     return ix
 
 

@@ -219,6 +219,15 @@ int  hsa_index_attach_sa(hsa_index_t *idx, const uint32_t *sa_value, size_t n_wo
 int  hsa_sa_values(const hsa_index_t *idx, const uint32_t *sa_index, size_t n, uint32_t *sa_value_out, uint64_t *steps_total);
 int  hsa_sa_values_device(const hsa_index_t *idx, const uint32_t *sa_index_dev, size_t n, uint32_t *sa_value_out_dev,
                           uint64_t *steps_total_dev, void *stream);
+/* The whole of BWTRetrievePositionFromSAIndex (2BWT-Interface.c:329-362): BWTSaValue, then the block search over
+ * HSP::blockList (HSP.h:41-46, read from <prefix>.index.ann by HSPLoad, HSP.c:85-106).  attach: n_blocks rows
+ * {chrID, blockStart, blockEnd, ori} as the reference holds them (ascending, disjoint; else HSA_E_ARG).
+ * hsa_sa_locate: per SA index *occ_pos = BWTSaValue, *seq_id = chrID and *ori_pos = occ_pos - blockStart + ori + 1 of the
+ * block holding it; where no block holds the position (only SA[0] = -1) seq_id and ori_pos are 0xFFFFFFFF (the reference
+ * leaves its outputs untouched there). */
+int  hsa_index_attach_blocks(hsa_index_t *idx, const uint32_t *blocks4, uint32_t n_blocks);
+int  hsa_sa_locate(const hsa_index_t *idx, const uint32_t *sa_index, size_t n, uint32_t *occ_pos_out, uint32_t *seq_id_out,
+                   uint32_t *ori_pos_out);
 
 /* ---- roofline probe: random 32-byte-sector loads over `footprint_bytes` ----
  * Reports the best achieved GB/s (sectors * 32 B / time) at full occupancy of two variants: four dependent chains per

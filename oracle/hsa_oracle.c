@@ -119,6 +119,21 @@ uint32_t hsao_sa_value(const hsa_bwt_view_t *bwt, const uint32_t *sa_value, uint
     return sa_value[sa_index / sa_interval] + skipped;       /* SA[0] is stored as -1 (BWT.c:222, :1221-1222) */
 }
 
+/* 2BWT-Interface.c:339-361.  The reference's loop runs `while (l <= h)` from h = numOfBlock with unsigned arithmetic; for
+ * a position inside some block it never looks at blockList[numOfBlock] and never takes m - 1 of m = 0, so it is the
+ * plain binary search restated here; positions outside every block (only SA[0] = -1 in practice) are "not found". */
+int hsao_locate(const uint32_t *b4, uint32_t n_blocks, uint32_t occ_pos, uint32_t *seq_id, uint32_t *ori_pos)
+{
+    uint32_t l = 0, h = n_blocks;
+    while (l < h) {
+        uint32_t m = (l + h) >> 1;
+        if (b4[4 * m + 1] > occ_pos) h = m;
+        else if (b4[4 * m + 2] < occ_pos) l = m + 1;
+        else { *seq_id = b4[4 * m]; *ori_pos = occ_pos - b4[4 * m + 1] + b4[4 * m + 3] + 1; return 1; }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ SA-range stepping (2BWT-Interface.c) */
 
 /* BWTSARangeForeward, 2BWT-Interface.c:121-132: forward extension = backward step on rev_bwt with the

@@ -573,6 +573,32 @@ static int mode_sa(int argc, char **argv)
     return 0;
 }
 
+/* locate <prefix> <idx.bin> <out.bin>: BWTRetrievePositionFromSAIndex (2BWT-Interface.c:329-362) for every listed SA
+ * index (full index needed: SA samples and the annotation's block list).  Output: n, then {occ_pos, seq_id, ori_pos}
+ * per index; seq_id / ori_pos are preset to -1 so that "no block found" is visible. */
+static int mode_locate(int argc, char **argv)
+{
+    Idx2BWT *bi; FILE *fi, *fo; uint32_t n, i, *idx;
+    if (argc < 5) die("usage: locate <prefix> <idx.bin> <out.bin>");
+    bi = load_index(argv[2]);
+    if (!bi->hsp || !bi->bwt->saValue) die("locate needs a full index");
+    fi = fopen(argv[3], "rb"); if (!fi) die("cannot open idx");
+    if (fread(&n, 4, 1, fi) != 1) die("short idx");
+    idx = (uint32_t*)malloc(4 * (size_t)n);
+    if (fread(idx, 4, n, fi) != n) die("short idx");
+    fclose(fi);
+    fo = fopen(argv[4], "wb");
+    fwrite(&n, 4, 1, fo);
+    for (i = 0; i < n; ++i) {
+        unsigned int o[3] = {0, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        BWTRetrievePositionFromSAIndex(bi, idx[i], &o[1], &o[2], &o[0]);
+        fwrite(o, 4, 3, fo);
+    }
+    fclose(fo);
+    printf("{\"mode\":\"locate\",\"n\":%u,\"blocks\":%d}\n", n, bi->hsp->numOfBlock);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc < 2) die("usage: hsa_ref <index|occ|width|percall|seeds|driver|whole|dumpindex|maxdiff> ...");
@@ -583,6 +609,7 @@ int main(int argc, char **argv)
     }
     if (strcmp(argv[1], "occ") == 0) return mode_occ(argc, argv);
     if (strcmp(argv[1], "sa") == 0) return mode_sa(argc, argv);
+    if (strcmp(argv[1], "locate") == 0) return mode_locate(argc, argv);
     if (strcmp(argv[1], "width") == 0) return mode_width(argc, argv);
     if (strcmp(argv[1], "percall") == 0) return mode_percall(argc, argv);
     if (strcmp(argv[1], "seeds") == 0) return mode_seeds(argc, argv);

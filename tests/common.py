@@ -30,6 +30,12 @@ class Golden:
         self.genome = synth.make_repeat_genome(**self.meta["genome"])
         self._reads = {}
 
+    def genome2(self):
+        """(records, concatenated text) of the multi-record golden genome (make_golden.make_genome2)."""
+        import make_golden
+        assert make_golden.GENOME2 == self.meta["genome2"], "multi-record genome spec drifted"
+        return make_golden.make_genome2()
+
     @property
     def cases(self):
         return list(self.meta["cases"].keys())

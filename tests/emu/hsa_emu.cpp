@@ -161,6 +161,16 @@ void emu_sa_values(void *p, const uint32_t *sa_value, uint32_t sa_interval, cons
     }
 }
 
+// the block search of BWTRetrievePositionFromSAIndex through the device code (hsa_core.cuh: locate_dev)
+void emu_locate(const uint32_t *blocks4, uint32_t n_blocks, const uint32_t *pos, size_t n, uint32_t *seq_id, uint32_t *ori_pos)
+{
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t a = 0xFFFFFFFFu, b = 0xFFFFFFFFu;
+        locate_dev(blocks4, n_blocks, pos[i], a, b);
+        seq_id[i] = a; ori_pos[i] = b;
+    }
+}
+
 static void to_devopt(const hsa_gap_opt_t &o, DevOpt &d)
 {
     memset(&d, 0, sizeof(d));

@@ -114,6 +114,16 @@ class Emu:
                       idx.shape[0], out.ctypes.data)
         return out
 
+    @staticmethod
+    def locate(blocks, pos: np.ndarray):
+        t = blocks.table()
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        a = np.zeros(pos.shape[0], dtype=np.uint32)
+        b = np.zeros(pos.shape[0], dtype=np.uint32)
+        lib().emu_locate(C.c_void_p(t.ctypes.data), C.c_uint32(t.shape[0]), C.c_void_p(pos.ctypes.data), C.c_size_t(pos.shape[0]),
+                         C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data))
+        return a, b
+
     def sa_values(self, idx: np.ndarray):
         b = self.index.fwd
         idx = np.ascontiguousarray(idx, dtype=np.uint32)

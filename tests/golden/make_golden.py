@@ -38,6 +38,14 @@ CASES = {
                     dict(max_diff=3, fnr=0.0, max_gapo=2, max_gape=3, indel_end_skip=0)),
 }
 GENOME = dict(length=120011, seed=77)
+GENOME2 = dict(lengths=[3001, 777, 12007, 150, 9001, 75, 20011], seed=78)     # several FASTA records -> several blocks
+
+
+def make_genome2():
+    """The records of the multi-record golden genome (ACGT only) and their concatenation = the indexed text."""
+    rng = np.random.default_rng(GENOME2["seed"])
+    recs = [rng.integers(0, 4, size=n, dtype=np.uint8) for n in GENOME2["lengths"]]
+    return recs, np.concatenate(recs)
 
 
 def make_reads(genome, spec):
@@ -119,6 +127,24 @@ def main():
             ol.run_ref(["width", prefix, wp, 1, os.path.join(td, name + ".w")])
             arrays[f"{name}.width"] = np.fromfile(os.path.join(td, name + ".w"), dtype=np.uint32)
             meta["cases"][name] = info
+        # multi-record genome: BWTRetrievePositionFromSAIndex = BWTSaValue + the block search over the annotation
+        recs, text2 = make_genome2()
+        td2 = os.path.join(td, "g2"); os.mkdir(td2)
+        with open(os.path.join(td2, "m.fa"), "wb") as f:
+            for i, r in enumerate(recs):
+                f.write(f">rec{i}\n".encode() + np.frombuffer(b"ACGT", dtype=np.uint8)[r].tobytes() + b"\n")
+        subprocess.run([ol.REF_BIN, "index", "m", "m.fa"], cwd=td2, check=True, stdout=subprocess.DEVNULL)
+        ix2 = index_io.load_index(os.path.join(td2, "m"))
+        assert ix2.fwd.text_length == text2.shape[0]
+        meta["genome2"] = GENOME2
+        meta["index2"] = index_digest(ix2)
+        lidx = np.arange(1, ix2.fwd.text_length + 1, dtype=np.uint32)          # every SA index but 0 (SA[0] = -1: no block)
+        with open(os.path.join(td2, "lidx.bin"), "wb") as f:
+            np.asarray([lidx.shape[0]], dtype=np.uint32).tofile(f)
+            lidx.tofile(f)
+        ol.run_ref(["locate", os.path.join(td2, "m"), os.path.join(td2, "lidx.bin"), os.path.join(td2, "loc.out")])
+        arrays["loc_out"] = np.fromfile(os.path.join(td2, "loc.out"), dtype=np.uint32)[1:].reshape(-1, 3)
+        arrays["loc_blocks"] = ix2.blocks.table()
         out = subprocess.run([ol.REF_BIN, "maxdiff", "400", "0.04"], check=True, capture_output=True, text=True).stdout
         meta["maxdiff"] = {int(a): int(b) for a, b in (ln.split() for ln in out.strip().splitlines())}
     np.savez_compressed(os.path.join(HERE, "golden.npz"), **arrays)

@@ -67,6 +67,7 @@ def lib():
         L.hsao_occ1.restype = C.c_uint32
         L.hsao_sa_value.argtypes = [C.POINTER(BwtView), C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.hsao_sa_value.restype = C.c_uint32
+        L.hsao_locate.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.hsao_cal_maxdiff.argtypes = [C.c_int, C.c_double, C.c_double]
         L.hsao_cal_maxdiff.restype = C.c_int
         L.hsao_gap_opt_default.argtypes = [C.POINTER(GapOpt)]
@@ -127,6 +128,19 @@ class Oracle:
             out[i] = L.hsao_sa_value(C.byref(self.ix.fwd), b.sa_value.ctypes.data, b.sa_interval, x, C.byref(st))
             steps[i] = st.value
         return out, steps
+
+    def locate(self, indices: np.ndarray, blocks):
+        """BWTRetrievePositionFromSAIndex: rows {occ_pos, seq_id, ori_pos} (-1, -1 where no block holds the position)."""
+        L = lib()
+        pos, _ = self.sa_values(indices)
+        t = blocks.table()
+        out = np.full((indices.shape[0], 3), 0xFFFFFFFF, dtype=np.uint32)
+        out[:, 0] = pos
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        for i, x in enumerate(pos.tolist()):
+            if L.hsao_locate(t.ctypes.data, t.shape[0], x, C.byref(a), C.byref(b)):
+                out[i, 1], out[i, 2] = a.value, b.value
+        return out
 
     def cal_width(self, seq: np.ndarray, type_: int = 1):
         L = lib()

@@ -36,6 +36,18 @@ def test_sa_value_is_the_suffix_position(golden, emu):
     assert sufs == sorted(sufs) and len(set(int(p) for p in pos)) == 64 and int(pos.max()) < n
 
 
+def test_locate_device_code(golden):
+    """locate_dev (the block search of BWTRetrievePositionFromSAIndex) on the reference's block list and positions."""
+    from hsa_b200 import index_io
+    recs, _ = golden.genome2()
+    blocks = index_io.blocks_of_records([r.shape[0] for r in recs])
+    exp = golden.arr["loc_out"]
+    sid, op = el.Emu.locate(blocks, exp[:, 0])
+    assert np.array_equal(sid, exp[:, 1]) and np.array_equal(op, exp[:, 2])
+    sid, op = el.Emu.locate(blocks, np.asarray([0xFFFFFFFF, int(blocks.end[-1]) + 1], dtype=np.uint32))
+    assert (sid == 0xFFFFFFFF).all() and (op == 0xFFFFFFFF).all()      # outside every block: outputs untouched
+
+
 def test_width(golden, emu):
     case = "ragged_nonstop"
     rs = golden.reads(case).subset(0, 64)

@@ -90,6 +90,25 @@ def test_sa_values_bad_and_empty(golden_index, dev_index):
         dev_index.sa_values(np.asarray([golden_index.fwd.text_length + 1], dtype=np.uint32))
 
 
+def test_sa_locate_matches_reference(golden):
+    """hsa_sa_locate == BWTRetrievePositionFromSAIndex on the multi-record golden genome (every SA index but 0), and
+    SA index 0 (SA[0] = -1) reports no block."""
+    from hsa_b200 import index_io
+    recs, text = golden.genome2()
+    index = index_build.build_index(text, device="cuda")
+    index.blocks = index_io.blocks_of_records([r.shape[0] for r in recs])
+    ix = api.Index.upload(index, 0)
+    try:
+        idx = np.arange(1, text.shape[0] + 1, dtype=np.uint32)
+        assert np.array_equal(ix.sa_locate(idx), golden.arr["loc_out"])
+        z = ix.sa_locate(np.zeros(1, dtype=np.uint32))
+        assert z.tolist() == [[0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF]]
+        with pytest.raises(api.HsaError):
+            ix.attach_blocks(np.asarray([[0, 10, 5, 0]], dtype=np.uint32))        # start > end
+    finally:
+        ix.close()
+
+
 def test_hit_intervals_to_positions(golden, golden_index, dev_index):
     """The consumer's view (bwa_cal_pac_pos bwtse.c:350-369, bwt_aln_corelate_check bwtgap.c:669-742): every SA index of
     the hit intervals of a whole-read batch -> text position; for gap-free hits the strand-resolved read lies there

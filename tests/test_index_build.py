@@ -47,3 +47,17 @@ def test_against_live_reference_builder(length, seed, repeat):
         subprocess.run([ol.REF_BIN, "index", "g", "g.fa"], cwd=td, check=True, stdout=subprocess.DEVNULL)
         ref = index_io.load_index(os.path.join(td, "g"))
     assert _digest(mine) == _digest(ref)
+
+
+def test_annotation_roundtrip(tmp_path):
+    """load_ann parses what the reference builder writes (HSP.c:330-345) for a multi-record FASTA."""
+    b = index_io.blocks_of_records([3001, 777, 150])
+    with open(tmp_path / "x.ann", "w") as f:
+        f.write("3928\t3\t0\n")
+        for i in range(3):
+            f.write(f"4\trec{i}\n")
+        f.write("3\n")
+        for row in b.table().tolist():
+            f.write("%d\t%u\t%u\t%u\n" % tuple(row))
+    back = index_io.load_ann(str(tmp_path / "x.ann"))
+    assert np.array_equal(back.table(), b.table()) and back.names == ["rec0", "rec1", "rec2"]

@@ -36,6 +36,26 @@ def test_sa_value_matches_reference(golden, oracle):
     assert int(val[ok].max()) < n
 
 
+def test_locate_matches_reference(golden):
+    """BWTRetrievePositionFromSAIndex (2BWT-Interface.c:329-362) on the multi-record genome: every SA index but 0 ->
+    {occ_pos, chromosome id, 1-based position in the chromosome}, against the reference's own output; the product's
+    builder and block list reproduce the reference's index and annotation for that FASTA."""
+    from hsa_b200 import index_build, index_io
+    import make_golden
+    recs, text = golden.genome2()
+    ix2 = index_build.build_index(text, device="cpu")
+    assert make_golden.index_digest(ix2) == golden.meta["index2"]
+    blocks = index_io.blocks_of_records([r.shape[0] for r in recs])
+    assert np.array_equal(blocks.table(), golden.arr["loc_blocks"])
+    idx = np.arange(1, text.shape[0] + 1, dtype=np.uint32)
+    out = ol.Oracle(ix2).locate(idx, blocks)
+    assert np.array_equal(out, golden.arr["loc_out"])
+    # what it means: record seq_id, 1-based offset ori_pos, holds the suffix that starts at occ_pos
+    for q in range(0, idx.shape[0], 997):
+        occ, sid, op = (int(x) for x in out[q])
+        assert np.array_equal(recs[sid][op - 1: op + 7], text[occ: occ + 8][: recs[sid].shape[0] - (op - 1)])
+
+
 @pytest.mark.parametrize("case", ["cfg1_75bp_n2o1", "cfg2_100bp_default", "ragged_nonstop"])
 def test_width_matches_reference(golden, oracle, case):
     rs = golden.reads(case)
