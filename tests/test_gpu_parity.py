@@ -383,3 +383,27 @@ def test_million_reads_properties_against_the_text():
         assert np.array_equal((win != seq).sum(axis=1), f["n_mm"][hit_of].astype(np.int64))
     finally:
         ix.close()
+
+
+def test_short_reads_and_filters_vs_oracle(golden, golden_index, dev_index):
+    """Edges of the per-read driver logic (bwtaln.c:314-332): reads no longer than seed_len (the reference then reads
+    width_seed out of bounds, SURVEY.md hazard 3; the oracle and the library both search them without seeding), reads
+    the N filter drops, and reads with a 15-base poly-A / poly-T prefix (dropped before any search)."""
+    o = ol.Oracle(golden_index)
+    opt_o = ol.default_opt()
+    opt = to_api_opt(opt_o)
+    rs = synth.ragged_reads(golden.genome, 600, 12, 40, 9, sub_rate=0.02)
+    codes = rs.codes.copy()
+    off = rs.offsets
+    for r in range(0, 60, 3):                       # a run of N at the start: beyond the N budget of short reads
+        codes[off[r]: off[r] + 6] = 4
+    for r in range(1, 60, 3):                       # poly-A / poly-T prefixes (only reads >= 15 bp can have one)
+        if rs.lens[r] >= 15:
+            codes[off[r]: off[r] + 15] = 0 if r % 2 else 3
+    rs2 = synth.ReadSet(rs.lens, codes)
+    n_ref, rows_ref = o.whole(rs2, opt_o)
+    res = dev_index.whole_reads(rs2.codes, rs2.offsets[:-1].astype(np.uint64), rs2.lens, opt)
+    assert np.array_equal(res.n_aln, n_ref)
+    assert np.array_equal(el.aln9_to_rows12(res.ordered()), rows_ref)
+    assert res.occ_lookups == o.last_lookups
+    assert int(n_ref.sum()) > 300 and int((n_ref[1:60:3] == 0).sum()) >= 15
