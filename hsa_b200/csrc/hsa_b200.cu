@@ -763,8 +763,7 @@ static int scratch_alloc(Scratch &s, uint32_t n_workers, uint32_t arena_cap, uin
 {
     if (s.n_workers >= n_workers && s.arena_cap == arena_cap && s.hit_cap == hit_cap && s.link_bytes == link_bytes) return HSA_OK;
     s.release();
-    CU(cudaMalloc((void **)&s.arena, (size_t)n_workers * arena_cap * sizeof(u32x4)));
-    CU(cudaMalloc((void **)&s.links, (size_t)n_workers * arena_cap * link_bytes));
+    CU(cudaMalloc((void **)&s.arena, (size_t)n_workers * arena_cap * 2 * sizeof(u32x4)));     // 32-byte slots: record + link
     CU(cudaMalloc((void **)&s.hits, (size_t)n_workers * hit_cap * sizeof(Hit)));
     s.n_workers = n_workers; s.arena_cap = arena_cap; s.hit_cap = hit_cap; s.link_bytes = link_bytes;
     return HSA_OK;

@@ -95,6 +95,26 @@ HSA_HD void st4(void *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w)      //
     u32x4 v; v.x = x; v.y = y; v.z = z; v.w = w;
     *reinterpret_cast<u32x4 *>(p) = v;
 }
+// one 32-byte stack slot {record, link word(s) + padding} in a single 256-bit access (the slot is private to its lane)
+HSA_HD void ld_slot(const u32x4 *p, u32x4 &a, u32x4 &b)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p) : "memory");
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+HSA_HD void st_slot(u32x4 *p, const u32x4 &a, const u32x4 &b)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
 HSA_HD uint32_t ld_ro1(const uint32_t *p)
 {
 #if defined(__CUDA_ARCH__)
@@ -383,7 +403,7 @@ struct Params {
     uint8_t *rows;
     uint32_t row_stride, row_bid_off, row_seed_off, row_tail_off;
     // worker-private scratch, indexed by worker slot
-    u32x4 *arena;  void *links;  uint32_t arena_cap;
+    u32x4 *arena;  void *links;  uint32_t arena_cap;      // arena: 2 x u32x4 per slot (record, link); links: unused
     Hit *hits;     uint32_t hit_cap;
     uint32_t n_buckets;             // size of the score-indexed head table (<= 128)
     uint32_t smem_opts_bytes;       // shared memory: option table first ...
@@ -722,8 +742,11 @@ struct Worker {
         if (seed_mode == SEED_ALIAS) return bb(i);
         return BIDS_SMEM ? HSA_SMEM[sm_seed + i] : row[P.row_seed_off + i];
     }
-    HSA_HD u32x4 *arena() const { return P.arena + (size_t)slot * P.arena_cap; }
-    HSA_HD LinkT *links() const { return reinterpret_cast<LinkT *>(P.links) + (size_t)slot * P.arena_cap; }
+    // stack slot s of this lane: 32 bytes = {the 16-byte record, the link word, padding} -- one sector per push / pop
+    HSA_HD u32x4 *slot_at(uint32_t s) const { return P.arena + ((size_t)slot * P.arena_cap + s) * 2; }
+    HSA_HD LinkT *link_at(uint32_t s) const { return reinterpret_cast<LinkT *>(slot_at(s) + 1); }
+    static HSA_HD LinkT link_of(const u32x4 &aux) { return WIDE ? (LinkT)((uint64_t)aux.x | (uint64_t)aux.y << 32) : (LinkT)aux.x; }
+    static HSA_HD u32x4 aux_of(LinkT v) { u32x4 a; a.x = (uint32_t)v; a.y = WIDE ? (uint32_t)((uint64_t)v >> 32) : 0u; a.z = 0; a.w = 0; return a; }
     HSA_HD bool bucket_nonempty(uint32_t b) const
     {
         if (!WIDE) return (mask0 >> b) & 1ull;
@@ -864,12 +887,12 @@ struct Worker {
         if (n_live == 0 || n_live + n_phantom > (uint32_t)o.max_entries) { st = LS_END; return; }
         if (budget && steps32 > budget) { fail(STATUS_NEED_STRICT); st = LS_END; return; }   // heavy: hand it on
         const uint32_t b = bucket_lowest();
-        LinkT *lk = links();
         const uint32_t ref = head_get(b);
         const uint32_t s = ref & NIL;
         const bool isB = (ref >> NEXT_BITS) != 0;
-        const u32x4 e = arena()[s];
-        const LinkT lw = lk[s];
+        u32x4 e, aux;
+        ld_slot(slot_at(s), e, aux);
+        const LinkT lw = link_of(aux);
         ++pops32;
         --n_live;
         if ((int32_t)b > pop_cut) { st = LS_END; return; }                            // :158-159
@@ -888,7 +911,7 @@ struct Worker {
             const uint32_t other = isB ? halfA >> MASK_SHIFT : halfB >> MASK_SHIFT;
             if (other == 0) { nw = (LinkT)free_head; free_head = s; }
         }
-        lk[s] = nw;
+        *link_at(s) = nw;
         // the child (bwtgap.c:267-314) as a candidate; its score is the bucket it was filed under
         const uint32_t pm = e.w;
         const uint32_t pi = pm & 0xFFFu, pst = (pm >> META_STATE_SHIFT) & 3u;
@@ -1041,14 +1064,12 @@ struct Worker {
                     fail(WIDE ? STATUS_BAD_SCORE : STATUS_NEED_STRICT);      // the fast kernel has 64 buckets
                 else {
                     uint32_t s = NIL;
-                    LinkT *lk = links();
-                    if (free_head != NIL) { s = free_head; free_head = (uint32_t)(lk[s] & (LinkT)NIL); }
+                    if (free_head != NIL) { s = free_head; free_head = (uint32_t)(*link_at(s) & (LinkT)NIL); }
                     else if (top < P.arena_cap) s = top++;
                     else fail(STATUS_NEED_STRICT);
                     if (s != NIL) {
                         u32x4 e;
                         e.x = ck; e.y = cl; e.z = crl; e.w = c_meta | (i + 1);
-                        arena()[s] = e;
                         uint32_t halfA = NIL, halfB = NIL;
                         if (maskA) {
                             halfA = (bucket_nonempty((uint32_t)gsc) ? head_get((uint32_t)gsc) : NIL) | maskA << MASK_SHIFT;
@@ -1058,7 +1079,7 @@ struct Worker {
                             halfB = (bucket_nonempty((uint32_t)msc) ? head_get((uint32_t)msc) : NIL) | maskB << MASK_SHIFT;
                             head_set((uint32_t)msc, s | 1u << NEXT_BITS); bucket_set((uint32_t)msc);
                         }
-                        lk[s] = (LinkT)halfA | (LinkT)halfB << HALF_BITS;
+                        st_slot(slot_at(s), e, aux_of((LinkT)halfA | (LinkT)halfB << HALF_BITS));
                         n_live += nA + nB;
                     }
                 }

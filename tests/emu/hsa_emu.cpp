@@ -233,7 +233,7 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
         std::vector<unsigned char> smem((size_t)P.smem_opts_bytes + (size_t)lanes * P.smem_lane_stride + 16);
         memcpy(smem.data(), dopts.data(), dopts.size() * sizeof(DevOpt));
         hsa_smem_host = smem.data();
-        std::vector<u32x4> arena((size_t)cap * lanes);
+        std::vector<u32x4> arena((size_t)cap * lanes * 2);            // 32-byte slots: record + link
         std::vector<uint64_t> links((size_t)cap * lanes);          // large enough for either link width
         std::vector<Hit> hits((size_t)hcap * lanes);
         std::vector<u32x4> rows(((size_t)std::max(n_work, 1u) * P.row_stride + 15) / 16);
