@@ -62,6 +62,7 @@ extern __shared__ __align__(16) unsigned char hsa_smem[];
 #else
 static thread_local unsigned char *hsa_smem_host = nullptr;
 #define HSA_SMEM hsa_smem_host
+static unsigned long long hsa_host_pair_count = 0, hsa_host_pair_same_sector = 0;   // emulation statistics
 #endif
 
 namespace hsa {
@@ -964,6 +965,9 @@ struct Worker {
         u32x4 kc, kw, lc, lw;
         ld_sector(B.blocks + 2 * (size_t)(pk >> 6), kc, kw);
         ld_sector(B.blocks + 2 * (size_t)(pl >> 6), lc, lw);
+#if !defined(__CUDA_ARCH__)
+        ++hsa_host_pair_count; hsa_host_pair_same_sector += (pk >> 6) == (pl >> 6);    // emulation only: SURVEY 8d's deduplicated figure
+#endif
         // i: index of the base the lookup extends by.  For a pending child the lookup is the PARENT's: deletion
         // children have ci == the parent's pre-decrement i, mismatch children ci == its post-decrement i.
         const uint32_t i = (pend & PEND_MM) ? ci : ci - 1;
