@@ -185,6 +185,8 @@ void hsa_result_free(hsa_result_t *res);
  * queued on `stream`.  The caller checks stats[1] <= aln_capacity, stats[4] == 0, stats[3] <= n_reads / 4 and
  * stats[7] == 0 (searches even the cooperative kernel could not hold; such batches go through
  * hsa_whole_reads, which finishes them with the large-capacity kernel). */
+/* codes_dev is read in aligned 32-bit words: it must be readable up to the next 4-byte boundary past its last base
+ * (any cudaMalloc / framework allocation is; a sub-allocation ending exactly on a page end is not). */
 typedef struct hsa_workspace hsa_workspace_t;
 int  hsa_workspace_create(const hsa_index_t *idx, size_t max_reads, uint32_t max_len, size_t aln_capacity,
                           hsa_workspace_t **out);
