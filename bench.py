@@ -108,10 +108,18 @@ def cpu_reference_run(index, reads_np, n_sample: int, procs: int) -> dict:
             synth.write_reads_bin(os.path.join(td, "r.reads"), rs)
             out = subprocess.run([ref_bin, "whole", os.path.join(td, "g"), os.path.join(td, "r.reads"), "x", "nout=1",
                                   f"procs={procs}"], check=True, capture_output=True, text=True).stdout
-        j = json.loads(out.strip().splitlines()[-1])
+            j = json.loads(out.strip().splitlines()[-1])
+            one = None
+            if procs > 1:                    # the reference as it ships: single-threaded
+                n1 = min(rs.n, 40_000)
+                synth.write_reads_bin(os.path.join(td, "r1.reads"), rs.subset(0, n1))
+                o1 = subprocess.run([ref_bin, "whole", os.path.join(td, "g"), os.path.join(td, "r1.reads"), "x", "nout=1",
+                                     "procs=1"], check=True, capture_output=True, text=True).stdout
+                j1 = json.loads(o1.strip().splitlines()[-1])
+                one = {"value": n1 / j1["secs"], "sample": f"{n1} reads, 1 process"}
         return {"value": rs.n / j["secs"], "unit": UNIT, "cores": procs, "kind": "reference",
                 "sample": f"{rs.n} of the step's reads, whole-read path (no splice fallback), {procs} processes",
-                "aligned": j["aligned"], "secs": j["secs"]}
+                "aligned": j["aligned"], "secs": j["secs"], "single_thread": one}
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     o = ol.Oracle(index)
