@@ -115,6 +115,7 @@ def lib():
     L.hsa_result_free.argtypes = [C.POINTER(_Result)]
     L.hsa_workspace_create.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.POINTER(C.c_void_p)]
     L.hsa_workspace_free.argtypes = [C.c_void_p]
+    L.hsa_workspace_check.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.hsa_workspace_last_launches.argtypes = [C.c_void_p]
     L.hsa_workspace_last_launches.restype = C.c_uint32
     L.hsa_workspace_launch_timing.argtypes = [C.c_void_p, C.c_int]
@@ -402,6 +403,14 @@ class DeviceWorkspace:
         _check(lib().hsa_whole_reads_device(self.index._h, self._h, codes_ptr, off_ptr, len_ptr, n_reads,
                                             lp.ctypes.data, lp.shape[0], C.byref(opt), keep_gape, n_aln_ptr,
                                             aln_off_ptr, aln_ptr, aln_capacity, stats_ptr, stream_ptr))
+
+    def check(self) -> list:
+        """Wait for the last whole_reads_device call and verify that its results are complete (raises HsaError if any
+        search was left unprocessed or the hit arena overflowed).  Returns the statistics block
+        {-, hits, lookups, heavy, bad, pops, steps, unprocessed}."""
+        st = (C.c_uint64 * 8)()
+        _check(lib().hsa_workspace_check(self._h, st))
+        return [int(x) for x in st]
 
     def last_launches(self) -> int:
         return int(lib().hsa_workspace_last_launches(self._h))

@@ -348,17 +348,19 @@ struct hsa_index {
     cudaStream_t h2d = nullptr, d2h = nullptr;                     // copy streams of the job pipeline
     int sm_count = 0;
     uint32_t *sa_value = nullptr; size_t sa_words = 0; uint32_t sa_interval = 0;    // forward text's SA samples (optional)
-    unsigned long long *sa_counters = nullptr;                                        // {work cursor, PsiMinus steps}
+    enum { SA_SLOTS = 8 };
+    unsigned long long *sa_counters = nullptr;                                        // SA_SLOTS x {work cursor, PsiMinus steps}: one slot per call, round-robin
+    mutable uint32_t sa_seq = 0;
     uint32_t *blocks4 = nullptr; uint32_t n_blocks = 0;                               // HSP::blockList rows (optional)
 };
 
 struct Scratch {                             // worker-private device memory for one launch configuration
     uint32_t n_workers = 0, arena_cap = 0, hit_cap = 0, link_bytes = 0;
-    u32x4 *arena = nullptr; void *links = nullptr; Hit *hits = nullptr;
+    u32x4 *arena = nullptr; Hit *hits = nullptr;
     void release()
     {
-        cudaFree(arena); cudaFree(links); cudaFree(hits);
-        arena = nullptr; links = nullptr; hits = nullptr; n_workers = 0;
+        cudaFree(arena); cudaFree(hits);
+        arena = nullptr; hits = nullptr; n_workers = 0;
     }
 };
 
@@ -397,8 +399,15 @@ struct hsa_workspace {
     uint32_t *strict_list = nullptr; size_t strict_list_cap = 0;
     DevOpt *opts_dev = nullptr; size_t opts_cap = 0;
     uint16_t *len2opt_dev = nullptr; size_t len2opt_cap = 0;
-    DevOpt *opts_host = nullptr; size_t opts_host_cap = 0;            // pinned staging: copies need no host sync
-    uint16_t *len2opt_host = nullptr; size_t len2opt_host_cap = 0;
+    // pinned staging of the option table + length map: copies need no host sync.  A ring of OPT_STAGES buffers, each
+    // guarded by an event recorded behind its H2D copy, so that an asynchronous caller (hsa_whole_reads_device) may
+    // change the options from one call to the next without overwriting a copy that has not run yet.
+    enum { OPT_STAGES = 4 };
+    DevOpt *opts_stage[OPT_STAGES] = {nullptr, nullptr, nullptr, nullptr}; size_t opts_stage_cap[OPT_STAGES] = {0, 0, 0, 0};
+    uint16_t *l2o_stage[OPT_STAGES] = {nullptr, nullptr, nullptr, nullptr}; size_t l2o_stage_cap[OPT_STAGES] = {0, 0, 0, 0};
+    cudaEvent_t stage_ev[OPT_STAGES] = {nullptr, nullptr, nullptr, nullptr}; bool stage_used[OPT_STAGES] = {false, false, false, false};
+    uint32_t stage_next = 0;
+    DevOpt *opts_host = nullptr;                                       // the stage of the current batch (host-side reads)
     uint8_t *status_dev = nullptr; size_t status_cap = 0;
     // staging for the host-buffer entry points
     uint8_t *codes_dev = nullptr; size_t codes_cap = 0;
@@ -412,13 +421,15 @@ struct hsa_workspace {
     std::vector<const char *> trace_name;
     int trace = -1;
     uint32_t last_launches = 0;
+    // what hsa_workspace_check needs to know about the last device-resident call
+    cudaStream_t last_stream = nullptr; bool last_valid = false; uint64_t last_n = 0, last_aln_cap = 0;
     // launch configuration (environment overrides are read once)
     bool configured = false;
     uint32_t block = 128; int minb = 5; int blocks_per_sm_cap = 0;
     uint32_t n_pipes = 1; uint64_t chunk_items = 12u << 20;
     uint32_t arena_cap = 1022, hit_cap = 32;
     uint32_t vote_slow_min = VOTE_SLOW_MIN_DEFAULT; int32_t vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
-    bool use_coop = true; uint32_t step_budget = 0, drain_budget = 2000;
+    bool use_coop = true; uint32_t step_budget = 0, drain_budget = 1000;
 };
 
 template <typename T>
@@ -526,6 +537,8 @@ static int validate_view(const hsa_bwt_view_t *v)
     return HSA_OK;
 }
 
+extern "C" void hsa_index_free(hsa_index_t *ix);
+
 extern "C" int hsa_index_upload(int device, const hsa_bwt_view_t *fwd, const hsa_bwt_view_t *rev, hsa_index_t **out)
 {
     if (!out) return fail(HSA_E_ARG, "out is null");
@@ -535,19 +548,24 @@ extern "C" int hsa_index_upload(int device, const hsa_bwt_view_t *fwd, const hsa
     if ((rc = init_index_common(ix, device))) { delete ix; return rc; }
     const hsa_bwt_view_t *vs[2] = {fwd, rev};
     ix->own_ref = true; ix->have_ref = true;
-    for (int d = 0; d < 2; ++d) {
-        const hsa_bwt_view_t *v = vs[d];
-        CU(cudaMalloc((void **)&ix->ref_code[d], (size_t)v->bwtSizeInWord * 4));
-        CU(cudaMalloc((void **)&ix->ref_occ[d], (size_t)v->occSizeInWord * 4));
-        CU(cudaMalloc((void **)&ix->ref_major[d], (size_t)v->occMajorSizeInWord * 4));
-        CU(cudaMemcpyAsync(ix->ref_code[d], v->bwtCode, (size_t)v->bwtSizeInWord * 4, cudaMemcpyHostToDevice, ix->stream));
-        CU(cudaMemcpyAsync(ix->ref_occ[d], v->occValue, (size_t)v->occSizeInWord * 4, cudaMemcpyHostToDevice, ix->stream));
-        CU(cudaMemcpyAsync(ix->ref_major[d], v->occValueMajor, (size_t)v->occMajorSizeInWord * 4, cudaMemcpyHostToDevice, ix->stream));
-        ix->ref[d].bwt_code = ix->ref_code[d]; ix->ref[d].occ_value = ix->ref_occ[d]; ix->ref[d].occ_major = ix->ref_major[d];
-        ix->ref[d].text_length = v->textLength; ix->ref[d].inverse_sa0 = v->inverseSa0;
-        if ((rc = repack_direction(ix, d, v))) return rc;
-    }
-    CU(cudaStreamSynchronize(ix->stream));
+    auto upload_all = [&]() -> int {
+        for (int d = 0; d < 2; ++d) {
+            const hsa_bwt_view_t *v = vs[d];
+            CU(cudaMalloc((void **)&ix->ref_code[d], (size_t)v->bwtSizeInWord * 4));
+            CU(cudaMalloc((void **)&ix->ref_occ[d], (size_t)v->occSizeInWord * 4));
+            CU(cudaMalloc((void **)&ix->ref_major[d], (size_t)v->occMajorSizeInWord * 4));
+            CU(cudaMemcpyAsync(ix->ref_code[d], v->bwtCode, (size_t)v->bwtSizeInWord * 4, cudaMemcpyHostToDevice, ix->stream));
+            CU(cudaMemcpyAsync(ix->ref_occ[d], v->occValue, (size_t)v->occSizeInWord * 4, cudaMemcpyHostToDevice, ix->stream));
+            CU(cudaMemcpyAsync(ix->ref_major[d], v->occValueMajor, (size_t)v->occMajorSizeInWord * 4, cudaMemcpyHostToDevice, ix->stream));
+            ix->ref[d].bwt_code = ix->ref_code[d]; ix->ref[d].occ_value = ix->ref_occ[d]; ix->ref[d].occ_major = ix->ref_major[d];
+            ix->ref[d].text_length = v->textLength; ix->ref[d].inverse_sa0 = v->inverseSa0;
+            int rc2;
+            if ((rc2 = repack_direction(ix, d, v))) return rc2;
+        }
+        CU(cudaStreamSynchronize(ix->stream));
+        return HSA_OK;
+    };
+    if ((rc = upload_all())) { const std::string keep = g_err; hsa_index_free(ix); g_err = keep; return rc; }   // nothing leaks on failure
     *out = ix;
     return HSA_OK;
 }
@@ -561,13 +579,14 @@ extern "C" int hsa_index_from_device(int device, const hsa_bwt_view_t *fwd, cons
     if ((rc = init_index_common(ix, device))) { delete ix; return rc; }
     const hsa_bwt_view_t *vs[2] = {fwd, rev};
     ix->own_ref = false; ix->have_ref = true;
-    for (int d = 0; d < 2; ++d) {
+    for (int d = 0; d < 2 && !rc; ++d) {
         const hsa_bwt_view_t *v = vs[d];
         ix->ref[d].bwt_code = v->bwtCode; ix->ref[d].occ_value = v->occValue; ix->ref[d].occ_major = v->occValueMajor;
         ix->ref[d].text_length = v->textLength; ix->ref[d].inverse_sa0 = v->inverseSa0;
-        if ((rc = repack_direction(ix, d, v))) return rc;
+        rc = repack_direction(ix, d, v);
     }
-    CU(cudaStreamSynchronize(ix->stream));
+    if (!rc && cudaStreamSynchronize(ix->stream) != cudaSuccess) rc = fail(HSA_E_CUDA, "re-pack kernel failed");
+    if (rc) { const std::string keep = g_err; hsa_index_free(ix); g_err = keep; return rc; }
     // the caller keeps ownership of the reference-layout arrays and may free them now
     ix->have_ref = false;
     *out = ix;
@@ -659,7 +678,7 @@ extern "C" int hsa_index_attach_sa(hsa_index_t *ix, const uint32_t *sa_value, si
     CU(cudaSetDevice(ix->device));
     cudaFree(ix->sa_value); ix->sa_value = nullptr;
     CU(cudaMalloc((void **)&ix->sa_value, n_words * sizeof(uint32_t)));
-    if (!ix->sa_counters) CU(cudaMalloc((void **)&ix->sa_counters, 2 * sizeof(unsigned long long)));
+    if (!ix->sa_counters) CU(cudaMalloc((void **)&ix->sa_counters, 2 * hsa_index::SA_SLOTS * sizeof(unsigned long long)));
     CU(cudaMemcpyAsync(ix->sa_value, sa_value, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
     const uint32_t minus1 = 0xFFFFFFFFu;                 // BWT.c:222: SA[0] is kept as -1 whatever the file holds
     CU(cudaMemcpyAsync(ix->sa_value, &minus1, sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
@@ -682,15 +701,19 @@ extern "C" int hsa_index_attach_blocks(hsa_index_t *ix, const uint32_t *blocks4,
     return HSA_OK;
 }
 
+// Every call takes its own {cursor, steps} slot, so calls on different streams never share a work cursor (up to SA_SLOTS
+// calls may be in flight per index).  *slot_out = the slot's counters.
 static int sa_launch(const hsa_index_t *ix, const uint32_t *idx_dev, size_t n, uint32_t *out_dev, cudaStream_t s,
-                     uint32_t *seq_dev = nullptr, uint32_t *ori_dev = nullptr)
+                     unsigned long long **slot_out, uint32_t *seq_dev = nullptr, uint32_t *ori_dev = nullptr)
 {
-    CU(cudaMemsetAsync(ix->sa_counters, 0, 2 * sizeof(unsigned long long), s));
+    unsigned long long *cnt = ix->sa_counters + 2 * (ix->sa_seq++ % hsa_index::SA_SLOTS);
+    *slot_out = cnt;
+    CU(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_kernel, 256, 0));
     const size_t want = (n + SA_CHUNK - 1) / SA_CHUNK;   // one warp per chunk is the most that can find work
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)ix->sm_count * std::max(occ, 1), (want + 7) / 8));
-    sa_kernel<<<grid, 256, 0, s>>>(ix->ix.fwd, ix->sa_value, ix->sa_interval, idx_dev, n, out_dev, ix->sa_counters, ix->sa_counters + 1,
+    sa_kernel<<<grid, 256, 0, s>>>(ix->ix.fwd, ix->sa_value, ix->sa_interval, idx_dev, n, out_dev, cnt, cnt + 1,
                                    seq_dev ? ix->blocks4 : nullptr, ix->n_blocks, seq_dev, ori_dev);
     CU(cudaGetLastError());
     return HSA_OK;
@@ -708,11 +731,12 @@ extern "C" int hsa_sa_values(const hsa_index_t *ix, const uint32_t *sa_index, si
     uint32_t *d_idx = nullptr, *d_out = nullptr;
     CU(cudaMalloc((void **)&d_idx, n * 4)); CU(cudaMalloc((void **)&d_out, n * 4));
     CU(cudaMemcpyAsync(d_idx, sa_index, n * 4, cudaMemcpyHostToDevice, ix->stream));
-    int rc = sa_launch(ix, d_idx, n, d_out, ix->stream);
+    unsigned long long *cnt = nullptr;
+    int rc = sa_launch(ix, d_idx, n, d_out, ix->stream, &cnt);
     if (rc == HSA_OK) {
         unsigned long long st = 0;
         CU(cudaMemcpyAsync(sa_value_out, d_out, n * 4, cudaMemcpyDeviceToHost, ix->stream));
-        CU(cudaMemcpyAsync(&st, ix->sa_counters + 1, sizeof(st), cudaMemcpyDeviceToHost, ix->stream));
+        CU(cudaMemcpyAsync(&st, cnt + 1, sizeof(st), cudaMemcpyDeviceToHost, ix->stream));
         CU(cudaStreamSynchronize(ix->stream));
         if (steps_total) *steps_total = st;
     }
@@ -733,7 +757,8 @@ extern "C" int hsa_sa_locate(const hsa_index_t *ix, const uint32_t *sa_index, si
     uint32_t *d = nullptr;                               // {indices, occ_pos, seq_id, ori_pos}
     CU(cudaMalloc((void **)&d, n * 16));
     CU(cudaMemcpyAsync(d, sa_index, n * 4, cudaMemcpyHostToDevice, ix->stream));
-    int rc = sa_launch(ix, d, n, d + n, ix->stream, d + 2 * n, d + 3 * n);
+    unsigned long long *cnt = nullptr;
+    int rc = sa_launch(ix, d, n, d + n, ix->stream, &cnt, d + 2 * n, d + 3 * n);
     if (rc == HSA_OK) {
         CU(cudaMemcpyAsync(occ_pos_out, d + n, n * 4, cudaMemcpyDeviceToHost, ix->stream));
         CU(cudaMemcpyAsync(seq_id_out, d + 2 * n, n * 4, cudaMemcpyDeviceToHost, ix->stream));
@@ -752,9 +777,10 @@ extern "C" int hsa_sa_values_device(const hsa_index_t *ix, const uint32_t *sa_in
     if (n == 0) return HSA_OK;
     CU(cudaSetDevice(ix->device));
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = sa_launch(ix, sa_index_dev, n, sa_value_out_dev, s);
+    unsigned long long *cnt = nullptr;
+    int rc = sa_launch(ix, sa_index_dev, n, sa_value_out_dev, s, &cnt);
     if (rc) return rc;
-    if (steps_total_dev) CU(cudaMemcpyAsync(steps_total_dev, ix->sa_counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+    if (steps_total_dev) CU(cudaMemcpyAsync(steps_total_dev, cnt + 1, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
     return HSA_OK;
 }
 
@@ -792,7 +818,11 @@ extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
     cudaFree(ws->status_dev); cudaFree(ws->codes_dev); cudaFree(ws->off_dev); cudaFree(ws->len_dev);
     cudaFree(ws->tasks_dev); cudaFree(ws->n_aln_dev); cudaFree(ws->aln_off_dev); cudaFree(ws->aln_dev);
     cudaFree(ws->width_out_dev); cudaFree(ws->bid_dev);
-    cudaFreeHost(ws->opts_host); cudaFreeHost(ws->len2opt_host);
+    for (int i = 0; i < hsa_workspace::OPT_STAGES; ++i) {
+        cudaFreeHost(ws->opts_stage[i]); cudaFreeHost(ws->l2o_stage[i]);
+        if (ws->stage_ev[i]) cudaEventDestroy(ws->stage_ev[i]);
+    }
+    for (cudaEvent_t e : ws->trace_ev) cudaEventDestroy(e);
     if (ws->ev0) cudaEventDestroy(ws->ev0);
     if (ws->ev1) cudaEventDestroy(ws->ev1);
     delete ws;
@@ -876,6 +906,7 @@ static const void *search_fn(Variant v, int block, int minb)
 struct Batch {                      // everything one batch needs, device pointers
     uint32_t kind = 0, n_groups = 0, n_items = 0, max_len = 0, n_opts = 0, n_buckets = 1, max_seed_len = 0;
     int32_t filter_max_n = 0;
+    bool scores_positive = true;    // every option set has s_mm, s_gapo, s_gape >= 1 (the cooperative stage needs that)
     const uint8_t *codes = nullptr; const Task *tasks = nullptr;
     const uint64_t *read_off = nullptr; const uint32_t *read_len = nullptr;
     int32_t *n_aln = nullptr; uint64_t *aln_off = nullptr; uint32_t *aln = nullptr; uint64_t aln_cap = 0;
@@ -1013,7 +1044,7 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     unsigned long long *slots = ws->counters + CNT_PIPE0 + 4 * pipe_slot;
     CU(cudaMemsetAsync(slots, 0, 4 * sizeof(unsigned long long), stream));
     P.rows = pipe.rows;
-    P.arena = pipe.sc.arena; P.links = pipe.sc.links; P.arena_cap = pipe.sc.arena_cap;
+    P.arena = pipe.sc.arena; P.arena_cap = pipe.sc.arena_cap;
     P.hits = pipe.sc.hits; P.hit_cap = pipe.sc.hit_cap;
     P.coop_payload = pipe.coop_payload; P.coop_info = pipe.coop_info; P.coop_prev = pipe.coop_prev;
     P.coop_out_payload = pipe.coop_out_payload; P.coop_out_info = pipe.coop_out_info; P.coop_hits = pipe.coop_hits;
@@ -1046,14 +1077,9 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
 
 // The warp-cooperative stage needs positive scores (a chain must only push into higher buckets) and reads short
 // enough for a warp's shared-memory block; otherwise heavy searches go straight to the large-capacity kernel.
-static bool coop_usable(hsa_workspace *ws, const Batch &b, const hsa_gap_opt_t *opts_host_unused)
+static bool coop_usable(hsa_workspace *ws, const Batch &b)
 {
-    (void)opts_host_unused;
-    if (!ws->use_coop || b.kind == KIND_WIDTH) return false;
-    for (uint32_t i = 0; i < b.n_opts; ++i) {
-        const DevOpt &o = ws->opts_host[i];
-        if (o.s_mm < 1 || o.s_gapo < 1 || o.s_gape < 1) return false;
-    }
+    if (!ws->use_coop || b.kind == KIND_WIDTH || !b.scores_positive) return false;
     return b.max_len <= 2000;
 }
 
@@ -1144,7 +1170,7 @@ static int batch_enqueue(hsa_workspace *ws, const Batch &b, cudaStream_t stream,
     // the heavy searches the fast kernel handed on (stack / hit capacity, scores >= 64, step budgets) go through the
     // warp-cooperative kernel right behind it: its work count is read from device memory, nothing is synchronised
     ws->heavy_enqueued = false;
-    if (b.kind != KIND_WIDTH && coop_usable(ws, b, nullptr)) {
+    if (b.kind != KIND_WIDTH && coop_usable(ws, b)) {
         ws->heavy_cap = (uint32_t)std::min<uint64_t>(n_work_total, std::max<uint64_t>(65536, n_work_total / 4));
         if ((rc = ensure(ws->strict2_list, ws->strict2_list_cap, (size_t)n_work_total + 1))) return rc;
         Params S = P;
@@ -1206,7 +1232,7 @@ static int batch_finish(hsa_workspace *ws, const Batch &b, cudaStream_t stream, 
     *ms = t;
     if (cnt[CNT_BAD]) return fail(HSA_E_ARG, "a score exceeded the bucket table (internal sizing error)");
     const uint64_t n_heavy = cnt[CNT_STRICT];                 // handed on by the fast kernel
-    const bool coop_ok = coop_usable(ws, b, nullptr);
+    const bool coop_ok = coop_usable(ws, b);
     Params SC = P, SL = P;
     coop_layout(SC, b, seed_cap);
     set_layout(SL, b.max_len, seed_cap, b.n_buckets, b.n_opts, 4, false);
@@ -1397,6 +1423,7 @@ static int upload_reads(hsa_job *j, const uint8_t *codes, const uint64_t *off, c
         if (len[i] < mn) mn = len[i];
     }
     if (mn == 0) return fail(HSA_E_ARG, "empty read (len == 0)");
+    if (ml > 4095) return fail(HSA_E_ARG, "reads longer than 4095 bases are not supported");
     int rc;
     if ((rc = ensure(ws->codes_dev, ws->codes_cap, bytes + 16))) return rc;
     if (n + 1 > ws->reads_cap || !ws->off_dev) {
@@ -1423,28 +1450,37 @@ static int upload_opts(hsa_workspace *ws, const std::vector<hsa_gap_opt_t> &opts
     for (const hsa_gap_opt_t &o : opts)
         if (o.seed_len > 0 && (uint32_t)o.seed_len < max_len) bt->max_seed_len = std::max(bt->max_seed_len, (uint32_t)o.seed_len);
     int rc;
-    if (opts.size() > ws->opts_host_cap || !ws->opts_host) {
-        cudaFreeHost(ws->opts_host); ws->opts_host = nullptr;
-        CU(cudaHostAlloc((void **)&ws->opts_host, (opts.size() + 16) * sizeof(DevOpt), cudaHostAllocDefault));
-        ws->opts_host_cap = opts.size() + 16;
+    const uint32_t st = ws->stage_next;
+    ws->stage_next = (st + 1) % hsa_workspace::OPT_STAGES;
+    if (!ws->stage_ev[st]) CU(cudaEventCreateWithFlags(&ws->stage_ev[st], cudaEventDisableTiming));
+    if (ws->stage_used[st]) CU(cudaEventSynchronize(ws->stage_ev[st]));     // the copy that last read this stage has run
+    if (opts.size() > ws->opts_stage_cap[st] || !ws->opts_stage[st]) {
+        cudaFreeHost(ws->opts_stage[st]); ws->opts_stage[st] = nullptr;
+        CU(cudaHostAlloc((void **)&ws->opts_stage[st], (opts.size() + 16) * sizeof(DevOpt), cudaHostAllocDefault));
+        ws->opts_stage_cap[st] = opts.size() + 16;
     }
+    ws->opts_host = ws->opts_stage[st];
     *n_buckets = 1;
+    bt->scores_positive = true;
     for (size_t i = 0; i < opts.size(); ++i) {
         if ((rc = check_opt(opts[i], max_len, n_buckets))) return rc;
         to_devopt(opts[i], ws->opts_host[i]);
+        if (opts[i].s_mm < 1 || opts[i].s_gapo < 1 || opts[i].s_gape < 1) bt->scores_positive = false;
     }
     if ((rc = ensure(ws->opts_dev, ws->opts_cap, opts.size()))) return rc;
     CU(cudaMemcpyAsync(ws->opts_dev, ws->opts_host, opts.size() * sizeof(DevOpt), cudaMemcpyHostToDevice, stream));
     if (len2opt) {
-        if (len2opt->size() > ws->len2opt_host_cap || !ws->len2opt_host) {
-            cudaFreeHost(ws->len2opt_host); ws->len2opt_host = nullptr;
-            CU(cudaHostAlloc((void **)&ws->len2opt_host, (len2opt->size() + 64) * sizeof(uint16_t), cudaHostAllocDefault));
-            ws->len2opt_host_cap = len2opt->size() + 64;
+        if (len2opt->size() > ws->l2o_stage_cap[st] || !ws->l2o_stage[st]) {
+            cudaFreeHost(ws->l2o_stage[st]); ws->l2o_stage[st] = nullptr;
+            CU(cudaHostAlloc((void **)&ws->l2o_stage[st], (len2opt->size() + 64) * sizeof(uint16_t), cudaHostAllocDefault));
+            ws->l2o_stage_cap[st] = len2opt->size() + 64;
         }
-        memcpy(ws->len2opt_host, len2opt->data(), len2opt->size() * sizeof(uint16_t));
+        memcpy(ws->l2o_stage[st], len2opt->data(), len2opt->size() * sizeof(uint16_t));
         if ((rc = ensure(ws->len2opt_dev, ws->len2opt_cap, len2opt->size()))) return rc;
-        CU(cudaMemcpyAsync(ws->len2opt_dev, ws->len2opt_host, len2opt->size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(ws->len2opt_dev, ws->l2o_stage[st], len2opt->size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
     }
+    CU(cudaEventRecord(ws->stage_ev[st], stream));
+    ws->stage_used[st] = true;
     return HSA_OK;
 }
 
@@ -1484,7 +1520,8 @@ extern "C" int hsa_match_gap_batch(const hsa_index_t *ix, const uint8_t *codes, 
     for (size_t i = 0; i < n_tasks; ++i) {
         const hsa_task_t &t = tasks[i];
         if (t.opt_idx >= n_opts) return fail(HSA_E_ARG, "task.opt_idx out of range");
-        if (t.read_off + t.read_len > codes_bytes || t.sub_off + t.len > t.read_len || t.wsrc_off + t.len > t.read_len)
+        if (t.read_off > codes_bytes || (uint64_t)t.read_len > codes_bytes - t.read_off || (uint64_t)t.sub_off + t.len > t.read_len ||
+            (uint64_t)t.wsrc_off + t.len > t.read_len)
             return fail(HSA_E_ARG, "task window outside its read / codes buffer");
         if (t.seed_mode > HSA_SEED_ALIAS || t.strand > 1) return fail(HSA_E_ARG, "bad task.seed_mode / strand");
         if (t.len == 0) return fail(HSA_E_ARG, "empty task (len == 0)");
@@ -1638,8 +1675,42 @@ extern "C" int hsa_whole_reads_device(const hsa_index_t *ix, hsa_workspace_t *ws
     if ((rc = run_batch(ws, b, s, false, stats, &ms))) return rc;
     if (stats_dev) {
         CU(cudaMemcpyAsync(stats_dev, ws->counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
-        // word 7: searches the queued stages left unprocessed (handed on by the cooperative kernel)
-        CU(cudaMemcpyAsync(stats_dev + 7, ws->counters + CNT_STRICT2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+        // word 7: searches the queued stages left unprocessed: what the cooperative kernel handed on or, when that
+        // stage could not be queued (HSA_B200_COOP=0, non-positive scores, reads > 2000 bases), every heavy search
+        CU(cudaMemcpyAsync(stats_dev + 7, ws->counters + (ws->heavy_enqueued ? (int)CNT_STRICT2 : (int)CNT_STRICT), sizeof(unsigned long long),
+                           cudaMemcpyDeviceToDevice, s));
+    }
+    ws->last_stream = s; ws->last_valid = true; ws->last_n = n_reads; ws->last_aln_cap = aln_capacity;
+    return HSA_OK;
+}
+
+// Completion check of the last hsa_whole_reads_device call on this workspace: waits for its stream, reads the statistics
+// and fails unless every read was searched to the end and every hit fits the caller's arena.
+extern "C" int hsa_workspace_check(hsa_workspace_t *ws, uint64_t stats_out[8])
+{
+    if (!ws || !ws->last_valid) return fail(HSA_E_ARG, "no device-resident call to check on this workspace");
+    CU(cudaSetDevice(ws->idx->device));
+    CU(cudaStreamSynchronize(ws->last_stream));
+    unsigned long long cnt[CNT_ALLOC];
+    CU(cudaMemcpy(cnt, ws->counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    const uint64_t heavy = cnt[CNT_STRICT];
+    uint64_t left = ws->heavy_enqueued ? cnt[CNT_STRICT2] + (heavy > ws->heavy_cap ? heavy - ws->heavy_cap : 0) : heavy;
+    if (stats_out) {
+        for (int i = 0; i < CNT_N; ++i) stats_out[i] = cnt[i];
+        stats_out[7] = left;
+    }
+    char msg[256];
+    if (cnt[CNT_BAD]) return fail(HSA_E_ARG, "a score exceeded the bucket table (internal sizing error)");
+    if (cnt[CNT_ALN] > ws->last_aln_cap) {
+        snprintf(msg, sizeof(msg), "hit arena too small: %llu hits, capacity %llu (results incomplete)", cnt[CNT_ALN],
+                 (unsigned long long)ws->last_aln_cap);
+        return fail(HSA_E_CAPACITY, msg);
+    }
+    if (left) {
+        snprintf(msg, sizeof(msg), "%llu of %llu searches were left unprocessed by the queued stages (%llu heavy, cooperative stage %s): "
+                 "run this batch through hsa_whole_reads, which finishes them with the large-capacity kernel",
+                 (unsigned long long)left, (unsigned long long)ws->last_n, (unsigned long long)heavy, ws->heavy_enqueued ? "queued" : "not usable");
+        return fail(HSA_E_CAPACITY, msg);
     }
     return HSA_OK;
 }

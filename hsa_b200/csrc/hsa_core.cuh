@@ -404,7 +404,7 @@ struct Params {
     uint8_t *rows;
     uint32_t row_stride, row_bid_off, row_seed_off, row_tail_off;
     // worker-private scratch, indexed by worker slot
-    u32x4 *arena;  void *links;  uint32_t arena_cap;      // arena: 2 x u32x4 per slot (record, link); links: unused
+    u32x4 *arena;  uint32_t arena_cap;                    // arena: one 32-byte slot per record = 2 x u32x4 (record, link word + padding)
     Hit *hits;     uint32_t hit_cap;
     uint32_t n_buckets;             // size of the score-indexed head table (<= 128)
     uint32_t smem_opts_bytes;       // shared memory: option table first ...

@@ -103,7 +103,8 @@ void hsa_index_free(hsa_index_t *idx);
 int  hsa_occ_batch(const hsa_index_t *idx, int which, int layout, const uint32_t *indices, size_t n,
                    uint32_t *occ4_out, uint32_t *occ1_out);
 
-/* ---- bwt_cal_width (bwtaln.c:73-116), type 1 (forward search on rev_bwt) and type 0 ---------------
+/* ---- bwt_cal_width (bwtaln.c:73-116), type 1 (forward search on rev_bwt, :85-97) -------------------
+ * Type 0 (the backward variant, :99-111, used only by the splice extension) is refused with HSA_E_ARG.
  * codes: concatenated base codes (0..3, N = 4); read r is codes[off[r] .. off[r]+len[r]).
  * width_out: sum(len[r]+1) entries, read r at off[r]+r; bid_out[r] = return value. */
 int  hsa_cal_width_batch(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off,
@@ -182,9 +183,10 @@ void hsa_result_free(hsa_result_t *res);
  * Results stay on the device: n_aln_dev[n_reads], aln_off_dev[n_reads], aln_dev[aln_capacity] and an
  * 8 x uint64 stats block {-, hits, lookups, heavy, bad, pops, steps, unprocessed}.  Nothing is synchronised:
  * the fast kernel and, behind it, the warp-cooperative kernel for the `heavy` searches it handed on are
- * queued on `stream`.  The caller checks stats[1] <= aln_capacity, stats[4] == 0, stats[3] <= n_reads / 4 and
- * stats[7] == 0 (searches even the cooperative kernel could not hold; such batches go through
- * hsa_whole_reads, which finishes them with the large-capacity kernel). */
+ * queued on `stream`.  Completion is verified with hsa_workspace_check(): it waits for the call's stream and
+ * returns HSA_E_CAPACITY unless every read was searched to the end and every hit fits aln_capacity (searches
+ * even the cooperative kernel could not hold leave n_aln = 0 behind; such batches go through hsa_whole_reads,
+ * which finishes them with the large-capacity kernel).  One workspace serves one stream at a time. */
 /* codes_dev is read in aligned 32-bit words: it must be readable up to the next 4-byte boundary past its last base
  * (any cudaMalloc / framework allocation is; a sub-allocation ending exactly on a page end is not). */
 typedef struct hsa_workspace hsa_workspace_t;
@@ -196,6 +198,9 @@ int  hsa_whole_reads_device(const hsa_index_t *idx, hsa_workspace_t *ws, const u
                             const uint32_t *lens_present, size_t n_lens_present,   /* host: distinct read lengths */
                             const hsa_gap_opt_t *opt, int keep_gape, int32_t *n_aln_dev, uint64_t *aln_off_dev,
                             hsa_aln1_t *aln_dev, size_t aln_capacity, uint64_t *stats_dev, void *stream);
+/* waits for the last hsa_whole_reads_device call of this workspace and checks that its results are complete;
+ * stats_out (may be NULL) receives the statistics block with word 7 = searches left unprocessed */
+int  hsa_workspace_check(hsa_workspace_t *ws, uint64_t stats_out[8]);
 /* number of kernels the last call on this workspace launched (for bench's gpu_launches) */
 uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws);
 /* per-launch timing of the workspace's next calls (bench.py's roofline of the dominant kernel): enable records one
@@ -216,7 +221,7 @@ int  hsa_workspace_launch_times(hsa_workspace_t *ws, char *names, size_t names_c
  * hsa_sa_values: host buffers, n SA indices (each <= textLength, else HSA_E_ARG) -> n values, bit-identical to
  * BWTSaValue's, including its SA[0] = -1 convention; *steps_total (may be NULL) = PsiMinus steps walked in total.
  * hsa_sa_values_device: the same with device buffers on `stream` (cudaStream_t as void*), nothing synchronised;
- * indices are not range-checked. */
+ * indices are not range-checked.  Each call takes its own work cursor; at most 8 calls may be in flight per index. */
 int  hsa_index_attach_sa(hsa_index_t *idx, const uint32_t *sa_value, size_t n_words, uint32_t sa_interval);
 int  hsa_sa_values(const hsa_index_t *idx, const uint32_t *sa_index, size_t n, uint32_t *sa_value_out, uint64_t *steps_total);
 int  hsa_sa_values_device(const hsa_index_t *idx, const uint32_t *sa_index_dev, size_t n, uint32_t *sa_value_out_dev,

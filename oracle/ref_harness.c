@@ -181,6 +181,81 @@ static void resolve_read_opt(gap_opt_t *dst, const gap_opt_t *src, int len, int 
     dst->seed_len = src->seed_len < len ? src->seed_len : 0x7fffffff;
 }
 
+/* ---------------------------------------------------------------- forked ranges
+ * The reference has no working threading (bwtaln.c:307-311, 481-504 are commented out), so a read set is cut into
+ * `procs` contiguous shards, one forked process each.  Every worker reports {its own seconds, two counters, occ4,
+ * occ1}; with an output path it also writes its items to <out>.part<p>, which the parent concatenates behind the
+ * header in shard order -- so a multi-process run produces the same dump as a single-process one. */
+typedef struct { double secs; unsigned long long a, b, occ4, occ1; } range_res_t;
+typedef void (*range_fn)(void *ctx, uint32_t lo, uint32_t hi, FILE *fo, range_res_t *res);
+
+static void run_ranges(range_fn fn, void *ctx, uint32_t n, int procs, const char *out_path, uint32_t items_per_read,
+                       range_res_t *tot)
+{
+    uint32_t hdr[2];
+    memset(tot, 0, sizeof(*tot));
+    if (procs <= 1) {
+        FILE *fo = NULL;
+        if (out_path) { fo = fopen(out_path, "wb"); if (!fo) die("cannot open output"); hdr[0] = 0x41415348u; hdr[1] = items_per_read * n; fwrite(hdr, 4, 2, fo); }
+        g_occ4 = g_occ1 = 0;
+        fn(ctx, 0, n, fo, tot);
+        tot->occ4 = g_occ4; tot->occ1 = g_occ1;
+        if (fo) fclose(fo);
+        return;
+    }
+    {
+        int p, (*fds)[2] = (int (*)[2])calloc((size_t)procs, sizeof(int[2]));
+        if (procs > 1024) die("procs too large");
+        fflush(stdout);
+        for (p = 0; p < procs; ++p) {
+            pid_t pid;
+            if (pipe(fds[p]) != 0) die("pipe");
+            pid = fork();
+            if (pid < 0) die("fork");
+            if (pid == 0) {
+                uint32_t lo = (uint32_t)((uint64_t)n * p / procs), hi = (uint32_t)((uint64_t)n * (p + 1) / procs);
+                range_res_t r; FILE *fo = NULL;
+                memset(&r, 0, sizeof(r));
+                if (out_path) {
+                    char *pp = (char*)malloc(strlen(out_path) + 32);
+                    sprintf(pp, "%s.part%d", out_path, p);
+                    fo = fopen(pp, "wb"); if (!fo) _exit(4);
+                }
+                g_occ4 = g_occ1 = 0;
+                fn(ctx, lo, hi, fo, &r);
+                r.occ4 = g_occ4; r.occ1 = g_occ1;
+                if (fo) fclose(fo);
+                if (write(fds[p][1], &r, sizeof(r)) != (ssize_t)sizeof(r)) _exit(3);
+                _exit(0);
+            }
+            close(fds[p][1]);
+        }
+        for (p = 0; p < procs; ++p) {
+            range_res_t r;
+            memset(&r, 0, sizeof(r));
+            if (read(fds[p][0], &r, sizeof(r)) != (ssize_t)sizeof(r)) die("worker failed");
+            if (r.secs > tot->secs) tot->secs = r.secs;
+            tot->a += r.a; tot->b += r.b; tot->occ4 += r.occ4; tot->occ1 += r.occ1;
+            close(fds[p][0]);
+        }
+        while (wait(NULL) > 0) {}
+        free(fds);
+        if (out_path) {
+            FILE *fo = fopen(out_path, "wb"); char *pp = (char*)malloc(strlen(out_path) + 32), *buf = (char*)malloc(1 << 20);
+            if (!fo) die("cannot open output");
+            hdr[0] = 0x41415348u; hdr[1] = items_per_read * n; fwrite(hdr, 4, 2, fo);
+            for (p = 0; p < procs; ++p) {
+                FILE *fi; size_t got;
+                sprintf(pp, "%s.part%d", out_path, p);
+                fi = fopen(pp, "rb"); if (!fi) die("missing part file");
+                while ((got = fread(buf, 1, 1 << 20, fi)) > 0) fwrite(buf, 1, got, fo);
+                fclose(fi); remove(pp);
+            }
+            fclose(fo); free(pp); free(buf);
+        }
+    }
+}
+
 /* ---------------------------------------------------------------- modes */
 static int mode_occ(int argc, char **argv)
 {
@@ -293,23 +368,21 @@ static int mode_percall(int argc, char **argv)
 /* the six seed calls of bwt_splice_match (bwtgap.c:797-820), WITHOUT its early-outs, through the real
  * bwt_cal_width / bwt_match_gap: gaps off, max_diff = max_seed_diff, seed_len = len_align,
  * width computed on the read PREFIX (bwtgap.c:807-808) and aliased as width_back (bwtgap.c:809). */
-static int mode_seeds(int argc, char **argv)
+typedef struct { Idx2BWT *bi; reads_t *r; const gap_opt_t *opt; const hopt_t *h; } range_ctx_t;
+
+static void seeds_range(void *vctx, uint32_t lo, uint32_t hi, FILE *fo, range_res_t *res)
 {
-    Idx2BWT *bi; reads_t r; FILE *fo = NULL; hopt_t h; gap_opt_t *opt, sopt; uint32_t i, hdr[2];
-    int max_len = 0; bwt_aux_t aux; double t0, t1;
-    if (argc < 5) die("usage: seeds <prefix> <reads> <out> [opts]");
-    bi = load_index(argv[2]); r = load_reads(argv[3]);
-    opt = parse_opts(argc, argv, 5, &h);
-    for (i = 0; i < r.n; ++i) if ((int)r.len[i] > max_len) max_len = (int)r.len[i];
-    if (!h.nout) { fo = fopen(argv[4], "wb"); hdr[0] = 0x41415348u; hdr[1] = 6 * r.n; fwrite(hdr, 4, 2, fo); }
+    range_ctx_t *c = (range_ctx_t*)vctx;
+    Idx2BWT *bi = c->bi; reads_t *r = c->r; const gap_opt_t *opt = c->opt; gap_opt_t sopt;
+    int max_len = 0; bwt_aux_t aux; double t0; uint32_t i;
+    for (i = lo; i < hi; ++i) if ((int)r->len[i] > max_len) max_len = (int)r->len[i];
     memset(&aux, 0, sizeof(aux));
     aux.bi_bwt = bi; aux.max_len = max_len;
     aux.width_seed = (bwt_width_t*)calloc(max_len + 1, sizeof(bwt_width_t));
-    g_occ4 = g_occ1 = 0;
     t0 = now_s();
-    for (i = 0; i < r.n; ++i) {
-        int len = (int)r.len[i], s, seed_len = len / 3;
-        ubyte_t *seq = r.codes + r.off[i];
+    for (i = lo; i < hi; ++i) {
+        int len = (int)r->len[i], s, seed_len = len / 3;
+        ubyte_t *seq = r->codes + r->off[i];
         ubyte_t *rc = (ubyte_t*)calloc(max_len + 1, 1);
         memcpy(rc, seq, len); seq_reverse(len, rc, 1);
         for (s = 0; s < 6; ++s) {
@@ -330,16 +403,27 @@ static int mode_seeds(int argc, char **argv)
             aux.width_back = aux.width_seed;
             aln = bwt_match_gap(&aux, &n_aln);
             { int j; for (j = 0; j < n_aln; ++j) { aln[j].start = (s % 3) * seed_len; aln[j].end = aln[j].start + len_align - 1; } } /* bwtgap.c:816-819 */
+            res->a += (n_aln != 0);
             if (fo) put_aln(fo, n_aln, aln);
             free(aln);
             gap_destroy_stack(aux.stack);
         }
         free(rc);
     }
-    t1 = now_s();
-    if (fo) fclose(fo);
-    printf("{\"mode\":\"seeds\",\"reads\":%u,\"calls\":%u,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu}\n",
-           r.n, 6 * r.n, t1 - t0, g_occ4, g_occ1);
+    res->secs = now_s() - t0;
+    free(aux.width_seed);
+}
+
+static int mode_seeds(int argc, char **argv)
+{
+    Idx2BWT *bi; reads_t r; hopt_t h; gap_opt_t *opt; range_ctx_t ctx; range_res_t tot;
+    if (argc < 5) die("usage: seeds <prefix> <reads> <out> [opts] [procs=P] [nout=1]");
+    bi = load_index(argv[2]); r = load_reads(argv[3]);
+    opt = parse_opts(argc, argv, 5, &h);
+    ctx.bi = bi; ctx.r = &r; ctx.opt = opt; ctx.h = &h;
+    run_ranges(seeds_range, &ctx, r.n, h.procs, h.nout ? NULL : argv[4], 6, &tot);
+    printf("{\"mode\":\"seeds\",\"reads\":%u,\"calls\":%u,\"procs\":%d,\"calls_with_hits\":%llu,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu}\n",
+           r.n, 6 * r.n, h.procs, tot.a, tot.secs, tot.occ4, tot.occ1);
     return 0;
 }
 
@@ -471,48 +555,24 @@ static double run_whole_range(Idx2BWT *bi, reads_t *r, uint32_t lo, uint32_t hi,
     return secs;
 }
 
+static void whole_range(void *vctx, uint32_t lo, uint32_t hi, FILE *fo, range_res_t *res)
+{
+    range_ctx_t *c = (range_ctx_t*)vctx;
+    unsigned long long n_hit = 0;
+    res->secs = run_whole_range(c->bi, c->r, lo, hi, c->opt, c->h, fo, &n_hit);
+    res->a = n_hit;
+}
+
 static int mode_whole(int argc, char **argv)
 {
-    Idx2BWT *bi; reads_t r; FILE *fo = NULL; hopt_t h; gap_opt_t *opt; uint32_t hdr[2];
-    unsigned long long n_hit = 0; double secs;
+    Idx2BWT *bi; reads_t r; hopt_t h; gap_opt_t *opt; range_ctx_t ctx; range_res_t tot;
     if (argc < 5) die("usage: whole <prefix> <reads> <out> [opts] [procs=P] [nout=1]");
     bi = load_index(argv[2]); r = load_reads(argv[3]);
     opt = parse_opts(argc, argv, 5, &h);
-    g_occ4 = g_occ1 = 0;
-    if (h.procs <= 1) {
-        if (!h.nout) { fo = fopen(argv[4], "wb"); hdr[0] = 0x41415348u; hdr[1] = r.n; fwrite(hdr, 4, 2, fo); }
-        secs = run_whole_range(bi, &r, 0, r.n, opt, &h, fo, &n_hit);
-        if (fo) fclose(fo);
-    } else {
-        int p, fds[512][2]; double mx = 0;
-        if (h.procs > 512) die("procs too large");
-        for (p = 0; p < h.procs; ++p) {
-            pid_t pid;
-            if (pipe(fds[p]) != 0) die("pipe");
-            pid = fork();
-            if (pid < 0) die("fork");
-            if (pid == 0) {
-                uint32_t lo = (uint32_t)((uint64_t)r.n * p / h.procs), hi = (uint32_t)((uint64_t)r.n * (p + 1) / h.procs);
-                double res[2]; unsigned long long w = 0;
-                res[0] = run_whole_range(bi, &r, lo, hi, opt, &h, NULL, &w);
-                res[1] = (double)w;
-                if (write(fds[p][1], res, sizeof(res)) != (ssize_t)sizeof(res)) _exit(3);
-                _exit(0);
-            }
-            close(fds[p][1]);
-        }
-        for (p = 0; p < h.procs; ++p) {
-            double res[2] = {0, 0};
-            if (read(fds[p][0], res, sizeof(res)) != (ssize_t)sizeof(res)) die("worker failed");
-            if (res[0] > mx) mx = res[0];
-            n_hit += (unsigned long long)res[1];
-            close(fds[p][0]);
-        }
-        while (wait(NULL) > 0) {}
-        secs = mx;
-    }
+    ctx.bi = bi; ctx.r = &r; ctx.opt = opt; ctx.h = &h;
+    run_ranges(whole_range, &ctx, r.n, h.procs, h.nout ? NULL : argv[4], 1, &tot);
     printf("{\"mode\":\"whole\",\"reads\":%u,\"procs\":%d,\"aligned\":%llu,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu}\n",
-           r.n, h.procs, n_hit, secs, g_occ4, g_occ1);
+           r.n, h.procs, tot.a, tot.secs, tot.occ4, tot.occ1);
     return 0;
 }
 

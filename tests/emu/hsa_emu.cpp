@@ -244,7 +244,7 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
         P.tasks = (const Task *)tasks; P.read_off = read_off; P.read_len = read_len;
         P.opts = dopts.data(); P.len2opt = len2opt; P.filter_max_n = filter_max_n;
         P.rows = reinterpret_cast<uint8_t *>(rows.data());
-        P.arena = arena.data(); P.links = links.data(); P.arena_cap = cap;
+        P.arena = arena.data(); P.arena_cap = cap;
         P.hits = hits.data(); P.hit_cap = hcap;
         P.n_aln = n_aln; P.aln_off = aln_off; P.status = status; P.aln = aln; P.aln_cap = aln_cap;
         P.counters = counters; P.strict_list = strict.data(); P.strict_count = &counters[CNT_STRICT];
