@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""bench.py -- aligned reads/s of the B200 inexact-search path on BASELINE.json's configs[1]
-(46 Mb synthetic genome, 10 M simulated 100 bp reads, default gap_opt_t), next to the reference's own
-CPU path on the host cores.
+"""bench.py -- aligned reads/s of the B200 inexact-search path on BASELINE.json's configs[2]: GRCh38-sized (3.1 Gb)
+synthetic genome, index replicated per GPU, ONE set of 100 M simulated 100 bp reads sharded over the GPUs (default
+gap_opt_t), next to the reference's own CPU path on the host cores.  At N = 1 the line also carries a `secondary` block
+for configs[1] (46 Mb genome, L2-resident index, 10 M reads).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads R] [--genome G]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads-total R] [--genome G]
 
-N > 1 is launched by torchrun (one rank per GPU): rank 0 builds the index and broadcasts its device
-blocks over NCCL once; every rank then searches its own shard of R reads (weak scaling, no collective
-on the data path).  One JSON line is printed by rank 0.  See DESIGN.md section 6 for definitions.
+A step = one pass of the whole-read path over the whole read set.  N > 1 is launched by torchrun (one rank per GPU):
+rank 0 builds the index and broadcasts its device blocks over NCCL once; the host partitions the read set into
+contiguous shards (hsa_b200.shard.shard_bounds); every rank searches its shard in batches of <= --batch reads; in the
+end-to-end leg the per-rank results are gathered to rank 0 in input order.  Total work is fixed as N grows ("strong").
+One JSON line is printed by rank 0.  See DESIGN.md section 6 for the definitions.
 """
 from __future__ import annotations
 
@@ -25,7 +28,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "aligned_reads_per_sec"
 UNIT = "reads/s"
-ALGO_BYTES_PER_LOOKUP = 64          # BWT window sector + minor-occ sector of the reference layout
+ALGO_BYTES_PER_LOOKUP = 64          # BWT window sector + minor-occ sector of the REFERENCE layout
+DEVICE_BYTES_PER_LOOKUP = 32        # the device layout: one 32-byte sector holds the counts and the 64 symbols
+GEN_BLOCK = 2_500_000               # reads are generated in blocks of this many: block b has seed READ_SEED + b
+READ_SEED = 1000
+GENOME_SEED = 1
 
 
 def parse_args():
@@ -34,12 +41,15 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step (configs[1]: 10 M)")
-    ap.add_argument("--genome", type=int, default=46_000_003, help="synthetic genome length (configs[1]: 46 Mb)")
+    ap.add_argument("--reads-total", type=int, default=100_000_000, help="reads of the whole job per step (configs[2]: 100 M)")
+    ap.add_argument("--batch", type=int, default=12_500_000, help="reads per device batch (one hsa_whole_reads call)")
+    ap.add_argument("--genome", type=int, default=3_100_000_003, help="synthetic genome length (configs[2]: 3.1 Gb)")
     ap.add_argument("--read-len", type=int, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = min(steps, 5))")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[1] block (N = 1 only)")
     return ap.parse_args()
 
 
@@ -85,6 +95,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------ workload
+def workload_name(genome: int) -> str:
+    return {46_000_003: "configs[1]", 3_100_000_003: "configs[2]", 4_600_003: "configs[0]-sized genome"}.get(genome, "custom")
+
+
+def gen_reads(genome_t, lo: int, hi: int, L: int):
+    """Reads [lo, hi) of the job's global read set: block b = reads [b * GEN_BLOCK, (b + 1) * GEN_BLOCK) is drawn with seed
+    READ_SEED + b, so every rank (and the reference arm) can make exactly its own part."""
+    import torch
+    from hsa_b200 import synth_torch
+    parts = []
+    for b in range(lo // GEN_BLOCK, (hi + GEN_BLOCK - 1) // GEN_BLOCK):
+        blk = synth_torch.simulate_reads(genome_t, GEN_BLOCK, L, READ_SEED + b)
+        parts.append(blk[max(lo - b * GEN_BLOCK, 0): min(hi - b * GEN_BLOCK, GEN_BLOCK)])
+    return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+
+
 def write_index_files(index, prefix: str):
     from hsa_b200 import index_io
     p = prefix + ".index"
@@ -92,42 +119,60 @@ def write_index_files(index, prefix: str):
     index_io.save_bwt(index.rev, p + ".rev.bwt", p + ".rev.fmv")
 
 
-def cpu_reference_run(index, reads_np, n_sample: int, procs: int) -> dict:
-    """Time the reference's own CPU implementation of the whole-read path (oracle/_ref/hsa_ref `whole`:
-    the unmodified bwt_cal_width / bwt_match_gap from /root/reference, P forked processes over contiguous
-    shards) or, where that binary is absent, the oracle port (1 thread).  Bounded sample of the workload."""
+class CpuReference:
+    """The reference's own CPU implementation of the whole-read path: oracle/_ref/hsa_ref `whole` = the unmodified
+    bwt_cal_width / bwt_match_gap from the reference tree, looped per read exactly as the whole-read part of
+    bwa_cal_sa_reg_gap does (oracle/ref_harness.c: run_whole_range; like-for-like with hsa_whole_reads, no splice
+    fallback), P forked processes over contiguous shards.  Test / baseline infrastructure: never on the product path."""
+
+    def __init__(self, index, td: str):
+        self.bin = os.path.join(ROOT, "oracle", "_ref", "hsa_ref")
+        if not os.path.exists(self.bin):
+            raise RuntimeError("oracle/_ref/hsa_ref is missing (built by __graft_entry__.build() where the reference sources exist)")
+        self.td = td
+        self.prefix = os.path.join(td, "g")
+        write_index_files(index, self.prefix)
+
+    def run(self, reads_np, procs: int, name: str, with_output: bool):
+        import numpy as np
+        from hsa_b200 import synth
+        n, L = reads_np.shape
+        rs = synth.ReadSet(np.full(n, L, dtype=np.uint32), np.ascontiguousarray(reads_np).reshape(-1))
+        rp = os.path.join(self.td, name + ".reads")
+        if not os.path.exists(rp):
+            synth.write_reads_bin(rp, rs)
+        out = os.path.join(self.td, name + ".aln")
+        args = [self.bin, "whole", self.prefix, rp, out, f"procs={procs}"] + ([] if with_output else ["nout=1"])
+        j = json.loads(subprocess.run(args, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
+        dump = synth.read_aln_dump(out) if with_output else None
+        return j, dump
+
+
+def cpu_baseline_block(cpu: CpuReference, reads_np, procs: int, gpu_n_aln=None, gpu_rows12=None):
+    """cpu_baseline + parity: the sample runs WITH output on all host cores; the same reads' GPU results are compared
+    with the dump bit for bit (n_aln and the 12 words of every hit, in hit order)."""
     import numpy as np
-    from hsa_b200 import synth
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "hsa_ref")
-    sample = reads_np[:n_sample]
-    L = sample.shape[1]
-    rs = synth.ReadSet(np.full(sample.shape[0], L, dtype=np.uint32), np.ascontiguousarray(sample).reshape(-1))
-    if os.path.exists(ref_bin):
-        with tempfile.TemporaryDirectory() as td:
-            write_index_files(index, os.path.join(td, "g"))
-            synth.write_reads_bin(os.path.join(td, "r.reads"), rs)
-            out = subprocess.run([ref_bin, "whole", os.path.join(td, "g"), os.path.join(td, "r.reads"), "x", "nout=1",
-                                  f"procs={procs}"], check=True, capture_output=True, text=True).stdout
-            j = json.loads(out.strip().splitlines()[-1])
-            one = None
-            if procs > 1:                    # the reference as it ships: single-threaded (SURVEY.md section 8d, (i))
-                n1 = min(rs.n, 40_000)
-                synth.write_reads_bin(os.path.join(td, "r1.reads"), rs.subset(0, n1))
-                o1 = subprocess.run([ref_bin, "whole", os.path.join(td, "g"), os.path.join(td, "r1.reads"), "x", "nout=1",
-                                     "procs=1"], check=True, capture_output=True, text=True).stdout
-                j1 = json.loads(o1.strip().splitlines()[-1])
-                one = {"value": n1 / j1["secs"], "sample": f"{n1} reads, 1 process"}
-        return {"value": rs.n / j["secs"], "unit": UNIT, "cores": procs, "kind": "reference",
-                "sample": f"{rs.n} of the step's reads, whole-read path (no splice fallback), {procs} processes",
-                "aligned": j["aligned"], "secs": j["secs"], "single_thread": one}
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as ol
-    o = ol.Oracle(index)
-    t0 = time.time()
-    n_aln, _ = o.whole(rs, ol.default_opt())
-    secs = time.time() - t0
-    return {"value": rs.n / secs, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{rs.n} of the step's reads, oracle port, 1 thread", "aligned": int((n_aln > 0).sum()), "secs": secs}
+    n = reads_np.shape[0]
+    j, dump = cpu.run(reads_np, procs, "sample", with_output=gpu_n_aln is not None)
+    n1 = min(n, 20_000)
+    j1, _ = cpu.run(reads_np[:n1], 1, "single", with_output=False)
+    per_core = n / j["secs"] / procs
+    block = {"value": n / j["secs"], "unit": UNIT, "cores": procs, "kind": "reference",
+             "sample": f"the first {n} reads of the job, whole-read path (bwt_cal_width + bwt_match_gap per read and strand as "
+                       f"bwa_cal_sa_reg_gap drives them; no splice fallback), {procs} forked processes",
+             "aligned": j["aligned"], "secs": j["secs"], "per_core": per_core,
+             "single_thread": {"value": n1 / j1["secs"], "sample": f"{n1} reads, 1 process (the reference as it ships)"}}
+    parity = None
+    if dump is not None:
+        ref_n, ref_rows = dump
+        bad_n = int((ref_n != gpu_n_aln).sum())
+        same_rows = ref_rows.shape == gpu_rows12.shape and bool(np.array_equal(ref_rows, gpu_rows12))
+        bad_rows = 0 if same_rows else (int((ref_rows != gpu_rows12).any(axis=1).sum()) if ref_rows.shape == gpu_rows12.shape
+                                        else abs(ref_rows.shape[0] - gpu_rows12.shape[0]) or 1)
+        parity = {"reads": n, "hits": int(ref_rows.shape[0]), "n_aln_mismatch": bad_n, "row_mismatch": bad_rows,
+                  "against": "oracle/_ref/hsa_ref whole: the unmodified reference's bwt_cal_width + bwt_match_gap on the same "
+                             "index files and the same reads, n_aln and all 12 words per hit in hit order"}
+    return block, parity
 
 
 class _CudaView:
@@ -137,46 +182,207 @@ class _CudaView:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
+class DeviceLeg:
+    """Reads and results resident in HBM: hsa_whole_reads_device per batch of the shard, all on one stream."""
+
+    def __init__(self, index, reads_t, batch: int):
+        import torch
+        from hsa_b200 import api
+        self.torch, self.api = torch, api
+        dev = reads_t.device
+        self.n, self.L = int(reads_t.shape[0]), int(reads_t.shape[1])
+        self.codes = reads_t.reshape(-1)
+        self.batches = [(lo, min(lo + batch, self.n)) for lo in range(0, self.n, batch)]
+        nb_max = max(hi - lo for lo, hi in self.batches)
+        self.off = torch.arange(nb_max, device=dev, dtype=torch.int64) * self.L          # offsets inside a batch
+        self.len = torch.full((nb_max,), self.L, dtype=torch.int32, device=dev)
+        self.cap = 2 * nb_max + 1024
+        self.n_aln = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self.aln_off = torch.zeros(self.n, dtype=torch.int64, device=dev)
+        self.aln = torch.zeros((len(self.batches), self.cap * 9), dtype=torch.int32, device=dev)
+        self.stats = torch.zeros((len(self.batches), 8), dtype=torch.int64, device=dev)
+        self.opt = api.gap_init_opt()
+        self.ws = api.DeviceWorkspace(index)
+        self.stream = torch.cuda.current_stream()
+
+    def batch(self, b: int):
+        lo, hi = self.batches[b]
+        self.ws.whole_reads_device(self.codes.data_ptr() + lo * self.L, self.off.data_ptr(), self.len.data_ptr(), hi - lo,
+                                   [self.L], self.opt, self.n_aln.data_ptr() + 4 * lo, self.aln_off.data_ptr() + 8 * lo,
+                                   self.aln[b].data_ptr(), self.cap, self.stats[b].data_ptr(), self.stream.cuda_stream)
+        return self.ws.last_launches()
+
+    def step(self, check_every_batch: bool) -> int:
+        launches = 0
+        for b in range(len(self.batches)):
+            launches += self.batch(b)
+            if check_every_batch or b == len(self.batches) - 1:
+                self.ws.check()                      # raises unless the batch was searched to the end
+        return launches
+
+    def verify_stats(self):
+        st = self.stats.cpu().tolist()
+        for b, s in enumerate(st):
+            if s[1] > self.cap or s[4] or s[7]:
+                raise RuntimeError(f"batch {b} left work undone / overflowed its buffers: {s}")
+        return st
+
+    def results_of(self, lo: int, hi: int):
+        """(n_aln, rows12 in item order) of reads [lo, hi) -- must lie inside batch 0 (the parity sample)."""
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        assert hi <= self.batches[0][1]
+        n_aln = self.n_aln[lo:hi].cpu().numpy()
+        off = self.aln_off[lo:hi].cpu().numpy().astype(np.int64)
+        arena = self.aln[0].cpu().numpy().view(np.uint32).reshape(-1, 9)
+        nz = np.nonzero(n_aln)[0]
+        cnt = n_aln[nz].astype(np.int64)
+        idx = np.repeat(off[nz] - np.concatenate([[0], np.cumsum(cnt)[:-1]]), cnt) + np.arange(int(cnt.sum()))
+        a = arena[idx]
+        r = np.zeros((a.shape[0], 12), dtype=np.uint32)          # the 12-word dump layout of oracle/ref_harness.c
+        r[:, 0], r[:, 1], r[:, 2] = a[:, 0] & 0xFFFF, (a[:, 0] >> 16) & 0xFF, (a[:, 0] >> 24) & 0xFF
+        r[:, 3:7] = a[:, 1:5]
+        r[:, 7], r[:, 8] = a[:, 5] & 0x3FFFFFFF, a[:, 5] >> 30
+        r[:, 9:12] = a[:, 6:9]
+        return n_aln, r
+
+
+def timed_device_steps(leg: DeviceLeg, steps: int, warmup: int, sync_all, world: int, dev, sampler=None):
+    import torch
+    import torch.distributed as dist
+    for _ in range(warmup):
+        leg.step(check_every_batch=True)
+    sync_all()
+    if sampler is not None:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record(leg.stream)
+    for _ in range(steps):
+        launches += leg.step(check_every_batch=False)
+    e1.record(leg.stream)
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    leg.verify_stats()
+    return float(ms.item()), launches
+
+
+def dominant_kernel(leg: DeviceLeg, peak_gbs: float, bound: str):
+    """The per-lane search kernel on its own: one more (untimed) batch with an event behind every launch."""
+    leg.ws.launch_timing(True)
+    leg.batch(0)
+    launch_ms, fast_lookups = leg.ws.launch_times()
+    leg.ws.launch_timing(False)
+    step_ms = sum(t for _, t in launch_ms) or 1e-9
+    search_ms = sum(t for nm, t in launch_ms if nm in ("search1", "search2"))
+    n_search = sum(1 for nm, _ in launch_ms if nm in ("search1", "search2")) or 1
+    dom_bytes = fast_lookups * ALGO_BYTES_PER_LOOKUP
+    achieved = dom_bytes / (search_ms * 1e-3) / 1e9 if search_ms > 0 else 0.0
+    phys = fast_lookups * DEVICE_BYTES_PER_LOOKUP / (search_ms * 1e-3) / 1e9 if search_ms > 0 else 0.0
+    lo, hi = leg.batches[0]
+    return {"bound": bound, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+            "physical": {"bytes_per_lookup": DEVICE_BYTES_PER_LOOKUP, "achieved": phys, "frac": phys / peak_gbs,
+                         "note": "the device layout answers one occ lookup from ONE 32-byte sector (counts + 64 symbols), so at most "
+                                 "32 B per lookup ever cross the memory system; `achieved`/`frac` above use SURVEY.md 8d's 64 B of the "
+                                 "reference layout (two sectors) and can therefore exceed 1"},
+            "kernel": "search_kernel: the per-lane search kernel, pass-1 + pass-2 launches of one batch",
+            "batch_reads": hi - lo, "kernel_launches_per_batch": n_search, "kernel_ms_per_launch": search_ms / n_search,
+            "kernel_share_of_step": search_ms / step_ms,
+            "algorithmic_bytes_per_launch": dom_bytes / n_search, "algorithmic_bytes_per_lookup": ALGO_BYTES_PER_LOOKUP,
+            "kernel_occ_lookups_per_batch": fast_lookups,
+            "launch_ms": [[nm, round(t, 3)] for nm, t in launch_ms]}
+
+
+def ncu_traffic(genome: int, batch_reads: int):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the same workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        for e in (tj if isinstance(tj, list) else [tj]):
+            if int(e.get("genome_bp", 0)) == genome and int(e.get("reads", 0)) == batch_reads:
+                return e.get("dram_bytes_per_launch"), e.get("source"), e
+    except Exception:
+        pass
+    return None, None, None
+
+
+def secondary_configs1(local_rank: int, dev, peaks: dict, args):
+    """configs[1]: 46 Mb genome (both directions L2-resident), 10 M reads, device-resident, with its own roofline."""
+    import torch
+    from hsa_b200 import api, index_build, synth_torch
+    G, n, L = 46_000_003, 10_000_000, args.read_len
+    genome = synth_torch.make_genome(G, GENOME_SEED, dev)
+    host_index = index_build.build_index(genome, device=dev, sa_interval=0)
+    index = api.Index.upload(host_index, local_rank)
+    reads = synth_torch.simulate_reads(genome, n, L, READ_SEED)
+    leg = DeviceLeg(index, reads, n)
+    ms, launches = timed_device_steps(leg, 5, 3, torch.cuda.synchronize, 1, dev)
+    idx_bytes = sum(index.blocks(w)[1] for w in (0, 1))
+    variants = api.random_sector_probe_ex(local_rank, idx_bytes, 64) if not args.no_probe else None
+    peak = max(variants.values()) if variants else peaks.get("hbm_gbs", 6650.0)
+    roof = dominant_kernel(leg, peak, "l2")
+    roof["random_sector_probe"] = {"footprint_index_bytes": idx_bytes, "variants_gbs": variants}
+    roof["peak_kind"] = f"measured live: random 32-byte-sector loads over {idx_bytes / 1e6:.1f} MB (the uploaded index, L2-resident)"
+    tr, src, _ = ncu_traffic(G, n)
+    roof["traffic"], roof["traffic_source"] = tr, src
+    st = leg.stats.cpu().tolist()[0]
+    out = {"workload": f"configs[1]: {G} bp i.i.d. synthetic genome, {n} simulated {L} bp reads, default gap_opt_t, 1 GPU",
+           "value": n * 5 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / 5, "steps": 5, "warmup": 3, "gpu_launches": launches,
+           "aligned_fraction": float((leg.n_aln > 0).sum().item()) / n, "occ_lookups_per_read": st[2] / n,
+           "heavy_searches_handed_to_cooperative_kernel": st[3], "roofline": roof}
+    leg.ws.close()
+    index.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse_args()
     rank, local_rank, world = dist_env()
     import numpy as np
 
-    cfg_name = {46_000_003: "configs[1]", 3_100_000_003: "configs[2] (10 M-read batches)", 4_600_003: "configs[0]-sized genome"}.get(
-        args.genome, "custom")
-    workload = (f"{cfg_name}: {args.genome} bp i.i.d. synthetic genome, {args.reads} simulated {args.read_len} bp "
-                f"reads per GPU per step, default gap_opt_t")
-    config = {"workload": workload, "reads_per_gpu_per_step": args.reads, "genome_bp": args.genome,
-              "read_len": args.read_len, "options": "gap_init_opt defaults (fnr 0.04 -> max_diff 5 @100bp, max_gapo 1)",
-              "parallelism": f"read-sharded x{world}, index replicated", "l2_policy": "inputs larger than L2 "
-              "(reads 1 GB/step + 5.5 GB of per-item rows and ~2 GB of per-worker stack arenas rewritten every step); "
-              "no explicit flush", "step": "whole-read part of bwa_cal_sa_reg_gap (both strand passes); reads without a "
-              "hit are what the host hands to bwt_splice_match (not timed, in either arm)"}
+    L = args.read_len
+    cfg_name = workload_name(args.genome)
+    workload = (f"{cfg_name}: {args.genome} bp i.i.d. synthetic genome, index replicated per GPU, one set of {args.reads_total} "
+                f"simulated {L} bp reads sharded over the GPUs, default gap_opt_t")
+    config = {"workload": workload, "reads_total_per_step": args.reads_total, "batch_reads": args.batch, "genome_bp": args.genome,
+              "read_len": L, "options": "gap_init_opt defaults (fnr 0.04 -> max_diff 5 @100bp, max_gapo 1)",
+              "parallelism": f"one read set, contiguous host shards x{world} (shard_bounds), index replicated (NCCL broadcast)",
+              "l2_policy": "inputs larger than L2 (per batch: 1.25 GB of reads, 6.9 GB of per-item rows, ~2 GB of per-worker stack "
+                           "arenas rewritten; the 3.1 GB index itself is 25x the L2); no explicit flush",
+              "step": "whole-read part of bwa_cal_sa_reg_gap (both strand passes) over the whole read set; reads without a hit "
+                      "are what the host hands to bwt_splice_match (not timed, in either arm)"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        from hsa_b200 import index_build, synth
         import torch
+        from hsa_b200 import index_build, synth_torch
         procs = os.cpu_count() or 1
-        # same generator / seeds as the b200 arm, bounded sample per step
-        dev = "cuda" if torch.cuda.is_available() else "cpu"
-        from hsa_b200 import synth_torch
-        genome = synth_torch.make_genome(args.genome, 1, dev)
-        index = index_build.build_index(genome, device=dev)
-        n_sample = args.cpu_sample or min(args.reads, 40_000 * procs)
-        reads = synth_torch.simulate_reads(genome, n_sample, args.read_len, 1000).cpu().numpy()
-        vals = []
-        for _ in range(args.warmup + args.steps):
-            vals.append(cpu_reference_run(index, reads, n_sample, procs))
-        timed = vals[args.warmup:]
-        secs = sum(v["secs"] for v in timed)
+        dev = "cuda" if torch.cuda.is_available() else "cpu"     # index construction is plumbing, not the timed path
+        genome = synth_torch.make_genome(args.genome, GENOME_SEED, dev)
+        index = index_build.build_index(genome, device=dev, sa_interval=0)
+        n_sample = args.cpu_sample or min(args.reads_total, (20_000 if args.genome > 1_000_000_000 else 40_000) * procs)
+        reads = gen_reads(genome, 0, n_sample, L).cpu().numpy()       # the FIRST n_sample reads of the b200 arm's job
+        del genome
+        with tempfile.TemporaryDirectory() as td:
+            cpu = CpuReference(index, td)
+            runs = [cpu.run(reads, procs, "sample", with_output=False)[0] for _ in range(args.warmup + args.steps)]
+            j1, _ = cpu.run(reads[: min(n_sample, 20_000)], 1, "single", with_output=False)
+        timed = runs[args.warmup:]
+        secs = sum(r["secs"] for r in timed)
         value = n_sample * len(timed) / secs
-        cb = dict(timed[-1]); cb["value"] = value
+        cb = {"value": value, "unit": UNIT, "cores": procs, "kind": "reference", "per_core": value / procs,
+              "sample": f"each step = the first {n_sample} reads of the job through oracle/_ref/hsa_ref whole (the unmodified reference's "
+                        f"bwt_cal_width + bwt_match_gap per read and strand as bwa_cal_sa_reg_gap drives them, no splice fallback), "
+                        f"{procs} forked processes", "aligned": timed[-1]["aligned"],
+              "single_thread": {"value": min(n_sample, 20_000) / j1["secs"], "sample": "20000 reads, 1 process (the reference as it ships)"}}
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / len(timed),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": dict(config, sample_reads_per_step=n_sample), "cpu_baseline": cb,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": config, "sample_reads_per_step": n_sample, "cpu_baseline": cb,
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -184,7 +390,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from hsa_b200 import api, build, index_build, synth_torch
+    from hsa_b200 import api, build, index_build, shard, synth_torch
 
     build.build_native()
     torch.cuda.set_device(local_rank)
@@ -192,22 +398,34 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     # ---- index: built once on rank 0 (torch ops on the GPU), broadcast as device blocks over NCCL ----
     t_idx = time.time()
     if rank == 0:
-        genome = synth_torch.make_genome(args.genome, 1, dev)
-        host_index = index_build.build_index(genome, device=dev)
+        genome = synth_torch.make_genome(args.genome, GENOME_SEED, dev)
+        host_index = index_build.build_index(genome, device=dev, sa_interval=0)
         idx0 = api.Index.upload(host_index, local_rank)
         metas = [idx0.meta(0), idx0.meta(1)]
     else:
         genome, host_index, idx0, metas = None, None, None, [[0] * 7, [0] * 7]
+    index_build_secs = time.time() - t_idx
+    bcast = None
     if world > 1:
         mt = torch.tensor(metas, dtype=torch.int64, device=dev)
         dist.broadcast(mt, 0)
         metas = mt.cpu().tolist()
-        blocks = []
+        sync_all()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        blocks, nbytes_total = [], 0
         for which in (0, 1):
             nbytes = (metas[which][0] // 64 + 1) * 32
+            nbytes_total += nbytes
             if rank == 0:
                 ptr, nb = idx0.blocks(which)
                 assert nb == nbytes
@@ -216,108 +434,96 @@ def main():
                 t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             dist.broadcast(t, 0)
             blocks.append(t)
+        b1.record()
+        torch.cuda.synchronize()
+        bms = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(bms, op=dist.ReduceOp.MAX)
+        bcast = {"index_broadcast_ms": float(bms.item()), "index_broadcast_bytes": nbytes_total,
+                 "index_broadcast_gbs": nbytes_total / (float(bms.item()) * 1e-3) / 1e9}
         index = idx0 if rank == 0 else api.Index.from_blocks(metas[0], metas[1], blocks[0].data_ptr(), blocks[1].data_ptr(), local_rank)
-        # every rank generates its reads from the same genome: broadcast it too (46 MB)
+        # synthetic reads are drawn from the genome: every rank needs it to make its shard (not part of the search path)
         if rank != 0:
             genome = torch.empty(args.genome, dtype=torch.uint8, device=dev)
         dist.broadcast(genome, 0)
     else:
         index = idx0
-    index_secs = time.time() - t_idx
 
-    # ---- synthetic reads of this rank's shard ------------------------------------------------------------
-    n, L = args.reads, args.read_len
-    reads = synth_torch.simulate_reads(genome, n, L, 1000 + rank)
-    codes_dev = reads.reshape(-1)
-    off_dev = (torch.arange(n, device=dev, dtype=torch.int64) * L)
-    len_dev = torch.full((n,), L, dtype=torch.int32, device=dev)
-    opt = api.gap_init_opt()
-    ws = api.DeviceWorkspace(index)
-    aln_cap = 2 * n + 1024
-    n_aln_dev = torch.zeros(n, dtype=torch.int32, device=dev)
-    aln_off_dev = torch.zeros(n, dtype=torch.int64, device=dev)
-    aln_dev = torch.zeros(aln_cap * 9, dtype=torch.int32, device=dev)
-    stats_dev = torch.zeros(8, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream()
+    # ---- this rank's contiguous shard of the one read set (host partition) -----------------------------
+    lo, hi = shard.shard_bounds(args.reads_total, world, align=min(GEN_BLOCK, max(1, args.reads_total // world)))[rank]
+    reads = gen_reads(genome, lo, hi, L)
+    n_local = hi - lo
+    if rank != 0:
+        del genome
+    leg = DeviceLeg(index, reads, args.batch)
 
-    def step_device():
-        ws.whole_reads_device(codes_dev.data_ptr(), off_dev.data_ptr(), len_dev.data_ptr(), n, [L], opt,
-                              n_aln_dev.data_ptr(), aln_off_dev.data_ptr(), aln_dev.data_ptr(), aln_cap,
-                              stats_dev.data_ptr(), stream.cuda_stream)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step_device()
-    sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-        launches += ws.last_launches()
-    e1.record(stream)
-    sync_all()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    stats = stats_dev.cpu().tolist()         # {-, hits, lookups, heavy, bad, pops, steps, unprocessed} of the last step
-    aligned = int((n_aln_dev > 0).sum().item())
-    if stats[1] > aln_cap or stats[4] or stats[7] or stats[3] > n // 4:
-        raise RuntimeError(f"device run left work undone / overflowed its buffers: {stats}")
-    value = world * n * args.steps / (ms_total * 1e-3)
-    kernel_ms = ms_total / args.steps
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, launches = timed_device_steps(leg, args.steps, args.warmup, sync_all, world, dev, sampler)
+    stats = leg.stats.cpu().numpy()
+    aligned = int((leg.n_aln > 0).sum().item())
+    value = args.reads_total * args.steps / (ms_total * 1e-3)
+    ms_per_step = ms_total / args.steps
 
     # ---- end to end through the host-buffer C ABI (pinned host memory in, pinned host results out) ---------
-    # The user-facing call pair hsa_whole_reads_submit / hsa_job_wait, double-buffered: while batch i runs, the
-    # H2D copy of batch i+1 and the D2H copy of batch i-1 use the copy engines.  Every step moves its own inputs
-    # host->device and its own results device->host inside the timed region.
+    # hsa_whole_reads_submit / hsa_job_wait per batch, double-buffered: while batch i runs, the H2D copy of batch i+1 and
+    # the D2H copy of batch i-1 use the copy engines.  Every batch moves its own inputs host->device and its own results
+    # device->host inside the timed region; with N > 1 every batch's results are also gathered to rank 0 (input order).
     codes_host = reads.reshape(-1).cpu().pin_memory()
-    off_host = off_dev.cpu().pin_memory()
-    len_host = len_dev.cpu().pin_memory()
+    off_host = leg.off.cpu().pin_memory()
+    len_host = leg.len.cpu().pin_memory()
+    opt = leg.opt
+    e2e_steps = args.e2e_steps or min(args.steps, 5)
+    gather_bytes = [0]
+
+    def submit(b):
+        blo, bhi = leg.batches[b]
+        return index.whole_reads_submit(codes_host[blo * L: bhi * L], off_host[: bhi - blo], len_host[: bhi - blo], opt)
+
     def e2e_loop(steps):
-        launches, last = 0, None
-        job = index.whole_reads_submit(codes_host, off_host, len_host, opt)
-        for k in range(steps):
-            nxt = index.whole_reads_submit(codes_host, off_host, len_host, opt) if k + 1 < steps else None
-            last = job.wait(copy=False)
-            launches += last.kernel_launches
+        jobs = [b for _ in range(steps) for b in range(len(leg.batches))]
+        n_launch, d2h, last0 = 0, 0, None
+        job = submit(jobs[0])
+        for k, b in enumerate(jobs):
+            nxt = submit(jobs[k + 1]) if k + 1 < len(jobs) else None
+            res = job.wait(copy=False)
+            n_launch += res.kernel_launches
+            d2h += res.n_aln.shape[0] * 12 + int(res.aln.shape[0]) * 36
+            if b == 0:
+                last0 = (res.n_aln.copy(), int(res.occ_lookups), int(res.n_strict))
+            if world > 1:
+                n_all, off_all, a_all = shard.gather_results(res.n_aln, res.aln_off, res.aln, device=dev, dst=0)
+                if rank == 0:
+                    gather_bytes[0] = n_all.nbytes + off_all.nbytes + a_all.nbytes
             job = nxt
         torch.cuda.synchronize()
-        return launches, last
+        return n_launch, d2h, last0
 
-    e2e_loop(max(4, args.warmup))     # warm-up: the job slots' device buffers and the four round-robin pinned result buffers
+    e2e_loop(1)                        # warm-up: job slots' device buffers, the round-robin pinned result buffers, gather buffers
     sync_all()
     t0 = time.perf_counter()
-    e2e_launches, res = e2e_loop(args.steps)
-    d2h = n * 4 + n * 8 + int(res.aln.shape[0]) * 36
+    e2e_launches, d2h_total, last0 = e2e_loop(e2e_steps)
     e2e_secs = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.steps / float(e2e_secs.item())
-    h2d = codes_host.numel() + off_host.numel() * 8 + len_host.numel() * 4
+    e2e_value = args.reads_total * e2e_steps / float(e2e_secs.item())
+    h2d = n_local * (L + 8 + 4)
+    d2h = d2h_total // e2e_steps
     clocks = sampler.stop() if rank == 0 else None
-    strict_reads = int(res.n_strict)
 
-    # ---- parity spot-check inside the bench: device-resident and host-buffer runs agree ------------------
-    same = bool(np.array_equal(n_aln_dev.cpu().numpy(), res.n_aln))
+    # the two entry points agree on batch 0 (n_aln of every read); a difference is a bug, not a statistic
+    blo, bhi = leg.batches[0]
+    if not np.array_equal(leg.n_aln[blo:bhi].cpu().numpy(), last0[0]):
+        raise RuntimeError("hsa_whole_reads_device and hsa_whole_reads disagree on batch 0")
+
+    tot = torch.tensor([aligned, int(stats[:, 2].sum()), int(stats[:, 3].sum()), h2d, d2h], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    aligned_all, lookups_all, heavy_all, h2d_all, d2h_all = [int(x) for x in tot.cpu().tolist()]
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    lookups = int(res.occ_lookups)
-    algo_bytes = lookups * ALGO_BYTES_PER_LOOKUP
-    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -327,58 +533,56 @@ def main():
     idx_bytes = sum(index.blocks(w)[1] for w in (0, 1))
     probe = None
     if not args.no_probe:
-        probe = {"footprint_index_gbs": api.random_sector_probe(local_rank, max(idx_bytes, 1 << 20), 64),
-                 "footprint_8GiB_gbs": api.random_sector_probe(local_rank, 8 << 30, 64)}
+        variants = api.random_sector_probe_ex(local_rank, max(idx_bytes, 1 << 20), 64)
+        probe = {"footprint_index_gbs": max(variants.values()), "footprint_index_bytes": idx_bytes, "variants_gbs": variants}
     peak = probe["footprint_index_gbs"] if probe else peaks.get("hbm_gbs", 6650.0)
-    # ---- the dominant kernel on its own: one more (untimed) step with an event behind every launch -----------
-    ws.launch_timing(True)
-    step_device()
-    launch_ms, fast_lookups = ws.launch_times()
-    ws.launch_timing(False)
-    step_ms = sum(t for _, t in launch_ms) or 1e-9
-    search_ms = sum(t for nm, t in launch_ms if nm in ("search1", "search2"))
-    n_search = sum(1 for nm, _ in launch_ms if nm in ("search1", "search2")) or 1
-    dom_bytes = fast_lookups * ALGO_BYTES_PER_LOOKUP
-    dom_achieved = dom_bytes / (search_ms * 1e-3) / 1e9 if search_ms > 0 else 0.0
-    traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tj = json.load(f)
-        if int(tj.get("genome_bp", 0)) == args.genome and int(tj.get("reads", 0)) == args.reads:   # same workload only
-            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
-    except Exception:
-        pass
-    resident = "L2-resident" if idx_bytes < 100e6 else "HBM-resident, far larger than the 126 MB L2"
-    roofline = {"bound": "hbm", "achieved": dom_achieved, "peak": peak, "unit": "GB/s", "frac": dom_achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "search_kernel<128,5,u32,true>: the per-lane search kernel, pass-1 + pass-2 launches of the step",
-                "kernel_launches_per_step": n_search, "kernel_ms_per_launch": search_ms / n_search,
-                "kernel_share_of_step": search_ms / step_ms,
-                "algorithmic_bytes_per_launch": dom_bytes / n_search, "algorithmic_bytes_per_lookup": ALGO_BYTES_PER_LOOKUP,
-                "kernel_occ_lookups_per_step": fast_lookups,
-                "launch_ms": [[nm, round(t, 3)] for nm, t in launch_ms],
-                "whole_step": {"achieved": achieved, "frac": achieved / peak, "occ_lookups_per_step": lookups,
-                               "lookups_per_read": lookups / n, "ms_per_step": kernel_ms,
-                               "note": "all kernels of the step (width + search + cooperative stage) over the timed region"},
-                "peak_kind": ("measured live: random 32-byte-sector loads over a footprint equal to the uploaded index "
-                              f"({idx_bytes / 1e6:.1f} MB, {resident})" if probe else "MEASURED_PEAKS.json streaming copy"),
-                "hbm_stream_peak_gbs": peaks.get("hbm_gbs"),
-                "frac_of_hbm_stream": dom_achieved / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                "random_sector_probe": probe}
-    cpu_baseline = None
-    if not args.no_cpu_baseline:
+    l2_resident = idx_bytes < 100e6
+    roofline = dominant_kernel(leg, peak, "l2" if l2_resident else "hbm")
+    tr, src, _ = ncu_traffic(args.genome, leg.batches[0][1] - leg.batches[0][0])
+    roofline.update({
+        "traffic": tr, "traffic_source": src,
+        "whole_step": {"achieved": lookups_all * ALGO_BYTES_PER_LOOKUP / (ms_per_step * 1e-3) / 1e9,
+                       "frac": lookups_all * ALGO_BYTES_PER_LOOKUP / (ms_per_step * 1e-3) / 1e9 / (peak * world),
+                       "physical_frac": lookups_all * DEVICE_BYTES_PER_LOOKUP / (ms_per_step * 1e-3) / 1e9 / (peak * world),
+                       "occ_lookups_per_step": lookups_all, "lookups_per_read": lookups_all / args.reads_total,
+                       "ms_per_step": ms_per_step,
+                       "note": "all kernels of the step (width + search + cooperative stage) over the timed region, all GPUs"},
+        "peak_kind": ("measured live: best of the random 32-byte-sector probes over a footprint equal to the uploaded index "
+                      f"({idx_bytes / 1e6:.1f} MB, {'L2-resident' if l2_resident else 'HBM-resident, 25x the 126 MB L2'})"
+                      if probe else "MEASURED_PEAKS.json streaming copy"),
+        "hbm_stream_peak_gbs": peaks.get("hbm_gbs"), "random_sector_probe": probe})
+
+    cpu_baseline, parity = None, None
+    if not args.no_cpu_baseline and world == 1:
         procs = os.cpu_count() or 1
-        n_sample = args.cpu_sample or min(n, 40_000 * procs)
-        cpu_baseline = cpu_reference_run(host_index, reads[:n_sample].cpu().numpy(), n_sample, procs)
+        n_sample = args.cpu_sample or min(leg.batches[0][1], (20_000 if args.genome > 1_000_000_000 else 40_000) * procs)
+        gpu_n, gpu_rows = leg.results_of(0, n_sample)
+        with tempfile.TemporaryDirectory() as td:
+            cpu_baseline, parity = cpu_baseline_block(CpuReference(host_index, td), reads[:n_sample].cpu().numpy(), procs, gpu_n, gpu_rows)
+        if parity["n_aln_mismatch"] or parity["row_mismatch"]:
+            print(json.dumps({"error": "GPU results differ from the reference", "parity": parity}), file=sys.stderr)
+            raise RuntimeError("parity failure against oracle/_ref/hsa_ref")
+
+    secondary = None
+    if world == 1 and not args.no_secondary and args.genome != 46_000_003:
+        leg.ws.close()
+        del leg, reads, codes_host
+        index.close()
+        torch.cuda.empty_cache()
+        secondary = secondary_configs1(local_rank, dev, peaks, args)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
+                    "steps": e2e_steps, "gathered_to_rank0_bytes_per_batch": gather_bytes[0] if world > 1 else 0,
+                    "path": "hsa_whole_reads_submit / hsa_job_wait per batch from pinned host buffers, double-buffered"
+                            + ("; every batch's results gathered to rank 0 over NCCL in input order" if world > 1 else "")},
             "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
-            "aligned_fraction": aligned / n, "heavy_searches_handed_to_cooperative_kernel": strict_reads,
-            "device_vs_host_path_identical": same, "index_build_secs": index_secs}
+            "cpu_baseline": cpu_baseline, "parity": parity, "secondary": secondary,
+            "aligned_fraction": aligned_all / args.reads_total,
+            "heavy_searches_handed_to_cooperative_kernel": heavy_all,
+            "index_build_secs": index_build_secs, "index_broadcast": bcast}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

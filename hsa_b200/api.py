@@ -125,6 +125,7 @@ def lib():
                                          C.c_void_p, C.c_size_t, C.POINTER(GapOpt), C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.hsa_random_sector_probe.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+    L.hsa_random_sector_probe_ex.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.c_int]
     L.hsa_index_attach_sa.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]
     L.hsa_sa_values.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint64)]
     L.hsa_sa_values_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -445,3 +446,13 @@ def random_sector_probe(device: int, footprint_bytes: int, iters: int = 64) -> f
     g = C.c_double()
     _check(lib().hsa_random_sector_probe(device, footprint_bytes, iters, C.byref(g)))
     return g.value
+
+
+PROBE_VARIANTS = ("chains4_2x128b", "mlp4_256b", "mlp8_256b", "mlp16_256b", "mix8_256b+32b")
+
+
+def random_sector_probe_ex(device: int, footprint_bytes: int, iters: int = 64) -> dict:
+    """Every probe variant's GB/s (see include/hsa_b200.h); the roofline peak is the best of them."""
+    v = (C.c_double * len(PROBE_VARIANTS))()
+    _check(lib().hsa_random_sector_probe_ex(device, footprint_bytes, iters, v, len(PROBE_VARIANTS)))
+    return {k: float(x) for k, x in zip(PROBE_VARIANTS, v)}

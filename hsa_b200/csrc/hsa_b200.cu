@@ -312,6 +312,33 @@ __global__ void probe_kernel_mlp(const uint4 *buf, uint64_t n_sectors, int iters
     if (acc == 0xDEADBEEFu) atomicAdd(sink, 1ull);
 }
 
+// Third probe variant, shaped like sa_kernel's traffic: per iteration one 256-bit sector load and one 4-byte load from
+// another random sector (an SA sample), UNROLL of each in flight per thread.  Counts two sectors per pair.
+template <int UNROLL>
+__global__ void probe_kernel_mix(const uint4 *buf, uint64_t n_sectors, int iters, unsigned long long *sink)
+{
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t s = tid * 0x9E3779B97F4A7C15ull + 0x7654321ull;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t v[UNROLL][8], u[UNROLL];
+#pragma unroll
+        for (int c = 0; c < UNROLL; ++c) {
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            const uint64_t sec = __umul64hi(s, n_sectors);
+            asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[c][0]), "=r"(v[c][1]), "=r"(v[c][2]), "=r"(v[c][3]), "=r"(v[c][4]), "=r"(v[c][5]), "=r"(v[c][6]), "=r"(v[c][7])
+                         : "l"(buf + 2 * sec));
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            const uint64_t sec2 = __umul64hi(s, n_sectors);
+            u[c] = __ldg(reinterpret_cast<const uint32_t *>(buf + 2 * sec2) + (c & 7));
+        }
+#pragma unroll
+        for (int c = 0; c < UNROLL; ++c) acc += v[c][0] ^ v[c][7] ^ u[c];
+    }
+    if (acc == 0xDEADBEEFu) atomicAdd(sink, 1ull);
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -1716,9 +1743,13 @@ extern "C" int hsa_workspace_check(hsa_workspace_t *ws, uint64_t stats_out[8])
 }
 
 // ---------------------------------------------------------------------------------------------- roofline probe
-extern "C" int hsa_random_sector_probe(int device, size_t footprint_bytes, int iters, double *gbs_out)
+// Variants, all at full occupancy over the same buffer: [0] four dependent chains per thread (two 16-byte loads per
+// sector), [1..3] 4 / 8 / 16 independent 256-bit loads in flight per thread, [4] the sa_kernel-shaped mix (a 256-bit load
+// and a 4-byte load per pair, 8 pairs in flight).  gbs_out[i] = sectors * 32 B / time of variant i, best of three runs.
+enum { PROBE_VARIANTS = 5 };
+extern "C" int hsa_random_sector_probe_ex(int device, size_t footprint_bytes, int iters, double *gbs_out, int n_out)
 {
-    if (!gbs_out || footprint_bytes < 4096 || iters < 1) return fail(HSA_E_ARG, "bad argument");
+    if (!gbs_out || n_out < 1 || footprint_bytes < 4096 || iters < 1) return fail(HSA_E_ARG, "bad argument");
     CU(cudaSetDevice(device));
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
@@ -1730,44 +1761,42 @@ extern "C" int hsa_random_sector_probe(int device, size_t footprint_bytes, int i
     CU(cudaMemset(sink, 0, 8));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    const int CH = 4, block = 256;
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_kernel<CH>, block, 0));
-    int grid = sms * occ;
-    probe_kernel<CH><<<grid, block>>>(buf, n_sectors, 8, sink);          // warm-up (also pulls an L2-sized set in)
-    CU(cudaGetLastError());
-    double best = 0;
-    for (int rep = 0; rep < 3; ++rep) {
-        CU(cudaEventRecord(e0));
-        probe_kernel<CH><<<grid, block>>>(buf, n_sectors, iters, sink);
-        CU(cudaEventRecord(e1));
-        CU(cudaEventSynchronize(e1));
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, e0, e1));
-        double bytes = (double)grid * block * CH * (double)iters * 32.0;
-        best = std::max(best, bytes / (ms * 1e-3) / 1e9);
-    }
-    // independent 256-bit loads, four / eight in flight per thread
-    for (int variant = 0; variant < 2; ++variant) {
-        const int UN = variant == 0 ? 4 : 8;
-        const void *fn = variant == 0 ? (const void *)probe_kernel_mlp<4> : (const void *)probe_kernel_mlp<8>;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, block, 0));
-        grid = sms * occ;
-        const int it2 = iters;
-        void *args[] = {(void *)&buf, (void *)&n_sectors, (void *)&it2, (void *)&sink};
+    const int block = 256;
+    struct V { const void *fn; int per_iter; } vs[PROBE_VARIANTS] = {
+        {(const void *)probe_kernel<4>, 4}, {(const void *)probe_kernel_mlp<4>, 4}, {(const void *)probe_kernel_mlp<8>, 8},
+        {(const void *)probe_kernel_mlp<16>, 16}, {(const void *)probe_kernel_mix<8>, 16}};
+    for (int v = 0; v < PROBE_VARIANTS && v < n_out; ++v) {
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vs[v].fn, block, 0));
+        const int grid = sms * std::max(occ, 1);
+        int it_warm = 4, it_run = iters;
+        void *aw[] = {(void *)&buf, (void *)&n_sectors, (void *)&it_warm, (void *)&sink};
+        void *ar[] = {(void *)&buf, (void *)&n_sectors, (void *)&it_run, (void *)&sink};
+        CU(cudaLaunchKernel(vs[v].fn, dim3(grid), dim3(block), aw, 0, nullptr));       // warm-up (pulls an L2-sized set in)
+        double best = 0;
         for (int rep = 0; rep < 3; ++rep) {
             CU(cudaEventRecord(e0));
-            CU(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, 0, nullptr));
+            CU(cudaLaunchKernel(vs[v].fn, dim3(grid), dim3(block), ar, 0, nullptr));
             CU(cudaEventRecord(e1));
             CU(cudaEventSynchronize(e1));
             float ms = 0;
             CU(cudaEventElapsedTime(&ms, e0, e1));
-            double bytes = (double)grid * block * UN * (double)iters * 32.0;
+            const double bytes = (double)grid * block * vs[v].per_iter * (double)iters * 32.0;
             best = std::max(best, bytes / (ms * 1e-3) / 1e9);
         }
+        gbs_out[v] = best;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(buf); cudaFree(sink);
-    *gbs_out = best;
+    return HSA_OK;
+}
+
+extern "C" int hsa_random_sector_probe(int device, size_t footprint_bytes, int iters, double *gbs_out)
+{
+    if (!gbs_out) return fail(HSA_E_ARG, "bad argument");
+    double v[PROBE_VARIANTS] = {0, 0, 0, 0, 0};
+    int rc = hsa_random_sector_probe_ex(device, footprint_bytes, iters, v, PROBE_VARIANTS);
+    if (rc) return rc;
+    *gbs_out = *std::max_element(v, v + PROBE_VARIANTS);
     return HSA_OK;
 }

@@ -54,27 +54,95 @@ def broadcast_bytes(t: torch.Tensor | None, nbytes: int, src: int, device) -> to
     return t
 
 
-def gather_in_input_order(n_aln: np.ndarray, aln: np.ndarray, dst: int = 0):
+def gather_in_input_order(n_aln: np.ndarray, aln: np.ndarray, dst: int = 0, device=None):
     """Gather per-rank results (n_aln[n_local], hits[(sum n_aln), 9] in item order) to rank `dst`, concatenated
     in input order (= rank order, because shards are contiguous).  Returns (n_aln_all, aln_all) on dst, else
-    (None, None).  Uses gather_object-free fixed-width exchanges: sizes first, then padded payloads."""
+    (None, None).  Fixed-width exchanges: sizes first, then payloads padded to the largest shard.
+    `device`: stage the payloads through this device (the NCCL backend moves device tensors: host results -> HBM ->
+    NVLink -> rank dst -> host); None = host tensors (gloo)."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    sizes = torch.tensor([int(n_aln.shape[0]), int(aln.shape[0])], dtype=torch.int64)
-    all_sizes = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dev = torch.device("cpu") if device is None else torch.device(device)
+    sizes = torch.tensor([int(n_aln.shape[0]), int(aln.shape[0])], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
-    max_n = max(int(s[0]) for s in all_sizes)
-    max_a = max(int(s[1]) for s in all_sizes)
-    pn = torch.zeros(max(max_n, 1), dtype=torch.int32)
-    pn[: n_aln.shape[0]] = torch.from_numpy(np.ascontiguousarray(n_aln, dtype=np.int32))
-    pa = torch.zeros((max(max_a, 1), 9), dtype=torch.int64)
+    all_sizes = [s.cpu().tolist() for s in all_sizes]
+    max_n = max(1, max(s[0] for s in all_sizes))
+    max_a = max(1, max(s[1] for s in all_sizes))
+    pn = torch.zeros(max_n, dtype=torch.int32, device=dev)
+    pn[: n_aln.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(n_aln, dtype=np.int32)), non_blocking=True)
+    pa = torch.zeros((max_a, 9), dtype=torch.int32, device=dev)
     if aln.shape[0]:
-        pa[: aln.shape[0]] = torch.from_numpy(np.ascontiguousarray(aln).astype(np.int64))
+        pa[: aln.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(aln, dtype=np.uint32).view(np.int32)), non_blocking=True)
     gn = [torch.zeros_like(pn) for _ in range(world)] if rank == dst else None
     ga = [torch.zeros_like(pa) for _ in range(world)] if rank == dst else None
     dist.gather(pn, gn, dst=dst)
     dist.gather(pa, ga, dst=dst)
     if rank != dst:
         return None, None
-    n_all = np.concatenate([gn[r][: int(all_sizes[r][0])].numpy() for r in range(world)])
-    a_all = np.concatenate([ga[r][: int(all_sizes[r][1])].numpy().astype(np.uint32) for r in range(world)])
+    n_all = torch.cat([gn[r][: all_sizes[r][0]] for r in range(world)]).cpu().numpy()
+    a_all = torch.cat([ga[r][: all_sizes[r][1]] for r in range(world)]).cpu().numpy().view(np.uint32)
     return n_all, a_all
+
+
+_pinned_cache: dict = {}
+
+
+def _pinned(name: str, n: int, dtype, cols: int = 0) -> torch.Tensor:
+    """A re-used pinned host buffer of at least n rows (D2H into pageable memory runs at a fraction of the PCIe rate)."""
+    t = _pinned_cache.get(name)
+    if t is None or t.shape[0] < n or t.dtype != dtype:
+        shape = (n + n // 8 + 16, cols) if cols else (n + n // 8 + 16,)
+        t = torch.empty(shape, dtype=dtype)
+        if torch.cuda.is_available():
+            t = t.pin_memory()
+        _pinned_cache[name] = t
+    return t[:n]
+
+
+def gather_results(n_aln: np.ndarray, aln_off: np.ndarray, aln: np.ndarray, device=None, dst: int = 0):
+    """Ordered gather of the flat result of a batch as the C ABI returns it (hsa_result_t: n_aln[n_local], aln_off[n_local]
+    = first hit of the item in this rank's hit arena, aln[(hits), 9]) to rank `dst`: (n_aln of all reads in input order,
+    aln_off rebased into the concatenated arena, the concatenated arena) on dst, (None, None, None) elsewhere.  The arenas
+    are moved as they are -- hits of one item stay contiguous and in discovery order, items are addressed through aln_off.
+    `device`: stage through this device (NCCL); on dst the outputs land in re-used pinned host buffers (valid until the
+    next call)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cpu") if device is None else torch.device(device)
+    sizes = torch.tensor([int(n_aln.shape[0]), int(aln.shape[0])], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [s.cpu().tolist() for s in all_sizes]
+    max_n = max(1, max(s[0] for s in all_sizes))
+    max_a = max(1, max(s[1] for s in all_sizes))
+    pn = torch.zeros(max_n, dtype=torch.int32, device=dev)
+    po = torch.zeros(max_n, dtype=torch.int64, device=dev)
+    pa = torch.zeros((max_a, 9), dtype=torch.int32, device=dev)
+    nl, al = int(n_aln.shape[0]), int(aln.shape[0])
+    if nl:
+        pn[:nl].copy_(torch.from_numpy(np.ascontiguousarray(n_aln, dtype=np.int32)), non_blocking=True)
+        po[:nl].copy_(torch.from_numpy(np.ascontiguousarray(aln_off).view(np.int64)), non_blocking=True)
+    if al:
+        pa[:al].copy_(torch.from_numpy(np.ascontiguousarray(aln, dtype=np.uint32).view(np.int32)), non_blocking=True)
+    gn = [torch.zeros_like(pn) for _ in range(world)] if rank == dst else None
+    go = [torch.zeros_like(po) for _ in range(world)] if rank == dst else None
+    ga = [torch.zeros_like(pa) for _ in range(world)] if rank == dst else None
+    dist.gather(pn, gn, dst=dst)
+    dist.gather(po, go, dst=dst)
+    dist.gather(pa, ga, dst=dst)
+    if rank != dst:
+        return None, None, None
+    base, offs = 0, []
+    for r in range(world):                                   # rebase every rank's offsets into the concatenated arena
+        offs.append(go[r][: all_sizes[r][0]] + base)
+        base += all_sizes[r][1]
+    n_tot = sum(s[0] for s in all_sizes)
+    out_n = _pinned("n_aln", n_tot, torch.int32)
+    out_o = _pinned("aln_off", n_tot, torch.int64)
+    out_a = _pinned("aln", max(base, 1), torch.int32, 9)[:base]
+    out_n.copy_(torch.cat([gn[r][: all_sizes[r][0]] for r in range(world)]), non_blocking=True)
+    out_o.copy_(torch.cat(offs), non_blocking=True)
+    if base:
+        out_a.copy_(torch.cat([ga[r][: all_sizes[r][1]] for r in range(world)]), non_blocking=True)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    return out_n.numpy(), out_o.numpy().view(np.uint64), out_a.numpy().view(np.uint32)

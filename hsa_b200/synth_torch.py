@@ -46,3 +46,23 @@ def simulate_reads(genome: torch.Tensor, n: int, length: int, seed: int, sub_rat
             r = torch.where(isn, torch.full_like(r, 4), r)
         out[lo:lo + m] = r
     return out
+
+
+def simulate_spliced_reads(genome: torch.Tensor, n: int, length: int, seed: int, sub_rate: float = 0.01,
+                           min_intron: int = 50, max_intron: int = 50_000) -> torch.Tensor:
+    """uint8 [n, length] RNA-seq-style reads (BASELINE.json configs[3]): two exons joined across an intron of
+    min_intron..max_intron bases, the junction in the middle third of the read, substitutions, 50 % reverse-complemented.
+    bwt_splice_match cuts such a read into three seed segments of length // 3 bases (bwtgap.c:763-764, 800-802)."""
+    dev = genome.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    G = genome.shape[0]
+    start = torch.randint(0, G - max_intron - 2 * length, (n, 1), device=dev, generator=gen)
+    split = torch.randint(length // 3, length - length // 3, (n, 1), device=dev, generator=gen)
+    intron = torch.randint(min_intron, max_intron, (n, 1), device=dev, generator=gen)
+    j = torch.arange(length, device=dev)[None, :]
+    reads = genome[start + j + torch.where(j >= split, intron, torch.zeros_like(intron))]
+    sub = torch.rand((n, length), device=dev, generator=gen) < sub_rate
+    reads = torch.where(sub, (reads + torch.randint(1, 4, (n, length), dtype=torch.uint8, device=dev, generator=gen)) & 3, reads)
+    rc = torch.rand((n, 1), device=dev, generator=gen) < 0.5
+    return torch.where(rc, 3 - torch.flip(reads, dims=[1]), reads)

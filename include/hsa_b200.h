@@ -237,11 +237,13 @@ int  hsa_sa_locate(const hsa_index_t *idx, const uint32_t *sa_index, size_t n, u
                    uint32_t *ori_pos_out);
 
 /* ---- roofline probe: random 32-byte-sector loads over `footprint_bytes` ----
- * Reports the best achieved GB/s (sectors * 32 B / time) at full occupancy of two variants: four dependent chains per
- * thread with two 16-byte loads per sector, and four independent 256-bit loads in flight per thread (the kernels' own
- * load shape, multiply-shift sector choice).  Used only by bench.py / tools/bench_sa.py to establish the random-access
- * denominator on this GPU. */
+ * The random-access denominator on this GPU: achieved GB/s (sectors * 32 B / time) at full occupancy of five access
+ * shapes -- [0] four dependent chains per thread with two 16-byte loads per sector, [1..3] 4 / 8 / 16 independent 256-bit
+ * loads in flight per thread (the kernels' own load shape, multiply-shift sector choice), [4] the SA kernel's mix (a
+ * 256-bit load plus a 4-byte load from another sector).  hsa_random_sector_probe returns the best of them, _ex all of
+ * them (gbs_out[0..min(n_out,5))).  Used only by bench.py / tools/ to establish the roofline. */
 int  hsa_random_sector_probe(int device, size_t footprint_bytes, int iters, double *gbs_out);
+int  hsa_random_sector_probe_ex(int device, size_t footprint_bytes, int iters, double *gbs_out, int n_out);
 
 #ifdef __cplusplus
 }

@@ -23,8 +23,10 @@ REF_GPU = os.path.join(ROOT, "oracle", "_ref", "hsa_ref_gpu")
 
 @pytest.fixture(scope="module")
 def workdir(tmp_path_factory):
-    if not (os.path.exists(REF) and os.path.exists(REF_GPU)):
-        pytest.skip("oracle/_ref binaries are not present (built only where /root/reference exists)")
+    # never skip on a GPU run: without these binaries the drop-in boundary would go unchecked
+    assert os.path.exists(REF) and os.path.exists(REF_GPU), (
+        "oracle/_ref/hsa_ref[_gpu] are missing: build them where the reference sources exist "
+        "(python -c 'import __graft_entry__ as g; g.build()' runs make -C oracle ref shim); they travel with the snapshot")
     d = tmp_path_factory.mktemp("shim")
     g = synth.make_genome(1200011, seed=41)
     synth.write_fasta(str(d / "g.fa"), g)

@@ -68,10 +68,23 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         rows9 = np.zeros((rows.shape[0], 9), dtype=np.uint32)
         rows9[:, :] = rows[:, [0, 3, 4, 5, 6, 8, 9, 10, 11]]            # any fixed 9 columns: payload identity is what is checked
         n_all, a_all = shard.gather_in_input_order(n_aln, rows9, dst=0)
+        # the C ABI's flat result form (arena + per-item offsets; arena order arbitrary): reverse this rank's arena
+        cnt = n_aln.astype(np.int64)
+        first = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+        arena = rows9[::-1].copy()
+        aln_off = (rows9.shape[0] - first - cnt).astype(np.uint64)
+        for i in np.nonzero(cnt > 1)[0]:                               # hits of one item stay in discovery order
+            o, c = int(aln_off[i]), int(cnt[i])
+            arena[o:o + c] = arena[o:o + c][::-1]
+        n2, off2, a2 = shard.gather_results(n_aln, aln_off, arena, dst=0)
         if rank == 0:
             exp_n, exp_rows = g.expected("cfg2_100bp_default", "whole")
+            exp9 = exp_rows[:, [0, 3, 4, 5, 6, 8, 9, 10, 11]]
             assert np.array_equal(n_all, exp_n)
-            assert np.array_equal(a_all, exp_rows[:, [0, 3, 4, 5, 6, 8, 9, 10, 11]])
+            assert np.array_equal(a_all, exp9)
+            assert np.array_equal(n2, exp_n)
+            idx = np.concatenate([np.arange(int(o), int(o) + int(c)) for o, c in zip(off2, n2) if c])
+            assert np.array_equal(a2[idx], exp9)
             open(os.path.join(out_dir, "ok"), "w").write("ok")
     finally:
         dist.destroy_process_group()
