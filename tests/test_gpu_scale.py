@@ -145,7 +145,7 @@ def test_device_resident_entry_point_46mb_vs_reference_binary(g46, monkeypatch, 
     try:
         n_aln, rows, stats = run.run()
         assert np.array_equal(n_aln, exp_n)
-        assert np.array_equal(el.aln9_to_rows12(rows), exp_rows)
+        assert np.array_equal(rows, exp_rows)
         assert stats[2] == exp_lk and stats[7] == 0
     finally:
         run.ws.close()
@@ -163,7 +163,7 @@ def test_device_resident_keep_gape_46mb_vs_reference_binary(g46):
     run = _DeviceRun(g46.ix, reads_t, api.gap_init_opt(), keep_gape=1)
     try:
         n_aln, rows, stats = run.run()
-        assert np.array_equal(n_aln, exp_n) and np.array_equal(el.aln9_to_rows12(rows), exp_rows) and stats[2] == exp_lk
+        assert np.array_equal(n_aln, exp_n) and np.array_equal(rows, exp_rows) and stats[2] == exp_lk
     finally:
         run.ws.close()
 
@@ -233,7 +233,7 @@ def test_whole_reads_3gb_vs_reference_binary():
         run = _DeviceRun(s.ix, reads_t, api.gap_init_opt())
         try:
             n_aln, rows, stats = run.run()
-            assert np.array_equal(n_aln, exp_n) and np.array_equal(el.aln9_to_rows12(rows), exp_rows) and stats[2] == exp_lk
+            assert np.array_equal(n_aln, exp_n) and np.array_equal(rows, exp_rows) and stats[2] == exp_lk
         finally:
             run.ws.close()
         # spliced reads at this size too (configs[3] names the 3.1 Gb genome): 20 k reads -> 120 k seed searches
