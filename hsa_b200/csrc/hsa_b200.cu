@@ -938,6 +938,7 @@ struct Batch {                      // everything one batch needs, device pointe
     const uint64_t *read_off = nullptr; const uint32_t *read_len = nullptr;
     int32_t *n_aln = nullptr; uint64_t *aln_off = nullptr; uint32_t *aln = nullptr; uint64_t aln_cap = 0;
     u32x2 *width_out = nullptr; int32_t *bid_out = nullptr;
+    const uint8_t *rows_host = nullptr; size_t rows_host_bytes = 0;   // per-call form: the caller's widths as one ready-made row
 };
 
 static void trace_mark(hsa_workspace *ws, const char *name, cudaStream_t stream)
@@ -1065,7 +1066,7 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
         if ((rc = coop_scratch_alloc(pipe, grid_full * (block / 32), (uint32_t)env_long("HSA_B200_COOP_CHUNKS", 2048)))) return rc;
     } else if ((rc = scratch_alloc(pipe.sc, grid_full * block, large ? (1u << 18) : ws->arena_cap, large ? 4096u : ws->hit_cap,
                                    large ? 8u : 4u))) return rc;
-    if ((rc = ensure(pipe.rows, pipe.rows_cap, (size_t)n_work * P.row_stride))) return rc;
+    if ((rc = ensure(pipe.rows, pipe.rows_cap, std::max((size_t)n_work * P.row_stride, b.rows_host_bytes)))) return rc;
     if (b.kind == KIND_WHOLE && (rc = ensure(pipe.next_list, pipe.next_cap, (size_t)n_work + 1))) return rc;
 
     unsigned long long *slots = ws->counters + CNT_PIPE0 + 4 * pipe_slot;
@@ -1084,9 +1085,14 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     const uint32_t wgrid = std::max<uint32_t>(1, std::min<uint32_t>((n_work + 255) / 256, (uint32_t)ix->sm_count * 8));
     void *args[] = {(void *)&P};
     const char *nm1 = large ? "search1L" : coop ? "search1C" : "search1", *nm2 = large ? "search2L" : coop ? "search2C" : "search2";
-    width_kernel<<<wgrid, 256, P.smem_opts_bytes, stream>>>(P);
-    CU(cudaGetLastError());
-    ++ws->last_launches; trace_mark(ws, "width1", stream);
+    if (b.rows_host) {
+        // hsa_match_gap_call: the caller computed the widths (they are arguments of bwt_match_gap): no width pass
+        CU(cudaMemcpyAsync(pipe.rows, b.rows_host, b.rows_host_bytes, cudaMemcpyHostToDevice, stream));
+    } else {
+        width_kernel<<<wgrid, 256, P.smem_opts_bytes, stream>>>(P);
+        CU(cudaGetLastError());
+        ++ws->last_launches; trace_mark(ws, "width1", stream);
+    }
     if (b.kind == KIND_WIDTH) return HSA_OK;
     CU(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream));
     ++ws->last_launches; trace_mark(ws, nm1, stream);
@@ -1572,6 +1578,77 @@ extern "C" int hsa_match_gap_batch(const hsa_index_t *ix, const uint8_t *codes, 
     b.n_opts = (uint32_t)n_opts; b.codes = ws->codes_dev; b.tasks = ws->tasks_dev;
     if ((rc = job_launch(j))) { job_release(j); return rc; }
     return hsa_job_wait(j, res);
+}
+
+// bwt_match_gap itself (bwtgap.h:26), one call: the caller's width arrays are arguments (in/out), exactly as in bwt_aux_t.
+extern "C" int hsa_match_gap_call(const hsa_index_t *ix, const uint8_t *seq, uint32_t len, hsa_width_t *width_back,
+                                  hsa_width_t *width_seed, const hsa_gap_opt_t *opt, int *n_aln_out, hsa_aln1_t **aln_out)
+{
+    if (!ix || !seq || !len || !width_back || !opt || !n_aln_out || !aln_out) return fail(HSA_E_ARG, "null / empty argument");
+    if (len > 4095) return fail(HSA_E_ARG, "sequences longer than 4095 bases are not supported");
+    uint32_t seed_mode = HSA_SEED_NONE;
+    if (width_seed == width_back) {
+        if (opt->seed_len != (int)len) return fail(HSA_E_ARG, "width_seed aliasing width_back needs opt->seed_len == len (bwtgap.c:802, :809)");
+        seed_mode = HSA_SEED_ALIAS;
+    } else if (width_seed && opt->seed_len > 0 && (uint32_t)opt->seed_len < len) seed_mode = HSA_SEED_TAIL;   // bwtaln.c:344-346
+    // (width_seed with seed_len >= len and no aliasing: the reference reads it out of bounds, SURVEY.md hazard 3 -> unseeded)
+    hsa_job *j; int rc;
+    if ((rc = job_begin(ix, &j))) return rc;
+    hsa_workspace *ws = j->ws; Batch &b = j->b;
+    struct Rel { hsa_job *j; bool armed; ~Rel() { if (armed) job_release(j); } } rel{j, true};
+    std::vector<hsa_gap_opt_t> ov(1, *opt);
+    if ((rc = upload_opts(ws, ov, len, &b, nullptr, j->ix->h2d)) || (rc = ensure(ws->codes_dev, ws->codes_cap, (size_t)len + 16)) ||
+        (rc = ensure(ws->tasks_dev, ws->tasks_cap, 1)) || (rc = ensure(ws->width_out_dev, ws->width_out_cap, (size_t)len + 1))) return rc;
+    Task t; memset(&t, 0, sizeof(t));
+    t.read_off = 0; t.read_len = len; t.strand = 0; t.sub_off = 0; t.len = len; t.wsrc_off = 0; t.seed_mode = seed_mode; t.opt_idx = 0;
+    CU(cudaMemcpyAsync(ws->codes_dev, seq, len, cudaMemcpyHostToDevice, j->ix->h2d));
+    CU(cudaMemcpyAsync(ws->tasks_dev, &t, sizeof(t), cudaMemcpyHostToDevice, j->ix->h2d));
+    CU(cudaStreamSynchronize(j->ix->h2d));                       // `t` lives on this stack frame
+    b.kind = KIND_TASKS; b.n_groups = 1; b.n_items = 1; b.max_len = len; b.n_opts = 1;
+    b.codes = ws->codes_dev; b.tasks = ws->tasks_dev; b.width_out = ws->width_out_dev;
+    // the caller's widths as the item's row (layout: hsa_core.cuh Params::rows)
+    Params P; Variant v; uint32_t seed_cap;
+    if ((rc = batch_params(ws, b, P, v, seed_cap))) return rc;
+    std::vector<uint8_t> row(P.row_stride, 0);
+    uint32_t *w = reinterpret_cast<uint32_t *>(row.data());
+    uint32_t w_prev = 0xFFFFFFFFu;
+    for (uint32_t i = 0; i <= len; ++i) {
+        w[i] = width_back[i].w;
+        row[P.row_bid_off + i] = bound_byte((uint32_t)width_back[i].bid, width_back[i].w, w_prev);
+        w_prev = width_back[i].w;
+    }
+    if (seed_mode == HSA_SEED_TAIL) {
+        w_prev = 0xFFFFFFFFu;
+        for (uint32_t i = 0; i <= (uint32_t)opt->seed_len; ++i) {
+            row[P.row_seed_off + i] = bound_byte((uint32_t)width_seed[i].bid, width_seed[i].w, w_prev);
+            w_prev = width_seed[i].w;
+        }
+    }
+    b.rows_host = row.data(); b.rows_host_bytes = row.size();
+    if ((rc = job_launch(j))) return rc;
+    hsa_result_t res; memset(&res, 0, sizeof(res));
+    rel.armed = false;
+    rc = hsa_job_wait(j, &res);                                  // releases the job
+    if (rc) { hsa_result_free(&res); return rc; }
+    // results as the reference returns them: a malloc-family array of at least 10 zero-filled entries (bwtgap.c:137-138)
+    const int n = res.n_aln[0];
+    hsa_aln1_t *out = (hsa_aln1_t *)calloc((size_t)(n < 10 ? 10 : n), sizeof(hsa_aln1_t));
+    if (!out) { hsa_result_free(&res); return fail(HSA_E_NOMEM, "calloc failed"); }
+    if (n) memcpy(out, res.aln + res.aln_off[0], (size_t)n * sizeof(hsa_aln1_t));
+    hsa_result_free(&res);
+    // width_back after gap_shadow (bids beyond the device's 6-bit field were never touched by it: keep the caller's)
+    std::vector<u32x2> wb((size_t)len + 1);
+    CU(cudaSetDevice(ix->device));
+    if (cudaMemcpy(wb.data(), ws->width_out_dev, wb.size() * sizeof(u32x2), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        free(out); return fail(HSA_E_CUDA, "D2H copy of the widths failed");
+    }
+    for (uint32_t i = 0; i <= len; ++i) {
+        const bool aliased_seed = false; (void)aliased_seed;
+        width_back[i].w = wb[i].x;
+        if (wb[i].y < 63u) width_back[i].bid = (int)wb[i].y;
+    }
+    *n_aln_out = n; *aln_out = out;
+    return HSA_OK;
 }
 
 extern "C" int hsa_whole_reads_submit(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len,

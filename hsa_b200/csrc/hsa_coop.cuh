@@ -713,6 +713,10 @@ HSA_HD void coop_run(const Params &P, CoopWarp &sh, uint8_t *bids, const CoopScr
                         }
                     }
                     P.n_aln[sh.out_idx] = (int32_t)n; P.aln_off[sh.out_idx] = off; P.status[sh.out_idx] = stt;
+                    if (P.kind == KIND_TASKS && P.width_out) {            // per-call form: see Worker::do_end
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>(sh.row);
+                        for (uint32_t i = 0; i <= sh.len; ++i) { u32x2 v; v.x = w[i]; v.y = bids[i] & 63u; P.width_out[i] = v; }
+                    }
                 }
             }
         }

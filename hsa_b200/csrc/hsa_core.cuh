@@ -63,6 +63,7 @@ extern __shared__ __align__(16) unsigned char hsa_smem[];
 static thread_local unsigned char *hsa_smem_host = nullptr;
 #define HSA_SMEM hsa_smem_host
 static unsigned long long hsa_host_pair_count = 0, hsa_host_pair_same_sector = 0;   // emulation statistics
+static unsigned long long hsa_host_hist[3][2][64];     // emulation statistics: lookup pairs by kind {expand, exact, materialise} x {two sectors, one} x depth
 #endif
 
 namespace hsa {
@@ -975,6 +976,7 @@ struct Worker {
         ld_sector(B.blocks + 2 * (size_t)(pl >> 6), lc, lw);
 #if !defined(__CUDA_ARCH__)
         ++hsa_host_pair_count; hsa_host_pair_same_sector += (pk >> 6) == (pl >> 6);    // emulation only: SURVEY 8d's deduplicated figure
+        { const uint32_t dp = len - ci > 63u ? 63u : len - ci; ++hsa_host_hist[pend ? 2 : exact ? 1 : 0][(pk >> 6) == (pl >> 6)][dp]; }
 #endif
         // i: index of the base the lookup extends by.  For a pending child the lookup is the PARENT's: deletion
         // children have ci == the parent's pre-decrement i, mismatch children ci == its post-decrement i.
@@ -1229,6 +1231,12 @@ struct Worker {
         }
         stat_add(STAT_LOOKUPS, mine + ((P.kind == KIND_WHOLE && P.pass == 2) ? P.aln_off[out_idx] : 0ull));
         finish_item(out_idx, n_hits, strand);
+        if (P.kind == KIND_TASKS && P.width_out) {
+            // per-call form (hsa_match_gap_call): width_back is an in/out argument of bwt_match_gap -- gap_shadow rewrites
+            // it in place (bwtgap.c:94-105, :217) and the splice path reads it again afterwards (bwtgap.c:1176-1192)
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(row);
+            for (uint32_t i = 0; i <= len; ++i) { u32x2 v; v.x = w[i]; v.y = bb(i) & 63u; P.width_out[i] = v; }
+        }
     }
 };
 

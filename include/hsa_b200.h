@@ -150,6 +150,17 @@ int  hsa_match_gap_batch(const hsa_index_t *idx, const uint8_t *codes, size_t co
                          const hsa_task_t *tasks, size_t n_tasks,
                          const hsa_gap_opt_t *opts, size_t n_opts, hsa_result_t *res);
 
+/* bwt_match_gap (bwtgap.h:26; bwtgap.c:118-331) itself, ONE call, with the arguments bwt_aux_t carries: the
+ * strand-resolved sequence (aux->strand ? aux->rc_seq : aux->seq), aux->len, aux->width_back (len + 1 entries, IN/OUT:
+ * gap_shadow rewrites it in place, bwtgap.c:217, and bwt_splice_match reads it again afterwards), aux->width_seed (NULL,
+ * == width_back as at bwtgap.c:809, or the opt->seed_len + 1 entries of bwtaln.c:344-346) and aux->opt.  *aln_out is a
+ * malloc-family array of max(n_aln, 10) entries owned by the caller (free()), zero-filled beyond n_aln like the
+ * reference's calloc (bwtgap.c:137-138); start / end / type / strand stay 0 as bwt_match_gap leaves them.
+ * A batch of one: every call costs a host round trip (tens of microseconds); the batched entry points below are
+ * the ones to build pipelines on.  Serves the callers at bwtaln.c:350 and bwtgap.c:812, 919, 1192. */
+int  hsa_match_gap_call(const hsa_index_t *idx, const uint8_t *seq, uint32_t len, hsa_width_t *width_back,
+                        hsa_width_t *width_seed, const hsa_gap_opt_t *opt, int *n_aln_out, hsa_aln1_t **aln_out);
+
 /* The whole-read part of bwa_cal_sa_reg_gap (bwtaln.c:303-360, 371-372) for n reads with ONE caller
  * gap_opt_t: per-read filters (too many N, poly-A/T prefix), per-read max_diff from opt->fnr
  * (bwtaln.c:330-331), seed_len clamp (:332), reverse-complement strand first, forward strand only if

@@ -41,7 +41,11 @@ int hsa_gpu_open(const Idx2BWT *bi, int device);
 void hsa_gpu_close(void);
 void hsa_gpu_sa_values(const Idx2BWT *bi, const unsigned int *sa_index, size_t n, unsigned int *occ_pos);
 void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bwt, int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt, bwt_array_t *arr);
+bwt_aln1_t *bwt_match_gap_gpu(bwt_aux_t *aux, int *_n_aln);
 #endif
+typedef bwt_aln1_t *(*match_fn)(bwt_aux_t *, int *);
+static match_fn g_match = bwt_match_gap;            /* gpupercall: shim/hsa_gpu_shim.c's bwt_match_gap_gpu */
+static unsigned long long g_call_mismatch = 0, g_width_mismatch = 0;
 typedef void (*driver_fn)(int, const Idx2BWT *, int, bwa_seq_t *, const gap_opt_t *, bwt_array_t *);
 static driver_fn g_driver = bwa_cal_sa_reg_gap;
 
@@ -65,6 +69,27 @@ static double now_s(void)
 }
 
 static void die(const char *msg) { fprintf(stderr, "ref_harness: %s\n", msg); exit(2); }
+
+/* bwt_match_gap through g_match.  With the per-call GPU symbol installed (gpupercall / gpuseeds) the reference runs
+ * first on a copy of the frame's width_back; hits AND the in-place rewrite of width_back by gap_shadow (bwtgap.c:217)
+ * must agree between the two. */
+static bwt_aln1_t *match_checked(bwt_aux_t *aux, int *n_aln)
+{
+    bwt_width_t *wb_ref, *wb_gpu = aux->width_back, *ws_keep = aux->width_seed;
+    int n_ref = 0, j, len = aux->len; bwt_aln1_t *a_ref, *aln;
+    if (g_match == bwt_match_gap) return bwt_match_gap(aux, n_aln);
+    wb_ref = (bwt_width_t*)malloc((len + 1) * sizeof(bwt_width_t));
+    memcpy(wb_ref, wb_gpu, (len + 1) * sizeof(bwt_width_t));
+    aux->width_back = wb_ref;
+    if (ws_keep == wb_gpu) aux->width_seed = wb_ref;           /* keep the aliasing of bwtgap.c:809 */
+    a_ref = bwt_match_gap(aux, &n_ref);
+    aux->width_back = wb_gpu; aux->width_seed = ws_keep;
+    aln = g_match(aux, n_aln);
+    if (n_ref != *n_aln || (*n_aln && memcmp(a_ref, aln, *n_aln * sizeof(bwt_aln1_t)) != 0)) ++g_call_mismatch;
+    for (j = 0; j <= len; ++j) if (wb_ref[j].w != wb_gpu[j].w || wb_ref[j].bid != wb_gpu[j].bid) { ++g_width_mismatch; break; }
+    free(a_ref); free(wb_ref);
+    return aln;
+}
 
 /* ---------------------------------------------------------------- reads */
 typedef struct { uint32_t n; uint32_t *len; uint64_t *off; ubyte_t *codes; } reads_t;
@@ -349,7 +374,7 @@ static int mode_percall(int argc, char **argv)
             {
                 bwt_width_t *keep = aux.width_seed;
                 aux.width_seed = wseed;
-                aln = bwt_match_gap(&aux, &n_aln);
+                aln = match_checked(&aux, &n_aln);
                 aux.width_seed = keep;
             }
             n_hits += (n_aln != 0);
@@ -360,8 +385,9 @@ static int mode_percall(int argc, char **argv)
     }
     t1 = now_s();
     if (fo) fclose(fo);
-    printf("{\"mode\":\"percall\",\"reads\":%u,\"calls\":%u,\"calls_with_hits\":%llu,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu}\n",
-           r.n, 2 * r.n, n_hits, t1 - t0, g_occ4, g_occ1);
+    printf("{\"mode\":\"percall\",\"reads\":%u,\"calls\":%u,\"calls_with_hits\":%llu,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu,"
+           "\"call_mismatches\":%llu,\"width_mismatches\":%llu}\n",
+           r.n, 2 * r.n, n_hits, t1 - t0, g_occ4, g_occ1, g_call_mismatch, g_width_mismatch);
     return 0;
 }
 
@@ -401,7 +427,7 @@ static void seeds_range(void *vctx, uint32_t lo, uint32_t hi, FILE *fo, range_re
             memset(aux.width_seed, 0, sizeof(bwt_width_t) * (max_len + 1));
             bwt_cal_width(bi, len_align, aux.strand == 0 ? seq : rc, aux.width_seed, 1);
             aux.width_back = aux.width_seed;
-            aln = bwt_match_gap(&aux, &n_aln);
+            aln = match_checked(&aux, &n_aln);
             { int j; for (j = 0; j < n_aln; ++j) { aln[j].start = (s % 3) * seed_len; aln[j].end = aln[j].start + len_align - 1; } } /* bwtgap.c:816-819 */
             res->a += (n_aln != 0);
             if (fo) put_aln(fo, n_aln, aln);
@@ -422,8 +448,9 @@ static int mode_seeds(int argc, char **argv)
     opt = parse_opts(argc, argv, 5, &h);
     ctx.bi = bi; ctx.r = &r; ctx.opt = opt; ctx.h = &h;
     run_ranges(seeds_range, &ctx, r.n, h.procs, h.nout ? NULL : argv[4], 6, &tot);
-    printf("{\"mode\":\"seeds\",\"reads\":%u,\"calls\":%u,\"procs\":%d,\"calls_with_hits\":%llu,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu}\n",
-           r.n, 6 * r.n, h.procs, tot.a, tot.secs, tot.occ4, tot.occ1);
+    printf("{\"mode\":\"seeds\",\"reads\":%u,\"calls\":%u,\"procs\":%d,\"calls_with_hits\":%llu,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu,"
+           "\"call_mismatches\":%llu,\"width_mismatches\":%llu}\n",
+           r.n, 6 * r.n, h.procs, tot.a, tot.secs, tot.occ4, tot.occ1, g_call_mismatch, g_width_mismatch);
     return 0;
 }
 
@@ -689,6 +716,31 @@ int main(int argc, char **argv)
     }
 #endif
 #ifdef HSA_WITH_GPU_SHIM
+    if (strcmp(argv[1], "gpupercall") == 0) {
+        /* percall with every bwt_match_gap call ALSO made through the per-call GPU symbol (bwt_match_gap_gpu) on the
+         * same bwt_aux_t frame; the dump holds the GPU results, the JSON line counts calls whose hits or rewritten
+         * width_back differ from the reference's */
+        Idx2BWT *bi; int rc;
+        if (argc < 5) die("usage: gpupercall <prefix> <reads> <out> [opts]");
+        bi = load_index(argv[2]);
+        if (hsa_gpu_open(bi, 0)) return 3;
+        g_match = bwt_match_gap_gpu;
+        rc = mode_percall(argc, argv);
+        hsa_gpu_close();
+        return rc ? rc : (g_call_mismatch || g_width_mismatch ? 4 : 0);
+    }
+    if (strcmp(argv[1], "gpuseeds") == 0) {
+        /* the same for the six seed calls of bwt_splice_match (width_seed aliasing width_back, prefix-width quirk);
+         * single process: the GPU context does not survive a fork */
+        Idx2BWT *bi; int rc;
+        if (argc < 5) die("usage: gpuseeds <prefix> <reads> <out> [opts]");
+        bi = load_index(argv[2]);
+        if (hsa_gpu_open(bi, 0)) return 3;
+        g_match = bwt_match_gap_gpu;
+        rc = mode_seeds(argc, argv);
+        hsa_gpu_close();
+        return rc ? rc : (g_call_mismatch || g_width_mismatch ? 4 : 0);
+    }
     if (strcmp(argv[1], "gpusa") == 0) {
         /* gpusa <prefix> <idx.bin>: every listed SA index through BWTSaValue on the host and through the shim's GPU
          * batch call; exits 0 only if all values agree (prints the count of mismatches) */

@@ -75,6 +75,22 @@ void hsa_gpu_close(void)
 
 static void die_gpu(void) { fprintf(stderr, "[hsa_gpu] %s\n", hsa_last_error()); exit(1); }
 
+/* same signature and contract as bwt_match_gap (bwtgap.h:26; bwtgap.c:118-331): one search on the GPU with the frame the
+ * caller built in `aux` -- sequence by aux->strand, aux->len, aux->width_back (rewritten in place by gap_shadow, as the
+ * reference does), aux->width_seed, aux->opt.  Returns a malloc-family array the caller frees (never NULL).  Serves the
+ * callers at bwtaln.c:350 and bwtgap.c:812, 919, 1192; a batch of one, so use it where call-for-call substitution
+ * matters, not for throughput. */
+bwt_aln1_t *bwt_match_gap_gpu(bwt_aux_t *aux, int *_n_aln)
+{
+    const ubyte_t *seq = aux->strand == 0 ? aux->seq : aux->rc_seq;
+    hsa_aln1_t *aln = NULL;
+    int n = 0;
+    if (hsa_match_gap_call(g_idx, seq, (uint32_t)aux->len, (hsa_width_t *)aux->width_back, (hsa_width_t *)aux->width_seed,
+                           (const hsa_gap_opt_t *)aux->opt, &n, &aln)) die_gpu();
+    *_n_aln = n;
+    return (bwt_aln1_t *)aln;
+}
+
 /* same signature as bwa_cal_sa_reg_gap (bwtaln.h:199-200) */
 void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt_c, bwt_array_t *arr)
 {

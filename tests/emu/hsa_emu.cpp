@@ -290,6 +290,7 @@ uint64_t emu_flagged_first(void) { return g_flagged_first; }
 void emu_set_item_steps(uint32_t *buf) { g_item_steps = buf; g_item_steps_pos = 0; }
 void emu_set_vote(uint32_t slow_min, int32_t pop_bias) { g_vote_slow_min = slow_min; g_vote_pop_bias = pop_bias; }
 void emu_pair_stats(uint64_t *o) { o[0] = hsa_host_pair_count; o[1] = hsa_host_pair_same_sector; hsa_host_pair_count = hsa_host_pair_same_sector = 0; }
+void emu_hist(uint64_t *o) { memcpy(o, hsa_host_hist, sizeof(hsa_host_hist)); memset(hsa_host_hist, 0, sizeof(hsa_host_hist)); }
 void emu_set_simt(int on) { g_simt = on; for (int i = 0; i < 3; ++i) { g_phase_runs[i] = 0; g_phase_lanes[i] = 0; } }
 void emu_phase_stats(uint64_t *runs, uint64_t *lanes) { for (int i = 0; i < 3; ++i) { runs[i] = g_phase_runs[i]; lanes[i] = g_phase_lanes[i]; } }
 uint64_t emu_last_extra(void) { return 0; }

@@ -73,3 +73,21 @@ def test_gpu_sa_values_match_BWTSaValue_inside_the_reference_program(workdir):
     r = subprocess.run([REF_GPU, "gpusa", "g", "sa.bin"], cwd=workdir, capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-2000:])
     assert '"mismatches":0' in r.stdout
+
+
+@pytest.mark.parametrize("mode,opts", [("percall", []), ("percall", ["clear_gape=0", "max_gapo=2"]), ("seeds", [])],
+                         ids=["whole_read_frames", "gape_counts_two_gap_opens", "splice_seed_frames"])
+def test_per_call_symbol_matches_bwt_match_gap(workdir, mode, opts):
+    """bwt_match_gap_gpu(bwt_aux_t*, int*) -- the per-call drop-in symbol (bwtgap.h:26), a batch of one through
+    hsa_match_gap_call with the CALLER's width arrays: every call of the harness's percall / seeds loop is made through
+    the reference and through the GPU symbol on the same frame; hits must be byte-identical (memcmp of the bwt_aln1_t
+    arrays) and so must width_back after gap_shadow's in-place rewrite.  The dump (GPU results) equals the CPU dump."""
+    rs = synth.read_reads_bin(str(workdir / "r.reads")).subset(0, 1500)
+    synth.write_reads_bin(str(workdir / "r_small.reads"), rs)
+    cpu = subprocess.run([REF, mode, "g", "r_small.reads", "pc_cpu.aln"] + opts, cwd=workdir, check=True, capture_output=True, text=True)
+    gpu = subprocess.run([REF_GPU, "gpu" + mode, "g", "r_small.reads", "pc_gpu.aln"] + opts, cwd=workdir, capture_output=True, text=True)
+    assert gpu.returncode == 0, (gpu.stdout[-500:], gpu.stderr[-2000:])
+    assert '"call_mismatches":0,"width_mismatches":0' in gpu.stdout
+    n_c, rows_c = synth.read_aln_dump(str(workdir / "pc_cpu.aln"))
+    n_g, rows_g = synth.read_aln_dump(str(workdir / "pc_gpu.aln"))
+    assert int((n_c > 0).sum()) > 1000 and np.array_equal(n_c, n_g) and np.array_equal(rows_c, rows_g)
