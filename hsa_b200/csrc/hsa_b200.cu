@@ -1581,7 +1581,7 @@ extern "C" int hsa_match_gap_batch(const hsa_index_t *ix, const uint8_t *codes, 
 }
 
 // bwt_match_gap itself (bwtgap.h:26), one call: the caller's width arrays are arguments (in/out), exactly as in bwt_aux_t.
-extern "C" int hsa_match_gap_call(const hsa_index_t *ix, const uint8_t *seq, uint32_t len, hsa_width_t *width_back,
+extern "C" int hsa_match_gap_call(const hsa_index_t *ix, const uint8_t *seq, uint32_t len, int strand, hsa_width_t *width_back,
                                   hsa_width_t *width_seed, const hsa_gap_opt_t *opt, int *n_aln_out, hsa_aln1_t **aln_out)
 {
     if (!ix || !seq || !len || !width_back || !opt || !n_aln_out || !aln_out) return fail(HSA_E_ARG, "null / empty argument");
@@ -1635,6 +1635,7 @@ extern "C" int hsa_match_gap_call(const hsa_index_t *ix, const uint8_t *seq, uin
     hsa_aln1_t *out = (hsa_aln1_t *)calloc((size_t)(n < 10 ? 10 : n), sizeof(hsa_aln1_t));
     if (!out) { hsa_result_free(&res); return fail(HSA_E_NOMEM, "calloc failed"); }
     if (n) memcpy(out, res.aln + res.aln_off[0], (size_t)n * sizeof(hsa_aln1_t));
+    for (int q = 0; q < n; ++q) out[q].strand = (uint32_t)strand & 3u;       // p->strand = aux->strand, bwtgap.c:235
     hsa_result_free(&res);
     // width_back after gap_shadow (bids beyond the device's 6-bit field were never touched by it: keep the caller's)
     std::vector<u32x2> wb((size_t)len + 1);
@@ -1643,7 +1644,6 @@ extern "C" int hsa_match_gap_call(const hsa_index_t *ix, const uint8_t *seq, uin
         free(out); return fail(HSA_E_CUDA, "D2H copy of the widths failed");
     }
     for (uint32_t i = 0; i <= len; ++i) {
-        const bool aliased_seed = false; (void)aliased_seed;
         width_back[i].w = wb[i].x;
         if (wb[i].y < 63u) width_back[i].bid = (int)wb[i].y;
     }

@@ -155,10 +155,11 @@ int  hsa_match_gap_batch(const hsa_index_t *idx, const uint8_t *codes, size_t co
  * gap_shadow rewrites it in place, bwtgap.c:217, and bwt_splice_match reads it again afterwards), aux->width_seed (NULL,
  * == width_back as at bwtgap.c:809, or the opt->seed_len + 1 entries of bwtaln.c:344-346) and aux->opt.  *aln_out is a
  * malloc-family array of max(n_aln, 10) entries owned by the caller (free()), zero-filled beyond n_aln like the
- * reference's calloc (bwtgap.c:137-138); start / end / type / strand stay 0 as bwt_match_gap leaves them.
+ * reference's calloc (bwtgap.c:137-138); `strand` (aux->strand) is stamped on every hit (bwtgap.c:235), start / end /
+ * type stay 0 as bwt_match_gap leaves them.
  * A batch of one: every call costs a host round trip (tens of microseconds); the batched entry points below are
  * the ones to build pipelines on.  Serves the callers at bwtaln.c:350 and bwtgap.c:812, 919, 1192. */
-int  hsa_match_gap_call(const hsa_index_t *idx, const uint8_t *seq, uint32_t len, hsa_width_t *width_back,
+int  hsa_match_gap_call(const hsa_index_t *idx, const uint8_t *seq, uint32_t len, int strand, hsa_width_t *width_back,
                         hsa_width_t *width_seed, const hsa_gap_opt_t *opt, int *n_aln_out, hsa_aln1_t **aln_out);
 
 /* The whole-read part of bwa_cal_sa_reg_gap (bwtaln.c:303-360, 371-372) for n reads with ONE caller

@@ -85,7 +85,7 @@ bwt_aln1_t *bwt_match_gap_gpu(bwt_aux_t *aux, int *_n_aln)
     const ubyte_t *seq = aux->strand == 0 ? aux->seq : aux->rc_seq;
     hsa_aln1_t *aln = NULL;
     int n = 0;
-    if (hsa_match_gap_call(g_idx, seq, (uint32_t)aux->len, (hsa_width_t *)aux->width_back, (hsa_width_t *)aux->width_seed,
+    if (hsa_match_gap_call(g_idx, seq, (uint32_t)aux->len, aux->strand, (hsa_width_t *)aux->width_back, (hsa_width_t *)aux->width_seed,
                            (const hsa_gap_opt_t *)aux->opt, &n, &aln)) die_gpu();
     *_n_aln = n;
     return (bwt_aln1_t *)aln;
