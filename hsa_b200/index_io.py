@@ -120,6 +120,8 @@ class Index2BWT:
     fwd: BWTArrays
     rev: BWTArrays
     blocks: Blocks | None = None
+    packed_dna: np.ndarray | None = None   # HSP::packedDNA as DNALoadPacked leaves it: 16 symbols per word, first in the MSBs
+    dna_length: int = 0
 
 
 def load_bwt(bwt_path: str, fmv_path: str) -> BWTArrays:
@@ -175,6 +177,42 @@ def save_sa(arr: BWTArrays, sa_path: str) -> None:
         arr.sa_value[1:].tofile(f)
 
 
+def pack_dna(text: np.ndarray) -> np.ndarray:
+    """The in-memory HSP::packedDNA of a text given as codes 0..3: symbol k sits in word k >> 4 at bit (~k & 15) << 1
+    (DNALoadPacked with convertToWordPacked, TextConverter.c:677-725), one spare zero word at the end."""
+    n = int(text.shape[0])
+    pad = np.zeros(((n + 15) // 16 + 1) * 16, dtype=np.uint32)
+    pad[:n] = text
+    sh = (30 - 2 * np.arange(16)).astype(np.uint32)
+    return (pad.reshape(-1, 16) << sh[None, :]).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+
+
+def load_pac(path: str):
+    """(packed words, dnaLength) of `<prefix>.index.pac` as written by the reference builder (HSP.c:311-323): four symbols
+    per byte, first in the MSBs, then [a zero byte if length % 4 == 0 and] a byte holding length % 4."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    n_data = raw.shape[0] - 1
+    n = (n_data - 1) * 4 + int(raw[-1])
+    words = (n + 15) // 16
+    buf = np.zeros((words + 1) * 4, dtype=np.uint8)
+    buf[:n_data] = raw[:n_data]
+    return buf.view(">u4").astype(np.uint32), n
+
+
+def save_pac(text: np.ndarray, path: str) -> None:
+    """Write a text (codes 0..3) in the reference's .pac format."""
+    n = int(text.shape[0])
+    pad = np.zeros((n + 3) // 4 * 4, dtype=np.uint8)
+    pad[:n] = text
+    q = pad.reshape(-1, 4)
+    body = (q[:, 0] << 6 | q[:, 1] << 4 | q[:, 2] << 2 | q[:, 3]).astype(np.uint8)
+    with open(path, "wb") as f:
+        body.tofile(f)
+        if n % 4 == 0:
+            f.write(b"\0")
+        f.write(bytes([n % 4]))
+
+
 def load_index(prefix: str, with_sa: bool = True) -> Index2BWT:
     """Load `<prefix>.index.{bwt,fmv,rev.bwt,rev.fmv}` (and `.sa` if present) as written by `HSA index <prefix> <fasta>`."""
     import os
@@ -184,6 +222,8 @@ def load_index(prefix: str, with_sa: bool = True) -> Index2BWT:
         load_sa(ix.fwd, p + ".sa")
     if os.path.exists(p + ".ann"):
         ix.blocks = load_ann(p + ".ann")
+    if os.path.exists(p + ".pac"):
+        ix.packed_dna, ix.dna_length = load_pac(p + ".pac")
     return ix
 
 

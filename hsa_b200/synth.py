@@ -204,3 +204,47 @@ def make_repeat_genome(length: int, seed: int, n_dups: int = 40, dup_len: int = 
         dst = int(rng.integers(0, length - t.shape[0]))
         g[dst:dst + t.shape[0]] = t
     return g
+
+
+def make_intron_genome(length: int, seed: int, n_introns: int, min_intron: int = 60, max_intron: int = 20000):
+    """An i.i.d. genome with `n_introns` planted introns whose ends carry the motifs the reference's splice path looks
+    for (bwtgap.c:536-537: GT..AG, GC..AG, AT..AC on the forward strand): returns (genome, introns[n, 2] = first and
+    one-past-last intron base).  Introns do not overlap and keep 200 bases of exon around them."""
+    rng = np.random.default_rng(seed)
+    g = make_genome(length, seed)
+    introns = []
+    pos = 300
+    slot = (length - 600) // n_introns
+    motifs = [((2, 3), (0, 2)), ((2, 1), (0, 2)), ((0, 3), (0, 1))]          # GT-AG, GC-AG, AT-AC
+    for i in range(n_introns):
+        ilen = int(rng.integers(min_intron, min(max_intron, slot - 420) + 1))
+        a = pos + 200 + int(rng.integers(0, slot - ilen - 400))
+        b = a + ilen
+        m = motifs[int(rng.choice(3, p=[0.8, 0.1, 0.1]))]
+        g[a], g[a + 1] = m[0]
+        g[b - 2], g[b - 1] = m[1]
+        introns.append((a, b))
+        pos += slot
+    return g, np.asarray(introns, dtype=np.int64)
+
+
+def simulate_junction_reads(genome: np.ndarray, introns: np.ndarray, n: int, length: int, seed: int,
+                            sub_rate: float = 0.01, min_anchor: int = 8) -> ReadSet:
+    """RNA-seq-style reads across the planted introns of make_intron_genome: `left` exon bases ending at the intron
+    start joined to length - left bases from the intron end, left uniform in [min_anchor, length - min_anchor];
+    substitutions, 50 % reverse-complemented."""
+    rng = np.random.default_rng(seed)
+    which = rng.integers(0, introns.shape[0], size=n)
+    left = rng.integers(min_anchor, length - min_anchor + 1, size=n)
+    reads = np.empty((n, length), dtype=np.uint8)
+    for r in range(n):
+        a, b = int(introns[which[r], 0]), int(introns[which[r], 1])
+        le = int(left[r])
+        reads[r, :le] = genome[a - le:a]
+        reads[r, le:] = genome[b:b + length - le]
+    sub = rng.random((n, length)) < sub_rate
+    shift = rng.integers(1, 4, size=(n, length), dtype=np.uint8)
+    reads = np.where(sub, (reads + shift) & 3, reads).astype(np.uint8)
+    rc = rng.random(n) < 0.5
+    reads[rc] = revcomp(reads[rc])
+    return ReadSet(np.full(n, length, dtype=np.uint32), reads.reshape(-1))

@@ -603,6 +603,57 @@ static int mode_whole(int argc, char **argv)
     return 0;
 }
 
+/* splice <prefix> <reads> <out> [opts] [procs=P]: bwt_splice_match (bwtgap.c:748) for EVERY read, with the frame the
+ * driver builds for a read that found nothing on either strand (bwtaln.c:279-288, 362-369): aux->opt = the options the
+ * driver would hold in local_opt at that point -- the caller's values with max_diff / seed_len resolved per read as
+ * bwtaln.c:330-332 writes them through aux->opt, MODE_GAPE kept (clear_gape=0, the first batch of a process) or cleared.
+ * Needs a full index (SA samples, packed DNA, annotation).  Output: per read n_aln (0..2) and its bwt_aln1_t entries. */
+static void splice_range(void *vctx, uint32_t lo, uint32_t hi, FILE *fo, range_res_t *res)
+{
+    range_ctx_t *c = (range_ctx_t*)vctx;
+    Idx2BWT *bi = c->bi; reads_t *r = c->r; const gap_opt_t *opt = c->opt; gap_opt_t ropt;
+    int max_len = 0; uint32_t i; bwt_aux_t aux; double t0; bwt_array_t *arr = bwt_array_init();
+    for (i = lo; i < hi; ++i) if ((int)r->len[i] > max_len) max_len = (int)r->len[i];
+    memset(&aux, 0, sizeof(aux));
+    aux.bi_bwt = bi; aux.arr = arr; aux.max_len = max_len;
+    aux.width_back = (bwt_width_t*)calloc(max_len + 1, sizeof(bwt_width_t));
+    aux.width_fore = (bwt_width_t*)calloc(max_len + 1, sizeof(bwt_width_t));
+    aux.width_seed = (bwt_width_t*)calloc(max_len + 1, sizeof(bwt_width_t));
+    aux.rc_seq = (ubyte_t*)calloc(max_len + 1, 1);
+    {
+        int md = opt->fnr > 0.0 ? bwa_cal_maxdiff(max_len, BWA_AVG_ERR, opt->fnr) : opt->max_diff;
+        aux.stack = gap_init_stack(md + 2, opt->max_gapo + 2, opt->max_gape + 2, opt);    /* covers every reachable score */
+    }
+    t0 = now_s();
+    for (i = lo; i < hi; ++i) {
+        int len = (int)r->len[i], n_aln = 0; bwt_aln1_t *aln;
+        ubyte_t *seq = r->codes + r->off[i];
+        resolve_read_opt(&ropt, opt, len, c->h->clear_gape);
+        memset(aux.rc_seq, 0, max_len);                          /* bwtaln.c:334-337 */
+        memcpy(aux.rc_seq, seq, len); seq_reverse(len, aux.rc_seq, 1);
+        aux.seq = seq; aux.len = len; aux.strand = 0; aux.opt = &ropt;
+        aln = bwt_splice_match(&aux, &n_aln);
+        res->a += (n_aln != 0); res->b += (n_aln == 2);
+        if (fo) put_aln(fo, n_aln, aln);
+        free(aln);
+    }
+    res->secs = now_s() - t0;
+}
+
+static int mode_splice(int argc, char **argv)
+{
+    Idx2BWT *bi; reads_t r; hopt_t h; gap_opt_t *opt; range_ctx_t ctx; range_res_t tot;
+    if (argc < 5) die("usage: splice <prefix> <reads> <out> [opts] [procs=P] [nout=1] [clear_gape=0|1]");
+    bi = load_index(argv[2]); r = load_reads(argv[3]);
+    if (!bi->hsp || !bi->bwt->saValue) die("splice needs a full index (SA samples, packed DNA, annotation)");
+    opt = parse_opts(argc, argv, 5, &h);
+    ctx.bi = bi; ctx.r = &r; ctx.opt = opt; ctx.h = &h;
+    run_ranges(splice_range, &ctx, r.n, h.procs, h.nout ? NULL : argv[4], 1, &tot);
+    printf("{\"mode\":\"splice\",\"reads\":%u,\"procs\":%d,\"aligned\":%llu,\"two_parts\":%llu,\"secs\":%.6f,\"occ4\":%llu,\"occ1\":%llu}\n",
+           r.n, h.procs, tot.a, tot.b, tot.secs, tot.occ4, tot.occ1);
+    return 0;
+}
+
 /* dump the raw search arrays of both BWTs so that the product's own index builder can be compared bit
  * for bit with the reference builder's output:  per direction
  *   textLength inverseSa0 cumulativeFreq[5] bwtWords occWords occMajorWords, then the three arrays. */
@@ -761,6 +812,7 @@ int main(int argc, char **argv)
     }
 #endif
     if (strcmp(argv[1], "whole") == 0) return mode_whole(argc, argv);
+    if (strcmp(argv[1], "splice") == 0) return mode_splice(argc, argv);
     if (strcmp(argv[1], "dumpindex") == 0) return mode_dumpindex(argc, argv);
     if (strcmp(argv[1], "maxdiff") == 0) {
         int l;

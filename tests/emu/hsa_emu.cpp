@@ -10,6 +10,7 @@
 #include <algorithm>
 #include "../../hsa_b200/csrc/hsa_core.cuh"
 #include "../../hsa_b200/csrc/hsa_coop.cuh"
+#include "../../hsa_b200/csrc/hsa_splice.cuh"
 #include "../../include/hsa_b200.h"
 
 using namespace hsa;
@@ -290,6 +291,47 @@ uint64_t emu_flagged_first(void) { return g_flagged_first; }
 void emu_set_item_steps(uint32_t *buf) { g_item_steps = buf; g_item_steps_pos = 0; }
 void emu_set_vote(uint32_t slow_min, int32_t pop_bias) { g_vote_slow_min = slow_min; g_vote_pop_bias = pop_bias; }
 void emu_pair_stats(uint64_t *o) { o[0] = hsa_host_pair_count; o[1] = hsa_host_pair_same_sector; hsa_host_pair_count = hsa_host_pair_same_sector = 0; }
+// bwt_splice_match for every read, one after the other, on the device code of hsa_splice.cuh.
+// opts: n_opts gap_opt_t as the driver holds them in aux->opt; opt_idx per read (may be null: all reads use opts[0]).
+// n_aln_out[n], aln_out[n * 18] (two hsa_aln1_t per read), status_out[n]; returns the occ lookups issued.
+uint64_t emu_splice(void *p, const uint32_t *sa_value, uint32_t sa_interval, const uint32_t *blocks4, uint32_t n_blocks,
+                    const uint32_t *packed_dna, uint32_t dna_length, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                    size_t n, const hsa_gap_opt_t *opts, size_t n_opts, const uint32_t *opt_idx, uint32_t arena_cap, uint32_t aln_cap,
+                    int32_t *n_aln_out, uint32_t *aln_out, uint8_t *status_out)
+{
+    EmuIndex *e = (EmuIndex *)p;
+    std::vector<DevOpt> dopts(n_opts);
+    for (size_t i = 0; i < n_opts; ++i) {
+        const hsa_gap_opt_t &o = opts[i]; DevOpt &d = dopts[i];
+        memset(&d, 0, sizeof(d));
+        d.s_mm = o.s_mm; d.s_gapo = o.s_gapo; d.s_gape = o.s_gape; d.mode = o.mode;
+        d.indel_end_skip = o.indel_end_skip; d.max_del_occ = o.max_del_occ; d.max_entries = o.max_entries;
+        d.max_diff = o.max_diff; d.max_gapo = o.max_gapo; d.max_gape = o.max_gape;
+        d.max_seed_diff = o.max_seed_diff; d.seed_len = o.seed_len; d.max_top2 = o.max_top2;
+    }
+    uint32_t max_len = 0;
+    for (size_t i = 0; i < n; ++i) max_len = std::max(max_len, len[i]);
+    SpliceParams P;
+    memset(&P, 0, sizeof(P));
+    P.env.ix = e->ix; P.env.sa_value = sa_value; P.env.sa_interval = sa_interval; P.env.blocks4 = blocks4; P.env.n_blocks = n_blocks;
+    P.env.packed_dna = packed_dna; P.env.dna_length = dna_length;
+    P.codes = codes; P.read_off = off; P.read_len = len; P.opts = dopts.data(); P.opt_idx = opt_idx;
+    P.n_work = (uint32_t)n; P.max_len = max_len;
+    std::vector<SEntry> arena(arena_cap);
+    std::vector<uint32_t> heads(SPL_BUCKETS), sites(4096);
+    std::vector<SWidth> widths(3 * ((size_t)max_len + 1) + 16);
+    std::vector<SAln> lists((size_t)6 * aln_cap);
+    std::vector<SPos> pos(SPL_POS_CAP);
+    P.arena = arena.data(); P.arena_cap = arena_cap; P.heads = heads.data(); P.widths = widths.data();
+    P.lists = lists.data(); P.aln_cap = aln_cap; P.site_pos = sites.data(); P.site_cap = (uint32_t)sites.size(); P.pos_info = pos.data();
+    P.n_aln = n_aln_out; P.aln = aln_out; P.status = status_out;
+    std::vector<uint32_t> fail_list(n + 1);
+    unsigned long long fail_count = 0, lookups = 0;
+    P.fail_list = fail_list.data(); P.fail_count = &fail_count; P.lookups = &lookups;
+    for (size_t i = 0; i < n; ++i) splice_item(P, (uint32_t)i, 0);
+    return lookups;
+}
+
 void emu_hist(uint64_t *o) { memcpy(o, hsa_host_hist, sizeof(hsa_host_hist)); memset(hsa_host_hist, 0, sizeof(hsa_host_hist)); }
 void emu_set_simt(int on) { g_simt = on; for (int i = 0; i < 3; ++i) { g_phase_runs[i] = 0; g_phase_lanes[i] = 0; } }
 void emu_phase_stats(uint64_t *runs, uint64_t *lanes) { for (int i = 0; i < 3; ++i) { runs[i] = g_phase_runs[i]; lanes[i] = g_phase_lanes[i]; } }

@@ -56,6 +56,10 @@ def lib():
                               C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                               C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.emu_splice.restype = C.c_uint64
+        L.emu_splice.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -123,6 +127,28 @@ class Emu:
         lib().emu_locate(C.c_void_p(t.ctypes.data), C.c_uint32(t.shape[0]), C.c_void_p(pos.ctypes.data), C.c_size_t(pos.shape[0]),
                          C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data))
         return a, b
+
+    def splice(self, rs, opts, opt_idx=None, arena_cap=1 << 16, aln_cap=512):
+        """bwt_splice_match for every read (hsa_splice.cuh on the host): (n_aln[n], rows12 of the n_aln entries in read
+        order, status[n]).  Needs index.fwd.sa_value, index.blocks and index.packed_dna."""
+        ix = self.index
+        opts = list(opts) if isinstance(opts, (list, tuple)) else [opts]
+        oa = (ol.GapOpt * len(opts))(*opts)
+        t = np.ascontiguousarray(ix.blocks.table(), dtype=np.uint32)
+        off = np.ascontiguousarray(rs.offsets[:-1], dtype=np.uint64)
+        lens = np.ascontiguousarray(rs.lens, dtype=np.uint32)
+        n = rs.n
+        n_aln = np.zeros(n, dtype=np.int32)
+        aln = np.zeros((n, 2, 9), dtype=np.uint32)
+        status = np.zeros(n, dtype=np.uint8)
+        oi = None if opt_idx is None else np.ascontiguousarray(opt_idx, dtype=np.uint32)
+        self.last_lookups = lib().emu_splice(self.h, ix.fwd.sa_value.ctypes.data, ix.fwd.sa_interval, t.ctypes.data, t.shape[0],
+                                             ix.packed_dna.ctypes.data, ix.dna_length, rs.codes.ctypes.data, off.ctypes.data,
+                                             lens.ctypes.data, n, C.cast(oa, C.c_void_p), len(opts),
+                                             None if oi is None else oi.ctypes.data, arena_cap, aln_cap,
+                                             n_aln.ctypes.data, aln.ctypes.data, status.ctypes.data)
+        keep = np.arange(2)[None, :] < n_aln[:, None]
+        return n_aln, aln9_to_rows12(aln[keep]), status
 
     def sa_values(self, idx: np.ndarray):
         b = self.index.fwd
