@@ -131,6 +131,11 @@ def lib():
     L.hsa_sa_values_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hsa_index_attach_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.hsa_sa_locate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hsa_index_attach_packed_dna.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.hsa_splice_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.hsa_match_gap_call.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(GapOpt),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
     _lib = L
     return L
 
@@ -225,6 +230,8 @@ class Index:
             ix.attach_sa(index2bwt.fwd.sa_value, index2bwt.fwd.sa_interval)
         if getattr(index2bwt, "blocks", None) is not None:
             ix.attach_blocks(index2bwt.blocks.table())
+        if getattr(index2bwt, "packed_dna", None) is not None:
+            ix.attach_packed_dna(index2bwt.packed_dna, index2bwt.dna_length)
         return ix
 
     @classmethod
@@ -292,6 +299,28 @@ class Index:
         o = [np.zeros(idx.shape[0], dtype=np.uint32) for _ in range(3)]
         _check(lib().hsa_sa_locate(self._h, idx.ctypes.data, idx.shape[0], o[0].ctypes.data, o[1].ctypes.data, o[2].ctypes.data))
         return np.stack(o, axis=1)
+
+    def attach_packed_dna(self, packed_dna: np.ndarray, dna_length: int) -> None:
+        """HSP::packedDNA / HSP::dnaLength (index_io.load_pac or index_io.pack_dna): the text the splice path scans."""
+        p = np.ascontiguousarray(packed_dna, dtype=np.uint32)
+        if p.shape[0] < (int(dna_length) + 15) // 16:
+            raise HsaError("packed_dna shorter than dna_length / 16 words")
+        _check(lib().hsa_index_attach_packed_dna(self._h, p.ctypes.data, int(dna_length)))
+
+    def splice_match(self, codes, off, lens, opts, opt_idx=None):
+        """bwt_splice_match (bwtgap.c:748) for every read: (n_aln[n] in 0..2, aln[n, 2, 9] hsa_aln1_t words).  opts = one
+        GapOpt or a list of them (the aux->opt the driver holds per read); opt_idx[n] selects per read."""
+        opts = list(opts) if isinstance(opts, (list, tuple)) else [opts]
+        oa = (GapOpt * len(opts))(*opts)
+        cp, op, lp, n = _ptr(codes, np.uint8), _ptr(off, np.uint64), _ptr(lens, np.uint32), _len(lens)
+        oi = None if opt_idx is None else np.ascontiguousarray(opt_idx, dtype=np.uint32)
+        n_aln = np.zeros(n, dtype=np.int32)
+        aln = np.zeros((n, 2, ALN_WORDS), dtype=np.uint32)
+        lk = C.c_uint64(0)
+        _check(lib().hsa_splice_match_batch(self._h, cp[0], op[0], lp[0], n, C.cast(oa, C.c_void_p), len(opts),
+                                            None if oi is None else oi.ctypes.data, n_aln.ctypes.data, aln.ctypes.data, C.byref(lk)))
+        self.last_splice_lookups = int(lk.value)
+        return n_aln, aln
 
     def sa_values_device(self, idx_ptr: int, n: int, out_ptr: int, steps_ptr: int = 0, stream_ptr: int = 0) -> None:
         _check(lib().hsa_sa_values_device(self._h, idx_ptr, n, out_ptr, steps_ptr, stream_ptr))

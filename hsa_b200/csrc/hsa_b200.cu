@@ -19,6 +19,7 @@
 #include <algorithm>
 #include "hsa_core.cuh"
 #include "hsa_coop.cuh"
+#include "hsa_splice.cuh"
 #include "../../include/hsa_b200.h"
 
 using namespace hsa;
@@ -265,6 +266,19 @@ __global__ void __launch_bounds__(BLOCK) coop_kernel(const __grid_constant__ Par
     }
 }
 
+// Splice fallback (hsa_splice.cuh): persistent grid, one read per thread at a time, atomic work queue.  Every thread owns
+// a slice of the scratch arrays (stack arena, hit lists, width arrays); reads that outgrow it are listed for a re-run
+// with larger slices.
+__global__ void __launch_bounds__(128) splice_kernel(const __grid_constant__ SpliceParams P)
+{
+    const size_t worker = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (;;) {
+        const unsigned long long w = atomicAdd(P.cursor, 1ull);
+        if (w >= P.n_work) break;
+        splice_item(P, (uint32_t)w, worker);
+    }
+}
+
 // Random-sector probe: every thread walks `iters` pseudo-random 32-byte sectors of `buf` (n_sectors),
 // two independent 16-byte loads per sector like an occ lookup, `CHAINS` independent chains per thread.
 template <int CHAINS>
@@ -379,6 +393,7 @@ struct hsa_index {
     unsigned long long *sa_counters = nullptr;                                        // SA_SLOTS x {work cursor, PsiMinus steps}: one slot per call, round-robin
     mutable uint32_t sa_seq = 0;
     uint32_t *blocks4 = nullptr; uint32_t n_blocks = 0;                               // HSP::blockList rows (optional)
+    uint32_t *packed_dna = nullptr; uint32_t dna_length = 0;                          // HSP::packedDNA (optional; splice path)
 };
 
 struct Scratch {                             // worker-private device memory for one launch configuration
@@ -670,7 +685,7 @@ extern "C" void hsa_index_free(hsa_index_t *ix)
     if (ix->d2h) cudaStreamDestroy(ix->d2h);
     if (ix->own_ref) for (int d = 0; d < 2; ++d) { cudaFree(ix->ref_code[d]); cudaFree(ix->ref_occ[d]); cudaFree(ix->ref_major[d]); }
     if (ix->own_blocks) for (int d = 0; d < 2; ++d) cudaFree(ix->blocks[d]);
-    cudaFree(ix->sa_value); cudaFree(ix->sa_counters); cudaFree(ix->blocks4);
+    cudaFree(ix->sa_value); cudaFree(ix->sa_counters); cudaFree(ix->blocks4); cudaFree(ix->packed_dna);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -808,6 +823,129 @@ extern "C" int hsa_sa_values_device(const hsa_index_t *ix, const uint32_t *sa_in
     int rc = sa_launch(ix, sa_index_dev, n, sa_value_out_dev, s, &cnt);
     if (rc) return rc;
     if (steps_total_dev) CU(cudaMemcpyAsync(steps_total_dev, cnt + 1, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+    return HSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- splice fallback
+extern "C" int hsa_index_attach_packed_dna(hsa_index_t *ix, const uint32_t *packed_dna, uint32_t dna_length)
+{
+    if (!ix || !packed_dna || dna_length == 0) return fail(HSA_E_ARG, "bad argument");
+    CU(cudaSetDevice(ix->device));
+    const size_t words = ((size_t)dna_length + 15) / 16 + 1;       // DNALoadPacked allocates one spare word (TextConverter.c:705)
+    cudaFree(ix->packed_dna); ix->packed_dna = nullptr;
+    CU(cudaMalloc((void **)&ix->packed_dna, words * 4));
+    CU(cudaMemset(ix->packed_dna, 0, words * 4));
+    CU(cudaMemcpy(ix->packed_dna, packed_dna, (words - 1) * 4, cudaMemcpyHostToDevice));
+    ix->dna_length = dna_length;
+    return HSA_OK;
+}
+
+namespace {
+struct DevBuf {                    // cudaMalloc'd array released on scope exit
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(size_t bytes) { cudaFree(p); p = nullptr; return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+}
+
+// one pass of splice_kernel over `n_work` reads with per-worker scratch of the given capacities
+static int splice_pass(const hsa_index_t *ix, SpliceParams P, uint32_t n_work, const uint32_t *work_list, uint32_t max_workers,
+                       uint32_t arena_cap, uint32_t aln_cap, uint32_t site_cap, unsigned long long *counters, cudaStream_t s)
+{
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, splice_kernel, 128, 0));
+    uint32_t grid = (uint32_t)ix->sm_count * (uint32_t)std::max(occ, 1);
+    grid = std::max<uint32_t>(1, std::min<uint32_t>(grid, std::min<uint32_t>((n_work + 127) / 128, std::max<uint32_t>(1, max_workers / 128))));
+    const size_t workers = (size_t)grid * 128, wl = (size_t)P.max_len + 1;
+    DevBuf arena, heads, widths, lists, sites, pos;
+    if (arena.alloc(workers * arena_cap * sizeof(SEntry)) || heads.alloc(workers * SPL_BUCKETS * 4) ||
+        widths.alloc(workers * (3 * wl + 16) * sizeof(SWidth)) || lists.alloc(workers * 6 * aln_cap * sizeof(SAln)) ||
+        sites.alloc(workers * site_cap * 4) || pos.alloc(workers * SPL_POS_CAP * sizeof(SPos)))
+        return fail(HSA_E_CUDA, "out of device memory for the splice scratch");
+    CU(cudaMemsetAsync(widths.p, 0, workers * (3 * wl + 16) * sizeof(SWidth), s));       // the driver's calloc (bwtaln.c:283-285)
+    P.arena = arena.as<SEntry>(); P.arena_cap = arena_cap; P.heads = heads.as<uint32_t>(); P.widths = widths.as<SWidth>();
+    P.lists = lists.as<SAln>(); P.aln_cap = aln_cap; P.site_pos = sites.as<uint32_t>(); P.site_cap = site_cap; P.pos_info = pos.as<SPos>();
+    P.n_work = n_work; P.work_list = work_list;
+    P.cursor = counters; P.fail_count = counters + 1; P.lookups = counters + 2;
+    CU(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), s));                 // cursor + fail count; lookups accumulate
+    splice_kernel<<<grid, 128, 0, s>>>(P);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+    return HSA_OK;
+}
+
+extern "C" int hsa_splice_match_batch(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                                      size_t n_reads, const hsa_gap_opt_t *opts, size_t n_opts, const uint32_t *opt_idx,
+                                      int32_t *n_aln_out, hsa_aln1_t *aln_out, uint64_t *occ_lookups)
+{
+    if (occ_lookups) *occ_lookups = 0;
+    if (n_reads == 0) return HSA_OK;
+    if (!ix || !codes || !off || !len || !opts || !n_opts || !n_aln_out || !aln_out) return fail(HSA_E_ARG, "null / empty argument");
+    if (!ix->sa_value || !ix->blocks4 || !ix->packed_dna)
+        return fail(HSA_E_ARG, "the splice path needs the SA samples, the block list and the packed text "
+                               "(hsa_index_attach_sa / _blocks / _packed_dna)");
+    if (n_reads > 0x7FFFFFF0ull) return fail(HSA_E_ARG, "too many reads in one batch");
+    size_t bytes = 0; uint32_t max_len = 0;
+    for (size_t i = 0; i < n_reads; ++i) {
+        if (len[i] < 36) return fail(HSA_E_ARG, "bwt_splice_match needs reads of at least 36 bases (three seeds, 12-base anchors)");
+        if (len[i] > 4095) return fail(HSA_E_ARG, "reads longer than 4095 bases are not supported");
+        if (opt_idx && opt_idx[i] >= n_opts) return fail(HSA_E_ARG, "opt_idx out of range");
+        bytes = std::max(bytes, (size_t)off[i] + len[i]); max_len = std::max(max_len, len[i]);
+    }
+    std::vector<DevOpt> dopts(n_opts);
+    for (size_t i = 0; i < n_opts; ++i) {
+        const hsa_gap_opt_t &o = opts[i];
+        if (o.s_mm < 0 || o.s_gapo < 0 || o.s_gape < 0 || o.max_diff < 0 || o.max_gapo < 0 || o.max_gape < 0 || o.max_seed_diff < 0)
+            return fail(HSA_E_ARG, "negative scores / limits are not supported");
+        const long top = (long)(std::max(o.max_diff, o.max_seed_diff) + 2) * o.s_mm + (long)(o.max_gapo + 2) * o.s_gapo +
+                         (long)(std::max(o.max_gape, 3) + 2) * o.s_gape;
+        if (top >= (long)SPL_BUCKETS) return fail(HSA_E_ARG, "score range exceeds the splice stack's 256 buckets");
+        to_devopt(o, dopts[i]);
+    }
+    CU(cudaSetDevice(ix->device));
+    cudaStream_t s = ix->stream;
+    DevBuf d_codes, d_off, d_len, d_opts, d_oi, d_n, d_aln, d_status, d_fail, d_cnt;
+    if (d_codes.alloc(bytes + 16) || d_off.alloc(n_reads * 8) || d_len.alloc(n_reads * 4) || d_opts.alloc(n_opts * sizeof(DevOpt)) ||
+        d_oi.alloc(n_reads * 4) || d_n.alloc(n_reads * 4) || d_aln.alloc(n_reads * 18 * 4) || d_status.alloc(n_reads) ||
+        d_fail.alloc((n_reads + 1) * 4) || d_cnt.alloc(4 * sizeof(unsigned long long)))
+        return fail(HSA_E_CUDA, "out of device memory for the splice batch");
+    CU(cudaMemcpyAsync(d_codes.p, codes, bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_off.p, off, n_reads * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_len.p, len, n_reads * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_opts.p, dopts.data(), n_opts * sizeof(DevOpt), cudaMemcpyHostToDevice, s));
+    if (opt_idx) CU(cudaMemcpyAsync(d_oi.p, opt_idx, n_reads * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(d_cnt.p, 0, 4 * sizeof(unsigned long long), s));
+    static bool stack_set = false;
+    if (!stack_set) { CU(cudaDeviceSetLimit(cudaLimitStackSize, 8192)); stack_set = true; }
+    SpliceParams P;
+    memset(&P, 0, sizeof(P));
+    P.env.ix = ix->ix; P.env.sa_value = ix->sa_value; P.env.sa_interval = ix->sa_interval;
+    P.env.blocks4 = ix->blocks4; P.env.n_blocks = ix->n_blocks; P.env.packed_dna = ix->packed_dna; P.env.dna_length = ix->dna_length;
+    P.codes = d_codes.as<uint8_t>(); P.read_off = d_off.as<uint64_t>(); P.read_len = d_len.as<uint32_t>();
+    P.opts = d_opts.as<DevOpt>(); P.opt_idx = opt_idx ? d_oi.as<uint32_t>() : nullptr; P.max_len = max_len;
+    P.n_aln = d_n.as<int32_t>(); P.aln = d_aln.as<uint32_t>(); P.status = d_status.as<uint8_t>(); P.fail_list = d_fail.as<uint32_t>();
+    unsigned long long *cnt = d_cnt.as<unsigned long long>();
+    int rc;
+    // first pass: every read, small slices for many workers; then the reads that outgrew them, large slices for few
+    const uint32_t arena_cap = (uint32_t)std::max<long>(64, env_long("HSA_B200_SPLICE_ARENA", 2048));
+    const uint32_t aln_cap = (uint32_t)std::max<long>(16, env_long("HSA_B200_SPLICE_ALNS", 128));
+    if ((rc = splice_pass(ix, P, (uint32_t)n_reads, nullptr, 1u << 20, arena_cap, aln_cap, 512, cnt, s))) return rc;
+    unsigned long long h[3];
+    CU(cudaMemcpy(h, cnt, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[1]) {
+        const uint32_t n_fail = (uint32_t)h[1];
+        DevBuf again;
+        if (again.alloc((size_t)n_fail * 4)) return fail(HSA_E_CUDA, "out of device memory");
+        CU(cudaMemcpy(again.p, d_fail.p, (size_t)n_fail * 4, cudaMemcpyDeviceToDevice));
+        if ((rc = splice_pass(ix, P, n_fail, again.as<uint32_t>(), 4096, 1u << 18, 1u << 13, 1u << 14, cnt, s))) return rc;
+        CU(cudaMemcpy(h, cnt, sizeof(h), cudaMemcpyDeviceToHost));
+        if (h[1]) return fail(HSA_E_CAPACITY, "a read exceeded the splice path's large-capacity scratch (262144 stack entries, 8192 hits per seed)");
+    }
+    CU(cudaMemcpyAsync(n_aln_out, d_n.p, n_reads * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(aln_out, d_aln.p, n_reads * 18 * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (occ_lookups) *occ_lookups = h[2];
     return HSA_OK;
 }
 

@@ -47,9 +47,11 @@
 #if defined(__CUDACC__)
 #define HSA_HD __host__ __device__ __forceinline__
 #define HSA_D  __device__ __forceinline__
+#define HSA_HD_CALL __host__ __device__ __noinline__      // large bodies with many call sites (hsa_splice.cuh): real calls
 #else
 #define HSA_HD inline
 #define HSA_D  inline
+#define HSA_HD_CALL
 #endif
 
 // Per-block shared memory (device) / per-run scratch (host emulation): option table, then per lane the bucket

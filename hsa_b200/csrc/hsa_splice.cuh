@@ -118,7 +118,7 @@ struct Splicer {
 
     // ---- SA range stepping --------------------------------------------------------------------------------------
     // BWTAllSARangesBackward_Bidirection (2BWT-Interface.c:235-271)
-    HSA_HD void back_all(uint32_t k, uint32_t l, uint32_t rev_l, uint32_t sk[4], uint32_t sl[4], uint32_t rsk[4], uint32_t rsl[4])
+    HSA_HD_CALL void back_all(uint32_t k, uint32_t l, uint32_t rev_l, uint32_t sk[4], uint32_t sl[4], uint32_t rsk[4], uint32_t rsl[4])
     {
         uint32_t oL[4], oR[4], oc = 0;
         occ4_dev(E.ix.fwd, k, oL); occ4_dev(E.ix.fwd, l + 1, oR);
@@ -132,7 +132,7 @@ struct Splicer {
         }
     }
     // BWTAllSARangesForward_Bidirection (2BWT-Interface.c:274-304): the same on rev_bwt with the roles swapped
-    HSA_HD void fore_all(uint32_t l, uint32_t rev_k, uint32_t rev_l, uint32_t sk[4], uint32_t sl[4], uint32_t rsk[4], uint32_t rsl[4])
+    HSA_HD_CALL void fore_all(uint32_t l, uint32_t rev_k, uint32_t rev_l, uint32_t sk[4], uint32_t sl[4], uint32_t rsk[4], uint32_t rsl[4])
     {
         uint32_t oL[4], oR[4], oc = 0;
         occ4_dev(E.ix.rev, rev_k, oL); occ4_dev(E.ix.rev, rev_l + 1, oR);
@@ -148,7 +148,7 @@ struct Splicer {
 
     // ---- bwt_cal_width (bwtaln.c:73-116) ----------------------------------------------------------------------------
     // `src`: first base of the n-base string inside the strand-resolved read
-    HSA_HD int32_t cal_width(uint32_t strand, int32_t src, int32_t n, SWidth *width, int type)
+    HSA_HD_CALL int32_t cal_width(uint32_t strand, int32_t src, int32_t n, SWidth *width, int type)
     {
         uint32_t k = 0, l = E.ix.fwd.text_length;
         int32_t bid = 0;
@@ -180,12 +180,12 @@ struct Splicer {
     }
 
     // ---- the score-bucketed stack (gap_reset_stack / gap_push / gap_pop, bwtgap.c:37-92) ---------------------------
-    HSA_HD void st_reset()
+    HSA_HD_CALL void st_reset()
     {
         for (uint32_t b = 0; b < SPL_BUCKETS; ++b) S.heads[b] = SPL_NIL;
         st_best = SPL_BUCKETS; st_n = 0; st_top = 0; st_free = SPL_NIL;
     }
-    HSA_HD void st_push(int32_t i, uint32_t k, uint32_t l, uint32_t rev_k, uint32_t rev_l, uint32_t n_mm, uint32_t n_gapo,
+    HSA_HD_CALL void st_push(int32_t i, uint32_t k, uint32_t l, uint32_t rev_k, uint32_t rev_l, uint32_t n_mm, uint32_t n_gapo,
                         uint32_t n_gape, uint32_t state, int is_diff, const DevOpt &o)
     {
         const int32_t score = score_of((int32_t)n_mm, (int32_t)n_gapo, (int32_t)n_gape, o);
@@ -205,7 +205,7 @@ struct Splicer {
         ++st_n;
         if (st_best > (uint32_t)score) st_best = (uint32_t)score;
     }
-    HSA_HD SEntry st_pop()
+    HSA_HD_CALL SEntry st_pop()
     {
         const uint32_t s = S.heads[st_best];
         const SEntry e = S.arena[s];
@@ -221,7 +221,7 @@ struct Splicer {
     }
 
     // ---- bwt_match_exact (2BWT-Interface.c:365-388) over bases [src, src + n) of the strand-resolved read ----------
-    HSA_HD bool match_exact(uint32_t strand, int32_t src, int32_t n, uint32_t &k, uint32_t &l, uint32_t &rev_k, uint32_t &rev_l)
+    HSA_HD_CALL bool match_exact(uint32_t strand, int32_t src, int32_t n, uint32_t &k, uint32_t &l, uint32_t &rev_k, uint32_t &rev_l)
     {
         uint32_t ck = k, cl = l, crk = rev_k, crl = rev_l;
         for (int32_t i = n - 1; i >= 0; --i) {
@@ -244,7 +244,7 @@ struct Splicer {
     // seq = bases [src, src + n) of the strand-resolved read; width / width_seed as in bwt_aux_t (width_seed may be null
     // or alias width); hits go to out[0..cap) in discovery order with k, l, rev_k, rev_l, counts, strand, score set and
     // everything else zero (the reference's calloc / zero-fill, :137-138, :218-227)
-    HSA_HD int32_t match_gap(uint32_t strand, int32_t src, int32_t n, SWidth *width, SWidth *width_seed, const DevOpt &o, SAln *out)
+    HSA_HD_CALL int32_t match_gap(uint32_t strand, int32_t src, int32_t n, SWidth *width, SWidth *width_seed, const DevOpt &o, SAln *out)
     {
         const uint32_t N = E.ix.fwd.text_length;
         int32_t best_score = score_of(o.max_diff + 1, o.max_gapo + 1, o.max_gape + 1, o);        // :128
@@ -349,7 +349,7 @@ struct Splicer {
     }
 
     // ---- bwt_extend_exact (2BWT-Interface.c:394-439) on the strand-resolved read ------------------------------------
-    HSA_HD void extend_exact(uint32_t strand, int32_t start, int32_t &leav, int type, uint32_t &k, uint32_t &l, uint32_t &rev_k, uint32_t &rev_l)
+    HSA_HD_CALL void extend_exact(uint32_t strand, int32_t start, int32_t &leav, int type, uint32_t &k, uint32_t &l, uint32_t &rev_k, uint32_t &rev_l)
     {
         uint32_t ck = k, cl = l, crk = rev_k, crl = rev_l;
         uint32_t sk[4], sl[4], rsk[4], rsl[4];
@@ -383,7 +383,7 @@ struct Splicer {
 
     // ---- bwt_backtracing_search (bwtgap.c:346-511) -------------------------------------------------------------------
     // ext_len = aux->len of the extension frame; returns -1 / 1 / 2 as the reference does
-    HSA_HD int32_t backtrack(uint32_t strand, int32_t ext_len, const DevOpt &o, SAln &aln, int is_backward, int32_t &max_pos_io)
+    HSA_HD_CALL int32_t backtrack(uint32_t strand, int32_t ext_len, const DevOpt &o, SAln &aln, int is_backward, int32_t &max_pos_io)
     {
         const int32_t best_score = score_of(o.max_diff + 1, o.max_gapo + 1, o.max_gape + 1, o);
         const int32_t max_diff = o.max_diff, ln = ext_len;
@@ -460,7 +460,7 @@ struct Splicer {
         return -1;
     }
     // bwt_extend_backward / bwt_extend_foreward (bwtgap.c:640-663)
-    HSA_HD int32_t extend(uint32_t strand, int32_t ext_len, const DevOpt &o, SAln &aln, int is_backward, int32_t &pos)
+    HSA_HD_CALL int32_t extend(uint32_t strand, int32_t ext_len, const DevOpt &o, SAln &aln, int is_backward, int32_t &pos)
     {
         st_reset();
         st_push(ext_len, aln.k, aln.l, aln.rev_k, aln.rev_l, aln.n_mm, aln.n_gapo, aln.n_gape, 0, 0, o);
@@ -480,7 +480,7 @@ struct Splicer {
     HSA_HD uint32_t dna_at(uint32_t k) const { return (ld_ro1(E.packed_dna + (k >> 4)) >> ((~k & 15u) << 1)) & 3u; }
 
     // ---- bwt_aln_corelate_check (bwtgap.c:669-742) on hit lists p, q (n_p, n_q updated) ------------------------------
-    HSA_HD uint32_t corelate(SAln *p, int32_t &n_p, SAln *q, int32_t &n_q)
+    HSA_HD_CALL uint32_t corelate(SAln *p, int32_t &n_p, SAln *q, int32_t &n_q)
     {
         int32_t tot_cnt = 0, cur = 0;
         uint32_t min_dist = 0xffffffffu, res_pos = 0xffffffffu, seq_id = 0, ori_pos = 0;
@@ -520,7 +520,7 @@ struct Splicer {
     }
 
     // ---- splice_site_search_from_pos (bwtgap.c:523-594): sites into S.site_pos, returns their number ------------------
-    HSA_HD int32_t site_search(int is_backward, uint32_t strand, uint32_t pos, int32_t ext, int32_t left, int32_t right)
+    HSA_HD_CALL int32_t site_search(int is_backward, uint32_t strand, uint32_t pos, int32_t ext, int32_t left, int32_t right)
     {
         const int32_t ref_len = right - left - 1;
         // motif tables of :535-536 (positive strand GT AG | GC AG | AT AC, negative strand CT AC | CT GC | GT AT)
@@ -555,7 +555,7 @@ struct Splicer {
     }
 
     // ---- check_site_by_intron_end (bwtgap.c:602-635) -----------------------------------------------------------------
-    HSA_HD int32_t check_site(const SAln &aln, int is_backward, int32_t type, uint32_t strand)
+    HSA_HD_CALL int32_t check_site(const SAln &aln, int is_backward, int32_t type, uint32_t strand)
     {
         const uint8_t motif_posv[12] = {2, 3, 0, 2, 2, 1, 0, 2, 0, 3, 0, 1};
         const uint8_t motif_neg[12] = {1, 3, 0, 1, 1, 3, 2, 1, 2, 3, 0, 3};
@@ -582,7 +582,7 @@ struct Splicer {
 
     // ---- bwt_splice_match (bwtgap.c:748-1332) ------------------------------------------------------------------------
     // opt = aux->opt as the driver holds it; res[0..2) = the reference's res_aln; returns *_n_aln
-    HSA_HD int32_t splice_match(const DevOpt &opt, SAln res[2])
+    HSA_HD_CALL int32_t splice_match(const DevOpt &opt, SAln res[2])
     {
         const int32_t seed_len = len / 3;
         DevOpt so = opt, xo = opt;                              // aux_seed->opt / aux_ext->opt (:768-783)

@@ -206,12 +206,13 @@ def make_repeat_genome(length: int, seed: int, n_dups: int = 40, dup_len: int = 
     return g
 
 
-def make_intron_genome(length: int, seed: int, n_introns: int, min_intron: int = 60, max_intron: int = 20000):
-    """An i.i.d. genome with `n_introns` planted introns whose ends carry the motifs the reference's splice path looks
-    for (bwtgap.c:536-537: GT..AG, GC..AG, AT..AC on the forward strand): returns (genome, introns[n, 2] = first and
-    one-past-last intron base).  Introns do not overlap and keep 200 bases of exon around them."""
+def make_intron_genome(length: int, seed: int, n_introns: int, min_intron: int = 60, max_intron: int = 20000,
+                       base: np.ndarray | None = None):
+    """A genome (i.i.d., or `base`) with `n_introns` planted introns whose ends carry the motifs the reference's splice
+    path looks for (bwtgap.c:536-537: GT..AG, GC..AG, AT..AC on the forward strand): returns (genome, introns[n, 2] =
+    first and one-past-last intron base).  Introns do not overlap and keep 200 bases of exon around them."""
     rng = np.random.default_rng(seed)
-    g = make_genome(length, seed)
+    g = make_genome(length, seed) if base is None else base.copy()
     introns = []
     pos = 300
     slot = (length - 600) // n_introns

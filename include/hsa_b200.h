@@ -248,6 +248,24 @@ int  hsa_index_attach_blocks(hsa_index_t *idx, const uint32_t *blocks4, uint32_t
 int  hsa_sa_locate(const hsa_index_t *idx, const uint32_t *sa_index, size_t n, uint32_t *occ_pos_out, uint32_t *seq_id_out,
                    uint32_t *ori_pos_out);
 
+/* ---- the spliced-read fallback ----------------------------------------------------------
+ * Replaces bwt_splice_match (bwtgap.h:31; bwtgap.c:748-1332) as bwa_cal_sa_reg_gap calls it for every read that found
+ * nothing on either strand (bwtaln.c:362-369), with everything under it: the six seed searches, bwt_aln_corelate_check
+ * (bwtgap.c:669-742), splice_site_search_from_pos / check_site_by_intron_end on the packed text (:523-635),
+ * bwt_extend_backward / _foreward = bwt_backtracing_search (:346-511, 640-663), bwt_cal_width types 1 and 0
+ * (bwtaln.c:73-116), the 12-base anchor searches (:919, :1192).  One read per GPU thread; results are bit-identical to the
+ * reference's, quirks included (hsa_b200/csrc/hsa_splice.cuh lists them).
+ * Needs hsa_index_attach_sa, hsa_index_attach_blocks and hsa_index_attach_packed_dna (HSP::packedDNA as DNALoadPacked
+ * leaves it -- 16 symbols per 32-bit word, first symbol in the two MSBs -- and HSP::dnaLength; HSP.c:67-82).
+ * opts[opt_idx[r]] (opt_idx NULL: opts[0]) = the gap_opt_t the driver holds in aux->opt when it calls bwt_splice_match
+ * for read r, i.e. local_opt after its per-read writes (bwtaln.c:254, 273-276, 330-332, 363); reads need >= 36 bases.
+ * n_aln_out[r] in {0, 1, 2}; aln_out[2 r], aln_out[2 r + 1] = the reference's res_aln[0..1] (type = BWA_TYPE_SPLICING,
+ * start / end = the read span of each part).  *occ_lookups (may be NULL) = rank lookups issued. */
+int  hsa_index_attach_packed_dna(hsa_index_t *idx, const uint32_t *packed_dna, uint32_t dna_length);
+int  hsa_splice_match_batch(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off, const uint32_t *len,
+                            size_t n_reads, const hsa_gap_opt_t *opts, size_t n_opts, const uint32_t *opt_idx,
+                            int32_t *n_aln_out, hsa_aln1_t *aln_out, uint64_t *occ_lookups);
+
 /* ---- roofline probe: random 32-byte-sector loads over `footprint_bytes` ----
  * The random-access denominator on this GPU: achieved GB/s (sectors * 32 B / time) at full occupancy of five access
  * shapes -- [0] four dependent chains per thread with two 16-byte loads per sector, [1..3] 4 / 8 / 16 independent 256-bit

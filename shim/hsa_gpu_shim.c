@@ -30,6 +30,7 @@
 
 static hsa_index_t *g_idx = NULL;
 static hsa_result_t g_res_a, g_res_b;
+static void g_sa_attached_flag(void);
 
 static void view_of(const BWT *b, hsa_bwt_view_t *v)          /* BWT.h:61-83 */
 {
@@ -41,11 +42,32 @@ static void view_of(const BWT *b, hsa_bwt_view_t *v)          /* BWT.h:61-83 */
     v->occValueMajor = b->occValueMajor; v->occMajorSizeInWord = b->occMajorSizeInWord;
 }
 
+static int g_splice_gpu = 0;    /* bwt_splice_match on the GPU too (needs the full index: SA samples, annotation, packed text) */
+
 int hsa_gpu_open(const Idx2BWT *bi, int device)                /* call once after BWTLoad2BWT, bwtaln.c:469 */
 {
     hsa_bwt_view_t f, r;
+    const char *env = getenv("HSA_GPU_SPLICE");
     view_of(bi->bwt, &f); view_of(bi->rev_bwt, &r);
     if (hsa_index_upload(device, &f, &r, &g_idx)) { fprintf(stderr, "[hsa_gpu] %s\n", hsa_last_error()); return -1; }
+    g_splice_gpu = 0;
+    if (bi->hsp && bi->hsp->packedDNA && bi->bwt->saValue && (!env || atoi(env) != 0)) {
+        /* what bwt_splice_match reads besides the two BWTs: BWT::saValue (BWT.c:205-223), HSP::blockList (HSP.c:85-106),
+         * HSP::packedDNA / dnaLength (HSP.c:74-77) */
+        const HSP *h = bi->hsp;
+        uint32_t *b4 = (uint32_t *)malloc(sizeof(uint32_t) * 4 * (size_t)(h->numOfBlock > 0 ? h->numOfBlock : 1));
+        int i;
+        for (i = 0; i < h->numOfBlock; ++i) {
+            b4[4 * i] = (uint32_t)h->blockList[i].chrID; b4[4 * i + 1] = h->blockList[i].blockStart;
+            b4[4 * i + 2] = h->blockList[i].blockEnd; b4[4 * i + 3] = h->blockList[i].ori;
+        }
+        if (hsa_index_attach_sa(g_idx, bi->bwt->saValue, bi->bwt->saValueSizeInWord, bi->bwt->saInterval) ||
+            hsa_index_attach_blocks(g_idx, b4, (uint32_t)h->numOfBlock) ||
+            hsa_index_attach_packed_dna(g_idx, h->packedDNA, h->dnaLength)) {
+            fprintf(stderr, "[hsa_gpu] splice path stays on the host: %s\n", hsa_last_error());
+        } else { g_splice_gpu = 1; g_sa_attached_flag(); }
+        free(b4);
+    }
     return 0;
 }
 
@@ -53,6 +75,7 @@ int hsa_gpu_open(const Idx2BWT *bi, int device)                /* call once afte
  * looks up for bwa_cal_pac_pos (bwtse.c:350-369) and bwt_aln_corelate_check (bwtgap.c:669-742).  The SA samples are
  * handed to the library on first use (they need the full index, which hsa_gpu_open's search-only callers may not load). */
 static int g_sa_attached = 0;
+static void g_sa_attached_flag(void) { g_sa_attached = 1; }
 void hsa_gpu_sa_values(const Idx2BWT *bi, const unsigned int *sa_index, size_t n, unsigned int *occ_pos)
 {
     if (!g_sa_attached) {
@@ -103,6 +126,7 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
     uint64_t *off, total = 0;
     uint32_t *len;
     uint32_t *sel; int n_sel = 0;                              /* reads handed to the GPU (index into seqs) */
+    int *pend_read = NULL; gap_opt_t *pend_opt = NULL; int n_pend = 0;   /* reads for the GPU splice batch + their aux->opt */
     (void)tid;
 
     opt->mode &= ~BWA_MODE_GAPE;                               /* :261, sticks in the caller's struct */
@@ -121,6 +145,10 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
     codes = (uint8_t *)malloc(total + 16); off = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1));
     len = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1)); state = (uint8_t *)calloc(n_seqs + 1, 1);
     sel = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1));
+    if (g_splice_gpu) {
+        pend_read = (int *)malloc(sizeof(int) * (n_seqs + 1));
+        pend_opt = (gap_opt_t *)malloc(sizeof(gap_opt_t) * (n_seqs + 1));
+    }
     total = 0;
     for (i = 0; i < n_seqs; ++i) {
         off[i] = total; len[i] = seqs[i].len;
@@ -186,7 +214,12 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
             memcpy(p->aln, res->aln + res->aln_off[ri], sizeof(bwt_aln1_t) * (size_t)p->n_aln);
             continue;
         }
-        /* nothing on either strand: the splice path, on the host, exactly as bwtaln.c:362-369 */
+        /* nothing on either strand: the splice path (bwtaln.c:362-369) with aux->opt = &local_opt as it stands NOW */
+        if (g_splice_gpu && p->len >= 36) {
+            aux->opt = &local_opt; leaked = 1;
+            pend_read[n_pend] = i; pend_opt[n_pend] = local_opt; ++n_pend;     /* searched in one GPU batch below */
+            continue;
+        }
         memset(aux->rc_seq, 0, max_len * sizeof(ubyte_t));
         memcpy(aux->rc_seq, p->seq, p->len * sizeof(ubyte_t));
         seq_reverse(p->len, aux->rc_seq, 1);
@@ -195,7 +228,37 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
         p->aln = bwt_splice_match(aux, &p->n_aln);
         if (p->n_aln == 0) { free(p->aln); p->aln = NULL; }
     }
+    if (n_pend) {
+        /* bwt_splice_match for all of them at once (hsa_splice_match_batch): distinct option states become an option
+         * table, reads keep their order */
+        uint8_t *pc; uint64_t *po; uint32_t *pl, *pi; int32_t *pn; hsa_aln1_t *pa; gap_opt_t *tab; int n_tab = 0, q, t;
+        uint64_t tot = 0;
+        for (q = 0; q < n_pend; ++q) tot += seqs[pend_read[q]].len;
+        pc = (uint8_t *)malloc(tot + 16); po = (uint64_t *)malloc(sizeof(uint64_t) * n_pend);
+        pl = (uint32_t *)malloc(sizeof(uint32_t) * n_pend); pi = (uint32_t *)malloc(sizeof(uint32_t) * n_pend);
+        pn = (int32_t *)calloc(n_pend, sizeof(int32_t)); pa = (hsa_aln1_t *)calloc((size_t)n_pend * 2, sizeof(hsa_aln1_t));
+        tab = (gap_opt_t *)malloc(sizeof(gap_opt_t) * n_pend);
+        tot = 0;
+        for (q = 0; q < n_pend; ++q) {
+            bwa_seq_t *p = seqs + pend_read[q];
+            po[q] = tot; pl[q] = p->len; memcpy(pc + tot, p->seq, p->len); tot += p->len;
+            for (t = 0; t < n_tab; ++t) if (memcmp(tab + t, pend_opt + q, sizeof(gap_opt_t)) == 0) break;
+            if (t == n_tab) tab[n_tab++] = pend_opt[q];
+            pi[q] = (uint32_t)t;
+        }
+        if (hsa_splice_match_batch(g_idx, pc, po, pl, (size_t)n_pend, (const hsa_gap_opt_t *)tab, (size_t)n_tab, pi, pn, pa, NULL)) die_gpu();
+        for (q = 0; q < n_pend; ++q) {
+            bwa_seq_t *p = seqs + pend_read[q];
+            p->n_aln = pn[q];
+            if (pn[q]) {                                       /* res_aln: calloc(2, ...) in the reference (bwtgap.c:853) */
+                p->aln = (bwt_aln1_t *)calloc(2, sizeof(bwt_aln1_t));
+                memcpy(p->aln, pa + 2 * (size_t)q, sizeof(bwt_aln1_t) * 2);
+            } else p->aln = NULL;                              /* bwtaln.c:366-369 */
+        }
+        free(pc); free(po); free(pl); free(pi); free(pn); free(pa); free(tab);
+    }
     (void)leaked; (void)sel;
+    free(pend_read); free(pend_opt);
     free(codes); free(off); free(len); free(state); free(sel);
     free(aux->width_seed); free(aux->width_fore); free(aux->width_back); free(aux->rc_seq);
     gap_destroy_stack(aux->stack);

@@ -44,9 +44,14 @@ def workdir(tmp_path_factory):
     return d
 
 
+@pytest.mark.parametrize("splice_on_gpu", ["1", "0"], ids=["splice_on_gpu", "splice_on_host"])
 @pytest.mark.parametrize("opts", [[], ["mode=2"], ["fnr=0", "max_diff=3", "max_gapo=2"], ["batch=1700"]],
                          ids=["default_gape_switch", "mode_without_gape", "fixed_maxdiff", "small_batches"])
-def test_gpu_driver_matches_stock_driver(workdir, opts):
+def test_gpu_driver_matches_stock_driver(workdir, opts, splice_on_gpu, monkeypatch):
+    """splice_on_gpu: the reads that found nothing go through hsa_splice_match_batch (bwt_splice_match on the GPU, one
+    batch per driver call, each read with the option state the driver holds for it); splice_on_host: through the
+    reference's own bwt_splice_match.  Either way every read's output equals the stock driver's."""
+    monkeypatch.setenv("HSA_GPU_SPLICE", splice_on_gpu)
     args = list(opts)
     if not any(o.startswith("batch=") for o in args):
         args.append("batch=3000")
