@@ -269,9 +269,14 @@ __global__ void __launch_bounds__(BLOCK) coop_kernel(const __grid_constant__ Par
 // Splice fallback (hsa_splice.cuh): persistent grid, one read per thread at a time, atomic work queue.  Every thread owns
 // a slice of the scratch arrays (stack arena, hit lists, width arrays); reads that outgrow it are listed for a re-run
 // with larger slices.
-__global__ void __launch_bounds__(128) splice_kernel(const __grid_constant__ SpliceParams P)
+__global__ void __launch_bounds__(128) splice_kernel(const __grid_constant__ SpliceParams P, uint32_t lane_stride)
 {
-    const size_t worker = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // Small batches are latency-bound: 32 lanes on 32 different control flows run one after the other, so a read takes
+    // 32 x longer than on a lane that has its warp to itself.  lane_stride > 1 leaves only every lane_stride-th lane of a
+    // warp working (the host picks it so that the batch still fills the machine once).
+    const uint32_t lane = threadIdx.x & 31u;
+    if (lane % lane_stride) return;
+    const size_t worker = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / lane_stride;
     for (;;) {
         const unsigned long long w = atomicAdd(P.cursor, 1ull);
         if (w >= P.n_work) break;
@@ -394,6 +399,7 @@ struct hsa_index {
     mutable uint32_t sa_seq = 0;
     uint32_t *blocks4 = nullptr; uint32_t n_blocks = 0;                               // HSP::blockList rows (optional)
     uint32_t *packed_dna = nullptr; uint32_t dna_length = 0;                          // HSP::packedDNA (optional; splice path)
+    struct SpliceCache *splice_cache = nullptr;                                       // per-worker scratch of the splice path, kept between calls
 };
 
 struct Scratch {                             // worker-private device memory for one launch configuration
@@ -675,6 +681,7 @@ extern "C" int hsa_index_from_blocks(int device, const uint32_t meta_fwd[7], con
 }
 
 extern "C" void hsa_workspace_free(hsa_workspace_t *ws);
+static void splice_cache_free(struct SpliceCache *c);
 
 extern "C" void hsa_index_free(hsa_index_t *ix)
 {
@@ -686,6 +693,7 @@ extern "C" void hsa_index_free(hsa_index_t *ix)
     if (ix->own_ref) for (int d = 0; d < 2; ++d) { cudaFree(ix->ref_code[d]); cudaFree(ix->ref_occ[d]); cudaFree(ix->ref_major[d]); }
     if (ix->own_blocks) for (int d = 0; d < 2; ++d) cudaFree(ix->blocks[d]);
     cudaFree(ix->sa_value); cudaFree(ix->sa_counters); cudaFree(ix->blocks4); cudaFree(ix->packed_dna);
+    splice_cache_free(ix->splice_cache);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -841,35 +849,51 @@ extern "C" int hsa_index_attach_packed_dna(hsa_index_t *ix, const uint32_t *pack
 }
 
 namespace {
-struct DevBuf {                    // cudaMalloc'd array released on scope exit
-    void *p = nullptr;
+struct DevBuf {                    // cudaMalloc'd array, grown on demand, released on scope exit
+    void *p = nullptr; size_t cap = 0;
     ~DevBuf() { cudaFree(p); }
-    int alloc(size_t bytes) { cudaFree(p); p = nullptr; return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
+    int alloc(size_t bytes)
+    {
+        if (bytes <= cap && p) return 0;
+        cudaFree(p); p = nullptr; cap = 0;
+        if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { p = nullptr; return -1; }
+        cap = bytes;
+        return 0;
+    }
+    void release() { cudaFree(p); p = nullptr; cap = 0; }
     template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 }
+struct SpliceCache { DevBuf arena, heads, widths, lists, sites, pos, codes, off, len, opts, oi, n, aln, status, fail, cnt, again; };
+static void splice_cache_free(SpliceCache *c) { delete c; }
 
 // one pass of splice_kernel over `n_work` reads with per-worker scratch of the given capacities
-static int splice_pass(const hsa_index_t *ix, SpliceParams P, uint32_t n_work, const uint32_t *work_list, uint32_t max_workers,
+static int splice_pass(const hsa_index_t *ix, SpliceCache &C, SpliceParams P, uint32_t n_work, const uint32_t *work_list, uint32_t max_workers,
                        uint32_t arena_cap, uint32_t aln_cap, uint32_t site_cap, unsigned long long *counters, cudaStream_t s)
 {
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, splice_kernel, 128, 0));
-    uint32_t grid = (uint32_t)ix->sm_count * (uint32_t)std::max(occ, 1);
-    grid = std::max<uint32_t>(1, std::min<uint32_t>(grid, std::min<uint32_t>((n_work + 127) / 128, std::max<uint32_t>(1, max_workers / 128))));
-    const size_t workers = (size_t)grid * 128, wl = (size_t)P.max_len + 1;
-    DevBuf arena, heads, widths, lists, sites, pos;
-    if (arena.alloc(workers * arena_cap * sizeof(SEntry)) || heads.alloc(workers * SPL_BUCKETS * 4) ||
-        widths.alloc(workers * (3 * wl + 16) * sizeof(SWidth)) || lists.alloc(workers * 6 * aln_cap * sizeof(SAln)) ||
-        sites.alloc(workers * site_cap * 4) || pos.alloc(workers * SPL_POS_CAP * sizeof(SPos)))
+    const uint32_t grid_full = (uint32_t)ix->sm_count * (uint32_t)std::max(occ, 1);
+    // lanes per warp that work: all 32 when the batch has enough reads for every lane of a full grid, fewer (down to one)
+    // for small batches, so that a read's latency is not multiplied by the divergence of its warp
+    uint32_t lane_stride = 32;
+    while (lane_stride > 1 && (uint64_t)grid_full * 128 / lane_stride < n_work) lane_stride >>= 1;
+    uint32_t workers = std::min<uint32_t>(std::min<uint32_t>(grid_full * 128 / lane_stride, max_workers), std::max<uint32_t>(n_work, 1));
+    const uint32_t per_block = 128 / lane_stride;
+    const uint32_t grid = std::max<uint32_t>(1, (workers + per_block - 1) / per_block);
+    workers = grid * per_block;
+    const size_t wl = (size_t)P.max_len + 1;
+    if (C.arena.alloc((size_t)workers * arena_cap * sizeof(SEntry)) || C.heads.alloc((size_t)workers * SPL_BUCKETS * 4) ||
+        C.widths.alloc((size_t)workers * (3 * wl + 16) * sizeof(SWidth)) || C.lists.alloc((size_t)workers * 6 * aln_cap * sizeof(SAln)) ||
+        C.sites.alloc((size_t)workers * site_cap * 4) || C.pos.alloc((size_t)workers * SPL_POS_CAP * sizeof(SPos)))
         return fail(HSA_E_CUDA, "out of device memory for the splice scratch");
-    CU(cudaMemsetAsync(widths.p, 0, workers * (3 * wl + 16) * sizeof(SWidth), s));       // the driver's calloc (bwtaln.c:283-285)
-    P.arena = arena.as<SEntry>(); P.arena_cap = arena_cap; P.heads = heads.as<uint32_t>(); P.widths = widths.as<SWidth>();
-    P.lists = lists.as<SAln>(); P.aln_cap = aln_cap; P.site_pos = sites.as<uint32_t>(); P.site_cap = site_cap; P.pos_info = pos.as<SPos>();
+    CU(cudaMemsetAsync(C.widths.p, 0, (size_t)workers * (3 * wl + 16) * sizeof(SWidth), s));     // the driver's calloc (bwtaln.c:283-285)
+    P.arena = C.arena.as<SEntry>(); P.arena_cap = arena_cap; P.heads = C.heads.as<uint32_t>(); P.widths = C.widths.as<SWidth>();
+    P.lists = C.lists.as<SAln>(); P.aln_cap = aln_cap; P.site_pos = C.sites.as<uint32_t>(); P.site_cap = site_cap; P.pos_info = C.pos.as<SPos>();
     P.n_work = n_work; P.work_list = work_list;
     P.cursor = counters; P.fail_count = counters + 1; P.lookups = counters + 2;
     CU(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), s));                 // cursor + fail count; lookups accumulate
-    splice_kernel<<<grid, 128, 0, s>>>(P);
+    splice_kernel<<<grid, 128, 0, s>>>(P, lane_stride);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
     return HSA_OK;
@@ -905,7 +929,11 @@ extern "C" int hsa_splice_match_batch(const hsa_index_t *ix, const uint8_t *code
     }
     CU(cudaSetDevice(ix->device));
     cudaStream_t s = ix->stream;
-    DevBuf d_codes, d_off, d_len, d_opts, d_oi, d_n, d_aln, d_status, d_fail, d_cnt;
+    hsa_index *mix = const_cast<hsa_index *>(ix);
+    if (!mix->splice_cache) mix->splice_cache = new SpliceCache();
+    SpliceCache &C = *mix->splice_cache;
+    DevBuf &d_codes = C.codes, &d_off = C.off, &d_len = C.len, &d_opts = C.opts, &d_oi = C.oi, &d_n = C.n, &d_aln = C.aln,
+           &d_status = C.status, &d_fail = C.fail, &d_cnt = C.cnt;
     if (d_codes.alloc(bytes + 16) || d_off.alloc(n_reads * 8) || d_len.alloc(n_reads * 4) || d_opts.alloc(n_opts * sizeof(DevOpt)) ||
         d_oi.alloc(n_reads * 4) || d_n.alloc(n_reads * 4) || d_aln.alloc(n_reads * 18 * 4) || d_status.alloc(n_reads) ||
         d_fail.alloc((n_reads + 1) * 4) || d_cnt.alloc(4 * sizeof(unsigned long long)))
@@ -930,17 +958,21 @@ extern "C" int hsa_splice_match_batch(const hsa_index_t *ix, const uint8_t *code
     // first pass: every read, small slices for many workers; then the reads that outgrew them, large slices for few
     const uint32_t arena_cap = (uint32_t)std::max<long>(64, env_long("HSA_B200_SPLICE_ARENA", 2048));
     const uint32_t aln_cap = (uint32_t)std::max<long>(16, env_long("HSA_B200_SPLICE_ALNS", 128));
-    if ((rc = splice_pass(ix, P, (uint32_t)n_reads, nullptr, 1u << 20, arena_cap, aln_cap, 512, cnt, s))) return rc;
+    if ((rc = splice_pass(ix, C, P, (uint32_t)n_reads, nullptr, 1u << 20, arena_cap, aln_cap, 512, cnt, s))) return rc;
     unsigned long long h[3];
     CU(cudaMemcpy(h, cnt, sizeof(h), cudaMemcpyDeviceToHost));
     if (h[1]) {
         const uint32_t n_fail = (uint32_t)h[1];
-        DevBuf again;
+        DevBuf &again = C.again;
         if (again.alloc((size_t)n_fail * 4)) return fail(HSA_E_CUDA, "out of device memory");
         CU(cudaMemcpy(again.p, d_fail.p, (size_t)n_fail * 4, cudaMemcpyDeviceToDevice));
-        if ((rc = splice_pass(ix, P, n_fail, again.as<uint32_t>(), 4096, 1u << 18, 1u << 13, 1u << 14, cnt, s))) return rc;
+        // large slices for few workers (2 MB of stack + 1.2 MB of hit lists each); the arrays are not kept afterwards
+        C.arena.release(); C.lists.release(); C.sites.release();
+        rc = splice_pass(ix, C, P, n_fail, again.as<uint32_t>(), 4096, 1u << 16, 1u << 12, 1u << 13, cnt, s);
+        C.arena.release(); C.lists.release(); C.sites.release();
+        if (rc) return rc;
         CU(cudaMemcpy(h, cnt, sizeof(h), cudaMemcpyDeviceToHost));
-        if (h[1]) return fail(HSA_E_CAPACITY, "a read exceeded the splice path's large-capacity scratch (262144 stack entries, 8192 hits per seed)");
+        if (h[1]) return fail(HSA_E_CAPACITY, "a read exceeded the splice path's large-capacity scratch (65536 stack entries, 4096 hits per seed)");
     }
     CU(cudaMemcpyAsync(n_aln_out, d_n.p, n_reads * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(aln_out, d_aln.p, n_reads * 18 * 4, cudaMemcpyDeviceToHost, s));

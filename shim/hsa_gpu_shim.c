@@ -98,6 +98,16 @@ void hsa_gpu_close(void)
 
 static void die_gpu(void) { fprintf(stderr, "[hsa_gpu] %s\n", hsa_last_error()); exit(1); }
 
+/* bwa_cal_maxdiff (bwtaln.c:46-58) is a pure function of (length, fnr): one table per fnr instead of an exp() per read */
+static int maxdiff_of(int len, float fnr)
+{
+    static int tab[4096]; static float tab_fnr = -1.0f;
+    if (len < 0 || len >= 4096) return bwa_cal_maxdiff(len, BWA_AVG_ERR, fnr);
+    if (tab_fnr != fnr) { memset(tab, 0xff, sizeof(tab)); tab_fnr = fnr; }
+    if (tab[len] < 0) tab[len] = bwa_cal_maxdiff(len, BWA_AVG_ERR, fnr);
+    return tab[len];
+}
+
 /* same signature and contract as bwt_match_gap (bwtgap.h:26; bwtgap.c:118-331): one search on the GPU with the frame the
  * caller built in `aux` -- sequence by aux->strand, aux->len, aux->width_back (rewritten in place by gap_shadow, as the
  * reference does), aux->width_seed, aux->opt.  Returns a malloc-family array the caller frees (never NULL).  Serves the
@@ -205,7 +215,7 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
             if (pa || pt) continue;                            /* :324-325 */
         }
         aux->seq = p->seq; aux->len = p->len;
-        if (opt->fnr > 0.0) aux->opt->max_diff = bwa_cal_maxdiff(p->len, BWA_AVG_ERR, opt->fnr);  /* :330-331, through aux->opt */
+        if (opt->fnr > 0.0) aux->opt->max_diff = maxdiff_of(p->len, opt->fnr);                    /* :330-331, through aux->opt */
         aux->opt->seed_len = opt->seed_len < (int)p->len ? opt->seed_len : 0x7fffffff;            /* :332 */
         if (res->n_aln[ri] > 0) {
             /* the GPU result: hits in the reference's order, strand stamped on every hit, start/end on the first */
