@@ -115,6 +115,44 @@ __global__ void __launch_bounds__(256) sa_kernel(DevBwt fwd, const uint32_t *sa_
     if (lane == 0 && steps_total) atomicAdd(steps_total, steps);
 }
 
+// Pre-binning of ragged batches (north star: "reads pre-binned by length and max_diff"): a counting sort of the batch's
+// work order by read length, longest first.  max_diff is a function of the length (bwtaln.c:330-331), so one bin = one
+// (length, max_diff) class: the lanes of a warp then walk reads of one shape through the width pass and start searches of
+// similar depth, and the longest searches start first.  Only the ORDER of work changes: results are written per item.
+enum : uint32_t { BIN_LENS = 4096 };
+__global__ void __launch_bounds__(256) bin_count_kernel(const uint32_t *len, uint32_t n, uint32_t *hist)
+{
+    __shared__ uint32_t sh[BIN_LENS];
+    for (uint32_t i = threadIdx.x; i < BIN_LENS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sh[min(len[i], BIN_LENS - 1u)], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < BIN_LENS; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// hist[L] -> first work index of length L, lengths in descending order (one block of BIN_LENS / 4 threads)
+__global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t *hist)
+{
+    __shared__ uint32_t part[1024];
+    const uint32_t t = threadIdx.x;
+    uint32_t v[4], sum = 0;
+    for (int q = 0; q < 4; ++q) { v[q] = hist[BIN_LENS - 1u - (4u * t + q)]; sum += v[q]; }
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        const uint32_t add = t >= d ? part[t - d] : 0u;
+        __syncthreads();
+        part[t] += add;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - sum;
+    for (int q = 0; q < 4; ++q) { hist[BIN_LENS - 1u - (4u * t + q)] = run; run += v[q]; }
+}
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const uint32_t *len, uint32_t n, uint32_t *next, uint32_t *work_list)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        work_list[atomicAdd(&next[min(len[i], BIN_LENS - 1u)], 1u)] = i;
+}
+
 // Width kernel of the split pipeline: one thread per work item, every thread of a warp walks reads of the
 // same shape, so the loop is divergence-free (bwt_cal_width is a strictly sequential chain per read).
 __global__ void __launch_bounds__(256, 5) width_kernel(const __grid_constant__ Params P)
@@ -457,6 +495,7 @@ struct hsa_workspace {
     uint32_t stage_next = 0;
     DevOpt *opts_host = nullptr;                                       // the stage of the current batch (host-side reads)
     uint8_t *status_dev = nullptr; size_t status_cap = 0;
+    uint32_t *bin_list = nullptr; size_t bin_list_cap = 0; uint32_t *bin_hist = nullptr;    // pre-binned work order of a ragged batch
     // staging for the host-buffer entry points
     uint8_t *codes_dev = nullptr; size_t codes_cap = 0;
     uint64_t *off_dev = nullptr; uint32_t *len_dev = nullptr; size_t reads_cap = 0;
@@ -478,6 +517,7 @@ struct hsa_workspace {
     uint32_t arena_cap = 1022, hit_cap = 32;
     uint32_t vote_slow_min = VOTE_SLOW_MIN_DEFAULT; int32_t vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
     bool use_coop = true; uint32_t step_budget = 0, drain_budget = 1000;
+    bool prebin = true;
 };
 
 template <typename T>
@@ -1012,7 +1052,7 @@ extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
     for (Pipe &p : ws->pipes) p.release();
     ws->strict.release(); ws->heavy.release();
     cudaFree(ws->counters); cudaFree(ws->strict_list); cudaFree(ws->strict2_list); cudaFree(ws->opts_dev); cudaFree(ws->len2opt_dev);
-    cudaFree(ws->status_dev); cudaFree(ws->codes_dev); cudaFree(ws->off_dev); cudaFree(ws->len_dev);
+    cudaFree(ws->status_dev); cudaFree(ws->codes_dev); cudaFree(ws->off_dev); cudaFree(ws->len_dev); cudaFree(ws->bin_list); cudaFree(ws->bin_hist);
     cudaFree(ws->tasks_dev); cudaFree(ws->n_aln_dev); cudaFree(ws->aln_off_dev); cudaFree(ws->aln_dev);
     cudaFree(ws->width_out_dev); cudaFree(ws->bid_dev);
     for (int i = 0; i < hsa_workspace::OPT_STAGES; ++i) {
@@ -1104,6 +1144,7 @@ struct Batch {                      // everything one batch needs, device pointe
     uint32_t kind = 0, n_groups = 0, n_items = 0, max_len = 0, n_opts = 0, n_buckets = 1, max_seed_len = 0;
     int32_t filter_max_n = 0;
     bool scores_positive = true;    // every option set has s_mm, s_gapo, s_gape >= 1 (the cooperative stage needs that)
+    bool ragged = false;            // KIND_WHOLE: more than one read length in the batch -> pre-bin the work order
     const uint8_t *codes = nullptr; const Task *tasks = nullptr;
     const uint64_t *read_off = nullptr; const uint32_t *read_len = nullptr;
     int32_t *n_aln = nullptr; uint64_t *aln_off = nullptr; uint32_t *aln = nullptr; uint64_t aln_cap = 0;
@@ -1173,6 +1214,7 @@ static int configure(hsa_workspace *ws)
     ws->use_coop = env_long("HSA_B200_COOP", 1) != 0;
     ws->step_budget = (uint32_t)std::max<long>(0, env_long("HSA_B200_STEP_BUDGET", 0));
     ws->drain_budget = (uint32_t)std::max<long>(0, env_long("HSA_B200_DRAIN_BUDGET", 1000));
+    ws->prebin = env_long("HSA_B200_PREBIN", 1) != 0;
     ws->configured = true;
     return HSA_OK;
 }
@@ -1343,6 +1385,19 @@ static int batch_enqueue(hsa_workspace *ws, const Batch &b, cudaStream_t stream,
 
     CU(cudaMemsetAsync(ws->counters, 0, CNT_ALLOC * sizeof(unsigned long long), stream));
     CU(cudaEventRecord(ws->ev0, stream));
+    const uint32_t *binned = nullptr;
+    if (b.kind == KIND_WHOLE && b.ragged && ws->prebin && b.n_items > 1) {
+        if ((rc = ensure(ws->bin_list, ws->bin_list_cap, (size_t)b.n_items))) return rc;
+        if (!ws->bin_hist) CU(cudaMalloc((void **)&ws->bin_hist, BIN_LENS * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(ws->bin_hist, 0, BIN_LENS * sizeof(uint32_t), stream));
+        const unsigned g = (unsigned)std::min<uint64_t>((uint64_t)ix->sm_count * 4, ((uint64_t)b.n_items + 255) / 256);
+        bin_count_kernel<<<g, 256, 0, stream>>>(b.read_len, b.n_items, ws->bin_hist);
+        bin_scan_kernel<<<1, 1024, 0, stream>>>(ws->bin_hist);
+        bin_scatter_kernel<<<g, 256, 0, stream>>>(b.read_len, b.n_items, ws->bin_hist, ws->bin_list);
+        CU(cudaGetLastError());
+        ws->last_launches += 3; trace_mark(ws, "prebin", stream);
+        binned = ws->bin_list;
+    }
     const uint64_t chunk = std::min<uint64_t>(ws->chunk_items, std::max<uint64_t>(n_work_total, 1));
     const uint32_t n_chunks = (uint32_t)((n_work_total + chunk - 1) / chunk);
     const uint32_t n_pipes = std::min<uint32_t>(ws->n_pipes, std::max<uint32_t>(n_chunks, 1));
@@ -1361,6 +1416,7 @@ static int batch_enqueue(hsa_workspace *ws, const Batch &b, cudaStream_t stream,
         cudaStream_t s = n_pipes > 1 ? pp.stream : stream;
         StageIO io;
         io.work_base = (uint32_t)w0; io.n_work = nw;
+        if (binned) io.work_list = binned + w0;               // work index -> read, longest reads first
         io.flag_list = ws->strict_list; io.flag_count = ws->counters + CNT_STRICT;
         if ((rc = issue_chunk(ws, b, P, pp, (int)(c % n_pipes), v, io, s))) return rc;
     }
@@ -1839,6 +1895,7 @@ extern "C" int hsa_whole_reads_submit(const hsa_index_t *ix, const uint8_t *code
         (rc = upload_opts(ws, opts, max_len, &b, &l2o, j->ix->h2d))) { job_release(j); return rc; }
     b.kind = KIND_WHOLE; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads; b.max_len = max_len;
     b.n_opts = (uint32_t)opts.size(); b.codes = ws->codes_dev; b.read_off = ws->off_dev; b.read_len = ws->len_dev;
+    b.ragged = lens.size() > 1;
     if ((rc = job_launch(j))) { job_release(j); return rc; }
     *job = j;
     return HSA_OK;
@@ -1944,6 +2001,7 @@ extern "C" int hsa_whole_reads_device(const hsa_index_t *ix, hsa_workspace_t *ws
     if ((rc = upload_opts(ws, opts, max_len, &b, &l2o, s))) return rc;
     b.kind = KIND_WHOLE; b.n_groups = (uint32_t)n_reads; b.n_items = (uint32_t)n_reads; b.max_len = max_len;
     b.n_opts = (uint32_t)opts.size(); b.codes = codes_dev; b.read_off = off_dev; b.read_len = len_dev;
+    b.ragged = n_lens_present > 1;
     b.n_aln = n_aln_dev; b.aln_off = aln_off_dev; b.aln = reinterpret_cast<uint32_t *>(aln_dev); b.aln_cap = aln_capacity;
     uint64_t stats[CNT_N]; float ms = 0;
     if ((rc = run_batch(ws, b, s, false, stats, &ms))) return rc;

@@ -407,3 +407,24 @@ def test_short_reads_and_filters_vs_oracle(golden, golden_index, dev_index):
     assert np.array_equal(el.aln9_to_rows12(res.ordered()), rows_ref)
     assert res.occ_lookups == o.last_lookups
     assert int(n_ref.sum()) > 300 and int((n_ref[1:60:3] == 0).sum()) >= 15
+
+
+@pytest.mark.parametrize("prebin", ["1", "0"], ids=["prebinned_by_length", "input_order"])
+def test_ragged_batch_vs_oracle(monkeypatch, prebin):
+    """A ragged batch (33..140 bp, so max_diff 3..6 and both seeded and unseeded reads) with and without the pre-binning
+    of the work order by (length, max_diff): bit-exact against the oracle either way, results in input order."""
+    monkeypatch.setenv("HSA_B200_PREBIN", prebin)
+    g = synth.make_genome(2000003, 51)
+    index = index_build.build_index(g, device="cuda")
+    ix = api.Index.upload(index, 0)
+    try:
+        rs = synth.ragged_reads(g, 24000, 33, 140, 52, sub_rate=0.012)
+        res = ix.whole_reads(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, api.gap_init_opt())
+        o = ol.Oracle(index)
+        n_ref, rows_ref = o.whole(rs, ol.default_opt())
+        assert np.array_equal(res.n_aln, n_ref)
+        assert np.array_equal(el.aln9_to_rows12(res.ordered()), rows_ref)
+        assert res.occ_lookups == o.last_lookups
+        assert int((n_ref > 0).sum()) > 0.9 * rs.n
+    finally:
+        ix.close()
