@@ -65,6 +65,7 @@ extern __shared__ __align__(16) unsigned char hsa_smem[];
 static thread_local unsigned char *hsa_smem_host = nullptr;
 #define HSA_SMEM hsa_smem_host
 static unsigned long long hsa_host_pair_count = 0, hsa_host_pair_same_sector = 0;   // emulation statistics
+static unsigned long long hsa_host_pop_out[8];           // emulation statistics: what a POP step led to (by next state)
 static unsigned long long hsa_host_hist[3][2][64];     // emulation statistics: lookup pairs by kind {expand, exact, materialise} x {two sectors, one} x depth
 #endif
 
@@ -944,6 +945,9 @@ struct Worker {
         }
         c_meta = m;
         vet();
+#if !defined(__CUDA_ARCH__)
+        ++hsa_host_pop_out[st == LS_POP ? 0 : st == LS_LOOKUP ? (pend ? 1 : 2) : st == LS_HIT ? 3 : 4];
+#endif
     }
 
     // ---------------------------------------------------------------- LOOKUP: one occ4 pair + what follows

@@ -218,3 +218,39 @@ def build_index(genome_codes, device: str | torch.device | None = None, sa_inter
     fwd = _to_arrays(build_bwt(text, sa_interval))
     rev = _to_arrays(build_bwt(torch.flip(text, dims=[0])))
     return Index2BWT(fwd, rev)
+
+
+def pack_dna_words(text: torch.Tensor, chunk: int = 1 << 28) -> np.ndarray:
+    """HSP::packedDNA (16 symbols per 32-bit word, first symbol in the two MSBs; index_io.pack_dna) of a text held as a
+    torch tensor, packed where the tensor lives (a 3.1 Gb text is packed on the GPU in chunks)."""
+    n = int(text.shape[0])
+    words = (n + 15) // 16 + 1
+    out = np.zeros(words, dtype=np.uint32)
+    sh = (30 - 2 * torch.arange(16, device=text.device, dtype=torch.int64))
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        t = text[lo:hi].to(torch.int64)
+        pad = (-t.shape[0]) % 16
+        if pad:
+            t = torch.cat([t, torch.zeros(pad, dtype=torch.int64, device=text.device)])
+        w = (t.reshape(-1, 16) << sh[None, :]).sum(dim=1)
+        out[lo // 16: lo // 16 + w.shape[0]] = w.to("cpu").numpy().astype(np.uint32)
+    return out
+
+
+def build_full_index(genome_codes, device=None, names=None) -> Index2BWT:
+    """Everything bwa_cal_sa_reg_gap reads for a one-record (or multi-record: pass the record lengths as `names` = list of
+    (name, length)) ACGT-only genome: both BWTs, the forward SA samples, the block list and the packed text."""
+    from .index_io import Blocks, blocks_of_records
+    ix = build_index(genome_codes, device=device)
+    text = torch.as_tensor(np.ascontiguousarray(genome_codes) if isinstance(genome_codes, np.ndarray) else genome_codes)
+    n = int(text.shape[0])
+    if names is None:
+        ix.blocks = blocks_of_records([n])
+        ix.blocks.names = ["synth"]
+    else:
+        ix.blocks = blocks_of_records([ln for _, ln in names])
+        ix.blocks.names = [nm for nm, _ in names]
+    dev = device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu")
+    ix.packed_dna, ix.dna_length = pack_dna_words(text.to(dev)), n
+    return ix

@@ -213,6 +213,43 @@ def save_pac(text: np.ndarray, path: str) -> None:
         f.write(bytes([n % 4]))
 
 
+def save_ann(blocks: Blocks, n_chars: int, path: str) -> None:
+    """`<prefix>.index.ann` as the reference builder writes it (HSP.c:325-339): total characters, record count and the
+    FASTA random seed (0), one line per record name, the block count, one line per block."""
+    with open(path, "w") as f:
+        f.write("%u\t%d\t%d\n" % (n_chars, len(blocks.names), 0))
+        for nm in blocks.names:
+            f.write("%d\t%s\n" % (len(nm), nm))
+        f.write("%d\n" % blocks.n)
+        for row in blocks.table().tolist():
+            f.write("%d\t%u\t%u\t%u\n" % tuple(row))
+
+
+def pack_bytes_of_words(words: np.ndarray, n: int) -> np.ndarray:
+    """The .pac body (four symbols per byte, first in the MSBs) from the in-memory packed words."""
+    return np.ascontiguousarray(words[: (n + 15) // 16]).astype(">u4").view(np.uint8)[: (n + 3) // 4]
+
+
+def save_index(ix: Index2BWT, prefix: str) -> None:
+    """Write every file BWTLoad2BWT reads (2BWT-Interface.c:13-66) in the reference's own formats, so that an index made
+    by the product's builder loads into the unmodified reference (`HSA aln <prefix> ...`): .index.{bwt,fmv,rev.bwt,rev.fmv}
+    and, when the index carries them, .index.sa (BWTConstruct.c:1373-1392), .index.pac (HSP.c:311-323), .index.ann."""
+    p = prefix + ".index"
+    save_bwt(ix.fwd, p + ".bwt", p + ".fmv")
+    save_bwt(ix.rev, p + ".rev.bwt", p + ".rev.fmv")
+    if ix.fwd.sa_value is not None:
+        save_sa(ix.fwd, p + ".sa")
+    if ix.packed_dna is not None:
+        n = int(ix.dna_length)
+        with open(p + ".pac", "wb") as f:
+            pack_bytes_of_words(ix.packed_dna, n).tofile(f)
+            if n % 4 == 0:
+                f.write(b"\0")
+            f.write(bytes([n % 4]))
+    if ix.blocks is not None:
+        save_ann(ix.blocks, int(ix.fwd.text_length), p + ".ann")
+
+
 def load_index(prefix: str, with_sa: bool = True) -> Index2BWT:
     """Load `<prefix>.index.{bwt,fmv,rev.bwt,rev.fmv}` (and `.sa` if present) as written by `HSA index <prefix> <fasta>`."""
     import os

@@ -66,3 +66,47 @@ def simulate_spliced_reads(genome: torch.Tensor, n: int, length: int, seed: int,
     reads = torch.where(sub, (reads + torch.randint(1, 4, (n, length), dtype=torch.uint8, device=dev, generator=gen)) & 3, reads)
     rc = torch.rand((n, 1), device=dev, generator=gen) < 0.5
     return torch.where(rc, 3 - torch.flip(reads, dims=[1]), reads)
+
+
+def plant_introns(genome: torch.Tensor, n_introns: int, seed: int, min_intron: int = 60, max_intron: int = 20000) -> torch.Tensor:
+    """Write the splice motifs the reference looks for (bwtgap.c:536-537) at the ends of `n_introns` non-overlapping
+    intervals of `genome` (in place): 80 % GT..AG, 10 % GC..AG, 10 % AT..AC.  Returns introns[n, 2] = first and
+    one-past-last intron base (int64, on the genome's device)."""
+    dev = genome.device
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    G = int(genome.shape[0])
+    slot = (G - 600) // n_introns
+    assert slot > max_intron + 900, "too many introns for this genome"
+    ilen = torch.randint(min_intron, max_intron + 1, (n_introns,), generator=gen)
+    a = 300 + torch.arange(n_introns) * slot + 200 + (torch.rand(n_introns, generator=gen) * (slot - ilen - 400).float()).long()
+    b = a + ilen
+    kind = torch.rand(n_introns, generator=gen)
+    d0 = torch.where(kind < 0.9, torch.tensor(2), torch.tensor(0))                    # G G A
+    d1 = torch.where(kind < 0.8, torch.tensor(3), torch.where(kind < 0.9, torch.tensor(1), torch.tensor(3)))   # T C T
+    a1 = torch.where(kind < 0.9, torch.tensor(2), torch.tensor(1))                    # AG AG AC
+    g = genome
+    g[a.to(dev)] = d0.to(dev, torch.uint8)
+    g[(a + 1).to(dev)] = d1.to(dev, torch.uint8)
+    g[(b - 2).to(dev)] = torch.zeros(n_introns, dtype=torch.uint8, device=dev)
+    g[(b - 1).to(dev)] = a1.to(dev, torch.uint8)
+    return torch.stack([a, b], dim=1).to(dev)
+
+
+def simulate_junction_reads(genome: torch.Tensor, introns: torch.Tensor, n: int, length: int, seed: int,
+                            sub_rate: float = 0.01, min_anchor: int = 8) -> torch.Tensor:
+    """uint8 [n, length] reads across the planted introns: `left` exon bases ending at the intron start joined to
+    length - left bases from the intron end; substitutions; 50 % reverse-complemented."""
+    dev = genome.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    which = torch.randint(0, introns.shape[0], (n,), device=dev, generator=gen)
+    left = torch.randint(min_anchor, length - min_anchor + 1, (n, 1), device=dev, generator=gen)
+    a, b = introns[which, 0][:, None], introns[which, 1][:, None]
+    j = torch.arange(length, device=dev)[None, :]
+    pos = torch.where(j < left, a - left + j, b + (j - left))
+    reads = genome[pos]
+    sub = torch.rand((n, length), device=dev, generator=gen) < sub_rate
+    reads = torch.where(sub, (reads + torch.randint(1, 4, (n, length), dtype=torch.uint8, device=dev, generator=gen)) & 3, reads)
+    rc = torch.rand((n, 1), device=dev, generator=gen) < 0.5
+    return torch.where(rc, 3 - torch.flip(reads, dims=[1]), reads)

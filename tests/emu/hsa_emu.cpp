@@ -332,6 +332,7 @@ uint64_t emu_splice(void *p, const uint32_t *sa_value, uint32_t sa_interval, con
     return lookups;
 }
 
+void emu_pop_out(uint64_t *o) { memcpy(o, hsa_host_pop_out, sizeof(hsa_host_pop_out)); memset(hsa_host_pop_out, 0, sizeof(hsa_host_pop_out)); }
 void emu_hist(uint64_t *o) { memcpy(o, hsa_host_hist, sizeof(hsa_host_hist)); memset(hsa_host_hist, 0, sizeof(hsa_host_hist)); }
 void emu_set_simt(int on) { g_simt = on; for (int i = 0; i < 3; ++i) { g_phase_runs[i] = 0; g_phase_lanes[i] = 0; } }
 void emu_phase_stats(uint64_t *runs, uint64_t *lanes) { for (int i = 0; i < 3; ++i) { runs[i] = g_phase_runs[i]; lanes[i] = g_phase_lanes[i]; } }

@@ -48,15 +48,20 @@ def run_ref(args):
 class Scale:
     """A synthetic genome indexed on the GPU by the product's builder, written where the reference binary loads it."""
 
-    def __init__(self, length: int, seed: int, sa: bool = False):
+    def __init__(self, length: int, seed: int, full: bool = False, n_introns: int = 0):
+        """full: everything bwa_cal_sa_reg_gap reads (SA samples, annotation, packed text) for the splice path, with
+        `n_introns` motif-carrying introns planted in the text; all seven files are written in the reference's formats
+        by the product's own writer (index_io.save_index)."""
         self.dev = torch.device("cuda", 0)
         self.td = tempfile.mkdtemp(prefix="hsa_scale_")
         self.genome = synth_torch.make_genome(length, seed, self.dev)
-        self.index = index_build.build_index(self.genome, device=self.dev, sa_interval=index_io.SA_INTERVAL if sa else 0)
+        self.introns = synth_torch.plant_introns(self.genome, n_introns, seed + 1) if n_introns else None
         self.prefix = os.path.join(self.td, "g")
-        p = self.prefix + ".index"
-        index_io.save_bwt(self.index.fwd, p + ".bwt", p + ".fmv")
-        index_io.save_bwt(self.index.rev, p + ".rev.bwt", p + ".rev.fmv")
+        if full:
+            self.index = index_build.build_full_index(self.genome, device=self.dev)
+        else:
+            self.index = index_build.build_index(self.genome, device=self.dev, sa_interval=0)
+        index_io.save_index(self.index, self.prefix)
         self.ix = api.Index.upload(self.index, 0)
 
     def reads_file(self, name: str, reads_t: torch.Tensor):
@@ -222,7 +227,7 @@ def test_index_46mb_equals_reference_builder(g46):
 def test_whole_reads_3gb_vs_reference_binary():
     """configs[2]: GRCh38-sized 3.1 Gb genome (textLength at 72 % of 2^32, 48 M blocks, 64-bit block offsets), 100 k x
     100 bp reads with default options, against the reference binary on the same index files."""
-    s = Scale(3_100_000_003, 1)
+    s = Scale(3_100_000_003, 1, full=True, n_introns=20_000)
     try:
         reads_t = synth_torch.simulate_reads(s.genome, 100_000, 100, 1000)
         rs, path = s.reads_file("cfg3g", reads_t)
@@ -241,5 +246,19 @@ def test_whole_reads_3gb_vs_reference_binary():
         exp_n, exp_rows, exp_lk = s.reference("seeds", path2, [])
         res = s.ix.splice_seeds(rs2.codes, rs2.offsets[:-1].astype(np.uint64), rs2.lens, api.gap_init_opt())
         assert_same(res, exp_n, exp_rows, exp_lk, "hsa_splice_seeds @3.1 Gb, 25 bp seeds")
+        # the whole spliced-read fallback at this size (configs[3]): bwt_splice_match on the reference, loading the index
+        # files the product wrote, against hsa_splice_match_batch: junction reads over planted introns + random introns
+        jr = torch.cat([synth_torch.simulate_junction_reads(s.genome, s.introns, 16_000, 100, 5, sub_rate=0.015),
+                        synth_torch.simulate_spliced_reads(s.genome, 4_000, 100, 6)])
+        rs3, path3 = s.reads_file("junc3g", jr)
+        out3 = path3 + ".splice.aln"
+        j = run_ref(["splice", s.prefix, path3, out3, f"procs={PROCS}", "clear_gape=1"])
+        exp_n, exp_rows = synth.read_aln_dump(out3)
+        assert j["two_parts"] > 3_000
+        ro = api.GapOpt.from_buffer_copy(bytes(el.resolve_read_opt(ol.default_opt(), 100, 1)))
+        n_aln, aln = s.ix.splice_match(rs3.codes, rs3.offsets[:-1].astype(np.uint64), rs3.lens, ro)
+        keep = np.arange(2)[None, :] < n_aln[:, None]
+        assert np.array_equal(n_aln, exp_n), "hsa_splice_match_batch @3.1 Gb: n_aln differs from the reference"
+        assert np.array_equal(el.aln9_to_rows12(aln[keep]), exp_rows), "hsa_splice_match_batch @3.1 Gb: rows differ from the reference"
     finally:
         s.close()
