@@ -585,6 +585,20 @@ extern "C" int hsa_cal_maxdiff(int l, double err, double thres) // bwa_cal_maxdi
 }
 
 // ---------------------------------------------------------------------------------------------- index
+// The path's memory traffic is random 32-byte sectors, and an L2 miss brings in more than the sector asked for (ncu,
+// 3.1 Gb genome: 831 GB read from DRAM for 396 GB delivered to the SMs).  cudaLimitMaxL2FetchGranularity is the knob
+// CUDA offers for that; on B200 it changes nothing measurable (HSA_B200_L2_FETCH = 32 / 64 / 128 / default: 646.3 /
+// 645.3 / 646.2 / 647.4 ms per 12.5 M-read batch, probe 1220 GB/s each time), so the driver default is left alone
+// unless the variable is set.
+static void apply_l2_fetch_granularity()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const long g = env_long("HSA_B200_L2_FETCH", 0);
+    if (g > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+}
+
 static int init_index_common(hsa_index *ix, int device)
 {
     ix->device = device;
@@ -593,6 +607,7 @@ static int init_index_common(hsa_index *ix, int device)
     CU(cudaStreamCreateWithFlags(&ix->h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ix->d2h, cudaStreamNonBlocking));
     CU(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device));
+    apply_l2_fetch_granularity();
     return HSA_OK;
 }
 
@@ -1838,11 +1853,15 @@ extern "C" int hsa_match_gap_call(const hsa_index_t *ix, const uint8_t *seq, uin
     std::vector<uint8_t> row(P.row_stride, 0);
     uint32_t *w = reinterpret_cast<uint32_t *>(row.data());
     uint32_t w_prev = 0xFFFFFFFFu;
+    bool has_n = false;
     for (uint32_t i = 0; i <= len; ++i) {
         w[i] = width_back[i].w;
-        row[P.row_bid_off + i] = bound_byte((uint32_t)width_back[i].bid, width_back[i].w, w_prev);
+        uint8_t byte = bound_byte((uint32_t)width_back[i].bid, width_back[i].w, w_prev);
+        if (i < len) { if (seq[i] > 3) has_n = true; else byte |= (uint8_t)(seq[i] << BB_BASE_SHIFT); }   // the base of step i
+        row[P.row_bid_off + i] = byte;
         w_prev = width_back[i].w;
     }
+    reinterpret_cast<uint32_t *>(row.data() + P.row_tail_off)[1] = has_n ? ROW_FLAG_HAS_N : 0u;
     if (seed_mode == HSA_SEED_TAIL) {
         w_prev = 0xFFFFFFFFu;
         for (uint32_t i = 0; i <= (uint32_t)opt->seed_len; ++i) {
@@ -1863,7 +1882,7 @@ extern "C" int hsa_match_gap_call(const hsa_index_t *ix, const uint8_t *seq, uin
     if (n) memcpy(out, res.aln + res.aln_off[0], (size_t)n * sizeof(hsa_aln1_t));
     for (int q = 0; q < n; ++q) out[q].strand = (uint32_t)strand & 3u;       // p->strand = aux->strand, bwtgap.c:235
     hsa_result_free(&res);
-    // width_back after gap_shadow (bids beyond the device's 6-bit field were never touched by it: keep the caller's)
+    // width_back after gap_shadow (bids beyond the device's 5-bit field were never touched by it: keep the caller's)
     std::vector<u32x2> wb((size_t)len + 1);
     CU(cudaSetDevice(ix->device));
     if (cudaMemcpy(wb.data(), ws->width_out_dev, wb.size() * sizeof(u32x2), cudaMemcpyDeviceToHost) != cudaSuccess) {
@@ -1871,7 +1890,7 @@ extern "C" int hsa_match_gap_call(const hsa_index_t *ix, const uint8_t *seq, uin
     }
     for (uint32_t i = 0; i <= len; ++i) {
         width_back[i].w = wb[i].x;
-        if (wb[i].y < 63u) width_back[i].bid = (int)wb[i].y;
+        if (wb[i].y < BB_BID) width_back[i].bid = (int)wb[i].y;
     }
     *n_aln_out = n; *aln_out = out;
     return HSA_OK;
@@ -2056,6 +2075,7 @@ extern "C" int hsa_random_sector_probe_ex(int device, size_t footprint_bytes, in
 {
     if (!gbs_out || n_out < 1 || footprint_bytes < 4096 || iters < 1) return fail(HSA_E_ARG, "bad argument");
     CU(cudaSetDevice(device));
+    apply_l2_fetch_granularity();
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     uint4 *buf = nullptr; unsigned long long *sink = nullptr;

@@ -161,7 +161,7 @@ struct Coop {
         }
         me.c.m_cur = sh.max_diff - me.c.c_nd;
         if (me.c.m_cur < 0) { me.status = CH_DEAD; return; }
-        if (me.c.ci > 0 && me.c.m_cur < (int32_t)(bb(me.c.ci - 1) & 63u)) { me.status = CH_DEAD; return; }
+        if (me.c.ci > 0 && me.c.m_cur < (int32_t)(bb(me.c.ci - 1) & BB_BID)) { me.status = CH_DEAD; return; }
         if (me.c.pend) { me.status = CH_RUN; return; }
         classify(me);
     }
@@ -228,14 +228,14 @@ struct Coop {
         bool allow_diff = true, allow_M = true;
         if (i > 0) {
             const uint32_t b0 = bb(i - 1), b1 = bb(i);
-            if ((int32_t)(b0 & 63u) > m - 1) allow_diff = false;
-            else if ((int32_t)(b0 & 63u) == m - 1 && (int32_t)(b1 & 63u) == m - 1 && (b1 & 0x80u)) allow_M = false;
+            if ((int32_t)(b0 & BB_BID) > m - 1) allow_diff = false;
+            else if ((int32_t)(b0 & BB_BID) == m - 1 && (int32_t)(b1 & BB_BID) == m - 1 && (b1 & BB_EQ)) allow_M = false;
             const int32_t ii = (int32_t)i - (int32_t)sh.seed_shift;
             if (sh.seed_mode != SEED_NONE && ii > 0) {
                 const int32_t m_seed = o.max_seed_diff - c.c_nd;
                 const uint32_t s0 = bs((uint32_t)ii - 1), s1 = bs((uint32_t)ii);
-                if ((int32_t)(s0 & 63u) > m_seed - 1) allow_diff = false;
-                else if ((int32_t)(s0 & 63u) == m_seed - 1 && (int32_t)(s1 & 63u) == m_seed - 1 && (s1 & 0x80u)) allow_M = false;
+                if ((int32_t)(s0 & BB_BID) > m_seed - 1) allow_diff = false;
+                else if ((int32_t)(s0 & BB_BID) == m_seed - 1 && (int32_t)(s1 & BB_BID) == m_seed - 1 && (s1 & BB_EQ)) allow_M = false;
             }
         }
         if (allow_diff) {
@@ -277,7 +277,7 @@ struct Coop {
             c.ck = nk; c.cl = nl; c.crl = nr; c.ci = i; c.flags &= ~2u;
             c.c_meta &= ~(3u << META_STATE_SHIFT);
             if (entries_exceeded(me)) { me.status = CH_ENTRIES; return; }
-            if (c.ci > 0 && m < (int32_t)(bb(c.ci - 1) & 63u)) { me.status = CH_DEAD; return; }
+            if (c.ci > 0 && m < (int32_t)(bb(c.ci - 1) & BB_BID)) { me.status = CH_DEAD; return; }
             classify(me);
         } else me.status = CH_DEAD;
     }
@@ -644,13 +644,13 @@ HSA_HD void coop_run(const Params &P, CoopWarp &sh, uint8_t *bids, const CoopScr
                             uint32_t *w = reinterpret_cast<uint32_t *>(sh.row);
                             uint32_t jj = 0, w_prev = 0xFFFFFFFFu;
                             for (uint32_t i = 0; i < ldp; ++i) {
-                                uint32_t v = w[i], bid = bids[i] & 63u;
+                                uint32_t v = w[i], bid = bids[i] & BB_BID;
                                 if (v > x) { v -= x; w[i] = v; }
                                 else if (v == x) { bid = 1; v = P.ix.fwd.text_length - (++jj); w[i] = v; }
                                 bids[i] = bound_byte(bid, v, w_prev);
                                 w_prev = v;
                             }
-                            if (ldp > 0 && ldp <= sh.len) bids[ldp] = bound_byte(bids[ldp] & 63u, w[ldp], w_prev);
+                            if (ldp > 0 && ldp <= sh.len) bids[ldp] = bound_byte(bids[ldp] & BB_BID, w[ldp], w_prev);
                             if (sh.n_hits >= COOP_HIT_CAP) { sh.fail_code = STATUS_NEED_STRICT; sh.done = 1; }
                             else {
                                 Hit h;
@@ -715,7 +715,7 @@ HSA_HD void coop_run(const Params &P, CoopWarp &sh, uint8_t *bids, const CoopScr
                     P.n_aln[sh.out_idx] = (int32_t)n; P.aln_off[sh.out_idx] = off; P.status[sh.out_idx] = stt;
                     if (P.kind == KIND_TASKS && P.width_out) {            // per-call form: see Worker::do_end
                         const uint32_t *w = reinterpret_cast<const uint32_t *>(sh.row);
-                        for (uint32_t i = 0; i <= sh.len; ++i) { u32x2 v; v.x = w[i]; v.y = bids[i] & 63u; P.width_out[i] = v; }
+                        for (uint32_t i = 0; i <= sh.len; ++i) { u32x2 v; v.x = w[i]; v.y = bids[i] & BB_BID; P.width_out[i] = v; }
                     }
                 }
             }

@@ -440,7 +440,7 @@ struct Params {
     int32_t  vote_pop_bias;         // phase_vote(): LOOKUP runs if n_lookup + bias >= n_pop
 };
 
-enum : uint32_t { ROW_FLAG_FILTERED = 1u };
+enum : uint32_t { ROW_FLAG_FILTERED = 1u, ROW_FLAG_HAS_N = 2u /* the bound bytes' base bits do not hold every base */ };
 
 // Row / shared-memory geometry of one launch configuration (shared by the host code and the emulation).
 // seed_cap = longest width_seed in the batch + 1 (0 if none); head_bytes = 2 (fast kernel) or 4 (large capacity).
@@ -544,17 +544,25 @@ HSA_HD uint32_t occ1_dev(const DevBwt &b, uint32_t index, uint32_t c)
 
 // the bound byte of one bwt_width_t entry given the previous entry's w (0xFFFFFFFF for entry 0: never equal,
 // because w <= textLength + 1 < 2^32 - 1 for every index the uint32 SA coordinates can hold)
+// Layout: bits 0..4 = min(bid, 31) (every comparison is against m <= max_diff <= 30), bits 5..6 = the base the search
+// reads at this step (BB_BASE_SHIFT; set by the width pass for the width_back array, see base_step), bit 7 = (w[i-1] == w[i]).
+enum : uint32_t { BB_BID = 31u, BB_BASE_SHIFT = 5u, BB_BASE = 3u << 5, BB_EQ = 0x80u };
 HSA_HD uint8_t bound_byte(uint32_t bid, uint32_t w, uint32_t w_prev)
 {
-    return (uint8_t)((bid < 63u ? bid : 63u) | (w == w_prev ? 0x80u : 0u));
+    return (uint8_t)((bid < BB_BID ? bid : BB_BID) | (w == w_prev ? BB_EQ : 0u));
 }
 
 // bwt_cal_width, type 1 (bwtaln.c:73-97, 113-114): `n` bases starting at strand-resolved position `src`.
 // Writes any of: w_out (uint32 per entry), b_out (bound byte per entry), pair_out (bwt_width_t per entry), n + 1
 // entries each.  w_out / b_out are 16-byte aligned and padded to a multiple of 16 entries: they are written 16
 // bytes at a time (entries past n are zero).  Returns bid; lookups += the BWTOccValue calls the reference issues.
+// base_src != NO_BASE: byte j of b_out also carries the base at strand-resolved position base_src + j (what the search
+// reads at step j; for the splice seeds that is not the position the width is computed on), and has_n reports whether any
+// of those n bases is not A/C/G/T (such items read their bases from the codes array instead).
+enum : uint32_t { NO_BASE = 0xFFFFFFFFu };
 HSA_HD int32_t cal_width_dev(const DevIndex &ix, const TaskDesc &t, uint32_t src, uint32_t n,
-                             uint32_t *w_out, uint8_t *b_out, u32x2 *pair_out, uint32_t &lookups)
+                             uint32_t *w_out, uint8_t *b_out, u32x2 *pair_out, uint32_t &lookups,
+                             uint32_t base_src = NO_BASE, bool *has_n = nullptr)
 {
     uint32_t k = 0, l = ix.fwd.text_length, w_prev = 0xFFFFFFFFu;
     int32_t bid = 0;
@@ -583,6 +591,10 @@ HSA_HD int32_t cal_width_dev(const DevIndex &ix, const TaskDesc &t, uint32_t src
                     if (k > l || c > 3) { k = 0; l = ix.fwd.text_length; ++bid; }
                     w = l - k + 1;
                     byte = bound_byte((uint32_t)bid, w, w_prev);
+                    if (base_src != NO_BASE) {
+                        const uint32_t cb = base_src == src ? c : task_base(t, base_src + j);
+                        if (cb > 3) *has_n = true; else byte |= cb << BB_BASE_SHIFT;
+                    }
                     if (pair_out) { u32x2 v; v.x = w; v.y = (uint32_t)bid; pair_out[j] = v; }
                     w_prev = w;
                 } else if (j == n) {                        // bwtaln.c:113-114
@@ -624,14 +636,15 @@ HSA_HD void width_item(const Params &P, const DevOpt *opts, uint32_t w)
         P.n_aln[t.out_idx] = 0; P.aln_off[t.out_idx] = 0; P.status[t.out_idx] = STATUS_OK;
         return;
     }
-    cal_width_dev(P.ix, t, t.wsrc_off, t.len, reinterpret_cast<uint32_t *>(row), row + P.row_bid_off, nullptr, lk);
+    bool has_n = false;
+    cal_width_dev(P.ix, t, t.wsrc_off, t.len, reinterpret_cast<uint32_t *>(row), row + P.row_bid_off, nullptr, lk, t.sub_off, &has_n);
     if (t.seed_mode == SEED_TAIL) {
         const uint32_t sl = (uint32_t)opts[t.opt_idx].seed_len;
         cal_width_dev(P.ix, t, t.sub_off + (t.len - sl), sl, nullptr, row + P.row_seed_off, nullptr, lk);
     }
     // the row's tail carries the width pass's lookup count; the search worker adds it when the item completes,
     // so items that are re-run with the large-capacity kernel are not counted twice
-    tail[0] = lk; tail[1] = 0;
+    tail[0] = lk; tail[1] = has_n ? ROW_FLAG_HAS_N : 0u;
 }
 
 // ---- the worker -------------------------------------------------------------------------------------
@@ -688,7 +701,8 @@ struct Worker {
     uint32_t work;                  // work-queue index of the current item == its row
     const uint8_t *rd;              // the read
     uint32_t rd_len, strand, sub_off, len, seed_mode, seed_shift, opt_idx, out_idx;
-    uint32_t rd_word, rd_widx;      // the four read bytes last loaded (base_at) and their word index
+    uint32_t rd_word, rd_widx;      // the four read bytes last loaded (base_at) and their word index; rd_widx == RD_IN_BYTES: the
+                                    // item has no N and its bases ride in the bound bytes (base_step)
     uint8_t *row;                   // the item's row (global)
     // search state
     uint64_t mask0, mask1;          // non-empty buckets (mask1: large-capacity configuration only)
@@ -797,6 +811,15 @@ struct Worker {
         const uint32_t c = (rd_word >> (8u * (a & 3u))) & 0xFFu;
         return (strand && c < 4) ? 3 - c : c;
     }
+    // base the search reads at step i (== base_at(sub_off + i)): bits 5..6 of bound byte i, which the width pass filled and
+    // which the step loads anyway -- unless the item has an N somewhere (ROW_FLAG_HAS_N), then from the codes array.
+    // ncu on the 3.1 Gb genome: the 4-byte read-word loads were 15 % of the sectors the SMs asked L2 for.
+    enum : uint32_t { RD_IN_BYTES = 0xFFFFFFFEu };
+    HSA_HD uint32_t base_step(uint32_t i, uint32_t byte_i)
+    {
+        if (rd_widx == RD_IN_BYTES) return (byte_i >> BB_BASE_SHIFT) & 3u;
+        return base_at(sub_off + i);
+    }
     HSA_HD void fail(uint32_t code) { if (fail_code == STATUS_OK) fail_code = code; }
     // statistics: per-block words in shared memory on the device (they would cost nine registers per lane otherwise),
     // plain members in the host emulation
@@ -841,7 +864,7 @@ struct Worker {
                 for (uint32_t j = 0; j < ((uint32_t)o.seed_len + 4) / 4; ++j) d2[j] = s2[j];
             }
         }
-        rd_word = 0; rd_widx = 0xFFFFFFFFu;
+        rd_word = 0; rd_widx = (tail[1] & ROW_FLAG_HAS_N) ? 0xFFFFFFFFu : (uint32_t)RD_IN_BYTES;
         lookups_item = 0; steps32 = 0; pops32 = 0; fail_code = STATUS_OK;
         mask0 = mask1 = 0; n_live = 0; n_phantom = 0; top = 0; free_head = NIL;
         best_score = (o.max_diff + 1) * o.s_mm + (o.max_gapo + 1) * o.s_gapo + (o.max_gape + 1) * o.s_gape; // :128
@@ -868,7 +891,7 @@ struct Worker {
         }
         m_cur = max_diff - c_nd;                                                     // :161-164
         // (single-exit form: every early return costs a set of register moves on its way to the loop's back edge)
-        const bool drop = m_cur < 0 || (ci > 0 && m_cur < (int32_t)(bb(ci ? ci - 1 : 0) & 63u));       // :172-173
+        const bool drop = m_cur < 0 || (ci > 0 && m_cur < (int32_t)(bb(ci ? ci - 1 : 0) & BB_BID));      // :172-173
         if (drop) st = LS_POP;
         else if (pend) st = LS_LOOKUP;                     // survived pop-time pruning: materialise it first
         else classify();
@@ -987,7 +1010,8 @@ struct Worker {
         // i: index of the base the lookup extends by.  For a pending child the lookup is the PARENT's: deletion
         // children have ci == the parent's pre-decrement i, mismatch children ci == its post-decrement i.
         const uint32_t i = (pend & PEND_MM) ? ci : ci - 1;
-        const uint32_t sc_ = base_at(sub_off + i);
+        const uint32_t byte_i = bb(i);                       // bound byte of step i: lower bound, equal-width flag, base
+        const uint32_t sc_ = base_step(i, byte_i);
         uint32_t oL[4], oR[4], sk[4], sl[4], rsl[4];
         occ4_from_sector(kc, kw, pk & 63u, oL);
         occ4_from_sector(lc, lw, pl & 63u, oR);
@@ -1030,15 +1054,15 @@ struct Worker {
         const int32_t m = m_cur;
         bool allow_diff = true, allow_M = true;
         if (i > 0) {                                                                        // :252-265
-            const uint32_t b0 = bb(i - 1), b1 = bb(i);
-            if ((int32_t)(b0 & 63u) > m - 1) allow_diff = false;
-            else if ((int32_t)(b0 & 63u) == m - 1 && (int32_t)(b1 & 63u) == m - 1 && (b1 & 0x80u)) allow_M = false;
+            const uint32_t b0 = bb(i - 1), b1 = byte_i;
+            if ((int32_t)(b0 & BB_BID) > m - 1) allow_diff = false;
+            else if ((int32_t)(b0 & BB_BID) == m - 1 && (int32_t)(b1 & BB_BID) == m - 1 && (b1 & BB_EQ)) allow_M = false;
             const int32_t ii = (int32_t)i - (int32_t)seed_shift;                            // :253
             if (seed_mode != SEED_NONE && ii > 0) {
                 const int32_t m_seed = o.max_seed_diff - c_nd;                              // :167-171
                 const uint32_t s0 = bs((uint32_t)ii - 1), s1 = bs((uint32_t)ii);
-                if ((int32_t)(s0 & 63u) > m_seed - 1) allow_diff = false;
-                else if ((int32_t)(s0 & 63u) == m_seed - 1 && (int32_t)(s1 & 63u) == m_seed - 1 && (s1 & 0x80u)) allow_M = false;
+                if ((int32_t)(s0 & BB_BID) > m_seed - 1) allow_diff = false;
+                else if ((int32_t)(s0 & BB_BID) == m_seed - 1 && (int32_t)(s1 & BB_BID) == m_seed - 1 && (s1 & BB_EQ)) allow_M = false;
             }
         }
         out.allow_M = allow_M;
@@ -1119,7 +1143,7 @@ struct Worker {
         ck = in.nk; cl = in.nl; crl = in.nr; ci = in.i; c_diff = false;
         c_meta &= ~(3u << META_STATE_SHIFT);            // STATE_M
         const bool over = n_live + n_phantom + 1 > (uint32_t)o.max_entries;                           // :150-151
-        const bool pruned = ci > 0 && m_cur < (int32_t)(bb(ci ? ci - 1 : 0) & 63u);                   // :172-173
+        const bool pruned = ci > 0 && m_cur < (int32_t)(bb(ci ? ci - 1 : 0) & BB_BID);                  // :172-173
         if (!exists) st = LS_POP;
         else if (over) st = LS_END;
         else if (pruned) st = LS_POP;
@@ -1159,13 +1183,14 @@ struct Worker {
         uint32_t *w = reinterpret_cast<uint32_t *>(row);
         uint32_t jj = 0, w_prev = 0xFFFFFFFFu;
         for (uint32_t i = 0; i < ldp; ++i) {
-            uint32_t v = w[i], bid = bb(i) & 63u;
+            const uint32_t old = bb(i);
+            uint32_t v = w[i], bid = old & BB_BID;
             if (v > x) { v -= x; w[i] = v; }
             else if (v == x) { bid = 1; v = P.ix.fwd.text_length - (++jj); w[i] = v; }
-            bb_set(i, bound_byte(bid, v, w_prev));
+            bb_set(i, bound_byte(bid, v, w_prev) | (old & BB_BASE));
             w_prev = v;
         }
-        if (ldp > 0 && ldp <= len) bb_set(ldp, bound_byte(bb(ldp) & 63u, w[ldp], w_prev));
+        if (ldp > 0 && ldp <= len) { const uint32_t old = bb(ldp); bb_set(ldp, bound_byte(old & BB_BID, w[ldp], w_prev) | (old & BB_BASE)); }
         if (n_hits >= P.hit_cap) { fail(STATUS_NEED_STRICT); st = LS_END; return; }
         Hit h;
         h.k = k; h.l = l; h.rev_k = rk; h.rev_l = rl;
@@ -1241,7 +1266,7 @@ struct Worker {
             // per-call form (hsa_match_gap_call): width_back is an in/out argument of bwt_match_gap -- gap_shadow rewrites
             // it in place (bwtgap.c:94-105, :217) and the splice path reads it again afterwards (bwtgap.c:1176-1192)
             const uint32_t *w = reinterpret_cast<const uint32_t *>(row);
-            for (uint32_t i = 0; i <= len; ++i) { u32x2 v; v.x = w[i]; v.y = bb(i) & 63u; P.width_out[i] = v; }
+            for (uint32_t i = 0; i <= len; ++i) { u32x2 v; v.x = w[i]; v.y = bb(i) & BB_BID; P.width_out[i] = v; }
         }
     }
 };
