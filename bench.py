@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=12_500_000, help="reads per device batch (one hsa_whole_reads call)")
     ap.add_argument("--genome", type=int, default=3_100_000_003, help="synthetic genome length (configs[2]: 3.1 Gb)")
     ap.add_argument("--read-len", type=int, default=100)
-    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = min(steps, 5))")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0 = min(steps, 5), 10 with N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
@@ -395,8 +395,10 @@ def main():
     build.build_native()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    ctl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        ctl = dist.new_group(backend="gloo")          # host-side control plane of the result gather (no GPU kernels)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -471,8 +473,10 @@ def main():
     off_host = leg.off.cpu().pin_memory()
     len_host = leg.len.cpu().pin_memory()
     opt = leg.opt
-    e2e_steps = args.e2e_steps or min(args.steps, 5)
+    e2e_steps = args.e2e_steps or min(args.steps, 5 if world == 1 else 10)     # N = 1: a step is the whole 100 M-read set (5 s)
     gather_bytes = [0]
+    nb_max = max(bhi - blo for blo, bhi in leg.batches)
+    gatherer = shard.HostGather(nb_max, 2 * nb_max + 1024, ctl=ctl) if world > 1 else None
 
     def submit(b):
         blo, bhi = leg.batches[b]
@@ -490,9 +494,12 @@ def main():
             if b == 0:
                 last0 = (res.n_aln.copy(), int(res.occ_lookups), int(res.n_strict))
             if world > 1:
-                n_all, off_all, a_all = shard.gather_results(res.n_aln, res.aln_off, res.aln, device=dev, dst=0)
+                # results of batch b of every rank -> rank 0, input order, through host shared memory (shard.HostGather)
+                got = gatherer.gather(res.n_aln, res.aln_off, res.aln)
                 if rank == 0:
-                    gather_bytes[0] = n_all.nbytes + off_all.nbytes + a_all.nbytes
+                    gather_bytes[0] = int(gatherer.counts[:, 0].sum()) * 12 + int(gatherer.counts[:, 1].sum()) * 36
+                    assert got[0].shape[0] == int(gatherer.counts[:, 0].sum())
+                    gatherer.release()
             job = nxt
         torch.cuda.synchronize()
         return n_launch, d2h, last0
@@ -519,6 +526,8 @@ def main():
         dist.all_reduce(tot)
     aligned_all, lookups_all, heavy_all, h2d_all, d2h_all = [int(x) for x in tot.cpu().tolist()]
 
+    if gatherer is not None:
+        gatherer.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -577,7 +586,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                     "steps": e2e_steps, "gathered_to_rank0_bytes_per_batch": gather_bytes[0] if world > 1 else 0,
                     "path": "hsa_whole_reads_submit / hsa_job_wait per batch from pinned host buffers, double-buffered"
-                            + ("; every batch's results gathered to rank 0 over NCCL in input order" if world > 1 else "")},
+                            + ("; every batch's results gathered to rank 0 in input order through host shared memory "
+                               "(shard.HostGather: no GPU kernels, so nothing queues behind the persistent search kernels)" if world > 1 else "")},
             "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "parity": parity, "secondary": secondary,
             "aligned_fraction": aligned_all / args.reads_total,

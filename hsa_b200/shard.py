@@ -146,3 +146,78 @@ def gather_results(n_aln: np.ndarray, aln_off: np.ndarray, aln: np.ndarray, devi
     if dev.type == "cuda":
         torch.cuda.synchronize(dev)
     return out_n.numpy(), out_o.numpy().view(np.uint64), out_a.numpy().view(np.uint32)
+
+
+class HostGather:
+    """Ordered gather of the per-rank results on the HOST, through one POSIX shared-memory segment ("per-GPU
+    n_aln[] + packed bwt_aln1_t[] D2H, host concatenates in input order").
+
+    Why not NCCL for this: the search kernels are persistent and fill every SM, so a collective's kernels queue behind them
+    and the gather serialises with the next batch (measured at 8 GPUs: 123 M reads/s end to end against 158 M device-
+    resident).  Results are already in pinned host memory after the D2H copy of hsa_job_wait; every rank copies its three
+    arrays into its slot of the segment (ranks in parallel, no GPU involved) and rank `dst` reads the whole structure in
+    place: n_aln / aln_off of all reads in input order, aln_off pointing into one arena in which rank r's hits start at
+    r * max_hits.  `ctl` is a gloo process group (host-side barrier; an NCCL barrier would queue behind the kernels too)."""
+
+    def __init__(self, max_items: int, max_hits: int, ctl=None, dst: int = 0):
+        from multiprocessing import shared_memory
+        self.world, self.rank, self.dst, self.ctl = dist.get_world_size(), dist.get_rank(), dst, ctl
+        self.max_items, self.max_hits = int(max_items), int(max_hits)
+        per_rank = self.max_items * 12 + self.max_hits * 36
+        name = [None]
+        if self.rank == dst:
+            self.shm = shared_memory.SharedMemory(create=True, size=self.world * per_rank + 16 * self.world)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=dst, group=ctl)
+        if self.rank != dst:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            try:                                        # the segment belongs to dst: keep this process's tracker out of it
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        buf = self.shm.buf
+        W, I, H = self.world, self.max_items, self.max_hits
+        self.counts = np.ndarray((W, 2), dtype=np.int64, buffer=buf, offset=0)
+        o = 16 * W
+        self.n_aln = np.ndarray((W, I), dtype=np.int32, buffer=buf, offset=o); o += W * I * 4
+        self.aln_off = np.ndarray((W, I), dtype=np.uint64, buffer=buf, offset=o); o += W * I * 8
+        self.aln = np.ndarray((W, H, 9), dtype=np.uint32, buffer=buf, offset=o)
+
+    def gather(self, n_aln: np.ndarray, aln_off: np.ndarray, aln: np.ndarray):
+        """Every rank calls it with its batch result; on `dst` returns (n_aln, aln_off, arena) of all ranks' reads in input
+        order as views of the shared segment (valid until the next call), elsewhere None."""
+        n, h = int(n_aln.shape[0]), int(aln.shape[0])
+        if n > self.max_items or h > self.max_hits:
+            raise ValueError("result larger than the gather slot")
+        r = self.rank
+        self.n_aln[r, :n] = n_aln
+        np.add(aln_off, np.uint64(r * self.max_hits), out=self.aln_off[r, :n])
+        if h:
+            self.aln[r, :h] = aln
+        self.counts[r] = (n, h)
+        dist.barrier(group=self.ctl)
+        if r != self.dst:
+            dist.barrier(group=self.ctl)                    # dst has consumed the segment: slots may be rewritten
+            return None
+        if all(int(self.counts[q, 0]) == self.max_items for q in range(self.world)):
+            out = (self.n_aln.reshape(-1), self.aln_off.reshape(-1), self.aln.reshape(-1, 9))
+        else:
+            out = (np.concatenate([self.n_aln[q, : int(self.counts[q, 0])] for q in range(self.world)]),
+                   np.concatenate([self.aln_off[q, : int(self.counts[q, 0])] for q in range(self.world)]),
+                   self.aln.reshape(-1, 9))
+        return out
+
+    def release(self):
+        """dst calls it when it is done with the views of the last gather()."""
+        if self.rank == self.dst:
+            dist.barrier(group=self.ctl)
+
+    def close(self):
+        self.n_aln = self.aln_off = self.aln = self.counts = None
+        try:
+            self.shm.close()
+            if self.rank == self.dst:
+                self.shm.unlink()
+        except Exception:
+            pass

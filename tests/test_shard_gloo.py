@@ -77,6 +77,17 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
             o, c = int(aln_off[i]), int(cnt[i])
             arena[o:o + c] = arena[o:o + c][::-1]
         n2, off2, a2 = shard.gather_results(n_aln, aln_off, arena, dst=0)
+        # the host-side gather through shared memory (what bench.py's end-to-end leg uses)
+        hg = shard.HostGather(max_items=rs.n, max_hits=2 * rs.n + 8)
+        got = hg.gather(n_aln, aln_off, arena)
+        if rank == 0:
+            n3, off3, a3 = got
+            exp_n3, exp_rows3 = g.expected("cfg2_100bp_default", "whole")
+            assert np.array_equal(n3, exp_n3)
+            idx3 = np.concatenate([np.arange(int(o), int(o) + int(c)) for o, c in zip(off3, n3) if c])
+            assert np.array_equal(a3[idx3], exp_rows3[:, [0, 3, 4, 5, 6, 8, 9, 10, 11]])
+            hg.release()
+        hg.close()
         if rank == 0:
             exp_n, exp_rows = g.expected("cfg2_100bp_default", "whole")
             exp9 = exp_rows[:, [0, 3, 4, 5, 6, 8, 9, 10, 11]]
