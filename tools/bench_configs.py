@@ -1,7 +1,8 @@
-"""Throughput of the other BASELINE.json configs through the public API (GPU box helper; bench.py stays on
+"""Throughput of the other BASELINE.json configs through the public API (GPU box helper; bench.py measures configs[2] and
 configs[1]).  Prints one JSON line per config:
   cfg0  4.6 Mb genome, 100 k x 75 bp, max_diff 2 / max_gapo 1            (hsa_whole_reads)
-  cfg3  spliced 100 bp reads -> six 33/33/34 bp seed searches per read    (hsa_splice_seeds), on --genome
+  cfg3  spliced reads on --genome: the six seed searches per read alone    (hsa_splice_seeds), and the whole path a spliced
+        read takes -- whole-read search, then bwt_splice_match for what found nothing (hsa_whole_reads + hsa_splice_match_batch)
   cfg4  150 bp reads, 2 % substitutions, up to two indels, max_diff 5 / max_gapo 2 (hsa_whole_reads)
 """
 import argparse
@@ -55,10 +56,12 @@ def main():
     ix0.close()
 
     g = synth_torch.make_genome(a.genome, 1, dev)
-    ix = api.Index.upload(index_build.build_index(g, device=dev), 0)
-    # cfg3: spliced reads = two exons across an intron; the seed searches are what the hot path sees
+    introns = synth_torch.plant_introns(g, max(100, a.genome // 150_000), 2)      # motif-carrying introns for cfg3
+    ix = api.Index.upload(index_build.build_full_index(g, device=dev), 0)
+    # cfg3: spliced reads = two exons across an intron
     for L in (100, 75):
         spliced_seeds(a, ix, g, dev, L)
+        spliced_pipeline(a, ix, g, introns, L)
     # cfg4 stress
     n = max(a.reads // 4, 100_000)
     r = synth_torch.simulate_reads(g, n, 150, 21, sub_rate=0.02, indel_frac=0.10)
@@ -67,20 +70,42 @@ def main():
     run(f"cfg4: {a.genome} bp, {n} x 150 bp, 2% subs, 10% indel reads, n5 o2", lambda: ix.whole_reads(codes, off, lens, opt, copy=False), n, reps=2)
 
 
+def spliced_pipeline(a, ix, g, introns, L):
+    """cfg3, the whole path of an RNA-seq read: hsa_whole_reads, then hsa_splice_match_batch (bwt_splice_match: seeds,
+    correlation, motif scan, extension) for the reads that found nothing -- 3/4 junction reads over planted introns, 1/4
+    ordinary reads."""
+    n = a.reads
+    nj = 3 * n // 4
+    reads = torch.cat([synth_torch.simulate_junction_reads(g, introns, nj, L, 31 + L), synth_torch.simulate_reads(g, n - nj, L, 32 + L)])
+    reads = reads[torch.randperm(n, device=reads.device, generator=torch.Generator(device=reads.device).manual_seed(3))]
+    codes, off, lens = pinned(reads.reshape(-1)), pinned(torch.arange(n, dtype=torch.int64) * L), pinned(torch.full((n,), L, dtype=torch.int32))
+    opt = api.gap_init_opt()
+    sopt = api.gap_init_opt(mode=2, max_diff=api.bwa_cal_maxdiff(L))          # local_opt as the driver holds it from batch 2 on
+    rd = codes.numpy().reshape(n, L)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        res = ix.whole_reads(codes, off, lens, opt, copy=False)
+        t1 = time.perf_counter()
+        un = np.nonzero(res.n_aln == 0)[0]
+        sub = np.ascontiguousarray(rd[un]).reshape(-1)
+        n_aln, _ = ix.splice_match(sub, (np.arange(un.shape[0], dtype=np.uint64) * L), np.full(un.shape[0], L, dtype=np.uint32), sopt)
+        t2 = time.perf_counter()
+        if best is None or t2 - t0 < best[0]:
+            best = (t2 - t0, t1 - t0, t2 - t1, int(un.shape[0]), int((n_aln == 2).sum()), int((n_aln > 0).sum()), ix.last_splice_lookups)
+    dt, t_whole, t_splice, n_un, two, any_, lk = best
+    print(json.dumps({"config": f"cfg3 whole path: {a.genome} bp, {n} x {L} bp reads (75 % across planted introns) -> hsa_whole_reads, then "
+                                f"hsa_splice_match_batch for the {n_un} reads that found nothing", "reads": n, "wall_ms": dt * 1e3,
+                      "reads_per_s_e2e": n / dt, "whole_reads_ms": t_whole * 1e3, "splice_ms": t_splice * 1e3,
+                      "splice_reads_per_s": n_un / t_splice, "spliced_two_part": two, "spliced_any": any_,
+                      "splice_occ_lookups_per_read": lk / max(n_un, 1)}), flush=True)
+
+
 def spliced_seeds(a, ix, g, dev, L):
     """cfg3: spliced reads = two exons across an intron; the six seed searches per read (len/3 bp each: 33/33/34 for
     100 bp reads, 25/25/25 for 75 bp reads -- the 25 bp figure of BASELINE.json's config) are what the hot path sees."""
     n = a.reads
-    gen = torch.Generator(device=dev); gen.manual_seed(5)
-    start = torch.randint(0, a.genome - 60_000, (n, 1), device=dev, generator=gen)
-    split = torch.randint(L // 3, L - L // 3, (n, 1), device=dev, generator=gen)
-    intron = torch.randint(50, 50_000, (n, 1), device=dev, generator=gen)
-    j = torch.arange(L, device=dev)[None, :]
-    reads = g[start + j + torch.where(j >= split, intron, torch.zeros_like(intron))]
-    sub = torch.rand((n, L), device=dev, generator=gen) < 0.01
-    reads = torch.where(sub, (reads + torch.randint(1, 4, (n, L), dtype=torch.uint8, device=dev, generator=gen)) & 3, reads)
-    rc = torch.rand((n, 1), device=dev, generator=gen) < 0.5
-    reads = torch.where(rc, 3 - torch.flip(reads, dims=[1]), reads)
+    reads = synth_torch.simulate_spliced_reads(g, n, L, 5)
     codes, off, lens = pinned(reads.reshape(-1)), pinned(torch.arange(n, dtype=torch.int64) * L), pinned(torch.full((n,), L, dtype=torch.int32))
     opt = api.gap_init_opt()
     run(f"cfg3: {a.genome} bp, {n} spliced {L} bp reads -> 6 seed searches each ({L // 3} bp segments)",
