@@ -438,6 +438,7 @@ struct hsa_index {
     uint32_t *blocks4 = nullptr; uint32_t n_blocks = 0;                               // HSP::blockList rows (optional)
     uint32_t *packed_dna = nullptr; uint32_t dna_length = 0;                          // HSP::packedDNA (optional; splice path)
     struct SpliceCache *splice_cache = nullptr;                                       // per-worker scratch of the splice path, kept between calls
+    bool splice_stack_set = false;                                                    // device stack limit raised for splice_kernel
 };
 
 struct Scratch {                             // worker-private device memory for one launch configuration
@@ -999,8 +1000,7 @@ extern "C" int hsa_splice_match_batch(const hsa_index_t *ix, const uint8_t *code
     CU(cudaMemcpyAsync(d_opts.p, dopts.data(), n_opts * sizeof(DevOpt), cudaMemcpyHostToDevice, s));
     if (opt_idx) CU(cudaMemcpyAsync(d_oi.p, opt_idx, n_reads * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(d_cnt.p, 0, 4 * sizeof(unsigned long long), s));
-    static bool stack_set = false;
-    if (!stack_set) { CU(cudaDeviceSetLimit(cudaLimitStackSize, 8192)); stack_set = true; }
+    if (!mix->splice_stack_set) { CU(cudaDeviceSetLimit(cudaLimitStackSize, 8192)); mix->splice_stack_set = true; }   // real calls in splice_kernel
     SpliceParams P;
     memset(&P, 0, sizeof(P));
     P.env.ix = ix->ix; P.env.sa_value = ix->sa_value; P.env.sa_interval = ix->sa_interval;
