@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256, 5) width_kernel(const __grid_constant__ P
     for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
         reinterpret_cast<int *>(sopt)[i] = reinterpret_cast<const int *>(P.opts)[i];
     __syncthreads();
-    const uint32_t n = P.n_work_dev ? min(*P.n_work_dev, P.n_work) : P.n_work;     // n_work caps a device-side count
+    const uint32_t n = work_count(P);                                              // n_work caps a device-side count
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x)
         width_item(P, sopt, w);
 }
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) search_kernel(const __grid_consta
 
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_work = P.n_work_dev ? min(*P.n_work_dev, P.n_work) : P.n_work;
+    const uint32_t n_work = work_count(P);
     Worker<LinkT, BIDS_SMEM> w(P, slot, threadIdx.x);
     unsigned long long warp_iters = 0;
     uint32_t pop_trips = 0;
@@ -285,8 +285,7 @@ __global__ void __launch_bounds__(BLOCK) coop_kernel(const __grid_constant__ Par
     g.out_payload = P.coop_out_payload + wg * 32 * COOP_OUT_CAP;
     g.out_info = P.coop_out_info + wg * 32 * COOP_OUT_CAP;
     g.hits = P.coop_hits + wg * COOP_HIT_CAP;
-    const uint32_t n_dev = P.n_work_dev ? *P.n_work_dev : P.n_work;
-    const uint32_t n_work = n_dev < P.n_work ? n_dev : P.n_work;
+    const uint32_t n_work = work_count(P);
     CoopLane me;
     coop_run(P, sh, bids, g, P.coop_cap_chunks, n_work, me);
     if (lane == 0) {
@@ -1240,6 +1239,7 @@ struct StageIO {
     uint32_t work_base = 0;
     uint32_t n_work = 0;                      // work items, or the cap of a device-side count
     const uint32_t *n_work_dev = nullptr;     // device-side count (low word of a counter)
+    uint32_t n_work_skip = 0;                 // ... of which the first n_work_skip belong to earlier rounds
     uint32_t *flag_list = nullptr;            // items handed on to the next stage ...
     unsigned long long *flag_count = nullptr; // ... and their count
 };
@@ -1307,6 +1307,7 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     P.strict_list = io.flag_list; P.strict_count = io.flag_count;
     if (v > V_FAST_ROWS) { P.step_budget = 0; P.drain_budget = 0; }
     P.pass = 1; P.work_list = io.work_list; P.work_base = io.work_base; P.n_work = n_work; P.n_work_dev = io.n_work_dev;
+    P.n_work_skip = io.n_work_skip;
     P.next_list = pipe.next_list; P.next_count = reinterpret_cast<uint32_t *>(slots + 2);
     P.cursor = slots;
     const uint32_t wgrid = std::max<uint32_t>(1, std::min<uint32_t>((n_work + 255) / 256, (uint32_t)ix->sm_count * 8));
@@ -1324,7 +1325,7 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     CU(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream));
     ++ws->last_launches; trace_mark(ws, nm1, stream);
     if (b.kind == KIND_WHOLE) {
-        P.pass = 2; P.work_list = pipe.next_list; P.work_base = 0; P.n_work_dev = P.next_count;
+        P.pass = 2; P.work_list = pipe.next_list; P.work_base = 0; P.n_work_dev = P.next_count; P.n_work_skip = 0;
         P.next_list = nullptr; P.next_count = nullptr; P.cursor = slots + 1;
         width_kernel<<<wgrid, 256, P.smem_opts_bytes, stream>>>(P);
         CU(cudaGetLastError());
@@ -1445,15 +1446,22 @@ static int batch_enqueue(hsa_workspace *ws, const Batch &b, cudaStream_t stream,
     // warp-cooperative kernel right behind it: its work count is read from device memory, nothing is synchronised
     ws->heavy_enqueued = false;
     if (b.kind != KIND_WIDTH && coop_usable(ws, b)) {
-        ws->heavy_cap = (uint32_t)std::min<uint64_t>(n_work_total, std::max<uint64_t>(65536, n_work_total / 4));
+        // in rounds of at most n / 4 searches (the stage's rows and record chunks are sized for one round); as many rounds
+        // are queued as it takes to cover the whole batch, so that nothing is left over whatever share of it is heavy --
+        // a round that finds its part of the list empty costs four empty launches
+        const uint32_t round_cap = (uint32_t)std::min<uint64_t>(n_work_total, std::max<uint64_t>(65536, n_work_total / 4));
+        const uint32_t rounds = (uint32_t)((n_work_total + round_cap - 1) / round_cap);
+        ws->heavy_cap = (uint32_t)std::min<uint64_t>(n_work_total, (uint64_t)round_cap * rounds);
         if ((rc = ensure(ws->strict2_list, ws->strict2_list_cap, (size_t)n_work_total + 1))) return rc;
         Params S = P;
         coop_layout(S, b, seed_cap);
-        StageIO io;
-        io.work_list = ws->strict_list; io.n_work = ws->heavy_cap;
-        io.n_work_dev = reinterpret_cast<const uint32_t *>(ws->counters + CNT_STRICT);
-        io.flag_list = ws->strict2_list; io.flag_count = ws->counters + CNT_STRICT2;
-        if ((rc = issue_chunk(ws, b, S, ws->heavy, MAX_PIPES, V_COOP, io, stream))) return rc;
+        for (uint32_t r = 0; r < rounds; ++r) {
+            StageIO io;
+            io.work_list = ws->strict_list + (size_t)r * round_cap; io.n_work = round_cap; io.n_work_skip = r * round_cap;
+            io.n_work_dev = reinterpret_cast<const uint32_t *>(ws->counters + CNT_STRICT);
+            io.flag_list = ws->strict2_list; io.flag_count = ws->counters + CNT_STRICT2;
+            if ((rc = issue_chunk(ws, b, S, ws->heavy, MAX_PIPES, V_COOP, io, stream))) return rc;
+        }
         ws->heavy_enqueued = true;
     }
     CU(cudaEventRecord(ws->ev1, stream));

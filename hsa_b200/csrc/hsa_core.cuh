@@ -389,7 +389,8 @@ struct Params {
     uint32_t kind;
     uint32_t pass;                  // KIND_WHOLE: 1 = reverse-complement strand pass, 2 = forward strand pass
     uint32_t n_work;                // work items of this launch ...
-    const uint32_t *n_work_dev;     // ... or, if set, read from device memory (pass 2)
+    const uint32_t *n_work_dev;     // ... or, if set, read from device memory (pass 2): items [n_work_skip, *n_work_dev) capped at n_work
+    uint32_t n_work_skip;
     const uint32_t *work_list;      // optional: work index -> item id (pass-2 list, large-capacity re-runs)
     uint32_t work_base;             // item id of work index 0 when there is no list
     const Task *tasks;              // KIND_TASKS
@@ -475,6 +476,14 @@ HSA_HD uint32_t task_base(const TaskDesc &t, uint32_t p)
 {
     if (t.strand) { uint32_t c = ld_ro_u8(t.rd + (t.rd_len - 1 - p)); return c < 4 ? 3 - c : c; }
     return ld_ro_u8(t.rd + p);
+}
+
+// work items of a launch: P.n_work, or -- with a device-side count -- what is left of it beyond n_work_skip, capped at P.n_work
+HSA_HD uint32_t work_count(const Params &P)
+{
+    if (!P.n_work_dev) return P.n_work;
+    const uint32_t n = *P.n_work_dev, left = n > P.n_work_skip ? n - P.n_work_skip : 0u;
+    return left < P.n_work ? left : P.n_work;
 }
 
 // Item ids:  KIND_TASKS: task index;  KIND_WHOLE: read index (the strand comes from P.pass: pass 1 = reverse

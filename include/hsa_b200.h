@@ -195,7 +195,8 @@ void hsa_result_free(hsa_result_t *res);
  * Results stay on the device: n_aln_dev[n_reads], aln_off_dev[n_reads], aln_dev[aln_capacity] and an
  * 8 x uint64 stats block {-, hits, lookups, heavy, bad, pops, steps, unprocessed}.  Nothing is synchronised:
  * the fast kernel and, behind it, the warp-cooperative kernel for the `heavy` searches it handed on are
- * queued on `stream`.  Completion is verified with hsa_workspace_check(): it waits for the call's stream and
+ * queued on `stream` (in as many rounds as it takes to cover the batch, whatever share of it is heavy).  Completion is
+ * verified with hsa_workspace_check(): it waits for the call's stream and
  * returns HSA_E_CAPACITY unless every read was searched to the end and every hit fits aln_capacity (searches
  * even the cooperative kernel could not hold leave n_aln = 0 behind; such batches go through hsa_whole_reads,
  * which finishes them with the large-capacity kernel).  One workspace serves one stream at a time. */

@@ -173,6 +173,22 @@ def test_device_resident_keep_gape_46mb_vs_reference_binary(g46):
         run.ws.close()
 
 
+def test_device_resident_entry_point_when_most_searches_are_heavy(g46, monkeypatch):
+    """A 24-record stack arena sends most searches to the cooperative stage, far more than one round of it holds (a quarter
+    of the batch): the queued rounds must cover them all, with results unchanged."""
+    monkeypatch.setenv("HSA_B200_ARENA_CAP", "24")
+    reads_t = synth_torch.simulate_reads(g46.genome, 200_000, 100, 77)
+    rs, path = g46.reads_file("cfg2heavy", reads_t)
+    exp_n, exp_rows, exp_lk = g46.reference("whole", path, [])
+    run = _DeviceRun(g46.ix, reads_t, api.gap_init_opt())
+    try:
+        n_aln, rows, stats = run.run()
+        assert stats[3] > 200_000 // 4 and stats[7] == 0          # heavy searches beyond one round, none left over
+        assert np.array_equal(n_aln, exp_n) and np.array_equal(rows, exp_rows) and stats[2] == exp_lk
+    finally:
+        run.ws.close()
+
+
 def test_device_entry_point_reports_unprocessed_searches(g46, monkeypatch):
     """Without the cooperative stage and with a tiny stack arena the fast kernel hands searches on that nothing finishes:
     hsa_workspace_check must fail loudly instead of leaving n_aln = 0 behind."""
