@@ -340,6 +340,47 @@ def secondary_configs1(local_rank: int, dev, peaks: dict, args):
     return out
 
 
+def dropin_block(dev, args):
+    """The drop-in as HSA would use it (N = 1): the reference's own batch loop (bwtaln.c:477, 506; 100 000-read batches)
+    with bwa_cal_sa_reg_gap replaced by shim/hsa_gpu_shim.c's bwa_cal_sa_reg_gap_gpu -- whole-read searches and the
+    spliced-read fallback on the GPU -- next to the stock driver on the host cores.  oracle/_ref/hsa_ref_gpu is the
+    unmodified reference linked with the shim; the index files are written by the product (index_io.save_index)."""
+    import numpy as np
+    import torch
+    from hsa_b200 import index_build, index_io, synth, synth_torch
+    ref, ref_gpu = os.path.join(ROOT, "oracle", "_ref", "hsa_ref"), os.path.join(ROOT, "oracle", "_ref", "hsa_ref_gpu")
+    if not (os.path.exists(ref) and os.path.exists(ref_gpu)):
+        return {"unavailable": "oracle/_ref/hsa_ref[_gpu] not built"}
+    G, n, L = 46_000_003, 1_000_000, args.read_len
+    procs = os.cpu_count() or 1
+    genome = synth_torch.make_genome(G, GENOME_SEED, dev)
+    introns = synth_torch.plant_introns(genome, 300, 7)
+    n_j = n // 100
+    reads = torch.cat([synth_torch.simulate_reads(genome, n - n_j, L, 41), synth_torch.simulate_junction_reads(genome, introns, n_j, L, 42)])
+    reads = reads[torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(5))].cpu().numpy()
+    with tempfile.TemporaryDirectory() as td:
+        index_io.save_index(index_build.build_full_index(genome, device=dev), os.path.join(td, "g"))
+        del genome
+        torch.cuda.empty_cache()
+        rs = synth.ReadSet(np.full(n, L, dtype=np.uint32), np.ascontiguousarray(reads).reshape(-1))
+        synth.write_reads_bin(os.path.join(td, "r.reads"), rs)
+        n1 = 50_000
+        synth.write_reads_bin(os.path.join(td, "r1.reads"), rs.subset(0, n1))
+
+        def run(cmd):
+            out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
+            return json.loads(out.strip().splitlines()[-1])
+        j1 = run([ref, "driver", os.path.join(td, "g"), os.path.join(td, "r1.reads"), "x", "nout=1", "procs=1"])
+        jp = run([ref, "driver", os.path.join(td, "g"), os.path.join(td, "r.reads"), "x", "nout=1", f"procs={procs}"])
+        jg = run([ref_gpu, "gpudriver", os.path.join(td, "g"), os.path.join(td, "r.reads"), "x", "nout=1"])
+    return {"workload": f"{G} bp genome with planted introns, {n} x {L} bp reads, 1 % of them across introns (splice fallback), default "
+                        f"options, the reference's 100 000-read batches; index files written by the product, loaded by the reference",
+            "value": n / jg["secs"], "unit": UNIT, "aligned_any": jg["aligned_any"],
+            "path": "oracle/_ref/hsa_ref_gpu gpudriver: the unmodified reference program with bwa_cal_sa_reg_gap_gpu (shim/hsa_gpu_shim.c)",
+            "stock_driver_all_cores": {"value": n / jp["secs"], "cores": procs, "aligned_any": jp["aligned_any"]},
+            "stock_driver_single_thread": {"value": n1 / j1["secs"], "sample": f"{n1} reads (the reference as it ships)"}}
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse_args()
@@ -575,13 +616,16 @@ def main():
             print(json.dumps({"error": "GPU results differ from the reference", "parity": parity}), file=sys.stderr)
             raise RuntimeError("parity failure against oracle/_ref/hsa_ref")
 
-    secondary = None
+    secondary, dropin = None, None
     if world == 1 and not args.no_secondary and args.genome != 46_000_003:
         leg.ws.close()
         del leg, reads, codes_host
         index.close()
         torch.cuda.empty_cache()
         secondary = secondary_configs1(local_rank, dev, peaks, args)
+        if not args.no_cpu_baseline:
+            torch.cuda.empty_cache()
+            dropin = dropin_block(dev, args)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
@@ -592,7 +636,7 @@ def main():
                             + ("; every batch's results gathered to rank 0 in input order through host shared memory "
                                "(shard.HostGather: no GPU kernels, so nothing queues behind the persistent search kernels)" if world > 1 else "")},
             "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity": parity, "secondary": secondary,
+            "cpu_baseline": cpu_baseline, "parity": parity, "secondary": secondary, "dropin": dropin,
             "aligned_fraction": aligned_all / args.reads_total,
             "heavy_searches_handed_to_cooperative_kernel": heavy_all,
             "index_build_secs": index_build_secs, "index_broadcast": bcast}
