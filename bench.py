@@ -351,7 +351,7 @@ def dropin_block(dev, args):
     ref, ref_gpu = os.path.join(ROOT, "oracle", "_ref", "hsa_ref"), os.path.join(ROOT, "oracle", "_ref", "hsa_ref_gpu")
     if not (os.path.exists(ref) and os.path.exists(ref_gpu)):
         return {"unavailable": "oracle/_ref/hsa_ref[_gpu] not built"}
-    G, n, L = 46_000_003, 1_000_000, args.read_len
+    G, n, L = 46_000_003, 3_000_000, args.read_len         # 30 driver batches: the first one's allocations are amortised
     procs = os.cpu_count() or 1
     genome = synth_torch.make_genome(G, GENOME_SEED, dev)
     introns = synth_torch.plant_introns(genome, 300, 7)
@@ -449,6 +449,12 @@ def main():
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # ---- the drop-in inside the reference program (N = 1), before this process fills the GPU and pins host memory ----
+    dropin = None
+    if world == 1 and not args.no_secondary and not args.no_cpu_baseline:
+        dropin = dropin_block(dev, args)
+        torch.cuda.empty_cache()
 
     # ---- index: built once on rank 0 (torch ops on the GPU), broadcast as device blocks over NCCL ----
     t_idx = time.time()
@@ -616,16 +622,13 @@ def main():
             print(json.dumps({"error": "GPU results differ from the reference", "parity": parity}), file=sys.stderr)
             raise RuntimeError("parity failure against oracle/_ref/hsa_ref")
 
-    secondary, dropin = None, None
+    secondary = None
     if world == 1 and not args.no_secondary and args.genome != 46_000_003:
         leg.ws.close()
         del leg, reads, codes_host
         index.close()
         torch.cuda.empty_cache()
         secondary = secondary_configs1(local_rank, dev, peaks, args)
-        if not args.no_cpu_baseline:
-            torch.cuda.empty_cache()
-            dropin = dropin_block(dev, args)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
