@@ -66,6 +66,16 @@ class _Result(C.Structure):
 ALN_WORDS = 9
 
 
+class _SamResult(C.Structure):        # == hsa_sam_result_t
+    _fields_ = [("n_reads", C.c_size_t), ("rec", C.c_void_p), ("multi", C.c_void_p), ("n_multi", C.c_size_t),
+                ("cigar", C.c_void_p), ("n_cigar", C.c_size_t), ("md", C.c_void_p), ("md_bytes", C.c_size_t),
+                ("n_refined", C.c_uint64), ("kernel_ms", C.c_float),
+                ("cap_rec", C.c_size_t), ("cap_multi", C.c_size_t), ("cap_cigar", C.c_size_t), ("cap_md", C.c_size_t)]
+
+
+SAM_REC_WORDS, SAM_MULTI_WORDS = 22, 12      # hsa_sam1_t / hsa_multi1_t in 32-bit words
+
+
 def aln_fields(aln9: np.ndarray) -> dict:
     """Unpack hsa_aln1_t words into named uint32/int32 columns."""
     return dict(n_mm=aln9[:, 0] & 0xFFFF, n_gapo=(aln9[:, 0] >> 16) & 0xFF, n_gape=(aln9[:, 0] >> 24) & 0xFF,
@@ -134,6 +144,11 @@ def lib():
     L.hsa_index_attach_packed_dna.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.hsa_splice_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.hsa_sam_se_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(GapOpt), C.c_int, C.POINTER(C.c_uint64), C.POINTER(_SamResult)]
+    L.hsa_sam_result_free.argtypes = [C.POINTER(_SamResult)]
+    L.hsa_sam_format.argtypes = [C.POINTER(_SamResult), C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.POINTER(C.c_char_p), C.c_size_t, C.POINTER(GapOpt), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.hsa_match_gap_call.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(GapOpt),
                                      C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
     _lib = L
@@ -322,6 +337,23 @@ class Index:
         self.last_splice_lookups = int(lk.value)
         return n_aln, aln
 
+    def sam_se(self, codes, off, lens, n_aln, aln_off, aln9, opt: GapOpt, n_occ: int = 3, rng48_state: int = 0) -> "SamResult":
+        """What generate_sam_se_core (bwtse.c:884) computes for a batch before printing: hit selection (host, the reference's
+        drand48 stream from `rng48_state`), then on the GPU positions, pairing of spliced parts, banded DP -> CIGAR, MD / NM.
+        n_aln / aln_off / aln9 = the reads' hits as hsa_whole_reads (+ hsa_splice_match_batch) leave them."""
+        cp, op, lp, n = _ptr(codes, np.uint8), _ptr(off, np.uint64), _ptr(lens, np.uint32), _len(lens)
+        na = np.ascontiguousarray(n_aln, dtype=np.int32)
+        ao = np.ascontiguousarray(aln_off, dtype=np.uint64)
+        a9 = np.ascontiguousarray(aln9, dtype=np.uint32)
+        res = _SamResult()
+        st = C.c_uint64(rng48_state)
+        rc = lib().hsa_sam_se_batch(self._h, cp[0], op[0], lp[0], n, na.ctypes.data, ao.ctypes.data, a9.ctypes.data, C.byref(opt),
+                                    n_occ, C.byref(st), C.byref(res))
+        if rc:
+            lib().hsa_sam_result_free(C.byref(res))
+            _check(rc)
+        return SamResult(res, st.value, (cp[1], op[1], lp[1]), opt)
+
     def sa_values_device(self, idx_ptr: int, n: int, out_ptr: int, steps_ptr: int = 0, stream_ptr: int = 0) -> None:
         _check(lib().hsa_sa_values_device(self._h, idx_ptr, n, out_ptr, steps_ptr, stream_ptr))
 
@@ -404,6 +436,54 @@ class Job:
         _check(lib().hsa_job_wait(h, C.byref(self._res)))
         self._keep = None
         return BatchResult(self._res, copy=copy)
+
+
+def _libc_free(p) -> None:
+    f = C.CDLL(None).free
+    f.argtypes, f.restype = [C.c_void_p], None
+    f(p)
+
+
+class SamResult:
+    """hsa_sam_result_t: rec[n, 22] (hsa_sam1_t words), multi[m, 12], cigar[...] (bwa_cigar_t), md bytes; format() = the SAM
+    text of bwa_print_sam1 for the batch."""
+
+    def __init__(self, r: _SamResult, rng48_state: int, reads, opt: GapOpt):
+        self._r, self.rng48_state, self._reads, self._opt = r, rng48_state, reads, opt
+        n = r.n_reads
+        self.rec = np.ctypeslib.as_array(C.cast(r.rec, C.POINTER(C.c_uint32)), shape=(n, SAM_REC_WORDS)).copy() if n else np.zeros((0, SAM_REC_WORDS), np.uint32)
+        self.multi = (np.ctypeslib.as_array(C.cast(r.multi, C.POINTER(C.c_uint32)), shape=(r.n_multi, SAM_MULTI_WORDS)).copy()
+                      if r.n_multi else np.zeros((0, SAM_MULTI_WORDS), np.uint32))
+        self.cigar = np.ctypeslib.as_array(C.cast(r.cigar, C.POINTER(C.c_uint32)), shape=(r.n_cigar,)).copy() if r.n_cigar else np.zeros(0, np.uint32)
+        self.md = C.string_at(r.md, r.md_bytes) if r.md_bytes else b""
+        self.n_refined, self.kernel_ms = int(r.n_refined), float(r.kernel_ms)
+
+    def format(self, chr_names, first: int = 0, count: int | None = None, names=None) -> bytes:
+        codes, off, lens = self._reads
+        n = self._r.n_reads
+        count = n - first if count is None else count
+        ca = (C.c_char_p * len(chr_names))(*[c.encode() if isinstance(c, str) else c for c in chr_names])
+        na = None
+        if names is not None:
+            na = (C.c_char_p * n)(*[x.encode() if isinstance(x, str) else x for x in names])
+        text, nb = C.c_void_p(), C.c_size_t()
+        cp, op, lp = _ptr(codes, np.uint8), _ptr(off, np.uint64), _ptr(lens, np.uint32)
+        _check(lib().hsa_sam_format(C.byref(self._r), first, count, cp[0], op[0], lp[0], C.cast(na, C.c_void_p) if na is not None else None,
+                                    ca, len(chr_names), C.byref(self._opt), C.byref(text), C.byref(nb)))
+        out = C.string_at(text, nb.value) if nb.value else b""
+        _libc_free(text)
+        return out
+
+    def close(self):
+        if self._r is not None:
+            lib().hsa_sam_result_free(C.byref(self._r))
+            self._r = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _ptr(x, dtype):

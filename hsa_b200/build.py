@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "hsa_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "hsa_core.cuh"), os.path.join(HERE, "csrc", "hsa_coop.cuh"), os.path.join(os.path.dirname(HERE), "include", "hsa_b200.h")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))] + [os.path.join(os.path.dirname(HERE), "include", "hsa_b200.h")]
 OUT = os.path.join(HERE, "libhsa_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

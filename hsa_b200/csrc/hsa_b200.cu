@@ -20,6 +20,7 @@
 #include "hsa_core.cuh"
 #include "hsa_coop.cuh"
 #include "hsa_splice.cuh"
+#include "hsa_sam.cuh"
 #include "../../include/hsa_b200.h"
 
 using namespace hsa;
@@ -437,6 +438,7 @@ struct hsa_index {
     uint32_t *blocks4 = nullptr; uint32_t n_blocks = 0;                               // HSP::blockList rows (optional)
     uint32_t *packed_dna = nullptr; uint32_t dna_length = 0;                          // HSP::packedDNA (optional; splice path)
     struct SpliceCache *splice_cache = nullptr;                                       // per-worker scratch of the splice path, kept between calls
+    struct SamCache *sam_cache = nullptr;                                             // device buffers of the SAM-field stage, kept between calls
     bool splice_stack_set = false;                                                    // device stack limit raised for splice_kernel
 };
 
@@ -737,6 +739,7 @@ extern "C" int hsa_index_from_blocks(int device, const uint32_t meta_fwd[7], con
 
 extern "C" void hsa_workspace_free(hsa_workspace_t *ws);
 static void splice_cache_free(struct SpliceCache *c);
+static void sam_cache_free(struct SamCache *c);
 
 extern "C" void hsa_index_free(hsa_index_t *ix)
 {
@@ -749,6 +752,7 @@ extern "C" void hsa_index_free(hsa_index_t *ix)
     if (ix->own_blocks) for (int d = 0; d < 2; ++d) cudaFree(ix->blocks[d]);
     cudaFree(ix->sa_value); cudaFree(ix->sa_counters); cudaFree(ix->blocks4); cudaFree(ix->packed_dna);
     splice_cache_free(ix->splice_cache);
+    sam_cache_free(ix->sam_cache);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -1279,6 +1283,10 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
                              : (size_t)P.smem_stats_off + 5 * sizeof(unsigned long long);
     const void *fn = search_fn(v, (int)block, ws->minb);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // experiment knob: shared-memory carve-out in percent of the SM's unified L1/shared array (-1 = driver default)
+        static const long carve = env_long("HSA_B200_CARVEOUT", -1);
+        if (carve >= 0 && v <= V_FAST_ROWS) CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)carve));
+    }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)block, smem));
     if (occ < 1) return fail(HSA_E_CUDA, "search kernel does not fit on an SM");
@@ -1366,7 +1374,7 @@ static int batch_params(hsa_workspace *ws, const Batch &b, Params &P, Variant &v
     P.vote_slow_min = ws->vote_slow_min; P.vote_pop_bias = ws->vote_pop_bias;
     P.step_budget = ws->step_budget; P.drain_budget = ws->drain_budget;
     // fast configuration: bound bytes in shared memory if a block's share leaves room for >= 4 blocks per SM
-    const uint32_t nb_fast = std::min<uint32_t>(b.n_buckets, 64);   // scores >= 64 send the item to the large-capacity kernel
+    const uint32_t nb_fast = std::min<uint32_t>(b.n_buckets, (uint32_t)std::min<long>(64, std::max<long>(8, env_long("HSA_B200_NB_FAST", 64))));   // scores >= 64 send the item to the large-capacity kernel
     set_layout(P, b.max_len, seed_cap, nb_fast, b.n_opts, 2, true);
     v = V_FAST;
     if ((size_t)P.smem_opts_bytes + (size_t)ws->block * P.smem_lane_stride > 56 * 1024 || env_long("HSA_B200_FORCE_ROWS", 0)) {
@@ -2133,3 +2141,5 @@ extern "C" int hsa_random_sector_probe(int device, size_t footprint_bytes, int i
     *gbs_out = *std::max_element(v, v + PROBE_VARIANTS);
     return HSA_OK;
 }
+
+#include "hsa_sam_api.inl"

@@ -1,0 +1,230 @@
+// hsa_sam_api.inl -- kernels and C ABI of the SAM-field stage (hsa_sam.cuh); included at the end of hsa_b200.cu.
+
+namespace hsa {
+
+// every read: positions, mapQ, pairing of spliced parts, MD where nothing has to be refined (hsa_sam.cuh: sam_pos_item)
+__global__ void __launch_bounds__(256) sam_pos_kernel(const __grid_constant__ SamParams P)
+{
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += (size_t)gridDim.x * blockDim.x)
+        sam_pos_item(P, (uint32_t)r);
+}
+
+// the listed reads: banded global alignment(s), CIGAR, MD.  Persistent threads, each with its interleaved scratch slice.
+__global__ void __launch_bounds__(128) sam_dp_kernel(const __grid_constant__ SamParams P, uint32_t n_work)
+{
+    const uint32_t worker = blockIdx.x * blockDim.x + threadIdx.x;
+    if (worker >= P.dp_workers) return;
+    for (;;) {
+        const unsigned long long w = atomicAdd(P.cursor, 1ull);
+        if (w >= n_work) break;
+        sam_dp_item(P, P.dp_list[w], worker);
+    }
+}
+
+}   // namespace hsa
+
+struct SamCache { DevBuf codes, off, len, n_aln, aln_off, aln, rec, multi, cigar, md, list, cnt, maxdiff, dp_bytes, dp_rows; };
+static void sam_cache_free(SamCache *c) { delete c; }
+
+template <typename T> static int host_grow(T *&p, size_t &cap, size_t need)
+{
+    if (need <= cap && p) return 0;
+    T *q = (T *)realloc(p, std::max<size_t>(need, 1) * sizeof(T));
+    if (!q) return -1;
+    p = q; cap = std::max<size_t>(need, 1);
+    return 0;
+}
+
+extern "C" void hsa_sam_result_free(hsa_sam_result_t *res)
+{
+    if (!res) return;
+    free(res->rec); free(res->multi); free(res->cigar); free(res->md);
+    memset(res, 0, sizeof(*res));
+}
+
+extern "C" int hsa_sam_se_batch(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len, size_t n_reads,
+                                const int32_t *n_aln, const uint64_t *aln_off, const hsa_aln1_t *aln, const hsa_gap_opt_t *opt,
+                                int n_occ, uint64_t *rng48_state, hsa_sam_result_t *res)
+{
+    static_assert(sizeof(SamRec) == sizeof(hsa_sam1_t) && sizeof(SamMulti) == sizeof(hsa_multi1_t), "record mirrors");
+    if (!ix || !opt || !rng48_state || !res) return fail(HSA_E_ARG, "null argument");
+    res->n_reads = n_reads; res->n_multi = res->n_cigar = res->md_bytes = 0; res->n_refined = 0; res->kernel_ms = 0;
+    if (n_reads == 0) return HSA_OK;
+    if (!codes || !off || !len || !n_aln || !aln_off) return fail(HSA_E_ARG, "null argument");
+    if (!ix->sa_value || !ix->blocks4 || !ix->packed_dna)
+        return fail(HSA_E_ARG, "the SAM stage needs the SA samples, the block list and the packed text "
+                               "(hsa_index_attach_sa / _blocks / _packed_dna)");
+    if (n_reads > 0x7FFFFFF0ull) return fail(HSA_E_ARG, "too many reads in one batch");
+    if (n_occ < 0 || n_occ > 1000) return fail(HSA_E_ARG, "n_occ out of range");
+    // ---- host: the drand48-ordered selection (bwtse.c:898-910) ----
+    size_t bytes = 0, n_hits = 0; uint32_t max_len = 0, max_ext = 0;
+    for (size_t i = 0; i < n_reads; ++i) {
+        if (len[i] > 4095) return fail(HSA_E_ARG, "reads longer than 4095 bases are not supported");
+        if (n_aln[i] < 0) return fail(HSA_E_ARG, "negative n_aln");
+        if (n_aln[i] && !aln) return fail(HSA_E_ARG, "hits without a hit array");
+        bytes = std::max(bytes, (size_t)off[i] + len[i]); max_len = std::max(max_len, len[i]);
+        if (n_aln[i]) n_hits = std::max(n_hits, (size_t)aln_off[i] + (size_t)n_aln[i]);
+    }
+    if (host_grow(res->rec, res->cap_rec, n_reads)) return fail(HSA_E_NOMEM, "out of host memory");
+    memset(res->rec, 0, n_reads * sizeof(hsa_sam1_t));
+    Rng48 rng{*rng48_state & 0xFFFFFFFFFFFFull};
+    size_t n_multi = 0; const uint32_t *words = reinterpret_cast<const uint32_t *>(aln);
+    for (size_t i = 0; i < n_reads; ++i) {
+        // worst case of one read: every occurrence of every hit (<= n_occ + 1) or 100 positions of a spliced pair
+        if (host_grow(res->multi, res->cap_multi, n_multi + std::max<size_t>(100, (size_t)n_occ + 2))) return fail(HSA_E_NOMEM, "out of host memory");
+        SamRec &s = *reinterpret_cast<SamRec *>(res->rec + i);
+        s.multi_off = (uint32_t)n_multi;
+        const uint32_t own = sam_select(n_aln[i] ? words + 9 * aln_off[i] : nullptr, n_aln[i], n_occ, rng, s,
+                                        reinterpret_cast<SamMulti *>(res->multi) + n_multi);
+        n_multi += own;
+        if (n_multi > 0xFFFFFFF0ull) return fail(HSA_E_ARG, "too many alternative hits in one batch");
+        max_ext = std::max(max_ext, s.n_gapo + s.n_gape);
+        for (uint32_t j = 0; j < s.n_multi; ++j) max_ext = std::max(max_ext, res->multi[s.multi_off + j].gap);
+    }
+    *rng48_state = rng.x;
+    res->n_multi = n_multi;
+    // ---- device ----
+    CU(cudaSetDevice(ix->device));
+    cudaStream_t s = ix->stream;
+    hsa_index *mix = const_cast<hsa_index *>(ix);
+    if (!mix->sam_cache) mix->sam_cache = new SamCache();
+    SamCache &C = *mix->sam_cache;
+    std::vector<int32_t> maxdiff;
+    if (opt->fnr > 0.0f) { maxdiff.resize((size_t)max_len + 1); for (uint32_t L = 0; L <= max_len; ++L) maxdiff[L] = hsa_cal_maxdiff((int)L, 0.02, opt->fnr); }
+    if (C.codes.alloc(bytes + 16) || C.off.alloc(n_reads * 8) || C.len.alloc(n_reads * 4) || C.n_aln.alloc(n_reads * 4) ||
+        C.aln_off.alloc(n_reads * 8) || C.aln.alloc(std::max<size_t>(n_hits, 1) * 36) || C.rec.alloc(n_reads * sizeof(SamRec)) ||
+        C.multi.alloc(std::max<size_t>(n_multi, 1) * sizeof(SamMulti)) || C.list.alloc(n_reads * 4) || C.cnt.alloc(8 * sizeof(unsigned long long)) ||
+        C.maxdiff.alloc(((size_t)max_len + 1) * 4))
+        return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
+    CU(cudaMemcpyAsync(C.codes.p, codes, bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(C.off.p, off, n_reads * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(C.len.p, len, n_reads * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(C.n_aln.p, n_aln, n_reads * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(C.aln_off.p, aln_off, n_reads * 8, cudaMemcpyHostToDevice, s));
+    if (n_hits) CU(cudaMemcpyAsync(C.aln.p, aln, n_hits * 36, cudaMemcpyHostToDevice, s));
+    if (!maxdiff.empty()) CU(cudaMemcpyAsync(C.maxdiff.p, maxdiff.data(), maxdiff.size() * 4, cudaMemcpyHostToDevice, s));
+    SamParams P;
+    memset(&P, 0, sizeof(P));
+    P.env.ix = ix->ix; P.env.sa_value = ix->sa_value; P.env.sa_interval = ix->sa_interval;
+    P.env.blocks4 = ix->blocks4; P.env.n_blocks = ix->n_blocks; P.env.packed_dna = ix->packed_dna; P.env.dna_length = ix->dna_length;
+    P.codes = C.codes.as<uint8_t>(); P.read_off = C.off.as<uint64_t>(); P.read_len = C.len.as<uint32_t>(); P.n_reads = (uint32_t)n_reads;
+    P.n_aln = C.n_aln.as<int32_t>(); P.aln_off = C.aln_off.as<uint64_t>(); P.aln = C.aln.as<uint32_t>();
+    P.rec = C.rec.as<SamRec>(); P.multi = C.multi.as<SamMulti>();
+    P.maxdiff_by_len = maxdiff.empty() ? nullptr : C.maxdiff.as<int32_t>(); P.max_mm = opt->max_diff; P.max_len = max_len;
+    P.dp_list = C.list.as<uint32_t>();
+    unsigned long long *cnt = C.cnt.as<unsigned long long>();        // {cigar words, md bytes, dp reads, cursor, status}
+    P.cigar_used = cnt; P.md_used = cnt + 1; P.dp_count = cnt + 2; P.cursor = cnt + 3; P.status = reinterpret_cast<uint32_t *>(cnt + 4);
+    // arena sizes: a guess first; the counters run past the caps, so a second attempt is sized exactly
+    size_t cigar_cap = n_reads / 2 + 4096, md_cap = n_reads * 16 + 4096;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    unsigned long long h[5] = {0, 0, 0, 0, 0};
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (C.cigar.alloc(cigar_cap * 4) || C.md.alloc(md_cap)) return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
+        P.cigar = C.cigar.as<uint32_t>(); P.cigar_cap = cigar_cap; P.md = C.md.as<char>(); P.md_cap = md_cap;
+        CU(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), s));
+        CU(cudaMemcpyAsync(C.rec.p, res->rec, n_reads * sizeof(SamRec), cudaMemcpyHostToDevice, s));
+        if (n_multi) CU(cudaMemcpyAsync(C.multi.p, res->multi, n_multi * sizeof(SamMulti), cudaMemcpyHostToDevice, s));
+        CU(cudaEventRecord(e0, s));
+        const uint32_t grid = (uint32_t)std::min<size_t>((n_reads + 255) / 256, (size_t)ix->sm_count * 8);
+        sam_pos_kernel<<<grid, 256, 0, s>>>(P);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        const uint32_t n_dp = (uint32_t)h[2];
+        if (n_dp) {
+            // scratch: (len2 + 1) rows of W trace-back bytes + len1 reference bases + 3 x (len1 + 1) score words per worker
+            const uint32_t len1_cap = max_len + max_ext, len2_cap = max_len;
+            const uint32_t W = std::min<uint32_t>(2u * DP_BAND + max_ext + 1u, len1_cap + 1u);
+            const size_t per_bytes = (size_t)(len2_cap + 1u) * W + len1_cap + 1u, per_rows = std::max<size_t>(3 * ((size_t)len1_cap + 1), (size_t)len1_cap + len2_cap + 2);
+            uint32_t workers = (uint32_t)std::min<size_t>({(size_t)n_dp, (size_t)ix->sm_count * 256, std::max<size_t>(128, ((size_t)1 << 30) / (per_bytes + 4 * per_rows))});
+            workers = (workers + 127u) / 128u * 128u;
+            if (C.dp_bytes.alloc(per_bytes * workers) || C.dp_rows.alloc(per_rows * 4 * workers)) return fail(HSA_E_CUDA, "out of device memory for the DP scratch");
+            P.dp_bytes = C.dp_bytes.as<uint8_t>(); P.dp_rows = C.dp_rows.as<int32_t>(); P.dp_workers = workers; P.dp_w = W;
+            P.dp_len1_cap = len1_cap; P.dp_len2_cap = len2_cap;
+            sam_dp_kernel<<<workers / 128u, 128, 0, s>>>(P, n_dp);
+            CU(cudaGetLastError());
+        }
+        CU(cudaEventRecord(e1, s));
+        CU(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        const uint32_t status = (uint32_t)(h[4] & 0xFFFFFFFFull);
+        if (status == SAM_SCRATCH) return fail(HSA_E_CAPACITY, "an alignment exceeded the DP scratch (gap count beyond the batch's maximum)");
+        if (h[0] <= cigar_cap && h[1] <= md_cap && status == SAM_OK) break;
+        if (attempt == 2) return fail(HSA_E_CAPACITY, "CIGAR / MD arenas overflowed twice");
+        cigar_cap = std::max<size_t>(cigar_cap, (size_t)h[0] + 64); md_cap = std::max<size_t>(md_cap, (size_t)h[1] + 64);
+    }
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    res->kernel_ms = ms; res->n_refined = h[2]; res->n_cigar = (size_t)h[0]; res->md_bytes = (size_t)h[1];
+    if (host_grow(res->cigar, res->cap_cigar, res->n_cigar) || host_grow(res->md, res->cap_md, res->md_bytes)) return fail(HSA_E_NOMEM, "out of host memory");
+    CU(cudaMemcpyAsync(res->rec, C.rec.p, n_reads * sizeof(SamRec), cudaMemcpyDeviceToHost, s));
+    if (n_multi) CU(cudaMemcpyAsync(res->multi, C.multi.p, n_multi * sizeof(SamMulti), cudaMemcpyDeviceToHost, s));
+    if (res->n_cigar) CU(cudaMemcpyAsync(res->cigar, C.cigar.p, res->n_cigar * 4, cudaMemcpyDeviceToHost, s));
+    if (res->md_bytes) CU(cudaMemcpyAsync(res->md, C.md.p, res->md_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return HSA_OK;
+}
+
+// ---- bwa_print_sam1 (bwtse.c:677-835), the single-end / no-quality / no-read-group case -------------------------------
+namespace {
+struct TextBuf {
+    char *p = nullptr; size_t n = 0, cap = 0; bool bad = false;
+    void need(size_t k) { if (n + k > cap) { size_t c = std::max(cap * 2, n + k + 4096); char *q = (char *)realloc(p, c); if (!q) { bad = true; return; } p = q; cap = c; } }
+    void put(char c) { need(1); if (!bad) p[n++] = c; }
+    void str(const char *s) { const size_t k = strlen(s); need(k); if (!bad) { memcpy(p + n, s, k); n += k; } }
+    void num(long long v) { char t[32]; snprintf(t, sizeof(t), "%lld", v); str(t); }
+};
+}
+
+extern "C" int hsa_sam_format(const hsa_sam_result_t *res, size_t first, size_t count, const uint8_t *codes, const uint64_t *off,
+                              const uint32_t *len, const char *const *names, const char *const *chr_names, size_t n_chr,
+                              const hsa_gap_opt_t *opt, char **text_out, size_t *bytes_out)
+{
+    if (!res || !codes || !off || !len || !chr_names || !opt || !text_out || !bytes_out) return fail(HSA_E_ARG, "null argument");
+    if (first + count > res->n_reads) return fail(HSA_E_ARG, "read range outside the result");
+    TextBuf T;
+    for (size_t r = first; r < first + count; ++r) {
+        const hsa_sam1_t &p = res->rec[r];
+        if (p.type == TYPE_NO_MATCH) continue;                                      // bwtse.c:923-924
+        if (p.seq_id >= n_chr) { free(T.p); return fail(HSA_E_ARG, "seq_id outside chr_names"); }
+        const uint8_t *seq = codes + off[r]; const uint32_t L = len[r];
+        char nm[32];
+        if (names && names[r]) T.str(names[r]); else { snprintf(nm, sizeof(nm), "r%zu", r); T.str(nm); }
+        T.put('\t'); T.num(p.strand ? 16 : 0); T.put('\t'); T.str(chr_names[p.seq_id]); T.put('\t');
+        T.num((int)p.ori_pos); T.put('\t'); T.num(p.mapQ); T.put('\t');
+        if (p.n_cigar) for (uint32_t j = 0; j < p.n_cigar; ++j) {
+            const uint32_t c = res->cigar[p.cigar_off + j], op = c >> 28;
+            T.num((int)(c & 0x0FFFFFFFu)); T.put(op < 9 ? "MIDNSHP=X"[op] : '?');      // (the reference indexes past its table there)
+        } else { T.num(L); T.put('M'); }
+        T.str("\t*\t0\t0\t");
+        if (!p.strand) for (uint32_t j = 0; j < L; ++j) T.put("ACGTN"[seq[j] > 4 ? 4 : seq[j]]);
+        else for (uint32_t j = 0; j < L; ++j) T.put("TGCAN"[seq[L - 1 - j] > 4 ? 4 : seq[L - 1 - j]]);
+        T.str("\t*");
+        T.str("\tXT:A:"); T.put("NURMS"[p.type > 4 ? 0 : p.type]);
+        T.str((opt->mode & HSA_MODE_COMPREAD) ? "\tNM:i:" : "\tCM:i:"); T.num(p.nm);
+        if (p.type != TYPE_MATESW) {
+            T.str("\tX0:i:"); T.num(p.c1);
+            if ((long long)p.c1 <= (long long)opt->max_top2) { T.str("\tX1:i:"); T.num(p.c2); }
+        }
+        T.str("\tXM:i:"); T.num(p.n_mm); T.str("\tXO:i:"); T.num(p.n_gapo); T.str("\tXG:i:"); T.num(p.n_gapo + p.n_gape);
+        if (p.md_len) { T.str("\tMD:Z:"); T.need(p.md_len); if (!T.bad) { memcpy(T.p + T.n, res->md + p.md_off, p.md_len); T.n += p.md_len; } }
+        if (p.n_multi) {
+            T.str("\tXA:Z:");
+            for (uint32_t i = 0; i < p.n_multi; ++i) {
+                const hsa_multi1_t &q = res->multi[p.multi_off + i];
+                if (q.seq_id >= n_chr) { free(T.p); return fail(HSA_E_ARG, "seq_id outside chr_names"); }
+                T.str(chr_names[q.seq_id]); T.put(','); T.put(q.strand ? '-' : '+'); T.num((int)q.ori_pos);
+                if (q.n_cigar) for (uint32_t k = 0; k < q.n_cigar; ++k) {
+                    const uint32_t c = res->cigar[q.cigar_off + k], op = c >> 28;
+                    T.num((int)(c & 0x0FFFFFFFu)); T.put(op < 5 ? "MIDNS"[op] : '?');
+                } else { T.put(','); T.num(q.gap + q.mm); T.put(';'); }
+            }
+        }
+        T.put('\n');
+        if (T.bad) { free(T.p); return fail(HSA_E_NOMEM, "out of host memory"); }
+    }
+    *text_out = T.p; *bytes_out = T.n;
+    return HSA_OK;
+}

@@ -267,6 +267,55 @@ int  hsa_splice_match_batch(const hsa_index_t *idx, const uint8_t *codes, const 
                             size_t n_reads, const hsa_gap_opt_t *opts, size_t n_opts, const uint32_t *opt_idx,
                             int32_t *n_aln_out, hsa_aln1_t *aln_out, uint64_t *occ_lookups);
 
+/* ---- from hits to SAM fields -----------------------------------------------------------------
+ * Replaces what generate_sam_se_core (bwtse.h:27; bwtse.c:884-931) computes for a batch before it prints: the hit selection
+ * of bwt_aln2seq_core (bwtse.c:21-113; n_occ = 3 at bwtaln.c:514), bwa_cal_pac_pos (bwtse.c:350-369) with
+ * bwt_aln2pos_splicing / bwt_combine_segment_splice for spliced hits (:197-348), bwa_refine_gapped (:536-638) with
+ * refine_gapped_core (:380-440) = aln_global_core (stdaln.c:345-524) + bwa_aln_path2cigar (bwtaln.c:624-634), and
+ * bwa_cal_md1 (bwtse.c:442-494).  Needs hsa_index_attach_sa / _blocks / _packed_dna.
+ * The selection consumes the reference's process-wide drand48 stream in read order (a sequential chain, evaluated on the
+ * host); *rng48_state is that stream's 48-bit state, in and out -- 0 for a process that has not drawn yet (glibc).  Everything
+ * after it runs on the GPU: positions, pairing of spliced parts, the banded dynamic programme, CIGAR, MD and NM.
+ * Inputs: the reads as for hsa_whole_reads, and per read its hits as the driver leaves them in bwa_seq_t::n_aln / aln
+ * (hsa_whole_reads' result, with hsa_splice_match_batch's two parts for the reads it rescued); opt: the caller's gap_opt_t
+ * as generate_sam_se_core sees it (fnr > 0: max_diff per read length as bwa_cal_pac_pos_core does, else opt->max_diff).
+ * Results (library-managed host arrays, released by hsa_sam_result_free; zero-initialise the struct before first use):
+ * rec[r] = the bwa_seq_t fields of read r; cigar words are bwa_cigar_t (op << 28 | len); md strings are not terminated. */
+typedef struct hsa_sam1_t {            /* bwa_seq_t (bwtaln.h:92-122), the fields generate_sam_se_core writes */
+    uint32_t type, strand, n_mm, n_gapo, n_gape, mapQ;
+    int32_t  score;
+    uint32_t sa, seq_id, ori_pos, occ_pos, c1, c2;
+    int32_t  start, end;
+    uint32_t n_cigar, cigar_off;        /* cigar[cigar_off .. + n_cigar); n_cigar == 0: no CIGAR array (prints "<len>M") */
+    uint32_t nm, md_len, md_off;        /* md[md_off .. + md_len); md_len == 0: no MD                                   */
+    uint32_t n_multi, multi_off;        /* multi[multi_off .. + n_multi): the alternative hits (XA)                      */
+} hsa_sam1_t;
+typedef struct hsa_multi1_t {          /* bwt_multi1_t (bwtaln.h:82-90) */
+    uint32_t n_cigar, cigar_off, gap, mm, strand, sa, ori_pos, occ_pos, seq_id, aln_id;
+    int32_t  start, end;
+} hsa_multi1_t;
+typedef struct hsa_sam_result_t {
+    size_t        n_reads;
+    hsa_sam1_t   *rec;
+    hsa_multi1_t *multi;  size_t n_multi;
+    uint32_t     *cigar;  size_t n_cigar;
+    char         *md;     size_t md_bytes;
+    uint64_t      n_refined;            /* reads that went through the dynamic programme */
+    float         kernel_ms;            /* device time of the two kernels */
+    size_t        cap_rec, cap_multi, cap_cigar, cap_md;
+} hsa_sam_result_t;
+int  hsa_sam_se_batch(const hsa_index_t *idx, const uint8_t *codes, const uint64_t *off, const uint32_t *len, size_t n_reads,
+                      const int32_t *n_aln, const uint64_t *aln_off, const hsa_aln1_t *aln, const hsa_gap_opt_t *opt,
+                      int n_occ, uint64_t *rng48_state, hsa_sam_result_t *res);
+void hsa_sam_result_free(hsa_sam_result_t *res);
+/* bwa_print_sam1 (bwtse.c:677-835) for single-end reads without qualities, read groups or barcodes: the SAM lines of reads
+ * [first, first + count) whose type is not BWA_TYPE_NO_MATCH, as generate_sam_se_core prints them (bwtse.c:922-926).
+ * names[r] (NULL: "r<r>"), chr_names[seq_id] = HSP::chrName; mode / max_top2 from the caller's gap_opt_t.  *text_out is a
+ * malloc'ed buffer of *bytes_out bytes (not terminated) owned by the caller.  Host-only formatting. */
+int  hsa_sam_format(const hsa_sam_result_t *res, size_t first, size_t count, const uint8_t *codes, const uint64_t *off,
+                    const uint32_t *len, const char *const *names, const char *const *chr_names, size_t n_chr,
+                    const hsa_gap_opt_t *opt, char **text_out, size_t *bytes_out);
+
 /* ---- roofline probe: random 32-byte-sector loads over `footprint_bytes` ----
  * The random-access denominator on this GPU: achieved GB/s (sectors * 32 B / time) at full occupancy of five access
  * shapes -- [0] four dependent chains per thread with two 16-byte loads per sector, [1..3] 4 / 8 / 16 independent 256-bit

@@ -737,6 +737,89 @@ static int mode_locate(int argc, char **argv)
     return 0;
 }
 
+
+/* ---------------------------------------------------------------- sam
+ * The stock batch loop of bwa_aln_core (bwtaln.c:477-522): bwa_cal_sa_reg_gap, then generate_sam_se_core (bwtse.c:884-931:
+ * bwt_aln2seq_core hit selection with the process-wide drand48 stream, bwa_cal_pac_pos, bwa_refine_gapped, bwa_print_sam1)
+ * with n_occ = 3 as bwtaln.c:514 passes it.  The SAM text the reference prints goes to <out.sam>; <out.bin> receives, per
+ * read, the bwa_seq_t fields generate_sam_se_core computed:
+ *   'HSAM' n, then per read 20 words {type, strand, n_mm, n_gapo, n_gape, mapQ, score, sa, seq_id, ori_pos, occ_pos, c1, c2,
+ *   start, end, n_cigar, nm, md_len, n_multi, 0}, n_cigar cigar words, md bytes padded to 4, and per multi record 12 words
+ *   {n_cigar, gap, mm, strand, sa, ori_pos, occ_pos, seq_id, aln_id, start, end, 0} + its cigar words.
+ * Reads of type NO_MATCH dump zeros after the type word (the reference leaves stale values there and prints nothing). */
+#include "bwtse.h"
+static void put_sam_rec(FILE *f, const bwa_seq_t *p)
+{
+    uint32_t w[20]; int j; uint32_t md_len = 0, pad = 0;
+    memset(w, 0, sizeof(w));
+    w[0] = p->type;
+    if (p->type != BWA_TYPE_NO_MATCH) {
+        md_len = p->md ? (uint32_t)strlen(p->md) : 0;
+        w[1] = p->strand; w[2] = p->n_mm; w[3] = p->n_gapo; w[4] = p->n_gape; w[5] = p->mapQ; w[6] = (uint32_t)p->score;
+        w[7] = p->sa; w[8] = p->seq_id; w[9] = p->ori_pos; w[10] = p->occ_pos; w[11] = (uint32_t)p->c1; w[12] = (uint32_t)p->c2;
+        w[13] = (uint32_t)p->start; w[14] = (uint32_t)p->end; w[15] = p->cigar ? (uint32_t)p->n_cigar : 0; w[16] = p->nm; w[17] = md_len;
+        w[18] = (uint32_t)p->n_multi;
+    }
+    fwrite(w, 4, 20, f);
+    if (p->type == BWA_TYPE_NO_MATCH) return;
+    if (p->cigar) fwrite(p->cigar, 4, p->n_cigar, f);
+    if (md_len) { fwrite(p->md, 1, md_len, f); if (md_len & 3) fwrite(&pad, 1, 4 - (md_len & 3), f); }
+    for (j = 0; j < p->n_multi; ++j) {
+        const bwt_multi1_t *q = p->multi + j; uint32_t m[12];
+        m[0] = q->cigar ? q->n_cigar : 0; m[1] = q->gap; m[2] = q->mm; m[3] = q->strand; m[4] = q->sa; m[5] = q->ori_pos; m[6] = q->occ_pos;
+        m[7] = q->seq_id; m[8] = q->aln_id; m[9] = (uint32_t)q->start; m[10] = (uint32_t)q->end; m[11] = 0;
+        fwrite(m, 4, 12, f);
+        if (q->cigar) fwrite(q->cigar, 4, q->n_cigar, f);
+    }
+}
+
+static int mode_sam(int argc, char **argv)
+{
+    Idx2BWT *bi; reads_t r; FILE *fo; hopt_t h; gap_opt_t *opt0, *opt; uint32_t hdr[2], b; int saved_stdout, n_occ = 3, i;
+    bwt_array_t *arr; double secs_search = 0, secs_sam = 0; unsigned long long n_matched = 0, n_gapped = 0, n_splice = 0;
+    if (argc < 6) die("usage: sam <prefix> <reads> <out.bin> <out.sam> [opts] [batch=N] [nocc=K]");
+    bi = load_index(argv[2]); r = load_reads(argv[3]);
+    for (i = 6; i < argc; ++i) if (strncmp(argv[i], "nocc=", 5) == 0) { n_occ = atoi(argv[i] + 5); argv[i] = "batch=100000"; }
+    opt0 = parse_opts(argc, argv, 6, &h);
+    opt = (gap_opt_t*)calloc(2, sizeof(gap_opt_t)); *opt = *opt0;
+    arr = bwt_array_init();
+    fo = fopen(argv[4], "wb"); if (!fo) die("cannot open out.bin");
+    hdr[0] = 0x4D415348u; hdr[1] = r.n; fwrite(hdr, 4, 2, fo);
+    fflush(stdout); saved_stdout = dup(1);
+    if (!freopen(argv[5], "w", stdout)) die("cannot open out.sam");
+    for (b = 0; b < r.n; b += (uint32_t)h.batch) {
+        uint32_t e = b + (uint32_t)h.batch < r.n ? b + (uint32_t)h.batch : r.n, k;
+        int n = (int)(e - b);
+        bwa_seq_t *seqs = (bwa_seq_t*)calloc(n, sizeof(bwa_seq_t));
+        double t0;
+        for (k = b; k < e; ++k) {                                  /* what bwa_read_seq leaves (bwaseqio.c:198-224), no qualities */
+            bwa_seq_t *p = seqs + (k - b); char nm[32];
+            p->tid = -1; p->full_len = p->clip_len = p->len = r.len[k];
+            p->seq = (ubyte_t*)calloc(p->len + 1, 1); memcpy(p->seq, r.codes + r.off[k], p->len);
+            p->rseq = (ubyte_t*)calloc(p->len + 1, 1); memcpy(p->rseq, p->seq, p->len);
+            seq_reverse(p->len, p->rseq, opt->mode & BWA_MODE_COMPREAD);
+            sprintf(nm, "r%u", k); p->name = strdup(nm);
+        }
+        t0 = now_s();
+        g_driver(0, bi, n, seqs, opt, arr);
+        secs_search += now_s() - t0;
+        t0 = now_s();
+        generate_sam_se_core(bi, n, seqs, opt, n_occ);
+        secs_sam += now_s() - t0;
+        for (k = 0; k < (uint32_t)n; ++k) {
+            bwa_seq_t *p = seqs + k;
+            put_sam_rec(fo, p);
+            if (p->type != BWA_TYPE_NO_MATCH) { ++n_matched; if (p->cigar) ++n_gapped; if (p->type == BWA_TYPE_SPLICING) ++n_splice; }
+        }
+        bwa_free_read_seq(n, seqs);
+    }
+    fclose(fo);
+    fflush(stdout); dup2(saved_stdout, 1); close(saved_stdout);
+    printf("{\"mode\":\"sam\",\"reads\":%u,\"batch\":%d,\"n_occ\":%d,\"matched\":%llu,\"with_cigar\":%llu,\"splicing\":%llu,"
+           "\"secs_search\":%.6f,\"secs_sam\":%.6f}\n", r.n, h.batch, n_occ, n_matched, n_gapped, n_splice, secs_search, secs_sam);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc < 2) die("usage: hsa_ref <index|occ|width|percall|seeds|driver|whole|dumpindex|maxdiff> ...");
@@ -752,6 +835,7 @@ int main(int argc, char **argv)
     if (strcmp(argv[1], "percall") == 0) return mode_percall(argc, argv);
     if (strcmp(argv[1], "seeds") == 0) return mode_seeds(argc, argv);
     if (strcmp(argv[1], "driver") == 0) return mode_driver(argc, argv);
+    if (strcmp(argv[1], "sam") == 0) return mode_sam(argc, argv);
 #ifdef HSA_WITH_GPU_SHIM
     if (strcmp(argv[1], "gpudriver") == 0) {
         /* the same batch loop with bwa_cal_sa_reg_gap replaced by the GPU shim (needs a full index: the splice

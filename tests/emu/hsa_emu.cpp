@@ -11,6 +11,7 @@
 #include "../../hsa_b200/csrc/hsa_core.cuh"
 #include "../../hsa_b200/csrc/hsa_coop.cuh"
 #include "../../hsa_b200/csrc/hsa_splice.cuh"
+#include "../../hsa_b200/csrc/hsa_sam.cuh"
 #include "../../include/hsa_b200.h"
 
 using namespace hsa;
@@ -338,5 +339,46 @@ void emu_set_simt(int on) { g_simt = on; for (int i = 0; i < 3; ++i) { g_phase_r
 void emu_phase_stats(uint64_t *runs, uint64_t *lanes) { for (int i = 0; i < 3; ++i) { runs[i] = g_phase_runs[i]; lanes[i] = g_phase_lanes[i]; } }
 uint64_t emu_last_extra(void) { return 0; }
 uint64_t emu_last_steps(void) { return g_last_steps; }
+
+// The SAM-field stage (hsa_sam.cuh) for every read, one after the other: the host selection, sam_pos_item, sam_dp_item.
+// counts_out: {multi slots, cigar words, md bytes, reads refined, status}; returns 0, or -1 when an output array is too small.
+int emu_sam(void *p, const uint32_t *sa_value, uint32_t sa_interval, const uint32_t *blocks4, uint32_t n_blocks,
+            const uint32_t *packed_dna, uint32_t dna_length, const uint8_t *codes, const uint64_t *off, const uint32_t *len, size_t n,
+            const int32_t *n_aln, const uint64_t *aln_off, const uint32_t *aln, const int32_t *maxdiff_by_len, int32_t max_mm, int n_occ, uint64_t *rng_state,
+            SamRec *rec_out, SamMulti *multi_out, size_t multi_cap, uint32_t *cigar_out, size_t cigar_cap, char *md_out, size_t md_cap,
+            uint64_t *counts_out)
+{
+    EmuIndex *e = (EmuIndex *)p;
+    Rng48 rng{*rng_state};
+    size_t n_multi = 0; uint32_t max_len = 0, max_ext = 0;
+    memset(rec_out, 0, n * sizeof(SamRec));
+    for (size_t i = 0; i < n; ++i) {
+        if (n_multi + 128 + (size_t)n_occ > multi_cap) return -1;
+        rec_out[i].multi_off = (uint32_t)n_multi;
+        n_multi += sam_select(n_aln[i] ? aln + 9 * aln_off[i] : nullptr, n_aln[i], n_occ, rng, rec_out[i], multi_out + n_multi);
+        max_len = std::max(max_len, len[i]); max_ext = std::max(max_ext, rec_out[i].n_gapo + rec_out[i].n_gape);
+        for (uint32_t j = 0; j < rec_out[i].n_multi; ++j) max_ext = std::max(max_ext, multi_out[rec_out[i].multi_off + j].gap);
+    }
+    *rng_state = rng.x;
+    SamParams P;
+    memset(&P, 0, sizeof(P));
+    P.env.ix = e->ix; P.env.sa_value = sa_value; P.env.sa_interval = sa_interval; P.env.blocks4 = blocks4; P.env.n_blocks = n_blocks;
+    P.env.packed_dna = packed_dna; P.env.dna_length = dna_length;
+    P.codes = codes; P.read_off = off; P.read_len = len; P.n_reads = (uint32_t)n;
+    P.n_aln = n_aln; P.aln_off = aln_off; P.aln = aln; P.rec = rec_out; P.multi = multi_out;
+    P.maxdiff_by_len = maxdiff_by_len; P.max_mm = max_mm; P.max_len = max_len;
+    unsigned long long cnt[5] = {0, 0, 0, 0, 0}; uint32_t status = 0;
+    std::vector<uint32_t> list(n + 1);
+    P.cigar = cigar_out; P.cigar_cap = cigar_cap; P.cigar_used = cnt; P.md = md_out; P.md_cap = md_cap; P.md_used = cnt + 1;
+    P.dp_list = list.data(); P.dp_count = cnt + 2; P.cursor = cnt + 3; P.status = &status;
+    for (size_t i = 0; i < n; ++i) sam_pos_item(P, (uint32_t)i);
+    const uint32_t len1_cap = max_len + max_ext, len2_cap = max_len, W = std::min<uint32_t>(2u * DP_BAND + max_ext + 1u, len1_cap + 1u);
+    std::vector<uint8_t> bytes((size_t)(len2_cap + 1u) * W + len1_cap + 1u);
+    std::vector<int32_t> rows(std::max<size_t>(3 * ((size_t)len1_cap + 1), (size_t)len1_cap + len2_cap + 2));
+    P.dp_bytes = bytes.data(); P.dp_rows = rows.data(); P.dp_workers = 1; P.dp_w = W; P.dp_len1_cap = len1_cap; P.dp_len2_cap = len2_cap;
+    for (unsigned long long w = 0; w < cnt[2]; ++w) sam_dp_item(P, list[w], 0);
+    counts_out[0] = n_multi; counts_out[1] = cnt[0]; counts_out[2] = cnt[1]; counts_out[3] = cnt[2]; counts_out[4] = status;
+    return (cnt[0] > cigar_cap || cnt[1] > md_cap) ? -1 : 0;
+}
 
 } // extern "C"

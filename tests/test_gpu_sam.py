@@ -1,0 +1,142 @@
+"""GPU (-m gpu): the SAM-field stage through the C ABI (hsa_sam_se_batch / hsa_sam_format) against the reference.
+
+* goldens made by the unmodified reference's generate_sam_se_core (tests/golden/golden_sam.*): every field of every read,
+  and the SAM text bwa_print_sam1 printed for them (sha256 of the printable lines);
+* end to end on the GPU: hsa_whole_reads + hsa_splice_match_batch -> hsa_sam_se_batch == the same goldens (the stage consumes
+  the search's own output, as generate_sam_se_core consumes bwa_cal_sa_reg_gap's);
+* at bench scale against the reference binary run on the box: 46 Mb genome, 120 k reads (gapped, repeated, spliced).
+"""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import emu_lib as el
+import oracle_lib as ol
+import sam_common as sc
+from hsa_b200 import api, synth, synth_torch
+from test_sam_emu import CASES, GoldenSam
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gs():
+    return GoldenSam()
+
+
+@pytest.fixture(scope="module")
+def index(gs):
+    ix = api.Index.upload(gs.base.index(), 0)
+    yield ix
+    ix.close()
+
+
+def _opt(okw):
+    return api.gap_init_opt(**okw)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_sam_fields_and_text_vs_golden(gs, index, name):
+    c, rs, n_aln, rows, want = gs.case(name)
+    na, off, a9 = sc.hits_input(n_aln, rows)
+    opt = _opt(c["opt"])
+    res = index.sam_se(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, na, off, a9, opt, n_occ=c["n_occ"])
+    got = sc.unpack_result(res.rec, res.multi, res.cigar, res.md)
+    bad = sc.diff(got, want)
+    assert not bad, "\n".join(bad)
+    assert res.n_refined >= c["with_cigar"]
+    opt.mode &= ~1                                          # the driver has cleared GAPE in the caller's options (bwtaln.c:261)
+    text = res.format(["synth"])
+    assert text.count(b"\n") == c["lines"]
+    assert hashlib.sha256(sc.printable_lines(text)).hexdigest() == c["text_sha256"]
+
+
+@pytest.mark.parametrize("name", ["dna_and_junctions", "dna_150_n5o2"])
+def test_search_then_sam_end_to_end(gs, index, name):
+    """hits straight from the GPU search (whole reads, then the splice fallback for the reads that found nothing)."""
+    c, rs, n_aln_ref, rows_ref, want = gs.case(name)
+    opt = _opt(c["opt"])
+    off = rs.offsets[:-1].astype(np.uint64)
+    res = index.whole_reads(rs.codes, off, rs.lens, opt)
+    n_aln = res.n_aln.copy()
+    rows = [el.aln9_to_rows12(res.item(i)) for i in range(rs.n)]
+    miss = np.flatnonzero(n_aln == 0)
+    # bwa_cal_sa_reg_gap skips reads with too many N / poly-A/T before it would reach the splice fallback (bwtaln.c:314-325)
+    fmax = api.bwa_cal_maxdiff(int(rs.lens.max()), 0.02, opt.fnr) if opt.fnr > 0 else opt.max_diff
+    keep = []
+    for i in miss.tolist():
+        r = rs.read(i)
+        if int((r > 3).sum()) > fmax or not r[:15].any() or bool((r[:15] == 3).all()):
+            continue
+        keep.append(i)
+    if keep:
+        sub = synth.ReadSet(rs.lens[keep], np.concatenate([rs.read(i) for i in keep]))
+        lens = sorted(set(sub.lens.tolist()))
+        base = ol.default_opt(**c["opt"])
+        opts = [api.GapOpt.from_buffer_copy(bytes(el.resolve_read_opt(base, L, 1))) for L in lens]
+        for o in opts:                                      # local_opt as the driver holds it (bwtaln.c:273-276)
+            if o.max_diff < o.max_gapo:
+                o.max_gapo = o.max_diff
+        oi = np.asarray([lens.index(int(x)) for x in sub.lens], dtype=np.uint32)
+        sn, sa = index.splice_match(sub.codes, sub.offsets[:-1].astype(np.uint64), sub.lens, opts, oi)
+        for j, i in enumerate(keep):
+            n_aln[i] = sn[j]
+            rows[i] = el.aln9_to_rows12(sa[j, :sn[j]])
+    rows = np.concatenate(rows) if rows else np.zeros((0, 12), np.uint32)
+    assert np.array_equal(n_aln, n_aln_ref) and np.array_equal(rows, rows_ref), "the GPU search's hits differ from the driver's"
+    na, ao, a9 = sc.hits_input(n_aln, rows)
+    out = index.sam_se(rs.codes, off, rs.lens, na, ao, a9, opt, n_occ=c["n_occ"])
+    bad = sc.diff(sc.unpack_result(out.rec, out.multi, out.cigar, out.md), want)
+    assert not bad, "\n".join(bad)
+
+
+def test_rng_state_chains_batches(gs, index):
+    c, rs, n_aln, rows, want = gs.case("repeats_75")
+    half = rs.n // 2
+    off_rows = np.concatenate([[0], np.cumsum(n_aln)])
+    got, state = [], 0
+    for lo, hi in ((0, half), (half, rs.n)):
+        sub = rs.subset(lo, hi)
+        na, off, a9 = sc.hits_input(n_aln[lo:hi], rows[off_rows[lo]:off_rows[hi]])
+        r = index.sam_se(sub.codes, sub.offsets[:-1].astype(np.uint64), sub.lens, na, off, a9, _opt({}), rng48_state=state)
+        state = r.rng48_state
+        got += sc.unpack_result(r.rec, r.multi, r.cigar, r.md)
+    assert not sc.diff(got, want)
+
+
+def test_sam_46mb_vs_reference_binary():
+    """Bench scale: 46 Mb genome with planted introns, 120 k reads (100 k DNA reads with indels in 20 %, 20 k junction reads),
+    the reference binary (bwa_cal_sa_reg_gap + generate_sam_se_core, one process: one drand48 stream) on the index files
+    the product wrote, against hsa_sam_se_batch fed with the reference driver's hits; SAM text compared line by line."""
+    from test_gpu_scale import Scale, need_ref
+    need_ref()
+    s = Scale(46_000_003, 5, full=True, n_introns=4000)
+    try:
+        reads = torch.cat([synth_torch.simulate_reads(s.genome, 100_000, 100, 91, indel_frac=0.20),
+                           synth_torch.simulate_junction_reads(s.genome, s.introns, 20_000, 100, 92, sub_rate=0.01)])
+        reads = reads[torch.randperm(reads.shape[0], generator=torch.Generator().manual_seed(3)).to(reads.device)]
+        rs, path = s.reads_file("sam", reads)
+        j = json.loads(subprocess.run([ol.REF_BIN, "sam", s.prefix, path, path + ".bin", path + ".sam"], check=True, capture_output=True,
+                                      text=True).stdout.strip().splitlines()[-1])
+        subprocess.run([ol.REF_BIN, "driver", s.prefix, path, path + ".aln"], check=True, capture_output=True)
+        n_aln, rows = synth.read_aln_dump(path + ".aln")
+        want = sc.parse_ref_dump(path + ".bin")
+        assert j["with_cigar"] > 15_000 and j["splicing"] > 5_000
+        na, off, a9 = sc.hits_input(n_aln, rows)
+        opt = api.gap_init_opt()
+        res = s.ix.sam_se(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, na, off, a9, opt)
+        bad = sc.diff(sc.unpack_result(res.rec, res.multi, res.cigar, res.md), want)
+        assert not bad, "\n".join(bad)
+        opt.mode &= ~1
+        text = sc.printable_lines(res.format(["synth"]))
+        ref_text = sc.printable_lines(open(path + ".sam", "rb").read())
+        assert text == ref_text, "SAM text differs from the reference's"
+        print(f"\n[sam @46 Mb] {rs.n} reads, {res.n_refined} refined, kernels {res.kernel_ms:.2f} ms; reference generate_sam_se_core "
+              f"{j['secs_sam']:.2f} s on one core")
+    finally:
+        s.close()
