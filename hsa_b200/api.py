@@ -557,7 +557,7 @@ def random_sector_probe(device: int, footprint_bytes: int, iters: int = 64) -> f
     return g.value
 
 
-PROBE_VARIANTS = ("chains4_2x128b", "mlp4_256b", "mlp8_256b", "mlp16_256b", "mix8_256b+32b")
+PROBE_VARIANTS = ("chains4_2x128b", "mlp4_256b", "mlp8_256b", "mlp16_256b", "mix8_256b+32b", "lf_walk_256b+4b")
 
 
 def random_sector_probe_ex(device: int, footprint_bytes: int, iters: int = 64) -> dict:

@@ -396,6 +396,32 @@ __global__ void probe_kernel_mix(const uint4 *buf, uint64_t n_sectors, int iters
     if (acc == 0xDEADBEEFu) atomicAdd(sink, 1ull);
 }
 
+// Fourth probe variant, shaped like the LF walk of sa_kernel (the one shipped kernel that out-ran the other variants,
+// VERDICT round 1): ONE dependent chain per thread, the next sector chosen from the data just loaded, chains of geometric
+// length (p = 1/8) that end with a 4-byte load from a second array; 2048 threads per SM, no shared memory.  Counts 1 + 1/8
+// sectors per step.  The first half of `buf` plays the index, the second half the SA samples.
+__global__ void __launch_bounds__(256) probe_kernel_walk(const uint4 *buf, uint64_t n_sectors, int iters, unsigned long long *sink)
+{
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, n_units = n_sectors / 2;
+    uint64_t s = (tid + 4242) * 0x9E3779B97F4A7C15ull;
+    uint32_t acc = 0;
+    const uint32_t *tail = reinterpret_cast<const uint32_t *>(buf + 2 * n_units);
+    for (int it = 0; it < iters; ++it) {
+        const uint64_t u = __umul64hi(s, n_units);
+        uint32_t v[8];
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(buf + 2 * u));
+        const uint32_t x = v[0] ^ v[7];
+        s = s * 6364136223846793005ull + 1442695040888963407ull + ((uint64_t)x << 32);
+        if (((s >> 40) & 7u) == 0u) {
+            acc += __ldg(tail + __umul64hi(s * 0x9E3779B97F4A7C15ull, n_units) * 8);
+            s ^= s >> 29;
+        }
+        acc += x;
+    }
+    if (acc == 0xDEADBEEFu) atomicAdd(sink, 1ull);
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -2085,8 +2111,9 @@ extern "C" int hsa_workspace_check(hsa_workspace_t *ws, uint64_t stats_out[8])
 // ---------------------------------------------------------------------------------------------- roofline probe
 // Variants, all at full occupancy over the same buffer: [0] four dependent chains per thread (two 16-byte loads per
 // sector), [1..3] 4 / 8 / 16 independent 256-bit loads in flight per thread, [4] the sa_kernel-shaped mix (a 256-bit load
-// and a 4-byte load per pair, 8 pairs in flight).  gbs_out[i] = sectors * 32 B / time of variant i, best of three runs.
-enum { PROBE_VARIANTS = 5 };
+// and a 4-byte load per pair, 8 pairs in flight), [5] the LF-walk shape (one data-dependent chain per thread, geometric
+// chain length, 4-byte terminal load).  gbs_out[i] = sectors * 32 B / time of variant i, best of three runs.
+enum { PROBE_VARIANTS = 6 };
 extern "C" int hsa_random_sector_probe_ex(int device, size_t footprint_bytes, int iters, double *gbs_out, int n_out)
 {
     if (!gbs_out || n_out < 1 || footprint_bytes < 4096 || iters < 1) return fail(HSA_E_ARG, "bad argument");
@@ -2103,14 +2130,14 @@ extern "C" int hsa_random_sector_probe_ex(int device, size_t footprint_bytes, in
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     const int block = 256;
-    struct V { const void *fn; int per_iter; } vs[PROBE_VARIANTS] = {
+    struct V { const void *fn; double per_iter; } vs[PROBE_VARIANTS] = {
         {(const void *)probe_kernel<4>, 4}, {(const void *)probe_kernel_mlp<4>, 4}, {(const void *)probe_kernel_mlp<8>, 8},
-        {(const void *)probe_kernel_mlp<16>, 16}, {(const void *)probe_kernel_mix<8>, 16}};
+        {(const void *)probe_kernel_mlp<16>, 16}, {(const void *)probe_kernel_mix<8>, 16}, {(const void *)probe_kernel_walk, 1.125}};
     for (int v = 0; v < PROBE_VARIANTS && v < n_out; ++v) {
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vs[v].fn, block, 0));
         const int grid = sms * std::max(occ, 1);
-        int it_warm = 4, it_run = iters;
+        int it_warm = 4, it_run = vs[v].per_iter < 2 ? iters * 8 : iters;      // the single-chain variant does one load per iteration
         void *aw[] = {(void *)&buf, (void *)&n_sectors, (void *)&it_warm, (void *)&sink};
         void *ar[] = {(void *)&buf, (void *)&n_sectors, (void *)&it_run, (void *)&sink};
         CU(cudaLaunchKernel(vs[v].fn, dim3(grid), dim3(block), aw, 0, nullptr));       // warm-up (pulls an L2-sized set in)
@@ -2122,7 +2149,7 @@ extern "C" int hsa_random_sector_probe_ex(int device, size_t footprint_bytes, in
             CU(cudaEventSynchronize(e1));
             float ms = 0;
             CU(cudaEventElapsedTime(&ms, e0, e1));
-            const double bytes = (double)grid * block * vs[v].per_iter * (double)iters * 32.0;
+            const double bytes = (double)grid * block * vs[v].per_iter * (double)it_run * 32.0;
             best = std::max(best, bytes / (ms * 1e-3) / 1e9);
         }
         gbs_out[v] = best;
@@ -2135,7 +2162,7 @@ extern "C" int hsa_random_sector_probe_ex(int device, size_t footprint_bytes, in
 extern "C" int hsa_random_sector_probe(int device, size_t footprint_bytes, int iters, double *gbs_out)
 {
     if (!gbs_out) return fail(HSA_E_ARG, "bad argument");
-    double v[PROBE_VARIANTS] = {0, 0, 0, 0, 0};
+    double v[PROBE_VARIANTS] = {0, 0, 0, 0, 0, 0};
     int rc = hsa_random_sector_probe_ex(device, footprint_bytes, iters, v, PROBE_VARIANTS);
     if (rc) return rc;
     *gbs_out = *std::max_element(v, v + PROBE_VARIANTS);

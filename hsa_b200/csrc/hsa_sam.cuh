@@ -54,6 +54,7 @@ struct SamParams {
     uint32_t *cigar; unsigned long long cigar_cap; unsigned long long *cigar_used;
     char *md; unsigned long long md_cap; unsigned long long *md_used;
     uint32_t *dp_list; unsigned long long *dp_count;
+    unsigned long long *dp_tasks;                                             // refinements + merges the listed reads will make
     unsigned long long *cursor; uint32_t *status;                             // status: first failure kind (0 = none)
     // DP scratch, interleaved over dp_workers workers
     uint8_t *dp_bytes; int32_t *dp_rows; uint32_t dp_workers, dp_w, dp_len1_cap, dp_len2_cap;
@@ -264,6 +265,9 @@ HSA_HD void sam_pos_item(const SamParams &P, uint32_t rid)
         bool ok;
         const uint32_t slot = sam_claim(P.dp_count, (unsigned long long)P.n_reads, 1u, ok);
         if (ok) P.dp_list[slot] = rid;
+        uint32_t tasks = r.type == TYPE_SPLICING ? 3u * r.n_multi : (r.n_gapo != 0 ? 1u : 0u);
+        if (r.type != TYPE_SPLICING) for (uint32_t j = 0; j < r.n_multi; ++j) tasks += P.multi[r.multi_off + j].gap ? 1u : 0u;
+        sam_claim(P.dp_tasks, ~0ull, tasks, ok);
     }
 }
 

@@ -114,14 +114,18 @@ extern "C" int hsa_sam_se_batch(const hsa_index_t *ix, const uint8_t *codes, con
     P.dp_list = C.list.as<uint32_t>();
     unsigned long long *cnt = C.cnt.as<unsigned long long>();        // {cigar words, md bytes, dp reads, cursor, status}
     P.cigar_used = cnt; P.md_used = cnt + 1; P.dp_count = cnt + 2; P.cursor = cnt + 3; P.status = reinterpret_cast<uint32_t *>(cnt + 4);
-    // arena sizes: a guess first; the counters run past the caps, so a second attempt is sized exactly
-    size_t cigar_cap = n_reads / 2 + 4096, md_cap = n_reads * 16 + 4096;
+    P.dp_tasks = cnt + 5;
+    // arena sizes: MD from the read count, CIGAR from the refinements the first kernel lists (12 words each); a batch that
+    // outgrows them is run again with four times the room (a read stops at its first failed claim, so the counters of a
+    // failed attempt are lower bounds, not sizes)
+    const bool tiny = env_long("HSA_B200_SAM_TINY", 0) != 0;          // tests: start with arenas that are certainly too small
+    size_t cigar_cap = tiny ? 16 : 4096, md_cap = tiny ? 64 : n_reads * 16 + 4096;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    unsigned long long h[5] = {0, 0, 0, 0, 0};
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        if (C.cigar.alloc(cigar_cap * 4) || C.md.alloc(md_cap)) return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
-        P.cigar = C.cigar.as<uint32_t>(); P.cigar_cap = cigar_cap; P.md = C.md.as<char>(); P.md_cap = md_cap;
+    unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        if (C.md.alloc(md_cap)) return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
+        P.cigar = nullptr; P.cigar_cap = 0; P.md = C.md.as<char>(); P.md_cap = md_cap;
         CU(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), s));
         CU(cudaMemcpyAsync(C.rec.p, res->rec, n_reads * sizeof(SamRec), cudaMemcpyHostToDevice, s));
         if (n_multi) CU(cudaMemcpyAsync(C.multi.p, res->multi, n_multi * sizeof(SamMulti), cudaMemcpyHostToDevice, s));
@@ -132,6 +136,9 @@ extern "C" int hsa_sam_se_batch(const hsa_index_t *ix, const uint8_t *codes, con
         CU(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         const uint32_t n_dp = (uint32_t)h[2];
+        if (!tiny) cigar_cap = std::max<size_t>(cigar_cap, (size_t)h[5] * 12 + 4096);
+        if (C.cigar.alloc(cigar_cap * 4)) return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
+        P.cigar = C.cigar.as<uint32_t>(); P.cigar_cap = cigar_cap;
         if (n_dp) {
             // scratch: (len2 + 1) rows of W trace-back bytes + len1 reference bases + 3 x (len1 + 1) score words per worker
             const uint32_t len1_cap = max_len + max_ext, len2_cap = max_len;
@@ -151,8 +158,9 @@ extern "C" int hsa_sam_se_batch(const hsa_index_t *ix, const uint8_t *codes, con
         const uint32_t status = (uint32_t)(h[4] & 0xFFFFFFFFull);
         if (status == SAM_SCRATCH) return fail(HSA_E_CAPACITY, "an alignment exceeded the DP scratch (gap count beyond the batch's maximum)");
         if (h[0] <= cigar_cap && h[1] <= md_cap && status == SAM_OK) break;
-        if (attempt == 2) return fail(HSA_E_CAPACITY, "CIGAR / MD arenas overflowed twice");
-        cigar_cap = std::max<size_t>(cigar_cap, (size_t)h[0] + 64); md_cap = std::max<size_t>(md_cap, (size_t)h[1] + 64);
+        if (attempt == 5) return fail(HSA_E_CAPACITY, "CIGAR / MD arenas overflowed repeatedly");
+        if (h[0] > cigar_cap || status == SAM_CIGAR_FULL) cigar_cap = std::max<size_t>(4 * cigar_cap, 2 * (size_t)h[0]);
+        if (h[1] > md_cap || status == SAM_MD_FULL) md_cap = std::max<size_t>(4 * md_cap, 2 * (size_t)h[1]);
     }
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e0, e1));

@@ -317,11 +317,12 @@ int  hsa_sam_format(const hsa_sam_result_t *res, size_t first, size_t count, con
                     const hsa_gap_opt_t *opt, char **text_out, size_t *bytes_out);
 
 /* ---- roofline probe: random 32-byte-sector loads over `footprint_bytes` ----
- * The random-access denominator on this GPU: achieved GB/s (sectors * 32 B / time) at full occupancy of five access
+ * The random-access denominator on this GPU: achieved GB/s (sectors * 32 B / time) at full occupancy of six access
  * shapes -- [0] four dependent chains per thread with two 16-byte loads per sector, [1..3] 4 / 8 / 16 independent 256-bit
  * loads in flight per thread (the kernels' own load shape, multiply-shift sector choice), [4] the SA kernel's mix (a
- * 256-bit load plus a 4-byte load from another sector).  hsa_random_sector_probe returns the best of them, _ex all of
- * them (gbs_out[0..min(n_out,5))).  Used only by bench.py / tools/ to establish the roofline. */
+ * 256-bit load plus a 4-byte load from another sector), [5] the LF-walk shape (one data-dependent chain per thread of geometric
+ * length, ended by a 4-byte load from a second array; 9/8 sectors per step).  hsa_random_sector_probe returns the best of them,
+ * _ex all of them (gbs_out[0..min(n_out,6))).  Used only by bench.py / tools/ to establish the roofline. */
 int  hsa_random_sector_probe(int device, size_t footprint_bytes, int iters, double *gbs_out);
 int  hsa_random_sector_probe_ex(int device, size_t footprint_bytes, int iters, double *gbs_out, int n_out);
 

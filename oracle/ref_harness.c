@@ -42,12 +42,16 @@ void hsa_gpu_close(void);
 void hsa_gpu_sa_values(const Idx2BWT *bi, const unsigned int *sa_index, size_t n, unsigned int *occ_pos);
 void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bwt, int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt, bwt_array_t *arr);
 bwt_aln1_t *bwt_match_gap_gpu(bwt_aux_t *aux, int *_n_aln);
+void generate_sam_se_core_gpu(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_opt_t *opt, int n_occ);
 #endif
 typedef bwt_aln1_t *(*match_fn)(bwt_aux_t *, int *);
 static match_fn g_match = bwt_match_gap;            /* gpupercall: shim/hsa_gpu_shim.c's bwt_match_gap_gpu */
 static unsigned long long g_call_mismatch = 0, g_width_mismatch = 0;
 typedef void (*driver_fn)(int, const Idx2BWT *, int, bwa_seq_t *, const gap_opt_t *, bwt_array_t *);
 static driver_fn g_driver = bwa_cal_sa_reg_gap;
+void generate_sam_se_core(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_opt_t *opt, int n_occ);
+typedef void (*sam_fn)(Idx2BWT *, int, bwa_seq_t *, gap_opt_t *, int);
+static sam_fn g_sam = generate_sam_se_core;            /* gpusam: shim/hsa_gpu_shim.c's generate_sam_se_core_gpu */
 
 #ifdef HSA_COUNT_OCC
 static unsigned long long g_occ4 = 0, g_occ1 = 0;
@@ -804,7 +808,7 @@ static int mode_sam(int argc, char **argv)
         g_driver(0, bi, n, seqs, opt, arr);
         secs_search += now_s() - t0;
         t0 = now_s();
-        generate_sam_se_core(bi, n, seqs, opt, n_occ);
+        g_sam(bi, n, seqs, opt, n_occ);
         secs_sam += now_s() - t0;
         for (k = 0; k < (uint32_t)n; ++k) {
             bwa_seq_t *p = seqs + k;
@@ -851,6 +855,17 @@ int main(int argc, char **argv)
     }
 #endif
 #ifdef HSA_WITH_GPU_SHIM
+    if (strcmp(argv[1], "gpusam") == 0) {
+        /* the stock batch loop with BOTH stages from the shim: bwa_cal_sa_reg_gap_gpu and generate_sam_se_core_gpu */
+        Idx2BWT *bi; int rc;
+        if (argc < 6) die("usage: gpusam <prefix> <reads> <out.bin> <out.sam> [opts] [batch=N] [nocc=K]");
+        bi = load_index(argv[2]);
+        if (hsa_gpu_open(bi, 0)) return 1;
+        g_driver = bwa_cal_sa_reg_gap_gpu; g_sam = generate_sam_se_core_gpu;
+        rc = mode_sam(argc, argv);
+        hsa_gpu_close();
+        return rc;
+    }
     if (strcmp(argv[1], "gpupercall") == 0) {
         /* percall with every bwt_match_gap call ALSO made through the per-call GPU symbol (bwt_match_gap_gpu) on the
          * same bwt_aux_t frame; the dump holds the GPU results, the JSON line counts calls whose hits or rewritten

@@ -6,8 +6,11 @@
  *     bwa_cal_sa_reg_gap_gpu()  -- same signature and same observable results as bwa_cal_sa_reg_gap
  *                                  (bwtaln.c:246-417), with the whole-read searches done on the GPU.
  *     hsa_gpu_sa_values()       -- BWTSaValue (BWT.c:1195) for a batch of SA indices.
- * Everything after the search -- bwt_splice_match for the reads that found nothing (bwtgap.c:748), SAM output --
- * stays the reference's host code and consumes the bwt_aln1_t arrays (and positions) unchanged.
+ *     generate_sam_se_core_gpu() -- same signature and same printed SAM as generate_sam_se_core (bwtse.c:884-931): hit
+ *                                  selection, positions, gapped refinement (CIGAR) and MD / NM come from hsa_sam_se_batch;
+ *                                  the lines are printed by the reference's own bwa_print_sam1.
+ * bwt_splice_match for the reads that found nothing (bwtgap.c:748) runs on the GPU when the full index is loaded
+ * (HSA_GPU_SPLICE=0 keeps it on the host).
  *
  * It is compiled only where the reference tree exists (oracle/Makefile target `shim`, outputs under oracle/_ref/)
  * and is exercised by tests/test_gpu_shim.py, which compares its per-read output with the stock driver's.
@@ -26,6 +29,7 @@
 #include "bwtaln.h"
 #include "bwtgap.h"
 #include "BWT.h"
+#include "bwtse.h"
 #include "hsa_b200.h"
 
 static hsa_index_t *g_idx = NULL;
@@ -273,4 +277,69 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
     free(aux->width_seed); free(aux->width_fore); free(aux->width_back); free(aux->rc_seq);
     gap_destroy_stack(aux->stack);
     free(aux);
+}
+
+
+/* same signature as generate_sam_se_core (bwtse.h:27; bwtse.c:884-931).  The fields it leaves in every bwa_seq_t come from
+ * hsa_sam_se_batch; the printing loop (:922-926) is the reference's own bwa_print_sam1.  The reference draws its random
+ * numbers from the process-wide drand48 stream and nothing else in HSA uses that stream, so the shim carries the stream's
+ * 48-bit state itself (0 = a process that has not drawn yet). */
+static uint64_t g_rng48 = 0;
+static hsa_sam_result_t g_sam;
+void bwa_print_sam1(const HSP *hsp, bwa_seq_t *p, const bwa_seq_t *mate, int mode, int max_top2);
+
+static bwa_cigar_t *cigar_copy(const hsa_sam_result_t *r, uint32_t off, uint32_t n)
+{
+    bwa_cigar_t *c = (bwa_cigar_t *)malloc(sizeof(bwa_cigar_t) * (n ? n : 1));
+    memcpy(c, r->cigar + off, sizeof(bwa_cigar_t) * n);
+    return c;
+}
+
+void generate_sam_se_core_gpu(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_opt_t *opt, int n_occ)
+{
+    uint8_t *codes; uint64_t *off, *aoff, total = 0, hits = 0; uint32_t *len; int32_t *n_aln; hsa_aln1_t *aln;
+    int i; uint32_t j;
+    if (!g_splice_gpu) { fprintf(stderr, "[hsa_gpu] the SAM stage needs the full index (SA samples, annotation, packed text)\n"); exit(1); }
+    for (i = 0; i < n_seqs; ++i) { total += seqs[i].len; hits += (uint64_t)(seqs[i].n_aln > 0 ? seqs[i].n_aln : 0); }
+    codes = (uint8_t *)malloc(total + 16); off = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1));
+    aoff = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1)); len = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1));
+    n_aln = (int32_t *)malloc(sizeof(int32_t) * (n_seqs + 1)); aln = (hsa_aln1_t *)malloc(sizeof(hsa_aln1_t) * (hits + 1));
+    total = hits = 0;
+    for (i = 0; i < n_seqs; ++i) {
+        const bwa_seq_t *p = seqs + i;
+        off[i] = total; len[i] = p->len; memcpy(codes + total, p->seq, p->len); total += p->len;
+        n_aln[i] = p->n_aln > 0 ? p->n_aln : 0; aoff[i] = hits;
+        if (n_aln[i]) { memcpy(aln + hits, p->aln, sizeof(bwt_aln1_t) * (size_t)n_aln[i]); hits += (uint64_t)n_aln[i]; }
+    }
+    if (hsa_sam_se_batch(g_idx, codes, off, len, (size_t)n_seqs, n_aln, aoff, aln, (const hsa_gap_opt_t *)opt, n_occ, &g_rng48, &g_sam)) die_gpu();
+    for (i = 0; i < n_seqs; ++i) {
+        bwa_seq_t *p = seqs + i; const hsa_sam1_t *r = g_sam.rec + i;
+        p->type = r->type;
+        if (p->multi) { free(p->multi); p->multi = NULL; }
+        p->n_multi = 0;
+        if (r->type == BWA_TYPE_NO_MATCH) { if (p->n_aln == 0) p->c1 = p->c2 = 0; continue; }
+        p->strand = r->strand; p->n_mm = r->n_mm; p->n_gapo = r->n_gapo; p->n_gape = r->n_gape; p->score = r->score;
+        p->mapQ = p->seQ = r->mapQ; p->sa = r->sa; p->seq_id = r->seq_id; p->ori_pos = r->ori_pos; p->occ_pos = r->occ_pos;
+        p->c1 = r->c1; p->c2 = r->c2; p->start = r->start; p->end = r->end;
+        if (r->n_cigar) { p->n_cigar = (int)r->n_cigar; p->cigar = cigar_copy(&g_sam, r->cigar_off, r->n_cigar); }
+        p->nm = r->nm;
+        if (r->type != BWA_TYPE_SPLICING) {                    /* bwa_cal_md1 returns strdup(str->s) (bwtse.c:493) */
+            p->md = (char *)malloc(r->md_len + 1); memcpy(p->md, g_sam.md + r->md_off, r->md_len); p->md[r->md_len] = 0;
+        }
+        if (r->n_multi) {
+            p->n_multi = (int)r->n_multi;
+            p->multi = (bwt_multi1_t *)calloc(r->n_multi, sizeof(bwt_multi1_t));
+            for (j = 0; j < r->n_multi; ++j) {
+                const hsa_multi1_t *q = g_sam.multi + r->multi_off + j; bwt_multi1_t *m = p->multi + j;
+                m->gap = q->gap; m->mm = q->mm; m->strand = q->strand; m->sa = q->sa; m->ori_pos = q->ori_pos; m->occ_pos = q->occ_pos;
+                m->seq_id = q->seq_id; m->aln_id = q->aln_id; m->start = q->start; m->end = q->end;
+                if (q->n_cigar) { m->n_cigar = q->n_cigar; m->cigar = cigar_copy(&g_sam, q->cigar_off, q->n_cigar); }
+            }
+        }
+    }
+    for (i = 0; i < n_seqs; ++i) {                             /* bwtse.c:922-926 */
+        if ((seqs + i)->type == BWA_TYPE_NO_MATCH) continue;
+        bwa_print_sam1(bi_bwt->hsp, seqs + i, 0, opt->mode, opt->max_top2);
+    }
+    free(codes); free(off); free(aoff); free(len); free(n_aln); free(aln);
 }

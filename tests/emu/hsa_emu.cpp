@@ -367,10 +367,10 @@ int emu_sam(void *p, const uint32_t *sa_value, uint32_t sa_interval, const uint3
     P.codes = codes; P.read_off = off; P.read_len = len; P.n_reads = (uint32_t)n;
     P.n_aln = n_aln; P.aln_off = aln_off; P.aln = aln; P.rec = rec_out; P.multi = multi_out;
     P.maxdiff_by_len = maxdiff_by_len; P.max_mm = max_mm; P.max_len = max_len;
-    unsigned long long cnt[5] = {0, 0, 0, 0, 0}; uint32_t status = 0;
+    unsigned long long cnt[6] = {0, 0, 0, 0, 0, 0}; uint32_t status = 0;
     std::vector<uint32_t> list(n + 1);
     P.cigar = cigar_out; P.cigar_cap = cigar_cap; P.cigar_used = cnt; P.md = md_out; P.md_cap = md_cap; P.md_used = cnt + 1;
-    P.dp_list = list.data(); P.dp_count = cnt + 2; P.cursor = cnt + 3; P.status = &status;
+    P.dp_list = list.data(); P.dp_count = cnt + 2; P.cursor = cnt + 3; P.status = &status; P.dp_tasks = cnt + 5;
     for (size_t i = 0; i < n; ++i) sam_pos_item(P, (uint32_t)i);
     const uint32_t len1_cap = max_len + max_ext, len2_cap = max_len, W = std::min<uint32_t>(2u * DP_BAND + max_ext + 1u, len1_cap + 1u);
     std::vector<uint8_t> bytes((size_t)(len2_cap + 1u) * W + len1_cap + 1u);

@@ -56,43 +56,78 @@ def test_sam_fields_and_text_vs_golden(gs, index, name):
     assert hashlib.sha256(sc.printable_lines(text)).hexdigest() == c["text_sha256"]
 
 
-@pytest.mark.parametrize("name", ["dna_and_junctions", "dna_150_n5o2"])
-def test_search_then_sam_end_to_end(gs, index, name):
-    """hits straight from the GPU search (whole reads, then the splice fallback for the reads that found nothing)."""
-    c, rs, n_aln_ref, rows_ref, want = gs.case(name)
-    opt = _opt(c["opt"])
+def _driver_on_gpu(index, rs, okw):
+    """bwa_cal_sa_reg_gap's results for one batch from the GPU entry points, option leak included -- the logic of
+    shim/hsa_gpu_shim.c in Python: whole-read pass A with the caller's options (GAPE cleared, bwtaln.c:261); from the first
+    read that falls through to the splice path on, aux->opt is local_opt (copied BEFORE the clear, :254, with max_diff of the
+    longest read and max_gapo clamped, :273-276), so the reads after it are searched again with that (pass B); reads without
+    a hit go through bwt_splice_match with local_opt as it stands for them."""
+    opt = api.gap_init_opt(**okw)
     off = rs.offsets[:-1].astype(np.uint64)
-    res = index.whole_reads(rs.codes, off, rs.lens, opt)
-    n_aln = res.n_aln.copy()
-    rows = [el.aln9_to_rows12(res.item(i)) for i in range(rs.n)]
-    miss = np.flatnonzero(n_aln == 0)
-    # bwa_cal_sa_reg_gap skips reads with too many N / poly-A/T before it would reach the splice fallback (bwtaln.c:314-325)
-    fmax = api.bwa_cal_maxdiff(int(rs.lens.max()), 0.02, opt.fnr) if opt.fnr > 0 else opt.max_diff
-    keep = []
-    for i in miss.tolist():
+    max_len = int(rs.lens.max())
+    local = api.GapOpt.from_buffer_copy(bytes(opt))
+    if opt.fnr > 0:
+        local.max_diff = api.bwa_cal_maxdiff(max_len, 0.02, opt.fnr)
+    if local.max_diff < local.max_gapo:
+        local.max_gapo = local.max_diff
+
+    def filtered(i):
         r = rs.read(i)
-        if int((r > 3).sum()) > fmax or not r[:15].any() or bool((r[:15] == 3).all()):
-            continue
-        keep.append(i)
-    if keep:
-        sub = synth.ReadSet(rs.lens[keep], np.concatenate([rs.read(i) for i in keep]))
-        lens = sorted(set(sub.lens.tolist()))
-        base = ol.default_opt(**c["opt"])
-        opts = [api.GapOpt.from_buffer_copy(bytes(el.resolve_read_opt(base, L, 1))) for L in lens]
-        for o in opts:                                      # local_opt as the driver holds it (bwtaln.c:273-276)
-            if o.max_diff < o.max_gapo:
-                o.max_gapo = o.max_diff
-        oi = np.asarray([lens.index(int(x)) for x in sub.lens], dtype=np.uint32)
-        sn, sa = index.splice_match(sub.codes, sub.offsets[:-1].astype(np.uint64), sub.lens, opts, oi)
-        for j, i in enumerate(keep):
+        return int((r > 3).sum()) > local.max_diff or not r[:15].any() or bool((r[:15] == 3).all())
+
+    a = index.whole_reads(rs.codes, off, rs.lens, opt)
+    n_aln = a.n_aln.copy()
+    rows = [el.aln9_to_rows12(a.item(i)) for i in range(rs.n)]
+    first = next((i for i in range(rs.n) if n_aln[i] == 0 and not filtered(i)), None)
+    if first is not None and first + 1 < rs.n:
+        sub = rs.subset(first + 1, rs.n)
+        b = index.whole_reads(sub.codes, sub.offsets[:-1].astype(np.uint64), sub.lens, local, keep_gape=local.mode & 1)
+        for j in range(sub.n):
+            n_aln[first + 1 + j] = b.n_aln[j]
+            rows[first + 1 + j] = el.aln9_to_rows12(b.item(j))
+    miss = [i for i in range(rs.n) if n_aln[i] == 0 and not filtered(i)]
+    if miss:
+        sub = synth.ReadSet(rs.lens[miss], np.concatenate([rs.read(i) for i in miss]))
+        opts, oi = [], []
+        for i in miss:
+            o = api.GapOpt.from_buffer_copy(bytes(local))
+            if i != first:                                  # written through aux->opt == &local_opt (bwtaln.c:330-332)
+                L = int(rs.lens[i])
+                if opt.fnr > 0:
+                    o.max_diff = api.bwa_cal_maxdiff(L, 0.02, opt.fnr)
+                o.seed_len = opt.seed_len if opt.seed_len < L else 0x7FFFFFFF
+            key = bytes(o)
+            if key not in [bytes(x) for x in opts]:
+                opts.append(o)
+            oi.append([bytes(x) for x in opts].index(key))
+        sn, sa = index.splice_match(sub.codes, sub.offsets[:-1].astype(np.uint64), sub.lens, opts, np.asarray(oi, dtype=np.uint32))
+        for j, i in enumerate(miss):
             n_aln[i] = sn[j]
             rows[i] = el.aln9_to_rows12(sa[j, :sn[j]])
-    rows = np.concatenate(rows) if rows else np.zeros((0, 12), np.uint32)
+    return n_aln, (np.concatenate(rows) if rows else np.zeros((0, 12), np.uint32))
+
+
+@pytest.mark.parametrize("name", ["dna_and_junctions", "dna_150_n5o2"])
+def test_search_then_sam_end_to_end(gs, index, name):
+    """hits straight from the GPU search (whole reads, then the splice fallback for the reads that found nothing), then
+    the SAM stage on them: equal to what the reference program computes from the reads alone."""
+    c, rs, n_aln_ref, rows_ref, want = gs.case(name)
+    n_aln, rows = _driver_on_gpu(index, rs, c["opt"])
     assert np.array_equal(n_aln, n_aln_ref) and np.array_equal(rows, rows_ref), "the GPU search's hits differ from the driver's"
     na, ao, a9 = sc.hits_input(n_aln, rows)
-    out = index.sam_se(rs.codes, off, rs.lens, na, ao, a9, opt, n_occ=c["n_occ"])
+    out = index.sam_se(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, na, ao, a9, _opt(c["opt"]), n_occ=c["n_occ"])
     bad = sc.diff(sc.unpack_result(out.rec, out.multi, out.cigar, out.md), want)
     assert not bad, "\n".join(bad)
+
+
+def test_arena_overflow_is_retried_not_truncated(gs, index, monkeypatch):
+    """CIGAR / MD arenas that start far too small (HSA_B200_SAM_TINY): the batch is run again with more room until it fits;
+    results are the same."""
+    monkeypatch.setenv("HSA_B200_SAM_TINY", "1")
+    c, rs, n_aln, rows, want = gs.case("dna_and_junctions")
+    na, off, a9 = sc.hits_input(n_aln, rows)
+    res = index.sam_se(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, na, off, a9, _opt(c["opt"]), n_occ=c["n_occ"])
+    assert not sc.diff(sc.unpack_result(res.rec, res.multi, res.cigar, res.md), want)
 
 
 def test_rng_state_chains_batches(gs, index):
@@ -115,7 +150,7 @@ def test_sam_46mb_vs_reference_binary():
     the product wrote, against hsa_sam_se_batch fed with the reference driver's hits; SAM text compared line by line."""
     from test_gpu_scale import Scale, need_ref
     need_ref()
-    s = Scale(46_000_003, 5, full=True, n_introns=4000)
+    s = Scale(46_000_003, 5, full=True, n_introns=2000)
     try:
         reads = torch.cat([synth_torch.simulate_reads(s.genome, 100_000, 100, 91, indel_frac=0.20),
                            synth_torch.simulate_junction_reads(s.genome, s.introns, 20_000, 100, 92, sub_rate=0.01)])
