@@ -373,10 +373,24 @@ def dropin_block(dev, args):
         j1 = run([ref, "driver", os.path.join(td, "g"), os.path.join(td, "r1.reads"), "x", "nout=1", "procs=1"])
         jp = run([ref, "driver", os.path.join(td, "g"), os.path.join(td, "r.reads"), "x", "nout=1", f"procs={procs}"])
         jg = run([ref_gpu, "gpudriver", os.path.join(td, "g"), os.path.join(td, "r.reads"), "x", "nout=1"])
+        jg1m = run([ref_gpu, "gpudriver", os.path.join(td, "g"), os.path.join(td, "r.reads"), "x", "nout=1", "batch=1000000"])
+        # the stage after the search (generate_sam_se_core, bwtse.c:884: selection, positions, CIGAR, MD, printing to a file)
+        n2 = 300_000
+        synth.write_reads_bin(os.path.join(td, "r2.reads"), rs.subset(0, n2))
+        js = run([ref, "sam", os.path.join(td, "g"), os.path.join(td, "r2.reads"), os.path.join(td, "c.bin"), os.path.join(td, "c.sam")])
+        jsg = run([ref_gpu, "gpusam", os.path.join(td, "g"), os.path.join(td, "r2.reads"), os.path.join(td, "d.bin"), os.path.join(td, "d.sam")])
+        with open(os.path.join(td, "c.bin"), "rb") as fa, open(os.path.join(td, "d.bin"), "rb") as fb:
+            sam_identical = fa.read() == fb.read()
     return {"workload": f"{G} bp genome with planted introns, {n} x {L} bp reads, 1 % of them across introns (splice fallback), default "
                         f"options, the reference's 100 000-read batches; index files written by the product, loaded by the reference",
             "value": n / jg["secs"], "unit": UNIT, "aligned_any": jg["aligned_any"],
             "path": "oracle/_ref/hsa_ref_gpu gpudriver: the unmodified reference program with bwa_cal_sa_reg_gap_gpu (shim/hsa_gpu_shim.c)",
+            "with_1M_read_batches": {"value": n / jg1m["secs"], "aligned_any": jg1m["aligned_any"],
+                                     "note": "the same program with the batch constant of bwtaln.c:477 raised from 100 000 to 1 000 000"},
+            "sam_stage": {"reads": n2, "gpu_reads_per_s": n2 / jsg["secs_sam"], "reference_single_thread_reads_per_s": n2 / js["secs_sam"],
+                          "fields_identical": sam_identical,
+                          "path": "generate_sam_se_core_gpu (hsa_sam_se_batch + the reference's bwa_print_sam1 writing to a file) vs "
+                                  "generate_sam_se_core, inside the reference's batch loop"},
             "stock_driver_all_cores": {"value": n / jp["secs"], "cores": procs, "aligned_any": jp["aligned_any"]},
             "stock_driver_single_thread": {"value": n1 / j1["secs"], "sample": f"{n1} reads (the reference as it ships)"}}
 

@@ -73,6 +73,12 @@ class _SamResult(C.Structure):        # == hsa_sam_result_t
                 ("cap_rec", C.c_size_t), ("cap_multi", C.c_size_t), ("cap_cigar", C.c_size_t), ("cap_md", C.c_size_t)]
 
 
+class _SamDevice(C.Structure):        # == hsa_sam_device_t
+    _fields_ = [("rec_dev", C.c_void_p), ("multi_dev", C.c_void_p), ("cigar_dev", C.c_void_p), ("md_dev", C.c_void_p),
+                ("n_multi", C.c_size_t), ("n_cigar", C.c_size_t), ("md_bytes", C.c_size_t),
+                ("n_refined", C.c_uint64), ("n_several_best", C.c_uint64), ("kernel_ms", C.c_float)]
+
+
 SAM_REC_WORDS, SAM_MULTI_WORDS = 22, 12      # hsa_sam1_t / hsa_multi1_t in 32-bit words
 
 
@@ -147,6 +153,8 @@ def lib():
     L.hsa_sam_se_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(GapOpt), C.c_int, C.POINTER(C.c_uint64), C.POINTER(_SamResult)]
     L.hsa_sam_result_free.argtypes = [C.POINTER(_SamResult)]
+    L.hsa_sam_se_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(GapOpt), C.c_int, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(_SamDevice)]
     L.hsa_sam_format.argtypes = [C.POINTER(_SamResult), C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.POINTER(C.c_char_p), C.c_size_t, C.POINTER(GapOpt), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.hsa_match_gap_call.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(GapOpt),
@@ -337,7 +345,8 @@ class Index:
         self.last_splice_lookups = int(lk.value)
         return n_aln, aln
 
-    def sam_se(self, codes, off, lens, n_aln, aln_off, aln9, opt: GapOpt, n_occ: int = 3, rng48_state: int = 0) -> "SamResult":
+    def sam_se(self, codes, off, lens, n_aln, aln_off, aln9, opt: GapOpt, n_occ: int = 3, rng48_state: int = 0,
+               copy: bool = True, into: "SamResult | None" = None) -> "SamResult":
         """What generate_sam_se_core (bwtse.c:884) computes for a batch before printing: hit selection (host, the reference's
         drand48 stream from `rng48_state`), then on the GPU positions, pairing of spliced parts, banded DP -> CIGAR, MD / NM.
         n_aln / aln_off / aln9 = the reads' hits as hsa_whole_reads (+ hsa_splice_match_batch) leave them."""
@@ -346,13 +355,25 @@ class Index:
         ao = np.ascontiguousarray(aln_off, dtype=np.uint64)
         a9 = np.ascontiguousarray(aln9, dtype=np.uint32)
         res = _SamResult()
+        if into is not None and into._r is not None:       # re-use the library-managed host arrays of an earlier result
+            res, into._r = into._r, None
         st = C.c_uint64(rng48_state)
         rc = lib().hsa_sam_se_batch(self._h, cp[0], op[0], lp[0], n, na.ctypes.data, ao.ctypes.data, a9.ctypes.data, C.byref(opt),
                                     n_occ, C.byref(st), C.byref(res))
         if rc:
             lib().hsa_sam_result_free(C.byref(res))
             _check(rc)
-        return SamResult(res, st.value, (cp[1], op[1], lp[1]), opt)
+        return SamResult(res, st.value, (cp[1], op[1], lp[1]), opt, copy)
+
+    def sam_se_device(self, codes_ptr: int, off_ptr: int, len_ptr: int, n_reads: int, max_len: int, n_aln_ptr: int, aln_off_ptr: int,
+                      aln_ptr: int, opt: GapOpt, n_occ: int = 3, rng48_state: int = 0, stream_ptr: int = 0):
+        """hsa_sam_se_device: reads and hits resident in HBM (raw device pointers), results left on the device.  Returns
+        (_SamDevice with the result pointers / counts, new rng48 state)."""
+        out = _SamDevice()
+        st = C.c_uint64(rng48_state)
+        _check(lib().hsa_sam_se_device(self._h, codes_ptr, off_ptr, len_ptr, n_reads, max_len, n_aln_ptr, aln_off_ptr, aln_ptr, C.byref(opt),
+                                       n_occ, C.byref(st), stream_ptr, C.byref(out)))
+        return out, st.value
 
     def sa_values_device(self, idx_ptr: int, n: int, out_ptr: int, steps_ptr: int = 0, stream_ptr: int = 0) -> None:
         _check(lib().hsa_sa_values_device(self._h, idx_ptr, n, out_ptr, steps_ptr, stream_ptr))
@@ -448,14 +469,17 @@ class SamResult:
     """hsa_sam_result_t: rec[n, 22] (hsa_sam1_t words), multi[m, 12], cigar[...] (bwa_cigar_t), md bytes; format() = the SAM
     text of bwa_print_sam1 for the batch."""
 
-    def __init__(self, r: _SamResult, rng48_state: int, reads, opt: GapOpt):
+    def __init__(self, r: _SamResult, rng48_state: int, reads, opt: GapOpt, copy: bool = True):
+        """copy=False: rec / multi / cigar are views of the library's arrays (valid until close()); md stays in the library."""
         self._r, self.rng48_state, self._reads, self._opt = r, rng48_state, reads, opt
         n = r.n_reads
-        self.rec = np.ctypeslib.as_array(C.cast(r.rec, C.POINTER(C.c_uint32)), shape=(n, SAM_REC_WORDS)).copy() if n else np.zeros((0, SAM_REC_WORDS), np.uint32)
-        self.multi = (np.ctypeslib.as_array(C.cast(r.multi, C.POINTER(C.c_uint32)), shape=(r.n_multi, SAM_MULTI_WORDS)).copy()
+        own = (lambda a: a.copy()) if copy else (lambda a: a)
+        self.rec = own(np.ctypeslib.as_array(C.cast(r.rec, C.POINTER(C.c_uint32)), shape=(n, SAM_REC_WORDS))) if n else np.zeros((0, SAM_REC_WORDS), np.uint32)
+        self.multi = (own(np.ctypeslib.as_array(C.cast(r.multi, C.POINTER(C.c_uint32)), shape=(r.n_multi, SAM_MULTI_WORDS)))
                       if r.n_multi else np.zeros((0, SAM_MULTI_WORDS), np.uint32))
-        self.cigar = np.ctypeslib.as_array(C.cast(r.cigar, C.POINTER(C.c_uint32)), shape=(r.n_cigar,)).copy() if r.n_cigar else np.zeros(0, np.uint32)
-        self.md = C.string_at(r.md, r.md_bytes) if r.md_bytes else b""
+        self.cigar = own(np.ctypeslib.as_array(C.cast(r.cigar, C.POINTER(C.c_uint32)), shape=(r.n_cigar,))) if r.n_cigar else np.zeros(0, np.uint32)
+        self.md = (C.string_at(r.md, r.md_bytes) if r.md_bytes else b"") if copy else None
+        self.md_bytes = int(r.md_bytes)
         self.n_refined, self.kernel_ms = int(r.n_refined), float(r.kernel_ms)
 
     def format(self, chr_names, first: int = 0, count: int | None = None, names=None) -> bytes:

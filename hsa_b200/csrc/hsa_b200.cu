@@ -10,10 +10,12 @@
 //
 // There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <chrono>
 #include <string>
 #include <vector>
 #include <algorithm>

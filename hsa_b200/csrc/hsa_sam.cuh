@@ -493,75 +493,233 @@ HSA_HD void sam_dp_item(const SamParams &P, uint32_t rid, uint32_t worker)
 }
 
 
-// ---- host: hit selection (generate_sam_se_core's first loop, bwtse.c:898-910, and bwt_aln2seq_core, :21-113) ------------
-// The reference draws from the process-wide drand48 stream, read after read: how many numbers a read consumes depends on
-// the numbers themselves, so the stream is a sequential chain over the batch and stays on the host (a few ns per read).
-// drand48 (POSIX): X' = (0x5DEECE66D X + 0xB) mod 2^48, value X' / 2^48; glibc starts an unseeded stream at X = 0.
+// ---- hit selection (generate_sam_se_core's first loop, bwtse.c:898-910, and bwt_aln2seq_core, :21-113) -------------------
+// The reference draws from the process-wide drand48 stream, read after read, and how many numbers a read consumes depends
+// on the numbers drawn.  drand48 (POSIX): X' = (0x5DEECE66D X + 0xB) mod 2^48, value X' / 2^48; glibc starts an unseeded
+// stream at X = 0.
+//
+// sam_select is the sequential statement (one read after the other).  The GPU path cuts the chain where it can be cut:
+//   * a read whose best score is held by ONE hit draws exactly twice (the take test of the first hit is r * w > 0, which only
+//     r = 0 fails) -- its position in the stream follows from a prefix sum, and an LCG can jump: X_n = A^n X + C (A^n - 1) / (A - 1);
+//   * reads with no hit or a spliced pair draw nothing;
+//   * only reads with SEVERAL best-score hits consume a data-dependent number of draws.  They are compacted into a list of
+//     32-byte descriptors and ONE thread walks that list (sel_chain), jumping over the fixed draws in between;
+//   * every other read then jumps straight to its own position (sel_finish).
+// A read that breaks the assumption (r = 0 on a first draw: probability 2^-48; the unreachable sampling branch of
+// bwtse.c:93-107) raises a flag and the batch is selected again by sam_select on one device thread -- exact either way.
 struct Rng48 {
     uint64_t x;
-    double next() { x = (x * 0x5DEECE66Dull + 0xBull) & 0xFFFFFFFFFFFFull; return (double)x * (1.0 / 281474976710656.0); }
+    HSA_HD double next() { x = (x * 0x5DEECE66Dull + 0xBull) & 0xFFFFFFFFFFFFull; return (double)x * (1.0 / 281474976710656.0); }
+    HSA_HD void jump(uint64_t n)                  // n draws ahead, O(log n)
+    {
+        uint64_t ca = 0x5DEECE66Dull, cc = 0xBull, aa = 1, ac = 0;
+        while (n) {
+            if (n & 1ull) { aa = aa * ca; ac = ac * ca + cc; }
+            cc = (ca + 1ull) * cc; ca = ca * ca;
+            n >>= 1;
+        }
+        x = (aa * x + ac) & 0xFFFFFFFFFFFFull;
+    }
 };
 
+enum : uint32_t { SEL_NONE = 0u, SEL_SPLICE = 1u, SEL_SINGLE = 2u, SEL_SEVERAL = 3u };
+enum : uint32_t { SEL_DESC_W = 5u };
+struct SelDesc { uint32_t read, m, fixed_before, w[SEL_DESC_W]; };       // a read with m >= 2 best-score hits; widths of the first five
+struct SelPick { uint32_t j; uint32_t taken; double r2; };               // the hit taken last and the draw that places sa inside it
+
 // hit words: {n_mm | n_gapo << 16 | n_gape << 24, k, l, rev_k, rev_l, type | strand << 30, start, end, score}
-// Fills rec (zero-initialised by the caller) and appends the read's alternative hits to multi[*n_multi_used ...]; returns
-// the number of multi slots the read owns (spliced hits: room for every position bwt_aln2pos_splicing will look up).
-inline uint32_t sam_select(const uint32_t *aln, int32_t n_aln, int32_t n_occ, Rng48 &rng, SamRec &s, SamMulti *multi)
+HSA_HD uint32_t sel_kind(const uint32_t *aln, int32_t n_aln, uint32_t &m)
 {
-    if (n_aln == 2 && (aln[5] & 0x3FFFFFFFu) == TYPE_SPLICING) {                   // bwtse.c:901-904
-        s.type = TYPE_SPLICING;
+    m = 0;
+    if (n_aln == 2 && (aln[5] & 0x3FFFFFFFu) == TYPE_SPLICING) return SEL_SPLICE;                // bwtse.c:901-904
+    if (n_aln == 0) return SEL_NONE;
+    const int32_t best = (int32_t)aln[8];
+    while ((int32_t)m < n_aln && (int32_t)aln[9 * m + 8] <= best) ++m;                            // :40-42
+    return m == 1 ? SEL_SINGLE : SEL_SEVERAL;
+}
+// multi slots the read owns: every occurrence of every hit when there are at most n_occ + 1 of them (:63-92), or room for
+// the positions bwt_aln2pos_splicing looks up (<= 50 per part, bwtse.c:322)
+HSA_HD uint32_t sel_slots(const uint32_t *aln, int32_t n_aln, int32_t n_occ, uint32_t kind)
+{
+    if (kind == SEL_SPLICE) {
         const uint32_t w0 = aln[2] - aln[1] + 1u, w1 = aln[9 + 2] - aln[9 + 1] + 1u;
         return (w0 < 50u ? w0 : 50u) + (w1 < 50u ? w1 : 50u);
     }
-    if (n_aln == 0) { s.type = TYPE_NO_MATCH; s.c1 = s.c2 = 0; return 0; }
-    if ((aln[5] & 0x3FFFFFFFu) == TYPE_SPLICING && n_aln == 1) s.type = aln[2] - aln[1] + 1u > 1u ? TYPE_REPEAT : TYPE_UNIQUE;
-    {                                                                               // set_main (:38-62)
-        const int32_t best = (int32_t)aln[8];
-        int32_t i, cnt;
-        for (i = cnt = 0; i < n_aln; ++i) {
-            const uint32_t *p = aln + 9 * i;
-            if ((int32_t)p[8] > best) break;
-            if (rng.next() * (double)(uint32_t)(p[2] - p[1] + 1u + (uint32_t)cnt) > (double)cnt) {
-                s.n_mm = p[0] & 0xFFu; s.n_gapo = (p[0] >> 16) & 0xFFu; s.n_gape = p[0] >> 24;   // 8-bit fields of bwa_seq_t
-                s.score = (int32_t)p[8]; s.start = (int32_t)p[6]; s.end = (int32_t)p[7];
-                s.sa = p[1] + (uint32_t)((double)(uint32_t)(p[2] - p[1] + 1u) * rng.next());
-                s.strand = (p[5] >> 30) & 1u;
-            }
-            cnt += (int32_t)(p[2] - p[1] + 1u);
-        }
-        s.c1 = (uint32_t)cnt & 0x0FFFFFFFu;
-        for (; i < n_aln; ++i) cnt += (int32_t)(aln[9 * i + 2] - aln[9 * i + 1] + 1u);
-        s.c2 = ((uint32_t)cnt - s.c1) & 0x0FFFFFFFu;
-        s.type = s.c1 > 1u ? TYPE_REPEAT : TYPE_UNIQUE;
+    if (kind == SEL_NONE || !n_occ) return 0;
+    int32_t tot = 0;
+    for (int32_t k = 0; k < n_aln; ++k) tot += (int32_t)(aln[9 * k + 2] - aln[9 * k + 1] + 1u);
+    return tot > n_occ + 1 ? 0u : (uint32_t)tot;
+}
+// the draws of one read's set_main loop (:38-53) from the stream at rng; returns the number drawn
+HSA_HD uint32_t sel_draw(const uint32_t *aln, uint32_t m, const uint32_t *w_inline, Rng48 &rng, SelPick &pick)
+{
+    int32_t cnt = 0; uint32_t drawn = 0;
+    pick.j = 0; pick.taken = 0; pick.r2 = 0.0;
+    for (uint32_t j = 0; j < m; ++j) {
+        const uint32_t w = (w_inline && j < SEL_DESC_W) ? w_inline[j] : aln[9 * j + 2] - aln[9 * j + 1] + 1u;
+        ++drawn;
+        if (rng.next() * (double)(uint32_t)(w + (uint32_t)cnt) > (double)cnt) { pick.j = j; pick.taken = 1; pick.r2 = rng.next(); ++drawn; }
+        cnt += (int32_t)w;
     }
-    uint32_t z = 0;
-    if (n_occ) {                                                                    // alternative hits (:63-112)
-        int32_t k, rest, tot = 0;
-        for (k = 0; k < n_aln; ++k) tot += (int32_t)(aln[9 * k + 2] - aln[9 * k + 1] + 1u);
-        if (tot > n_occ + 1) { s.n_multi = 0; return 0; }
-        rest = tot > n_occ + 1 ? n_occ + 1 : tot;
-        for (k = 0; k < n_aln; ++k) {
+    return drawn;
+}
+// the fields of a matched read once its pick is known (:44-61), and its alternative-hit list (:63-92); false: the read needs
+// the sampling branch (:93-107), which only the sequential statement evaluates
+HSA_HD bool sel_fill(const uint32_t *aln, int32_t n_aln, int32_t n_occ, uint32_t m, const SelPick &pick, SamRec &s, SamMulti *multi)
+{
+    if (pick.taken) {
+        const uint32_t *p = aln + 9 * pick.j;
+        s.n_mm = p[0] & 0xFFu; s.n_gapo = (p[0] >> 16) & 0xFFu; s.n_gape = p[0] >> 24;               // 8-bit fields of bwa_seq_t
+        s.score = (int32_t)p[8]; s.start = (int32_t)p[6]; s.end = (int32_t)p[7];
+        s.sa = p[1] + (uint32_t)((double)(uint32_t)(p[2] - p[1] + 1u) * pick.r2);
+        s.strand = (p[5] >> 30) & 1u;
+    }
+    int32_t cnt = 0, i;
+    for (i = 0; i < (int32_t)m; ++i) cnt += (int32_t)(aln[9 * i + 2] - aln[9 * i + 1] + 1u);
+    s.c1 = (uint32_t)cnt & 0x0FFFFFFFu;
+    for (; i < n_aln; ++i) cnt += (int32_t)(aln[9 * i + 2] - aln[9 * i + 1] + 1u);
+    s.c2 = ((uint32_t)cnt - s.c1) & 0x0FFFFFFFu;
+    s.type = s.c1 > 1u ? TYPE_REPEAT : TYPE_UNIQUE;
+    s.n_multi = 0;
+    if (!n_occ) return true;
+    if (cnt > n_occ + 1) return true;                                                   // too many occurrences: no list (:70-75)
+    int32_t rest = cnt; uint32_t z = 0;
+    for (int32_t k = 0; k < n_aln; ++k) {
+        const uint32_t *q = aln + 9 * k;
+        const uint32_t w = q[2] - q[1] + 1u;
+        if (w > (uint32_t)rest) return false;
+        SamMulti t;
+        t.n_cigar = t.cigar_off = 0; t.sa = t.ori_pos = t.occ_pos = t.seq_id = t.aln_id = 0;
+        t.start = (int32_t)q[6]; t.end = (int32_t)q[7]; t.strand = (q[5] >> 30) & 1u;
+        t.gap = (((q[0] >> 16) & 0xFFu) + (q[0] >> 24)) & 0xFFu; t.mm = q[0] & 0xFFu;
+        for (uint32_t l = q[1]; l <= q[2]; ++l) { t.sa = l; multi[z++] = t; if (l == 0xFFFFFFFFu) break; }
+        rest -= (int32_t)w;
+    }
+    s.n_multi = z;
+    return true;
+}
+
+// The sequential statement.  Fills rec (zero-initialised by the caller) and the read's alternative hits in multi[0 ...];
+// returns the number of multi slots the read owns.
+HSA_HD uint32_t sam_select(const uint32_t *aln, int32_t n_aln, int32_t n_occ, Rng48 &rng, SamRec &s, SamMulti *multi)
+{
+    uint32_t m;
+    const uint32_t kind = sel_kind(aln, n_aln, m);
+    if (kind == SEL_SPLICE) { s.type = TYPE_SPLICING; return sel_slots(aln, n_aln, n_occ, kind); }
+    if (kind == SEL_NONE) { s.type = TYPE_NO_MATCH; s.c1 = s.c2 = 0; return 0; }
+    SelPick pick;
+    sel_draw(aln, m, nullptr, rng, pick);
+    if (!sel_fill(aln, n_aln, n_occ, m, pick, s, multi)) {
+        // the sampling branch (:93-107): unreachable while the list holds every occurrence (rest == the sum of the widths),
+        // kept for the record
+        int32_t rest = 0; uint32_t z = 0;
+        for (int32_t k = 0; k < n_aln; ++k) rest += (int32_t)(aln[9 * k + 2] - aln[9 * k + 1] + 1u);
+        for (int32_t k = 0; k < n_aln; ++k) {
             const uint32_t *q = aln + 9 * k;
             const uint32_t w = q[2] - q[1] + 1u;
-            SamMulti t; memset(&t, 0, sizeof(t));
+            SamMulti t;
+            t.n_cigar = t.cigar_off = 0; t.sa = t.ori_pos = t.occ_pos = t.seq_id = t.aln_id = 0;
             t.start = (int32_t)q[6]; t.end = (int32_t)q[7]; t.strand = (q[5] >> 30) & 1u;
             t.gap = (((q[0] >> 16) & 0xFFu) + (q[0] >> 24)) & 0xFFu; t.mm = q[0] & 0xFFu;
             if (w <= (uint32_t)rest) {
                 for (uint32_t l = q[1]; l <= q[2]; ++l) { t.sa = l; multi[z++] = t; if (l == 0xFFFFFFFFu) break; }
                 rest -= (int32_t)w;
-            } else {                                                                // random sample (:93-107); unreachable while
-                int32_t j, i;                                                       // tot <= n_occ + 1, kept for the record
+            } else {
+                int32_t j, i;
                 for (j = rest, i = (int32_t)w; j > 0; --j) {
                     double p = 1.0; const double x = rng.next();
                     while (x < p) p -= p * j / (i--);
                     t.sa = q[2] - (uint32_t)i; multi[z++] = t;
                 }
-                rest = 0;
                 break;
             }
         }
         s.n_multi = z;
     }
-    return z;
+    return sel_slots(aln, n_aln, n_occ, kind);
+}
+
+// ---- the selection as kernels' bodies ------------------------------------------------------------------------------------
+struct SelParams {
+    const int32_t *n_aln; const uint64_t *aln_off; const uint32_t *aln; uint32_t n_reads; int32_t n_occ;
+    uint32_t *fixed, *dep, *slots;              // per read; after the scans: exclusive prefix sums (n_reads + 1 entries)
+    SelDesc *desc; SelPick *pick; uint32_t *vcum;   // per dependent read: descriptor, outcome, draws of the dependent reads so far
+    SamRec *rec; SamMulti *multi;
+    uint64_t x0; uint64_t *x_end;               // stream state at the start of the batch / at its end
+    uint32_t *rare;                             // != 0: the batch must be selected by the sequential statement
+};
+
+HSA_HD void sel_classify_item(const SelParams &P, uint32_t r)
+{
+    uint32_t m;
+    const uint32_t *a = P.aln + 9 * P.aln_off[r];
+    const uint32_t kind = sel_kind(a, P.n_aln[r], m);
+    P.fixed[r] = kind == SEL_SINGLE ? 2u : 0u;
+    P.dep[r] = kind == SEL_SEVERAL ? 1u : 0u;
+    P.slots[r] = sel_slots(a, P.n_aln[r], P.n_occ, kind);
+}
+HSA_HD void sel_desc_item(const SelParams &P, uint32_t r)          // after the scans
+{
+    if (P.dep[r + 1] == P.dep[r]) return;
+    uint32_t m;
+    const uint32_t *a = P.aln + 9 * P.aln_off[r];
+    sel_kind(a, P.n_aln[r], m);
+    SelDesc d;
+    d.read = r; d.m = m; d.fixed_before = P.fixed[r];
+    for (uint32_t j = 0; j < SEL_DESC_W; ++j) d.w[j] = j < m ? a[9 * j + 2] - a[9 * j + 1] + 1u : 0u;
+    P.desc[P.dep[r]] = d;
+}
+HSA_HD void sel_chain(const SelParams &P)                          // one thread
+{
+    Rng48 rng{P.x0};
+    const uint32_t n_dep = P.dep[P.n_reads];
+    uint32_t prev_fixed = 0, v = 0;
+    for (uint32_t d = 0; d < n_dep; ++d) {
+        const SelDesc e = P.desc[d];
+        rng.jump(e.fixed_before - prev_fixed); prev_fixed = e.fixed_before;
+        SelPick pk;
+        v += sel_draw(P.aln + 9 * P.aln_off[e.read], e.m, e.w, rng, pk);
+        P.pick[d] = pk; P.vcum[d] = v;
+    }
+    rng.jump(P.fixed[P.n_reads] - prev_fixed);
+    *P.x_end = rng.x;
+}
+HSA_HD void sel_finish_item(const SelParams &P, uint32_t r)
+{
+    SamRec s;
+    s.type = s.strand = s.n_mm = s.n_gapo = s.n_gape = s.mapQ = 0; s.score = 0; s.sa = s.seq_id = s.ori_pos = s.occ_pos = s.c1 = s.c2 = 0;
+    s.start = s.end = 0; s.n_cigar = s.cigar_off = s.nm = s.md_len = s.md_off = s.n_multi = 0;
+    s.multi_off = P.slots[r];
+    const uint32_t *a = P.aln + 9 * P.aln_off[r];
+    const int32_t n_aln = P.n_aln[r];
+    uint32_t m;
+    const uint32_t kind = sel_kind(a, n_aln, m);
+    if (kind == SEL_SPLICE) s.type = TYPE_SPLICING;
+    else if (kind == SEL_NONE) s.type = TYPE_NO_MATCH;
+    else {
+        SelPick pk;
+        if (kind == SEL_SINGLE) {
+            const uint32_t d = P.dep[r];                            // dependent reads before this one
+            Rng48 rng{P.x0};
+            rng.jump((uint64_t)P.fixed[r] + (d ? P.vcum[d - 1] : 0u));
+            if (sel_draw(a, 1u, nullptr, rng, pk) != 2u) *P.rare = 1u;      // r = 0 on the first draw: the prefix sums are off
+        } else pk = P.pick[P.dep[r]];
+        if (!sel_fill(a, n_aln, P.n_occ, m, pk, s, P.multi + s.multi_off)) *P.rare = 1u;
+    }
+    P.rec[r] = s;
+}
+HSA_HD void sel_sequential(const SelParams &P)                      // one thread: the whole batch by the sequential statement
+{
+    Rng48 rng{P.x0};
+    for (uint32_t r = 0; r < P.n_reads; ++r) {
+        SamRec s;
+        s.type = s.strand = s.n_mm = s.n_gapo = s.n_gape = s.mapQ = 0; s.score = 0; s.sa = s.seq_id = s.ori_pos = s.occ_pos = s.c1 = s.c2 = 0;
+        s.start = s.end = 0; s.n_cigar = s.cigar_off = s.nm = s.md_len = s.md_off = s.n_multi = 0;
+        s.multi_off = P.slots[r];
+        sam_select(P.aln + 9 * P.aln_off[r], P.n_aln[r], P.n_occ, rng, s, P.multi + s.multi_off);
+        P.rec[r] = s;
+    }
+    *P.x_end = rng.x;
 }
 
 }   // namespace hsa

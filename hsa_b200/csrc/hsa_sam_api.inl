@@ -21,17 +21,44 @@ __global__ void __launch_bounds__(128) sam_dp_kernel(const __grid_constant__ Sam
     }
 }
 
+// the hit selection, cut where the drand48 stream allows it (hsa_sam.cuh)
+__global__ void __launch_bounds__(256) sel_classify_kernel(const __grid_constant__ SelParams P, uint32_t *max_gaps)
+{
+    uint32_t g = 0;
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += (size_t)gridDim.x * blockDim.x) {
+        sel_classify_item(P, (uint32_t)r);
+        const uint32_t *a = P.aln + 9 * P.aln_off[r];
+        for (int32_t j = 0; j < P.n_aln[r]; ++j) g = max(g, ((a[9 * j] >> 16) & 0xFFu) + (a[9 * j] >> 24));     // n_gapo + n_gape: sizes the DP scratch
+    }
+    for (int o = 16; o > 0; o >>= 1) g = max(g, __shfl_down_sync(0xffffffffu, g, o));
+    if ((threadIdx.x & 31u) == 0 && g) atomicMax(max_gaps, g);
+}
+__global__ void __launch_bounds__(256) sel_desc_kernel(const __grid_constant__ SelParams P)
+{
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += (size_t)gridDim.x * blockDim.x) sel_desc_item(P, (uint32_t)r);
+}
+__global__ void sel_chain_kernel(const __grid_constant__ SelParams P) { sel_chain(P); }
+__global__ void __launch_bounds__(256) sel_finish_kernel(const __grid_constant__ SelParams P)
+{
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += (size_t)gridDim.x * blockDim.x) sel_finish_item(P, (uint32_t)r);
+}
+__global__ void sel_sequential_kernel(const __grid_constant__ SelParams P) { sel_sequential(P); }
+
 }   // namespace hsa
 
-struct SamCache { DevBuf codes, off, len, n_aln, aln_off, aln, rec, multi, cigar, md, list, cnt, maxdiff, dp_bytes, dp_rows; };
+struct SamCache {
+    DevBuf codes, off, len, n_aln, aln_off, aln, rec, multi, cigar, md, list, cnt, maxdiff, dp_bytes, dp_rows;
+    DevBuf fixed, dep, slots, desc, pick, vcum, scan_tmp, sel_out;
+};
 static void sam_cache_free(SamCache *c) { delete c; }
 
 template <typename T> static int host_grow(T *&p, size_t &cap, size_t need)
 {
     if (need <= cap && p) return 0;
-    T *q = (T *)realloc(p, std::max<size_t>(need, 1) * sizeof(T));
+    const size_t want = std::max<size_t>({need, cap + cap / 2, (size_t)1024});
+    T *q = (T *)realloc(p, want * sizeof(T));
     if (!q) return -1;
-    p = q; cap = std::max<size_t>(need, 1);
+    p = q; cap = want;
     return 0;
 }
 
@@ -42,77 +69,84 @@ extern "C" void hsa_sam_result_free(hsa_sam_result_t *res)
     memset(res, 0, sizeof(*res));
 }
 
-extern "C" int hsa_sam_se_batch(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len, size_t n_reads,
-                                const int32_t *n_aln, const uint64_t *aln_off, const hsa_aln1_t *aln, const hsa_gap_opt_t *opt,
-                                int n_occ, uint64_t *rng48_state, hsa_sam_result_t *res)
+// What the stage leaves on the device (valid until the next SAM call on the index)
+struct SamDeviceOut { size_t n_multi = 0, n_cigar = 0, md_bytes = 0; uint64_t n_refined = 0, n_dependent = 0; float kernel_ms = 0; bool sequential = false; };
+
+// The whole stage on device-resident inputs: selection (classify, prefix sums, chain, finish), positions, refinement.
+static int sam_run_device(const hsa_index_t *ix, SamCache &C, const uint8_t *codes_dev, const uint64_t *off_dev, const uint32_t *len_dev,
+                          size_t n_reads, uint32_t max_len, const int32_t *n_aln_dev, const uint64_t *aln_off_dev, const uint32_t *aln_dev,
+                          const hsa_gap_opt_t *opt, int n_occ, uint64_t *rng48_state, cudaStream_t s, SamDeviceOut &out)
 {
-    static_assert(sizeof(SamRec) == sizeof(hsa_sam1_t) && sizeof(SamMulti) == sizeof(hsa_multi1_t), "record mirrors");
-    if (!ix || !opt || !rng48_state || !res) return fail(HSA_E_ARG, "null argument");
-    res->n_reads = n_reads; res->n_multi = res->n_cigar = res->md_bytes = 0; res->n_refined = 0; res->kernel_ms = 0;
-    if (n_reads == 0) return HSA_OK;
-    if (!codes || !off || !len || !n_aln || !aln_off) return fail(HSA_E_ARG, "null argument");
-    if (!ix->sa_value || !ix->blocks4 || !ix->packed_dna)
-        return fail(HSA_E_ARG, "the SAM stage needs the SA samples, the block list and the packed text "
-                               "(hsa_index_attach_sa / _blocks / _packed_dna)");
-    if (n_reads > 0x7FFFFFF0ull) return fail(HSA_E_ARG, "too many reads in one batch");
-    if (n_occ < 0 || n_occ > 1000) return fail(HSA_E_ARG, "n_occ out of range");
-    // ---- host: the drand48-ordered selection (bwtse.c:898-910) ----
-    size_t bytes = 0, n_hits = 0; uint32_t max_len = 0, max_ext = 0;
-    for (size_t i = 0; i < n_reads; ++i) {
-        if (len[i] > 4095) return fail(HSA_E_ARG, "reads longer than 4095 bases are not supported");
-        if (n_aln[i] < 0) return fail(HSA_E_ARG, "negative n_aln");
-        if (n_aln[i] && !aln) return fail(HSA_E_ARG, "hits without a hit array");
-        bytes = std::max(bytes, (size_t)off[i] + len[i]); max_len = std::max(max_len, len[i]);
-        if (n_aln[i]) n_hits = std::max(n_hits, (size_t)aln_off[i] + (size_t)n_aln[i]);
+    const uint32_t n = (uint32_t)n_reads;
+    const size_t n1 = n_reads + 1;
+    if (C.fixed.alloc(n1 * 4) || C.dep.alloc(n1 * 4) || C.slots.alloc(n1 * 4) || C.rec.alloc(n_reads * sizeof(SamRec)) ||
+        C.list.alloc(n_reads * 4) || C.cnt.alloc(8 * sizeof(unsigned long long)) || C.maxdiff.alloc(((size_t)max_len + 1) * 4) ||
+        C.sel_out.alloc(4 * sizeof(unsigned long long)))
+        return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, s));
+    // ---- selection ----
+    SelParams S;
+    memset(&S, 0, sizeof(S));
+    S.n_aln = n_aln_dev; S.aln_off = aln_off_dev; S.aln = aln_dev; S.n_reads = n; S.n_occ = n_occ;
+    S.fixed = C.fixed.as<uint32_t>(); S.dep = C.dep.as<uint32_t>(); S.slots = C.slots.as<uint32_t>(); S.rec = C.rec.as<SamRec>();
+    S.x0 = *rng48_state & 0xFFFFFFFFFFFFull;
+    unsigned long long *so = C.sel_out.as<unsigned long long>();     // {stream state at the end, rare flag, max gaps of any hit}
+    S.x_end = reinterpret_cast<uint64_t *>(so); S.rare = reinterpret_cast<uint32_t *>(so + 1);
+    uint32_t *max_gaps = reinterpret_cast<uint32_t *>(so + 2);
+    CU(cudaMemsetAsync(so, 0, 4 * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(S.fixed + n, 0, 4, s)); CU(cudaMemsetAsync(S.dep + n, 0, 4, s)); CU(cudaMemsetAsync(S.slots + n, 0, 4, s));
+    const uint32_t grid = (uint32_t)std::min<size_t>((n_reads + 255) / 256, (size_t)ix->sm_count * 8);
+    sel_classify_kernel<<<grid, 256, 0, s>>>(S, max_gaps);
+    CU(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, S.fixed, S.fixed, (int)n1, s));
+    if (C.scan_tmp.alloc(tmp_bytes + 256)) return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
+    for (uint32_t *v : {S.fixed, S.dep, S.slots}) {
+        size_t tb = C.scan_tmp.cap;
+        CU(cub::DeviceScan::ExclusiveSum(C.scan_tmp.p, tb, v, v, (int)n1, s));
     }
-    if (host_grow(res->rec, res->cap_rec, n_reads)) return fail(HSA_E_NOMEM, "out of host memory");
-    memset(res->rec, 0, n_reads * sizeof(hsa_sam1_t));
-    Rng48 rng{*rng48_state & 0xFFFFFFFFFFFFull};
-    size_t n_multi = 0; const uint32_t *words = reinterpret_cast<const uint32_t *>(aln);
-    for (size_t i = 0; i < n_reads; ++i) {
-        // worst case of one read: every occurrence of every hit (<= n_occ + 1) or 100 positions of a spliced pair
-        if (host_grow(res->multi, res->cap_multi, n_multi + std::max<size_t>(100, (size_t)n_occ + 2))) return fail(HSA_E_NOMEM, "out of host memory");
-        SamRec &s = *reinterpret_cast<SamRec *>(res->rec + i);
-        s.multi_off = (uint32_t)n_multi;
-        const uint32_t own = sam_select(n_aln[i] ? words + 9 * aln_off[i] : nullptr, n_aln[i], n_occ, rng, s,
-                                        reinterpret_cast<SamMulti *>(res->multi) + n_multi);
-        n_multi += own;
-        if (n_multi > 0xFFFFFFF0ull) return fail(HSA_E_ARG, "too many alternative hits in one batch");
-        max_ext = std::max(max_ext, s.n_gapo + s.n_gape);
-        for (uint32_t j = 0; j < s.n_multi; ++j) max_ext = std::max(max_ext, res->multi[s.multi_off + j].gap);
+    uint32_t totals[3] = {0, 0, 0}, h_gaps = 0;                       // fixed draws, reads with several best hits, multi slots
+    CU(cudaMemcpyAsync(&totals[0], S.fixed + n, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&totals[1], S.dep + n, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&totals[2], S.slots + n, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&h_gaps, max_gaps, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const size_t n_dep = totals[1], n_multi = totals[2];
+    if (C.multi.alloc(std::max<size_t>(n_multi, 1) * sizeof(SamMulti)) || C.desc.alloc(std::max<size_t>(n_dep, 1) * sizeof(SelDesc)) ||
+        C.pick.alloc(std::max<size_t>(n_dep, 1) * sizeof(SelPick)) || C.vcum.alloc(std::max<size_t>(n_dep, 1) * 4))
+        return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
+    S.multi = C.multi.as<SamMulti>(); S.desc = C.desc.as<SelDesc>(); S.pick = C.pick.as<SelPick>(); S.vcum = C.vcum.as<uint32_t>();
+    const bool force_seq = env_long("HSA_B200_SAM_SEQUENTIAL", 0) != 0;      // tests: the sequential statement on one device thread
+    bool sequential = force_seq;
+    if (!sequential) {
+        sel_desc_kernel<<<grid, 256, 0, s>>>(S);
+        sel_chain_kernel<<<1, 1, 0, s>>>(S);
+        sel_finish_kernel<<<grid, 256, 0, s>>>(S);
+        CU(cudaGetLastError());
+        uint32_t rare = 0;
+        CU(cudaMemcpyAsync(&rare, S.rare, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        sequential = rare != 0;
     }
-    *rng48_state = rng.x;
-    res->n_multi = n_multi;
-    // ---- device ----
-    CU(cudaSetDevice(ix->device));
-    cudaStream_t s = ix->stream;
-    hsa_index *mix = const_cast<hsa_index *>(ix);
-    if (!mix->sam_cache) mix->sam_cache = new SamCache();
-    SamCache &C = *mix->sam_cache;
+    if (sequential) { sel_sequential_kernel<<<1, 1, 0, s>>>(S); CU(cudaGetLastError()); }
+    uint64_t x_end = 0;
+    CU(cudaMemcpyAsync(&x_end, S.x_end, 8, cudaMemcpyDeviceToHost, s));
+    // ---- positions, refinement ----
     std::vector<int32_t> maxdiff;
     if (opt->fnr > 0.0f) { maxdiff.resize((size_t)max_len + 1); for (uint32_t L = 0; L <= max_len; ++L) maxdiff[L] = hsa_cal_maxdiff((int)L, 0.02, opt->fnr); }
-    if (C.codes.alloc(bytes + 16) || C.off.alloc(n_reads * 8) || C.len.alloc(n_reads * 4) || C.n_aln.alloc(n_reads * 4) ||
-        C.aln_off.alloc(n_reads * 8) || C.aln.alloc(std::max<size_t>(n_hits, 1) * 36) || C.rec.alloc(n_reads * sizeof(SamRec)) ||
-        C.multi.alloc(std::max<size_t>(n_multi, 1) * sizeof(SamMulti)) || C.list.alloc(n_reads * 4) || C.cnt.alloc(8 * sizeof(unsigned long long)) ||
-        C.maxdiff.alloc(((size_t)max_len + 1) * 4))
-        return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
-    CU(cudaMemcpyAsync(C.codes.p, codes, bytes, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(C.off.p, off, n_reads * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(C.len.p, len, n_reads * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(C.n_aln.p, n_aln, n_reads * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(C.aln_off.p, aln_off, n_reads * 8, cudaMemcpyHostToDevice, s));
-    if (n_hits) CU(cudaMemcpyAsync(C.aln.p, aln, n_hits * 36, cudaMemcpyHostToDevice, s));
     if (!maxdiff.empty()) CU(cudaMemcpyAsync(C.maxdiff.p, maxdiff.data(), maxdiff.size() * 4, cudaMemcpyHostToDevice, s));
     SamParams P;
     memset(&P, 0, sizeof(P));
     P.env.ix = ix->ix; P.env.sa_value = ix->sa_value; P.env.sa_interval = ix->sa_interval;
     P.env.blocks4 = ix->blocks4; P.env.n_blocks = ix->n_blocks; P.env.packed_dna = ix->packed_dna; P.env.dna_length = ix->dna_length;
-    P.codes = C.codes.as<uint8_t>(); P.read_off = C.off.as<uint64_t>(); P.read_len = C.len.as<uint32_t>(); P.n_reads = (uint32_t)n_reads;
-    P.n_aln = C.n_aln.as<int32_t>(); P.aln_off = C.aln_off.as<uint64_t>(); P.aln = C.aln.as<uint32_t>();
+    P.codes = codes_dev; P.read_off = off_dev; P.read_len = len_dev; P.n_reads = n;
+    P.n_aln = n_aln_dev; P.aln_off = aln_off_dev; P.aln = aln_dev;
     P.rec = C.rec.as<SamRec>(); P.multi = C.multi.as<SamMulti>();
     P.maxdiff_by_len = maxdiff.empty() ? nullptr : C.maxdiff.as<int32_t>(); P.max_mm = opt->max_diff; P.max_len = max_len;
     P.dp_list = C.list.as<uint32_t>();
-    unsigned long long *cnt = C.cnt.as<unsigned long long>();        // {cigar words, md bytes, dp reads, cursor, status}
+    unsigned long long *cnt = C.cnt.as<unsigned long long>();        // {cigar words, md bytes, dp reads, cursor, status, dp tasks}
     P.cigar_used = cnt; P.md_used = cnt + 1; P.dp_count = cnt + 2; P.cursor = cnt + 3; P.status = reinterpret_cast<uint32_t *>(cnt + 4);
     P.dp_tasks = cnt + 5;
     // arena sizes: MD from the read count, CIGAR from the refinements the first kernel lists (12 words each); a batch that
@@ -120,17 +154,15 @@ extern "C" int hsa_sam_se_batch(const hsa_index_t *ix, const uint8_t *codes, con
     // failed attempt are lower bounds, not sizes)
     const bool tiny = env_long("HSA_B200_SAM_TINY", 0) != 0;          // tests: start with arenas that are certainly too small
     size_t cigar_cap = tiny ? 16 : 4096, md_cap = tiny ? 64 : n_reads * 16 + 4096;
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const uint32_t max_ext = h_gaps;
     unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
     for (int attempt = 0; attempt < 6; ++attempt) {
         if (C.md.alloc(md_cap)) return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
         P.cigar = nullptr; P.cigar_cap = 0; P.md = C.md.as<char>(); P.md_cap = md_cap;
         CU(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), s));
-        CU(cudaMemcpyAsync(C.rec.p, res->rec, n_reads * sizeof(SamRec), cudaMemcpyHostToDevice, s));
-        if (n_multi) CU(cudaMemcpyAsync(C.multi.p, res->multi, n_multi * sizeof(SamMulti), cudaMemcpyHostToDevice, s));
-        CU(cudaEventRecord(e0, s));
-        const uint32_t grid = (uint32_t)std::min<size_t>((n_reads + 255) / 256, (size_t)ix->sm_count * 8);
+        if (attempt) {                                               // the first kernel rewrites records in place: select again
+            if (sequential) sel_sequential_kernel<<<1, 1, 0, s>>>(S); else sel_finish_kernel<<<grid, 256, 0, s>>>(S);
+        }
         sam_pos_kernel<<<grid, 256, 0, s>>>(P);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -144,7 +176,8 @@ extern "C" int hsa_sam_se_batch(const hsa_index_t *ix, const uint8_t *codes, con
             const uint32_t len1_cap = max_len + max_ext, len2_cap = max_len;
             const uint32_t W = std::min<uint32_t>(2u * DP_BAND + max_ext + 1u, len1_cap + 1u);
             const size_t per_bytes = (size_t)(len2_cap + 1u) * W + len1_cap + 1u, per_rows = std::max<size_t>(3 * ((size_t)len1_cap + 1), (size_t)len1_cap + len2_cap + 2);
-            uint32_t workers = (uint32_t)std::min<size_t>({(size_t)n_dp, (size_t)ix->sm_count * 256, std::max<size_t>(128, ((size_t)1 << 30) / (per_bytes + 4 * per_rows))});
+            // 80 registers: six blocks of 128 per SM; scratch capped at 2 GB (fewer workers for long reads)
+            uint32_t workers = (uint32_t)std::min<size_t>({(size_t)n_dp, (size_t)ix->sm_count * 768, std::max<size_t>(128, ((size_t)2 << 30) / (per_bytes + 4 * per_rows))});
             workers = (workers + 127u) / 128u * 128u;
             if (C.dp_bytes.alloc(per_bytes * workers) || C.dp_rows.alloc(per_rows * 4 * workers)) return fail(HSA_E_CUDA, "out of device memory for the DP scratch");
             P.dp_bytes = C.dp_bytes.as<uint8_t>(); P.dp_rows = C.dp_rows.as<int32_t>(); P.dp_workers = workers; P.dp_w = W;
@@ -165,13 +198,97 @@ extern "C" int hsa_sam_se_batch(const hsa_index_t *ix, const uint8_t *codes, con
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    res->kernel_ms = ms; res->n_refined = h[2]; res->n_cigar = (size_t)h[0]; res->md_bytes = (size_t)h[1];
-    if (host_grow(res->cigar, res->cap_cigar, res->n_cigar) || host_grow(res->md, res->cap_md, res->md_bytes)) return fail(HSA_E_NOMEM, "out of host memory");
+    *rng48_state = x_end;
+    out.n_multi = n_multi; out.n_cigar = (size_t)h[0]; out.md_bytes = (size_t)h[1]; out.n_refined = h[2]; out.n_dependent = n_dep;
+    out.kernel_ms = ms; out.sequential = sequential;
+    return HSA_OK;
+}
+
+extern "C" int hsa_sam_se_batch(const hsa_index_t *ix, const uint8_t *codes, const uint64_t *off, const uint32_t *len, size_t n_reads,
+                                const int32_t *n_aln, const uint64_t *aln_off, const hsa_aln1_t *aln, const hsa_gap_opt_t *opt,
+                                int n_occ, uint64_t *rng48_state, hsa_sam_result_t *res)
+{
+    static_assert(sizeof(SamRec) == sizeof(hsa_sam1_t) && sizeof(SamMulti) == sizeof(hsa_multi1_t), "record mirrors");
+    if (!ix || !opt || !rng48_state || !res) return fail(HSA_E_ARG, "null argument");
+    res->n_reads = n_reads; res->n_multi = res->n_cigar = res->md_bytes = 0; res->n_refined = 0; res->kernel_ms = 0;
+    if (n_reads == 0) return HSA_OK;
+    if (!codes || !off || !len || !n_aln || !aln_off) return fail(HSA_E_ARG, "null argument");
+    if (!ix->sa_value || !ix->blocks4 || !ix->packed_dna)
+        return fail(HSA_E_ARG, "the SAM stage needs the SA samples, the block list and the packed text "
+                               "(hsa_index_attach_sa / _blocks / _packed_dna)");
+    if (n_reads > 0x3FFFFFF0ull) return fail(HSA_E_ARG, "too many reads in one batch");
+    if (n_occ < 0 || n_occ > 1000) return fail(HSA_E_ARG, "n_occ out of range");
+    const bool trace = env_long("HSA_B200_TRACE", 0) != 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    size_t bytes = 0, n_hits = 0; uint32_t max_len = 0;
+    for (size_t i = 0; i < n_reads; ++i) {
+        if (len[i] > 4095) return fail(HSA_E_ARG, "reads longer than 4095 bases are not supported");
+        if (n_aln[i] < 0) return fail(HSA_E_ARG, "negative n_aln");
+        if (n_aln[i] && !aln) return fail(HSA_E_ARG, "hits without a hit array");
+        bytes = std::max(bytes, (size_t)off[i] + len[i]); max_len = std::max(max_len, len[i]);
+        if (n_aln[i]) n_hits = std::max(n_hits, (size_t)aln_off[i] + (size_t)n_aln[i]);
+    }
+    CU(cudaSetDevice(ix->device));
+    cudaStream_t s = ix->stream;
+    hsa_index *mix = const_cast<hsa_index *>(ix);
+    if (!mix->sam_cache) mix->sam_cache = new SamCache();
+    SamCache &C = *mix->sam_cache;
+    if (C.codes.alloc(bytes + 16) || C.off.alloc(n_reads * 8) || C.len.alloc(n_reads * 4) || C.n_aln.alloc(n_reads * 4) ||
+        C.aln_off.alloc(n_reads * 8) || C.aln.alloc(std::max<size_t>(n_hits, 1) * 36))
+        return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
+    CU(cudaMemcpyAsync(C.codes.p, codes, bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(C.off.p, off, n_reads * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(C.len.p, len, n_reads * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(C.n_aln.p, n_aln, n_reads * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(C.aln_off.p, aln_off, n_reads * 8, cudaMemcpyHostToDevice, s));
+    if (n_hits) CU(cudaMemcpyAsync(C.aln.p, aln, n_hits * 36, cudaMemcpyHostToDevice, s));
+    const double ms_h2d = since(t_begin);
+    SamDeviceOut o;
+    int rc = sam_run_device(ix, C, C.codes.as<uint8_t>(), C.off.as<uint64_t>(), C.len.as<uint32_t>(), n_reads, max_len, C.n_aln.as<int32_t>(),
+                            C.aln_off.as<uint64_t>(), C.aln.as<uint32_t>(), opt, n_occ, rng48_state, s, o);
+    if (rc) return rc;
+    const double ms_dev = since(t_begin) - ms_h2d;
+    res->kernel_ms = o.kernel_ms; res->n_refined = o.n_refined; res->n_multi = o.n_multi; res->n_cigar = o.n_cigar; res->md_bytes = o.md_bytes;
+    if (host_grow(res->rec, res->cap_rec, n_reads) || host_grow(res->multi, res->cap_multi, o.n_multi) ||
+        host_grow(res->cigar, res->cap_cigar, o.n_cigar) || host_grow(res->md, res->cap_md, o.md_bytes)) return fail(HSA_E_NOMEM, "out of host memory");
     CU(cudaMemcpyAsync(res->rec, C.rec.p, n_reads * sizeof(SamRec), cudaMemcpyDeviceToHost, s));
-    if (n_multi) CU(cudaMemcpyAsync(res->multi, C.multi.p, n_multi * sizeof(SamMulti), cudaMemcpyDeviceToHost, s));
-    if (res->n_cigar) CU(cudaMemcpyAsync(res->cigar, C.cigar.p, res->n_cigar * 4, cudaMemcpyDeviceToHost, s));
-    if (res->md_bytes) CU(cudaMemcpyAsync(res->md, C.md.p, res->md_bytes, cudaMemcpyDeviceToHost, s));
+    if (o.n_multi) CU(cudaMemcpyAsync(res->multi, C.multi.p, o.n_multi * sizeof(SamMulti), cudaMemcpyDeviceToHost, s));
+    if (o.n_cigar) CU(cudaMemcpyAsync(res->cigar, C.cigar.p, o.n_cigar * 4, cudaMemcpyDeviceToHost, s));
+    if (o.md_bytes) CU(cudaMemcpyAsync(res->md, C.md.p, o.md_bytes, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    if (trace)
+        fprintf(stderr, "[hsa_b200 trace] sam_se: %zu reads | checks + H2D %.1f ms | device stage %.1f ms (%.2f ms between its first and last kernel; "
+                        "%llu reads with several best hits on the chain%s) | D2H %.1f ms | refined %llu, cigar words %zu, md bytes %zu\n",
+                n_reads, ms_h2d, ms_dev, o.kernel_ms, (unsigned long long)o.n_dependent, o.sequential ? "; SEQUENTIAL selection" : "",
+                since(t_begin) - ms_h2d - ms_dev, (unsigned long long)o.n_refined, o.n_cigar, o.md_bytes);
+    return HSA_OK;
+}
+
+extern "C" int hsa_sam_se_device(const hsa_index_t *ix, const uint8_t *codes_dev, const uint64_t *off_dev, const uint32_t *len_dev, size_t n_reads,
+                                 uint32_t max_len, const int32_t *n_aln_dev, const uint64_t *aln_off_dev, const hsa_aln1_t *aln_dev,
+                                 const hsa_gap_opt_t *opt, int n_occ, uint64_t *rng48_state, void *stream, hsa_sam_device_t *out)
+{
+    if (!ix || !opt || !rng48_state || !out) return fail(HSA_E_ARG, "null argument");
+    memset(out, 0, sizeof(*out));
+    if (n_reads == 0) return HSA_OK;
+    if (!codes_dev || !off_dev || !len_dev || !n_aln_dev || !aln_off_dev || !aln_dev) return fail(HSA_E_ARG, "null argument");
+    if (!ix->sa_value || !ix->blocks4 || !ix->packed_dna)
+        return fail(HSA_E_ARG, "the SAM stage needs the SA samples, the block list and the packed text "
+                               "(hsa_index_attach_sa / _blocks / _packed_dna)");
+    if (n_reads > 0x3FFFFFF0ull || max_len > 4095 || n_occ < 0 || n_occ > 1000) return fail(HSA_E_ARG, "argument out of range");
+    CU(cudaSetDevice(ix->device));
+    hsa_index *mix = const_cast<hsa_index *>(ix);
+    if (!mix->sam_cache) mix->sam_cache = new SamCache();
+    SamCache &C = *mix->sam_cache;
+    SamDeviceOut o;
+    int rc = sam_run_device(ix, C, codes_dev, off_dev, len_dev, n_reads, max_len, n_aln_dev, aln_off_dev, reinterpret_cast<const uint32_t *>(aln_dev),
+                            opt, n_occ, rng48_state, (cudaStream_t)stream, o);
+    if (rc) return rc;
+    out->rec_dev = C.rec.as<hsa_sam1_t>(); out->multi_dev = C.multi.as<hsa_multi1_t>(); out->cigar_dev = C.cigar.as<uint32_t>();
+    out->md_dev = C.md.as<char>();
+    out->n_multi = o.n_multi; out->n_cigar = o.n_cigar; out->md_bytes = o.md_bytes; out->n_refined = o.n_refined; out->n_several_best = o.n_dependent;
+    out->kernel_ms = o.kernel_ms;
     return HSA_OK;
 }
 

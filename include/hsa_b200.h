@@ -273,9 +273,10 @@ int  hsa_splice_match_batch(const hsa_index_t *idx, const uint8_t *codes, const 
  * bwt_aln2pos_splicing / bwt_combine_segment_splice for spliced hits (:197-348), bwa_refine_gapped (:536-638) with
  * refine_gapped_core (:380-440) = aln_global_core (stdaln.c:345-524) + bwa_aln_path2cigar (bwtaln.c:624-634), and
  * bwa_cal_md1 (bwtse.c:442-494).  Needs hsa_index_attach_sa / _blocks / _packed_dna.
- * The selection consumes the reference's process-wide drand48 stream in read order (a sequential chain, evaluated on the
- * host); *rng48_state is that stream's 48-bit state, in and out -- 0 for a process that has not drawn yet (glibc).  Everything
- * after it runs on the GPU: positions, pairing of spliced parts, the banded dynamic programme, CIGAR, MD and NM.
+ * The selection consumes the reference's process-wide drand48 stream in read order; *rng48_state is that stream's 48-bit
+ * state, in and out -- 0 for a process that has not drawn yet (glibc).  Everything runs on the GPU: the selection (reads with
+ * one best hit jump to their place in the stream, reads with several are walked by one thread; hsa_sam.cuh), positions,
+ * pairing of spliced parts, the banded dynamic programme, CIGAR, MD and NM.
  * Inputs: the reads as for hsa_whole_reads, and per read its hits as the driver leaves them in bwa_seq_t::n_aln / aln
  * (hsa_whole_reads' result, with hsa_splice_match_batch's two parts for the reads it rescued); opt: the caller's gap_opt_t
  * as generate_sam_se_core sees it (fnr > 0: max_diff per read length as bwa_cal_pac_pos_core does, else opt->max_diff).
@@ -308,6 +309,22 @@ int  hsa_sam_se_batch(const hsa_index_t *idx, const uint8_t *codes, const uint64
                       const int32_t *n_aln, const uint64_t *aln_off, const hsa_aln1_t *aln, const hsa_gap_opt_t *opt,
                       int n_occ, uint64_t *rng48_state, hsa_sam_result_t *res);
 void hsa_sam_result_free(hsa_sam_result_t *res);
+/* The same stage with reads AND hits resident in HBM (device pointers; e.g. the n_aln / aln_off / aln arrays
+ * hsa_whole_reads_device wrote): nothing crosses PCIe but a few counters.  max_len = the longest read of the batch.  The call
+ * waits for `stream` (cudaStream_t as void*) where it has to size arrays; on return the results are complete and stay on the
+ * device, in library-managed arrays that remain valid until the next SAM call on this index. */
+typedef struct hsa_sam_device_t {
+    const hsa_sam1_t   *rec_dev;        /* [n_reads]  */
+    const hsa_multi1_t *multi_dev;      /* [n_multi]  */
+    const uint32_t     *cigar_dev;      /* [n_cigar]  */
+    const char         *md_dev;         /* [md_bytes] */
+    size_t   n_multi, n_cigar, md_bytes;
+    uint64_t n_refined, n_several_best; /* reads through the dynamic programme; reads whose best score is held by several hits */
+    float    kernel_ms;                 /* first kernel to last kernel, CUDA events on `stream` (sizing syncs included) */
+} hsa_sam_device_t;
+int  hsa_sam_se_device(const hsa_index_t *idx, const uint8_t *codes_dev, const uint64_t *off_dev, const uint32_t *len_dev, size_t n_reads,
+                       uint32_t max_len, const int32_t *n_aln_dev, const uint64_t *aln_off_dev, const hsa_aln1_t *aln_dev,
+                       const hsa_gap_opt_t *opt, int n_occ, uint64_t *rng48_state, void *stream, hsa_sam_device_t *out);
 /* bwa_print_sam1 (bwtse.c:677-835) for single-end reads without qualities, read groups or barcodes: the SAM lines of reads
  * [first, first + count) whose type is not BWA_TYPE_NO_MATCH, as generate_sam_se_core prints them (bwtse.c:922-926).
  * names[r] (NULL: "r<r>"), chr_names[seq_id] = HSP::chrName; mode / max_top2 from the caller's gap_opt_t.  *text_out is a

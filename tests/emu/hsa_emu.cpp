@@ -340,6 +340,9 @@ void emu_phase_stats(uint64_t *runs, uint64_t *lanes) { for (int i = 0; i < 3; +
 uint64_t emu_last_extra(void) { return 0; }
 uint64_t emu_last_steps(void) { return g_last_steps; }
 
+static int g_sel_sequential = 0; static uint32_t g_sel_dependent = 0;
+void emu_sam_set_sequential(int on) { g_sel_sequential = on; }
+uint32_t emu_sam_dependent_reads(void) { return g_sel_dependent; }
 // The SAM-field stage (hsa_sam.cuh) for every read, one after the other: the host selection, sam_pos_item, sam_dp_item.
 // counts_out: {multi slots, cigar words, md bytes, reads refined, status}; returns 0, or -1 when an output array is too small.
 int emu_sam(void *p, const uint32_t *sa_value, uint32_t sa_interval, const uint32_t *blocks4, uint32_t n_blocks,
@@ -349,17 +352,37 @@ int emu_sam(void *p, const uint32_t *sa_value, uint32_t sa_interval, const uint3
             uint64_t *counts_out)
 {
     EmuIndex *e = (EmuIndex *)p;
-    Rng48 rng{*rng_state};
     size_t n_multi = 0; uint32_t max_len = 0, max_ext = 0;
     memset(rec_out, 0, n * sizeof(SamRec));
+    {
+        // the selection, cut into the pieces the kernels run (hsa_sam.cuh): classify, prefix sums, descriptors of the reads
+        // with several best hits, the chain over them, every read's own jump -- or, with g_sel_sequential, the sequential statement
+        std::vector<uint32_t> fixed(n + 1), dep(n + 1), slots(n + 1), vcum(n + 1);
+        std::vector<SelDesc> desc(n + 1); std::vector<SelPick> pick(n + 1);
+        uint64_t x_end = 0; uint32_t rare = 0;
+        SelParams S;
+        memset(&S, 0, sizeof(S));
+        S.n_aln = n_aln; S.aln_off = aln_off; S.aln = aln; S.n_reads = (uint32_t)n; S.n_occ = n_occ;
+        S.fixed = fixed.data(); S.dep = dep.data(); S.slots = slots.data(); S.desc = desc.data(); S.pick = pick.data(); S.vcum = vcum.data();
+        S.rec = rec_out; S.multi = multi_out; S.x0 = *rng_state; S.x_end = &x_end; S.rare = &rare;
+        for (size_t i = 0; i < n; ++i) sel_classify_item(S, (uint32_t)i);
+        auto scan = [&](std::vector<uint32_t> &v) { uint32_t acc = 0; for (size_t i = 0; i <= n; ++i) { const uint32_t t = i < n ? v[i] : 0; v[i] = acc; acc += t; } };
+        scan(fixed); scan(dep); scan(slots);
+        n_multi = slots[n];
+        if (n_multi + 16 > multi_cap) return -1;
+        if (!g_sel_sequential) {
+            for (size_t i = 0; i < n; ++i) sel_desc_item(S, (uint32_t)i);
+            sel_chain(S);
+            for (size_t i = 0; i < n; ++i) sel_finish_item(S, (uint32_t)i);
+        }
+        if (g_sel_sequential || rare) sel_sequential(S);
+        g_sel_dependent = dep[n];
+        *rng_state = x_end;
+    }
     for (size_t i = 0; i < n; ++i) {
-        if (n_multi + 128 + (size_t)n_occ > multi_cap) return -1;
-        rec_out[i].multi_off = (uint32_t)n_multi;
-        n_multi += sam_select(n_aln[i] ? aln + 9 * aln_off[i] : nullptr, n_aln[i], n_occ, rng, rec_out[i], multi_out + n_multi);
         max_len = std::max(max_len, len[i]); max_ext = std::max(max_ext, rec_out[i].n_gapo + rec_out[i].n_gape);
         for (uint32_t j = 0; j < rec_out[i].n_multi; ++j) max_ext = std::max(max_ext, multi_out[rec_out[i].multi_off + j].gap);
     }
-    *rng_state = rng.x;
     SamParams P;
     memset(&P, 0, sizeof(P));
     P.env.ix = e->ix; P.env.sa_value = sa_value; P.env.sa_interval = sa_interval; P.env.blocks4 = blocks4; P.env.n_blocks = n_blocks;

@@ -19,7 +19,7 @@ import emu_lib as el
 import oracle_lib as ol
 import sam_common as sc
 from hsa_b200 import api, synth, synth_torch
-from test_sam_emu import CASES, GoldenSam
+from test_sam_emu import CASES, GoldenSam, _fabricated_hits
 
 pytestmark = pytest.mark.gpu
 
@@ -128,6 +128,29 @@ def test_arena_overflow_is_retried_not_truncated(gs, index, monkeypatch):
     na, off, a9 = sc.hits_input(n_aln, rows)
     res = index.sam_se(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, na, off, a9, _opt(c["opt"]), n_occ=c["n_occ"])
     assert not sc.diff(sc.unpack_result(res.rec, res.multi, res.cigar, res.md), want)
+
+
+@pytest.mark.parametrize("sequential", ["0", "1"], ids=["cut_selection", "sequential_statement_on_one_thread"])
+def test_selection_with_many_best_score_ties(gs, index, sequential, monkeypatch):
+    """Hit lists full of ties for the best score (the data-dependent part of the drand48 stream): the kernels' cut selection
+    (prefix sums, LCG jumps, one chain over the reads with several best hits) and the fallback that runs the sequential
+    statement on one device thread both equal the host build of the sequential statement, stream state included."""
+    import ctypes as C
+    monkeypatch.setenv("HSA_B200_SAM_SEQUENTIAL", sequential)
+    n = 3000
+    rs = synth.simulate_reads(gs.base.genome, n, 100, 51)
+    emu = el.Emu(gs.base.index())
+    n_aln, rows = _fabricated_hits(n, int(gs.base.genome.shape[0]), 1, emu)
+    na, off, a9 = sc.hits_input(n_aln, rows)
+    try:
+        el.lib().emu_sam_set_sequential(C.c_int(1))
+        want, want_state, _ = sc.emu_sam(emu, rs, na, off, a9, ol.default_opt(), n_occ=3, rng_state=0x1234ABCD330E)
+    finally:
+        el.lib().emu_sam_set_sequential(C.c_int(0))
+    res = index.sam_se(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, na, off, a9, _opt({}), n_occ=3, rng48_state=0x1234ABCD330E)
+    assert res.rng48_state == want_state
+    bad = sc.diff(sc.unpack_result(res.rec, res.multi, res.cigar, res.md), want)
+    assert not bad, "\n".join(bad)
 
 
 def test_rng_state_chains_batches(gs, index):

@@ -107,3 +107,73 @@ def test_sam_fields_vs_reference_live(gs, emu, seed, length, okw):
     got, _, _ = sc.emu_sam(emu, rs, na, off, a9, opt)
     bad = sc.diff(got, want)
     assert not bad, "\n".join(bad)
+
+
+def _fabricated_hits(n_reads, text_length, seed, emu):
+    """Hit lists with many ties for the best score (several intervals of widths 1..3 at one score), which i.i.d.-genome searches
+    rarely produce: the data-dependent part of the drand48 stream.  Intervals are drawn from SA indices whose suffixes start at
+    least 200 bases before the end of the text (a real full-length hit cannot hang over the end; MD would read past it)."""
+    rng = np.random.default_rng(seed)
+    cand = rng.integers(1, text_length - 4, size=40 * n_reads).astype(np.uint32)
+    ok = np.ones(cand.shape[0], dtype=bool)
+    for d in range(3):
+        ok &= emu.sa_values(cand + d)[0] < text_length - 200
+    pool = cand[ok]
+    n_aln = rng.integers(0, 6, size=n_reads).astype(np.int32)
+    rows = []
+    for c in n_aln.tolist():
+        if c == 0:
+            continue
+        m = int(rng.integers(1, c + 1))                      # hits sharing the best score
+        best = int(rng.integers(0, 4)) * 3
+        for j in range(c):
+            k = int(pool[int(rng.integers(0, pool.shape[0]))]); w = int(rng.integers(1, 4))
+            score = best if j < m else best + 3 * int(rng.integers(1, 3))
+            rows.append([score // 3, 0, 0, k, k + w - 1, 0, 0, 0, int(rng.integers(0, 2)), 0, 99 if j == 0 else 0, score])
+    return n_aln, np.asarray(rows, dtype=np.uint32).reshape(-1, 12)
+
+
+@pytest.mark.parametrize("seed,n_occ", [(1, 3), (2, 0), (3, 8)])
+def test_cut_selection_equals_the_sequential_statement(gs, emu, seed, n_occ):
+    """The selection as the kernels run it (prefix sums + LCG jumps for reads with one best hit, a single chain over the reads
+    with several) against sam_select, the read-after-read statement, on hit lists full of best-score ties: same records, same
+    stream state at the end."""
+    import ctypes as C
+    n = 3000
+    rs = synth.simulate_reads(gs.base.genome, n, 100, 50 + seed)
+    n_aln, rows = _fabricated_hits(n, int(gs.base.genome.shape[0]), seed, emu)
+    na, off, a9 = sc.hits_input(n_aln, rows)
+    out = {}
+    try:
+        for seq in (1, 0):
+            el.lib().emu_sam_set_sequential(C.c_int(seq))
+            got, state, _ = sc.emu_sam(emu, rs, na, off, a9, ol.default_opt(), n_occ=n_occ, rng_state=0x1234ABCD330E)
+            out[seq] = (got, state)
+        el.lib().emu_sam_dependent_reads.restype = C.c_uint32
+        assert el.lib().emu_sam_dependent_reads() > 500          # the chain over reads with several best hits is really walked
+    finally:
+        el.lib().emu_sam_set_sequential(C.c_int(0))
+    assert out[0][1] == out[1][1] and not sc.diff(out[0][0], out[1][0])
+    assert sum(1 for g in out[0][0] if g[0]["type"] == 2) > 500
+
+
+def test_rng48_jump_is_n_single_steps():
+    """Rng48::jump (hsa_sam.cuh) against n applications of drand48's recurrence, python integers."""
+    A, Cc, M = 0x5DEECE66D, 0xB, (1 << 48) - 1
+    def jump(x, n):
+        ca, cc, aa, ac = A, Cc, 1, 0
+        while n:
+            if n & 1:
+                aa, ac = (aa * ca) & ((1 << 64) - 1), (ac * ca + cc) & ((1 << 64) - 1)
+            cc, ca = ((ca + 1) * cc) & ((1 << 64) - 1), (ca * ca) & ((1 << 64) - 1)
+            n >>= 1
+        return (aa * x + ac) & M
+    for x0 in (0, 0x1234ABCD330E, M):
+        x = x0
+        for n in range(1, 300):
+            x = (x * A + Cc) & M
+            assert jump(x0, n) == x
+    x = 0
+    for _ in range(100000):
+        x = (x * A + Cc) & M
+    assert jump(0, 100000) == x

@@ -1,0 +1,101 @@
+"""GPU-box measurement of the SAM-field stage (hsa_sam_se_batch).
+
+One step = what generate_sam_se_core (bwtse.c:884) computes for a batch before it prints, through the host-buffer C ABI: the
+drand48-ordered hit selection on the host, H2D of reads + hits, sam_pos_kernel + sam_dp_kernel, D2H of the records / CIGARs / MD
+strings.  Workload: 46 Mb genome with planted introns, N simulated 100 bp reads (indels in 5 %, 2 % across introns), hits produced
+by the library's own searches (hsa_whole_reads, then hsa_splice_match_batch for the reads that found nothing).
+Reported: reads/s of the stage (wall clock of the call), the two kernels' device time, and -- on the first `--sample` reads --
+parity against the reference program (oracle/_ref/hsa_ref `driver` hits -> hsa_sam_se_batch vs `sam` mode's dump) with the
+reference's own generate_sam_se_core time on one host core.
+    python tools/bench_sam.py [--genome 46000003] [--n 2000000] [--sample 100000]"""
+import argparse, json, os, subprocess, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+from hsa_b200 import api, build, index_build, index_io, synth, synth_torch
+
+
+def search_hits(ix, rs, opt):
+    """(n_aln, aln_off, aln9) for the whole set from the GPU searches."""
+    off = rs.offsets[:-1].astype(np.uint64)
+    res = ix.whole_reads(rs.codes, off, rs.lens, opt)
+    n_aln, aln_off, aln = res.n_aln.astype(np.int32), res.aln_off.astype(np.uint64), res.aln
+    miss = np.flatnonzero(n_aln == 0)
+    if miss.shape[0]:
+        L = int(rs.lens[0])
+        codes = rs.codes.reshape(-1, L)[miss]
+        keep = ~((codes > 3).sum(1) > 5) & codes[:, :15].any(1) & ~(codes[:, :15] == 3).all(1)
+        miss, codes = miss[keep], np.ascontiguousarray(codes[keep]).reshape(-1)
+        lo = api.GapOpt.from_buffer_copy(bytes(opt))
+        lo.max_diff = api.bwa_cal_maxdiff(L, 0.02, opt.fnr)
+        lo.max_gapo = min(lo.max_gapo, lo.max_diff)
+        sn, sa = ix.splice_match(codes, (np.arange(miss.shape[0], dtype=np.uint64) * L), np.full(miss.shape[0], L, np.uint32), lo)
+        got = np.flatnonzero(sn == 2)
+        base = aln.shape[0]
+        aln = np.concatenate([aln, sa[got].reshape(-1, 9)])
+        n_aln[miss[got]] = 2
+        aln_off[miss[got]] = base + 2 * np.arange(got.shape[0], dtype=np.uint64)
+    return n_aln, aln_off, np.ascontiguousarray(aln)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--genome", type=int, default=46_000_003)
+    ap.add_argument("--n", type=int, default=2_000_000)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--sample", type=int, default=100_000)
+    a = ap.parse_args()
+    build.build_native()
+    dev = torch.device("cuda", 0)
+    genome = synth_torch.make_genome(a.genome, 5, dev)
+    introns = synth_torch.plant_introns(genome, 2000, 6)
+    host = index_build.build_full_index(genome, device=dev)
+    ix = api.Index.upload(host, 0)
+    n_j = a.n // 50
+    reads = torch.cat([synth_torch.simulate_reads(genome, a.n - n_j, 100, 91), synth_torch.simulate_junction_reads(genome, introns, n_j, 100, 92)])
+    reads = reads[torch.randperm(reads.shape[0], generator=torch.Generator().manual_seed(3)).to(reads.device)].cpu().numpy()
+    rs = synth.ReadSet(np.full(a.n, 100, dtype=np.uint32), np.ascontiguousarray(reads).reshape(-1))
+    opt = api.gap_init_opt()
+    n_aln, aln_off, aln9 = search_hits(ix, rs, opt)
+    off = rs.offsets[:-1].astype(np.uint64)
+    best, res = None, None
+    for _ in range(1 + a.steps):
+        t0 = time.perf_counter()
+        res = ix.sam_se(rs.codes, off, rs.lens, n_aln, aln_off, aln9, opt, copy=False, into=res)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    types = np.bincount(res.rec[:, 0], minlength=5)
+    line = {"metric": "sam_records_per_sec", "value": a.n / best, "unit": "reads/s", "n": a.n, "ms_per_step": best * 1e3,
+            "kernel_ms": res.kernel_ms, "kernels": "sam_pos_kernel + sam_dp_kernel (CUDA events around both)",
+            "genome_bp": a.genome, "matched": int(a.n - types[0]), "refined_by_dp": res.n_refined, "spliced": int(types[4]),
+            "cigar_words": int(res.cigar.shape[0]), "md_bytes": res.md_bytes, "alternative_hits": int(res.multi.shape[0]),
+            "path": "hsa_sam_se_batch from host buffers: drand48-ordered selection on the host, H2D, two kernels, D2H"}
+    ref = os.path.join(ROOT, "oracle", "_ref", "hsa_ref")
+    if os.path.exists(ref) and a.sample:
+        import sam_common as sc
+        with tempfile.TemporaryDirectory() as td:
+            prefix = os.path.join(td, "g")
+            index_io.save_index(host, prefix)
+            sub = rs.subset(0, a.sample)
+            rp = os.path.join(td, "r.reads")
+            synth.write_reads_bin(rp, sub)
+            j = json.loads(subprocess.run([ref, "sam", prefix, rp, rp + ".bin", rp + ".sam"], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
+            subprocess.run([ref, "driver", prefix, rp, rp + ".aln"], check=True, capture_output=True)
+            rn, rrows = synth.read_aln_dump(rp + ".aln")
+            want = sc.parse_ref_dump(rp + ".bin")
+            na, ao, a9 = sc.hits_input(rn, rrows)
+            r2 = ix.sam_se(sub.codes, sub.offsets[:-1].astype(np.uint64), sub.lens, na, ao, a9, opt)
+            got = sc.unpack_result(r2.rec, r2.multi, r2.cigar, r2.md)
+            bad = sum(1 for g, w in zip(got, want) if g != w)
+            o2 = api.GapOpt.from_buffer_copy(bytes(opt)); o2.mode &= ~1
+            r2._opt = o2
+            same_text = sc.printable_lines(r2.format(["synth"])) == sc.printable_lines(open(rp + ".sam", "rb").read())
+            line["parity"] = {"reads": a.sample, "record_mismatch": bad, "sam_text_identical": bool(same_text)}
+            line["cpu_baseline"] = {"value": a.sample / j["secs_sam"], "unit": "reads/s", "cores": 1, "kind": "reference",
+                                    "sample": f"generate_sam_se_core on the first {a.sample} reads of the set, one process (the reference has no threading)"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
