@@ -465,9 +465,17 @@ def main():
             torch.cuda.synchronize()
 
     # ---- the drop-in inside the reference program (N = 1), before this process fills the GPU and pins host memory ----
-    dropin = None
+    dropin, sam_stage = None, None
     if world == 1 and not args.no_secondary and not args.no_cpu_baseline:
         dropin = dropin_block(dev, args)
+        torch.cuda.empty_cache()
+        # the stage after the search on its own: tools/bench_sam.py, 46 Mb genome, 2 M reads
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_sam
+            sam_stage = bench_sam.measure(argparse.Namespace(genome=46_000_003, n=2_000_000, steps=3, sample=100_000))
+        except Exception as e:                                  # a side block must never take the headline measurement down
+            sam_stage = {"unavailable": repr(e)[:300]}
         torch.cuda.empty_cache()
 
     # ---- index: built once on rank 0 (torch ops on the GPU), broadcast as device blocks over NCCL ----
@@ -659,7 +667,7 @@ def main():
                             + ("; every batch's results gathered to rank 0 in input order through host shared memory "
                                "(shard.HostGather: no GPU kernels, so nothing queues behind the persistent search kernels)" if world > 1 else "")},
             "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity": parity, "secondary": secondary, "dropin": dropin,
+            "cpu_baseline": cpu_baseline, "parity": parity, "secondary": secondary, "dropin": dropin, "sam_stage": sam_stage,
             "aligned_fraction": aligned_all / args.reads_total,
             "heavy_searches_handed_to_cooperative_kernel": heavy_all,
             "index_build_secs": index_build_secs, "index_broadcast": bcast}

@@ -153,6 +153,7 @@ def lib():
     L.hsa_sam_se_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(GapOpt), C.c_int, C.POINTER(C.c_uint64), C.POINTER(_SamResult)]
     L.hsa_sam_result_free.argtypes = [C.POINTER(_SamResult)]
+    L.hsa_copy_from_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.hsa_sam_se_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(GapOpt), C.c_int, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(_SamDevice)]
     L.hsa_sam_format.argtypes = [C.POINTER(_SamResult), C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -364,6 +365,12 @@ class Index:
             lib().hsa_sam_result_free(C.byref(res))
             _check(rc)
         return SamResult(res, st.value, (cp[1], op[1], lp[1]), opt, copy)
+
+    def copy_from_device(self, ptr: int, shape, dtype) -> np.ndarray:
+        """numpy copy of a device array the library returned a raw pointer to."""
+        out = np.zeros(shape, dtype=dtype)
+        _check(lib().hsa_copy_from_device(self._h, out.ctypes.data, ptr, out.nbytes))
+        return out
 
     def sam_se_device(self, codes_ptr: int, off_ptr: int, len_ptr: int, n_reads: int, max_len: int, n_aln_ptr: int, aln_off_ptr: int,
                       aln_ptr: int, opt: GapOpt, n_occ: int = 3, rng48_state: int = 0, stream_ptr: int = 0):

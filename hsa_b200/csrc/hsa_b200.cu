@@ -1311,6 +1311,26 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
                              : (size_t)P.smem_stats_off + 5 * sizeof(unsigned long long);
     const void *fn = search_fn(v, (int)block, ws->minb);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // experiment knob (north_star: "L2 persisting-access window"): HSA_B200_L2_PERSIST=1 marks the forward direction's blocks as
+        // persisting in L2 for the kernels of this stream when they fit the device's persisting carve-out (the 46 Mb index: 23 MB)
+        static const long persist = env_long("HSA_B200_L2_PERSIST", 0);
+        if (persist) {
+            cudaDeviceProp prop;
+            CU(cudaGetDeviceProperties(&prop, ix->device));
+            const size_t bytes = (size_t)ix->ix.fwd.n_blocks * 32;
+            if (bytes <= (size_t)prop.persistingL2CacheMaxSize && bytes <= (size_t)prop.accessPolicyMaxWindowSize) {
+                CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes + (8u << 20))));
+                cudaStreamAttrValue av;
+                memset(&av, 0, sizeof(av));
+                av.accessPolicyWindow.base_ptr = const_cast<u32x4 *>(ix->ix.fwd.blocks);
+                av.accessPolicyWindow.num_bytes = bytes;
+                av.accessPolicyWindow.hitRatio = 1.0f;
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                CU(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+            }
+        }
+    }
     {   // experiment knob: shared-memory carve-out in percent of the SM's unified L1/shared array (-1 = driver default)
         static const long carve = env_long("HSA_B200_CARVEOUT", -1);
         if (carve >= 0 && v <= V_FAST_ROWS) CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)carve));

@@ -3,8 +3,8 @@
 //
 // Compiled by nvcc for sm_100a (sam_pos_kernel / sam_dp_kernel in hsa_b200.cu) and by g++ for tests/emu (CPU suite only).
 //
-//   bwt_aln2seq_core                 bwtse.c:21-113     host (select_hits below): it consumes the process-wide drand48
-//                                                       stream in read order, a sequential chain by definition
+//   bwt_aln2seq_core                 bwtse.c:21-113     hit selection on the process-wide drand48 stream, cut where the stream
+//                                                       allows it (sel_* below; sam_select is the sequential statement)
 //   bwa_approx_mapQ                  bwtse.c:122-131    with g_log_n all zero (bwase_initialize is never called, :892)
 //   bwa_cal_pac_pos[_core]           bwtse.c:139-149, 350-369   SA index -> text position of the chosen hit and of the
 //                                                       alternative hits, which are dropped where they coincide with it
@@ -17,7 +17,7 @@
 //   bwa_refine_gapped                bwtse.c:536-638    which hits are refined; merging the two parts of a spliced hit
 //   bwa_cal_md1                      bwtse.c:442-494    MD string and NM
 //
-// Work split: sam_pos (every read: positions, mapQ, pairing; MD directly when no alignment has to be refined; the reads
+// Work split: sel_* (the selection), sam_pos (every read: positions, mapQ, pairing; MD directly when no alignment has to be refined; the reads
 // that need the dynamic programme are appended to a list) and sam_dp (one listed read per thread: every refinement of the
 // read, then its MD).  The DP keeps ONE score row in place (the reference's curr/last pair collapses to a row plus the
 // carried diagonal) and one byte of trace-back per cell; a thread's scratch is interleaved with its neighbours' (element

@@ -265,6 +265,14 @@ extern "C" int hsa_sam_se_batch(const hsa_index_t *ix, const uint8_t *codes, con
     return HSA_OK;
 }
 
+extern "C" int hsa_copy_from_device(const hsa_index_t *ix, void *dst_host, const void *src_dev, size_t bytes)
+{
+    if (!ix || (bytes && (!dst_host || !src_dev))) return fail(HSA_E_ARG, "null argument");
+    CU(cudaSetDevice(ix->device));
+    if (bytes) CU(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+    return HSA_OK;
+}
+
 extern "C" int hsa_sam_se_device(const hsa_index_t *ix, const uint8_t *codes_dev, const uint64_t *off_dev, const uint32_t *len_dev, size_t n_reads,
                                  uint32_t max_len, const int32_t *n_aln_dev, const uint64_t *aln_off_dev, const hsa_aln1_t *aln_dev,
                                  const hsa_gap_opt_t *opt, int n_occ, uint64_t *rng48_state, void *stream, hsa_sam_device_t *out)

@@ -322,6 +322,9 @@ typedef struct hsa_sam_device_t {
     uint64_t n_refined, n_several_best; /* reads through the dynamic programme; reads whose best score is held by several hits */
     float    kernel_ms;                 /* first kernel to last kernel, CUDA events on `stream` (sizing syncs included) */
 } hsa_sam_device_t;
+/* plain cudaMemcpy device -> host on the index's device, for callers without a CUDA runtime of their own (ctypes / cgo) that
+ * want to look at device-resident results */
+int  hsa_copy_from_device(const hsa_index_t *idx, void *dst_host, const void *src_dev, size_t bytes);
 int  hsa_sam_se_device(const hsa_index_t *idx, const uint8_t *codes_dev, const uint64_t *off_dev, const uint32_t *len_dev, size_t n_reads,
                        uint32_t max_len, const int32_t *n_aln_dev, const uint64_t *aln_off_dev, const hsa_aln1_t *aln_dev,
                        const hsa_gap_opt_t *opt, int n_occ, uint64_t *rng48_state, void *stream, hsa_sam_device_t *out);

@@ -153,6 +153,29 @@ def test_selection_with_many_best_score_ties(gs, index, sequential, monkeypatch)
     assert not bad, "\n".join(bad)
 
 
+@pytest.mark.parametrize("name", ["dna_and_junctions", "ragged_nocc6"])
+def test_device_resident_entry_point(gs, index, name):
+    """hsa_sam_se_device: reads and hits as device tensors (what hsa_whole_reads_device leaves in HBM), results left on the
+    device -- fetched here only to compare them with the goldens."""
+    c, rs, n_aln, rows, want = gs.case(name)
+    na, off, a9 = sc.hits_input(n_aln, rows)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    codes = torch.cat([t(rs.codes), torch.zeros(16, dtype=torch.uint8, device=dev)])
+    roff, rlen = t(rs.offsets[:-1].astype(np.int64)), t(rs.lens.astype(np.int32))
+    dna, dao, da9 = t(na), t(off.astype(np.int64)), t(a9.view(np.int32))
+    torch.cuda.synchronize()
+    out, state = index.sam_se_device(codes.data_ptr(), roff.data_ptr(), rlen.data_ptr(), rs.n, int(rs.lens.max()), dna.data_ptr(),
+                                     dao.data_ptr(), da9.data_ptr(), _opt(c["opt"]), n_occ=c["n_occ"])
+    rec = index.copy_from_device(out.rec_dev, (rs.n, api.SAM_REC_WORDS), np.uint32)
+    multi = index.copy_from_device(out.multi_dev, (out.n_multi, api.SAM_MULTI_WORDS), np.uint32)
+    cigar = index.copy_from_device(out.cigar_dev, (out.n_cigar,), np.uint32)
+    md = index.copy_from_device(out.md_dev, (out.md_bytes,), np.uint8).tobytes()
+    bad = sc.diff(sc.unpack_result(rec, multi, cigar, md), want)
+    assert not bad, "\n".join(bad)
+    assert out.n_refined >= c["with_cigar"] and out.kernel_ms > 0
+
+
 def test_rng_state_chains_batches(gs, index):
     c, rs, n_aln, rows, want = gs.case("repeats_75")
     half = rs.n // 2
