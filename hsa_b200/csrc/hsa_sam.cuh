@@ -347,6 +347,9 @@ HSA_HD int32_t dp_global(const DpScratch &S, int32_t len1, int32_t len2, const S
     if (len1 > len2) { b1 = len1 - len2 + DP_BAND; b2 = DP_BAND; } else { b1 = DP_BAND; b2 = len2 - len1 + DP_BAND; }
     if (b1 > len1) b1 = len1;
     if (b2 > len2) b2 = len2;
+    // the trace-back rows hold b1 + b2 + 1 cells (:380); a reference window clipped at the end of the text (len1 < len2) makes
+    // the band wider than the batch's scratch was sized for: the caller runs the batch again with full-width rows
+    if ((uint32_t)((b1 + b2 <= len1) ? b1 + b2 + 1 : len1 + 1) > S.W) { n_runs = -1; return 0; }
     // first row (:386-391)
     S.row(0, 0) = 0; S.row(0, 1) = DP_INF; S.row(0, 2) = DP_INF;
     {
@@ -408,6 +411,7 @@ HSA_HD bool sam_refine(const SamParams &P, const DpScratch &S, int32_t len, cons
     for (uint32_t k = pos; k < pos + (uint32_t)ref_len && k < E.dna_length; ++k) S.refb(++l) = (uint8_t)sam_dna_at(E, k);
     int32_t n_runs;
     dp_global(S, l, len, q, n_runs);
+    if (n_runs < 0) { sam_fail(P, SAM_SCRATCH); return false; }
     if (n_runs == 0) { n_cigar_out = 0; cigar_off_out = 0; return true; }           // (the reference dereferences NULL here)
     // runs are stored last-first: run(n_runs - 1 - k) is cigar[k]
     int32_t first = 0, n = n_runs;                    // cigar[k] = run(n_runs - 1 - first - k), k < n

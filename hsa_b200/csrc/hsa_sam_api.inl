@@ -156,7 +156,8 @@ static int sam_run_device(const hsa_index_t *ix, SamCache &C, const uint8_t *cod
     size_t cigar_cap = tiny ? 16 : 4096, md_cap = tiny ? 64 : n_reads * 16 + 4096;
     const uint32_t max_ext = h_gaps;
     unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
-    for (int attempt = 0; attempt < 6; ++attempt) {
+    bool wide = false;                                               // full-width trace-back rows (a window clipped at the text's end)
+    for (int attempt = 0; attempt < 7; ++attempt) {
         if (C.md.alloc(md_cap)) return fail(HSA_E_CUDA, "out of device memory for the SAM batch");
         P.cigar = nullptr; P.cigar_cap = 0; P.md = C.md.as<char>(); P.md_cap = md_cap;
         CU(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), s));
@@ -174,7 +175,7 @@ static int sam_run_device(const hsa_index_t *ix, SamCache &C, const uint8_t *cod
         if (n_dp) {
             // scratch: (len2 + 1) rows of W trace-back bytes + len1 reference bases + 3 x (len1 + 1) score words per worker
             const uint32_t len1_cap = max_len + max_ext, len2_cap = max_len;
-            const uint32_t W = std::min<uint32_t>(2u * DP_BAND + max_ext + 1u, len1_cap + 1u);
+            const uint32_t W = wide ? len1_cap + 1u : std::min<uint32_t>(2u * DP_BAND + max_ext + 1u, len1_cap + 1u);
             const size_t per_bytes = (size_t)(len2_cap + 1u) * W + len1_cap + 1u, per_rows = std::max<size_t>(3 * ((size_t)len1_cap + 1), (size_t)len1_cap + len2_cap + 2);
             // 80 registers: six blocks of 128 per SM; scratch capped at 2 GB (fewer workers for long reads)
             uint32_t workers = (uint32_t)std::min<size_t>({(size_t)n_dp, (size_t)ix->sm_count * 768, std::max<size_t>(128, ((size_t)2 << 30) / (per_bytes + 4 * per_rows))});
@@ -189,9 +190,13 @@ static int sam_run_device(const hsa_index_t *ix, SamCache &C, const uint8_t *cod
         CU(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         const uint32_t status = (uint32_t)(h[4] & 0xFFFFFFFFull);
-        if (status == SAM_SCRATCH) return fail(HSA_E_CAPACITY, "an alignment exceeded the DP scratch (gap count beyond the batch's maximum)");
+        if (status == SAM_SCRATCH) {
+            if (wide) return fail(HSA_E_CAPACITY, "an alignment exceeded the DP scratch (gap count beyond the batch's maximum)");
+            wide = true;
+            continue;
+        }
         if (h[0] <= cigar_cap && h[1] <= md_cap && status == SAM_OK) break;
-        if (attempt == 5) return fail(HSA_E_CAPACITY, "CIGAR / MD arenas overflowed repeatedly");
+        if (attempt == 6) return fail(HSA_E_CAPACITY, "CIGAR / MD arenas overflowed repeatedly");
         if (h[0] > cigar_cap || status == SAM_CIGAR_FULL) cigar_cap = std::max<size_t>(4 * cigar_cap, 2 * (size_t)h[0]);
         if (h[1] > md_cap || status == SAM_MD_FULL) md_cap = std::max<size_t>(4 * md_cap, 2 * (size_t)h[1]);
     }

@@ -824,6 +824,37 @@ static int mode_sam(int argc, char **argv)
     return 0;
 }
 
+
+/* ---------------------------------------------------------------- dp
+ * aln_global_core (stdaln.c:345) + bwa_aln_path2cigar (bwtaln.c:624) with aln_param_bwa, as refine_gapped_core calls them
+ * (bwtse.c:398-399), on arbitrary (reference window, read) pairs: in = n, then per pair {len1, len2, len1 + len2 bytes};
+ * out = n, then per pair {score, n_cigar, cigar words}. */
+#include "stdaln.h"
+bwa_cigar_t *bwa_aln_path2cigar(const path_t *path, int path_len, int *n_cigar);
+static int mode_dp(int argc, char **argv)
+{
+    FILE *fi, *fo; uint32_t n, i;
+    if (argc < 4) die("usage: dp <pairs.bin> <out.bin>");
+    fi = fopen(argv[2], "rb"); fo = fopen(argv[3], "wb");
+    if (!fi || !fo || fread(&n, 4, 1, fi) != 1) die("dp: cannot open files");
+    fwrite(&n, 4, 1, fo);
+    for (i = 0; i < n; ++i) {
+        uint32_t len[2]; ubyte_t *a, *b; path_t *path; int path_len = 0, n_cigar = 0, score; bwa_cigar_t *cigar; AlnParam ap = aln_param_bwa;
+        if (fread(len, 4, 2, fi) != 2) die("dp: short input");
+        a = (ubyte_t*)calloc(len[0] + 1, 1); b = (ubyte_t*)calloc(len[1] + 1, 1);
+        if (fread(a, 1, len[0], fi) != len[0] || fread(b, 1, len[1], fi) != len[1]) die("dp: short input");
+        path = (path_t*)calloc(len[0] + len[1] + 2, sizeof(path_t));
+        score = aln_global_core(a, (int)len[0], b, (int)len[1], &ap, path, &path_len);
+        cigar = path_len ? bwa_aln_path2cigar(path, path_len, &n_cigar) : NULL;
+        fwrite(&score, 4, 1, fo); fwrite(&n_cigar, 4, 1, fo);
+        if (n_cigar) fwrite(cigar, 4, n_cigar, fo);
+        free(cigar); free(path); free(a); free(b);
+    }
+    fclose(fi); fclose(fo);
+    printf("{\"mode\":\"dp\",\"pairs\":%u}\n", n);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc < 2) die("usage: hsa_ref <index|occ|width|percall|seeds|driver|whole|dumpindex|maxdiff> ...");
@@ -840,6 +871,7 @@ int main(int argc, char **argv)
     if (strcmp(argv[1], "seeds") == 0) return mode_seeds(argc, argv);
     if (strcmp(argv[1], "driver") == 0) return mode_driver(argc, argv);
     if (strcmp(argv[1], "sam") == 0) return mode_sam(argc, argv);
+    if (strcmp(argv[1], "dp") == 0) return mode_dp(argc, argv);
 #ifdef HSA_WITH_GPU_SHIM
     if (strcmp(argv[1], "gpudriver") == 0) {
         /* the same batch loop with bwa_cal_sa_reg_gap replaced by the GPU shim (needs a full index: the splice

@@ -340,6 +340,24 @@ void emu_phase_stats(uint64_t *runs, uint64_t *lanes) { for (int i = 0; i < 3; +
 uint64_t emu_last_extra(void) { return 0; }
 uint64_t emu_last_steps(void) { return g_last_steps; }
 
+// dp_global (hsa_sam.cuh) on one (reference window, read) pair: score and the CIGAR in path order (op << 28 | len), as
+// aln_global_core + bwa_aln_path2cigar return them; returns n_cigar, or -1 if the band does not fit W
+int emu_dp(const uint8_t *ref, int32_t len1, const uint8_t *read, int32_t len2, uint32_t W, int32_t *score_out, uint32_t *cigar_out)
+{
+    std::vector<uint8_t> bytes((size_t)(len2 + 1) * W + len1 + 2);
+    std::vector<int32_t> rows(std::max<size_t>(3 * ((size_t)len1 + 1), (size_t)len1 + len2 + 2) + 8);
+    DpScratch S;
+    S.T = 1; S.W = W; S.len1_cap = (uint32_t)len1; S.len2_cap = (uint32_t)len2;
+    S.cells = bytes.data(); S.ref = bytes.data() + (size_t)(len2 + 1) * W; S.rows = rows.data();
+    for (int32_t i = 0; i < len1; ++i) S.refb(i + 1) = ref[i];
+    const SamRead q{read, (uint32_t)len2, 0u, 0u};
+    int32_t n_runs = 0;
+    *score_out = dp_global(S, len1, len2, q, n_runs);
+    if (n_runs < 0) return -1;
+    for (int32_t k = 0; k < n_runs; ++k) cigar_out[k] = (uint32_t)S.run(n_runs - 1 - k);
+    return n_runs;
+}
+
 static int g_sel_sequential = 0; static uint32_t g_sel_dependent = 0;
 void emu_sam_set_sequential(int on) { g_sel_sequential = on; }
 uint32_t emu_sam_dependent_reads(void) { return g_sel_dependent; }
@@ -394,12 +412,18 @@ int emu_sam(void *p, const uint32_t *sa_value, uint32_t sa_interval, const uint3
     std::vector<uint32_t> list(n + 1);
     P.cigar = cigar_out; P.cigar_cap = cigar_cap; P.cigar_used = cnt; P.md = md_out; P.md_cap = md_cap; P.md_used = cnt + 1;
     P.dp_list = list.data(); P.dp_count = cnt + 2; P.cursor = cnt + 3; P.status = &status; P.dp_tasks = cnt + 5;
-    for (size_t i = 0; i < n; ++i) sam_pos_item(P, (uint32_t)i);
-    const uint32_t len1_cap = max_len + max_ext, len2_cap = max_len, W = std::min<uint32_t>(2u * DP_BAND + max_ext + 1u, len1_cap + 1u);
-    std::vector<uint8_t> bytes((size_t)(len2_cap + 1u) * W + len1_cap + 1u);
-    std::vector<int32_t> rows(std::max<size_t>(3 * ((size_t)len1_cap + 1), (size_t)len1_cap + len2_cap + 2));
-    P.dp_bytes = bytes.data(); P.dp_rows = rows.data(); P.dp_workers = 1; P.dp_w = W; P.dp_len1_cap = len1_cap; P.dp_len2_cap = len2_cap;
-    for (unsigned long long w = 0; w < cnt[2]; ++w) sam_dp_item(P, list[w], 0);
+    // (a reference window clipped at the end of the text needs full-width trace-back rows: second pass, as the library does)
+    std::vector<SamRec> rec0(rec_out, rec_out + n); std::vector<SamMulti> multi0(multi_out, multi_out + n_multi);
+    for (int wide = 0; wide < 2; ++wide) {
+        if (wide) { memcpy(rec_out, rec0.data(), n * sizeof(SamRec)); memcpy(multi_out, multi0.data(), n_multi * sizeof(SamMulti)); memset(cnt, 0, sizeof(cnt)); status = 0; }
+        for (size_t i = 0; i < n; ++i) sam_pos_item(P, (uint32_t)i);
+        const uint32_t len1_cap = max_len + max_ext, len2_cap = max_len, W = wide ? len1_cap + 1u : std::min<uint32_t>(2u * DP_BAND + max_ext + 1u, len1_cap + 1u);
+        std::vector<uint8_t> bytes((size_t)(len2_cap + 1u) * W + len1_cap + 1u);
+        std::vector<int32_t> rows(std::max<size_t>(3 * ((size_t)len1_cap + 1), (size_t)len1_cap + len2_cap + 2));
+        P.dp_bytes = bytes.data(); P.dp_rows = rows.data(); P.dp_workers = 1; P.dp_w = W; P.dp_len1_cap = len1_cap; P.dp_len2_cap = len2_cap;
+        for (unsigned long long w = 0; w < cnt[2]; ++w) sam_dp_item(P, list[w], 0);
+        if (status != SAM_SCRATCH) break;
+    }
     counts_out[0] = n_multi; counts_out[1] = cnt[0]; counts_out[2] = cnt[1]; counts_out[3] = cnt[2]; counts_out[4] = status;
     return (cnt[0] > cigar_cap || cnt[1] > md_cap) ? -1 : 0;
 }

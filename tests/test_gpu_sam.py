@@ -176,6 +176,30 @@ def test_device_resident_entry_point(gs, index, name):
     assert out.n_refined >= c["with_cigar"] and out.kernel_ms > 0
 
 
+def test_window_clipped_at_the_end_of_the_text(gs, index):
+    """A gapped hit whose reference window runs past the end of the text: refine_gapped_core clips the window (bwtse.c:393-394), the
+    band gets wider than the batch's scratch rows, and the library runs the batch again with full-width rows.  GPU == the host
+    build of the same code (which tests/test_sam_emu.py pins to aln_global_core on such geometries)."""
+    emu = el.Emu(gs.base.index())
+    n_text = int(gs.base.genome.shape[0])
+    cand = np.arange(1, 60000, dtype=np.uint32)
+    pos = emu.sa_values(cand)[0]
+    ks = cand[(pos > n_text - 140) & (pos < n_text - 110)][:3]
+    assert ks.shape[0] == 3
+    L = 150
+    rs = synth.simulate_reads(gs.base.genome, 40, L, 77)
+    n_aln = np.zeros(40, dtype=np.int32); rows = []
+    for i, k in zip((3, 17, 30), ks.tolist()):
+        n_aln[i] = 1
+        rows.append([1, 1, 0, k, k, 0, 0, 0, 0, 0, L - 1, 14])      # one mismatch, one gap open
+    na, off, a9 = sc.hits_input(n_aln, np.asarray(rows, dtype=np.uint32))
+    want, _, counts = sc.emu_sam(emu, rs, na, off, a9, ol.default_opt())
+    res = index.sam_se(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, na, off, a9, _opt({}))
+    bad = sc.diff(sc.unpack_result(res.rec, res.multi, res.cigar, res.md), want)
+    assert not bad, "\n".join(bad)
+    assert res.n_refined == 3 and sum(1 for g in want if g[1]) == 3
+
+
 def test_rng_state_chains_batches(gs, index):
     c, rs, n_aln, rows, want = gs.case("repeats_75")
     half = rs.n // 2

@@ -177,3 +177,59 @@ def test_rng48_jump_is_n_single_steps():
     for _ in range(100000):
         x = (x * A + Cc) & M
     assert jump(0, 100000) == x
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref/hsa_ref not built (reference sources absent)")
+def test_banded_dp_vs_aln_global_core_on_odd_geometries(tmp_path):
+    """dp_global (hsa_sam.cuh) against the reference's aln_global_core + bwa_aln_path2cigar (harness mode `dp`) on window / read
+    pairs the pipeline tests rarely produce: windows clipped at the end of the text (shorter than the read), windows much
+    longer than the read, lengths below the band width, reads with N, unrelated sequences -- score and CIGAR identical."""
+    import ctypes as C
+    rng = np.random.default_rng(9)
+    pairs = []
+    for _ in range(600):
+        len2 = int(rng.choice([1, 2, 7, 30, 49, 50, 51, 75, 100, 101, 150, 260]))
+        kind = int(rng.integers(0, 5))
+        len1 = max(1, len2 + int(rng.integers(-min(len2 - 1, 60), 12))) if kind < 3 else int(rng.integers(1, len2 + 70))
+        read = rng.integers(0, 4, size=len2).astype(np.uint8)
+        ref = rng.integers(0, 4, size=len1).astype(np.uint8)
+        if kind != 4:                                        # related sequences: the window is the read with edits
+            src = list(read)
+            for _e in range(int(rng.integers(0, 6))):
+                p = int(rng.integers(0, max(1, len(src))))
+                op = int(rng.integers(0, 3))
+                if op == 0 and src:
+                    src[p] = int(rng.integers(0, 4))
+                elif op == 1:
+                    src.insert(p, int(rng.integers(0, 4)))
+                elif src:
+                    del src[p]
+            src = (src + list(rng.integers(0, 4, size=len1)))[:len1]
+            ref = np.asarray(src, dtype=np.uint8)
+        if rng.random() < 0.2:
+            read[rng.integers(0, len2)] = 4
+        pairs.append((ref, read))
+    with open(tmp_path / "p.bin", "wb") as f:
+        np.asarray([len(pairs)], dtype=np.uint32).tofile(f)
+        for ref, read in pairs:
+            np.asarray([ref.shape[0], read.shape[0]], dtype=np.uint32).tofile(f)
+            ref.tofile(f); read.tofile(f)
+    ol.run_ref(["dp", str(tmp_path / "p.bin"), str(tmp_path / "o.bin")])
+    w = np.fromfile(tmp_path / "o.bin", dtype=np.uint32)
+    L = el.lib()
+    L.emu_dp.restype = C.c_int
+    L.emu_dp.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_uint32, C.POINTER(C.c_int32), C.c_void_p]
+    p, narrow_refused = 1, 0
+    for ref, read in pairs:
+        score, n_cig = int(w[p].view(np.int32) if hasattr(w[p], "view") else w[p]), int(w[p + 1])
+        want = w[p + 2:p + 2 + n_cig].tolist()
+        p += 2 + n_cig
+        out = np.zeros(ref.shape[0] + read.shape[0] + 4, dtype=np.uint32)
+        sc_ = C.c_int32(0)
+        # first with the width the library sizes for a batch without gaps beyond 8, then full width if that is refused
+        n = L.emu_dp(ref.ctypes.data, ref.shape[0], read.ctypes.data, read.shape[0], min(2 * 50 + 8 + 1, ref.shape[0] + 1), C.byref(sc_), out.ctypes.data)
+        if n < 0:
+            narrow_refused += 1
+            n = L.emu_dp(ref.ctypes.data, ref.shape[0], read.ctypes.data, read.shape[0], ref.shape[0] + 1, C.byref(sc_), out.ctypes.data)
+        assert n == n_cig and out[:n].tolist() == want and (sc_.value & 0xFFFFFFFF) == (score & 0xFFFFFFFF), (ref.shape[0], read.shape[0])
+    assert narrow_refused > 0        # the clipped-window guard was exercised
