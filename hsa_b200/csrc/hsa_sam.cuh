@@ -20,8 +20,9 @@
 // Work split: sel_* (the selection), sam_pos (every read: positions, mapQ, pairing; MD directly when no alignment has to be refined; the reads
 // that need the dynamic programme are appended to a list) and sam_dp (one listed read per thread: every refinement of the
 // read, then its MD).  The DP keeps ONE score row in place (the reference's curr/last pair collapses to a row plus the
-// carried diagonal) and one byte of trace-back per cell; a thread's scratch is interleaved with its neighbours' (element
-// e of worker t at e * T + t) so that the 32 lanes of a warp, which walk cells of the same index, touch one sector.
+// carried diagonal) -- in shared memory for reads up to ~250 bases -- and one byte of trace-back per cell in global memory;
+// a thread's scratch is interleaved with its neighbours' (element e of worker t at e * T + t) so that the 32 lanes of a
+// warp, which walk cells of the same index, touch one sector (or 32 banks).
 #pragma once
 #include "hsa_splice.cuh"
 #include <cstring>
@@ -58,6 +59,7 @@ struct SamParams {
     unsigned long long *cursor; uint32_t *status;                             // status: first failure kind (0 = none)
     // DP scratch, interleaved over dp_workers workers
     uint8_t *dp_bytes; int32_t *dp_rows; uint32_t dp_workers, dp_w, dp_len1_cap, dp_len2_cap;
+    uint32_t dp_rows_smem;      // score row + reference bases of a worker in shared memory (reads up to ~250 bases)
 };
 
 // ---- small pieces ---------------------------------------------------------------------------------------------------
@@ -272,21 +274,26 @@ HSA_HD void sam_pos_item(const SamParams &P, uint32_t rid)
 }
 
 // ---- stage 2: the dynamic programme ---------------------------------------------------------------------------------------
-struct DpScratch {              // worker t of T: element e of an array lives at e * T + t
-    uint8_t *cells, *ref; int32_t *rows; uint32_t T, W, len1_cap, len2_cap;
+struct DpScratch {              // interleaved arrays: element e of worker t lives at e * stride + t
+    uint8_t *cells, *ref; int32_t *rows;
+    uint32_t T;                 // stride of the trace-back cells (global memory: all workers of the launch)
+    uint32_t RT;                // stride of the score row and the reference bases (global: T; shared memory: the block's threads)
+    uint32_t W, len1_cap, len2_cap, run_cap;
     HSA_HD uint8_t &cell(uint32_t row, uint32_t col) const { return cells[((size_t)row * W + col) * T]; }
-    HSA_HD int32_t &row(uint32_t i, uint32_t c) const { return rows[((size_t)i * 3u + c) * T]; }
-    HSA_HD uint8_t &refb(uint32_t i) const { return ref[(size_t)i * T]; }
-    HSA_HD int32_t &run(uint32_t i) const { return rows[(size_t)i * T]; }      // the run list re-uses the score row
+    HSA_HD int32_t &row(uint32_t i, uint32_t c) const { return rows[((size_t)i * 3u + c) * RT]; }
+    HSA_HD uint8_t &refb(uint32_t i) const { return ref[(size_t)i * RT]; }
+    HSA_HD int32_t &run(uint32_t i) const { return rows[(size_t)i * RT]; }     // the run list re-uses the score row
 };
 
+// everything in global memory (long reads, the host build)
 HSA_HD DpScratch dp_scratch_of(const SamParams &P, uint32_t w)
 {
     DpScratch s;
-    s.T = P.dp_workers; s.W = P.dp_w; s.len1_cap = P.dp_len1_cap; s.len2_cap = P.dp_len2_cap;
+    s.T = s.RT = P.dp_workers; s.W = P.dp_w; s.len1_cap = P.dp_len1_cap; s.len2_cap = P.dp_len2_cap;
     s.cells = P.dp_bytes + w;
     s.ref = P.dp_bytes + (size_t)(P.dp_len2_cap + 1u) * P.dp_w * P.dp_workers + w;
     s.rows = P.dp_rows + w;
+    s.run_cap = 3u * (P.dp_len1_cap + 1u) > P.dp_len1_cap + P.dp_len2_cap + 2u ? 3u * (P.dp_len1_cap + 1u) : P.dp_len1_cap + P.dp_len2_cap + 2u;
     return s;
 }
 
@@ -390,7 +397,10 @@ HSA_HD int32_t dp_global(const DpScratch &S, int32_t len1, int32_t len2, const S
     uint32_t run_op = ctype, run_len = 0;
     do {
         if (ctype == run_op) ++run_len;
-        else { S.run(n_runs++) = (int32_t)(run_op << 28 | run_len); run_op = ctype; run_len = 1; }
+        else {
+            if ((uint32_t)n_runs + 2u > S.run_cap) { n_runs = -1; return 0; }       // (shared-memory rows of a clipped window: full-width retry)
+            S.run(n_runs++) = (int32_t)(run_op << 28 | run_len); run_op = ctype; run_len = 1;
+        }
         if (ctype == CIG_M) { --i; --j; } else if (ctype == CIG_I) --j; else --i;
         c = S.cell(j, i - (j > b2 ? j - b2 : 0));
         ctype = type;
@@ -452,9 +462,8 @@ HSA_HD bool sam_merge(const SamParams &P, const SamMulti &a, const SamMulti &b, 
 }
 
 // bwa_refine_gapped for one read that needs it (bwtse.c:536-638), then its MD
-HSA_HD void sam_dp_item(const SamParams &P, uint32_t rid, uint32_t worker)
+HSA_HD void sam_dp_item(const SamParams &P, uint32_t rid, const DpScratch &S)
 {
-    const DpScratch S = dp_scratch_of(P, worker);
     SamRec r = P.rec[rid];
     const uint8_t *rd = P.codes + P.read_off[rid]; const uint32_t len = P.read_len[rid];
     SamMulti *m = P.multi + r.multi_off;

@@ -10,14 +10,24 @@ __global__ void __launch_bounds__(256) sam_pos_kernel(const __grid_constant__ Sa
 }
 
 // the listed reads: banded global alignment(s), CIGAR, MD.  Persistent threads, each with its interleaved scratch slice.
+// The trace-back cells (one byte each, written once, read once) always live in global memory; the score row and the
+// reference bases, which every cell reads and rewrites, sit in shared memory when a block's share fits (dp_rows_smem).
 __global__ void __launch_bounds__(128) sam_dp_kernel(const __grid_constant__ SamParams P, uint32_t n_work)
 {
+    extern __shared__ int32_t dp_smem[];
     const uint32_t worker = blockIdx.x * blockDim.x + threadIdx.x;
     if (worker >= P.dp_workers) return;
+    DpScratch S = dp_scratch_of(P, worker);
+    if (P.dp_rows_smem) {
+        S.RT = blockDim.x;
+        S.rows = dp_smem + threadIdx.x;
+        S.ref = reinterpret_cast<uint8_t *>(dp_smem + (size_t)3u * (P.dp_len1_cap + 1u) * blockDim.x) + threadIdx.x;
+        S.run_cap = 3u * (P.dp_len1_cap + 1u);
+    }
     for (;;) {
         const unsigned long long w = atomicAdd(P.cursor, 1ull);
         if (w >= n_work) break;
-        sam_dp_item(P, P.dp_list[w], worker);
+        sam_dp_item(P, P.dp_list[w], S);
     }
 }
 
@@ -177,13 +187,20 @@ static int sam_run_device(const hsa_index_t *ix, SamCache &C, const uint8_t *cod
             const uint32_t len1_cap = max_len + max_ext, len2_cap = max_len;
             const uint32_t W = wide ? len1_cap + 1u : std::min<uint32_t>(2u * DP_BAND + max_ext + 1u, len1_cap + 1u);
             const size_t per_bytes = (size_t)(len2_cap + 1u) * W + len1_cap + 1u, per_rows = std::max<size_t>(3 * ((size_t)len1_cap + 1), (size_t)len1_cap + len2_cap + 2);
-            // 80 registers: six blocks of 128 per SM; scratch capped at 2 GB (fewer workers for long reads)
-            uint32_t workers = (uint32_t)std::min<size_t>({(size_t)n_dp, (size_t)ix->sm_count * 768, std::max<size_t>(128, ((size_t)2 << 30) / (per_bytes + 4 * per_rows))});
-            workers = (workers + 127u) / 128u * 128u;
+            // score row + reference bases in shared memory when 64 workers' share leaves room for two blocks per SM
+            // (13 bytes per reference position and worker: reads up to ~125 bases), or one (~250 bases); else everything in
+            // global memory with 128-thread blocks, six per SM (80 registers).  Scratch capped at 2 GB.
+            const size_t smem64 = (size_t)64 * 13 * ((size_t)len1_cap + 1) + 64;
+            const bool rows_smem = !wide && smem64 <= 200 * 1024 && env_long("HSA_B200_SAM_DP_GLOBAL", 0) == 0;
+            const uint32_t block = rows_smem ? 64u : 128u;
+            const size_t per_sm = rows_smem ? (smem64 <= 100 * 1024 ? 128 : 64) : 768;
+            uint32_t workers = (uint32_t)std::min<size_t>({(size_t)n_dp, (size_t)ix->sm_count * per_sm, std::max<size_t>(128, ((size_t)2 << 30) / (per_bytes + 4 * per_rows))});
+            workers = (workers + block - 1u) / block * block;
             if (C.dp_bytes.alloc(per_bytes * workers) || C.dp_rows.alloc(per_rows * 4 * workers)) return fail(HSA_E_CUDA, "out of device memory for the DP scratch");
             P.dp_bytes = C.dp_bytes.as<uint8_t>(); P.dp_rows = C.dp_rows.as<int32_t>(); P.dp_workers = workers; P.dp_w = W;
-            P.dp_len1_cap = len1_cap; P.dp_len2_cap = len2_cap;
-            sam_dp_kernel<<<workers / 128u, 128, 0, s>>>(P, n_dp);
+            P.dp_len1_cap = len1_cap; P.dp_len2_cap = len2_cap; P.dp_rows_smem = rows_smem ? 1u : 0u;
+            if (rows_smem) CU(cudaFuncSetAttribute(sam_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+            sam_dp_kernel<<<workers / block, block, rows_smem ? smem64 : 0, s>>>(P, n_dp);
             CU(cudaGetLastError());
         }
         CU(cudaEventRecord(e1, s));

@@ -347,7 +347,7 @@ int emu_dp(const uint8_t *ref, int32_t len1, const uint8_t *read, int32_t len2, 
     std::vector<uint8_t> bytes((size_t)(len2 + 1) * W + len1 + 2);
     std::vector<int32_t> rows(std::max<size_t>(3 * ((size_t)len1 + 1), (size_t)len1 + len2 + 2) + 8);
     DpScratch S;
-    S.T = 1; S.W = W; S.len1_cap = (uint32_t)len1; S.len2_cap = (uint32_t)len2;
+    S.T = S.RT = 1; S.W = W; S.len1_cap = (uint32_t)len1; S.len2_cap = (uint32_t)len2; S.run_cap = (uint32_t)rows.size();
     S.cells = bytes.data(); S.ref = bytes.data() + (size_t)(len2 + 1) * W; S.rows = rows.data();
     for (int32_t i = 0; i < len1; ++i) S.refb(i + 1) = ref[i];
     const SamRead q{read, (uint32_t)len2, 0u, 0u};
@@ -421,7 +421,7 @@ int emu_sam(void *p, const uint32_t *sa_value, uint32_t sa_interval, const uint3
         std::vector<uint8_t> bytes((size_t)(len2_cap + 1u) * W + len1_cap + 1u);
         std::vector<int32_t> rows(std::max<size_t>(3 * ((size_t)len1_cap + 1), (size_t)len1_cap + len2_cap + 2));
         P.dp_bytes = bytes.data(); P.dp_rows = rows.data(); P.dp_workers = 1; P.dp_w = W; P.dp_len1_cap = len1_cap; P.dp_len2_cap = len2_cap;
-        for (unsigned long long w = 0; w < cnt[2]; ++w) sam_dp_item(P, list[w], 0);
+        { const DpScratch S0 = dp_scratch_of(P, 0); for (unsigned long long w = 0; w < cnt[2]; ++w) sam_dp_item(P, list[w], S0); }
         if (status != SAM_SCRATCH) break;
     }
     counts_out[0] = n_multi; counts_out[1] = cnt[0]; counts_out[2] = cnt[1]; counts_out[3] = cnt[2]; counts_out[4] = status;
