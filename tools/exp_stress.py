@@ -17,6 +17,8 @@ def run(name, n, L, opt, **kw):
         res = index.whole_reads(codes, off, lens, opt, copy=False)
         best = res.kernel_ms if best is None else min(best, res.kernel_ms)
     print(f"{name}: kernel={best:.1f}ms reads/s={n / best / 1e3:.2f}M heavy={res.n_strict} hits={int(res.n_aln.sum())}", flush=True)
-run("stress 500k x 150bp n5o2", 500_000, 150, api.gap_init_opt(fnr=0.0, max_diff=5, max_gapo=2), sub_rate=0.02, indel_frac=0.10)
-run("default 2M x 100bp", 2_000_000, 100, api.gap_init_opt())
-run("default 10M x 100bp", 10_000_000, 100, api.gap_init_opt())
+N_STRESS = int(os.environ.get("EXP_N", 500_000))
+run(f"stress {N_STRESS} x 150bp n5o2", N_STRESS, 150, api.gap_init_opt(fnr=0.0, max_diff=5, max_gapo=2), sub_rate=0.02, indel_frac=0.10)
+if not os.environ.get("EXP_N"):
+    run("default 2M x 100bp", 2_000_000, 100, api.gap_init_opt())
+    run("default 10M x 100bp", 10_000_000, 100, api.gap_init_opt())
