@@ -444,6 +444,17 @@ static long env_long(const char *name, long dflt)
     return (v && *v) ? atol(v) : dflt;
 }
 
+// HSA_B200_HOST_TIMING=1: wall seconds of the host-buffer entry points by phase, printed when the index is freed
+static double g_host_t[12];
+static int g_host_timing = -1;
+static inline bool host_timing() { if (g_host_timing < 0) g_host_timing = env_long("HSA_B200_HOST_TIMING", 0) ? 1 : 0; return g_host_timing > 0; }
+static inline double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct HostTick {
+    double t; bool on;
+    HostTick() : t(0), on(host_timing()) { if (on) t = wall_s(); }
+    void mark(int k) { if (on) { const double n = wall_s(); g_host_t[k] += n - t; t = n; } }
+};
+
 struct hsa_index {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -772,6 +783,10 @@ static void sam_cache_free(struct SamCache *c);
 extern "C" void hsa_index_free(hsa_index_t *ix)
 {
     if (!ix) return;
+    if (host_timing())
+        fprintf(stderr, "[hsa_b200 host] whole_reads: submit (checks + H2D + enqueue) %.4f | wait for the batch %.4f | results D2H %.4f || "
+                        "splice: checks + H2D %.4f | pass 1 %.4f | large-slice pass %.4f | D2H %.4f\n",
+                g_host_t[0], g_host_t[1], g_host_t[2], g_host_t[3], g_host_t[4], g_host_t[5], g_host_t[6]);
     cudaSetDevice(ix->device);
     for (hsa_workspace *w : ix->pool) if (w) hsa_workspace_free(w);
     if (ix->h2d) cudaStreamDestroy(ix->h2d);
@@ -997,6 +1012,7 @@ extern "C" int hsa_splice_match_batch(const hsa_index_t *ix, const uint8_t *code
         return fail(HSA_E_ARG, "the splice path needs the SA samples, the block list and the packed text "
                                "(hsa_index_attach_sa / _blocks / _packed_dna)");
     if (n_reads > 0x7FFFFFF0ull) return fail(HSA_E_ARG, "too many reads in one batch");
+    HostTick tk;
     size_t bytes = 0; uint32_t max_len = 0;
     for (size_t i = 0; i < n_reads; ++i) {
         if (len[i] < 36) return fail(HSA_E_ARG, "bwt_splice_match needs reads of at least 36 bases (three seeds, 12-base anchors)");
@@ -1044,9 +1060,11 @@ extern "C" int hsa_splice_match_batch(const hsa_index_t *ix, const uint8_t *code
     // first pass: every read, small slices for many workers; then the reads that outgrew them, large slices for few
     const uint32_t arena_cap = (uint32_t)std::max<long>(64, env_long("HSA_B200_SPLICE_ARENA", 2048));
     const uint32_t aln_cap = (uint32_t)std::max<long>(16, env_long("HSA_B200_SPLICE_ALNS", 128));
+    tk.mark(3);
     if ((rc = splice_pass(ix, C, P, (uint32_t)n_reads, nullptr, 1u << 20, arena_cap, aln_cap, 512, cnt, s))) return rc;
     unsigned long long h[3];
     CU(cudaMemcpy(h, cnt, sizeof(h), cudaMemcpyDeviceToHost));
+    tk.mark(4);
     if (h[1]) {
         const uint32_t n_fail = (uint32_t)h[1];
         DevBuf &again = C.again;
@@ -1060,9 +1078,11 @@ extern "C" int hsa_splice_match_batch(const hsa_index_t *ix, const uint8_t *code
         CU(cudaMemcpy(h, cnt, sizeof(h), cudaMemcpyDeviceToHost));
         if (h[1]) return fail(HSA_E_CAPACITY, "a read exceeded the splice path's large-capacity scratch (65536 stack entries, 4096 hits per seed)");
     }
+    tk.mark(5);
     CU(cudaMemcpyAsync(n_aln_out, d_n.p, n_reads * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(aln_out, d_aln.p, n_reads * 18 * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    tk.mark(6);
     if (occ_lookups) *occ_lookups = h[2];
     return HSA_OK;
 }
@@ -1716,6 +1736,7 @@ static int job_finish(hsa_job *j, hsa_result_t *res)
     uint64_t stats[CNT_N];
     float ms = 0, ms_total = 0;
     uint32_t launches = ws->last_launches;
+    HostTick tk;
     for (int attempt = 0;; ++attempt) {
         if ((rc = batch_finish(ws, b, ix->stream, ix->d2h, stats, &ms))) return rc;
         ms_total += ms;
@@ -1727,6 +1748,7 @@ static int job_finish(hsa_job *j, hsa_result_t *res)
         if ((rc = batch_enqueue(ws, b, ix->stream, true))) return rc;
         launches += ws->last_launches;
     }
+    tk.mark(1);
     const size_t total = stats[CNT_ALN];
     if ((rc = result_reserve(res, b.n_items, total))) return rc;
     CU(cudaStreamWaitEvent(ix->d2h, ws->ev1, 0));
@@ -1734,6 +1756,7 @@ static int job_finish(hsa_job *j, hsa_result_t *res)
     CU(cudaMemcpyAsync(res->aln_off, ws->aln_off_dev, (size_t)b.n_items * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->d2h));
     if (total) CU(cudaMemcpyAsync(res->aln, ws->aln_dev, total * sizeof(hsa_aln1_t), cudaMemcpyDeviceToHost, ix->d2h));
     CU(cudaStreamSynchronize(ix->d2h));
+    tk.mark(2);
     res->n_items = b.n_items; res->n_aln_total = total;
     res->occ_lookups = stats[CNT_LOOKUPS]; res->n_strict = stats[CNT_STRICT];
     res->pops = stats[CNT_POPS]; res->steps = stats[CNT_STEPS];
@@ -1990,7 +2013,9 @@ extern "C" int hsa_whole_reads(const hsa_index_t *ix, const uint8_t *codes, cons
     if (!res || !opt) return fail(HSA_E_ARG, "null argument");
     if (n_reads == 0) return empty_result(res);
     hsa_job_t *j; int rc;
+    HostTick tk;
     if ((rc = hsa_whole_reads_submit(ix, codes, off, len, n_reads, opt, keep_gape, &j))) return rc;
+    tk.mark(0);
     return hsa_job_wait(j, res);
 }
 

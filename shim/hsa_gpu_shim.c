@@ -31,10 +31,19 @@
 #include "BWT.h"
 #include "bwtse.h"
 #include "hsa_b200.h"
+#include <time.h>
+#include <pthread.h>
+#include <unistd.h>
+
+/* HSA_GPU_SHIM_TIMING=1: seconds per phase of bwa_cal_sa_reg_gap_gpu, summed over the calls, printed by hsa_gpu_close */
+static double g_t[8]; static int g_timing = -1;
+static double now_s_(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+#define TICK(k) do { if (g_timing > 0) { double t_ = now_s_(); g_t[k] += t_ - t_last; t_last = t_; } } while (0)
 
 static hsa_index_t *g_idx = NULL;
 static hsa_result_t g_res_a, g_res_b;
 static void g_sa_attached_flag(void);
+static void pool_stop(void);
 
 static void view_of(const BWT *b, hsa_bwt_view_t *v)          /* BWT.h:61-83 */
 {
@@ -95,6 +104,11 @@ void hsa_gpu_sa_values(const Idx2BWT *bi, const unsigned int *sa_index, size_t n
 
 void hsa_gpu_close(void)
 {
+    if (g_timing > 0)
+        fprintf(stderr, "[hsa_gpu] seconds: pack %.4f | pass A (hsa_whole_reads) %.4f | first leak + pass B %.4f | order-dependent pass %.4f | "
+                        "hit arrays (splice batch in flight) %.4f | wait for the splice batch %.4f | frees %.4f\n",
+                g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]);
+    pool_stop();
     g_sa_attached = 0;
     hsa_result_free(&g_res_a); hsa_result_free(&g_res_b);
     hsa_index_free(g_idx); g_idx = NULL;
@@ -128,6 +142,133 @@ bwt_aln1_t *bwt_match_gap_gpu(bwt_aux_t *aux, int *_n_aln)
     return (bwt_aln1_t *)aln;
 }
 
+/* ---- helper threads ---------------------------------------------------------------------------------------------
+ * What is left on the host per batch is byte shuffling: packing the reads for the GPU call, counting Ns, and giving every
+ * read its own calloc'ed hit array (the contract of bwa_seq_t.aln).  None of it depends on the order of the reads, so it
+ * is spread over a few helper threads (HSA_GPU_SHIM_THREADS, default min(8, online CPUs); 1 = none).  Everything whose
+ * outcome depends on the order of the reads -- the option switch -- stays one sequential pass. */
+typedef void (*range_fn)(void *ctx, int lo, int hi);
+static struct {
+    pthread_t th[32]; int n_helpers, started, stop;
+    pthread_mutex_t mu; pthread_cond_t cv_go, cv_done;
+    range_fn fn; void *ctx; int total, chunk, next, active; unsigned gen;
+} g_pool = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv_go = PTHREAD_COND_INITIALIZER, .cv_done = PTHREAD_COND_INITIALIZER };
+
+static void pool_work(void)
+{
+    for (;;) {
+        int lo = __atomic_fetch_add(&g_pool.next, g_pool.chunk, __ATOMIC_RELAXED), hi;
+        if (lo >= g_pool.total) break;
+        hi = lo + g_pool.chunk < g_pool.total ? lo + g_pool.chunk : g_pool.total;
+        g_pool.fn(g_pool.ctx, lo, hi);
+    }
+}
+static void *pool_main(void *arg)
+{
+    unsigned seen = 0;
+    (void)arg;
+    for (;;) {
+        pthread_mutex_lock(&g_pool.mu);
+        while (g_pool.gen == seen && !g_pool.stop) pthread_cond_wait(&g_pool.cv_go, &g_pool.mu);
+        if (g_pool.stop) { pthread_mutex_unlock(&g_pool.mu); return NULL; }
+        seen = g_pool.gen;
+        pthread_mutex_unlock(&g_pool.mu);
+        pool_work();
+        pthread_mutex_lock(&g_pool.mu);
+        if (--g_pool.active == 0) pthread_cond_signal(&g_pool.cv_done);
+        pthread_mutex_unlock(&g_pool.mu);
+    }
+}
+static void pool_start(void)
+{
+    const char *e = getenv("HSA_GPU_SHIM_THREADS");
+    long want = e ? atol(e) : 8, cpus = sysconf(_SC_NPROCESSORS_ONLN);
+    int i;
+    g_pool.started = 1;
+    if (want > cpus) want = cpus;
+    if (want > 32) want = 32;
+    for (i = 0; i + 1 < want; ++i) {
+        if (pthread_create(&g_pool.th[g_pool.n_helpers], NULL, pool_main, NULL) != 0) break;
+        ++g_pool.n_helpers;
+    }
+}
+static void pool_stop(void)
+{
+    int i;
+    if (!g_pool.started) return;
+    pthread_mutex_lock(&g_pool.mu); g_pool.stop = 1; pthread_cond_broadcast(&g_pool.cv_go); pthread_mutex_unlock(&g_pool.mu);
+    for (i = 0; i < g_pool.n_helpers; ++i) pthread_join(g_pool.th[i], NULL);
+    g_pool.n_helpers = 0; g_pool.started = 0; g_pool.stop = 0;
+}
+/* fn over [0, total) in chunks, on the helpers and the calling thread; returns when all of it is done */
+static void pool_run(range_fn fn, void *ctx, int total, int chunk)
+{
+    if (!g_pool.started) pool_start();
+    if (g_pool.n_helpers == 0 || total <= chunk) { if (total > 0) fn(ctx, 0, total); return; }
+    pthread_mutex_lock(&g_pool.mu);
+    g_pool.fn = fn; g_pool.ctx = ctx; g_pool.total = total; g_pool.chunk = chunk; g_pool.next = 0;
+    g_pool.active = g_pool.n_helpers; ++g_pool.gen;
+    pthread_cond_broadcast(&g_pool.cv_go);
+    pthread_mutex_unlock(&g_pool.mu);
+    pool_work();
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.active > 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
+    pthread_mutex_unlock(&g_pool.mu);
+}
+
+/* per-read facts that do not depend on the option state: number of Ns (bwtaln.c:314-316) and the poly-A / poly-T test on
+ * the first 15 bases (:324-325) */
+enum { RD_POLY = 1 };
+typedef struct {
+    bwa_seq_t *seqs; uint8_t *codes; const uint64_t *off; uint32_t *nn; uint8_t *flag;
+} pack_ctx_t;
+static void pack_range(void *c_, int lo, int hi)
+{
+    pack_ctx_t *c = (pack_ctx_t *)c_;
+    int i, j;
+    for (i = lo; i < hi; ++i) {
+        const bwa_seq_t *p = c->seqs + i;
+        uint32_t nn = 0; int pa = 1, pt = 1;
+        memcpy(c->codes + c->off[i], p->seq, p->len);
+        for (j = 0; j < (int)p->len; ++j) nn += p->seq[j] > 3;
+        for (j = 0; j < 15; ++j) { if (p->seq[j] != 0) pa = 0; if (p->seq[j] != 3) pt = 0; }
+        c->nn[i] = nn; c->flag[i] = (pa || pt) ? RD_POLY : 0;
+    }
+}
+/* the GPU's hits of one read as the array bwa_seq_t.aln owns (hits in the reference's order, strand stamped on every hit,
+ * start / end on the first) */
+enum { ST_SKIP = 0, ST_TAKE_A = 1, ST_TAKE_B = 2 };
+typedef struct {
+    bwa_seq_t *seqs; const uint8_t *state; const hsa_result_t *res_a, *res_b; int first_leak;
+} take_ctx_t;
+static void take_range(void *c_, int lo, int hi)
+{
+    take_ctx_t *c = (take_ctx_t *)c_;
+    int i;
+    for (i = lo; i < hi; ++i) {
+        bwa_seq_t *p = c->seqs + i;
+        const hsa_result_t *res; size_t ri;
+        if (c->state[i] == ST_SKIP) continue;
+        res = c->state[i] == ST_TAKE_B ? c->res_b : c->res_a;
+        ri = c->state[i] == ST_TAKE_B ? (size_t)(i - c->first_leak - 1) : (size_t)i;
+        p->n_aln = res->n_aln[ri];
+        p->aln = (bwt_aln1_t *)calloc(p->n_aln < 10 ? 10 : p->n_aln, sizeof(bwt_aln1_t));
+        memcpy(p->aln, res->aln + res->aln_off[ri], sizeof(bwt_aln1_t) * (size_t)p->n_aln);
+    }
+}
+/* bwt_splice_match for the batch's fallback reads on its own thread, so that the hit arrays of the other reads are built
+ * while the GPU works on these */
+typedef struct {
+    const uint8_t *pc; const uint64_t *po; const uint32_t *pl, *pi; size_t n; const gap_opt_t *tab; size_t n_tab;
+    int32_t *pn; hsa_aln1_t *pa; int rc;
+} splice_job_t;
+static void *splice_main(void *a_)
+{
+    splice_job_t *a = (splice_job_t *)a_;
+    a->rc = hsa_splice_match_batch(g_idx, a->pc, a->po, a->pl, a->n, (const hsa_gap_opt_t *)a->tab, a->n_tab, a->pi, a->pn, a->pa, NULL);
+    return NULL;
+}
+
 /* same signature as bwa_cal_sa_reg_gap (bwtaln.h:199-200) */
 void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt_c, bwt_array_t *arr)
 {
@@ -135,13 +276,15 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
     gap_opt_t local_opt = *opt;                                /* :254, BEFORE the clear */
     gap_opt_t opt_a, opt_b;
     bwt_aux_t *aux = (bwt_aux_t *)calloc(1, sizeof(bwt_aux_t));
-    int i, j, max_len = 0, leaked = 0, first_leak = -1;
-    uint8_t *codes, *state;                                    /* state: 0 run, 1 N-filtered (untouched), 2 poly-A/T */
+    int i, max_len = 0, first_leak = -1, pass_b = 0;
+    uint8_t *codes, *state, *flag;                             /* state: what the last phase does with the read (ST_*) */
     uint64_t *off, total = 0;
-    uint32_t *len;
-    uint32_t *sel; int n_sel = 0;                              /* reads handed to the GPU (index into seqs) */
+    uint32_t *len, *nn;
     int *pend_read = NULL; gap_opt_t *pend_opt = NULL; int n_pend = 0;   /* reads for the GPU splice batch + their aux->opt */
+    double t_last = 0;
     (void)tid;
+    if (g_timing < 0) { const char *e = getenv("HSA_GPU_SHIM_TIMING"); g_timing = e && atoi(e) ? 1 : 0; }
+    if (g_timing > 0) t_last = now_s_();
 
     opt->mode &= ~BWA_MODE_GAPE;                               /* :261, sticks in the caller's struct */
     for (i = 0; i < n_seqs; ++i) if ((int)seqs[i].len > max_len) max_len = seqs[i].len;
@@ -155,21 +298,19 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
     /* ---- pass A on every read: GPU whole-read search with the pre-switch options --------------------------------
      * The per-read filters depend on state that drifts after the switch, so they are applied on the host further
      * down; the GPU's own N filter uses bwa_cal_maxdiff(max_len), never stricter than the drifting one. */
-    for (i = 0; i < n_seqs; ++i) total += seqs[i].len;
-    codes = (uint8_t *)malloc(total + 16); off = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1));
-    len = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1)); state = (uint8_t *)calloc(n_seqs + 1, 1);
-    sel = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1));
+    off = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1)); len = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1));
+    nn = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1)); flag = (uint8_t *)malloc(n_seqs + 1);
+    state = (uint8_t *)calloc(n_seqs + 1, 1);
+    for (i = 0; i < n_seqs; ++i) { off[i] = total; len[i] = seqs[i].len; total += seqs[i].len; }
+    codes = (uint8_t *)malloc(total + 16);
     if (g_splice_gpu) {
         pend_read = (int *)malloc(sizeof(int) * (n_seqs + 1));
         pend_opt = (gap_opt_t *)malloc(sizeof(gap_opt_t) * (n_seqs + 1));
     }
-    total = 0;
-    for (i = 0; i < n_seqs; ++i) {
-        off[i] = total; len[i] = seqs[i].len;
-        memcpy(codes + total, seqs[i].seq, seqs[i].len);
-        total += seqs[i].len;
-    }
+    { pack_ctx_t pc = { seqs, codes, off, nn, flag }; pool_run(pack_range, &pc, n_seqs, 4096); }
+    TICK(0);
     if (n_seqs && hsa_whole_reads(g_idx, codes, off, len, (size_t)n_seqs, (const hsa_gap_opt_t *)&opt_a, 0, &g_res_a)) die_gpu();
+    TICK(1);
 
     /* ---- sequential host part: filters, the option switch, splice fallback -------------------------------------- */
     aux->bi_bwt = (Idx2BWT *)bi_bwt; aux->arr = arr; aux->max_len = max_len;
@@ -186,11 +327,8 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
         int need_b = (local_opt.mode != opt->mode) || (local_opt.max_gapo != opt->max_gapo) ||
                      (opt->fnr <= 0.0 && local_opt.max_diff != opt->max_diff);
         for (i = 0; i < n_seqs && first_leak < 0; ++i) {
-            bwa_seq_t *p = seqs + i; int nn = 0, pa = 1, pt = 1;
-            for (j = 0; j < (int)p->len; ++j) if (p->seq[j] > 3) ++nn;
-            if (nn > local_opt.max_diff) continue;
-            for (j = 0; j < 15; ++j) { if (p->seq[j] != 0) pa = 0; if (p->seq[j] != 3) pt = 0; }
-            if (pa || pt) continue;
+            if ((int)nn[i] > local_opt.max_diff) continue;
+            if (flag[i] & RD_POLY) continue;
             if (g_res_a.n_aln[i] == 0) first_leak = i;
         }
         if (first_leak >= 0 && need_b && first_leak + 1 < n_seqs) {
@@ -201,36 +339,26 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
             if (hsa_whole_reads(g_idx, codes + off[k0], off_b, len + k0, nb, (const hsa_gap_opt_t *)&opt_b,
                                 (opt_b.mode & BWA_MODE_GAPE) ? 1 : 0, &g_res_b)) die_gpu();
             free(off_b);
-            n_sel = 1;                                         /* marks "pass B valid" */
+            pass_b = 1;
         }
     }
+    TICK(2);
 
+    /* the order-dependent pass: what happens to every read (the hit arrays themselves are built afterwards, in parallel) */
     for (i = 0; i < n_seqs; ++i) {
         bwa_seq_t *p = seqs + i;
-        const hsa_result_t *res = (n_sel && i > first_leak) ? &g_res_b : &g_res_a;
-        size_t ri = (n_sel && i > first_leak) ? (size_t)(i - first_leak - 1) : (size_t)i;
-        int nn = 0;
-        for (j = 0; j < (int)p->len; ++j) if (p->seq[j] > 3) ++nn;
-        if (nn > local_opt.max_diff) continue;                 /* :314-317 (fields stay as bwa_read_seq left them) */
+        const int use_b = pass_b && i > first_leak;
+        const int32_t n_hits = use_b ? g_res_b.n_aln[i - first_leak - 1] : g_res_a.n_aln[i];
+        if ((int)nn[i] > local_opt.max_diff) continue;         /* :314-317 (fields stay as bwa_read_seq left them) */
         p->sa = 0; p->type = BWA_TYPE_NO_MATCH; p->c1 = p->c2 = 0; p->n_aln = 0; p->aln = 0;    /* :319-323 */
-        {
-            int pa = 1, pt = 1;
-            for (j = 0; j < 15; ++j) { if (p->seq[j] != 0) pa = 0; if (p->seq[j] != 3) pt = 0; }
-            if (pa || pt) continue;                            /* :324-325 */
-        }
+        if (flag[i] & RD_POLY) continue;                       /* :324-325 */
         aux->seq = p->seq; aux->len = p->len;
         if (opt->fnr > 0.0) aux->opt->max_diff = maxdiff_of(p->len, opt->fnr);                    /* :330-331, through aux->opt */
         aux->opt->seed_len = opt->seed_len < (int)p->len ? opt->seed_len : 0x7fffffff;            /* :332 */
-        if (res->n_aln[ri] > 0) {
-            /* the GPU result: hits in the reference's order, strand stamped on every hit, start/end on the first */
-            p->n_aln = res->n_aln[ri];
-            p->aln = (bwt_aln1_t *)calloc(p->n_aln < 10 ? 10 : p->n_aln, sizeof(bwt_aln1_t));
-            memcpy(p->aln, res->aln + res->aln_off[ri], sizeof(bwt_aln1_t) * (size_t)p->n_aln);
-            continue;
-        }
+        if (n_hits > 0) { state[i] = use_b ? ST_TAKE_B : ST_TAKE_A; continue; }
         /* nothing on either strand: the splice path (bwtaln.c:362-369) with aux->opt = &local_opt as it stands NOW */
         if (g_splice_gpu && p->len >= 36) {
-            aux->opt = &local_opt; leaked = 1;
+            aux->opt = &local_opt;
             pend_read[n_pend] = i; pend_opt[n_pend] = local_opt; ++n_pend;     /* searched in one GPU batch below */
             continue;
         }
@@ -238,45 +366,60 @@ void bwa_cal_sa_reg_gap_gpu(int tid, const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_
         memcpy(aux->rc_seq, p->seq, p->len * sizeof(ubyte_t));
         seq_reverse(p->len, aux->rc_seq, 1);
         aux->strand = 0;
-        aux->opt = &local_opt; leaked = 1;
+        aux->opt = &local_opt;
         p->aln = bwt_splice_match(aux, &p->n_aln);
         if (p->n_aln == 0) { free(p->aln); p->aln = NULL; }
     }
-    if (n_pend) {
-        /* bwt_splice_match for all of them at once (hsa_splice_match_batch): distinct option states become an option
-         * table, reads keep their order */
-        uint8_t *pc; uint64_t *po; uint32_t *pl, *pi; int32_t *pn; hsa_aln1_t *pa; gap_opt_t *tab; int n_tab = 0, q, t;
-        uint64_t tot = 0;
-        for (q = 0; q < n_pend; ++q) tot += seqs[pend_read[q]].len;
-        pc = (uint8_t *)malloc(tot + 16); po = (uint64_t *)malloc(sizeof(uint64_t) * n_pend);
-        pl = (uint32_t *)malloc(sizeof(uint32_t) * n_pend); pi = (uint32_t *)malloc(sizeof(uint32_t) * n_pend);
-        pn = (int32_t *)calloc(n_pend, sizeof(int32_t)); pa = (hsa_aln1_t *)calloc((size_t)n_pend * 2, sizeof(hsa_aln1_t));
-        tab = (gap_opt_t *)malloc(sizeof(gap_opt_t) * n_pend);
-        tot = 0;
-        for (q = 0; q < n_pend; ++q) {
-            bwa_seq_t *p = seqs + pend_read[q];
-            po[q] = tot; pl[q] = p->len; memcpy(pc + tot, p->seq, p->len); tot += p->len;
-            for (t = 0; t < n_tab; ++t) if (memcmp(tab + t, pend_opt + q, sizeof(gap_opt_t)) == 0) break;
-            if (t == n_tab) tab[n_tab++] = pend_opt[q];
-            pi[q] = (uint32_t)t;
+    TICK(3);
+    {
+        /* bwt_splice_match for all fallback reads at once (hsa_splice_match_batch): distinct option states become an
+         * option table, reads keep their order.  It runs on its own thread while the hit arrays are built. */
+        uint8_t *pc = NULL; uint64_t *po = NULL; uint32_t *pl = NULL, *pi = NULL; int32_t *pn = NULL; hsa_aln1_t *pa = NULL;
+        gap_opt_t *tab = NULL; int n_tab = 0, q, t, threaded = 0;
+        splice_job_t job; pthread_t th;
+        if (n_pend) {
+            uint64_t tot = 0;
+            for (q = 0; q < n_pend; ++q) tot += seqs[pend_read[q]].len;
+            pc = (uint8_t *)malloc(tot + 16); po = (uint64_t *)malloc(sizeof(uint64_t) * n_pend);
+            pl = (uint32_t *)malloc(sizeof(uint32_t) * n_pend); pi = (uint32_t *)malloc(sizeof(uint32_t) * n_pend);
+            pn = (int32_t *)calloc(n_pend, sizeof(int32_t)); pa = (hsa_aln1_t *)calloc((size_t)n_pend * 2, sizeof(hsa_aln1_t));
+            tab = (gap_opt_t *)malloc(sizeof(gap_opt_t) * n_pend);
+            tot = 0;
+            for (q = 0; q < n_pend; ++q) {
+                bwa_seq_t *p = seqs + pend_read[q];
+                po[q] = tot; pl[q] = p->len; memcpy(pc + tot, p->seq, p->len); tot += p->len;
+                for (t = 0; t < n_tab; ++t) if (memcmp(tab + t, pend_opt + q, sizeof(gap_opt_t)) == 0) break;
+                if (t == n_tab) tab[n_tab++] = pend_opt[q];
+                pi[q] = (uint32_t)t;
+            }
+            job.pc = pc; job.po = po; job.pl = pl; job.pi = pi; job.n = (size_t)n_pend; job.tab = tab; job.n_tab = (size_t)n_tab;
+            job.pn = pn; job.pa = pa; job.rc = 0;
+            threaded = pthread_create(&th, NULL, splice_main, &job) == 0;
+            if (!threaded) splice_main(&job);
         }
-        if (hsa_splice_match_batch(g_idx, pc, po, pl, (size_t)n_pend, (const hsa_gap_opt_t *)tab, (size_t)n_tab, pi, pn, pa, NULL)) die_gpu();
-        for (q = 0; q < n_pend; ++q) {
-            bwa_seq_t *p = seqs + pend_read[q];
-            p->n_aln = pn[q];
-            if (pn[q]) {                                       /* res_aln: calloc(2, ...) in the reference (bwtgap.c:853) */
-                p->aln = (bwt_aln1_t *)calloc(2, sizeof(bwt_aln1_t));
-                memcpy(p->aln, pa + 2 * (size_t)q, sizeof(bwt_aln1_t) * 2);
-            } else p->aln = NULL;                              /* bwtaln.c:366-369 */
+        { take_ctx_t tc = { seqs, state, &g_res_a, &g_res_b, first_leak }; pool_run(take_range, &tc, n_seqs, 2048); }
+        TICK(4);
+        if (n_pend) {
+            if (threaded) pthread_join(th, NULL);
+            if (job.rc) die_gpu();
+            for (q = 0; q < n_pend; ++q) {
+                bwa_seq_t *p = seqs + pend_read[q];
+                p->n_aln = pn[q];
+                if (pn[q]) {                                   /* res_aln: calloc(2, ...) in the reference (bwtgap.c:853) */
+                    p->aln = (bwt_aln1_t *)calloc(2, sizeof(bwt_aln1_t));
+                    memcpy(p->aln, pa + 2 * (size_t)q, sizeof(bwt_aln1_t) * 2);
+                } else p->aln = NULL;                          /* bwtaln.c:366-369 */
+            }
+            free(pc); free(po); free(pl); free(pi); free(pn); free(pa); free(tab);
         }
-        free(pc); free(po); free(pl); free(pi); free(pn); free(pa); free(tab);
     }
-    (void)leaked; (void)sel;
+    TICK(5);
     free(pend_read); free(pend_opt);
-    free(codes); free(off); free(len); free(state); free(sel);
+    free(codes); free(off); free(len); free(nn); free(flag); free(state);
     free(aux->width_seed); free(aux->width_fore); free(aux->width_back); free(aux->rc_seq);
     gap_destroy_stack(aux->stack);
     free(aux);
+    TICK(6);
 }
 
 
