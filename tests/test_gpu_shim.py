@@ -66,6 +66,23 @@ def test_gpu_driver_matches_stock_driver(workdir, opts, splice_on_gpu, monkeypat
     assert '"aligned_any"' in cpu.stdout and '"aligned_any"' in gpu.stdout
 
 
+@pytest.mark.parametrize("threads", ["1", "8"], ids=["no_helper_threads", "eight_threads"])
+def test_gpu_driver_helper_threads_do_not_change_the_output(workdir, threads, monkeypatch):
+    """The shim spreads the order-independent host work (packing, N counts, the per-read hit arrays) over helper threads and
+    keeps the splice batch in flight meanwhile; one batch of all 6 560 reads is large enough for every threaded loop to be
+    cut into several chunks.  Output equals the stock driver's with and without helpers."""
+    monkeypatch.setenv("HSA_GPU_SHIM_THREADS", threads)
+    monkeypatch.setenv("HSA_GPU_SHIM_TIMING", "1")
+    args = ["batch=100000"]
+    subprocess.run([REF, "driver", "g", "r.reads", "cpu_t.aln"] + args, cwd=workdir, check=True, capture_output=True, text=True)
+    gpu = subprocess.run([REF_GPU, "gpudriver", "g", "r.reads", "gpu_t.aln"] + args, cwd=workdir, capture_output=True, text=True)
+    assert gpu.returncode == 0, gpu.stderr[-2000:]
+    assert "[hsa_gpu] seconds:" in gpu.stderr
+    n_c, rows_c = synth.read_aln_dump(str(workdir / "cpu_t.aln"))
+    n_g, rows_g = synth.read_aln_dump(str(workdir / "gpu_t.aln"))
+    assert (n_c > 0).sum() > 4000 and np.array_equal(n_c, n_g) and np.array_equal(rows_c, rows_g)
+
+
 def test_gpu_sa_values_match_BWTSaValue_inside_the_reference_program(workdir):
     """`gpusa`: the reference's own BWTSaValue (host) against shim/hsa_gpu_shim.c's hsa_gpu_sa_values (GPU batch call on
     the reference-loaded saValue array) for 200 000 SA indices of the reference-built index, compared in C."""
