@@ -641,8 +641,8 @@ def main():
         "limit": (None if l2_resident else
                   "what caps the probe (and the kernel) past L2 is address translation, not DRAM: every SM's TLB reaches 128 x 2 MB "
                   "pages; the random-sector rate is a function of the PAGES touched, not of the bytes (96 MB spread over 6 GiB: 37 G "
-                  "sectors/s, L2-resident; the same pages private to each SM: 264 G/s), and DRAM itself delivers about 45 G sectors/s "
-                  "(128 B fetched per 32 B missed) -- profiles/r02_probe_pages.jsonl, r02_probe_pages2.jsonl, DESIGN.md section 3")})
+                  "sectors/s, L2-resident; the same pages private to each SM: 264 G/s), and DRAM itself delivers 50 G sectors/s "
+                  "(128 B fetched per 32 B missed = the streaming bandwidth) -- profiles/r02_probe_pages[23]?.jsonl, DESIGN.md section 3")})
 
     cpu_baseline, parity = None, None
     if not args.no_cpu_baseline and world == 1:
