@@ -36,7 +36,7 @@
 #include <unistd.h>
 
 /* HSA_GPU_SHIM_TIMING=1: seconds per phase of bwa_cal_sa_reg_gap_gpu, summed over the calls, printed by hsa_gpu_close */
-static double g_t[8]; static int g_timing = -1;
+static double g_t[12]; static int g_timing = -1;
 static double now_s_(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 #define TICK(k) do { if (g_timing > 0) { double t_ = now_s_(); g_t[k] += t_ - t_last; t_last = t_; } } while (0)
 
@@ -108,6 +108,9 @@ void hsa_gpu_close(void)
         fprintf(stderr, "[hsa_gpu] seconds: pack %.4f | pass A (hsa_whole_reads) %.4f | first leak + pass B %.4f | order-dependent pass %.4f | "
                         "hit arrays (splice batch in flight) %.4f | wait for the splice batch %.4f | frees %.4f\n",
                 g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]);
+    if (g_timing > 0 && g_t[9] > 0)
+        fprintf(stderr, "[hsa_gpu] SAM stage seconds: pack %.4f | hsa_sam_se_batch %.4f | fields into bwa_seq_t %.4f | SAM text %.4f\n",
+                g_t[8], g_t[9], g_t[10], g_t[11]);
     pool_stop();
     g_sa_attached = 0;
     hsa_result_free(&g_res_a); hsa_result_free(&g_res_b);
@@ -438,10 +441,128 @@ static bwa_cigar_t *cigar_copy(const hsa_sam_result_t *r, uint32_t off, uint32_t
     return c;
 }
 
+/* ---- bwa_print_sam1 (bwtse.c:677-835) for the lines generate_sam_se_core prints (mate == NULL, type != NO_MATCH), into a
+ * buffer.  The reference formats every line with a dozen printf calls and a putchar per base -- 2 us per read, ten times the
+ * rest of the stage -- and nothing in a line depends on another read, so the shim formats chunks of reads on the helper threads
+ * and writes the chunks to stdout in order.  Reads whose CIGAR holds an operation beyond the reference's letter tables (it indexes
+ * past "MIDNSHP=X" / "MIDNS" there, bwtse.c:713, 811) are printed by the reference's own function, byte for byte what it prints. */
+extern char *bwt_rg_id;
+typedef struct { char *p; size_t n, cap; } tbuf_t;
+static void tb_need(tbuf_t *b, size_t m)
+{
+    if (b->n + m > b->cap) {
+        b->cap = (b->n + m) * 2 + 4096;
+        b->p = (char *)realloc(b->p, b->cap);
+        if (!b->p) { fprintf(stderr, "[hsa_gpu] out of memory formatting SAM text\n"); exit(1); }
+    }
+}
+static void tb_str(tbuf_t *b, const char *s) { size_t m = strlen(s); tb_need(b, m); memcpy(b->p + b->n, s, m); b->n += m; }
+static void tb_put(tbuf_t *b, char c) { tb_need(b, 1); b->p[b->n++] = c; }
+static void tb_int(tbuf_t *b, long long v)                     /* %d / %lld */
+{
+    char t[24]; int k = 0; unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    tb_need(b, 24);
+    if (v < 0) b->p[b->n++] = '-';
+    do { t[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+    while (k) b->p[b->n++] = t[--k];
+}
+static int sam_line_is_plain(const bwa_seq_t *p)
+{
+    int j, k;
+    if (p->cigar) for (j = 0; j < p->n_cigar; ++j) if (__cigar_op(p->cigar[j]) > 8) return 0;
+    for (j = 0; j < p->n_multi; ++j) {
+        const bwt_multi1_t *q = p->multi + j;
+        if (q->cigar) for (k = 0; k < (int)q->n_cigar; ++k) if (__cigar_op(q->cigar[k]) > 4) return 0;
+    }
+    for (j = 0; j < (int)p->full_len; ++j) if (p->seq[j] > 4) return 0;
+    return 1;
+}
+static void sam_line(tbuf_t *b, const HSP *hsp, bwa_seq_t *p, int mode, int max_top2)
+{
+    int j, flag = p->extra_flag;
+    if (p->strand) flag |= SAM_FSR;
+    tb_str(b, p->name); tb_put(b, '\t'); tb_int(b, flag); tb_put(b, '\t'); tb_str(b, hsp->chrName[p->seq_id]); tb_put(b, '\t');
+    tb_int(b, (int)(p->ori_pos)); tb_put(b, '\t'); tb_int(b, p->mapQ); tb_put(b, '\t');
+    if (p->cigar) {
+        for (j = 0; j != p->n_cigar; ++j) { tb_int(b, (int)__cigar_len(p->cigar[j])); tb_put(b, "MIDNSHP=X"[__cigar_op(p->cigar[j])]); }
+    } else { tb_int(b, p->len); tb_put(b, 'M'); }
+    tb_str(b, "\t*\t0\t0\t");
+    tb_need(b, (size_t)p->full_len + 2);
+    if (p->strand == 0) for (j = 0; j != (int)p->full_len; ++j) b->p[b->n++] = "ACGTN"[(int)p->seq[j]];
+    else for (j = 0; j != (int)p->full_len; ++j) b->p[b->n++] = "TGCAN"[p->seq[p->full_len - 1 - j]];
+    b->p[b->n++] = '\t';
+    if (p->qual) {
+        if (p->strand) seq_reverse(p->len, p->qual, 0);        /* in place, as the reference leaves it (:745-746) */
+        tb_str(b, (const char *)p->qual);
+    } else tb_put(b, '*');
+    if (bwt_rg_id) { tb_str(b, "\tRG:Z:"); tb_str(b, bwt_rg_id); }
+    if (p->bc[0]) { tb_str(b, "\tBC:Z:"); tb_str(b, p->bc); }
+    if (p->clip_len < (int)p->full_len) { tb_str(b, "\tXC:i:"); tb_int(b, p->clip_len); }
+    tb_str(b, "\tXT:A:"); tb_put(b, "NURMS"[p->type]);
+    tb_str(b, (mode & BWA_MODE_COMPREAD) ? "\tNM:i:" : "\tCM:i:"); tb_int(b, p->nm);
+    if (p->type != BWA_TYPE_MATESW) {
+        tb_str(b, "\tX0:i:"); tb_int(b, (int)p->c1);
+        if ((long long)p->c1 <= (long long)max_top2) { tb_str(b, "\tX1:i:"); tb_int(b, (int)p->c2); }
+    }
+    tb_str(b, "\tXM:i:"); tb_int(b, p->n_mm); tb_str(b, "\tXO:i:"); tb_int(b, p->n_gapo); tb_str(b, "\tXG:i:"); tb_int(b, p->n_gapo + p->n_gape);
+    if (p->md) { tb_str(b, "\tMD:Z:"); tb_str(b, p->md); }
+    if (p->n_multi) {
+        int i, k;
+        tb_str(b, "\tXA:Z:");
+        for (i = 0; i < p->n_multi; ++i) {
+            bwt_multi1_t *q = p->multi + i;
+            tb_str(b, hsp->chrName[q->seq_id]); tb_put(b, ','); tb_put(b, q->strand ? '-' : '+'); tb_int(b, (int)(q->ori_pos));
+            if (q->cigar) {
+                for (k = 0; k < (int)q->n_cigar; ++k) { tb_int(b, (int)__cigar_len(q->cigar[k])); tb_put(b, "MIDNS"[__cigar_op(q->cigar[k])]); }
+            } else { tb_put(b, ','); tb_int(b, q->gap + q->mm); tb_put(b, ';'); }
+        }
+    }
+    tb_put(b, '\n');
+}
+enum { SAM_CHUNK = 2048 };
+typedef struct { const HSP *hsp; bwa_seq_t *seqs; int mode, max_top2; tbuf_t *bufs; } fmt_ctx_t;
+static void fmt_range(void *c_, int lo, int hi)
+{
+    fmt_ctx_t *c = (fmt_ctx_t *)c_;
+    tbuf_t *b = c->bufs + lo / SAM_CHUNK;
+    int i;
+    for (i = lo; i < hi; ++i) if (c->seqs[i].type != BWA_TYPE_NO_MATCH) sam_line(b, c->hsp, c->seqs + i, c->mode, c->max_top2);
+}
+static void sam_print_batch(const HSP *hsp, int n_seqs, bwa_seq_t *seqs, int mode, int max_top2)
+{
+    int i, plain = 1;
+    const char *e = getenv("HSA_GPU_SHIM_PRINT");               /* =ref: every line through the reference's bwa_print_sam1 */
+    if (e && strcmp(e, "ref") == 0) plain = -1;
+    for (i = 0; i < n_seqs && plain > 0; ++i) if (seqs[i].type != BWA_TYPE_NO_MATCH && !sam_line_is_plain(seqs + i)) plain = 0;
+    if (plain > 0) {
+        const int n_chunks = (n_seqs + SAM_CHUNK - 1) / SAM_CHUNK;
+        fmt_ctx_t c = { hsp, seqs, mode, max_top2, (tbuf_t *)calloc(n_chunks ? n_chunks : 1, sizeof(tbuf_t)) };
+        pool_run(fmt_range, &c, n_seqs, SAM_CHUNK);
+        for (i = 0; i < n_chunks; ++i) { if (c.bufs[i].n) fwrite(c.bufs[i].p, 1, c.bufs[i].n, stdout); free(c.bufs[i].p); }
+        free(c.bufs);
+        return;
+    }
+    {   /* in read order on this thread: plain lines into one buffer, the others through the reference's function */
+        tbuf_t b = { NULL, 0, 0 };
+        for (i = 0; i < n_seqs; ++i) {                         /* bwtse.c:922-926 */
+            bwa_seq_t *p = seqs + i;
+            if (p->type == BWA_TYPE_NO_MATCH) continue;
+            if (plain == 0 && sam_line_is_plain(p)) { sam_line(&b, hsp, p, mode, max_top2); continue; }
+            if (b.n) { fwrite(b.p, 1, b.n, stdout); b.n = 0; }
+            bwa_print_sam1(hsp, p, 0, mode, max_top2);
+        }
+        if (b.n) fwrite(b.p, 1, b.n, stdout);
+        free(b.p);
+    }
+}
+
 void generate_sam_se_core_gpu(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_opt_t *opt, int n_occ)
 {
     uint8_t *codes; uint64_t *off, *aoff, total = 0, hits = 0; uint32_t *len; int32_t *n_aln; hsa_aln1_t *aln;
     int i; uint32_t j;
+    double t_last = 0;
+    if (g_timing < 0) { const char *e = getenv("HSA_GPU_SHIM_TIMING"); g_timing = e && atoi(e) ? 1 : 0; }
+    if (g_timing > 0) t_last = now_s_();
     if (!g_splice_gpu) { fprintf(stderr, "[hsa_gpu] the SAM stage needs the full index (SA samples, annotation, packed text)\n"); exit(1); }
     for (i = 0; i < n_seqs; ++i) { total += seqs[i].len; hits += (uint64_t)(seqs[i].n_aln > 0 ? seqs[i].n_aln : 0); }
     codes = (uint8_t *)malloc(total + 16); off = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1));
@@ -454,7 +575,9 @@ void generate_sam_se_core_gpu(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_
         n_aln[i] = p->n_aln > 0 ? p->n_aln : 0; aoff[i] = hits;
         if (n_aln[i]) { memcpy(aln + hits, p->aln, sizeof(bwt_aln1_t) * (size_t)n_aln[i]); hits += (uint64_t)n_aln[i]; }
     }
+    TICK(8);
     if (hsa_sam_se_batch(g_idx, codes, off, len, (size_t)n_seqs, n_aln, aoff, aln, (const hsa_gap_opt_t *)opt, n_occ, &g_rng48, &g_sam)) die_gpu();
+    TICK(9);
     for (i = 0; i < n_seqs; ++i) {
         bwa_seq_t *p = seqs + i; const hsa_sam1_t *r = g_sam.rec + i;
         p->type = r->type;
@@ -480,9 +603,8 @@ void generate_sam_se_core_gpu(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_
             }
         }
     }
-    for (i = 0; i < n_seqs; ++i) {                             /* bwtse.c:922-926 */
-        if ((seqs + i)->type == BWA_TYPE_NO_MATCH) continue;
-        bwa_print_sam1(bi_bwt->hsp, seqs + i, 0, opt->mode, opt->max_top2);
-    }
+    TICK(10);
+    sam_print_batch(bi_bwt->hsp, n_seqs, seqs, opt->mode, opt->max_top2);
     free(codes); free(off); free(aoff); free(len); free(n_aln); free(aln);
+    TICK(11);
 }

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--reads", type=int, default=3_000_000)
     ap.add_argument("--batches", default="100000,1000000")
     ap.add_argument("--stock", action="store_true", help="also time the stock driver on all host cores")
+    ap.add_argument("--sam", type=int, default=0, help="also run the SAM stage (sam / gpusam) on the first N reads")
     ap.add_argument("--trace", action="store_true", help="HSA_B200_TRACE=1: per-launch completion times of every batch (stderr)")
     a = ap.parse_args()
     import numpy as np
@@ -46,7 +47,20 @@ def main():
                                  check=True, capture_output=True, text=True).stdout
             j = json.loads(out.strip().splitlines()[-1])
             print(json.dumps({"what": f"stock driver, {procs} processes", "reads_per_s": n / j["secs"], "aligned_any": j["aligned_any"]}), flush=True)
-        for b in [int(x) for x in a.batches.split(",")]:
+        if a.sam:
+            n2 = min(n, a.sam)
+            synth.write_reads_bin(os.path.join(td, "r2.reads"), rs.subset(0, n2))
+            out = subprocess.run([ref, "sam", os.path.join(td, "g"), os.path.join(td, "r2.reads"), os.path.join(td, "c.bin"), os.path.join(td, "c.sam")],
+                                 check=True, capture_output=True, text=True).stdout
+            js = json.loads(out.strip().splitlines()[-1])
+            print(json.dumps({"what": "reference sam (one thread)", "reads": n2, "secs_sam": js["secs_sam"], "secs_search": js["secs_search"]}), flush=True)
+            for rep in range(2):
+                p = subprocess.run([ref_gpu, "gpusam", os.path.join(td, "g"), os.path.join(td, "r2.reads"), os.path.join(td, "d.bin"), os.path.join(td, "d.sam")],
+                                   check=True, capture_output=True, text=True, env=env)
+                jg = json.loads(p.stdout.strip().splitlines()[-1])
+                print(json.dumps({"what": "gpusam", "rep": rep, "reads": n2, "secs_sam": jg["secs_sam"], "secs_search": jg["secs_search"],
+                                  "phases": [ln for ln in p.stderr.splitlines() if "seconds:" in ln or "host]" in ln]}), flush=True)
+        for b in [int(x) for x in a.batches.split(",") if x]:
             for rep in range(2):
                 p = subprocess.run([ref_gpu, "gpudriver", os.path.join(td, "g"), os.path.join(td, "r.reads"), "x", "nout=1", f"batch={b}"],
                                    check=True, capture_output=True, text=True, env=env)
