@@ -646,6 +646,12 @@ def main():
                       f"both directions together: {idx_bytes / 1e6:.1f} MB)"
                       if probe else "MEASURED_PEAKS.json streaming copy"),
         "hbm_stream_peak_gbs": peaks.get("hbm_gbs"), "random_sector_probe": probe,
+        "deduplicated": (None if l2_resident else
+                         {"index_sectors_per_lookup": 0.79, "pairs_sharing_one_sector": 0.43,
+                          "source": "ncu, profiles/r02_search_3g_summary.txt: 8.0 G index sectors delivered for 10.16 G lookups -- the two "
+                                    "lookups of a pair (k and l + 1) fall into one 64-symbol block for 43 % of the pairs (SURVEY.md 8d's "
+                                    "deduplicated figure); frac counts every lookup as one sector, so the sectors that really cross L2 are "
+                                    "0.79 x achieved"}),
         "limit": (None if l2_resident else
                   "what caps the probe (and the kernel) past L2 is address translation, not DRAM: every SM's TLB reaches 128 x 2 MB "
                   "pages; the random-sector rate is a function of the PAGES touched, not of the bytes (96 MB spread over 6 GiB: 37 G "
