@@ -303,7 +303,7 @@ def ncu_traffic(genome: int, batch_reads: int):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        for e in (tj if isinstance(tj, list) else [tj]):
+        for e in reversed(tj if isinstance(tj, list) else [tj]):          # the latest capture of a workload wins
             if int(e.get("genome_bp", 0)) == genome and int(e.get("reads", 0)) == batch_reads:
                 return e.get("dram_bytes_per_launch"), e.get("source"), e
     except Exception:
