@@ -15,7 +15,10 @@ import oracle_lib as ol
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU_DIR = os.path.join(HERE, "emu")
-LIB = os.path.join(EMU_DIR, "libhsa_emu.so")
+# HSA_EMU_SANITIZE=1: the same sources with -fsanitize=address,undefined (run the suite with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+# ASAN_OPTIONS=detect_leaks=0): the only memory checker this pool offers for the device algorithm -- compute-sanitizer is closed
+SANITIZE = os.environ.get("HSA_EMU_SANITIZE", "") not in ("", "0")
+LIB = os.path.join(EMU_DIR, "libhsa_emu_asan.so" if SANITIZE else "libhsa_emu.so")
 CORE = os.path.join(ol.ROOT, "hsa_b200", "csrc", "hsa_core.cuh")
 
 
@@ -31,10 +34,19 @@ def build():
     deps = [src, os.path.join(ol.ROOT, "include", "hsa_b200.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     newest = max(os.path.getmtime(d) for d in deps)
     if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < newest:
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", LIB, src])
+        extra = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if SANITIZE else ["-O2"]
+        subprocess.check_call(["g++"] + extra + ["-fPIC", "-shared", "-std=c++17", "-o", LIB, src])
 
 
 _lib = None
+
+
+def _padded(codes):
+    """The read codes with 16 readable bytes behind them, as the product's device copy has (hsa_b200.cu: upload_reads):
+    the device code loads the bases as aligned 32-bit words (include/hsa_b200.h)."""
+    c = np.zeros(codes.shape[0] + 16, dtype=np.uint8)
+    c[: codes.shape[0]] = codes
+    return c
 
 
 def lib():
@@ -142,8 +154,9 @@ class Emu:
         aln = np.zeros((n, 2, 9), dtype=np.uint32)
         status = np.zeros(n, dtype=np.uint8)
         oi = None if opt_idx is None else np.ascontiguousarray(opt_idx, dtype=np.uint32)
+        codes = _padded(rs.codes)
         self.last_lookups = lib().emu_splice(self.h, ix.fwd.sa_value.ctypes.data, ix.fwd.sa_interval, t.ctypes.data, t.shape[0],
-                                             ix.packed_dna.ctypes.data, ix.dna_length, rs.codes.ctypes.data, off.ctypes.data,
+                                             ix.packed_dna.ctypes.data, ix.dna_length, codes.ctypes.data, off.ctypes.data,
                                              lens.ctypes.data, n, C.cast(oa, C.c_void_p), len(opts),
                                              None if oi is None else oi.ctypes.data, arena_cap, aln_cap,
                                              n_aln.ctypes.data, aln.ctypes.data, status.ctypes.data)
@@ -163,7 +176,7 @@ class Emu:
             n_items=None, want_width=False, rerun_cap=0, coop=False, step_budget=0):
         """rerun_cap: 0 = items the configuration cannot hold are reported in `status` (1); otherwise they are
         re-run with that arena capacity (the large-capacity configuration), as the product's host code does."""
-        codes = np.ascontiguousarray(rs.codes, dtype=np.uint8)
+        codes = _padded(rs.codes)
         off = np.ascontiguousarray(rs.offsets[:-1], dtype=np.uint64)
         lens = np.ascontiguousarray(rs.lens, dtype=np.uint32)
         max_len = int(lens.max()) if rs.n else 0

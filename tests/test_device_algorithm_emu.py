@@ -106,3 +106,28 @@ def test_cooperative_kernel_matches_reference(golden, emu, case, mode):
     assert np.array_equal(n_aln, exp_n)
     assert np.array_equal(rows, exp_rows)
     assert emu.last_lookups == golden.lookups(case, mode)
+
+
+def test_device_sources_under_address_and_ub_sanitizers():
+    """compute-sanitizer is not available on the GPU pool, so the memory checker for the device algorithm is the host
+    build of the same sources with -fsanitize=address,undefined (emu_lib.SANITIZE): a slice of this file, the splice path
+    and the SAM stage re-run in a child process under it (the whole three files pass under it too: DESIGN.md section 5)."""
+    import os
+    import subprocess
+    import sys
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not installed")
+    if os.environ.get("HSA_EMU_SANITIZE"):
+        return                                                   # already inside the sanitized child
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, HSA_EMU_SANITIZE="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", UBSAN_OPTIONS="print_stacktrace=1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-s", "-m", "not gpu", "-p", "no:cacheprovider",
+                        os.path.join(here, "test_device_algorithm_emu.py"), os.path.join(here, "test_splice_emu.py"),
+                        os.path.join(here, "test_sam_emu.py"),
+                        "-k", "(ragged_nonstop and fast16) or (cooperative and cfg5) or (splice_match_vs_golden and 100) or "
+                              "(sam_fields_vs_golden) or test_width or capacity_overflow"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0 and "AddressSanitizer" not in tail and "runtime error" not in tail, tail
+    assert " passed" in r.stdout
