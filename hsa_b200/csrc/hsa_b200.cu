@@ -554,6 +554,7 @@ struct hsa_workspace {
     // launch configuration (environment overrides are read once)
     bool configured = false;
     uint32_t block = 128; int minb = 5; int blocks_per_sm_cap = 0;
+    bool minb_auto = true; long nb_fast_env = -1;   // HSA_B200_MINB / HSA_B200_NB_FAST not given: dense_fast() decides per batch
     uint32_t n_pipes = 1; uint64_t chunk_items = 12u << 20;
     uint32_t arena_cap = 1022, hit_cap = 32;
     uint32_t vote_slow_min = VOTE_SLOW_MIN_DEFAULT; int32_t vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
@@ -1178,6 +1179,9 @@ extern "C" int hsa_workspace_launch_times(hsa_workspace_t *ws, char *names, size
 // (FAST_ROWS: in the rows, for reads too long for shared memory).  LARGE: 32-bit halves, 64-thread blocks.
 enum Variant { V_FAST = 0, V_FAST_ROWS = 1, V_LARGE = 2, V_COOP = 3 };
 
+struct Batch;
+static bool dense_fast(const hsa_workspace *ws, const Batch &b);
+
 static const void *search_fn(Variant v, int block, int minb)
 {
     if (v == V_COOP) return (const void *)coop_kernel<128>;
@@ -1217,6 +1221,26 @@ struct Batch {                      // everything one batch needs, device pointe
     u32x2 *width_out = nullptr; int32_t *bid_out = nullptr;
     const uint8_t *rows_host = nullptr; size_t rows_host_bytes = 0;   // per-call form: the caller's widths as one ready-made row
 };
+
+// Six resident blocks per SM instead of five (24 warps instead of 20 waiting on their lookups) for the batches that allow it.
+// The fast kernel is bound by the latency of its dependent lookups times the warps in flight (ncu: 50 % issue-active, 4 long-
+// scoreboard stall cycles per issue at 3.1 Gb); a sixth block needs <= 85 registers (launch bound 6: no spills) and a shared-
+// memory share that leaves the SM >= 60 KB of L1 -- below that the random-sector rate halves (tools/probe_sweep.cu, carve-out
+// sweep).  40 score buckets per lane instead of 64 (80 instead of 128 bytes of bucket heads) give 31.3 KB per block: 188 KB for
+// six.  Searches that push a record of score >= 40 are handed to the cooperative kernel like those that reached 64 before
+// (+22 % of an 0.9 % share with the default options).  Measured (profiles/r02_occupancy_buckets.log): search kernels -7.3 % at
+// 3.1 Gb, -8.5 % at 46 Mb, seed searches +7 %; 48 buckets fall off the L1 cliff (+30 %), eight blocks (64 registers, spills) +50 %.
+// Not for small batches (one read per lane: nothing to overlap, 100 000 x 75 bp: +6 % time) nor for option sets whose scores go
+// far beyond 64 anyway (the stress configuration hands 16 % more searches on and loses 3 %).
+enum : long { DENSE_NB_FAST = 40 };
+static bool dense_fast(const hsa_workspace *ws, const Batch &b)
+{
+    if (!ws->minb_auto || ws->nb_fast_env >= 0 || ws->block != 128) return false;
+    const uint64_t n_work = (uint64_t)b.n_groups * (b.kind == KIND_SEEDS ? 6u : 1u);
+    // n_buckets = highest score an option set can reach + 1 (check_opt): 69 with the default options, 60 for -n 2 -o 1, 80 for the
+    // stress configuration
+    return b.kind != KIND_WIDTH && b.n_buckets <= 72 && n_work >= 400000 && b.max_len <= 128;
+}
 
 static void trace_mark(hsa_workspace *ws, const char *name, cudaStream_t stream)
 {
@@ -1269,6 +1293,8 @@ static int configure(hsa_workspace *ws)
     ws->block = (uint32_t)env_long("HSA_B200_BLOCK", 128);
     if (ws->block != 128) ws->block = 256;
     ws->minb = (int)env_long("HSA_B200_MINB", ws->block == 128 ? 5 : 2);
+    ws->minb_auto = getenv("HSA_B200_MINB") == nullptr;
+    ws->nb_fast_env = env_long("HSA_B200_NB_FAST", -1);
     ws->blocks_per_sm_cap = (int)env_long("HSA_B200_BLOCKS_PER_SM", 0);
     ws->n_pipes = (uint32_t)std::min<long>(MAX_PIPES, std::max<long>(1, env_long("HSA_B200_PIPES", 1)));
     ws->chunk_items = (uint64_t)std::max<long>(6 * 1024, env_long("HSA_B200_CHUNK", 12 << 20));
@@ -1329,7 +1355,7 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     if (!coop) P.smem_stats_off = (uint32_t)(((size_t)P.smem_opts_bytes + (size_t)block * P.smem_lane_stride + 7) & ~size_t(7));
     const size_t smem = coop ? (size_t)P.smem_opts_bytes + (size_t)(block / 32) * P.coop_warp_smem
                              : (size_t)P.smem_stats_off + 5 * sizeof(unsigned long long);
-    const void *fn = search_fn(v, (int)block, ws->minb);
+    const void *fn = search_fn(v, (int)block, (v == V_FAST && dense_fast(ws, b)) ? 6 : ws->minb);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {   // experiment knob (north_star: "L2 persisting-access window"): HSA_B200_L2_PERSIST=1 marks the forward direction's blocks as
         // persisting in L2 for the kernels of this stream when they fit the device's persisting carve-out (the 46 Mb index: 23 MB)
@@ -1442,7 +1468,8 @@ static int batch_params(hsa_workspace *ws, const Batch &b, Params &P, Variant &v
     P.vote_slow_min = ws->vote_slow_min; P.vote_pop_bias = ws->vote_pop_bias;
     P.step_budget = ws->step_budget; P.drain_budget = ws->drain_budget;
     // fast configuration: bound bytes in shared memory if a block's share leaves room for >= 4 blocks per SM
-    const uint32_t nb_fast = std::min<uint32_t>(b.n_buckets, (uint32_t)std::min<long>(64, std::max<long>(8, env_long("HSA_B200_NB_FAST", 64))));   // scores >= 64 send the item to the large-capacity kernel
+    const long nb_want = ws->nb_fast_env >= 0 ? ws->nb_fast_env : dense_fast(ws, b) ? DENSE_NB_FAST : 64;
+    const uint32_t nb_fast = std::min<uint32_t>(b.n_buckets, (uint32_t)std::min<long>(64, std::max<long>(8, nb_want)));   // scores >= nb_fast send the item on
     set_layout(P, b.max_len, seed_cap, nb_fast, b.n_opts, 2, true);
     v = V_FAST;
     if ((size_t)P.smem_opts_bytes + (size_t)ws->block * P.smem_lane_stride > 56 * 1024 || env_long("HSA_B200_FORCE_ROWS", 0)) {

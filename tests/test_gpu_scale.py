@@ -137,10 +137,13 @@ class _DeviceRun:
         return n_aln, rows, stats
 
 
-@pytest.mark.parametrize("env", [{}, {"HSA_B200_CHUNK": "49152", "HSA_B200_PIPES": "2"}], ids=["one_chunk", "multi_chunk_two_pipes"])
+@pytest.mark.parametrize("env", [{}, {"HSA_B200_CHUNK": "49152", "HSA_B200_PIPES": "2"}, {"HSA_B200_MINB": "6", "HSA_B200_NB_FAST": "40"}],
+                         ids=["one_chunk", "multi_chunk_two_pipes", "six_blocks_40_buckets"])
 def test_device_resident_entry_point_46mb_vs_reference_binary(g46, monkeypatch, env):
     """The entry point behind bench.py's `value` (reads and results resident in HBM): same reference comparison, also
-    with the batch cut into several chunks on two internal streams."""
+    with the batch cut into several chunks on two internal streams, and with the configuration large batches get by
+    themselves (six resident blocks per SM, 40 score buckets per lane: searches that push a record of score >= 40 go
+    through the cooperative kernel)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     reads_t = synth_torch.simulate_reads(g46.genome, 200_000, 100, 77)
@@ -154,6 +157,16 @@ def test_device_resident_entry_point_46mb_vs_reference_binary(g46, monkeypatch, 
         assert stats[2] == exp_lk and stats[7] == 0
     finally:
         run.ws.close()
+
+
+def test_large_batch_configuration_46mb_vs_reference_binary(g46):
+    """420 000 reads: above the size from which a batch runs with six blocks per SM and 40 score buckets on its own
+    (hsa_b200.cu: dense_fast) -- host-buffer entry point, every hit compared with the reference binary."""
+    reads_t = synth_torch.simulate_reads(g46.genome, 420_000, 100, 79)
+    rs, path = g46.reads_file("cfg2dense", reads_t)
+    exp_n, exp_rows, exp_lk = g46.reference("whole", path, [])
+    res = g46.ix.whole_reads(rs.codes, rs.offsets[:-1].astype(np.uint64), rs.lens, api.gap_init_opt())
+    assert_same(res, exp_n, exp_rows, exp_lk, "hsa_whole_reads @46 Mb, 420 k reads (six blocks per SM, 40 buckets)")
 
 
 def test_device_resident_keep_gape_46mb_vs_reference_binary(g46):
