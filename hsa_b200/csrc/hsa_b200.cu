@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const uint32_t *len, u
 
 // Width kernel of the split pipeline: one thread per work item, every thread of a warp walks reads of the
 // same shape, so the loop is divergence-free (bwt_cal_width is a strictly sequential chain per read).
-__global__ void __launch_bounds__(256, 5) width_kernel(const __grid_constant__ Params P)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) width_kernel(const __grid_constant__ Params P)
 {
     DevOpt *sopt = reinterpret_cast<DevOpt *>(hsa_smem);
     for (uint32_t i = threadIdx.x; i < P.n_opts * (sizeof(DevOpt) / 4); i += blockDim.x)
@@ -1412,14 +1413,26 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     P.n_work_skip = io.n_work_skip;
     P.next_list = pipe.next_list; P.next_count = reinterpret_cast<uint32_t *>(slots + 2);
     P.cursor = slots;
-    const uint32_t wgrid = std::max<uint32_t>(1, std::min<uint32_t>((n_work + 255) / 256, (uint32_t)ix->sm_count * 8));
+    // The width pass is a chain of dependent lookups per read and nothing else.  Measured (profiles/r02_width_ab.log): with the index
+    // in L2 (46 Mb) a grid of exactly one wave of resident blocks is 14 % faster than the first version's 8 blocks per SM (the loop
+    // is grid-strided with equal shares, so 1 184 blocks ran as a full wave of 740 and a second one of 444); with the index in HBM
+    // (3.1 Gb) the pass sits at the address-translation limit, the second wave costs nothing and more resident warps only hurt
+    // (launch bound 6 = 48 warps per SM: +30 % time), so the grid stays as it was there.
+    // HSA_B200_WIDTH_MINB=6 / HSA_B200_WIDTH_GRID=<blocks per SM> select the other forms.
+    static const long width_minb = env_long("HSA_B200_WIDTH_MINB", 5), width_grid = env_long("HSA_B200_WIDTH_GRID", 0);
+    void (*wfn)(Params) = width_minb == 6 ? width_kernel<6> : width_kernel<5>;
+    int wocc = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, wfn, 256, P.smem_opts_bytes));
+    const bool index_in_l2 = (size_t)ix->ix.rev.n_blocks * 32 <= (96u << 20);
+    const uint32_t wblocks = (uint32_t)ix->sm_count * (uint32_t)(width_grid > 0 ? width_grid : index_in_l2 ? std::max(wocc, 1) : 8);
+    const uint32_t wgrid = std::max<uint32_t>(1, std::min<uint32_t>((n_work + 255) / 256, wblocks));
     void *args[] = {(void *)&P};
     const char *nm1 = large ? "search1L" : coop ? "search1C" : "search1", *nm2 = large ? "search2L" : coop ? "search2C" : "search2";
     if (b.rows_host) {
         // hsa_match_gap_call: the caller computed the widths (they are arguments of bwt_match_gap): no width pass
         CU(cudaMemcpyAsync(pipe.rows, b.rows_host, b.rows_host_bytes, cudaMemcpyHostToDevice, stream));
     } else {
-        width_kernel<<<wgrid, 256, P.smem_opts_bytes, stream>>>(P);
+        wfn<<<wgrid, 256, P.smem_opts_bytes, stream>>>(P);
         CU(cudaGetLastError());
         ++ws->last_launches; trace_mark(ws, "width1", stream);
     }
@@ -1429,7 +1442,7 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     if (b.kind == KIND_WHOLE) {
         P.pass = 2; P.work_list = pipe.next_list; P.work_base = 0; P.n_work_dev = P.next_count; P.n_work_skip = 0;
         P.next_list = nullptr; P.next_count = nullptr; P.cursor = slots + 1;
-        width_kernel<<<wgrid, 256, P.smem_opts_bytes, stream>>>(P);
+        wfn<<<wgrid, 256, P.smem_opts_bytes, stream>>>(P);
         CU(cudaGetLastError());
         ++ws->last_launches; trace_mark(ws, "width2", stream);
         CU(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream));
