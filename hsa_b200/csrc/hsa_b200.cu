@@ -1381,6 +1381,13 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     {   // experiment knob: shared-memory carve-out in percent of the SM's unified L1/shared array (-1 = driver default)
         static const long carve = env_long("HSA_B200_CARVEOUT", -1);
         if (carve >= 0 && v <= V_FAST_ROWS) CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)carve));
+        // cooperative kernel: 8 blocks x 25 KB of shared memory take the largest carve-out and leave 28 KB of L1, the size at which
+        // the random-sector rate halves.  With the index in HBM a 164 KB carve-out (six blocks, 92 KB of L1) makes the stage 10 %
+        // faster (2 x 32.2 -> 2 x 28.8 ms per 12.5 M-read batch at 3.1 Gb); with the index in L2 the two extra blocks are worth more
+        // than the L1 (stress configuration 13.05 vs 12.78 M reads/s), so the default stays there (profiles/r02_coop_carveout.log).
+        static const long coop_carve_env = env_long("HSA_B200_COOP_CARVEOUT", -2);
+        const long coop_carve = coop_carve_env >= -1 ? coop_carve_env : ((size_t)ix->ix.fwd.n_blocks * 32 > (96u << 20) ? 72 : -1);
+        if (v == V_COOP) CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)coop_carve));
     }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int)block, smem));
