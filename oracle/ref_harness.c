@@ -133,18 +133,19 @@ static void apply_opt(gap_opt_t *o, const char *kv)
     fprintf(stderr, "ref_harness: unknown option %s\n", key); exit(2);
 }
 
-typedef struct { int batch; int nout; int procs; int clear_gape; } hopt_t;
+typedef struct { int batch; int nout; int procs; int clear_gape; int qual; } hopt_t;
 
 static gap_opt_t *parse_opts(int argc, char **argv, int first, hopt_t *h)
 {
     gap_opt_t *o = gap_init_opt();
     int i;
-    h->batch = 0x186A0; h->nout = 0; h->procs = 1; h->clear_gape = 1;
+    h->batch = 0x186A0; h->nout = 0; h->procs = 1; h->clear_gape = 1; h->qual = 0;
     for (i = first; i < argc; ++i) {
         if (strncmp(argv[i], "batch=", 6) == 0) h->batch = atoi(argv[i] + 6);
         else if (strncmp(argv[i], "nout=", 5) == 0) h->nout = atoi(argv[i] + 5);
         else if (strncmp(argv[i], "procs=", 6) == 0) h->procs = atoi(argv[i] + 6);
         else if (strncmp(argv[i], "clear_gape=", 11) == 0) h->clear_gape = atoi(argv[i] + 11);
+        else if (strncmp(argv[i], "qual=", 5) == 0) h->qual = atoi(argv[i] + 5);
         else apply_opt(o, argv[i]);
     }
     return o;
@@ -777,6 +778,24 @@ static void put_sam_rec(FILE *f, const bwa_seq_t *p)
     }
 }
 
+#ifdef HSA_WITH_GPU_SHIM
+void hsa_gpu_sam_print(const HSP *hsp, int n_seqs, bwa_seq_t *seqs, int mode, int max_top2);
+void bwt_aln2seq_core(bwa_seq_t *s, int set_main, int n_multi);
+void bwa_cal_pac_pos(const Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seq, int max_mm, float fnr);
+static void sam_fields_ref_print_shim(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_opt_t *opt, int n_occ)
+{
+    int i;
+    for (i = 0; i < n_seqs; ++i) {                                 /* bwtse.c:899-908 */
+        bwa_seq_t *p = seqs + i;
+        if (p->n_aln == 2 && p->aln->type == BWA_TYPE_SPLICING) p->type = BWA_TYPE_SPLICING;
+        else bwt_aln2seq_core(p, 1, n_occ);
+    }
+    bwa_cal_pac_pos(bi_bwt, n_seqs, seqs, opt->max_diff, opt->fnr);  /* :911 */
+    bwa_refine_gapped(bi_bwt->hsp, n_seqs, seqs);                    /* :916 */
+    hsa_gpu_sam_print(bi_bwt->hsp, n_seqs, seqs, opt->mode, opt->max_top2);
+}
+#endif
+
 static int mode_sam(int argc, char **argv)
 {
     Idx2BWT *bi; reads_t r; FILE *fo; hopt_t h; gap_opt_t *opt0, *opt; uint32_t hdr[2], b; int saved_stdout, n_occ = 3, i;
@@ -803,6 +822,13 @@ static int mode_sam(int argc, char **argv)
             p->rseq = (ubyte_t*)calloc(p->len + 1, 1); memcpy(p->rseq, p->seq, p->len);
             seq_reverse(p->len, p->rseq, opt->mode & BWA_MODE_COMPREAD);
             sprintf(nm, "r%u", k); p->name = strdup(nm);
+            if (h.qual) {                                          /* qual=1: what a FASTQ with barcodes and trimming leaves (bwaseqio.c:150-203) */
+                uint32_t j;
+                p->qual = (ubyte_t*)calloc(p->len + 1, 1);
+                for (j = 0; j < p->len; ++j) p->qual[j] = (ubyte_t)(33 + (k * 7u + j * 13u) % 30u);   /* below 63: the tests drop lines that hold a question mark */
+                if (k % 3 == 0) strcpy(p->bc, k % 2 ? "ACgT" : "TTAGGC");
+                if (k % 5 == 0) p->clip_len = (int)p->len - 3;     /* only printed (XC:i), bwtse.c:757 */
+            }
         }
         t0 = now_s();
         g_driver(0, bi, n, seqs, opt, arr);
@@ -887,6 +913,12 @@ int main(int argc, char **argv)
     }
 #endif
 #ifdef HSA_WITH_GPU_SHIM
+    if (strcmp(argv[1], "samfmt") == 0) {
+        /* the stock program with ONLY the print loop replaced: fields by the reference's own generate_sam_se_core steps
+         * (bwtse.c:899-918), lines by the shim's formatter (hsa_gpu_sam_print) -- runs without a GPU */
+        g_sam = sam_fields_ref_print_shim;
+        return mode_sam(argc, argv);
+    }
     if (strcmp(argv[1], "gpusam") == 0) {
         /* the stock batch loop with BOTH stages from the shim: bwa_cal_sa_reg_gap_gpu and generate_sam_se_core_gpu */
         Idx2BWT *bi; int rc;

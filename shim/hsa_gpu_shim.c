@@ -556,6 +556,13 @@ static void sam_print_batch(const HSP *hsp, int n_seqs, bwa_seq_t *seqs, int mod
     }
 }
 
+/* the print loop of generate_sam_se_core (bwtse.c:922-926) on its own: used by generate_sam_se_core_gpu below, and by the
+ * harness mode `samfmt`, which checks the formatter against bwa_print_sam1 on fields computed by the reference (no GPU needed) */
+void hsa_gpu_sam_print(const HSP *hsp, int n_seqs, bwa_seq_t *seqs, int mode, int max_top2)
+{
+    sam_print_batch(hsp, n_seqs, seqs, mode, max_top2);
+}
+
 void generate_sam_se_core_gpu(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_opt_t *opt, int n_occ)
 {
     uint8_t *codes; uint64_t *off, *aoff, total = 0, hits = 0; uint32_t *len; int32_t *n_aln; hsa_aln1_t *aln;
