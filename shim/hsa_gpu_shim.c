@@ -563,30 +563,27 @@ void hsa_gpu_sam_print(const HSP *hsp, int n_seqs, bwa_seq_t *seqs, int mode, in
     sam_print_batch(hsp, n_seqs, seqs, mode, max_top2);
 }
 
-void generate_sam_se_core_gpu(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_opt_t *opt, int n_occ)
+/* the two per-read loops of the SAM stage that do not depend on the order of the reads, for the helper threads */
+typedef struct {
+    bwa_seq_t *seqs; uint8_t *codes; const uint64_t *off, *aoff; const int32_t *n_aln; hsa_aln1_t *aln; const hsa_sam_result_t *res;
+} sam_ctx_t;
+static void sam_pack_range(void *c_, int lo, int hi)
 {
-    uint8_t *codes; uint64_t *off, *aoff, total = 0, hits = 0; uint32_t *len; int32_t *n_aln; hsa_aln1_t *aln;
-    int i; uint32_t j;
-    double t_last = 0;
-    if (g_timing < 0) { const char *e = getenv("HSA_GPU_SHIM_TIMING"); g_timing = e && atoi(e) ? 1 : 0; }
-    if (g_timing > 0) t_last = now_s_();
-    if (!g_splice_gpu) { fprintf(stderr, "[hsa_gpu] the SAM stage needs the full index (SA samples, annotation, packed text)\n"); exit(1); }
-    for (i = 0; i < n_seqs; ++i) { total += seqs[i].len; hits += (uint64_t)(seqs[i].n_aln > 0 ? seqs[i].n_aln : 0); }
-    codes = (uint8_t *)malloc(total + 16); off = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1));
-    aoff = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1)); len = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1));
-    n_aln = (int32_t *)malloc(sizeof(int32_t) * (n_seqs + 1)); aln = (hsa_aln1_t *)malloc(sizeof(hsa_aln1_t) * (hits + 1));
-    total = hits = 0;
-    for (i = 0; i < n_seqs; ++i) {
-        const bwa_seq_t *p = seqs + i;
-        off[i] = total; len[i] = p->len; memcpy(codes + total, p->seq, p->len); total += p->len;
-        n_aln[i] = p->n_aln > 0 ? p->n_aln : 0; aoff[i] = hits;
-        if (n_aln[i]) { memcpy(aln + hits, p->aln, sizeof(bwt_aln1_t) * (size_t)n_aln[i]); hits += (uint64_t)n_aln[i]; }
+    sam_ctx_t *c = (sam_ctx_t *)c_;
+    int i;
+    for (i = lo; i < hi; ++i) {
+        const bwa_seq_t *p = c->seqs + i;
+        memcpy(c->codes + c->off[i], p->seq, p->len);
+        if (c->n_aln[i]) memcpy(c->aln + c->aoff[i], p->aln, sizeof(bwt_aln1_t) * (size_t)c->n_aln[i]);
     }
-    TICK(8);
-    if (hsa_sam_se_batch(g_idx, codes, off, len, (size_t)n_seqs, n_aln, aoff, aln, (const hsa_gap_opt_t *)opt, n_occ, &g_rng48, &g_sam)) die_gpu();
-    TICK(9);
-    for (i = 0; i < n_seqs; ++i) {
-        bwa_seq_t *p = seqs + i; const hsa_sam1_t *r = g_sam.rec + i;
+}
+static void sam_fields_range(void *c_, int lo, int hi)
+{
+    sam_ctx_t *c = (sam_ctx_t *)c_;
+    const hsa_sam_result_t *R = c->res;
+    int i; uint32_t j;
+    for (i = lo; i < hi; ++i) {
+        bwa_seq_t *p = c->seqs + i; const hsa_sam1_t *r = R->rec + i;
         p->type = r->type;
         if (p->multi) { free(p->multi); p->multi = NULL; }
         p->n_multi = 0;
@@ -594,21 +591,50 @@ void generate_sam_se_core_gpu(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_
         p->strand = r->strand; p->n_mm = r->n_mm; p->n_gapo = r->n_gapo; p->n_gape = r->n_gape; p->score = r->score;
         p->mapQ = p->seQ = r->mapQ; p->sa = r->sa; p->seq_id = r->seq_id; p->ori_pos = r->ori_pos; p->occ_pos = r->occ_pos;
         p->c1 = r->c1; p->c2 = r->c2; p->start = r->start; p->end = r->end;
-        if (r->n_cigar) { p->n_cigar = (int)r->n_cigar; p->cigar = cigar_copy(&g_sam, r->cigar_off, r->n_cigar); }
+        if (r->n_cigar) { p->n_cigar = (int)r->n_cigar; p->cigar = cigar_copy(R, r->cigar_off, r->n_cigar); }
         p->nm = r->nm;
         if (r->type != BWA_TYPE_SPLICING) {                    /* bwa_cal_md1 returns strdup(str->s) (bwtse.c:493) */
-            p->md = (char *)malloc(r->md_len + 1); memcpy(p->md, g_sam.md + r->md_off, r->md_len); p->md[r->md_len] = 0;
+            p->md = (char *)malloc(r->md_len + 1); memcpy(p->md, R->md + r->md_off, r->md_len); p->md[r->md_len] = 0;
         }
         if (r->n_multi) {
             p->n_multi = (int)r->n_multi;
             p->multi = (bwt_multi1_t *)calloc(r->n_multi, sizeof(bwt_multi1_t));
             for (j = 0; j < r->n_multi; ++j) {
-                const hsa_multi1_t *q = g_sam.multi + r->multi_off + j; bwt_multi1_t *m = p->multi + j;
+                const hsa_multi1_t *q = R->multi + r->multi_off + j; bwt_multi1_t *m = p->multi + j;
                 m->gap = q->gap; m->mm = q->mm; m->strand = q->strand; m->sa = q->sa; m->ori_pos = q->ori_pos; m->occ_pos = q->occ_pos;
                 m->seq_id = q->seq_id; m->aln_id = q->aln_id; m->start = q->start; m->end = q->end;
-                if (q->n_cigar) { m->n_cigar = q->n_cigar; m->cigar = cigar_copy(&g_sam, q->cigar_off, q->n_cigar); }
+                if (q->n_cigar) { m->n_cigar = q->n_cigar; m->cigar = cigar_copy(R, q->cigar_off, q->n_cigar); }
             }
         }
+    }
+}
+
+void generate_sam_se_core_gpu(Idx2BWT *bi_bwt, int n_seqs, bwa_seq_t *seqs, gap_opt_t *opt, int n_occ)
+{
+    uint8_t *codes; uint64_t *off, *aoff, total = 0, hits = 0; uint32_t *len; int32_t *n_aln; hsa_aln1_t *aln;
+    int i;
+    double t_last = 0;
+    if (g_timing < 0) { const char *e = getenv("HSA_GPU_SHIM_TIMING"); g_timing = e && atoi(e) ? 1 : 0; }
+    if (g_timing > 0) t_last = now_s_();
+    if (!g_splice_gpu) { fprintf(stderr, "[hsa_gpu] the SAM stage needs the full index (SA samples, annotation, packed text)\n"); exit(1); }
+    off = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1)); aoff = (uint64_t *)malloc(sizeof(uint64_t) * (n_seqs + 1));
+    len = (uint32_t *)malloc(sizeof(uint32_t) * (n_seqs + 1)); n_aln = (int32_t *)malloc(sizeof(int32_t) * (n_seqs + 1));
+    for (i = 0; i < n_seqs; ++i) {
+        const bwa_seq_t *p = seqs + i;
+        off[i] = total; len[i] = p->len; total += p->len;
+        n_aln[i] = p->n_aln > 0 ? p->n_aln : 0; aoff[i] = hits; hits += (uint64_t)n_aln[i];
+    }
+    codes = (uint8_t *)malloc(total + 16); aln = (hsa_aln1_t *)malloc(sizeof(hsa_aln1_t) * (hits + 1));
+    {
+        sam_ctx_t c = { seqs, codes, off, aoff, n_aln, aln, NULL };
+        pool_run(sam_pack_range, &c, n_seqs, 4096);
+    }
+    TICK(8);
+    if (hsa_sam_se_batch(g_idx, codes, off, len, (size_t)n_seqs, n_aln, aoff, aln, (const hsa_gap_opt_t *)opt, n_occ, &g_rng48, &g_sam)) die_gpu();
+    TICK(9);
+    {
+        sam_ctx_t c = { seqs, NULL, NULL, NULL, NULL, NULL, &g_sam };
+        pool_run(sam_fields_range, &c, n_seqs, 2048);
     }
     TICK(10);
     sam_print_batch(bi_bwt->hsp, n_seqs, seqs, opt->mode, opt->max_top2);
