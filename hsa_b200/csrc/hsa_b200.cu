@@ -556,6 +556,7 @@ struct hsa_workspace {
     bool configured = false;
     uint32_t block = 128; int minb = 5; int blocks_per_sm_cap = 0;
     bool minb_auto = true; long nb_fast_env = -1;   // HSA_B200_MINB / HSA_B200_NB_FAST not given: dense_fast() decides per batch
+    bool dense_now = false;                          // ... and this is its verdict on the batch batch_params() saw last
     uint32_t n_pipes = 1; uint64_t chunk_items = 12u << 20;
     uint32_t arena_cap = 1022, hit_cap = 32;
     uint32_t vote_slow_min = VOTE_SLOW_MIN_DEFAULT; int32_t vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
@@ -1181,7 +1182,7 @@ extern "C" int hsa_workspace_launch_times(hsa_workspace_t *ws, char *names, size
 enum Variant { V_FAST = 0, V_FAST_ROWS = 1, V_LARGE = 2, V_COOP = 3 };
 
 struct Batch;
-static bool dense_fast(const hsa_workspace *ws, const Batch &b);
+static bool dense_fast(const hsa_workspace *ws, const Batch &b, uint32_t seed_cap);
 
 static const void *search_fn(Variant v, int block, int minb)
 {
@@ -1231,16 +1232,24 @@ struct Batch {                      // everything one batch needs, device pointe
 // six.  Searches that push a record of score >= 40 are handed to the cooperative kernel like those that reached 64 before
 // (+22 % of an 0.9 % share with the default options).  Measured (profiles/r02_occupancy_buckets.log): search kernels -7.3 % at
 // 3.1 Gb, -8.5 % at 46 Mb, seed searches +7 %; 48 buckets fall off the L1 cliff (+30 %), eight blocks (64 registers, spills) +50 %.
-// Not for small batches (one read per lane: nothing to overlap, 100 000 x 75 bp: +6 % time) nor for option sets whose scores go
-// far beyond 64 anyway (the stress configuration hands 16 % more searches on and loses 3 %).
+// Not for small batches (one read per lane: nothing to overlap, 100 000 x 75 bp: +6 % time), nor for option sets whose scores go
+// far beyond 64 anyway (the stress configuration hands 16 % more searches on and loses 3 %), nor for reads so long that six blocks'
+// bound bytes no longer fit the 196 KB carve-out (> 111 bases with a seed region).
 enum : long { DENSE_NB_FAST = 40 };
-static bool dense_fast(const hsa_workspace *ws, const Batch &b)
+static bool dense_fast(const hsa_workspace *ws, const Batch &b, uint32_t seed_cap)
 {
     if (!ws->minb_auto || ws->nb_fast_env >= 0 || ws->block != 128) return false;
     const uint64_t n_work = (uint64_t)b.n_groups * (b.kind == KIND_SEEDS ? 6u : 1u);
     // n_buckets = highest score an option set can reach + 1 (check_opt): 69 with the default options, 60 for -n 2 -o 1, 80 for the
     // stress configuration
-    return b.kind != KIND_WIDTH && b.n_buckets <= 72 && n_work >= 400000 && b.max_len <= 128;
+    if (b.kind == KIND_WIDTH || b.n_buckets > 72 || n_work < 400000) return false;
+    // six blocks (+ 1 KB each that the system reserves) must fit the 196 KB carve-out, the largest that leaves 60 KB of L1:
+    // reads of up to 111 bases with a 32-base seed region
+    Params T;
+    memset(&T, 0, sizeof(T));
+    set_layout(T, b.max_len, seed_cap, std::min<uint32_t>(b.n_buckets, (uint32_t)DENSE_NB_FAST), b.n_opts, 2, true);
+    const size_t per_block = (size_t)T.smem_opts_bytes + 128u * (size_t)T.smem_lane_stride + 8 + 5 * sizeof(unsigned long long) + 1024;
+    return 6 * per_block <= 196u * 1024u;
 }
 
 static void trace_mark(hsa_workspace *ws, const char *name, cudaStream_t stream)
@@ -1356,7 +1365,7 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
     if (!coop) P.smem_stats_off = (uint32_t)(((size_t)P.smem_opts_bytes + (size_t)block * P.smem_lane_stride + 7) & ~size_t(7));
     const size_t smem = coop ? (size_t)P.smem_opts_bytes + (size_t)(block / 32) * P.coop_warp_smem
                              : (size_t)P.smem_stats_off + 5 * sizeof(unsigned long long);
-    const void *fn = search_fn(v, (int)block, (v == V_FAST && dense_fast(ws, b)) ? 6 : ws->minb);
+    const void *fn = search_fn(v, (int)block, (v == V_FAST && ws->dense_now) ? 6 : ws->minb);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {   // experiment knob (north_star: "L2 persisting-access window"): HSA_B200_L2_PERSIST=1 marks the forward direction's blocks as
         // persisting in L2 for the kernels of this stream when they fit the device's persisting carve-out (the 46 Mb index: 23 MB)
@@ -1488,7 +1497,8 @@ static int batch_params(hsa_workspace *ws, const Batch &b, Params &P, Variant &v
     P.vote_slow_min = ws->vote_slow_min; P.vote_pop_bias = ws->vote_pop_bias;
     P.step_budget = ws->step_budget; P.drain_budget = ws->drain_budget;
     // fast configuration: bound bytes in shared memory if a block's share leaves room for >= 4 blocks per SM
-    const long nb_want = ws->nb_fast_env >= 0 ? ws->nb_fast_env : dense_fast(ws, b) ? DENSE_NB_FAST : 64;
+    ws->dense_now = dense_fast(ws, b, seed_cap);        // issue_chunk, called for this batch right after, picks the launch bound by it
+    const long nb_want = ws->nb_fast_env >= 0 ? ws->nb_fast_env : ws->dense_now ? DENSE_NB_FAST : 64;
     const uint32_t nb_fast = std::min<uint32_t>(b.n_buckets, (uint32_t)std::min<long>(64, std::max<long>(8, nb_want)));   // scores >= nb_fast send the item on
     set_layout(P, b.max_len, seed_cap, nb_fast, b.n_opts, 2, true);
     v = V_FAST;
