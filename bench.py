@@ -269,6 +269,14 @@ def timed_device_steps(leg: DeviceLeg, steps: int, warmup: int, sync_all, world:
     return float(ms.item()), launches
 
 
+def kernel_config(leg):
+    """Launch configuration of the per-lane search kernel for this batch size and option set (reporting only)."""
+    try:
+        return leg.ws.last_config()
+    except Exception as e:                                     # an older library: the line stays valid without it
+        return {"unavailable": str(e)[:80]}
+
+
 def dominant_kernel(leg: DeviceLeg, peak_gbs: float, bound: str):
     """The per-lane search kernel on its own: one more (untimed) batch with an event behind every launch."""
     leg.ws.launch_timing(True)
@@ -291,6 +299,7 @@ def dominant_kernel(leg: DeviceLeg, peak_gbs: float, bound: str):
                                          "reference's two-sector roofline"},
             "physical": {"bytes_per_lookup": DEVICE_BYTES_PER_LOOKUP, "achieved": phys, "frac": phys / peak_gbs},
             "kernel": "search_kernel: the per-lane search kernel, pass-1 + pass-2 launches of one batch",
+            "kernel_config": kernel_config(leg),
             "batch_reads": hi - lo, "kernel_launches_per_batch": n_search, "kernel_ms_per_launch": search_ms / n_search,
             "kernel_share_of_step": search_ms / step_ms,
             "algorithmic_bytes_per_launch": fast_lookups * DEVICE_BYTES_PER_LOOKUP / n_search, "algorithmic_bytes_per_lookup": DEVICE_BYTES_PER_LOOKUP,

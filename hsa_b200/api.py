@@ -134,6 +134,8 @@ def lib():
     L.hsa_workspace_check.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.hsa_workspace_last_launches.argtypes = [C.c_void_p]
     L.hsa_workspace_last_launches.restype = C.c_uint32
+    L.hsa_workspace_last_config.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    L.hsa_workspace_last_config.restype = None
     L.hsa_workspace_launch_timing.argtypes = [C.c_void_p, C.c_int]
     L.hsa_workspace_launch_times.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_size_t,
                                              C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
@@ -555,6 +557,13 @@ class DeviceWorkspace:
 
     def last_launches(self) -> int:
         return int(lib().hsa_workspace_last_launches(self._h))
+
+    def last_config(self) -> dict:
+        """How the per-lane search kernel of the last call was configured (hsa_workspace_last_config)."""
+        o = (C.c_uint32 * 4)()
+        lib().hsa_workspace_last_config(self._h, o)
+        return {"resident_blocks_per_sm_bound": int(o[0]), "score_buckets_per_lane": int(o[1]), "shared_memory_per_block_bytes": int(o[2]),
+                "bound_bytes_in_shared_memory": bool(o[3])}
 
     def launch_timing(self, enable: bool) -> None:
         _check(lib().hsa_workspace_launch_timing(self._h, 1 if enable else 0))

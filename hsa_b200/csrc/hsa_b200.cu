@@ -557,6 +557,7 @@ struct hsa_workspace {
     uint32_t block = 128; int minb = 5; int blocks_per_sm_cap = 0;
     bool minb_auto = true; long nb_fast_env = -1;   // HSA_B200_MINB / HSA_B200_NB_FAST not given: dense_fast() decides per batch
     bool dense_now = false;                          // ... and this is its verdict on the batch batch_params() saw last
+    uint32_t last_config[4] = {0, 0, 0, 0};          // hsa_workspace_last_config
     uint32_t n_pipes = 1; uint64_t chunk_items = 12u << 20;
     uint32_t arena_cap = 1022, hit_cap = 32;
     uint32_t vote_slow_min = VOTE_SLOW_MIN_DEFAULT; int32_t vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
@@ -1135,6 +1136,11 @@ extern "C" void hsa_workspace_free(hsa_workspace_t *ws)
 }
 
 extern "C" uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws) { return ws ? ws->last_launches : 0; }
+extern "C" void hsa_workspace_last_config(const hsa_workspace_t *ws, uint32_t out[4])
+{
+    if (!out) return;
+    for (int i = 0; i < 4; ++i) out[i] = ws ? ws->last_config[i] : 0;
+}
 
 // Per-launch timing of the workspace's next calls (bench.py: the dominant kernel's own duration and algorithmic
 // bytes).  enable: one CUDA event is recorded behind every kernel launch; read: waits for the device, returns for the
@@ -1367,6 +1373,10 @@ static int issue_chunk(hsa_workspace *ws, const Batch &b, Params P, Pipe &pipe, 
                              : (size_t)P.smem_stats_off + 5 * sizeof(unsigned long long);
     const void *fn = search_fn(v, (int)block, (v == V_FAST && ws->dense_now) ? 6 : ws->minb);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (v <= V_FAST_ROWS) {
+        ws->last_config[0] = (uint32_t)((v == V_FAST && ws->dense_now) ? 6 : ws->minb); ws->last_config[1] = P.n_buckets;
+        ws->last_config[2] = (uint32_t)smem; ws->last_config[3] = v == V_FAST ? 1u : 0u;
+    }
     {   // experiment knob (north_star: "L2 persisting-access window"): HSA_B200_L2_PERSIST=1 marks the forward direction's blocks as
         // persisting in L2 for the kernels of this stream when they fit the device's persisting carve-out (the 46 Mb index: 23 MB)
         static const long persist = env_long("HSA_B200_L2_PERSIST", 0);

@@ -216,6 +216,10 @@ int  hsa_whole_reads_device(const hsa_index_t *idx, hsa_workspace_t *ws, const u
 int  hsa_workspace_check(hsa_workspace_t *ws, uint64_t stats_out[8]);
 /* number of kernels the last call on this workspace launched (for bench's gpu_launches) */
 uint32_t hsa_workspace_last_launches(const hsa_workspace_t *ws);
+/* how the per-lane search kernel of the last call was configured (reporting only): out[0] = launch bound = resident blocks per SM
+ * the register allocation allows, out[1] = score buckets per lane (a search that files a record of a higher score is handed to
+ * the cooperative kernel), out[2] = shared memory per block in bytes, out[3] = 1 if the bound bytes sit in shared memory */
+void hsa_workspace_last_config(const hsa_workspace_t *ws, uint32_t out[4]);
 /* per-launch timing of the workspace's next calls (bench.py's roofline of the dominant kernel): enable records one
  * CUDA event behind every kernel launch; launch_times waits for the device and returns, for the last call, the
  * launches' names ("width1;search1;width2;search2;...": passes 1/2 of the width and search kernels, suffix C for the
