@@ -6,7 +6,7 @@
 // (tests/test_shim_emu.py, build container only) can run the drop-in end to end -- bwa_cal_sa_reg_gap_gpu with its option switch,
 // helper threads and splice batch, generate_sam_se_core_gpu with its formatter -- against the stock program without a GPU.
 // It is NOT a fallback: nothing in hsa_b200/ knows about it, libhsa_b200.so does not contain it, and the product's C ABI fails
-// loudly without CUDA.  Entry points the shim's batch path does not use (hsa_sa_values, hsa_match_gap_call) return an error here.
+// loudly without CUDA.  The per-call entry point (hsa_match_gap_call) is not emulated and returns an error here.
 #include "hsa_emu.cpp"
 #include <string>
 
@@ -56,7 +56,14 @@ int hsa_index_attach_packed_dna(hsa_index_t *ix, const uint32_t *packed_dna, uin
 {
     ix->packed_dna = packed_dna; ix->dna_length = dna_length; return HSA_OK;
 }
-int hsa_sa_values(const hsa_index_t *, const uint32_t *, size_t, uint32_t *, uint64_t *) { return fail(HSA_E_ARG, "not in the emulation backend"); }
+int hsa_sa_values(const hsa_index_t *ix, const uint32_t *sa_index, size_t n, uint32_t *sa_value_out, uint64_t *steps_total)
+{
+    if (!ix->sa_value) return fail(HSA_E_ARG, "SA samples not attached");
+    std::vector<uint32_t> steps(n ? n : 1);
+    emu_sa_values(ix->emu, ix->sa_value, ix->sa_interval, sa_index, n, sa_value_out, steps.data());
+    if (steps_total) { *steps_total = 0; for (size_t i = 0; i < n; ++i) *steps_total += steps[i]; }
+    return HSA_OK;
+}
 int hsa_match_gap_call(const hsa_index_t *, const uint8_t *, uint32_t, int, hsa_width_t *, hsa_width_t *, const hsa_gap_opt_t *, int *, hsa_aln1_t **)
 {
     return fail(HSA_E_ARG, "not in the emulation backend");

@@ -68,3 +68,17 @@ def test_whole_program_with_both_shim_stages(workdir, opts):
     assert a.count(b"\n") > 2500 and b"XT:A:S" in a and b"M1I" in a
     assert a == b, "SAM text differs from the stock program's"
     assert open(workdir / "c.bin", "rb").read() == open(workdir / "e.bin", "rb").read()
+
+
+def test_sa_values_through_the_shim(workdir):
+    """`gpusa`: the reference's BWTSaValue against shim/hsa_gpu_shim.c's hsa_gpu_sa_values (sa_value_dev on the host) for 50 000 SA
+    indices, compared in C."""
+    rng = np.random.default_rng(75)
+    idx = rng.integers(0, 700001 + 1, size=50_000).astype(np.uint32)
+    idx[:4] = [0, 1, 700001, 700000]
+    with open(workdir / "sa.bin", "wb") as f:
+        np.asarray([idx.shape[0]], dtype=np.uint32).tofile(f)
+        idx.tofile(f)
+    r = subprocess.run([REF_EMU, "gpusa", "g", "sa.bin"], cwd=workdir, capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-2000:])
+    assert '"mismatches":0' in r.stdout
