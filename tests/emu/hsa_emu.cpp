@@ -51,6 +51,7 @@ static uint32_t g_rerun_cap = 0;
 static int g_use_coop = 0;                       // re-runs go through the warp-cooperative kernel first
 static uint32_t g_step_budget = 0;               // fast configuration: hand searches on after this many steps                 // 0 = report flagged items instead of re-running them
 static uint64_t g_flagged_first = 0;
+static const uint8_t *g_rows_host = nullptr; static size_t g_rows_host_bytes = 0;   // per-call form: the caller's widths as item 0's row
 static uint32_t g_vote_slow_min = VOTE_SLOW_MIN_DEFAULT; static int32_t g_vote_pop_bias = VOTE_POP_BIAS_DEFAULT;
 static uint64_t g_phase_runs[3], g_phase_lanes[3];
 
@@ -259,6 +260,7 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
         P.pass = 1; P.work_base = 0; P.work_list = round == 0 ? nullptr : strict_in.data(); P.n_work = n_work;
         P.next_list = next_list.data(); P.next_count = &next_count;
         for (uint32_t w = 0; w < n_work; ++w) width_item(P, dopts.data(), w);
+        if (g_rows_host && n_work == 1) memcpy(P.rows, g_rows_host, std::min<size_t>(g_rows_host_bytes, P.row_stride));   // hsa_match_gap_call: Batch::rows_host
         if (kind != KIND_WIDTH) {
             if (coop) run_coop(P, n_work, st);
             else if (wide) run_worker<uint64_t, false>(P, n_work, st); else run_worker<uint32_t, true>(P, n_work, st);
@@ -285,6 +287,7 @@ long emu_run(void *p, uint32_t kind, const uint8_t *codes, const hsa_task_t *tas
 }
 
 void emu_set_rerun(uint32_t cap) { g_rerun_cap = cap; }
+void emu_set_rows_host(const uint8_t *row, size_t bytes) { g_rows_host = row; g_rows_host_bytes = bytes; }
 void emu_set_coop(int on, uint32_t step_budget) { g_use_coop = on; g_step_budget = step_budget; }
 uint64_t emu_coop_waves(void) { return g_coop_waves; }
 void emu_coop_stats(uint64_t *o) { o[0] = g_coop_waves; o[1] = g_coop_wave_steps; o[2] = g_coop_steps; g_coop_waves = g_coop_wave_steps = g_coop_steps = 0; }

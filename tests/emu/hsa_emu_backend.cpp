@@ -6,7 +6,7 @@
 // (tests/test_shim_emu.py, build container only) can run the drop-in end to end -- bwa_cal_sa_reg_gap_gpu with its option switch,
 // helper threads and splice batch, generate_sam_se_core_gpu with its formatter -- against the stock program without a GPU.
 // It is NOT a fallback: nothing in hsa_b200/ knows about it, libhsa_b200.so does not contain it, and the product's C ABI fails
-// loudly without CUDA.  The per-call entry point (hsa_match_gap_call) is not emulated and returns an error here.
+// loudly without CUDA.
 #include "hsa_emu.cpp"
 #include <string>
 
@@ -64,9 +64,64 @@ int hsa_sa_values(const hsa_index_t *ix, const uint32_t *sa_index, size_t n, uin
     if (steps_total) { *steps_total = 0; for (size_t i = 0; i < n; ++i) *steps_total += steps[i]; }
     return HSA_OK;
 }
-int hsa_match_gap_call(const hsa_index_t *, const uint8_t *, uint32_t, int, hsa_width_t *, hsa_width_t *, const hsa_gap_opt_t *, int *, hsa_aln1_t **)
+// bwt_match_gap itself, one call with the frame's own arguments: as hsa_b200.cu's hsa_match_gap_call -- the caller's widths become
+// the item's row (bound bytes + bases), the search runs as a one-task batch, width_back comes back as gap_shadow left it
+int hsa_match_gap_call(const hsa_index_t *ix, const uint8_t *seq, uint32_t len, int strand, hsa_width_t *width_back, hsa_width_t *width_seed,
+                       const hsa_gap_opt_t *opt, int *n_aln_out, hsa_aln1_t **aln_out)
 {
-    return fail(HSA_E_ARG, "not in the emulation backend");
+    if (!ix || !seq || !len || !width_back || !opt || !n_aln_out || !aln_out) return fail(HSA_E_ARG, "null / empty argument");
+    uint32_t seed_mode = HSA_SEED_NONE;
+    if (width_seed == width_back) {
+        if (opt->seed_len != (int)len) return fail(HSA_E_ARG, "width_seed aliasing width_back needs opt->seed_len == len");
+        seed_mode = HSA_SEED_ALIAS;
+    } else if (width_seed && opt->seed_len > 0 && (uint32_t)opt->seed_len < len) seed_mode = HSA_SEED_TAIL;
+    const uint32_t seed_cap = (opt->seed_len > 0 && (uint32_t)opt->seed_len < len) ? (uint32_t)opt->seed_len + 1 : 0;
+    Params L;
+    memset(&L, 0, sizeof(L));
+    set_layout(L, len, seed_cap, 64, 1, 2, true);                     // the row's geometry depends on max_len and seed_cap only
+    std::vector<uint8_t> row(L.row_stride, 0);
+    uint32_t *w = reinterpret_cast<uint32_t *>(row.data());
+    uint32_t w_prev = 0xFFFFFFFFu;
+    bool has_n = false;
+    for (uint32_t i = 0; i <= len; ++i) {
+        w[i] = width_back[i].w;
+        uint8_t byte = bound_byte((uint32_t)width_back[i].bid, width_back[i].w, w_prev);
+        if (i < len) { if (seq[i] > 3) has_n = true; else byte |= (uint8_t)(seq[i] << BB_BASE_SHIFT); }
+        row[L.row_bid_off + i] = byte;
+        w_prev = width_back[i].w;
+    }
+    reinterpret_cast<uint32_t *>(row.data() + L.row_tail_off)[1] = has_n ? ROW_FLAG_HAS_N : 0u;
+    if (seed_mode == HSA_SEED_TAIL) {
+        w_prev = 0xFFFFFFFFu;
+        for (uint32_t i = 0; i <= (uint32_t)opt->seed_len; ++i) {
+            row[L.row_seed_off + i] = bound_byte((uint32_t)width_seed[i].bid, width_seed[i].w, w_prev);
+            w_prev = width_seed[i].w;
+        }
+    }
+    hsa_task_t t; memset(&t, 0, sizeof(t));
+    t.read_off = 0; t.read_len = len; t.strand = 0; t.sub_off = 0; t.len = len; t.wsrc_off = 0; t.seed_mode = seed_mode; t.opt_idx = 0;
+    std::vector<uint8_t> c((size_t)len + 16, 0);
+    memcpy(c.data(), seq, len);
+    const uint64_t off0 = 0; const uint32_t len0 = len;
+    int32_t n_aln = 0; uint64_t aln_off = 0; uint8_t status = 0xFF;
+    std::vector<uint32_t> aln(9 * 8192);
+    std::vector<u32x2> wout((size_t)len + 1);
+    uint64_t lk = 0, ns = 0, pops = 0;
+    emu_set_rerun(1u << 18); emu_set_coop(0, 0);
+    emu_set_rows_host(row.data(), row.size());
+    const long total = emu_run(ix->emu, KIND_TASKS, c.data(), &t, &off0, &len0, 1, opt, 1, nullptr, len, 0, 1022, 32, &n_aln, &aln_off, &status,
+                               aln.data(), 8192, reinterpret_cast<uint32_t *>(wout.data()), nullptr, &lk, &ns, &pops);
+    emu_set_rows_host(nullptr, 0);
+    if (total < 0 || status != STATUS_OK) return fail(HSA_E_CAPACITY, "emulation: the call was left unprocessed");
+    hsa_aln1_t *out = (hsa_aln1_t *)calloc((size_t)(n_aln < 10 ? 10 : n_aln), sizeof(hsa_aln1_t));
+    if (n_aln) memcpy(out, aln.data() + aln_off * 9, (size_t)n_aln * sizeof(hsa_aln1_t));
+    for (int q = 0; q < n_aln; ++q) out[q].strand = (uint32_t)strand & 3u;
+    for (uint32_t i = 0; i <= len; ++i) {
+        width_back[i].w = wout[i].x;
+        if (wout[i].y < BB_BID) width_back[i].bid = (int)wout[i].y;
+    }
+    *n_aln_out = n_aln; *aln_out = out;
+    return HSA_OK;
 }
 
 void hsa_result_free(hsa_result_t *r)

@@ -82,3 +82,21 @@ def test_sa_values_through_the_shim(workdir):
     r = subprocess.run([REF_EMU, "gpusa", "g", "sa.bin"], cwd=workdir, capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-2000:])
     assert '"mismatches":0' in r.stdout
+
+
+@pytest.mark.parametrize("mode,opts", [("percall", []), ("percall", ["clear_gape=0", "max_gapo=2"]), ("seeds", [])],
+                         ids=["whole_read_frames", "gape_counts_two_gap_opens", "splice_seed_frames"])
+def test_per_call_symbol(workdir, mode, opts):
+    """bwt_match_gap_gpu(bwt_aux_t*, int*) (bwtgap.h:26) through hsa_match_gap_call with the CALLER's width arrays: every call of
+    the harness's percall / seeds loop goes through the reference and through the symbol on the same frame; hits are compared with
+    memcmp and width_back after gap_shadow's rewrite word for word, in C; the dumps are compared here."""
+    rs = synth.read_reads_bin(str(workdir / "r.reads")).subset(0, 1000)
+    synth.write_reads_bin(str(workdir / "r_small.reads"), rs)
+    cpu = subprocess.run([ol.REF_BIN, mode, "g", "r_small.reads", "pc_cpu.aln"] + opts, cwd=workdir, capture_output=True, text=True)
+    assert cpu.returncode == 0, cpu.stderr[-2000:]
+    emu = subprocess.run([REF_EMU, "gpu" + mode, "g", "r_small.reads", "pc_emu.aln"] + opts, cwd=workdir, capture_output=True, text=True)
+    assert emu.returncode == 0, (emu.stdout[-500:], emu.stderr[-2000:])
+    assert '"call_mismatches":0,"width_mismatches":0' in emu.stdout
+    n_c, rows_c = synth.read_aln_dump(str(workdir / "pc_cpu.aln"))
+    n_e, rows_e = synth.read_aln_dump(str(workdir / "pc_emu.aln"))
+    assert int((n_c > 0).sum()) > 500 and np.array_equal(n_c, n_e) and np.array_equal(rows_c, rows_e)
